@@ -1,0 +1,295 @@
+"""ctypes binding of libbart_b200.so (include/bart_b200.h) -- the host-side mirror of the
+reference's `transit_module` interface plus the additive batched entry points.
+
+There is no CPU path: loading fails loudly when the shared library is missing, and every
+compute call fails loudly without a CUDA device (the library itself checks for sm_100).
+"""
+import ctypes as C
+import os
+import numpy as np
+
+_trapz = getattr(np, "trapezoid", None) or np.trapz
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIBPATH = os.path.join(HERE, "libbart_b200.so")
+
+dp = C.POINTER(C.c_double)
+ip = C.POINTER(C.c_int)
+
+REJ_TGRID, REJ_TCIA, REJ_SUMQ, REJ_FEWPTS = 1, 2, 4, 8
+
+
+class BartError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Load libbart_b200.so (built in-tree by __graft_entry__.build / bart_b200/csrc/Makefile)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIBPATH):
+        raise BartError("libbart_b200.so is not built (%s): run `python -c 'import "
+                        "__graft_entry__ as g; g.build()'` or `make -C bart_b200/csrc`; there is "
+                        "no CPU fallback" % LIBPATH)
+    L = C.CDLL(LIBPATH, mode=C.RTLD_GLOBAL)
+    L.transit_init.argtypes = [C.c_int, C.POINTER(C.c_char_p)]
+    L.get_no_samples.restype = C.c_int
+    L.get_waveno_arr.argtypes = [dp, C.c_int]
+    L.set_radius.argtypes = [C.c_double]
+    L.set_cloudtop.argtypes = [C.c_double]
+    L.set_scattering.argtypes = [C.c_int, C.c_double]
+    L.run_transit.argtypes = [dp, C.c_int, dp, C.c_int]
+    L.bart_last_error.restype = C.c_char_p
+    L.bart_set_batch_knobs.argtypes = [C.c_int, dp, dp, ip, dp]
+    L.bart_run_batch.argtypes = [dp, C.c_int, C.c_int, dp, C.c_int, ip]
+    L.bart_run_batch_device.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    L.bart_set_filters.argtypes = [C.c_int, ip, ip, dp, dp, C.c_double]
+    L.bart_band_integrate.argtypes = [dp, C.c_int, C.c_int, dp]
+    L.bart_bandflux_batch.argtypes = [dp, C.c_int, C.c_int, dp, ip]
+    L.bart_bandflux_batch_device.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.bart_extinction_batch.argtypes = [dp, C.c_int, C.c_int, dp, C.c_int]
+    L.bart_dev_alloc.restype = C.c_void_p
+    L.bart_dev_alloc.argtypes = [C.c_longlong]
+    L.bart_dev_free.argtypes = [C.c_void_p]
+    L.bart_host_alloc_pinned.restype = C.c_void_p
+    L.bart_host_alloc_pinned.argtypes = [C.c_longlong]
+    L.bart_host_free_pinned.argtypes = [C.c_void_p]
+    L.bart_memcpy_h2d.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong]
+    L.bart_memcpy_d2h.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong]
+    L.bart_timer_end.restype = C.c_double
+    L.bart_kernel_stats.argtypes = [C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_longlong), dp]
+    L.bart_launch_count.restype = C.c_longlong
+    L.bart_grid_bytes.restype = C.c_longlong
+    L.bart_debug_get.restype = C.c_longlong
+    L.bart_debug_get.argtypes = [C.c_char_p, C.c_int, dp, C.c_longlong]
+    L.bart_device_info.argtypes = [C.c_char_p, C.c_int, ip, ip, ip, C.POINTER(C.c_longlong),
+                                   C.POINTER(C.c_longlong)]
+    L.bart_comm_unique_id.argtypes = [C.c_char_p]
+    L.bart_comm_init.argtypes = [C.c_int, C.c_int, C.c_char_p]
+    L.bart_comm_allgather.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong]
+    L.bart_build_opacity_slice.argtypes = [C.c_int, C.c_int, dp]
+    L.bart_builder_stats.restype = C.c_longlong
+    L.bart_builder_stats.argtypes = [C.POINTER(C.c_longlong)] * 3
+    L.bart_line_bins.restype = C.c_longlong
+    L.bart_line_bins.argtypes = [C.POINTER(C.c_longlong), C.c_longlong]
+    L.bart_voigt_profile.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_float), C.c_longlong,
+                                     C.POINTER(C.c_longlong)]
+    L.bart_set_error_mode(1)
+    _lib = L
+    return L
+
+
+def _check(rc=0):
+    L = lib()
+    if L.bart_error_pending() or rc != 0:
+        msg = L.bart_last_error().decode(errors="replace")
+        L.bart_clear_error()
+        raise BartError(msg or "libbart_b200 call failed (rc=%d)" % rc)
+
+
+def _d(a):
+    return a.ctypes.data_as(dp)
+
+
+class PinnedArray:
+    """Page-locked host array (for end-to-end timing with real host<->device copies)."""
+
+    def __init__(self, shape, dtype=np.float64):
+        self.shape = tuple(np.atleast_1d(shape))
+        self.dtype = np.dtype(dtype)
+        n = int(np.prod(self.shape)) * self.dtype.itemsize
+        self.ptr = lib().bart_host_alloc_pinned(n)
+        if not self.ptr:
+            raise BartError("pinned allocation of %d bytes failed" % n)
+        buf = (C.c_char * n).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=self.dtype).reshape(self.shape)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            lib().bart_host_free_pinned(self.ptr)
+            self.ptr = None
+
+
+class Transit:
+    """One transit instance per process, like the reference (transit.c:7-12)."""
+
+    def __init__(self, cfg=None, argv=None, device=None):
+        L = lib()
+        if device is not None:
+            _check(L.bart_set_device(int(device)))
+        if argv is None:
+            argv = ["transit", "-c", cfg]
+        args = [a.encode() if isinstance(a, str) else a for a in argv]
+        arr = (C.c_char_p * (len(args) + 1))(*args, None)
+        L.transit_init(len(args), arr)
+        _check()
+        self.nwave = L.get_no_samples()
+        self.nlayer = L.bart_nlayers()
+        self.nspec = L.bart_nspecies()
+        self.n_in = (self.nspec + 1) * self.nlayer
+        self.eclipse = bool(L.bart_is_eclipse())
+        self.nfilters = 0
+
+    # ---- the reference surface ----
+    def get_no_samples(self):
+        return lib().get_no_samples()
+
+    def get_waveno_arr(self, n=None):
+        n = self.nwave if n is None else n
+        out = np.zeros(n)
+        lib().get_waveno_arr(_d(out), n)
+        return out
+
+    def set_radius(self, r):
+        lib().set_radius(float(r))
+
+    def set_cloudtop(self, c):
+        lib().set_cloudtop(float(c))
+
+    def set_scattering(self, flag, v):
+        lib().set_scattering(int(flag), float(v))
+
+    def run_transit(self, profiles, nwave=None):
+        nwave = self.nwave if nwave is None else nwave
+        p = np.ascontiguousarray(profiles, dtype=np.float64).ravel()
+        out = np.zeros(nwave)
+        lib().run_transit(_d(p), p.size, _d(out), nwave)
+        _check()
+        return out
+
+    def free_memory(self):
+        lib().free_memory()
+        _check()
+
+    # ---- additive ----
+    def set_batch_knobs(self, nmodels, refradius=None, cloudtop=None, scat_flag=None,
+                        scat_logext=None):
+        def arr(x, dt):
+            return None if x is None else np.ascontiguousarray(x, dtype=dt)
+        r, c, f, s = arr(refradius, np.float64), arr(cloudtop, np.float64), \
+            arr(scat_flag, np.int32), arr(scat_logext, np.float64)
+        _check(lib().bart_set_batch_knobs(
+            int(nmodels), None if r is None else _d(r), None if c is None else _d(c),
+            None if f is None else f.ctypes.data_as(ip), None if s is None else _d(s)))
+
+    def run_batch(self, profiles, out=None, status=None):
+        p = np.ascontiguousarray(profiles, dtype=np.float64)
+        if p.ndim == 1:
+            p = p[None, :]
+        M = p.shape[0]
+        if out is None:
+            out = np.empty((M, self.nwave))
+        if status is None:
+            status = np.zeros(M, dtype=np.int32)
+        _check(lib().bart_run_batch(_d(p), M, p.shape[1], _d(out), self.nwave,
+                                    status.ctypes.data_as(ip)))
+        return out, status
+
+    def set_filters(self, start, count, weight, star=None, rprs=1.0):
+        start = np.ascontiguousarray(start, dtype=np.int32)
+        count = np.ascontiguousarray(count, dtype=np.int32)
+        weight = np.ascontiguousarray(weight, dtype=np.float64)
+        st = None if star is None else np.ascontiguousarray(star, dtype=np.float64)
+        _check(lib().bart_set_filters(len(start), start.ctypes.data_as(ip),
+                                      count.ctypes.data_as(ip), _d(weight),
+                                      None if st is None else _d(st), float(rprs)))
+        self.nfilters = len(start)
+
+    def band_integrate(self, spectra):
+        s = np.ascontiguousarray(spectra, dtype=np.float64)
+        if s.ndim == 1:
+            s = s[None, :]
+        out = np.empty((s.shape[0], self.nfilters))
+        _check(lib().bart_band_integrate(_d(s), s.shape[0], s.shape[1], _d(out)))
+        return out
+
+    def bandflux_batch(self, profiles, out=None, status=None):
+        p = np.ascontiguousarray(profiles, dtype=np.float64)
+        if p.ndim == 1:
+            p = p[None, :]
+        M = p.shape[0]
+        if out is None:
+            out = np.empty((M, self.nfilters))
+        if status is None:
+            status = np.zeros(M, dtype=np.int32)
+        _check(lib().bart_bandflux_batch(_d(p), M, p.shape[1], _d(out),
+                                         status.ctypes.data_as(ip)))
+        return out, status
+
+    def extinction_batch(self, profiles, total=False, fetch=True):
+        p = np.ascontiguousarray(profiles, dtype=np.float64)
+        if p.ndim == 1:
+            p = p[None, :]
+        M = p.shape[0]
+        out = np.empty((M, self.nlayer, self.nwave)) if fetch else None
+        _check(lib().bart_extinction_batch(_d(p), M, p.shape[1],
+                                           None if out is None else _d(out), 1 if total else 0))
+        return out
+
+    def debug_keep(self, on=True):
+        lib().bart_debug_keep(1 if on else 0)
+
+    def debug_get(self, name, model=0, n=None):
+        cap = n if n is not None else max(self.nwave * self.nlayer, 64 * self.nlayer)
+        out = np.zeros(cap)
+        got = lib().bart_debug_get(name.encode(), model, _d(out), cap)
+        _check(0 if got >= 0 else -1)
+        return out[:got]
+
+
+# ---- module-level helpers ----
+def device_info():
+    name = C.create_string_buffer(256)
+    sm, ma, mi = C.c_int(), C.c_int(), C.c_int()
+    l2, hbm = C.c_longlong(), C.c_longlong()
+    _check(lib().bart_device_info(name, 256, C.byref(sm), C.byref(ma), C.byref(mi), C.byref(l2),
+                                  C.byref(hbm)))
+    return dict(name=name.value.decode(), sm_count=sm.value, cc=(ma.value, mi.value),
+                l2_bytes=l2.value, hbm_bytes=hbm.value)
+
+
+def kernel_stats():
+    out = {}
+    i = 0
+    while True:
+        name = C.create_string_buffer(128)
+        n, ms = C.c_longlong(), C.c_double()
+        if lib().bart_kernel_stats(i, name, 128, C.byref(n), C.byref(ms)) != 0:
+            break
+        out[name.value.decode()] = dict(launches=n.value, ms=ms.value)
+        i += 1
+    return out
+
+
+def filters_from_files(specwn, filter_files, starwn=None, starfl=None):
+    """Host-side precompute of stage (c): the same resampling BARTfunc.py:245-291 does with
+    wine.readfilter / wine.resample (linear interpolation of filter and stellar spectrum onto the
+    spectrum grid inside the filter span, filter normalised to unit trapezoid integral).
+    Returns (start, count, weight_concat, star_concat|None)."""
+    starts, counts, weights, stars = [], [], [], []
+    for path in filter_files:
+        with open(path) as f:
+            lines = f.readlines()
+        while lines[0].startswith("#") or not lines[0].strip():
+            lines.pop(0)
+        wl = np.array([float(l.split()[0]) for l in lines])
+        tr = np.array([float(l.split()[1]) for l in lines])
+        fwn, ftr = (1.0 / (wl * 1e-4))[::-1], tr[::-1]
+        idx = np.where((specwn < fwn[-1]) & (fwn[0] < specwn))[0]
+        if len(idx) < 2 or np.any(np.diff(idx) != 1):
+            raise BartError("filter %s does not map to a contiguous spectrum range" % path)
+        ifilt = np.interp(specwn[idx], fwn, ftr)
+        nif = ifilt / _trapz(ifilt, specwn[idx])
+        starts.append(idx[0])
+        counts.append(len(idx))
+        weights.append(nif)
+        if starwn is not None:
+            stars.append(np.interp(specwn[idx], starwn, starfl))
+    star = np.concatenate(stars) if stars else None
+    return (np.array(starts, dtype=np.int32), np.array(counts, dtype=np.int32),
+            np.concatenate(weights), star)

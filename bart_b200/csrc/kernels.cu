@@ -1,0 +1,358 @@
+// kernels.cu -- sm_100a kernels of the forward model (stages a, b, c of the north star).
+//
+//   atm_prep_kernel        K0   one CTA per model: densities, hydrostatic radii, per-layer tables
+//   eclipse_column_kernel  K1+K2e+K3e fused: opacity lookup + tau scan + intensity + flux
+//   transit_weights_kernel K2t  chord-integration weights per model
+//   transit_column_kernel  K1+K2t+K3t fused: lookup + chord tau + modulation
+//   extinction_kernel      K1 stand-alone lookup (materialises extinction; roofline/debug)
+//   band_integrate_kernel  K4   batched fp64 filter-band reduction
+//
+// Thread mapping: thread <-> wavenumber (the grid's contiguous axis), sequential over depth, so
+// every global load of the opacity grid is a fully coalesced 256-byte-per-warp stream and the
+// tau scan needs no cross-thread communication.  The per-model coefficient table (~18 KB) is
+// staged into shared memory with ONE bulk-async (TMA) copy per CTA and read as warp-wide
+// broadcasts.  CTAs are ordered model-fastest inside a wavenumber tile so that concurrently
+// resident CTAs stream the same grid columns (different temperature planes) through the L2.
+// Tensor cores are not used: nothing here is a dense contraction (4 flop per 16 B).
+#include "column_math.cuh"
+#include "kernels.hpp"
+#include <cuda_runtime.h>
+
+namespace bart {
+
+// ---------------------------------------------------------------------------------------
+// TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+
+// Stage one model's table into shared memory.  Bulk-async when the size allows (multiple of 16 B,
+// always true by TabLayout::stride), else a cooperative copy.
+__device__ __forceinline__ void stage_table(double *s_tab, const double *g_tab, int ndoubles,
+                                            uint64_t *bar, bool use_tma) {
+  if (use_tma) {
+    if (threadIdx.x == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const uint32_t bytes = (uint32_t)ndoubles * 8u;
+      mbar_expect_tx(bar, bytes);
+      // bulk copies are limited by the mbarrier tx-count (2^20-1); chunk for safety
+      uint32_t off = 0;
+      while (off < bytes) {
+        uint32_t n = bytes - off;
+        if (n > 65536u) n = 65536u;
+        bulk_g2s((char *)s_tab + off, (const char *)g_tab + off, n, bar);
+        off += n;
+      }
+    }
+    mbar_wait(bar, 0);
+  } else {
+    for (int i = threadIdx.x; i < ndoubles; i += blockDim.x) s_tab[i] = g_tab[i];
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// K0
+__global__ void __launch_bounds__(128)
+atm_prep_kernel(DevConfig c, Knobs knobs, const double *__restrict__ profiles, int n_in,
+                double *__restrict__ tabs, int *__restrict__ status, int nmodels) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int m = blockIdx.x;
+  if (m >= nmodels) return;
+  const int nl = c.nlayer;
+  double *s_rho = reinterpret_cast<double *>(smem_raw);        // [nspec][nl]
+  double *s_mu = s_rho + (size_t)c.nspec * nl;                 // [nl]
+  double *s_rad = s_mu + nl;                                   // [nl]
+  __shared__ int s_status;
+  if (threadIdx.x == 0) s_status = 0;
+  __syncthreads();
+  const double *in = profiles + (size_t)m * n_in;
+  int st = 0;
+  for (int l = threadIdx.x; l < nl; l += blockDim.x) st |= prep_layer(c, in, l, s_rho + l, nl, s_mu + l);
+  if (st) atomicOr(&s_status, st);
+  __syncthreads();
+  const KnobVals kv = knobs_for(knobs, m);
+  if (threadIdx.x == 0) hydrostatic_radii(c, kv.r0, in, s_mu, s_rad);
+  __syncthreads();
+  double *tab = tabs + (size_t)m * c.lay.stride();
+  st = 0;
+  for (int d = threadIdx.x; d < nl; d += blockDim.x)
+    st |= prep_table_row(c, kv, d, in, s_rho, nl, s_rad, tab);
+  if (st) atomicOr(&s_status, st);
+  __syncthreads();
+  if (threadIdx.x == 0) status[m] = s_status;
+}
+
+// ---------------------------------------------------------------------------------------
+// fused eclipse column kernel
+template <int NANG, bool KEEP>
+__global__ void __launch_bounds__(kColThreads)
+eclipse_column_kernel(DevConfig c, const double *__restrict__ tabs, const int *__restrict__ status,
+                      double *__restrict__ spectra, double *__restrict__ tau_keep,
+                      int *__restrict__ last_keep, int nmodels, int use_tma) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t bar;
+  double *s_tab = reinterpret_cast<double *>(smem_raw);
+  const int m = blockIdx.x % nmodels;           // model-fastest: neighbours share grid columns
+  const int tile = blockIdx.x / nmodels;
+  const int w = tile * kColThreads + threadIdx.x;
+  const int nd = c.lay.stride();
+  if (status[m] != 0) {                          // rejected model: -1 fill (BARTfunc.py:327-330)
+    if (w < c.nwave) spectra[(size_t)m * c.nwave + w] = -1.0;
+    return;
+  }
+  stage_table(s_tab, tabs + (size_t)m * nd, nd, &bar, use_tma != 0);
+  if (w >= c.nwave) return;
+  double *tk = KEEP ? tau_keep + ((size_t)m * c.nwave + w) * c.nlayer : nullptr;
+  int *lk = KEEP ? last_keep + (size_t)m * c.nwave + w : nullptr;
+  spectra[(size_t)m * c.nwave + w] = eclipse_column<NANG, KEEP>(c, s_tab, w, tk, lk);
+}
+
+// ---------------------------------------------------------------------------------------
+// transit geometry
+__global__ void __launch_bounds__(128)
+transit_weights_kernel(DevConfig c, const double *__restrict__ tabs, double *__restrict__ wts,
+                       int nmodels) {
+  const int m = blockIdx.x;
+  if (m >= nmodels) return;
+  const int nl = c.nlayer;
+  const double *tab = tabs + (size_t)m * c.lay.stride();
+  double *wm = wts + (size_t)m * ((size_t)nl * (nl + 1) / 2);
+  for (int d = threadIdx.x; d < nl; d += blockDim.x)
+    transit_weight_row(c, tab, d, wm + (size_t)d * (d + 1) / 2);
+}
+
+template <bool KEEP>
+__global__ void __launch_bounds__(kTransitThreads)
+transit_column_kernel(DevConfig c, const double *__restrict__ tabs, const double *__restrict__ wts,
+                      const int *__restrict__ status, int *__restrict__ status_col,
+                      double *__restrict__ spectra,
+                      double *__restrict__ tau_keep, int *__restrict__ last_keep, int nmodels,
+                      int use_tma) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t bar;
+  const int nd = c.lay.stride();
+  double *s_tab = reinterpret_cast<double *>(smem_raw);
+  double *s_er = s_tab + nd;                                   // [nl][kTransitThreads]
+  const int m = blockIdx.x % nmodels;
+  const int tile = blockIdx.x / nmodels;
+  const int w = tile * kTransitThreads + threadIdx.x;
+  if (status[m] != 0) {
+    if (w < c.nwave) spectra[(size_t)m * c.nwave + w] = -1.0;
+    return;
+  }
+  stage_table(s_tab, tabs + (size_t)m * nd, nd, &bar, use_tma != 0);
+  if (w >= c.nwave) return;
+  const double *wm = wts + (size_t)m * ((size_t)c.nlayer * (c.nlayer + 1) / 2);
+  double *tk = KEEP ? tau_keep + ((size_t)m * c.nwave + w) * c.nlayer : nullptr;
+  int *lk = KEEP ? last_keep + (size_t)m * c.nwave + w : nullptr;
+  int st = 0;
+  const double r = transit_column<KEEP>(c, s_tab, wm, w, s_er + threadIdx.x, kTransitThreads, tk, lk, &st);
+  spectra[(size_t)m * c.nwave + w] = r;
+  if (st) atomicOr(&status_col[m], st);
+}
+
+__global__ void merge_status_kernel(int *status, const int *status_col, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) status[i] |= status_col[i];
+}
+
+// ---------------------------------------------------------------------------------------
+// K1 stand-alone lookup: ext[m][layer][w], layer index bottom -> top like the reference's e[r][w]
+__global__ void __launch_bounds__(kColThreads)
+extinction_kernel(DevConfig c, const double *__restrict__ tabs, double *__restrict__ ext,
+                  int nmodels, int mol_only, int use_tma) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t bar;
+  double *s_tab = reinterpret_cast<double *>(smem_raw);
+  const int m = blockIdx.x % nmodels;
+  const int tile = blockIdx.x / nmodels;
+  const int w = tile * kColThreads + threadIdx.x;
+  const int nd = c.lay.stride();
+  stage_table(s_tab, tabs + (size_t)m * nd, nd, &bar, use_tma != 0);
+  if (w >= c.nwave) return;
+  const double wn = c.wn[w];
+  const double wn4 = (wn * wn) * (wn * wn);
+  const int nl = c.nlayer;
+  // blockIdx.y splits the layers so that small batches still fill the machine
+  const int per = (nl + gridDim.y - 1) / gridDim.y;
+  const int d0 = blockIdx.y * per, d1 = min(nl, d0 + per);
+  double *out = ext + (size_t)m * nl * c.nwave + w;
+  for (int d = d0; d < d1; d++)
+    out[(size_t)(nl - 1 - d) * c.nwave] = cell_extinction(c, s_tab, d, w, wn4, mol_only != 0);
+}
+
+// ---------------------------------------------------------------------------------------
+// K4 band integration: one CTA per (model, filter); trapezoid of (spectrum/star*rprs^2)*weight
+// over the filter's contiguous sample range (wine.py:177-199, BARTfunc.py:386-396).
+__global__ void __launch_bounds__(128)
+band_integrate_kernel(const double *__restrict__ spectra, const double *__restrict__ wn,
+                      const int *__restrict__ fstart, const int *__restrict__ fcount,
+                      const int *__restrict__ foffset, const double *__restrict__ weight,
+                      const double *__restrict__ star, double rprs2, const int *__restrict__ status,
+                      double *__restrict__ bandflux, int nfilters, int nwave) {
+  const int m = blockIdx.x, f = blockIdx.y;
+  double *out = bandflux + (size_t)m * nfilters + f;
+  if (status && status[m] != 0) { if (threadIdx.x == 0) *out = -1.0; return; }
+  const int s0 = fstart[f], n = fcount[f], off = foffset[f];
+  const double *sp = spectra + (size_t)m * nwave + s0;
+  const double *x = wn + s0;
+  const double *wt = weight + off;
+  const double *st = star ? star + off : nullptr;
+  double acc = 0.0;
+  for (int k = threadIdx.x; k < n - 1; k += blockDim.x) {
+    double y0 = sp[k], y1 = sp[k + 1];
+    if (st) { y0 = y0 / st[k] * rprs2; y1 = y1 / st[k + 1] * rprs2; }
+    acc += (x[k + 1] - x[k]) * (y1 * wt[k + 1] + y0 * wt[k]);
+  }
+  // fixed-shape reduction: deterministic for a given launch configuration
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  __shared__ double s_part[4];
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) *out = 0.5 * ((s_part[0] + s_part[1]) + (s_part[2] + s_part[3]));
+}
+
+// L2 flush helper: stream-write a buffer larger than the L2
+__global__ void fill_kernel(double *p, size_t n, double v) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    p[i] = v;
+}
+
+// ---------------------------------------------------------------------------------------
+// launchers
+static size_t table_smem(const DevConfig &c) { return (size_t)c.lay.stride() * sizeof(double); }
+
+void launch_atm_prep(const DevConfig &c, const Knobs &k, const double *profiles, int n_in,
+                     double *tabs, int *status, int nmodels, cudaStream_t s) {
+  const size_t smem = ((size_t)c.nspec + 2) * c.nlayer * sizeof(double);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaFuncSetAttribute(atm_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = smem;
+  }
+  atm_prep_kernel<<<nmodels, 128, smem, s>>>(c, k, profiles, n_in, tabs, status, nmodels);
+}
+
+template <int NANG, bool KEEP>
+static void launch_eclipse_t(const DevConfig &c, const double *tabs, const int *status,
+                             double *spectra, double *tau_keep, int *last_keep, int nmodels,
+                             int use_tma, cudaStream_t s) {
+  const size_t smem = table_smem(c);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaFuncSetAttribute(eclipse_column_kernel<NANG, KEEP>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = smem;
+  }
+  const int tiles = (c.nwave + kColThreads - 1) / kColThreads;
+  eclipse_column_kernel<NANG, KEEP><<<(unsigned)((size_t)tiles * nmodels), kColThreads, smem, s>>>(
+      c, tabs, status, spectra, tau_keep, last_keep, nmodels, use_tma);
+}
+
+void launch_eclipse(const DevConfig &c, const double *tabs, const int *status, double *spectra,
+                    double *tau_keep, int *last_keep, int nmodels, bool keep, int use_tma,
+                    cudaStream_t s) {
+#define BART_ECL(N)                                                                              \
+  case N:                                                                                        \
+    if (keep) launch_eclipse_t<N, true>(c, tabs, status, spectra, tau_keep, last_keep, nmodels,  \
+                                        use_tma, s);                                             \
+    else launch_eclipse_t<N, false>(c, tabs, status, spectra, tau_keep, last_keep, nmodels,      \
+                                    use_tma, s);                                                 \
+    break;
+  switch (c.nang) {
+    BART_ECL(1) BART_ECL(2) BART_ECL(3) BART_ECL(4) BART_ECL(5) BART_ECL(6) BART_ECL(7) BART_ECL(8)
+    default:
+      if (keep) launch_eclipse_t<0, true>(c, tabs, status, spectra, tau_keep, last_keep, nmodels,
+                                          use_tma, s);
+      else launch_eclipse_t<0, false>(c, tabs, status, spectra, tau_keep, last_keep, nmodels,
+                                      use_tma, s);
+  }
+#undef BART_ECL
+}
+
+void launch_merge_status(int *status, const int *status_col, int nmodels, cudaStream_t s) {
+  merge_status_kernel<<<(nmodels + 255) / 256, 256, 0, s>>>(status, status_col, nmodels);
+}
+
+void launch_transit(const DevConfig &c, const double *tabs, double *wts, const int *status,
+                    int *status_col, double *spectra, double *tau_keep, int *last_keep,
+                    int nmodels, bool keep, int use_tma, cudaStream_t s) {
+  transit_weights_kernel<<<nmodels, 128, 0, s>>>(c, tabs, wts, nmodels);
+  const size_t smem = table_smem(c) + (size_t)c.nlayer * kTransitThreads * sizeof(double);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaFuncSetAttribute(transit_column_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)smem);
+    cudaFuncSetAttribute(transit_column_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)smem);
+    configured = smem;
+  }
+  const int tiles = (c.nwave + kTransitThreads - 1) / kTransitThreads;
+  const unsigned grid = (unsigned)((size_t)tiles * nmodels);
+  if (keep)
+    transit_column_kernel<true><<<grid, kTransitThreads, smem, s>>>(
+        c, tabs, wts, status, status_col, spectra, tau_keep, last_keep, nmodels, use_tma);
+  else
+    transit_column_kernel<false><<<grid, kTransitThreads, smem, s>>>(
+        c, tabs, wts, status, status_col, spectra, tau_keep, last_keep, nmodels, use_tma);
+}
+
+void launch_extinction(const DevConfig &c, const double *tabs, double *ext, int nmodels,
+                       bool mol_only, int layer_splits, int use_tma, cudaStream_t s) {
+  const size_t smem = table_smem(c);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaFuncSetAttribute(extinction_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = smem;
+  }
+  const int tiles = (c.nwave + kColThreads - 1) / kColThreads;
+  dim3 grid((unsigned)((size_t)tiles * nmodels), (unsigned)layer_splits);
+  extinction_kernel<<<grid, kColThreads, smem, s>>>(c, tabs, ext, nmodels, mol_only ? 1 : 0, use_tma);
+}
+
+void launch_band_integrate(const double *spectra, const double *wn, const int *fstart,
+                           const int *fcount, const int *foffset, const double *weight,
+                           const double *star, double rprs2, const int *status, double *bandflux,
+                           int nfilters, int nwave, int nmodels, cudaStream_t s) {
+  dim3 grid((unsigned)nmodels, (unsigned)nfilters);
+  band_integrate_kernel<<<grid, 128, 0, s>>>(spectra, wn, fstart, fcount, foffset, weight, star,
+                                             rprs2, status, bandflux, nfilters, nwave);
+}
+
+void launch_fill(double *p, size_t n, double v, cudaStream_t s) {
+  fill_kernel<<<148 * 8, 256, 0, s>>>(p, n, v);
+}
+
+}  // namespace bart

@@ -1,0 +1,29 @@
+// kernels.hpp -- host-callable launchers of kernels.cu / builder.cu
+#pragma once
+#include "device.cuh"
+#include <cuda_runtime.h>
+#include <cstddef>
+
+namespace bart {
+
+constexpr int kColThreads = 128;      // wavenumbers per CTA, eclipse / lookup kernels
+constexpr int kTransitThreads = 64;   // wavenumbers per CTA, transit kernel (smem: nlayer x 64 x 8 B)
+
+void launch_atm_prep(const DevConfig &c, const Knobs &k, const double *profiles, int n_in,
+                     double *tabs, int *status, int nmodels, cudaStream_t s);
+void launch_eclipse(const DevConfig &c, const double *tabs, const int *status, double *spectra,
+                    double *tau_keep, int *last_keep, int nmodels, bool keep, int use_tma,
+                    cudaStream_t s);
+void launch_transit(const DevConfig &c, const double *tabs, double *wts, const int *status,
+                    int *status_col, double *spectra, double *tau_keep, int *last_keep,
+                    int nmodels, bool keep, int use_tma, cudaStream_t s);
+void launch_merge_status(int *status, const int *status_col, int nmodels, cudaStream_t s);
+void launch_extinction(const DevConfig &c, const double *tabs, double *ext, int nmodels,
+                       bool mol_only, int layer_splits, int use_tma, cudaStream_t s);
+void launch_band_integrate(const double *spectra, const double *wn, const int *fstart,
+                           const int *fcount, const int *foffset, const double *weight,
+                           const double *star, double rprs2, const int *status, double *bandflux,
+                           int nfilters, int nwave, int nmodels, cudaStream_t s);
+void launch_fill(double *p, size_t n, double v, cudaStream_t s);
+
+}  // namespace bart

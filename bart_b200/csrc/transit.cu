@@ -1,0 +1,1021 @@
+// transit.cu -- the C ABI of libbart_b200 (include/bart_b200.h): process-global state, init
+// sequence, batched execution, timing, introspection and the multi-GPU exchange.
+//
+// Mirrors the stage sequence of the reference's transit_init (transit/src/transit.c:25-74) and
+// run_transit/do_transit (118-214), but everything per-model runs on the device, batched over
+// models, with no per-call allocation, no file output inside the MCMC loop (the reference's
+// printflux/printmod rewrite the spectrum file on every call, eclipse.c:355-380,
+// slantpath.c:510-555; see DESIGN.md "deviations") and no host round trips between stages.
+#include "../../include/bart_b200.h"
+#include "host.hpp"
+#include "kernels.hpp"
+#include "column_math.cuh"
+#include "builder.hpp"
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <cstdarg>
+#include <cstring>
+#include <cstdlib>
+#include <cmath>
+#include <string>
+#include <vector>
+#include <map>
+#include <algorithm>
+#include <unistd.h>
+#include <sys/stat.h>
+
+namespace bart {
+
+// ---------------------------------------------------------------------------------------
+// errors
+struct BartError {};
+static int g_error_mode = 0;
+static bool g_error_pending = false;
+static char g_error_msg[4096] = "";
+int g_verb = 2;
+
+void fail(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error_msg, sizeof(g_error_msg), fmt, ap);
+  va_end(ap);
+  g_error_pending = true;
+  if (g_error_mode == 0) {
+    // reference behaviour: message, then exit(EXIT_FAILURE) (transit.h:91-98)
+    fprintf(stderr, "\nTransit ERROR :: %s\n", g_error_msg);
+    exit(EXIT_FAILURE);
+  }
+  throw BartError();
+}
+
+void warn(int level, const char *fmt, ...) {
+  if (g_verb < level) return;
+  va_list ap;
+  va_start(ap, fmt);
+  fprintf(stderr, "Transit WARNING :: ");
+  vfprintf(stderr, fmt, ap);
+  fprintf(stderr, "\n");
+  va_end(ap);
+}
+
+static void info(int level, const char *fmt, ...) {
+  if (g_verb < level) return;
+  va_list ap;
+  va_start(ap, fmt);
+  vfprintf(stdout, fmt, ap);
+  va_end(ap);
+}
+
+#define CUDA_OK(call)                                                                      \
+  do {                                                                                     \
+    cudaError_t e_ = (call);                                                               \
+    if (e_ != cudaSuccess) fail("CUDA error %s at %s:%d (%s)", cudaGetErrorString(e_),     \
+                                __FILE__, __LINE__, #call);                                \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------
+// profiling: per-kernel CUDA-event timing on the library stream
+struct KStat { long long launches = 0; double ms = 0; };
+struct PendingEv { std::string name; cudaEvent_t a, b; };
+
+template <class T> struct DevBuf {
+  T *p = nullptr;
+  size_t cap = 0;
+  void ensure(size_t n) {
+    if (n <= cap) return;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc((void **)&p, n * sizeof(T));
+    if (e != cudaSuccess) fail("cudaMalloc of %zu bytes failed: %s", n * sizeof(T), cudaGetErrorString(e));
+    cap = n;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct State {
+  bool init = false;
+  int device = -1;
+  cudaStream_t stream = nullptr;
+  Options opt;
+  Atmosphere atm;
+  Molecules mol;
+  Tli tli;
+  OpacityGrid og;
+  std::vector<CiaTable> cia;
+  std::vector<double> wn;
+  std::vector<double> angles;
+  DevConfig dc{};
+  Knobs knobs{};
+  // static device arrays
+  DevBuf<double> d_grid, d_gtemp, d_wn, d_press, d_mass, d_pol;
+  DevBuf<double> d_ciaP[kMaxCia], d_ciaQ[kMaxCia], d_ciaT[kMaxCia];
+  // batch buffers
+  DevBuf<double> d_prof, d_tabs, d_spec, d_wts, d_tau, d_band, d_ext, d_flush;
+  DevBuf<int> d_status, d_status_col, d_last;
+  DevBuf<double> d_kr0, d_kcloud, d_klogext;
+  DevBuf<int> d_kflag;
+  int knob_models = 0;
+  // filters
+  int nfilters = 0;
+  DevBuf<int> d_fstart, d_fcount, d_foffset;
+  DevBuf<double> d_fweight, d_fstar;
+  bool have_star = false;
+  double rprs2 = 1.0;
+  // debug
+  bool keep = false;
+  int last_batch = 0;
+  int use_tma = 1;
+  // profiling
+  bool profile = false;
+  std::map<std::string, KStat> stats;
+  std::vector<PendingEv> pending;
+  long long launches = 0;
+  cudaEvent_t t0 = nullptr, t1 = nullptr;
+  // comm
+  void *nccl_lib = nullptr;
+  void *nccl_comm = nullptr;
+  int rank = 0, world = 1;
+  // builder
+  BuilderState *builder = nullptr;
+};
+static State G;
+
+struct KernelScope {
+  const char *name;
+  cudaEvent_t a = nullptr, b = nullptr;
+  explicit KernelScope(const char *n) : name(n) {
+    G.launches++;
+    if (G.profile) {
+      cudaEventCreate(&a); cudaEventCreate(&b);
+      cudaEventRecord(a, G.stream);
+    }
+  }
+  ~KernelScope() {
+    if (G.profile) {
+      cudaEventRecord(b, G.stream);
+      G.pending.push_back({name, a, b});
+    }
+  }
+};
+
+static void drain_profile() {
+  for (auto &p : G.pending) {
+    cudaEventSynchronize(p.b);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, p.a, p.b);
+    KStat &k = G.stats[p.name];
+    k.launches++; k.ms += ms;
+    cudaEventDestroy(p.a); cudaEventDestroy(p.b);
+  }
+  G.pending.clear();
+}
+
+static void check_launch(const char *what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) fail("kernel launch '%s' failed: %s", what, cudaGetErrorString(e));
+}
+
+// ---------------------------------------------------------------------------------------
+// device
+static void ensure_device() {
+  if (G.stream) return;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    fail("no CUDA device available (%s): libbart_b200 has no CPU path",
+         e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  if (G.device < 0) {
+    const char *s = getenv("BART_DEVICE");
+    if (!s) s = getenv("LOCAL_RANK");
+    G.device = s ? atoi(s) % n : 0;
+  }
+  if (G.device >= n) fail("device ordinal %d out of range (%d devices)", G.device, n);
+  CUDA_OK(cudaSetDevice(G.device));
+  cudaDeviceProp p;
+  CUDA_OK(cudaGetDeviceProperties(&p, G.device));
+  if (p.major < 10)
+    fail("device %d (%s, sm_%d%d) is not a Blackwell sm_100 part; this library ships sm_100a "
+         "code only", G.device, p.name, p.major, p.minor);
+  CUDA_OK(cudaStreamCreateWithFlags(&G.stream, cudaStreamNonBlocking));
+  CUDA_OK(cudaEventCreate(&G.t0));
+  CUDA_OK(cudaEventCreate(&G.t1));
+  const char *t = getenv("BART_NO_TMA");
+  G.use_tma = (t && atoi(t)) ? 0 : 1;
+}
+
+template <class T> static void upload(DevBuf<T> &b, const std::vector<T> &v) {
+  b.ensure(v.size() ? v.size() : 1);
+  if (!v.empty()) CUDA_OK(cudaMemcpy(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+}
+
+// ---------------------------------------------------------------------------------------
+// init pieces
+static void setup_sampling() {
+  Options &o = G.opt;
+  double lo, hi;
+  // makewnsample, makesample.c:308-400
+  if (o.wnlow > 0) {
+    if (o.wnfct <= 0) fail("User specified wavenumber factor is negative (%g).", o.wnfct);
+    lo = o.wnlow * o.wnfct;
+  } else if (o.wlhigh > 0) {
+    if (o.wlfct <= 0) fail("User specified wavelength factor is negative (%g).", o.wlfct);
+    lo = 1.0 / (o.wlhigh * o.wlfct);
+  } else fail("Initial wavenumber (nor final wavelength) were correctly provided by the user.");
+  if (o.wnhigh > 0) {
+    if (o.wnfct < 0) fail("User specified wavenumber factor is negative (%g).", o.wnfct);
+    hi = o.wnhigh * o.wnfct;
+  } else if (o.wllow > 0) {
+    if (o.wlfct < 0) fail("User specified wavelength factor is negative (%g).", o.wlfct);
+    hi = 1.0 / (o.wllow * o.wlfct);
+  } else fail("Final wavenumber (nor initial wavelength) were correctly provided by the user.");
+  if (o.wndelt <= 0) fail("Incorrect wavenumber spacing (%g), it must be positive.", o.wndelt);
+  G.wn = make_sampling(lo, hi, o.wndelt, 1);
+}
+
+// CIA tables pre-folded through the wavenumber spline.  The reference interpolates, per model and
+// per layer, (1) every table row in temperature and (2) the resulting column in wavenumber
+// (bicubicinterpolate, crosssec.c:353-428).  Both steps are linear in the table values and step
+// (2) does not depend on the model, so it is applied ONCE here to the table columns P_k = y(:,T_k)
+// and to their temperature second derivatives Q_k = z(:,T_k); a model then needs only the four
+// cubic coefficients of step (1) per layer.
+static void setup_cia() {
+  const int nw = (int)G.wn.size();
+  G.dc.ncia = (int)G.cia.size();
+  if (G.dc.ncia > kMaxCia) fail("at most %d cross-section files are supported (%d given)", kMaxCia, G.dc.ncia);
+  for (int f = 0; f < G.dc.ncia; f++) {
+    const CiaTable &c = G.cia[f];
+    const int nx = (int)c.wn.size(), nt = (int)c.temp.size();
+    if (c.wn[0] > G.wn[0] || c.wn[nx - 1] < G.wn[nw - 1])
+      fail("The wavelength range [%.2f, %.2f] cm-1 of the cross-section file:\n  '%s',\ndoes not "
+           "cover Transit's wavelength range [%.2f, %.2f] cm-1.", c.wn[0], c.wn[nx - 1],
+           c.file.c_str(), G.wn[0], G.wn[nw - 1]);
+    std::vector<double> P, Q;
+    fold_cia_table(c, G.wn, P, Q);
+    upload(G.d_ciaP[f], P); upload(G.d_ciaQ[f], Q); upload(G.d_ciaT[f], c.temp);
+    G.dc.ciaP[f] = G.d_ciaP[f].p; G.dc.ciaQ[f] = G.d_ciaQ[f].p; G.dc.ciaT[f] = G.d_ciaT[f].p;
+    G.dc.cia_nt[f] = nt;
+    G.dc.cia_nspec[f] = (int)c.species.size();
+    for (size_t s = 0; s < c.species.size(); s++) {
+      int idx = -1;
+      for (int j = 0; j < G.atm.nspec(); j++) if (G.atm.species[j] == c.species[s]) idx = j;
+      if (idx < 0)
+        fail("Cross-section species '%s' from file '%s' does not match any in the atmsopheric "
+             "file.", c.species[s].c_str(), c.file.c_str());
+      G.dc.cia_spec[f][s] = idx;
+    }
+  }
+}
+
+static void load_grid_to_device(const std::string &path) {
+  OpacityGrid &g = G.og;
+  if (g.nlayer != G.atm.nlayer())
+    fail("Opacity grid has %ld layers but the atmosphere has %d.", g.nlayer, G.atm.nlayer());
+  if (g.nwave != (long)G.wn.size())
+    fail("Opacity grid has %ld wavenumber samples but the configuration asks for %zu.", g.nwave, G.wn.size());
+  const size_t n = (size_t)g.nlayer * g.ntemp * g.nmol * g.nwave;
+  G.d_grid.ensure(n);
+  FILE *f = fopen(path.c_str(), "rb");
+  if (!f) fail("Opening opacity file '%s' failed.", path.c_str());
+  fseek(f, g.data_offset, SEEK_SET);
+  // stream the file through a pinned staging buffer (files reach tens of GB at high resolution)
+  const size_t chunk = 64u << 20;
+  void *stage = nullptr;
+  CUDA_OK(cudaMallocHost(&stage, chunk));
+  size_t done = 0, total = n * sizeof(double);
+  while (done < total) {
+    size_t want = std::min(chunk, total - done);
+    size_t got = fread(stage, 1, want, f);
+    if (got != want) { cudaFreeHost(stage); fclose(f); fail("Opacity file '%s' is truncated.", path.c_str()); }
+    CUDA_OK(cudaMemcpy((char *)G.d_grid.p + done, stage, got, cudaMemcpyHostToDevice));
+    done += got;
+  }
+  cudaFreeHost(stage);
+  fclose(f);
+}
+
+static void finish_grid_config() {
+  OpacityGrid &g = G.og;
+  if (g.nmol > kMaxGridMol) fail("at most %d line-list molecules are supported", kMaxGridMol);
+  G.dc.ntemp = (int)g.ntemp; G.dc.ngmol = (int)g.nmol;
+  upload(G.d_gtemp, g.temp);
+  G.dc.gtemp = G.d_gtemp.p;
+  G.dc.grid = G.d_grid.p;
+  for (int m = 0; m < g.nmol; m++) {
+    int idx = -1;
+    for (int j = 0; j < G.atm.nspec(); j++) if (G.mol.id[j] == g.molid[m]) idx = j;   // valueinarray, extinction.c:575
+    if (idx < 0) fail("Opacity-grid molecule ID %d is not among the atmospheric species.", g.molid[m]);
+    G.dc.gmol_spec[m] = idx;
+  }
+}
+
+static void reset_state() {
+  G.d_grid.release(); G.d_gtemp.release(); G.d_wn.release(); G.d_press.release();
+  G.d_mass.release(); G.d_pol.release();
+  for (int f = 0; f < kMaxCia; f++) { G.d_ciaP[f].release(); G.d_ciaQ[f].release(); G.d_ciaT[f].release(); }
+  G.d_prof.release(); G.d_tabs.release(); G.d_spec.release(); G.d_wts.release(); G.d_tau.release();
+  G.d_band.release(); G.d_ext.release(); G.d_status.release(); G.d_status_col.release();
+  G.d_last.release(); G.d_kr0.release(); G.d_kcloud.release(); G.d_klogext.release(); G.d_kflag.release();
+  G.d_fstart.release(); G.d_fcount.release(); G.d_foffset.release(); G.d_fweight.release();
+  G.d_fstar.release(); G.d_flush.release();
+  if (G.builder) { builder_free(G.builder); G.builder = nullptr; }
+  G.nfilters = 0; G.knob_models = 0; G.last_batch = 0;
+  G.cia.clear(); G.wn.clear(); G.angles.clear();
+  G.init = false;
+}
+
+static void do_init(int argc, char **argv) {
+  if (G.init) reset_state();
+  G.opt = Options();
+  parse_options(argc, argv, G.opt);
+  Options &o = G.opt;
+  // acceptgenhints, argum.c:773-911
+  if (o.solution != "eclipse" && o.solution != "transit")
+    fail("Solution kind '%s' is invalid.\nCurrently Accepted are:\n transit\n eclipse", o.solution.c_str());
+  if (o.nwidth < 1) fail("Times of maximum width has to be greater than one: %g", (double)o.nwidth);
+  if (o.ethreshold <= 0) fail("Extinction-coefficient threshold (%.3e) has to be positive.", o.ethreshold);
+  if (o.refradius < 0) fail("Reference radius level (%g) must be positive.", o.refradius);
+  if (o.refpress < 0) fail("Reference pressure level (%g) must be positive.", o.refpress);
+  if (o.gsurf < 0) fail("Surface gravity (%g cm s^-2) must be positive.", o.gsurf);
+  if (o.raddelt != -1) fail("raddelt %g: resampling the atmosphere to an equidistant radius grid is "
+                            "not supported (BART always uses the atmosphere-file layers)", o.raddelt);
+  if (o.taulevel != 1) fail("slantpath:: totaltau:: Level %i of detail has not been implemented to "
+                            "compute optical depth.", o.taulevel);
+  if (o.modlevel != 1) fail("modlevel %d is not supported (only 1)", o.modlevel);
+  ensure_device();
+
+  info(2, "--------------------------------------------------\n"
+          "        TRANSIT (bart_b200, sm_100a)\n"
+          "--------------------------------------------------\n");
+  setup_sampling();
+  read_atmosphere(o.atm, G.atm);
+  read_molecules(o.molfile, G.atm, G.mol);
+  read_tli_header(o.linedb, G.tli);
+  const int nl = G.atm.nlayer(), ns = G.atm.nspec(), nw = (int)G.wn.size();
+  if (ns > kMaxSpec) fail("at most %d atmospheric species are supported", kMaxSpec);
+  // makeradsample's temperature check against the TLI range (makesample.c:488-503)
+  for (int i = 0; i < nl; i++) {
+    if (G.atm.temp[i] * G.atm.tfct < G.tli.tmin)
+      fail("The layer %d in the atmospheric model has a lower temperature (%.1f K) than the lowest "
+           "allowed TLI temperature (%.1f K).", i, G.atm.temp[i], G.tli.tmin);
+    if (G.atm.temp[i] * G.atm.tfct > G.tli.tmax)
+      fail("The layer %d in the atmospheric model has a higher temperature (%.1f K) than the "
+           "highest allowed TLI temperature (%.1f K).", i, G.atm.temp[i], G.tli.tmax);
+  }
+
+  DevConfig &c = G.dc;
+  c = DevConfig();
+  c.nlayer = nl; c.nspec = ns; c.nwave = nw;
+  c.eclipse = o.solution == "eclipse";
+  c.transparent = o.transparent ? 1 : 0;
+  c.pfct = G.atm.pfct; c.rfct = G.atm.rfct; c.gsurf = o.gsurf; c.p0 = o.refpress;
+  c.toomuch = o.toomuch;
+  upload(G.d_wn, G.wn); c.wn = G.d_wn.p;
+  upload(G.d_press, G.atm.press); c.press = G.d_press.p;
+  upload(G.d_mass, G.mol.mass); c.mass = G.d_mass.p;
+  upload(G.d_pol, G.mol.pol); c.pol = G.d_pol.p;
+  // ray grid (acceptgenhints 878-881; flux(), eclipse.c:262-279)
+  G.angles.clear();
+  if (c.eclipse) {
+    char *dup = strdup(o.raygrid.c_str());
+    for (char *t = strtok(dup, " \t"); t; t = strtok(nullptr, " \t")) G.angles.push_back(atof(t));
+    free(dup);
+    if (G.angles.empty() || (int)G.angles.size() > kMaxAng)
+      fail("raygrid must hold between 1 and %d angles", kMaxAng);
+    c.nang = (int)G.angles.size();
+    std::vector<double> area(c.nang + 1);
+    area[0] = 0.0 * kDEG; area[c.nang] = 90.0 * kDEG;
+    for (int a = 1; a < c.nang; a++) area[a] = (G.angles[a - 1] + G.angles[a]) * kDEG / 2.0;
+    for (int a = 0; a < c.nang; a++) {
+      c.inv_mu[a] = 1.0 / cos(G.angles[a] * kDEG);
+      c.wgt[a] = pow(sin(area[a + 1]), 2.0) - pow(sin(area[a]), 2.0);
+    }
+  }
+  const double srad = o.starrad * kSUNRADIUS;                      // geometry.c:36,50
+  c.inv_srad2 = 1.0 / (srad * srad);
+
+  // knobs: process-wide defaults from the configuration
+  Knobs &k = G.knobs;
+  k = Knobs();
+  k.r0_all = o.refradius;
+  k.cloud_flag_all = o.cloud_flag; k.cloudext_all = o.cloudext;
+  k.cloudtop_all = o.cloudtop; k.cloudbot_all = o.cloudbot;
+  k.scat_flag_all = o.scat_flag; k.scat_logext_all = o.scat_logext;
+
+  // opacity(): opacity.c:8-214
+  bool have_file = false;
+  if (!o.opacityfile.empty()) {
+    struct stat st;
+    have_file = stat(o.opacityfile.c_str(), &st) == 0 && S_ISREG(st.st_mode);
+  }
+  if (o.opacityfile.empty())
+    fail("No opacity file given: the on-the-fly line-by-line mode of the reference (tau.c:163-175) "
+         "is not part of this library yet; set 'opacityfile' (it is built when missing).");
+  if (!have_file) {
+    if (!G.tli.present) fail("Cannot build the opacity grid '%s': no TLI line list (linedb) given.", o.opacityfile.c_str());
+    info(2, "Calculating new grid of opacities: '%s'.\n", o.opacityfile.c_str());
+    builder_run_and_write(G.builder, G.opt, G.atm, G.mol, G.tli, G.wn, G.stream, o.opacityfile);
+  }
+  if (o.justOpacity) {            // transit.c:133-136 opabreak: nothing else to do
+    G.init = true;
+    return;
+  }
+  if (!read_opacity_header(o.opacityfile, G.og)) fail("Opening opacity file failed.");
+  load_grid_to_device(o.opacityfile);
+  finish_grid_config();
+
+  // readcs(): crosssec.c:9-268
+  G.cia.resize(o.csfiles.size());
+  for (size_t i = 0; i < o.csfiles.size(); i++) read_cia(o.csfiles[i], G.cia[i]);
+  setup_cia();
+
+  c.lay.nl = nl; c.lay.ngmol = c.ngmol; c.lay.ncia = c.ncia;
+  G.init = true;
+  info(2, "transit_init done: %d layers, %d species, %d wavenumbers, grid %ld T x %ld mol (%.1f MB "
+          "in HBM), %d CIA file(s), %s geometry.\n", nl, ns, nw, G.og.ntemp, G.og.nmol,
+       (double)bart_grid_bytes() / 1e6, c.ncia, c.eclipse ? "eclipse" : "transit");
+}
+
+// ---------------------------------------------------------------------------------------
+// batched execution (device-resident inputs)
+static Knobs effective_knobs(int nmodels) {
+  Knobs k = G.knobs;
+  if (G.knob_models != nmodels) { k.r0 = nullptr; k.cloudtop = nullptr; k.scat_flag = nullptr; k.scat_logext = nullptr; }
+  return k;
+}
+
+static void run_models_device(const double *d_prof, int nmodels, int n_in, double *d_spec) {
+  DevConfig &c = G.dc;
+  if (!G.init || G.opt.justOpacity) fail("Transit init not run, please initialize transit.");
+  if (n_in < (c.nspec + 1) * c.nlayer)
+    fail("run_transit: input has %d values, expected (1+%d species) x %d layers = %d", n_in, c.nspec,
+         c.nlayer, (c.nspec + 1) * c.nlayer);
+  if (nmodels <= 0) return;
+  G.d_tabs.ensure((size_t)nmodels * c.lay.stride());
+  G.d_status.ensure(nmodels);
+  G.d_status_col.ensure(nmodels);
+  if (G.keep) {
+    G.d_tau.ensure((size_t)nmodels * c.nwave * c.nlayer);
+    G.d_last.ensure((size_t)nmodels * c.nwave);
+    CUDA_OK(cudaMemsetAsync(G.d_tau.p, 0, (size_t)nmodels * c.nwave * c.nlayer * sizeof(double), G.stream));
+  }
+  Knobs k = effective_knobs(nmodels);
+  {
+    KernelScope ks("atm_prep");
+    launch_atm_prep(c, k, d_prof, n_in, G.d_tabs.p, G.d_status.p, nmodels, G.stream);
+    check_launch("atm_prep");
+  }
+  if (c.eclipse) {
+    KernelScope ks("eclipse_column");
+    launch_eclipse(c, G.d_tabs.p, G.d_status.p, d_spec, G.d_tau.p, G.d_last.p, nmodels, G.keep, G.use_tma, G.stream);
+    check_launch("eclipse_column");
+  } else {
+    G.d_wts.ensure((size_t)nmodels * c.nlayer * (c.nlayer + 1) / 2);
+    CUDA_OK(cudaMemsetAsync(G.d_status_col.p, 0, nmodels * sizeof(int), G.stream));
+    {
+      KernelScope ks("transit_column");
+      launch_transit(c, G.d_tabs.p, G.d_wts.p, G.d_status.p, G.d_status_col.p, d_spec, G.d_tau.p,
+                     G.d_last.p, nmodels, G.keep, G.use_tma, G.stream);
+      check_launch("transit_column");
+    }
+    launch_merge_status(G.d_status.p, G.d_status_col.p, nmodels, G.stream);
+    G.launches++;
+  }
+  G.last_batch = nmodels;
+}
+
+static void band_device(const double *d_spec, int nmodels, const int *d_status, double *d_band) {
+  if (G.nfilters <= 0) fail("bart_set_filters has not been called");
+  KernelScope ks("band_integrate");
+  launch_band_integrate(d_spec, G.d_wn.p, G.d_fstart.p, G.d_fcount.p, G.d_foffset.p, G.d_fweight.p,
+                        G.have_star ? G.d_fstar.p : nullptr, G.rprs2, d_status, d_band, G.nfilters,
+                        G.dc.nwave, nmodels, G.stream);
+  check_launch("band_integrate");
+}
+
+static void finish_stream() {
+  cudaError_t e = cudaStreamSynchronize(G.stream);
+  if (e != cudaSuccess) fail("CUDA execution failed: %s", cudaGetErrorString(e));
+  if (G.profile) drain_profile();
+}
+
+}  // namespace bart
+
+using namespace bart;
+
+#define API_BEGIN try {
+#define API_END_INT                                   \
+  } catch (BartError &) { return -1; }                \
+  catch (std::exception & e) {                        \
+    snprintf(g_error_msg, sizeof(g_error_msg), "%s", e.what()); g_error_pending = true; return -1; }
+#define API_END_VOID                                  \
+  } catch (BartError &) { return; }                   \
+  catch (std::exception & e) {                        \
+    snprintf(g_error_msg, sizeof(g_error_msg), "%s", e.what()); g_error_pending = true; return; }
+
+extern "C" {
+
+// =========================================================================================
+// Part 1: the reference boundary
+void transit_init(int argc, char **argv) {
+  API_BEGIN
+  do_init(argc, argv);
+  API_END_VOID
+}
+
+int get_no_samples(void) { return (int)G.wn.size(); }
+
+void get_waveno_arr(double *waveno_arr, int waveno) {
+  const int n = std::min((int)G.wn.size(), waveno);
+  if (G.init) for (int i = 0; i < n; i++) waveno_arr[i] = G.wn[i];
+  else {
+    printf("Transit not initialized, please run init. Values set -1\n");
+    for (int i = 0; i < waveno; i++) waveno_arr[i] = -1;
+  }
+}
+
+void set_radius(double refradius) { G.knobs.r0_all = refradius; }
+
+void set_cloudtop(double cloudtop) {
+  G.knobs.cloudtop_all = cloudtop; G.knobs.cloudbot_all = cloudtop + 10;
+  G.knobs.cloudext_all = 100; G.knobs.cloud_flag_all = 1;
+}
+
+void set_scattering(int flag, double scattering) {
+  G.knobs.scat_flag_all = flag; G.knobs.scat_logext_all = scattering;
+}
+
+void run_transit(double *re_input, int transint, double *transit_out, int transit_out_size) {
+  API_BEGIN
+  if (!G.init) { printf("Transit init not run, please initialize transit.\n"); return; }
+  int status = 0;
+  const int saved = G.knob_models;
+  G.knob_models = 0;                         // the single-model call uses the process-wide setters
+  int rc = bart_run_batch(re_input, 1, transint, transit_out, transit_out_size, &status);
+  G.knob_models = saved;
+  if (rc != 0) return;
+  // the reference exit()s where the batched path reports a per-model status
+  if (status & REJ_SUMQ) fail("Sum of abundances of isotopes adds up to more than 1");
+  if (status & REJ_TCIA) fail("A layer in the atmospheric model has a temperature outside the allowed "
+                              "cross-section temperature range.");
+  if (status & REJ_TGRID) fail("A layer in the atmospheric model has a temperature outside the "
+                               "opacity-grid temperature range [%g, %g] K.", G.og.temp.front(), G.og.temp.back());
+  if (status & REJ_FEWPTS) fail("Condition failed, less than 3 items for radial integration.");
+  API_END_VOID
+}
+
+void free_memory(void) {
+  API_BEGIN
+  reset_state();
+  API_END_VOID
+}
+
+// =========================================================================================
+// Part 2
+void bart_set_error_mode(int mode) { g_error_mode = mode; }
+const char *bart_last_error(void) { return g_error_msg; }
+int bart_error_pending(void) { return g_error_pending ? 1 : 0; }
+void bart_clear_error(void) { g_error_pending = false; g_error_msg[0] = 0; }
+
+int bart_set_device(int ordinal) {
+  API_BEGIN
+  if (G.stream && ordinal != G.device) fail("bart_set_device must be called before transit_init");
+  G.device = ordinal;
+  return 0;
+  API_END_INT
+}
+int bart_get_device(void) { return G.device; }
+
+int bart_device_info(char *name, int name_len, int *sm_count, int *cc_major, int *cc_minor,
+                     long long *l2_bytes, long long *hbm_bytes) {
+  API_BEGIN
+  ensure_device();
+  cudaDeviceProp p;
+  CUDA_OK(cudaGetDeviceProperties(&p, G.device));
+  if (name && name_len > 0) snprintf(name, name_len, "%s", p.name);
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  if (cc_major) *cc_major = p.major;
+  if (cc_minor) *cc_minor = p.minor;
+  if (l2_bytes) *l2_bytes = p.l2CacheSize;
+  if (hbm_bytes) *hbm_bytes = (long long)p.totalGlobalMem;
+  return 0;
+  API_END_INT
+}
+
+int bart_nlayers(void) { return G.dc.nlayer; }
+int bart_nspecies(void) { return G.dc.nspec; }
+int bart_ngridmol(void) { return G.dc.ngmol; }
+int bart_ngridtemp(void) { return G.dc.ntemp; }
+int bart_is_eclipse(void) { return G.dc.eclipse; }
+long long bart_grid_bytes(void) {
+  return (long long)G.og.nlayer * G.og.ntemp * G.og.nmol * G.og.nwave * 8;
+}
+
+int bart_set_batch_knobs(int nmodels, const double *refradius, const double *cloudtop,
+                         const int *scat_flag, const double *scat_logext) {
+  API_BEGIN
+  ensure_device();
+  Knobs &k = G.knobs;
+  k.r0 = nullptr; k.cloudtop = nullptr; k.scat_flag = nullptr; k.scat_logext = nullptr;
+  G.knob_models = 0;
+  if (nmodels <= 0) return 0;
+  if (refradius) { G.d_kr0.ensure(nmodels); CUDA_OK(cudaMemcpy(G.d_kr0.p, refradius, nmodels * 8, cudaMemcpyHostToDevice)); k.r0 = G.d_kr0.p; }
+  if (cloudtop) { G.d_kcloud.ensure(nmodels); CUDA_OK(cudaMemcpy(G.d_kcloud.p, cloudtop, nmodels * 8, cudaMemcpyHostToDevice)); k.cloudtop = G.d_kcloud.p; }
+  if (scat_flag) { G.d_kflag.ensure(nmodels); CUDA_OK(cudaMemcpy(G.d_kflag.p, scat_flag, nmodels * 4, cudaMemcpyHostToDevice)); k.scat_flag = G.d_kflag.p; }
+  if (scat_logext) { G.d_klogext.ensure(nmodels); CUDA_OK(cudaMemcpy(G.d_klogext.p, scat_logext, nmodels * 8, cudaMemcpyHostToDevice)); k.scat_logext = G.d_klogext.p; }
+  G.knob_models = nmodels;
+  return 0;
+  API_END_INT
+}
+
+int bart_run_batch_device(const double *d_profiles, int nmodels, int n_in, double *d_spectra,
+                          int n_out, int *d_status) {
+  API_BEGIN
+  if (n_out < G.dc.nwave) fail("output holds %d values per model, %d needed", n_out, G.dc.nwave);
+  if (n_out != G.dc.nwave) fail("bart_run_batch_device needs n_out == nwave (%d)", G.dc.nwave);
+  run_models_device(d_profiles, nmodels, n_in, d_spectra);
+  if (d_status)
+    CUDA_OK(cudaMemcpyAsync(d_status, G.d_status.p, nmodels * sizeof(int), cudaMemcpyDeviceToDevice, G.stream));
+  finish_stream();
+  return 0;
+  API_END_INT
+}
+
+int bart_run_batch(const double *profiles, int nmodels, int n_in, double *spectra, int n_out,
+                   int *status) {
+  API_BEGIN
+  if (!G.init || G.opt.justOpacity) fail("Transit init not run, please initialize transit.");
+  const int nw = G.dc.nwave;
+  if (n_out < nw) fail("output holds %d values per model, %d needed", n_out, nw);
+  if (nmodels <= 0) return 0;
+  G.d_prof.ensure((size_t)nmodels * n_in);
+  G.d_spec.ensure((size_t)nmodels * nw);
+  CUDA_OK(cudaMemcpyAsync(G.d_prof.p, profiles, (size_t)nmodels * n_in * 8, cudaMemcpyHostToDevice, G.stream));
+  run_models_device(G.d_prof.p, nmodels, n_in, G.d_spec.p);
+  if (n_out == nw)
+    CUDA_OK(cudaMemcpyAsync(spectra, G.d_spec.p, (size_t)nmodels * nw * 8, cudaMemcpyDeviceToHost, G.stream));
+  else
+    CUDA_OK(cudaMemcpy2DAsync(spectra, (size_t)n_out * 8, G.d_spec.p, (size_t)nw * 8, (size_t)nw * 8,
+                              nmodels, cudaMemcpyDeviceToHost, G.stream));
+  std::vector<int> st;
+  if (status)
+    CUDA_OK(cudaMemcpyAsync(status, G.d_status.p, nmodels * sizeof(int), cudaMemcpyDeviceToHost, G.stream));
+  finish_stream();
+  return 0;
+  API_END_INT
+}
+
+int bart_set_filters(int nfilters, const int *start, const int *count, const double *weight,
+                     const double *star, double rprs) {
+  API_BEGIN
+  ensure_device();
+  if (nfilters <= 0) { G.nfilters = 0; return 0; }
+  std::vector<int> off(nfilters);
+  long long tot = 0;
+  for (int f = 0; f < nfilters; f++) {
+    if (start[f] < 0 || count[f] < 2 || start[f] + count[f] > (int)G.wn.size())
+      fail("filter %d covers samples [%d, %d) outside the spectrum (%zu samples)", f, start[f],
+           start[f] + count[f], G.wn.size());
+    off[f] = (int)tot; tot += count[f];
+  }
+  G.d_fstart.ensure(nfilters); G.d_fcount.ensure(nfilters); G.d_foffset.ensure(nfilters);
+  G.d_fweight.ensure(tot);
+  CUDA_OK(cudaMemcpy(G.d_fstart.p, start, nfilters * 4, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(G.d_fcount.p, count, nfilters * 4, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(G.d_foffset.p, off.data(), nfilters * 4, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(G.d_fweight.p, weight, tot * 8, cudaMemcpyHostToDevice));
+  G.have_star = star != nullptr;
+  if (star) { G.d_fstar.ensure(tot); CUDA_OK(cudaMemcpy(G.d_fstar.p, star, tot * 8, cudaMemcpyHostToDevice)); }
+  G.rprs2 = rprs * rprs;
+  G.nfilters = nfilters;
+  return 0;
+  API_END_INT
+}
+
+int bart_band_integrate(const double *spectra, int nmodels, int nwave, double *bandflux) {
+  API_BEGIN
+  if (nwave != (int)G.wn.size()) fail("bart_band_integrate: nwave %d != %zu", nwave, G.wn.size());
+  G.d_spec.ensure((size_t)nmodels * nwave);
+  G.d_band.ensure((size_t)nmodels * std::max(1, G.nfilters));
+  CUDA_OK(cudaMemcpyAsync(G.d_spec.p, spectra, (size_t)nmodels * nwave * 8, cudaMemcpyHostToDevice, G.stream));
+  band_device(G.d_spec.p, nmodels, nullptr, G.d_band.p);
+  CUDA_OK(cudaMemcpyAsync(bandflux, G.d_band.p, (size_t)nmodels * G.nfilters * 8, cudaMemcpyDeviceToHost, G.stream));
+  finish_stream();
+  return 0;
+  API_END_INT
+}
+
+int bart_bandflux_batch_device(const double *d_profiles, int nmodels, int n_in, double *d_bandflux,
+                               int *d_status) {
+  API_BEGIN
+  G.d_spec.ensure((size_t)nmodels * G.dc.nwave);
+  run_models_device(d_profiles, nmodels, n_in, G.d_spec.p);
+  band_device(G.d_spec.p, nmodels, G.d_status.p, d_bandflux);
+  if (d_status)
+    CUDA_OK(cudaMemcpyAsync(d_status, G.d_status.p, nmodels * sizeof(int), cudaMemcpyDeviceToDevice, G.stream));
+  finish_stream();
+  return 0;
+  API_END_INT
+}
+
+int bart_bandflux_batch(const double *profiles, int nmodels, int n_in, double *bandflux, int *status) {
+  API_BEGIN
+  if (!G.init || G.opt.justOpacity) fail("Transit init not run, please initialize transit.");
+  if (nmodels <= 0) return 0;
+  G.d_prof.ensure((size_t)nmodels * n_in);
+  G.d_spec.ensure((size_t)nmodels * G.dc.nwave);
+  G.d_band.ensure((size_t)nmodels * std::max(1, G.nfilters));
+  CUDA_OK(cudaMemcpyAsync(G.d_prof.p, profiles, (size_t)nmodels * n_in * 8, cudaMemcpyHostToDevice, G.stream));
+  run_models_device(G.d_prof.p, nmodels, n_in, G.d_spec.p);
+  band_device(G.d_spec.p, nmodels, G.d_status.p, G.d_band.p);
+  CUDA_OK(cudaMemcpyAsync(bandflux, G.d_band.p, (size_t)nmodels * G.nfilters * 8, cudaMemcpyDeviceToHost, G.stream));
+  if (status)
+    CUDA_OK(cudaMemcpyAsync(status, G.d_status.p, nmodels * sizeof(int), cudaMemcpyDeviceToHost, G.stream));
+  finish_stream();
+  return 0;
+  API_END_INT
+}
+
+int bart_extinction_batch(const double *profiles, int nmodels, int n_in, double *ext_out, int what) {
+  API_BEGIN
+  if (!G.init || G.opt.justOpacity) fail("Transit init not run, please initialize transit.");
+  DevConfig &c = G.dc;
+  if (nmodels <= 0) return 0;
+  const size_t n = (size_t)nmodels * c.nlayer * c.nwave;
+  G.d_prof.ensure((size_t)nmodels * n_in);
+  G.d_tabs.ensure((size_t)nmodels * c.lay.stride());
+  G.d_status.ensure(nmodels);
+  G.d_ext.ensure(n);
+  CUDA_OK(cudaMemcpyAsync(G.d_prof.p, profiles, (size_t)nmodels * n_in * 8, cudaMemcpyHostToDevice, G.stream));
+  Knobs k = effective_knobs(nmodels);
+  { KernelScope ks("atm_prep");
+    launch_atm_prep(c, k, G.d_prof.p, n_in, G.d_tabs.p, G.d_status.p, nmodels, G.stream); check_launch("atm_prep"); }
+  const int tiles = (c.nwave + kColThreads - 1) / kColThreads;
+  int splits = 1;
+  while ((long long)tiles * nmodels * splits < 148 * 8 && splits < c.nlayer) splits *= 2;
+  { KernelScope ks("opacity_lookup");
+    launch_extinction(c, G.d_tabs.p, G.d_ext.p, nmodels, what == 0, splits, G.use_tma, G.stream);
+    check_launch("opacity_lookup"); }
+  if (ext_out)
+    CUDA_OK(cudaMemcpyAsync(ext_out, G.d_ext.p, n * 8, cudaMemcpyDeviceToHost, G.stream));
+  finish_stream();
+  G.last_batch = nmodels;
+  return 0;
+  API_END_INT
+}
+
+// ---- memory helpers ----
+void *bart_dev_alloc(long long bytes) {
+  try { ensure_device(); } catch (BartError &) { return nullptr; }
+  void *p = nullptr;
+  if (cudaMalloc(&p, (size_t)bytes) != cudaSuccess) return nullptr;
+  return p;
+}
+void bart_dev_free(void *p) { if (p) cudaFree(p); }
+void *bart_host_alloc_pinned(long long bytes) {
+  try { ensure_device(); } catch (BartError &) { return nullptr; }
+  void *p = nullptr;
+  if (cudaMallocHost(&p, (size_t)bytes) != cudaSuccess) return nullptr;
+  return p;
+}
+void bart_host_free_pinned(void *p) { if (p) cudaFreeHost(p); }
+int bart_memcpy_h2d(void *dst, const void *src, long long bytes) {
+  API_BEGIN ensure_device();
+  CUDA_OK(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyHostToDevice, G.stream));
+  CUDA_OK(cudaStreamSynchronize(G.stream));
+  return 0; API_END_INT
+}
+int bart_memcpy_d2h(void *dst, const void *src, long long bytes) {
+  API_BEGIN ensure_device();
+  CUDA_OK(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost, G.stream));
+  CUDA_OK(cudaStreamSynchronize(G.stream));
+  return 0; API_END_INT
+}
+int bart_sync(void) { API_BEGIN ensure_device(); finish_stream(); return 0; API_END_INT }
+
+// ---- timing ----
+int bart_timer_begin(void) {
+  API_BEGIN ensure_device();
+  CUDA_OK(cudaEventRecord(G.t0, G.stream));
+  return 0; API_END_INT
+}
+double bart_timer_end(void) {
+  try {
+    ensure_device();
+    CUDA_OK(cudaEventRecord(G.t1, G.stream));
+    CUDA_OK(cudaEventSynchronize(G.t1));
+    float ms = 0;
+    CUDA_OK(cudaEventElapsedTime(&ms, G.t0, G.t1));
+    return (double)ms;
+  } catch (BartError &) { return -1.0; }
+}
+void bart_profile_enable(int on) { G.profile = on != 0; }
+void bart_profile_reset(void) { G.stats.clear(); G.launches = 0; }
+int bart_kernel_stats(int index, char *name, int name_len, long long *launches, double *ms) {
+  if (index < 0 || index >= (int)G.stats.size()) return -1;
+  auto it = G.stats.begin();
+  std::advance(it, index);
+  if (name && name_len > 0) snprintf(name, name_len, "%s", it->first.c_str());
+  if (launches) *launches = it->second.launches;
+  if (ms) *ms = it->second.ms;
+  return 0;
+}
+long long bart_launch_count(void) { return G.launches; }
+int bart_flush_l2(void) {
+  API_BEGIN ensure_device();
+  const size_t n = (size_t)(256u << 20) / 8;            // 256 MB > 126 MB L2
+  G.d_flush.ensure(n);
+  launch_fill(G.d_flush.p, n, 0.0, G.stream);
+  check_launch("l2_flush");
+  return 0; API_END_INT
+}
+
+// ---- introspection ----
+void bart_debug_keep(int on) { G.keep = on != 0; }
+
+long long bart_debug_get(const char *name, int model, double *out, long long capacity) {
+  API_BEGIN
+  if (!G.init) fail("not initialised");
+  DevConfig &c = G.dc;
+  const int nl = c.nlayer, nw = c.nwave;
+  const std::string n = name;
+  if (model < 0 || model >= G.last_batch) fail("bart_debug_get: model %d outside the last batch (%d)", model, G.last_batch);
+  finish_stream();
+  auto field = [&](int f, bool to_layer_order) -> long long {
+    if (capacity < nl) fail("bart_debug_get: capacity too small");
+    std::vector<double> tmp(nl);
+    CUDA_OK(cudaMemcpy(tmp.data(), G.d_tabs.p + (size_t)model * c.lay.stride() + (size_t)f * nl,
+                       nl * 8, cudaMemcpyDeviceToHost));
+    for (int d = 0; d < nl; d++) out[to_layer_order ? nl - 1 - d : d] = tmp[d];
+    return nl;
+  };
+  if (n == "radius") return field(c.lay.RAD(), true);
+  if (n == "temp") return field(c.lay.T(), true);
+  if (n == "bracket") return field(c.lay.IT(), true);
+  if (n == "scat") return field(c.lay.SCAT(), true);
+  if (n == "cloud") return field(c.lay.CLOUD(), true);
+  if (n == "simpson_a") return field(c.lay.SA(), false);
+  if (n == "simpson_b") return field(c.lay.SB(), false);
+  if (n == "simpson_c") return field(c.lay.SC(), false);
+  if (n == "trapezoid") return field(c.lay.TR(), false);
+  if (n == "table") {
+    const long long cnt = c.lay.nfields() * nl;
+    if (capacity < cnt) fail("bart_debug_get: capacity too small");
+    CUDA_OK(cudaMemcpy(out, G.d_tabs.p + (size_t)model * c.lay.stride(), cnt * 8, cudaMemcpyDeviceToHost));
+    return cnt;
+  }
+  if (n == "tau") {          // [nwave][nlayer(depth)], like the reference's tau->t
+    if (!G.keep || !G.d_tau.p) fail("bart_debug_get(tau): call bart_debug_keep(1) before the batch");
+    const long long cnt = (long long)nw * nl;
+    if (capacity < cnt) fail("bart_debug_get: capacity too small");
+    CUDA_OK(cudaMemcpy(out, G.d_tau.p + (size_t)model * cnt, cnt * 8, cudaMemcpyDeviceToHost));
+    return cnt;
+  }
+  if (n == "last") {
+    if (!G.keep || !G.d_last.p) fail("bart_debug_get(last): call bart_debug_keep(1) before the batch");
+    if (capacity < nw) fail("bart_debug_get: capacity too small");
+    std::vector<int> tmp(nw);
+    CUDA_OK(cudaMemcpy(tmp.data(), G.d_last.p + (size_t)model * nw, nw * 4, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < nw; i++) out[i] = tmp[i];
+    return nw;
+  }
+  if (n == "ext") {          // after bart_extinction_batch: [nlayer][nwave]
+    const long long cnt = (long long)nw * nl;
+    if (!G.d_ext.p || capacity < cnt) fail("bart_debug_get(ext): no extinction batch or capacity too small");
+    CUDA_OK(cudaMemcpy(out, G.d_ext.p + (size_t)model * cnt, cnt * 8, cudaMemcpyDeviceToHost));
+    return cnt;
+  }
+  if (n == "status") {
+    if (capacity < 1) fail("bart_debug_get: capacity too small");
+    int s = 0;
+    CUDA_OK(cudaMemcpy(&s, G.d_status.p + model, 4, cudaMemcpyDeviceToHost));
+    out[0] = s;
+    return 1;
+  }
+  fail("bart_debug_get: unknown name '%s'", name);
+  return -1;
+  API_END_INT
+}
+
+// ---- multi-GPU exchange: NCCL through dlopen (no link-time dependency) ----
+typedef struct { char internal[128]; } nccl_uid_t;
+typedef int (*fn_getuid)(nccl_uid_t *);
+typedef int (*fn_initrank)(void **, int, nccl_uid_t, int);
+typedef int (*fn_allgather)(const void *, void *, size_t, int, void *, cudaStream_t);
+typedef int (*fn_destroy)(void *);
+typedef const char *(*fn_errstr)(int);
+
+static void *nccl_sym(const char *name) {
+  if (!G.nccl_lib) {
+    const char *cands[] = {"libnccl.so.2", "libnccl.so", nullptr};
+    for (int i = 0; cands[i] && !G.nccl_lib; i++) G.nccl_lib = dlopen(cands[i], RTLD_NOW | RTLD_GLOBAL);
+    if (!G.nccl_lib) fail("cannot load libnccl.so.2: %s", dlerror());
+  }
+  void *s = dlsym(G.nccl_lib, name);
+  if (!s) fail("libnccl: symbol %s not found", name);
+  return s;
+}
+
+int bart_comm_unique_id(char *id128) {
+  API_BEGIN
+  nccl_uid_t id;
+  int rc = ((fn_getuid)nccl_sym("ncclGetUniqueId"))(&id);
+  if (rc != 0) fail("ncclGetUniqueId failed: %s", ((fn_errstr)nccl_sym("ncclGetErrorString"))(rc));
+  memcpy(id128, id.internal, 128);
+  return 0;
+  API_END_INT
+}
+
+int bart_comm_init(int rank, int world, const char *id128) {
+  API_BEGIN
+  ensure_device();
+  nccl_uid_t id;
+  memcpy(id.internal, id128, 128);
+  int rc = ((fn_initrank)nccl_sym("ncclCommInitRank"))(&G.nccl_comm, world, id, rank);
+  if (rc != 0) fail("ncclCommInitRank failed: %s", ((fn_errstr)nccl_sym("ncclGetErrorString"))(rc));
+  G.rank = rank; G.world = world;
+  return 0;
+  API_END_INT
+}
+
+int bart_comm_allgather(const double *d_send, double *d_recv, long long count_per_rank) {
+  API_BEGIN
+  if (!G.nccl_comm) fail("bart_comm_init has not been called");
+  const int ncclFloat64 = 8;
+  int rc = ((fn_allgather)nccl_sym("ncclAllGather"))(d_send, d_recv, (size_t)count_per_rank, ncclFloat64,
+                                                      G.nccl_comm, G.stream);
+  if (rc != 0) fail("ncclAllGather failed: %s", ((fn_errstr)nccl_sym("ncclGetErrorString"))(rc));
+  G.launches++;
+  finish_stream();
+  return 0;
+  API_END_INT
+}
+
+int bart_comm_finalize(void) {
+  API_BEGIN
+  if (G.nccl_comm) { ((fn_destroy)nccl_sym("ncclCommDestroy"))(G.nccl_comm); G.nccl_comm = nullptr; }
+  return 0;
+  API_END_INT
+}
+
+// ---- CLI support: one model from the atmosphere file's own profiles (transit.c:230-242 main) ----
+int bart_cli_run(void) {
+  API_BEGIN
+  if (!G.init) fail("Transit init not run, please initialize transit.");
+  if (G.opt.justOpacity) return 0;
+  const int nl = G.atm.nlayer(), ns = G.atm.nspec(), nw = (int)G.wn.size();
+  std::vector<double> in((size_t)(ns + 1) * nl), out(nw);
+  for (int i = 0; i < nl; i++) in[i] = G.atm.temp[i];
+  for (int j = 0; j < ns; j++)
+    for (int i = 0; i < nl; i++) in[(size_t)(j + 1) * nl + i] = G.atm.q[(size_t)j * nl + i];
+  run_transit(in.data(), (int)in.size(), out.data(), nw);
+  if (bart_error_pending()) return -1;
+  // printflux / printmod text format: eclipse.c:355-380, slantpath.c:510-555
+  FILE *f = stdout;
+  const std::string &name = G.opt.outspec;
+  if (!name.empty() && name != "-") {
+    f = fopen(name.c_str(), "w");
+    if (!f) fail("Cannot open output file '%s'", name.c_str());
+  }
+  const double wfct = 1.0;                       // wns.fct is always 1 (makesample.c:367)
+  if (G.dc.eclipse) {
+    fprintf(f, "#wvl [um]%*sFlux [erg/s/cm]\n", 6, " ");
+    for (int w = 0; w < nw; w++) fprintf(f, "%-15.10g%-18.9g\n", 1e4 / (G.wn[w] / wfct), out[w]);
+  } else {
+    fprintf(f, "#wvl [um]        modulation\n");
+    for (int w = 0; w < nw; w++) fprintf(f, "%-17.9g%-18.9g\n", 1e4 / (G.wn[w] / wfct), out[w]);
+  }
+  if (f != stdout) fclose(f);
+  return 0;
+  API_END_INT
+}
+
+// ---- builder entry points (builder.cu) ----
+int bart_build_opacity_slice(int t_begin, int t_end, double *host_out) {
+  API_BEGIN
+  if (!G.init && !G.builder) fail("transit_init has not been called");
+  ensure_device();
+  builder_slice(G.builder, G.opt, G.atm, G.mol, G.tli, G.wn, G.stream, t_begin, t_end, host_out);
+  return 0;
+  API_END_INT
+}
+
+long long bart_builder_stats(long long *nlines, long long *ngroups, long long *neval) {
+  if (!G.builder) return -1;
+  return builder_stats(G.builder, nlines, ngroups, neval);
+}
+
+long long bart_line_bins(long long *iown_out, long long capacity) {
+  API_BEGIN
+  if (!G.builder) fail("the opacity-grid builder has not run in this process");
+  return builder_line_bins(G.builder, iown_out, capacity);
+  API_END_INT
+}
+
+int bart_voigt_profile(int idop, int ilor, float *out, long long capacity, long long *halfsize) {
+  API_BEGIN
+  if (!G.builder) fail("the opacity-grid builder has not run in this process");
+  return builder_profile(G.builder, idop, ilor, out, capacity, halfsize);
+  API_END_INT
+}
+
+}  // extern "C"

@@ -1,0 +1,169 @@
+/* bart_b200.h -- C ABI of libbart_b200.so: the B200-native `transit` forward model.
+ *
+ * Plain C, pointers + sizes only.  Part 1 is the reference's own boundary, same names,
+ * argument meaning and units, so the existing SWIG/ctypes/cgo binding of BART's `transit`
+ * binds this library unchanged.  Part 2 is additive (batched evaluation, band integration,
+ * multi-GPU exchange, timing, introspection); nothing in part 1 depends on it being called.
+ *
+ * Reference citations are into exosports/BART, modules/transit/transit/.
+ * One instance per process (the reference keeps one global `struct transit`, src/transit.c:7-12).
+ * All arithmetic is fp64.  There is no CPU fallback: every entry point that computes needs a
+ * CUDA device of compute capability 10.0 and fails loudly without one.
+ */
+#ifndef BART_B200_H
+#define BART_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ===================================================================================== */
+/* Part 1 -- the reference boundary (src/transit.c:14-22, include/transit.h:44-49,
+ *           SWIG surface src/transit.i:12-31)                                            */
+
+/* replaces transit_init (src/transit.c:25-74): parse `argv` (["transit","-c",cfgfile,...],
+ * option table of src/argum.c:112-320, `key value` file grammar of pu/src/procopt.c:649-704),
+ * read atmosphere / molecules / TLI header / CIA files, read -- or, when the named opacity
+ * file does not exist, BUILD (Voigt line-by-line, src/opacity.c:218-427) and write -- the
+ * opacity grid, and make everything resident in HBM.                                     */
+void transit_init(int argc, char **argv);
+
+/* replaces get_no_samples (src/transit.c:77-80): number of spectrum wavenumbers.         */
+int get_no_samples(void);
+
+/* replaces get_waveno_arr (src/transit.c:82-95): wavenumber grid in cm-1; -1 fill when not
+ * initialised, like the reference.                                                       */
+void get_waveno_arr(double *waveno_arr, int waveno);
+
+/* replaces set_radius (src/transit.c:98-100): reference radius r0, units of the atmosphere
+ * file's radius factor (km for TEA files); applies to subsequent models.                 */
+void set_radius(double refradius);
+
+/* replaces set_cloudtop (src/transit.c:103-109): opaque cloud deck, log10(bar).          */
+void set_cloudtop(double cloudtop);
+
+/* replaces set_scattering (src/transit.c:112-115): flag 1 = Lecavelier (logext), 2 = polar. */
+void set_scattering(int flag, double scattering);
+
+/* replaces run_transit (src/transit.c:118-122): one forward model.
+ * re_input[(1+nspecies)*nlayers] = [T(layers) | q_species0(layers) | ...], layers bottom ->
+ * top in atmosphere-file order (src/readatm.c:735-744); transit_out[nwave] receives the
+ * emergent flux (eclipse, erg s-1 cm-1) or the modulation (transit, (Rp/Rs)^2).          */
+void run_transit(double *re_input, int transint, double *transit_out, int transit_out_size);
+
+/* replaces free_memory (src/transit.c:216-228).                                          */
+void free_memory(void);
+
+/* ===================================================================================== */
+/* Part 2 -- additive entry points                                                         */
+
+#define BART_OK 0
+
+/* Error handling.  The reference prints and exit()s on any failure (include/transit.h:91-98).
+ * mode 0 (default) reproduces that for the part-1 functions; mode 1 makes every function
+ * return, leaving a message for bart_last_error (the Python module uses mode 1).         */
+void        bart_set_error_mode(int mode);
+const char *bart_last_error(void);
+int         bart_error_pending(void);
+void        bart_clear_error(void);
+
+/* Device selection; call before transit_init (default: $BART_DEVICE, else $LOCAL_RANK, else 0). */
+int  bart_set_device(int ordinal);
+int  bart_get_device(void);
+int  bart_device_info(char *name, int name_len, int *sm_count, int *cc_major, int *cc_minor,
+                      long long *l2_bytes, long long *hbm_bytes);
+
+/* Shapes after transit_init.                                                              */
+int  bart_nlayers(void);
+int  bart_nspecies(void);
+int  bart_ngridmol(void);
+int  bart_ngridtemp(void);
+int  bart_is_eclipse(void);
+long long bart_grid_bytes(void);
+
+/* Batched forward model.  profiles[nmodels][n_in] (same per-model layout as run_transit),
+ * spectra[nmodels][n_out].  Host pointers; the call copies in, computes and copies out.
+ * status[nmodels] (may be NULL) receives 0 or a rejection code per model (BART_REJ_*)
+ * instead of the reference's exit(): the spectrum of a rejected model is filled with -1.   */
+int  bart_run_batch(const double *profiles, int nmodels, int n_in, double *spectra, int n_out,
+                    int *status);
+#define BART_REJ_TGRID   1   /* a layer temperature outside the opacity-grid range          */
+#define BART_REJ_TCIA    2   /* outside a CIA table's range (src/crosssec.c:293-309)        */
+#define BART_REJ_SUMQ    4   /* sum of abundances > 1.001 (src/readatm.c:152-156)           */
+#define BART_REJ_FEWPTS  8   /* transit: fewer than 3 points for the modulation integral    */
+
+/* Per-model knobs for the batched calls (the reference's setters are per-process state that
+ * BARTfunc.py sets before each run_transit, code/BARTfunc.py:350-360).  Any pointer may be
+ * NULL to keep the process-wide value; arrays have nmodels entries.                       */
+int  bart_set_batch_knobs(int nmodels, const double *refradius, const double *cloudtop,
+                          const int *scat_flag, const double *scat_logext);
+
+/* Same, with device-resident buffers (for callers that keep proposals on the GPU).        */
+int  bart_run_batch_device(const double *d_profiles, int nmodels, int n_in, double *d_spectra,
+                           int n_out, int *d_status);
+
+/* Stage (c): band integration (code/wine.py:127-199, code/BARTfunc.py:386-396).
+ * nfilters filters; filter f covers spectrum samples [start[f], start[f]+count[f]);
+ * weight[] and star[] are the concatenated per-sample normalised filter transmission and
+ * stellar flux (star may be NULL: no division, `transit`/`direct` modes); rprs = Rp/Rs.    */
+int  bart_set_filters(int nfilters, const int *start, const int *count, const double *weight,
+                      const double *star, double rprs);
+int  bart_band_integrate(const double *spectra, int nmodels, int nwave, double *bandflux);
+/* profiles -> band fluxes in one call; spectra never leave the device.
+ * bandflux[nmodels][nfilters]; rejected models get -1 in every band (BARTfunc.py:327-330).  */
+int  bart_bandflux_batch(const double *profiles, int nmodels, int n_in, double *bandflux,
+                         int *status);
+int  bart_bandflux_batch_device(const double *d_profiles, int nmodels, int n_in,
+                                double *d_bandflux, int *d_status);
+
+/* Stand-alone opacity lookup (src/extinction.c:534-581 + the sum of src/tau.c:231-232):
+ * materialises ext[nmodels][nlayer][nwave] on the device (debug/roofline use).            */
+int  bart_extinction_batch(const double *profiles, int nmodels, int n_in, double *ext_out,
+                           int what /*0 molecular, 1 total incl. CIA/scattering/cloud*/);
+
+/* Device memory helpers for callers without a CUDA runtime of their own.                  */
+void *bart_dev_alloc(long long bytes);
+void  bart_dev_free(void *p);
+void *bart_host_alloc_pinned(long long bytes);
+void  bart_host_free_pinned(void *p);
+int   bart_memcpy_h2d(void *dst, const void *src, long long bytes);
+int   bart_memcpy_d2h(void *dst, const void *src, long long bytes);
+int   bart_sync(void);
+
+/* Timing on the library's own stream (CUDA events).  bart_timer_begin/end bracket a region
+ * and return milliseconds; with profiling on, every kernel launch is bracketed too and
+ * bart_kernel_stats reports, per kernel name, launches and total milliseconds.             */
+int    bart_timer_begin(void);
+double bart_timer_end(void);
+void   bart_profile_enable(int on);
+void   bart_profile_reset(void);
+int    bart_kernel_stats(int index, char *name, int name_len, long long *launches, double *ms);
+long long bart_launch_count(void);
+int    bart_flush_l2(void);
+
+/* Introspection for parity tests: copy an intermediate of the LAST batched call to host.
+ * names: "radius","density","temp","tau","last","cia","ext","simpson"...; returns the number
+ * of doubles written or <0.                                                                */
+long long bart_debug_get(const char *name, int model, double *out, long long capacity);
+void      bart_debug_keep(int on);   /* keep tau/last columns of the next calls (costs HBM) */
+
+/* Multi-GPU: one process per GPU; chains are partitioned by rank and each generation ends with
+ * one all-gather of [nlocal][width] doubles (replaces the MPI Scatter/Gather of
+ * modules/MCcubed/MCcubed/mc/mcmc.py:583-585 / code/BARTfunc.py:312,399).                   */
+int  bart_comm_unique_id(char *id128);
+int  bart_comm_init(int rank, int world, const char *id128);
+int  bart_comm_allgather(const double *d_send, double *d_recv, long long count_per_rank);
+int  bart_comm_finalize(void);
+
+/* Opacity-grid builder (--justOpacity; src/opacity.c:218-427, src/extinction.c:281-529,
+ * pu/src/voigt.c).  transit_init builds the grid itself when the file is missing; these expose
+ * the pieces: t_begin/t_end select a slice of the temperature axis (T-sharded multi-GPU build). */
+int  bart_build_opacity_slice(int t_begin, int t_end, double *host_out /*[layer][t][mol][wn]*/);
+long long bart_builder_stats(long long *nlines, long long *ngroups, long long *neval);
+long long bart_line_bins(long long *iown_out, long long capacity);  /* bit-exact bin trace   */
+int  bart_voigt_profile(int idop, int ilor, float *out, long long capacity, long long *halfsize);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BART_B200_H */

@@ -14,6 +14,8 @@ import struct
 import subprocess
 import numpy as np
 
+_trapz = getattr(np, "trapezoid", None) or np.trapz
+
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIBPATH = os.path.join(HERE, "liboracle.so")
 REFLIB = os.path.join(HERE, "_ref", "libtransit_ref.so")
@@ -308,12 +310,12 @@ def resample(specwn, filterwn, filtertr, starwn, starfl):
     idx = np.where((specwn < filterwn[-1]) & (filterwn[0] < specwn))[0]
     ifilter = np.interp(specwn[idx], filterwn, filtertr)
     istarfl = np.interp(specwn[idx], starwn, starfl)
-    nifilter = ifilter / np.trapz(ifilter, specwn[idx])
+    nifilter = ifilter / _trapz(ifilter, specwn[idx])
     return nifilter, istarfl, idx
 
 
 def bandintegrate(spectrum, specwn, nifilter, idx):
-    return np.trapz(spectrum * nifilter, specwn[idx])
+    return _trapz(spectrum * nifilter, specwn[idx])
 
 
 def bandflux(spectrum, specwn, filters, star=None, rprs=None):

@@ -1,0 +1,51 @@
+"""Named parity configurations shared by tests/ and tests/golden/make_golden.py.
+
+Every case is regenerated bit-identically from its seed by bart_b200.synth (the golden files
+carry sha256 digests of the generated opacity grid and model batch to prove it)."""
+import hashlib
+import os
+import sys
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from bart_b200 import synth  # noqa: E402
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+# name -> (make_case kwargs, n_models, model seed, setters)
+CASES = {
+    "tiny_eclipse": (dict(shape="tiny", solution="eclipse", seed=12345), 3, 99, {}),
+    "tiny_transit": (dict(shape="tiny", solution="transit", seed=12345, refradius_km=95000.0),
+                     3, 98, {"radius": 94000.0}),
+    "small4_eclipse_cloud": (dict(shape="small4", solution="eclipse", seed=777), 3, 97,
+                             {"cloudtop": -1.0, "scattering": 1.5}),
+    "small4_transit_cloud": (dict(shape="small4", solution="transit", seed=778,
+                                  refradius_km=95000.0), 2, 96,
+                             {"radius": 94500.0, "cloudtop": -2.0, "scattering": 0.5}),
+    "demo_eclipse": (dict(shape="demo", solution="eclipse", seed=12345), 2, 95, {}),
+    "demo_transit": (dict(shape="demo", solution="transit", seed=12345, refradius_km=95000.0),
+                     2, 94, {"radius": 94000.0}),
+    "tiny_eclipse_3ang": (dict(shape="tiny", solution="eclipse", seed=4242,
+                               extra_cfg=["raygrid 0 30 70"]), 2, 93, {}),
+    "tiny_eclipse_t20": (dict(shape="tiny", solution="eclipse", seed=4243,
+                              overrides={"toomuch": 20.0}, nlayer=60), 2, 92, {}),
+}
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def build_case(name, workdir):
+    kw, nm, mseed, setters = CASES[name]
+    case = synth.make_case(os.path.join(workdir, name), **kw)
+    molfit = ("CH4",) if len(case["shape"]["mols"]) == 1 else ("H2O", "CO2", "CO", "CH4")
+    models = synth.make_models(case, nm, seed=mseed, molfit=molfit)
+    return case, models, setters
+
+
+def golden_path(name):
+    return os.path.join(GOLDEN_DIR, name + ".npz")

@@ -1,0 +1,149 @@
+// tests/cpu_emu/emu.cpp -- TEST-ONLY host emulation of the CUDA kernels' thread loops.
+//
+// The arithmetic of the forward model lives in bart_b200/csrc/column_math.cuh as inline
+// host+device functions; the CUDA kernels are thin wrappers that map (model, wavenumber) to
+// threads.  This file maps the same functions over plain loops on the host so that the math
+// can be compared with the oracle in the CPU-only container (pytest -m "not gpu").  It is NOT
+// part of the product: libbart_b200.so contains no host execution path, nothing under
+// bart_b200/ links or loads this file, and the GPU parity tests never use it.
+#include "../../bart_b200/csrc/host.hpp"
+#include "../../bart_b200/csrc/column_math.cuh"
+#include <cstdarg>
+#include <cstring>
+#include <cstdlib>
+#include <stdexcept>
+#include <cmath>
+
+namespace bart {
+int g_verb = 0;
+static char g_msg[2048];
+void fail(const char *fmt, ...) {
+  va_list ap; va_start(ap, fmt); vsnprintf(g_msg, sizeof(g_msg), fmt, ap); va_end(ap);
+  throw std::runtime_error(g_msg);
+}
+void warn(int, const char *, ...) {}
+}  // namespace bart
+
+using namespace bart;
+
+struct Emu {
+  Options opt; Atmosphere atm; Molecules mol; Tli tli; OpacityGrid og;
+  std::vector<CiaTable> cia;
+  std::vector<double> wn, grid, P[kMaxCia], Q[kMaxCia];
+  DevConfig c{};
+  Knobs k{};
+};
+static Emu *E = nullptr;
+
+extern "C" {
+
+const char *emu_error() { return g_msg; }
+
+int emu_init(const char *cfg) {
+  try {
+    delete E; E = new Emu();
+    const char *argv[] = {"transit", "-c", cfg, nullptr};
+    parse_options(3, (char **)argv, E->opt);
+    Options &o = E->opt;
+    double lo = o.wnlow > 0 ? o.wnlow * o.wnfct : 1.0 / (o.wlhigh * o.wlfct);
+    double hi = o.wnhigh > 0 ? o.wnhigh * o.wnfct : 1.0 / (o.wllow * o.wlfct);
+    E->wn = make_sampling(lo, hi, o.wndelt, 1);
+    read_atmosphere(o.atm, E->atm);
+    read_molecules(o.molfile, E->atm, E->mol);
+    read_tli_header(o.linedb, E->tli);
+    if (!read_opacity_header(o.opacityfile, E->og)) fail("no opacity file");
+    OpacityGrid &g = E->og;
+    size_t n = (size_t)g.nlayer * g.ntemp * g.nmol * g.nwave;
+    E->grid.resize(n);
+    FILE *f = fopen(o.opacityfile.c_str(), "rb");
+    fseek(f, g.data_offset, SEEK_SET);
+    if (fread(E->grid.data(), 8, n, f) != n) fail("short grid");
+    fclose(f);
+    DevConfig &c = E->c;
+    c.nlayer = E->atm.nlayer(); c.nspec = E->atm.nspec(); c.nwave = (int)E->wn.size();
+    c.ntemp = (int)g.ntemp; c.ngmol = (int)g.nmol;
+    c.eclipse = o.solution == "eclipse"; c.transparent = o.transparent;
+    c.grid = E->grid.data(); c.gtemp = g.temp.data(); c.wn = E->wn.data();
+    c.press = E->atm.press.data(); c.mass = E->mol.mass.data(); c.pol = E->mol.pol.data();
+    for (int m = 0; m < c.ngmol; m++)
+      for (int j = 0; j < c.nspec; j++) if (E->mol.id[j] == g.molid[m]) c.gmol_spec[m] = j;
+    E->cia.resize(o.csfiles.size());
+    c.ncia = (int)o.csfiles.size();
+    for (int i = 0; i < c.ncia; i++) {
+      read_cia(o.csfiles[i], E->cia[i]);
+      fold_cia_table(E->cia[i], E->wn, E->P[i], E->Q[i]);
+      c.ciaP[i] = E->P[i].data(); c.ciaQ[i] = E->Q[i].data(); c.ciaT[i] = E->cia[i].temp.data();
+      c.cia_nt[i] = (int)E->cia[i].temp.size();
+      c.cia_nspec[i] = (int)E->cia[i].species.size();
+      for (size_t s = 0; s < E->cia[i].species.size(); s++)
+        for (int j = 0; j < c.nspec; j++) if (E->atm.species[j] == E->cia[i].species[s]) c.cia_spec[i][s] = j;
+    }
+    c.pfct = E->atm.pfct; c.rfct = E->atm.rfct; c.gsurf = o.gsurf; c.p0 = o.refpress; c.toomuch = o.toomuch;
+    std::vector<double> ang;
+    char *dup = strdup(o.raygrid.c_str());
+    for (char *t = strtok(dup, " \t"); t; t = strtok(nullptr, " \t")) ang.push_back(atof(t));
+    free(dup);
+    c.nang = (int)ang.size();
+    std::vector<double> area(c.nang + 1);
+    area[0] = 0.0; area[c.nang] = 90.0 * kDEG;
+    for (int a = 1; a < c.nang; a++) area[a] = (ang[a - 1] + ang[a]) * kDEG / 2.0;
+    for (int a = 0; a < c.nang; a++) {
+      c.inv_mu[a] = 1.0 / cos(ang[a] * kDEG);
+      c.wgt[a] = pow(sin(area[a + 1]), 2.0) - pow(sin(area[a]), 2.0);
+    }
+    double srad = o.starrad * kSUNRADIUS;
+    c.inv_srad2 = 1.0 / (srad * srad);
+    c.lay.nl = c.nlayer; c.lay.ngmol = c.ngmol; c.lay.ncia = c.ncia;
+    Knobs &k = E->k;
+    k = Knobs();
+    k.r0_all = o.refradius; k.cloud_flag_all = o.cloud_flag; k.cloudext_all = o.cloudext;
+    k.cloudtop_all = o.cloudtop; k.cloudbot_all = o.cloudbot;
+    k.scat_flag_all = o.scat_flag; k.scat_logext_all = o.scat_logext;
+    return 0;
+  } catch (std::exception &) { return -1; }
+}
+
+int emu_nwave() { return E ? E->c.nwave : 0; }
+int emu_nlayer() { return E ? E->c.nlayer : 0; }
+void emu_wn(double *out) { for (int i = 0; i < E->c.nwave; i++) out[i] = E->wn[i]; }
+void emu_set_radius(double r) { E->k.r0_all = r; }
+void emu_set_cloudtop(double t) { E->k.cloud_flag_all = 1; E->k.cloudext_all = 100; E->k.cloudtop_all = t; E->k.cloudbot_all = t + 10; }
+void emu_set_scattering(int f, double v) { E->k.scat_flag_all = f; E->k.scat_logext_all = v; }
+
+// one model; tau[nwave][nlayer], last[nwave], radius[nlayer] optional
+int emu_run(const double *in, double *spectrum, double *tau, int *last, double *radius,
+            double *ext_total) {
+  DevConfig &c = E->c;
+  const int nl = c.nlayer, ns = c.nspec, nw = c.nwave;
+  std::vector<double> rho((size_t)ns * nl), mu(nl), rad(nl), tab(c.lay.stride());
+  int status = 0;
+  for (int l = 0; l < nl; l++) status |= prep_layer(c, in, l, rho.data() + l, nl, &mu[l]);
+  KnobVals kv = knobs_for(E->k, 0);
+  hydrostatic_radii(c, kv.r0, in, mu.data(), rad.data());
+  for (int d = 0; d < nl; d++) status |= prep_table_row(c, kv, d, in, rho.data(), nl, rad.data(), tab.data());
+  if (radius) for (int l = 0; l < nl; l++) radius[l] = rad[l];
+  if (status) { for (int w = 0; w < nw; w++) spectrum[w] = -1; return status; }
+  std::vector<double> tk(nl), wts((size_t)nl * (nl + 1) / 2), er(nl);
+  if (!c.eclipse) for (int d = 0; d < nl; d++) transit_weight_row(c, tab.data(), d, &wts[(size_t)d * (d + 1) / 2]);
+  for (int w = 0; w < nw; w++) {
+    int lk = 0;
+    std::fill(tk.begin(), tk.end(), 0.0);
+    if (c.eclipse) {
+      switch (c.nang) {
+        case 5: spectrum[w] = eclipse_column<5, true>(c, tab.data(), w, tk.data(), &lk); break;
+        default: spectrum[w] = eclipse_column<0, true>(c, tab.data(), w, tk.data(), &lk);
+      }
+    } else {
+      spectrum[w] = transit_column<true>(c, tab.data(), wts.data(), w, er.data(), 1, tk.data(), &lk, &status);
+    }
+    if (tau) memcpy(tau + (size_t)w * nl, tk.data(), nl * 8);
+    if (last) last[w] = lk;
+    if (ext_total) {
+      const double wn = c.wn[w], wn4 = (wn * wn) * (wn * wn);
+      for (int d = 0; d < nl; d++) ext_total[(size_t)(nl - 1 - d) * nw + w] = cell_extinction(c, tab.data(), d, w, wn4, true);
+    }
+  }
+  return status;
+}
+
+}  // extern "C"

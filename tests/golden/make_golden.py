@@ -1,0 +1,53 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (oracle/_ref/libtransit_ref.so,
+compiled from /root/reference by oracle/Makefile) on the synthetic configurations of
+tests/cases.py.  Run in the build container (the reference sources do not exist on the GPU box):
+
+    python tests/golden/make_golden.py
+
+Each file stores the reference's spectra, last[] (index where tau exceeds toomuch), hydrostatic
+radii and a strided sample of tau, plus sha256 digests of the generated inputs."""
+import os
+import subprocess
+import sys
+import tempfile
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import cases  # noqa: E402
+
+
+def main():
+    only = sys.argv[1:]
+    with tempfile.TemporaryDirectory() as tmp:
+        for name in cases.CASES:
+            if only and name not in only:
+                continue
+            case, models, setters = cases.build_case(name, tmp)
+            mpath = os.path.join(case["workdir"], "models.npy")
+            opath = os.path.join(case["workdir"], "ref.npz")
+            np.save(mpath, models)
+            cmd = [sys.executable, os.path.join(ROOT, "oracle", "ref_driver.py"), case["cfg"], mpath,
+                   opath, "--inter"] + ["--%s=%r" % (k, v) for k, v in setters.items()]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                raise SystemExit("reference failed on %s:\n%s\n%s" % (name, r.stdout[-2000:], r.stderr[-2000:]))
+            d = np.load(opath)
+            nw = len(d["wn"])
+            wsel = np.unique(np.linspace(0, nw - 1, 16).astype(int))
+            np.savez_compressed(
+                cases.golden_path(name), wn=d["wn"], spectra=d["spectra"], last=d["last"],
+                radius=d["radius"], tau_sample=d["tau"][:, wsel, :], tau_wsel=wsel,
+                ext_sample=d["ext"][:, :, wsel], cia_sample=d["cia"][:, wsel, :],
+                grid_sha=cases.sha(case["grid"]), models_sha=cases.sha(models),
+                toomuch=d["toomuch"])
+            print("%-24s nwave %5d  models %d  last[min,max]=%d,%d  -> %s (%d bytes)" % (
+                name, nw, models.shape[0], d["last"].min(), d["last"].max(),
+                os.path.basename(cases.golden_path(name)), os.path.getsize(cases.golden_path(name))))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,45 @@
+"""CPU: the forward-model arithmetic shared with the CUDA kernels (bart_b200/csrc/column_math.cuh:
+prefix-scan optical depth, pre-folded CIA splines, chord weights, modulation scan) mapped over
+host loops by tests/cpu_emu and compared with the oracle and the reference's golden vectors.
+This exercises the host-side readers/config parser of the product as well.  The GPU parity tests
+(tests/test_gpu_parity.py) are the real gate; this catches math errors without a GPU."""
+import numpy as np
+import pytest
+
+import cases
+from emu import Emu
+from util import relerr, tau_relerr, apply_setters
+
+
+@pytest.mark.parametrize("name", list(cases.CASES))
+def test_column_math_vs_oracle_and_golden(name, built, get_case):
+    from oracle import oracle as orc
+    case, models, setters = get_case(name)
+    g = np.load(cases.golden_path(name))
+    E = Emu(case["cfg"])
+    O = orc.Oracle(case["cfg"])
+    apply_setters(E, setters)
+    apply_setters(O, setters)
+    assert np.array_equal(E.wn(), g["wn"])
+    for m in range(models.shape[0]):
+        e = E.run(models[m])
+        o = O.run(models[m], inter=True)
+        assert e["status"] == 0
+        assert relerr(e["radius"], o["radius"]) < 1e-13
+        assert relerr(e["ext"], o["ext"]) < 1e-13
+        assert np.array_equal(e["last"], g["last"][m]), "last[] differs from the reference"
+        assert tau_relerr(e["tau"], o["tau"], o["last"]) < 5e-9
+        assert relerr(e["spectrum"], o["spectrum"]) < 1e-9
+        assert relerr(e["spectrum"], g["spectra"][m]) < 1e-9
+
+
+def test_rejection_status(built, get_case):
+    case, models, _ = get_case("tiny_eclipse")
+    E = Emu(case["cfg"])
+    bad = models[0].copy()
+    bad[5] = 3500.0                      # above the opacity grid (3000 K)
+    assert E.run(bad)["status"] & 1
+    bad = models[0].copy()
+    nl = E.nlayer
+    bad[nl * 6: nl * 7] = 0.9            # H2 abundance -> sum > 1.001
+    assert E.run(bad)["status"] & 4
