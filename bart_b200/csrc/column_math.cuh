@@ -7,6 +7,7 @@
 #pragma once
 #include "device.cuh"
 #include <cmath>
+#include <cstring>
 
 namespace bart {
 
@@ -21,6 +22,92 @@ constexpr double cNAVO = 6.02214076e23;
 constexpr double cMICRON = 1e-4;
 
 enum { REJ_TGRID = 1, REJ_TCIA = 2, REJ_SUMQ = 4, REJ_FEWPTS = 8 };
+
+// ---------------------------------------------------------------------------------------
+// fp64 exp and reciprocal for the column kernels.  libdevice's exp() costs ~45 issue slots per
+// call on sm_100 (half of them integer moves that materialise the polynomial coefficients),
+// and the eclipse column needs six per (layer, wavenumber) cell.  This version keeps the
+// coefficients as immediate/constant-bank operands of the FMAs, uses a Cody-Waite reduction and
+// builds the 2^n scaling in the exponent field.
+BART_HD double bits_to_double(long long b) {
+#ifdef __CUDA_ARCH__
+  return __longlong_as_double(b);
+#else
+  double d; memcpy(&d, &b, 8); return d;
+#endif
+}
+BART_HD long long double_to_bits(double d) {
+#ifdef __CUDA_ARCH__
+  return __double_as_longlong(d);
+#else
+  long long b; memcpy(&b, &d, 8); return b;
+#endif
+}
+
+// 16-byte pair load from a table record (records and pair offsets are 16-byte aligned)
+struct alignas(16) D2 { double x, y; };
+BART_HD D2 ld2(const double *p) { return *reinterpret_cast<const D2 *>(p); }
+
+// Table-driven variant used by the column kernels: exp(x) = 2^n * 2^(j/16) * e^r with
+// m = round(16 x / ln2) = 16 n + j and |r| <= ln2/32, so a degree-6 polynomial suffices
+// (truncation 4e-16) -- 11 fp64 instructions instead of 19.  `tab16` holds 2^(j/16), j = 0..15,
+// in shared memory: 128 bytes = one full bank row, so divergent lanes never conflict.
+// GUARD_LO: x may be below -708 (result 0); GUARD_HI: x may exceed 709 (result saturates).  The
+// guards are selects on the result (cheaper than clamping the argument); out-of-range arguments
+// only ever produce a discarded product.
+constexpr int kExpTabSize = 16;
+BART_HD void fill_exp_table(double *tab16) {
+  // 2^(j/16) correctly rounded
+  const double v[kExpTabSize] = {
+      1.0, 1.0442737824274138403, 1.0905077326652576592, 1.1387886347566916537,
+      1.1892071150027210667, 1.2418578120734840486, 1.2968395546510096659, 1.3542555469368927283,
+      1.4142135623730950488, 1.4768261459394993114, 1.5422108254079408236, 1.6104903319492543082,
+      1.6817928305074290861, 1.7562521603732994831, 1.8340080864093424635, 1.9152065613971472939};
+  for (int j = 0; j < kExpTabSize; j++) tab16[j] = v[j];
+}
+
+template <bool GUARD_LO, bool GUARD_HI>
+BART_HD double fast_exp_t(double x, const double *tab16) {
+  const double MAGIC = 6755399441055744.0;                        // 1.5 * 2^52
+  const double t = fma(x, 23.083120654223414518, MAGIC);          // low word = round(16 x / ln2)
+  const double kf = t - MAGIC;
+  double r = fma(kf, -4.33216987730702385306e-02, x);             // (ln2 high part) / 16, exact product
+  r = fma(kf, -1.19263433079411731251e-11, r);                    // (ln2 low part) / 16
+  double p = 1.38888888888888888889e-03;                          // 1/6!
+  p = fma(p, r, 8.33333333333333333333e-03);
+  p = fma(p, r, 4.16666666666666666667e-02);
+  p = fma(p, r, 1.66666666666666666667e-01);
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  const int m = (int)double_to_bits(t);                           // low word of t
+  const long long sc = double_to_bits(tab16[m & (kExpTabSize - 1)]) + ((long long)(m >> 4) << 52);
+  double res = p * bits_to_double(sc);
+  if (GUARD_LO) res = x < -708.0 ? 0.0 : res;
+  if (GUARD_HI) res = x > 709.0 ? 1.0e308 : res;
+  return res;
+}
+BART_HD double fast_exp(double x, const double *t) { return fast_exp_t<true, true>(x, t); }
+BART_HD double fast_exp_neg(double x, const double *t) { return fast_exp_t<true, false>(x, t); }  // x <= 0
+BART_HD double fast_exp_pos(double x, const double *t) { return fast_exp_t<false, true>(x, t); }  // x >= 0
+
+// 1/d for finite d > 0: hardware seed (>= 20 bits) + three Newton steps (full fp64 precision); the compiler's IEEE divide
+// is ~3x the issue slots because of its special-case branches.
+BART_HD double fast_rcp(double d) {
+#ifdef __CUDA_ARCH__
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  double e = fma(-d, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-d, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-d, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+#else
+  return 1.0 / d;
+#endif
+}
 
 struct KnobVals {
   double r0;
@@ -121,27 +208,30 @@ BART_HD int bracket(const double *x, int n, double v) {
   return lo;
 }
 
-// atm_prep stage 3, one depth d (0 = top): every per-layer coefficient the column kernels need.
-// temp/radius are indexed by layer (bottom -> top); rho[j*rho_stride + layer].
+// atm_prep stage 3, one depth d (0 = top): every per-layer coefficient the column kernels need,
+// written as one record (layout: TabLayout).  temp/radius are indexed by layer (bottom -> top);
+// rho[j*rho_stride + layer].
 BART_HD int prep_table_row(const DevConfig &c, const KnobVals &kv, int d, const double *temp,
                            const double *rho, int rho_stride, const double *radius, double *tab) {
   const TabLayout &L = c.lay;
   const int nl = c.nlayer;
   const int l = nl - 1 - d;
   const double T = temp[l];
+  double *row = tab + (size_t)d * L.nf();
   int status = 0;
-  tab[L.T() * nl + d] = T;
-  tab[L.RAD() * nl + d] = radius[l];
+  row[L.T] = T;
+  row[L.INVT] = 1.0 / T;
+  row[L.RAD] = radius[l];
 
   // opacity-grid bracket and folded weights (interpolmolext, extinction.c:534-581)
   if (T < c.gtemp[0] || T > c.gtemp[c.ntemp - 1]) status |= REJ_TGRID;
   const int it = bracket(c.gtemp, c.ntemp, T);
   const double t0 = c.gtemp[it], t1 = c.gtemp[it + 1];
-  tab[L.IT() * nl + d] = (double)it;
+  row[L.GOFF] = bits_to_double((((long long)l * c.ntemp + it) * c.ngmol) * (long long)c.nwave);
   for (int m = 0; m < c.ngmol; m++) {
     const double r = rho[(size_t)c.gmol_spec[m] * rho_stride + l];
-    tab[L.W0(m) * nl + d] = r * (t1 - T) / (t1 - t0);
-    tab[L.W1(m) * nl + d] = r * (T - t0) / (t1 - t0);
+    row[L.W + 2 * m] = r * (t1 - T) / (t1 - t0);
+    row[L.W + 2 * m + 1] = r * (T - t0) / (t1 - t0);
   }
 
   // CIA: cubic-spline-in-T coefficients (splinterp_pt, spline.c:131-183) applied to the
@@ -166,11 +256,13 @@ BART_HD int prep_table_row(const DevConfig &c, const KnobVals &kv, int d, const 
       cz0 = dx * (-h / 3.0 + dx * (0.5 - dx / (6.0 * h)));
       cz1 = dx * (-h / 6.0 + dx * dx / (6.0 * h));
     }
-    tab[L.CIAK(f) * nl + d] = (double)k;
-    tab[L.CIAC(f, 0) * nl + d] = cy0 * dens;
-    tab[L.CIAC(f, 1) * nl + d] = cy1 * dens;
-    tab[L.CIAC(f, 2) * nl + d] = cz0 * dens;
-    tab[L.CIAC(f, 3) * nl + d] = cz1 * dens;
+    double *cr = row + L.cia(f);
+    cr[0] = bits_to_double((long long)k * c.nwave);
+    cr[1] = (double)k;
+    cr[2] = cy0 * dens;
+    cr[3] = cy1 * dens;
+    cr[4] = cz0 * dens;
+    cr[5] = cz1 * dens;
   }
 
   // scattering (computeextscat, extinction.c:586-624): coefficient of wn^4
@@ -183,7 +275,7 @@ BART_HD int prep_table_row(const DevConfig &c, const KnobVals &kv, int d, const 
       sc += cPI * 8e-32 / 3.0 * (c.pol[j] * c.pol[j]) * k4 * rho[(size_t)j * rho_stride + l] /
             c.mass[j] * cNAVO;
   }
-  tab[L.SCAT() * nl + d] = sc;
+  row[L.SCAT] = sc;
 
   // gray cloud deck (computeextcloud flag 1, extinction.c:629-693)
   double cl = 0.0;
@@ -191,7 +283,7 @@ BART_HD int prep_table_row(const DevConfig &c, const KnobVals &kv, int d, const 
     const double top = pow(10.0, kv.cloudtop), bot = pow(10.0, kv.cloudbot);
     if (c.press[l] >= top && c.press[l] < bot) cl = kv.cloudext;
   }
-  tab[L.CLOUD() * nl + d] = cl;
+  row[L.CLOUD] = cl;
 
   // Simpson / trapezoid coefficients on the radius spacing (geth + simpson, numerical.c:390-525),
   // top-aligned panels: the panel ending at even depth d spans depths d-2, d-1, d.
@@ -208,41 +300,55 @@ BART_HD int prep_table_row(const DevConfig &c, const KnobVals &kv, int d, const 
       scf = (2.0 - 1.0 / hratio) * s6;
     }
   }
-  tab[L.SA() * nl + d] = sa;
-  tab[L.SB() * nl + d] = sb;
-  tab[L.SC() * nl + d] = scf;
-  tab[L.TR() * nl + d] = tr;
+  row[L.SA] = sa;
+  row[L.SB] = sb;
+  row[L.SC] = scf;
+  row[L.TR] = tr;
   return status;
 }
 
 // ---------------------------------------------------------------------------------------
 // Total extinction of one (depth, wavenumber) cell: opacity-grid lookup with temperature
 // interpolation and abundance scaling (extinction.c:534-581), + scattering + cloud + CIA in the
-// reference's summation order (tau.c:231-232).  `mol_only` returns the molecular part alone.
-BART_HD double cell_extinction(const DevConfig &c, const double *tab, int d, int w, double wn4,
+// reference's summation order (tau.c:231-232).  `row` is the depth's table record.  NMOL / NCIA
+// are compile-time counts (0 = take them from the configuration at run time).
+template <int NMOL, int NCIA>
+BART_HD double cell_extinction(const DevConfig &c, const double *row, int w, double wn4,
                                bool mol_only) {
-  const TabLayout &L = c.lay;
-  const int nl = c.nlayer;
+  typedef TabLayout L;
+  const int ngmol = NMOL > 0 ? NMOL : c.ngmol;
+  const int ncia = NCIA >= 0 ? NCIA : c.ncia;
   const size_t nw = (size_t)c.nwave;
-  const int l = nl - 1 - d;
-  const int it = (int)tab[L.IT() * nl + d];
-  const double *lo = c.grid + (((size_t)l * c.ntemp + it) * c.ngmol) * nw + w;
-  const double *hi = lo + (size_t)c.ngmol * nw;
-  double e = 0.0;
-#pragma unroll 4
-  for (int m = 0; m < c.ngmol; m++)
-    e += tab[L.W0(m) * nl + d] * lo[m * nw] + tab[L.W1(m) * nl + d] * hi[m * nw];
+  const D2 head = ld2(row + L::INVT);                        // (1/T, grid offset)
+  const double *lo = c.grid + double_to_bits(head.y) + w;
+  const double *hi = lo + (size_t)ngmol * nw;
+  double e;
+  {
+    const D2 wt = ld2(row + L::W);
+    e = wt.x * lo[0] + wt.y * hi[0];
+  }
+#pragma unroll
+  for (int m = 1; m < (NMOL > 0 ? NMOL : kMaxGridMol); m++)
+    if (m < ngmol) {
+      const D2 wt = ld2(row + L::W + 2 * m);
+      e += wt.x * lo[m * nw] + wt.y * hi[m * nw];
+    }
   if (mol_only) return e;
   double ecs = 0.0;
-  for (int f = 0; f < c.ncia; f++) {
-    const int k = (int)tab[L.CIAK(f) * nl + d];
-    const double *P = c.ciaP[f] + (size_t)k * nw + w;
-    const double *Q = c.ciaQ[f] + (size_t)k * nw + w;
-    const double v = tab[L.CIAC(f, 0) * nl + d] * P[0] + tab[L.CIAC(f, 1) * nl + d] * P[nw] +
-                     tab[L.CIAC(f, 2) * nl + d] * Q[0] + tab[L.CIAC(f, 3) * nl + d] * Q[nw];
-    if (v > 0) ecs += v;
+  const double *cr = row + L::W + 2 * ngmol;
+#pragma unroll
+  for (int f = 0; f < (NCIA >= 0 ? NCIA : kMaxCia); f++) {
+    if (f < ncia) {
+      const long long off = double_to_bits(cr[6 * f]) + w;
+      const double *P = c.ciaP[f] + off;
+      const double *Q = c.ciaQ[f] + off;
+      const D2 cy = ld2(cr + 6 * f + 2), cz = ld2(cr + 6 * f + 4);
+      const double v = cy.x * P[0] + cy.y * P[nw] + cz.x * Q[0] + cz.y * Q[nw];
+      if (v > 0) ecs += v;
+    }
   }
-  return e + tab[L.SCAT() * nl + d] * wn4 + tab[L.CLOUD() * nl + d] + ecs;
+  const D2 sc = ld2(row + L::SCAT);                          // (scattering coefficient, cloud)
+  return e + sc.x * wn4 + sc.y + ecs;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -253,11 +359,12 @@ BART_HD double cell_extinction(const DevConfig &c, const double *tab, int d, int
 //        the top sample, numerical.c:454-525, so tau(d) = sum of completed panels (+ one
 //        trapezoid when d is odd));  stop at the first tau > toomuch (tau.c:277-287).
 //   intensity: eclipse_intens eclipse.c:117-160; flux eclipse.c:242-287.
-template <int NANG, bool KEEP>
-BART_HD double eclipse_column(const DevConfig &c, const double *tab, int w, double *tau_keep,
-                              int *last_keep) {
-  const TabLayout &L = c.lay;
+template <int NMOL, int NCIA, int NANG, bool KEEP>
+BART_HD double eclipse_column(const DevConfig &c, const double *tab, const double *etab, int w,
+                              double *tau_keep, int *last_keep) {
+  typedef TabLayout L;
   const int nl = c.nlayer;
+  const int nf = c.lay.nf();
   const int nang = NANG > 0 ? NANG : c.nang;
   const double wn = c.wn[w];
   const double wn4 = (wn * wn) * (wn * wn);
@@ -268,23 +375,28 @@ BART_HD double eclipse_column(const DevConfig &c, const double *tab, int w, doub
   for (int a = 0; a < (NANG > 0 ? NANG : kMaxAng); a++) { trap[a] = 0.0; dprev[a] = 1.0; }
   double S = 0.0, er1 = 0.0, er2 = 0.0, Bprev = 0.0;
   int last = nl - 1;
-  for (int d = 0; d < nl; d++) {
-    const double er = cell_extinction(c, tab, d, w, wn4, false);
+  const double *row = tab;
+  for (int d = 0; d < nl; d++, row += nf) {
+    const double er = cell_extinction<NMOL, NCIA>(c, row, w, wn4, false);
     double tau;
     if (d == 0) tau = 0.0;
-    else if (d & 1) tau = S + tab[L.TR() * nl + d] * (er + er1);
     else {
-      S += tab[L.SA() * nl + d] * er + tab[L.SB() * nl + d] * er1 + tab[L.SC() * nl + d] * er2;
-      tau = S;
+      const D2 s1 = ld2(row + L::SA), s2 = ld2(row + L::SC);   // (SA, SB), (SC, TR)
+      if (d & 1) tau = S + s2.y * (er + er1);
+      else {
+        S += s1.x * er + s1.y * er1 + s2.x * er2;
+        tau = S;
+      }
     }
     er2 = er1; er1 = er;
     if (KEEP) tau_keep[d] = tau;
-    const double B = c1 / (exp(c2 / tab[L.T() * nl + d]) - 1.0);
+    const double B = c1 * fast_rcp(fast_exp_pos(c2 * row[L::INVT], etab) - 1.0);
+    const double Bs = B + Bprev;
 #pragma unroll
     for (int a = 0; a < (NANG > 0 ? NANG : kMaxAng); a++) {
       if (a < nang) {
-        const double dt = exp(-tau * c.inv_mu[a]);
-        if (d > 0) trap[a] += (dt - dprev[a]) * (B + Bprev);
+        const double dt = fast_exp_neg(-tau * c.inv_mu[a], etab);
+        trap[a] += (dt - dprev[a]) * Bs;       // d = 0: dprev = 1 = dt, contributes exactly 0
         dprev[a] = dt;
       }
     }
@@ -306,16 +418,15 @@ BART_HD double eclipse_column(const DevConfig &c, const double *tab, int w, doub
 // interval when the count is even, the two-point case through the reference's 3-point
 // construction, result x2 (both halves of the chord) and x rfct (tau.c:274).
 BART_HD void transit_weight_row(const DevConfig &c, const double *tab, int d, double *wt) {
-  const TabLayout &L = c.lay;
-  const int nl = c.nlayer;
-  const double *rad = tab + L.RAD() * nl;                    // depth-indexed radii
+  const int nf = c.lay.nf();
+  auto rad = [&](int i) { return tab[(size_t)i * nf + TabLayout::RAD]; };   // depth-indexed radii
   for (int i = 0; i <= d; i++) wt[i] = 0.0;
   if (d == 0) return;
-  const double b = rad[d];
+  const double b = rad(d);
   const double f = 2.0 * c.rfct;
   if (d == 1) {
-    const double rm = (rad[1] + rad[0]) / 2.0;
-    const double s1 = sqrt(rm * rm - b * b), s2 = sqrt(rad[0] * rad[0] - b * b);
+    const double rm = (rad(1) + rad(0)) / 2.0;
+    const double s1 = sqrt(rm * rm - b * b), s2 = sqrt(rad(0) * rad(0) - b * b);
     const double h0 = s1, h1 = s2 - s1;
     const double hsum = h0 + h1, hratio = h1 / h0, hfactor = hsum * hsum / (h0 * h1);
     const double a0 = (2.0 - hratio) * hsum / 6.0, a1 = hfactor * hsum / 6.0,
@@ -325,7 +436,7 @@ BART_HD void transit_weight_row(const DevConfig &c, const double *tab, int d, do
     return;
   }
   // s at depth i
-  auto sdep = [&](int i) { return i == d ? 0.0 : sqrt(rad[i] * rad[i] - b * b); };
+  auto sdep = [&](int i) { return i == d ? 0.0 : sqrt(rad(i) * rad(i) - b * b); };
   for (int p = 0; 2 * p + 2 <= d; p++) {
     const double sB = sdep(2 * p + 2), sM = sdep(2 * p + 1), sT = sdep(2 * p);
     const double h0 = sM - sB, h1 = sT - sM;
@@ -344,27 +455,28 @@ BART_HD void transit_weight_row(const DevConfig &c, const double *tab, int d, do
 // Transit column: tau(d) by the chord weights, stop at toomuch, then the modulation integral
 // (modulation1, slantpath.c:350-436) as a top-aligned Simpson scan over impact parameter.
 // `er` is per-thread scratch with stride `es` (shared memory in the kernel).
-template <bool KEEP>
-BART_HD double transit_column(const DevConfig &c, const double *tab, const double *wts, int w,
-                              double *er, int es, double *tau_keep, int *last_keep, int *status) {
-  const TabLayout &L = c.lay;
+template <int NMOL, int NCIA, bool KEEP>
+BART_HD double transit_column(const DevConfig &c, const double *tab, const double *etab,
+                              const double *wts, int w, double *er, int es, double *tau_keep,
+                              int *last_keep, int *status) {
+  typedef TabLayout L;
   const int nl = c.nlayer;
+  const int nf = c.lay.nf();
   const double wn = c.wn[w];
   const double wn4 = (wn * wn) * (wn * wn);
-  const double *rad = tab + L.RAD() * nl;
   double S = 0.0, f1 = 0.0, f2 = 0.0, tau = 0.0;
   int last = nl - 1;
   int d;
   for (d = 0; d < nl; d++) {
-    er[(size_t)d * es] = cell_extinction(c, tab, d, w, wn4, false);
+    const double *row = tab + (size_t)d * nf;
+    er[(size_t)d * es] = cell_extinction<NMOL, NCIA>(c, row, w, wn4, false);
     const double *wr = wts + (size_t)d * (d + 1) / 2;
     tau = 0.0;
     for (int i = 0; i <= d; i++) tau += wr[i] * er[(size_t)i * es];
     if (KEEP) tau_keep[d] = tau;
-    const double bd = rad[d] * c.rfct;
-    const double fd = exp(-tau) * bd;
-    if (d >= 2 && !(d & 1))
-      S += tab[L.SA() * nl + d] * fd + tab[L.SB() * nl + d] * f1 + tab[L.SC() * nl + d] * f2;
+    const double bd = row[L::RAD] * c.rfct;
+    const double fd = fast_exp_neg(-tau, etab) * bd;
+    if (d >= 2 && !(d & 1)) S += row[L::SA] * fd + row[L::SB] * f1 + row[L::SC] * f2;
     f2 = f1; f1 = fd;
     if (tau > c.toomuch) { last = d; break; }
   }
@@ -372,18 +484,19 @@ BART_HD double transit_column(const DevConfig &c, const double *tab, const doubl
   int n;                                                       // number of integration points
   if (last < nl - 1) {
     const int dd = last + 1;                                   // appended zero-integrand point
-    if (dd >= 2 && !(dd & 1)) S += tab[L.SB() * nl + dd] * f1 + tab[L.SC() * nl + dd] * f2;
+    const double *row = tab + (size_t)dd * nf;
+    if (dd >= 2 && !(dd & 1)) S += row[L::SB] * f1 + row[L::SC] * f2;
     f2 = f1; f1 = 0.0;
     n = dd + 1;
   } else n = nl;
   if (n < 3) { *status |= REJ_FEWPTS; return -1.0; }
-  if (!(n & 1)) S += tab[L.TR() * nl + (n - 1)] * (f1 + f2);
-  const double btop = rad[0] * c.rfct;
+  if (!(n & 1)) S += tab[(size_t)(n - 1) * nf + L::TR] * (f1 + f2);
+  const double btop = tab[L::RAD] * c.rfct;
   double res = btop * btop - 2.0 * S;
   if (c.transparent) {
     const double maxtau = tau > c.toomuch ? tau : c.toomuch;
-    const double bl = rad[n - 1] * c.rfct;
-    res -= exp(-maxtau) * bl * bl;
+    const double bl = tab[(size_t)(n - 1) * nf + L::RAD] * c.rfct;
+    res -= fast_exp_neg(-maxtau, etab) * bl * bl;
   }
   return res * c.inv_srad2;
 }

@@ -26,25 +26,21 @@ constexpr int kMaxCia = 4;
 constexpr int kMaxAng = 16;
 constexpr int kMaxSpec = 64;
 
-// field indices inside one model table (each field is `nlayer` doubles, depth-indexed)
+// One model table = nlayer records of `nf()` doubles, one record per depth (0 = top layer), so a
+// column kernel reads everything it needs for a layer from one contiguous, 16-byte aligned
+// shared-memory record with compile-time offsets (warp-wide broadcast loads, LDS.128 for pairs).
+//   [0] 1/T      [1] grid offset (int64 bits) of plane (layer, it)   [2] scattering coef (x wn^4)
+//   [3] cloud    [4..6] Simpson panel coefficients   [7] trapezoid half-width
+//   [8] T        [9] radius (file units)
+//   [10+2m, 11+2m]  W0, W1 of grid molecule m:  rho*(t1-T)/(t1-t0), rho*(T-t0)/(t1-t0)
+//   [cia(f) .. +5]  CIA file f: table offset (int64 bits), bracket index, 4 cubic coefficients
 struct TabLayout {
   int nl, ngmol, ncia;
-  BART_HD int T() const { return 0; }
-  BART_HD int IT() const { return 1; }                        // bracket index (exact int)
-  BART_HD int W0(int m) const { return 2 + 2 * m; }          // rho*(t1-T)/(t1-t0)
-  BART_HD int W1(int m) const { return 3 + 2 * m; }          // rho*(T-t0)/(t1-t0)
-  BART_HD int CIAK(int f) const { return 2 + 2 * ngmol + 5 * f; }
-  BART_HD int CIAC(int f, int c) const { return 3 + 2 * ngmol + 5 * f + c; }
-  BART_HD int SCAT() const { return 2 + 2 * ngmol + 5 * ncia; }
-  BART_HD int CLOUD() const { return SCAT() + 1; }
-  BART_HD int SA() const { return SCAT() + 2; }              // Simpson panel coefficients
-  BART_HD int SB() const { return SCAT() + 3; }
-  BART_HD int SC() const { return SCAT() + 4; }
-  BART_HD int TR() const { return SCAT() + 5; }              // trapezoid half-width
-  BART_HD int RAD() const { return SCAT() + 6; }             // radius (file units)
-  BART_HD int nfields() const { return SCAT() + 7; }
-  // doubles per model, padded to a multiple of 2 (16-byte bulk-copy granularity)
-  BART_HD int stride() const { int n = nfields() * nl; return (n + 1) & ~1; }
+  static constexpr int INVT = 0, GOFF = 1, SCAT = 2, CLOUD = 3, SA = 4, SB = 5, SC = 6, TR = 7,
+                       T = 8, RAD = 9, W = 10;
+  BART_HD int cia(int f) const { return W + 2 * ngmol + 6 * f; }
+  BART_HD int nf() const { return W + 2 * ngmol + 6 * ncia; }
+  BART_HD int stride() const { return nf() * nl; }   // nf() is even: 16-byte granularity holds
 };
 
 struct DevConfig {

@@ -59,7 +59,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 // Stage one model's table into shared memory.  Bulk-async when the size allows (multiple of 16 B,
 // always true by TabLayout::stride), else a cooperative copy.
 __device__ __forceinline__ void stage_table(double *s_tab, const double *g_tab, int ndoubles,
-                                            uint64_t *bar, bool use_tma) {
+                                            uint64_t *bar, bool use_tma, double *s_etab = nullptr) {
+  if (s_etab && threadIdx.x == 32) fill_exp_table(s_etab);
   if (use_tma) {
     if (threadIdx.x == 0) { mbar_init(bar, 1); fence_mbar_init(); }
     __syncthreads();
@@ -76,6 +77,7 @@ __device__ __forceinline__ void stage_table(double *s_tab, const double *g_tab, 
       }
     }
     mbar_wait(bar, 0);
+    if (s_etab) __syncthreads();               // the exp table is written by a generic-proxy store
   } else {
     for (int i = threadIdx.x; i < ndoubles; i += blockDim.x) s_tab[i] = g_tab[i];
     __syncthreads();
@@ -116,14 +118,15 @@ atm_prep_kernel(DevConfig c, Knobs knobs, const double *__restrict__ profiles, i
 
 // ---------------------------------------------------------------------------------------
 // fused eclipse column kernel
-template <int NANG, bool KEEP>
+template <int NMOL, int NCIA, int NANG, bool KEEP>
 __global__ void __launch_bounds__(kColThreads)
 eclipse_column_kernel(DevConfig c, const double *__restrict__ tabs, const int *__restrict__ status,
                       double *__restrict__ spectra, double *__restrict__ tau_keep,
                       int *__restrict__ last_keep, int nmodels, int use_tma) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar;
-  double *s_tab = reinterpret_cast<double *>(smem_raw);
+  double *s_etab = reinterpret_cast<double *>(smem_raw);       // 2^(j/16), one 128-byte bank row
+  double *s_tab = s_etab + kExpTabSize;
   const int m = blockIdx.x % nmodels;           // model-fastest: neighbours share grid columns
   const int tile = blockIdx.x / nmodels;
   const int w = tile * kColThreads + threadIdx.x;
@@ -132,11 +135,12 @@ eclipse_column_kernel(DevConfig c, const double *__restrict__ tabs, const int *_
     if (w < c.nwave) spectra[(size_t)m * c.nwave + w] = -1.0;
     return;
   }
-  stage_table(s_tab, tabs + (size_t)m * nd, nd, &bar, use_tma != 0);
+  stage_table(s_tab, tabs + (size_t)m * nd, nd, &bar, use_tma != 0, s_etab);
   if (w >= c.nwave) return;
   double *tk = KEEP ? tau_keep + ((size_t)m * c.nwave + w) * c.nlayer : nullptr;
   int *lk = KEEP ? last_keep + (size_t)m * c.nwave + w : nullptr;
-  spectra[(size_t)m * c.nwave + w] = eclipse_column<NANG, KEEP>(c, s_tab, w, tk, lk);
+  spectra[(size_t)m * c.nwave + w] =
+      eclipse_column<NMOL, NCIA, NANG, KEEP>(c, s_tab, s_etab, w, tk, lk);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -163,7 +167,8 @@ transit_column_kernel(DevConfig c, const double *__restrict__ tabs, const double
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar;
   const int nd = c.lay.stride();
-  double *s_tab = reinterpret_cast<double *>(smem_raw);
+  double *s_etab = reinterpret_cast<double *>(smem_raw);
+  double *s_tab = s_etab + kExpTabSize;
   double *s_er = s_tab + nd;                                   // [nl][kTransitThreads]
   const int m = blockIdx.x % nmodels;
   const int tile = blockIdx.x / nmodels;
@@ -172,13 +177,13 @@ transit_column_kernel(DevConfig c, const double *__restrict__ tabs, const double
     if (w < c.nwave) spectra[(size_t)m * c.nwave + w] = -1.0;
     return;
   }
-  stage_table(s_tab, tabs + (size_t)m * nd, nd, &bar, use_tma != 0);
+  stage_table(s_tab, tabs + (size_t)m * nd, nd, &bar, use_tma != 0, s_etab);
   if (w >= c.nwave) return;
   const double *wm = wts + (size_t)m * ((size_t)c.nlayer * (c.nlayer + 1) / 2);
   double *tk = KEEP ? tau_keep + ((size_t)m * c.nwave + w) * c.nlayer : nullptr;
   int *lk = KEEP ? last_keep + (size_t)m * c.nwave + w : nullptr;
   int st = 0;
-  const double r = transit_column<KEEP>(c, s_tab, wm, w, s_er + threadIdx.x, kTransitThreads, tk, lk, &st);
+  const double r = transit_column<0, -1, KEEP>(c, s_tab, s_etab, wm, w, s_er + threadIdx.x, kTransitThreads, tk, lk, &st);
   spectra[(size_t)m * c.nwave + w] = r;
   if (st) atomicOr(&status_col[m], st);
 }
@@ -210,7 +215,8 @@ extinction_kernel(DevConfig c, const double *__restrict__ tabs, double *__restri
   const int d0 = blockIdx.y * per, d1 = min(nl, d0 + per);
   double *out = ext + (size_t)m * nl * c.nwave + w;
   for (int d = d0; d < d1; d++)
-    out[(size_t)(nl - 1 - d) * c.nwave] = cell_extinction(c, s_tab, d, w, wn4, mol_only != 0);
+    out[(size_t)(nl - 1 - d) * c.nwave] =
+        cell_extinction<0, -1>(c, s_tab + (size_t)d * c.lay.nf(), w, wn4, mol_only != 0);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -252,7 +258,9 @@ __global__ void fill_kernel(double *p, size_t n, double v) {
 
 // ---------------------------------------------------------------------------------------
 // launchers
-static size_t table_smem(const DevConfig &c) { return (size_t)c.lay.stride() * sizeof(double); }
+static size_t table_smem(const DevConfig &c) {
+  return ((size_t)c.lay.stride() + kExpTabSize) * sizeof(double);
+}
 
 void launch_atm_prep(const DevConfig &c, const Knobs &k, const double *profiles, int n_in,
                      double *tabs, int *status, int nmodels, cudaStream_t s) {
@@ -265,41 +273,57 @@ void launch_atm_prep(const DevConfig &c, const Knobs &k, const double *profiles,
   atm_prep_kernel<<<nmodels, 128, smem, s>>>(c, k, profiles, n_in, tabs, status, nmodels);
 }
 
-template <int NANG, bool KEEP>
+template <int NMOL, int NCIA, int NANG, bool KEEP>
 static void launch_eclipse_t(const DevConfig &c, const double *tabs, const int *status,
                              double *spectra, double *tau_keep, int *last_keep, int nmodels,
                              int use_tma, cudaStream_t s) {
   const size_t smem = table_smem(c);
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
-    cudaFuncSetAttribute(eclipse_column_kernel<NANG, KEEP>,
+    cudaFuncSetAttribute(eclipse_column_kernel<NMOL, NCIA, NANG, KEEP>,
                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = smem;
   }
   const int tiles = (c.nwave + kColThreads - 1) / kColThreads;
-  eclipse_column_kernel<NANG, KEEP><<<(unsigned)((size_t)tiles * nmodels), kColThreads, smem, s>>>(
-      c, tabs, status, spectra, tau_keep, last_keep, nmodels, use_tma);
+  eclipse_column_kernel<NMOL, NCIA, NANG, KEEP>
+      <<<(unsigned)((size_t)tiles * nmodels), kColThreads, smem, s>>>(
+          c, tabs, status, spectra, tau_keep, last_keep, nmodels, use_tma);
+}
+
+// Specialised instantiations for the shapes BART runs (1-4 line-list molecules, 0-2 CIA files, the
+// default 5-angle ray grid); anything else takes the run-time-count kernel.
+template <int NMOL, int NCIA>
+static void launch_eclipse_nang(const DevConfig &c, const double *tabs, const int *status,
+                                double *spectra, int nmodels, int use_tma, cudaStream_t s) {
+  if (c.nang == 5) launch_eclipse_t<NMOL, NCIA, 5, false>(c, tabs, status, spectra, nullptr, nullptr, nmodels, use_tma, s);
+  else launch_eclipse_t<NMOL, NCIA, 0, false>(c, tabs, status, spectra, nullptr, nullptr, nmodels, use_tma, s);
+}
+
+template <int NMOL>
+static void launch_eclipse_ncia(const DevConfig &c, const double *tabs, const int *status,
+                                double *spectra, int nmodels, int use_tma, cudaStream_t s) {
+  switch (c.ncia) {
+    case 0: launch_eclipse_nang<NMOL, 0>(c, tabs, status, spectra, nmodels, use_tma, s); break;
+    case 1: launch_eclipse_nang<NMOL, 1>(c, tabs, status, spectra, nmodels, use_tma, s); break;
+    case 2: launch_eclipse_nang<NMOL, 2>(c, tabs, status, spectra, nmodels, use_tma, s); break;
+    default: launch_eclipse_t<0, -1, 0, false>(c, tabs, status, spectra, nullptr, nullptr, nmodels, use_tma, s);
+  }
 }
 
 void launch_eclipse(const DevConfig &c, const double *tabs, const int *status, double *spectra,
                     double *tau_keep, int *last_keep, int nmodels, bool keep, int use_tma,
                     cudaStream_t s) {
-#define BART_ECL(N)                                                                              \
-  case N:                                                                                        \
-    if (keep) launch_eclipse_t<N, true>(c, tabs, status, spectra, tau_keep, last_keep, nmodels,  \
-                                        use_tma, s);                                             \
-    else launch_eclipse_t<N, false>(c, tabs, status, spectra, tau_keep, last_keep, nmodels,      \
-                                    use_tma, s);                                                 \
-    break;
-  switch (c.nang) {
-    BART_ECL(1) BART_ECL(2) BART_ECL(3) BART_ECL(4) BART_ECL(5) BART_ECL(6) BART_ECL(7) BART_ECL(8)
-    default:
-      if (keep) launch_eclipse_t<0, true>(c, tabs, status, spectra, tau_keep, last_keep, nmodels,
-                                          use_tma, s);
-      else launch_eclipse_t<0, false>(c, tabs, status, spectra, tau_keep, last_keep, nmodels,
-                                      use_tma, s);
+  if (keep) {   // introspection path: run-time counts, stores tau[] and last[]
+    launch_eclipse_t<0, -1, 0, true>(c, tabs, status, spectra, tau_keep, last_keep, nmodels, use_tma, s);
+    return;
   }
-#undef BART_ECL
+  switch (c.ngmol) {
+    case 1: launch_eclipse_ncia<1>(c, tabs, status, spectra, nmodels, use_tma, s); break;
+    case 2: launch_eclipse_ncia<2>(c, tabs, status, spectra, nmodels, use_tma, s); break;
+    case 3: launch_eclipse_ncia<3>(c, tabs, status, spectra, nmodels, use_tma, s); break;
+    case 4: launch_eclipse_ncia<4>(c, tabs, status, spectra, nmodels, use_tma, s); break;
+    default: launch_eclipse_t<0, -1, 0, false>(c, tabs, status, spectra, nullptr, nullptr, nmodels, use_tma, s);
+  }
 }
 
 void launch_merge_status(int *status, const int *status_col, int nmodels, cudaStream_t s) {

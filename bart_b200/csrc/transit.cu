@@ -842,23 +842,23 @@ long long bart_debug_get(const char *name, int model, double *out, long long cap
   finish_stream();
   auto field = [&](int f, bool to_layer_order) -> long long {
     if (capacity < nl) fail("bart_debug_get: capacity too small");
-    std::vector<double> tmp(nl);
-    CUDA_OK(cudaMemcpy(tmp.data(), G.d_tabs.p + (size_t)model * c.lay.stride() + (size_t)f * nl,
-                       nl * 8, cudaMemcpyDeviceToHost));
-    for (int d = 0; d < nl; d++) out[to_layer_order ? nl - 1 - d : d] = tmp[d];
+    const int nf = c.lay.nf();
+    std::vector<double> tmp((size_t)nl * nf);
+    CUDA_OK(cudaMemcpy(tmp.data(), G.d_tabs.p + (size_t)model * c.lay.stride(), tmp.size() * 8,
+                       cudaMemcpyDeviceToHost));
+    for (int d = 0; d < nl; d++) out[to_layer_order ? nl - 1 - d : d] = tmp[(size_t)d * nf + f];
     return nl;
   };
-  if (n == "radius") return field(c.lay.RAD(), true);
-  if (n == "temp") return field(c.lay.T(), true);
-  if (n == "bracket") return field(c.lay.IT(), true);
-  if (n == "scat") return field(c.lay.SCAT(), true);
-  if (n == "cloud") return field(c.lay.CLOUD(), true);
-  if (n == "simpson_a") return field(c.lay.SA(), false);
-  if (n == "simpson_b") return field(c.lay.SB(), false);
-  if (n == "simpson_c") return field(c.lay.SC(), false);
-  if (n == "trapezoid") return field(c.lay.TR(), false);
+  if (n == "radius") return field(TabLayout::RAD, true);
+  if (n == "temp") return field(TabLayout::T, true);
+  if (n == "scat") return field(TabLayout::SCAT, true);
+  if (n == "cloud") return field(TabLayout::CLOUD, true);
+  if (n == "simpson_a") return field(TabLayout::SA, false);
+  if (n == "simpson_b") return field(TabLayout::SB, false);
+  if (n == "simpson_c") return field(TabLayout::SC, false);
+  if (n == "trapezoid") return field(TabLayout::TR, false);
   if (n == "table") {
-    const long long cnt = c.lay.nfields() * nl;
+    const long long cnt = c.lay.stride();
     if (capacity < cnt) fail("bart_debug_get: capacity too small");
     CUDA_OK(cudaMemcpy(out, G.d_tabs.p + (size_t)model * c.lay.stride(), cnt * 8, cudaMemcpyDeviceToHost));
     return cnt;

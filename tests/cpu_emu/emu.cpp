@@ -124,26 +124,31 @@ int emu_run(const double *in, double *spectrum, double *tau, int *last, double *
   if (radius) for (int l = 0; l < nl; l++) radius[l] = rad[l];
   if (status) { for (int w = 0; w < nw; w++) spectrum[w] = -1; return status; }
   std::vector<double> tk(nl), wts((size_t)nl * (nl + 1) / 2), er(nl);
+  alignas(16) double etab[kExpTabSize];
+  fill_exp_table(etab);
   if (!c.eclipse) for (int d = 0; d < nl; d++) transit_weight_row(c, tab.data(), d, &wts[(size_t)d * (d + 1) / 2]);
   for (int w = 0; w < nw; w++) {
     int lk = 0;
     std::fill(tk.begin(), tk.end(), 0.0);
     if (c.eclipse) {
-      switch (c.nang) {
-        case 5: spectrum[w] = eclipse_column<5, true>(c, tab.data(), w, tk.data(), &lk); break;
-        default: spectrum[w] = eclipse_column<0, true>(c, tab.data(), w, tk.data(), &lk);
-      }
+      // exercise both the specialised and the run-time-count instantiations
+      if (c.nang == 5 && c.ngmol == 1 && c.ncia == 1) spectrum[w] = eclipse_column<1, 1, 5, true>(c, tab.data(), etab, w, tk.data(), &lk);
+      else if (c.nang == 5 && c.ngmol == 4 && c.ncia == 1) spectrum[w] = eclipse_column<4, 1, 5, true>(c, tab.data(), etab, w, tk.data(), &lk);
+      else spectrum[w] = eclipse_column<0, -1, 0, true>(c, tab.data(), etab, w, tk.data(), &lk);
     } else {
-      spectrum[w] = transit_column<true>(c, tab.data(), wts.data(), w, er.data(), 1, tk.data(), &lk, &status);
+      spectrum[w] = transit_column<0, -1, true>(c, tab.data(), etab, wts.data(), w, er.data(), 1, tk.data(), &lk, &status);
     }
     if (tau) memcpy(tau + (size_t)w * nl, tk.data(), nl * 8);
     if (last) last[w] = lk;
     if (ext_total) {
       const double wn = c.wn[w], wn4 = (wn * wn) * (wn * wn);
-      for (int d = 0; d < nl; d++) ext_total[(size_t)(nl - 1 - d) * nw + w] = cell_extinction(c, tab.data(), d, w, wn4, true);
+      for (int d = 0; d < nl; d++)
+        ext_total[(size_t)(nl - 1 - d) * nw + w] = cell_extinction<0, -1>(c, tab.data() + (size_t)d * c.lay.nf(), w, wn4, true);
     }
   }
   return status;
 }
+
+double emu_fast_exp(double x) { double t[kExpTabSize]; fill_exp_table(t); return fast_exp(x, t); }
 
 }  // extern "C"

@@ -43,3 +43,23 @@ def test_rejection_status(built, get_case):
     nl = E.nlayer
     bad[nl * 6: nl * 7] = 0.9            # H2 abundance -> sum > 1.001
     assert E.run(bad)["status"] & 4
+
+
+def test_fast_exp_accuracy(built):
+    """The kernels' exp (column_math.cuh fast_exp) against libm: <= 1e-15 relative over the ranges
+    the forward model uses (-tau/mu down to the clamp, Planck exponents up to ~150)."""
+    import ctypes as C
+    lib = C.CDLL(__import__("os").path.join(cases.ROOT, "tests", "cpu_emu", "libemu.so"))
+    lib.emu_fast_exp.restype = C.c_double
+    lib.emu_fast_exp.argtypes = [C.c_double]
+    rng = np.random.default_rng(1)
+    xs = np.concatenate([-10.0 ** rng.uniform(-12, 2.8, 20000), rng.uniform(0, 150, 5000),
+                         [0.0, -0.0, -1e-300, -708.0, 1.0, -1.0, 0.5 * np.log(2), -0.5 * np.log(2)]])
+    worst = 0.0
+    for x in xs:
+        got, ref = lib.emu_fast_exp(float(x)), float(np.exp(x))
+        worst = max(worst, abs(got - ref) / ref)
+    assert worst < 1e-15, worst
+    assert lib.emu_fast_exp(0.0) == 1.0
+    assert lib.emu_fast_exp(-1e9) == 0.0 and lib.emu_fast_exp(-709.0) == 0.0   # opaque deck
+    assert lib.emu_fast_exp(1e5) == 1e308 and np.isfinite(lib.emu_fast_exp(709.0))
