@@ -137,7 +137,8 @@ def read_atm(path):
             rows.append([float(v) for v in s.split()])
         i += 1
     a = np.array(rows)
-    return dict(species=species, radius=a[:, 0], press=a[:, 1], temp=a[:, 2], q=a[:, 3:],
+    c = np.ascontiguousarray
+    return dict(species=species, radius=c(a[:, 0]), press=c(a[:, 1]), temp=c(a[:, 2]), q=c(a[:, 3:]),
                 rfct=rfct, pfct=pfct, tfct=tfct)
 
 
@@ -327,3 +328,223 @@ def bandflux(spectrum, specwn, filters, star=None, rprs=None):
         else:
             out[i] = bandintegrate(spectrum[idx], specwn, nif, idx)
     return out
+
+
+# ----------------------------------------------------------------------------------------
+# Stage (d): line-by-line opacity-grid builder oracle (opacity.c:218-427 driving
+# orc_voigtn / orc_computemolext of transit_oracle.c)
+class OrcLbl(C.Structure):
+    _fields_ = [
+        ("nlines", C.c_long), ("wl_um", dp), ("elow", dp), ("gf", dp),
+        ("isoid", C.POINTER(C.c_short)), ("niso", C.c_int), ("iso_mass", dp), ("iso_ratio", dp),
+        ("iso_spec", ip), ("iso_gmol", ip), ("ngmol", C.c_int), ("nspec", C.c_int),
+        ("spec_mass", dp), ("spec_radius", dp), ("wn_lo", C.c_double), ("dwn", C.c_double),
+        ("nwave", C.c_long), ("osamp", C.c_int), ("nowns", C.c_long),
+        ("nDop", C.c_int), ("nLor", C.c_int), ("aDop", dp), ("aLor", dp),
+        ("profsize", C.POINTER(C.c_long)), ("profile", C.POINTER(C.POINTER(C.c_float))),
+        ("ethresh", C.c_double),
+    ]
+
+
+def read_tli(path):
+    """TLI v6 (readlineinfo.c:87-244, 416-537)."""
+    with open(path, "rb") as f:
+        buf = f.read()
+    pos = 4
+    ver, _, _ = struct.unpack_from("3h", buf, pos); pos += 6
+    assert ver == 6
+    wl_ini, wl_fin = struct.unpack_from("2d", buf, pos); pos += 16
+    (ndb,) = struct.unpack_from("h", buf, pos); pos += 2
+    isos = []
+    for d in range(ndb):
+        (n,) = struct.unpack_from("h", buf, pos); pos += 2
+        dbname = buf[pos:pos + n].decode(); pos += n
+        (n,) = struct.unpack_from("h", buf, pos); pos += 2
+        molname = buf[pos:pos + n].decode(); pos += n
+        nT, niso = struct.unpack_from("hh", buf, pos); pos += 4
+        T = np.frombuffer(buf, dtype="<f8", count=nT, offset=pos).copy(); pos += 8 * nT
+        for i in range(niso):
+            (n,) = struct.unpack_from("h", buf, pos); pos += 2
+            name = buf[pos:pos + n].decode(); pos += n
+            mass, ratio = struct.unpack_from("2d", buf, pos); pos += 16
+            Z = np.frombuffer(buf, dtype="<f8", count=nT, offset=pos).copy(); pos += 8 * nT
+            isos.append(dict(db=dbname, mol=molname, name=name, mass=mass, ratio=ratio, T=T, Z=Z))
+    (nlines,) = struct.unpack_from("Q", buf, pos); pos += 8
+    (niso_l,) = struct.unpack_from("i", buf, pos); pos += 4
+    per = struct.unpack_from("%dQ" % niso_l, buf, pos); pos += 8 * niso_l
+    wl = np.frombuffer(buf, dtype="<f8", count=nlines, offset=pos).copy(); pos += 8 * nlines
+    isoid = np.frombuffer(buf, dtype="<i2", count=nlines, offset=pos).copy(); pos += 2 * nlines
+    elow = np.frombuffer(buf, dtype="<f8", count=nlines, offset=pos).copy(); pos += 8 * nlines
+    gf = np.frombuffer(buf, dtype="<f8", count=nlines, offset=pos).copy()
+    return dict(isos=isos, per=per, wl=wl, isoid=isoid, elow=elow, gf=gf, wl_ini=wl_ini, wl_fin=wl_fin)
+
+
+def select_lines(tli, wnlow, wnhigh):
+    """Per-isotope slice by the reference's binary search + linear refinement
+    (readlineinfo.c:16-77, 496-525)."""
+    iniw, finw = 1.0 / wnhigh / 1e-4, 1.0 / wnlow / 1e-4
+    keep = []
+    off = 0
+    for n in tli["per"]:
+        w = tli["wl"][off:off + n]
+        if n > 0:
+            lo, hi = 0, n - 1
+            while True:
+                loc = (hi + lo) // 2
+                if iniw > w[loc]:
+                    lo = loc
+                else:
+                    hi = loc
+                if hi - lo <= 1:
+                    break
+            first = hi
+            while first > 0 and not (w[first - 1] < iniw):
+                first -= 1
+            lo, hi = 0, n - 1
+            while True:
+                loc = (hi + lo) // 2
+                if finw > w[loc]:
+                    lo = loc
+                else:
+                    hi = loc
+                if hi - lo <= 1:
+                    break
+            last = lo
+            while last < n - 1 and not (w[last + 1] > finw):
+                last += 1
+            if last >= first:
+                keep.append(np.arange(off + first, off + last + 1))
+        off += n
+    idx = np.concatenate(keep) if keep else np.zeros(0, dtype=int)
+    return idx
+
+
+class BuilderOracle:
+    """calcprofiles + calcopacity restated: builds o[layer][temp][mol][wave] on the CPU."""
+
+    def __init__(self, cfgpath, with_profiles=True):
+        L = lib()
+        L.orc_computemolext.argtypes = [C.POINTER(OrcLbl), C.c_double, dp, dp, dp,
+                                        C.POINTER(C.c_long), C.POINTER(C.c_long)]
+        L.orc_spline_init.argtypes = [dp, dp, dp, C.c_long]
+        L.orc_splinterp_pt.restype = C.c_double
+        L.orc_splinterp_pt.argtypes = [dp, C.c_long, dp, dp, C.c_double]
+        cfg = read_cfg(cfgpath)
+        self.cfg = cfg
+        atm = read_atm(cfg["atm"])
+        mols = read_molecules(cfg["molfile"])
+        self.atm = atm
+        species = atm["species"]
+        self.spec_mass = np.array([mols[s]["mass"] for s in species])
+        self.spec_radius = np.array([mols[s]["radius"] for s in species])
+        ids = [mols[s]["id"] for s in species]
+        lo, hi, d = float(cfg["wnlow"]), float(cfg["wnhigh"]), float(cfg["wndelt"])
+        self.wn = wn_grid(lo, hi, d)
+        self.osamp = int(float(cfg.get("wnosamp", 2160)))
+        self.nowns = (len(self.wn) - 1) * self.osamp + 1
+        self.odwn = d / self.osamp
+        self.dwn = d
+        self.temps = wn_grid(float(cfg.get("tlow", 500)), float(cfg.get("thigh", 3000)),
+                             float(cfg.get("tempdelt", 100)))
+        tli = read_tli(cfg["linedb"])
+        self.tli = tli
+        idx = select_lines(tli, lo, hi)
+        self.line_idx = idx
+        self.wl = np.ascontiguousarray(tli["wl"][idx])
+        self.elow = np.ascontiguousarray(tli["elow"][idx])
+        self.gf = np.ascontiguousarray(tli["gf"][idx])
+        self.isoid = np.ascontiguousarray(tli["isoid"][idx])
+        isos = tli["isos"]
+        self.niso = len(isos)
+        self.iso_mass = np.array([i["mass"] for i in isos])
+        self.iso_ratio = np.array([i["ratio"] for i in isos])
+        self.iso_spec = np.array([species.index(i["mol"]) for i in isos], dtype=np.int32)
+        gm, gmol = [], []
+        for i in isos:
+            mid = ids[species.index(i["mol"])]
+            if mid not in gm:
+                gm.append(mid)
+            gmol.append(gm.index(mid))
+        self.gmol_id = gm
+        self.iso_gmol = np.array(gmol, dtype=np.int32)
+        # Z(T grid) by natural spline (opacity.c:325-339)
+        self.ziso = np.zeros((self.niso, len(self.temps)))
+        for k, i in enumerate(isos):
+            z = np.zeros(len(i["T"]))
+            L.orc_spline_init(_d(z), _d(i["T"]), _d(i["Z"]), len(i["T"]))
+            for t, T in enumerate(self.temps):
+                self.ziso[k, t] = L.orc_splinterp_pt(_d(z), len(i["T"]), _d(i["T"]), _d(i["Z"]), float(T))
+        # Voigt table (calcprofiles)
+        self.nDop, self.nLor = int(cfg.get("ndop", 60)), int(cfg.get("nlor", 60))
+        f32 = np.float32
+        dmin, dmax = f32(cfg.get("dmin", 1e-3)), f32(cfg.get("dmax", 0.25))
+        lmin, lmax = f32(cfg.get("lmin", 1e-4)), f32(cfg.get("lmax", 10.0))
+
+        def logspace(a, b, n):
+            l0, l1 = np.log10(float(a)), np.log10(float(b))
+            st = (l1 - l0) / (n - 1.0)
+            return np.array([10.0 ** (l0 + i * st) for i in range(n)])
+        self.aDop, self.aLor = logspace(dmin, dmax, self.nDop), logspace(lmin, lmax, self.nLor)
+        self.ta = f32(cfg.get("nwidth", 20))
+        self.ethresh = float(cfg.get("ethresh", cfg.get("ethreshold", 1e-8)))
+        self.profsize = np.zeros(self.nDop * self.nLor, dtype=np.int64)
+        self.profiles = [None] * (self.nDop * self.nLor)
+        if with_profiles:
+            for i in range(self.nDop):
+                for j in range(self.nLor):
+                    p = i * self.nLor + j
+                    if self.aDop[i] * 10.0 < self.aLor[j] and i != 0:
+                        self.profsize[p] = self.profsize[p - self.nLor]
+                        self.profiles[p] = self.profiles[p - self.nLor]
+                        continue
+                    self.profiles[p], self.profsize[p] = self.profile(i, j)
+
+    def profile(self, i, j):
+        L = lib()
+        dop, lor = float(np.float32(self.aDop[i])), float(np.float32(self.aLor[j]))
+        ps = L.orc_profile_halfsize(self.odwn, dop, lor, self.ta, self.nowns)
+        n = 2 * ps + 1
+        out = np.zeros(n, dtype=np.float32)
+        L.orc_voigtn(n, self.odwn * ps, lor, dop, out.ctypes.data_as(C.POINTER(C.c_float)),
+                     1 if n > 99999 else 0)
+        return out, ps
+
+    def build(self, layers=None, temps=None, trace=False):
+        L = lib()
+        atm = self.atm
+        nl = len(atm["press"])
+        layers = range(nl) if layers is None else layers
+        temps = range(len(self.temps)) if temps is None else temps
+        nw = len(self.wn)
+        ng = len(self.gmol_id)
+        lb = OrcLbl()
+        lb.nlines = len(self.wl)
+        lb.wl_um, lb.elow, lb.gf = _d(self.wl), _d(self.elow), _d(self.gf)
+        lb.isoid = self.isoid.ctypes.data_as(C.POINTER(C.c_short))
+        lb.niso, lb.iso_mass, lb.iso_ratio = self.niso, _d(self.iso_mass), _d(self.iso_ratio)
+        lb.iso_spec, lb.iso_gmol = self.iso_spec.ctypes.data_as(ip), self.iso_gmol.ctypes.data_as(ip)
+        lb.ngmol, lb.nspec = ng, len(self.spec_mass)
+        lb.spec_mass, lb.spec_radius = _d(self.spec_mass), _d(self.spec_radius)
+        lb.wn_lo, lb.dwn, lb.nwave, lb.osamp, lb.nowns = self.wn[0], self.dwn, nw, self.osamp, self.nowns
+        lb.nDop, lb.nLor, lb.aDop, lb.aLor = self.nDop, self.nLor, _d(self.aDop), _d(self.aLor)
+        psz = self.profsize.astype(np.int64)
+        lb.profsize = psz.ctypes.data_as(C.POINTER(C.c_long))
+        ptrs = (C.POINTER(C.c_float) * len(self.profiles))(
+            *[p.ctypes.data_as(C.POINTER(C.c_float)) for p in self.profiles])
+        lb.profile = ptrs
+        lb.ethresh = self.ethresh
+        out = np.zeros((len(list(layers)), len(list(temps)), ng, nw))
+        tr = np.zeros(len(self.wl), dtype=np.int64) if trace else None
+        for a, r in enumerate(layers):
+            for b, t in enumerate(temps):
+                T = float(self.temps[t])
+                dens = 1.66053886e-24 * atm["q"][r] * (atm["press"][r] * atm["pfct"]) / 1.380658e-16 / T \
+                    * self.spec_mass
+                dens = np.ascontiguousarray(dens)
+                Z = np.ascontiguousarray(self.ziso[:, t])
+                k = np.zeros((ng, nw))
+                L.orc_computemolext(C.byref(lb), T, _d(dens), _d(Z), _d(k),
+                                    tr.ctypes.data_as(C.POINTER(C.c_long)) if trace else None, None)
+                out[a, b] = k
+        self.trace = tr
+        return out

@@ -35,6 +35,25 @@ CASES = {
 }
 
 
+# Opacity-grid builder (--justOpacity) cases: name -> make_case kwargs (no pre-made grid)
+BUILD_CASES = {
+    "build_ch4": dict(shape="tiny", nlayer=12, with_grid=False, nlines=3000, tempdelt=600.0,
+                      seed=4711, ethresh=1e-6),
+    "build_h2o_ch4": dict(shape=dict(wnlow=2000.0, wnhigh=2120.0, wndelt=1.0, mols=["H2O", "CH4"],
+                                     toomuch=10.0),
+                          nlayer=10, with_grid=False, nlines=5000, tempdelt=800.0, seed=4712,
+                          ethresh=1e-4, wnosamp=1080, nwidth=30),
+}
+
+
+def build_builder_case(name, workdir):
+    import os as _os
+    case = synth.make_case(_os.path.join(workdir, name), **BUILD_CASES[name])
+    if _os.path.exists(case["opacity"]):
+        _os.remove(case["opacity"])
+    return case
+
+
 def sha(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 

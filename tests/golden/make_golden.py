@@ -49,5 +49,26 @@ def main():
                 os.path.basename(cases.golden_path(name)), os.path.getsize(cases.golden_path(name))))
 
 
+def builder_golden(only):
+    """Grids built by the reference's `transit --justOpacity` from synthetic TLI files."""
+    from bart_b200 import synth
+    exe = os.path.join(ROOT, "oracle", "_ref", "transit_ref")
+    with tempfile.TemporaryDirectory() as tmp:
+        for name in cases.BUILD_CASES:
+            if only and name not in only:
+                continue
+            case = cases.build_builder_case(name, tmp)
+            r = subprocess.run([exe, "-c", case["cfg"], "--justOpacity"], capture_output=True, text=True)
+            if r.returncode != 0 or not os.path.exists(case["opacity"]):
+                raise SystemExit("reference builder failed on %s:\n%s\n%s" % (name, r.stdout[-2000:], r.stderr[-2000:]))
+            g = synth.read_opacity(case["opacity"], mmap=False)
+            np.savez_compressed(cases.golden_path(name), grid=g["o"], temps=g["temps"], molids=g["molids"],
+                                press=g["press"], wn=g["wn"], tli_sha=cases.sha(np.fromfile(case["tli"], dtype=np.uint8)),
+                                file_bytes=os.path.getsize(case["opacity"]))
+            print("%-24s grid %s  max %.3g  nonzero %.3f -> %d bytes" % (
+                name, g["o"].shape, g["o"].max(), (g["o"] > 0).mean(), os.path.getsize(cases.golden_path(name))))
+
+
 if __name__ == "__main__":
+    builder_golden(sys.argv[1:])
     main()

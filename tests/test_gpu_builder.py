@@ -1,0 +1,93 @@
+"""GPU (B200): the CUDA opacity-grid builder (K5 Voigt table, K6 line binning) through the C ABI
+against (1) grids built by the unmodified reference (`transit --justOpacity`, tests/golden),
+(2) the builder oracle, with line-to-bin indices bit-exact and the opacity file byte layout of
+opacity.c:406-421."""
+import os
+import numpy as np
+import pytest
+
+import cases
+from util import relerr
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-6      # grid values: float32 Voigt table => north-star tolerance 1e-6 relative
+
+
+@pytest.fixture(scope="module")
+def api(built):
+    from bart_b200 import api as a
+    a.device_info()
+    return a
+
+
+@pytest.mark.parametrize("name", list(cases.BUILD_CASES))
+def test_built_grid_vs_reference(name, api, workdir):
+    from bart_b200 import synth
+    case = cases.build_builder_case(name, workdir)
+    g = np.load(cases.golden_path(name))
+    assert cases.sha(np.fromfile(case["tli"], dtype=np.uint8)) == str(g["tli_sha"])
+    assert not os.path.exists(case["opacity"])
+    tr = api.Transit(argv=["transit", "-c", case["cfg"], "--justOpacity"])      # BART.py:563-565
+    assert os.path.getsize(case["opacity"]) == int(g["file_bytes"])
+    mine = synth.read_opacity(case["opacity"], mmap=False)
+    assert np.array_equal(mine["molids"], g["molids"])
+    assert np.array_equal(mine["temps"], g["temps"])
+    assert relerr(mine["press"], g["press"]) < 1e-14     # reference: after its identity spline resample
+    assert np.array_equal(mine["wn"], g["wn"])
+    ref = g["grid"]
+    assert np.array_equal(mine["o"] > 0, ref > 0)
+    assert relerr(mine["o"], ref) < TOL
+    tr.free_memory()
+    # the file just written drives a forward model (init path with an existing grid)
+    tr2 = api.Transit(case["cfg"])
+    models = synth.make_models(case, 2, seed=5)
+    spectra, status = tr2.run_batch(models)
+    assert (status == 0).all() and np.isfinite(spectra).all()
+    tr2.free_memory()
+
+
+def test_bins_and_profiles_vs_oracle(api, workdir):
+    """Bit-exact line -> oversampled-bin indices (incl. the co-add grouping) and Voigt profiles
+    within one float32 ulp of the oracle's long-double evaluation."""
+    import ctypes as C
+    from oracle import oracle as orc
+    case = cases.build_builder_case("build_h2o_ch4", workdir)
+    tr = api.Transit(argv=["transit", "-c", case["cfg"], "--justOpacity"])
+    L = api.lib()
+    B = orc.BuilderOracle(case["cfg"])
+    B.build(layers=[0], temps=[0], trace=True)
+    n = len(B.wl)
+    bins = np.zeros(n, dtype=np.int64)
+    got = L.bart_line_bins(bins.ctypes.data_as(C.POINTER(C.c_longlong)), n)
+    assert got == n
+    assert np.array_equal(bins, B.trace), "line-to-bin indices differ"
+    worst = 0.0
+    for (i, j) in ((0, 0), (5, 40), (30, 10), (59, 59), (20, 59), (59, 0)):
+        ref, ps = B.profile(i, j) if B.profiles[i * B.nLor + j] is None else \
+            (B.profiles[i * B.nLor + j], B.profsize[i * B.nLor + j])
+        hs = C.c_longlong()
+        out = np.zeros(2 * int(ps) + 1, dtype=np.float32)
+        api._check(L.bart_voigt_profile(i, j, out.ctypes.data_as(C.POINTER(C.c_float)), out.size, C.byref(hs)))
+        assert hs.value == ps
+        worst = max(worst, relerr(out, ref))
+    assert worst < 5e-7, worst
+    tr.free_memory()
+
+
+def test_temperature_sharded_build(api, workdir):
+    """T-sharded build (bart_build_opacity_slice): slices reassemble to the full grid bit for bit."""
+    case = cases.build_builder_case("build_ch4", workdir)
+    g = np.load(cases.golden_path("build_ch4"))
+    tr = api.Transit(argv=["transit", "-c", case["cfg"], "--justOpacity"])
+    L = api.lib()
+    from bart_b200 import synth
+    full = synth.read_opacity(case["opacity"], mmap=False)["o"]
+    nl, nt, nm, nw = full.shape
+    parts = []
+    for (a, b) in ((0, 2), (2, 3), (3, nt)):
+        out = np.zeros((nl, b - a, nm, nw))
+        api._check(L.bart_build_opacity_slice(a, b, out.ctypes.data_as(api.dp)))
+        parts.append(out)
+    assert np.array_equal(np.concatenate(parts, axis=1), full)
+    assert relerr(full, g["grid"]) < TOL
+    tr.free_memory()
