@@ -95,7 +95,8 @@ template <class T> struct DevBuf {
 struct State {
   bool init = false;
   int device = -1;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;          // compute (and default copy) stream
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;   // copy streams of the pipelined host path
   Options opt;
   Atmosphere atm;
   Molecules mol;
@@ -112,6 +113,8 @@ struct State {
   // batch buffers
   DevBuf<double> d_prof, d_tabs, d_spec, d_wts, d_tau, d_band, d_ext, d_flush;
   DevBuf<int> d_status, d_status_col, d_last;
+  int *h_status = nullptr;                 // pinned staging for per-model status
+  size_t h_status_cap = 0;
   DevBuf<double> d_kr0, d_kcloud, d_klogext;
   DevBuf<int> d_kflag;
   int knob_models = 0;
@@ -197,6 +200,8 @@ static void ensure_device() {
     fail("device %d (%s, sm_%d%d) is not a Blackwell sm_100 part; this library ships sm_100a "
          "code only", G.device, p.name, p.major, p.minor);
   CUDA_OK(cudaStreamCreateWithFlags(&G.stream, cudaStreamNonBlocking));
+  CUDA_OK(cudaStreamCreateWithFlags(&G.s_h2d, cudaStreamNonBlocking));
+  CUDA_OK(cudaStreamCreateWithFlags(&G.s_d2h, cudaStreamNonBlocking));
   CUDA_OK(cudaEventCreate(&G.t0));
   CUDA_OK(cudaEventCreate(&G.t1));
   const char *t = getenv("BART_NO_TMA");
@@ -443,43 +448,64 @@ static Knobs effective_knobs(int nmodels) {
   return k;
 }
 
-static void run_models_device(const double *d_prof, int nmodels, int n_in, double *d_spec) {
+// Launch the forward model for models [off, off+count) of a batch of `total` models whose
+// buffers (tables, status, keep arrays, per-model knobs) are indexed by the global model number.
+static void prepare_batch(int total, int n_in) {
   DevConfig &c = G.dc;
   if (!G.init || G.opt.justOpacity) fail("Transit init not run, please initialize transit.");
   if (n_in < (c.nspec + 1) * c.nlayer)
     fail("run_transit: input has %d values, expected (1+%d species) x %d layers = %d", n_in, c.nspec,
          c.nlayer, (c.nspec + 1) * c.nlayer);
-  if (nmodels <= 0) return;
-  G.d_tabs.ensure((size_t)nmodels * c.lay.stride());
-  G.d_status.ensure(nmodels);
-  G.d_status_col.ensure(nmodels);
+  G.d_tabs.ensure((size_t)total * c.lay.stride());
+  G.d_status.ensure(total);
+  G.d_status_col.ensure(total);
   if (G.keep) {
-    G.d_tau.ensure((size_t)nmodels * c.nwave * c.nlayer);
-    G.d_last.ensure((size_t)nmodels * c.nwave);
-    CUDA_OK(cudaMemsetAsync(G.d_tau.p, 0, (size_t)nmodels * c.nwave * c.nlayer * sizeof(double), G.stream));
+    G.d_tau.ensure((size_t)total * c.nwave * c.nlayer);
+    G.d_last.ensure((size_t)total * c.nwave);
+    CUDA_OK(cudaMemsetAsync(G.d_tau.p, 0, (size_t)total * c.nwave * c.nlayer * sizeof(double), G.stream));
   }
-  Knobs k = effective_knobs(nmodels);
+  if (!c.eclipse) G.d_wts.ensure((size_t)total * c.nlayer * (c.nlayer + 1) / 2);
+}
+
+static void launch_models(const double *d_prof, int off, int count, int total, int n_in, double *d_spec) {
+  DevConfig &c = G.dc;
+  if (count <= 0) return;
+  Knobs k = effective_knobs(total);
+  if (k.r0) k.r0 += off;
+  if (k.cloudtop) k.cloudtop += off;
+  if (k.scat_flag) k.scat_flag += off;
+  if (k.scat_logext) k.scat_logext += off;
+  double *tabs = G.d_tabs.p + (size_t)off * c.lay.stride();
+  int *status = G.d_status.p + off;
+  double *tau = G.keep ? G.d_tau.p + (size_t)off * c.nwave * c.nlayer : nullptr;
+  int *last = G.keep ? G.d_last.p + (size_t)off * c.nwave : nullptr;
   {
     KernelScope ks("atm_prep");
-    launch_atm_prep(c, k, d_prof, n_in, G.d_tabs.p, G.d_status.p, nmodels, G.stream);
+    launch_atm_prep(c, k, d_prof, n_in, tabs, status, count, G.stream);
     check_launch("atm_prep");
   }
   if (c.eclipse) {
     KernelScope ks("eclipse_column");
-    launch_eclipse(c, G.d_tabs.p, G.d_status.p, d_spec, G.d_tau.p, G.d_last.p, nmodels, G.keep, G.use_tma, G.stream);
+    launch_eclipse(c, tabs, status, d_spec, tau, last, count, G.keep, G.use_tma, G.stream);
     check_launch("eclipse_column");
   } else {
-    G.d_wts.ensure((size_t)nmodels * c.nlayer * (c.nlayer + 1) / 2);
-    CUDA_OK(cudaMemsetAsync(G.d_status_col.p, 0, nmodels * sizeof(int), G.stream));
+    int *scol = G.d_status_col.p + off;
+    CUDA_OK(cudaMemsetAsync(scol, 0, count * sizeof(int), G.stream));
     {
       KernelScope ks("transit_column");
-      launch_transit(c, G.d_tabs.p, G.d_wts.p, G.d_status.p, G.d_status_col.p, d_spec, G.d_tau.p,
-                     G.d_last.p, nmodels, G.keep, G.use_tma, G.stream);
+      launch_transit(c, tabs, G.d_wts.p + (size_t)off * c.nlayer * (c.nlayer + 1) / 2, status, scol,
+                     d_spec, tau, last, count, G.keep, G.use_tma, G.stream);
       check_launch("transit_column");
     }
-    launch_merge_status(G.d_status.p, G.d_status_col.p, nmodels, G.stream);
-    G.launches++;
+    launch_merge_status(status, scol, count, G.stream);
+    G.launches += 2;                 // transit_weights + merge_status
   }
+}
+
+static void run_models_device(const double *d_prof, int nmodels, int n_in, double *d_spec) {
+  if (nmodels <= 0) { prepare_batch(0, n_in); return; }
+  prepare_batch(nmodels, n_in);
+  launch_models(d_prof, 0, nmodels, nmodels, n_in, d_spec);
   G.last_batch = nmodels;
 }
 
@@ -649,17 +675,55 @@ int bart_run_batch(const double *profiles, int nmodels, int n_in, double *spectr
   if (nmodels <= 0) return 0;
   G.d_prof.ensure((size_t)nmodels * n_in);
   G.d_spec.ensure((size_t)nmodels * nw);
-  CUDA_OK(cudaMemcpyAsync(G.d_prof.p, profiles, (size_t)nmodels * n_in * 8, cudaMemcpyHostToDevice, G.stream));
-  run_models_device(G.d_prof.p, nmodels, n_in, G.d_spec.p);
-  if (n_out == nw)
-    CUDA_OK(cudaMemcpyAsync(spectra, G.d_spec.p, (size_t)nmodels * nw * 8, cudaMemcpyDeviceToHost, G.stream));
-  else
-    CUDA_OK(cudaMemcpy2DAsync(spectra, (size_t)n_out * 8, G.d_spec.p, (size_t)nw * 8, (size_t)nw * 8,
-                              nmodels, cudaMemcpyDeviceToHost, G.stream));
-  std::vector<int> st;
-  if (status)
-    CUDA_OK(cudaMemcpyAsync(status, G.d_status.p, nmodels * sizeof(int), cudaMemcpyDeviceToHost, G.stream));
+  prepare_batch(nmodels, n_in);
+  // Software pipeline over chunks of the batch: H2D of chunk k+1 and D2H of chunk k-1 run on
+  // their own streams (both copy engines) while chunk k computes.  Buffers are indexed by the
+  // global model number, so chunks never alias.
+  int nchunks = std::min(8, std::max(1, nmodels / 512));
+  if (G.keep || G.profile) nchunks = 1;
+  const int per = (nmodels + nchunks - 1) / nchunks;
+  std::vector<cudaEvent_t> ev_in(nchunks), ev_k(nchunks);
+  for (int c = 0; c < nchunks; c++) {
+    CUDA_OK(cudaEventCreateWithFlags(&ev_in[c], cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&ev_k[c], cudaEventDisableTiming));
+  }
+  cudaEvent_t ev_start;
+  CUDA_OK(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
+  CUDA_OK(cudaEventRecord(ev_start, G.stream));             // order after earlier work on the stream
+  CUDA_OK(cudaStreamWaitEvent(G.s_h2d, ev_start, 0));
+  for (int c = 0; c < nchunks; c++) {
+    const int off = c * per, cnt = std::min(per, nmodels - off);
+    if (cnt <= 0) break;
+    CUDA_OK(cudaMemcpyAsync(G.d_prof.p + (size_t)off * n_in, profiles + (size_t)off * n_in,
+                            (size_t)cnt * n_in * 8, cudaMemcpyHostToDevice, G.s_h2d));
+    CUDA_OK(cudaEventRecord(ev_in[c], G.s_h2d));
+    CUDA_OK(cudaStreamWaitEvent(G.stream, ev_in[c], 0));
+    launch_models(G.d_prof.p + (size_t)off * n_in, off, cnt, nmodels, n_in, G.d_spec.p + (size_t)off * nw);
+    CUDA_OK(cudaEventRecord(ev_k[c], G.stream));
+    CUDA_OK(cudaStreamWaitEvent(G.s_d2h, ev_k[c], 0));
+    if (n_out == nw)
+      CUDA_OK(cudaMemcpyAsync(spectra + (size_t)off * nw, G.d_spec.p + (size_t)off * nw,
+                              (size_t)cnt * nw * 8, cudaMemcpyDeviceToHost, G.s_d2h));
+    else
+      CUDA_OK(cudaMemcpy2DAsync(spectra + (size_t)off * n_out, (size_t)n_out * 8,
+                                G.d_spec.p + (size_t)off * nw, (size_t)nw * 8, (size_t)nw * 8, cnt,
+                                cudaMemcpyDeviceToHost, G.s_d2h));
+  }
+  if (status) {      // one small copy through pinned staging (a pageable target would block the loop)
+    if ((size_t)nmodels > G.h_status_cap) {
+      if (G.h_status) cudaFreeHost(G.h_status);
+      CUDA_OK(cudaMallocHost((void **)&G.h_status, (size_t)nmodels * sizeof(int)));
+      G.h_status_cap = nmodels;
+    }
+    CUDA_OK(cudaMemcpyAsync(G.h_status, G.d_status.p, nmodels * sizeof(int), cudaMemcpyDeviceToHost, G.s_d2h));
+  }
+  G.last_batch = nmodels;
+  cudaError_t e = cudaStreamSynchronize(G.s_d2h);
+  if (e != cudaSuccess) fail("CUDA execution failed: %s", cudaGetErrorString(e));
   finish_stream();
+  if (status) memcpy(status, G.h_status, nmodels * sizeof(int));
+  for (int c = 0; c < nchunks; c++) { cudaEventDestroy(ev_in[c]); cudaEventDestroy(ev_k[c]); }
+  cudaEventDestroy(ev_start);
   return 0;
   API_END_INT
 }

@@ -1,0 +1,158 @@
+"""Host-side mirror of the MC3 worker / master exchange around the forward model.
+
+* `BandModel` is the per-proposal input and output converter of code/BARTfunc.py:309-399,
+  vectorised over a batch of proposals: abundance scaling 10**p with H2/He renormalisation
+  (333-347), the temperature-bounds and sum-of-metals rejections (327-330, 339-344: rejected
+  proposals return a -1 band-flux vector), per-model radius / cloud-top / scattering knobs
+  (350-360), then ONE batched library call profiles -> band fluxes.
+* `partition` / `evaluate_generation` replace MC3's one-MPI-process-per-chain Scatter/Gather
+  (modules/MCcubed/MCcubed/mc/mcmc.py:583-585, code/BARTfunc.py:312,399): chains are split into
+  contiguous blocks, one per rank (= one per GPU); every rank evaluates its block as one batch
+  and a single all-gather per generation returns every chain's band fluxes to every rank.
+  The communicator is pluggable: `TorchComm` (torch.distributed, gloo on CPU in the tests, nccl
+  on GPUs) or `LibComm` (the library's own NCCL communicator on device buffers).
+
+The temperature-profile generator (code/PT.py) stays on the caller's side (SURVEY.md section
+8f, "next"): pass any callable `pt_func(pressure_bar, pt_params) -> T[layers]`.
+"""
+import numpy as np
+
+
+def partition(nchains, world, rank):
+    """Contiguous block of chains owned by `rank`: sizes differ by at most one."""
+    base, extra = divmod(nchains, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+class BandModel:
+    def __init__(self, transit, pressure_bar, species, abundances, molfit, pt_func, npt,
+                 tmin=400.0, tmax=3000.0, fit_radius=None, fit_cloud=False, fit_scattering=False):
+        """abundances[layer, species] in atmosphere-file order (bottom -> top), like
+        makeatm.readatm returns; parameters are ordered [PT..., radius?, cloudtop?, scattering?,
+        molfit...] as in BARTfunc.py:176-181."""
+        self.tr = transit
+        self.press = np.asarray(pressure_bar, dtype=float)
+        self.species = list(species)
+        self.base = np.asarray(abundances, dtype=float)
+        self.nlayer, self.nspec = self.base.shape
+        self.imol = [self.species.index(m) for m in molfit]
+        self.iH2, self.iHe = self.species.index("H2"), self.species.index("He")
+        self.imetals = [i for i, s in enumerate(self.species) if s not in ("H2", "He", "H-", "e-")]
+        self.ratio = self.base[:, self.iH2] / self.base[:, self.iHe]
+        self.pt_func, self.npt = pt_func, npt
+        self.tmin, self.tmax = tmin, tmax
+        self.nrad = 1 if (fit_radius if fit_radius is not None else not transit.eclipse) else 0
+        self.ncloud, self.nray = int(bool(fit_cloud)), int(bool(fit_scattering))
+
+    def profiles(self, params):
+        """params[M, npars] -> (profiles[M, (1+nspec)*nlayer], rejected[M] bool, knobs)."""
+        params = np.atleast_2d(np.asarray(params, dtype=float))
+        M = params.shape[0]
+        nl, ns = self.nlayer, self.nspec
+        prof = np.zeros((M, (ns + 1) * nl))
+        rejected = np.zeros(M, dtype=bool)
+        off = self.npt + self.nrad + self.ncloud + self.nray
+        for m in range(M):
+            T = np.asarray(self.pt_func(self.press[::-1], params[m, :self.npt]))[::-1]
+            if np.any(T < self.tmin) or np.any(T > self.tmax) or not np.all(np.isfinite(T)):
+                rejected[m] = True
+                continue
+            q = self.base.copy()
+            for k, i in enumerate(self.imol):
+                q[:, i] = self.base[:, i] * 10.0 ** params[m, off + k]
+            rest = 1.0 - q[:, self.imetals].sum(axis=1)
+            if np.any(rest < 0.0):
+                rejected[m] = True
+                continue
+            q[:, self.iH2] = self.ratio * rest / (1.0 + self.ratio)
+            q[:, self.iHe] = rest / (1.0 + self.ratio)
+            prof[m, :nl] = T
+            prof[m, nl:] = q.T.ravel()
+        knobs = {}
+        c = self.npt
+        if self.nrad:
+            knobs["refradius"] = params[:, c].copy(); c += 1
+        if self.ncloud:
+            knobs["cloudtop"] = params[:, c].copy(); c += 1
+        if self.nray:
+            knobs["scat_flag"] = np.ones(M, dtype=np.int32)
+            knobs["scat_logext"] = params[:, c].copy()
+        return prof, rejected, knobs
+
+    def evaluate(self, params):
+        """Band fluxes [M, nfilters]; rejected proposals get -1 in every band."""
+        prof, rejected, knobs = self.profiles(params)
+        M = prof.shape[0]
+        out = -np.ones((M, self.tr.nfilters))
+        ok = np.where(~rejected)[0]
+        if len(ok):
+            if knobs:
+                self.tr.set_batch_knobs(len(ok), **{k: v[ok] for k, v in knobs.items()})
+            flux, status = self.tr.bandflux_batch(prof[ok])
+            if knobs:
+                self.tr.set_batch_knobs(0)
+            flux[status != 0] = -1.0
+            out[ok] = flux
+        return out
+
+
+class TorchComm:
+    """All-gather through torch.distributed (backend gloo on CPU, nccl on GPUs)."""
+
+    def __init__(self, dist, device="cpu"):
+        self.dist, self.device = dist, device
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+
+    def allgather(self, local, counts):
+        import torch
+        width = local.shape[1]
+        pad = max(counts)
+        buf = torch.zeros((pad, width), dtype=torch.float64, device=self.device)
+        buf[:local.shape[0]] = torch.as_tensor(local, dtype=torch.float64)
+        outs = [torch.zeros_like(buf) for _ in range(self.world)]
+        self.dist.all_gather(outs, buf)
+        return np.concatenate([o[:n].cpu().numpy() for o, n in zip(outs, counts)], axis=0)
+
+
+class LibComm:
+    """All-gather on the library's own NCCL communicator (bart_comm_*), device buffers."""
+
+    def __init__(self, api, rank, world):
+        self.api, self.rank, self.world = api, rank, world
+        self.cap = 0
+        self.d_send = self.d_recv = None
+
+    def allgather(self, local, counts):
+        L = self.api.lib()
+        width = local.shape[1]
+        pad = max(counts)
+        n = pad * width
+        if n > self.cap:
+            for p in (self.d_send, self.d_recv):
+                if p:
+                    L.bart_dev_free(p)
+            self.d_send = L.bart_dev_alloc(n * 8)
+            self.d_recv = L.bart_dev_alloc(n * 8 * self.world)
+            self.cap = n
+        send = np.zeros((pad, width))
+        send[:local.shape[0]] = local
+        self.api._check(L.bart_memcpy_h2d(self.d_send, send.ctypes.data, n * 8))
+        self.api._check(L.bart_comm_allgather(self.d_send, self.d_recv, n))
+        recv = np.zeros((self.world, pad, width))
+        self.api._check(L.bart_memcpy_d2h(recv.ctypes.data, self.d_recv, n * 8 * self.world))
+        return np.concatenate([recv[r, :c] for r, c in enumerate(counts)], axis=0)
+
+
+def evaluate_generation(evaluate, params_all, comm):
+    """One MCMC generation: `params_all[nchains, npars]` (identical on every rank, as after MC3's
+    proposal step) -> band fluxes [nchains, nfilters] on every rank."""
+    params_all = np.atleast_2d(params_all)
+    nchains = params_all.shape[0]
+    lo, hi = partition(nchains, comm.world, comm.rank)
+    local = np.asarray(evaluate(params_all[lo:hi]), dtype=float)
+    if local.ndim == 1:
+        local = local[:, None]
+    counts = [partition(nchains, comm.world, r)[1] - partition(nchains, comm.world, r)[0]
+              for r in range(comm.world)]
+    return comm.allgather(local, counts)

@@ -54,7 +54,7 @@ class ClockSampler(threading.Thread):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 self.lines.append(line.strip())
         except Exception:
@@ -217,11 +217,11 @@ def main():
         if dist is not None:
             dist.barrier()
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(W):
         step_device()
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
     L.bart_profile_reset()
     L.bart_profile_enable(1)
     launches0 = L.bart_launch_count()
@@ -233,7 +233,7 @@ def main():
         step_device()
         ms.append(L.bart_timer_end())
     barrier()
-    launches = L.bart_launch_count() - launches0 - args.steps      # minus the flush kernels
+    launches = L.bart_launch_count() - launches0                   # L2-flush fills are not counted
     L.bart_profile_enable(0)
     stats = api.kernel_stats()
     total_ms = float(np.sum(ms))

@@ -62,6 +62,20 @@ def main():
                     lines.append("  %8s  %s" % (r[si], " | ".join(r[1:3])[:150]))
             except Exception as e:
                 lines.append("  (source page not parsed: %s)" % e)
+    if "--traffic-json" in sys.argv:
+        import json
+        jpath = sys.argv[sys.argv.index("--traffic-json") + 1]
+        models = int(sys.argv[sys.argv.index("--models") + 1])
+        r = rows[2]
+
+        def num(k):
+            v, u = float(r[hdr.index(k)]), units[hdr.index(k)]
+            return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+        json.dump({"kernel": r[hdr.index("Kernel Name")][:80], "models_per_launch": models,
+                   "dram_bytes_per_launch": num("dram__bytes_read.sum") + num("dram__bytes_write.sum"),
+                   "dram_bytes_read": num("dram__bytes_read.sum"), "dram_bytes_write": num("dram__bytes_write.sum"),
+                   "source": rep.split("/")[-1] + " (ncu --set full --clock-control none)"},
+                  open(jpath, "w"), indent=1)
     open(out, "w").write("\n".join(lines) + "\n")
     print("\n".join(lines[:70]))
 
