@@ -25,10 +25,8 @@ enum { REJ_TGRID = 1, REJ_TCIA = 2, REJ_SUMQ = 4, REJ_FEWPTS = 8 };
 
 // ---------------------------------------------------------------------------------------
 // fp64 exp and reciprocal for the column kernels.  libdevice's exp() costs ~45 issue slots per
-// call on sm_100 (half of them integer moves that materialise the polynomial coefficients),
-// and the eclipse column needs six per (layer, wavenumber) cell.  This version keeps the
-// coefficients as immediate/constant-bank operands of the FMAs, uses a Cody-Waite reduction and
-// builds the 2^n scaling in the exponent field.
+// call on sm_100 and the column kernels need several per (layer, wavenumber) cell, so the fp64
+// pipe (16 lanes per SM sub-partition) is what bounds them.
 BART_HD double bits_to_double(long long b) {
 #ifdef __CUDA_ARCH__
   return __longlong_as_double(b);
@@ -43,70 +41,131 @@ BART_HD long long double_to_bits(double d) {
   long long b; memcpy(&b, &d, 8); return b;
 #endif
 }
+BART_HD int hi_word(double d) { return (int)(double_to_bits(d) >> 32); }
 
-// 16-byte pair load from a table record (records and pair offsets are 16-byte aligned)
+// 16-byte pair load (records, pair offsets and grid samples are 16-byte aligned)
 struct alignas(16) D2 { double x, y; };
 BART_HD D2 ld2(const double *p) { return *reinterpret_cast<const D2 *>(p); }
+BART_HD D2 ld2b(const char *p) { return *reinterpret_cast<const D2 *>(p); }
+BART_HD double ld1b(const char *p) { return *reinterpret_cast<const double *>(p); }
 
-// Table-driven variant used by the column kernels: exp(x) = 2^n * 2^(j/16) * e^r with
-// m = round(16 x / ln2) = 16 n + j and |r| <= ln2/32, so a degree-6 polynomial suffices
-// (truncation 4e-16) -- 11 fp64 instructions instead of 19.  `tab16` holds 2^(j/16), j = 0..15,
-// in shared memory: 128 bytes = one full bank row, so divergent lanes never conflict.
-// GUARD_LO: x may be below -708 (result 0); GUARD_HI: x may exceed 709 (result saturates).  The
-// guards are selects on the result (cheaper than clamping the argument); out-of-range arguments
-// only ever produce a discarded product.
-constexpr int kExpTabSize = 16;
-BART_HD void fill_exp_table(double *tab16) {
-  // 2^(j/16) correctly rounded
-  const double v[kExpTabSize] = {
-      1.0, 1.0442737824274138403, 1.0905077326652576592, 1.1387886347566916537,
-      1.1892071150027210667, 1.2418578120734840486, 1.2968395546510096659, 1.3542555469368927283,
-      1.4142135623730950488, 1.4768261459394993114, 1.5422108254079408236, 1.6104903319492543082,
-      1.6817928305074290861, 1.7562521603732994831, 1.8340080864093424635, 1.9152065613971472939};
-  for (int j = 0; j < kExpTabSize; j++) tab16[j] = v[j];
+// Warp-uniform decisions of the column kernels.  On the host (tests/cpu_emu, one column at a
+// time) they degenerate to the column's own predicate.
+#ifdef __CUDA_ARCH__
+#define BART_WARP_ALL(p) (__all_sync(0xffffffffu, (p)) != 0)
+#define BART_WARP_ANY(p) (__any_sync(0xffffffffu, (p)) != 0)
+#else
+#define BART_WARP_ALL(p) (p)
+#define BART_WARP_ANY(p) (p)
+#endif
+
+// exp(x) = 2^n 2^(j/N) e^(r ln2/N) with y = x N/ln2 = (N n + j) + r, |r| <= 1/2, N = 128:
+// |r ln2/N| <= 2.7e-3, so a degree-4 polynomial is exact to 1.2e-15.  The caller supplies y as a
+// product a*b (one factor usually a constant that already carries N/ln2), so the reduction is two
+// FMAs with the SAME exact product: t = a b + 1.5 2^52 rounds y to the nearest integer m (low
+// word of t), r = a b - m is exact.  8 fp64 instructions per exp in all.
+// The table (shared memory, 1 KB) holds the bit patterns of 2^(j/N) with (j << 13) subtracted
+// from the high word, so that adding (m << 13) -- one integer multiply-add -- yields the high word
+// of 2^n 2^(j/N) without masking j out of m.  Arguments must satisfy |x| <= 708 (callers clamp).
+constexpr int kExpBits = 7;
+constexpr int kExpTabSize = 1 << kExpBits;
+constexpr double kExpScale = 184.6649652337873;                 // N / ln2
+constexpr double kExpYmax = 700.0 * kExpScale;                   // clamp for y
+constexpr double kExpQ1 = 0.0054152123481245725;                 // (ln2/N)^k / k!
+constexpr double kExpQ2 = 1.4662262387640425e-05;
+constexpr double kExpQ3 = 2.646642144433097e-08;
+constexpr double kExpQ4 = 3.583032305400251e-11;
+
+static const unsigned long long kExpTabBits[kExpTabSize] = {
+#include "exp_table.inc"
+};
+// entry j as stored in the kernels' shared-memory table
+inline unsigned long long exp_table_entry(int j) {
+  return kExpTabBits[j] - ((unsigned long long)j << (32 + 20 - kExpBits));
+}
+inline void fill_exp_table(unsigned long long *tab) {
+  for (int j = 0; j < kExpTabSize; j++) tab[j] = exp_table_entry(j);
 }
 
-template <bool GUARD_LO, bool GUARD_HI>
-BART_HD double fast_exp_t(double x, const double *tab16) {
+// exp(a*b*ln2/N) + addend   (addend 0, or -1 for the Planck denominator)
+BART_HD double exp_core(double a, double b, const unsigned long long *tab, double addend) {
   const double MAGIC = 6755399441055744.0;                        // 1.5 * 2^52
-  const double t = fma(x, 23.083120654223414518, MAGIC);          // low word = round(16 x / ln2)
+  const double t = fma(a, b, MAGIC);
   const double kf = t - MAGIC;
-  double r = fma(kf, -4.33216987730702385306e-02, x);             // (ln2 high part) / 16, exact product
-  r = fma(kf, -1.19263433079411731251e-11, r);                    // (ln2 low part) / 16
-  double p = 1.38888888888888888889e-03;                          // 1/6!
-  p = fma(p, r, 8.33333333333333333333e-03);
-  p = fma(p, r, 4.16666666666666666667e-02);
-  p = fma(p, r, 1.66666666666666666667e-01);
-  p = fma(p, r, 0.5);
+  const double r = fma(a, b, -kf);
+  double p = kExpQ4;
+  p = fma(p, r, kExpQ3);
+  p = fma(p, r, kExpQ2);
+  p = fma(p, r, kExpQ1);
   p = fma(p, r, 1.0);
-  p = fma(p, r, 1.0);
-  const int m = (int)double_to_bits(t);                           // low word of t
-  const long long sc = double_to_bits(tab16[m & (kExpTabSize - 1)]) + ((long long)(m >> 4) << 52);
-  double res = p * bits_to_double(sc);
-  if (GUARD_LO) res = x < -708.0 ? 0.0 : res;
-  if (GUARD_HI) res = x > 709.0 ? 1.0e308 : res;
-  return res;
+#ifdef __CUDA_ARCH__
+  const int m = __double2loint(t);
+  const uint2 e = *reinterpret_cast<const uint2 *>(tab + (m & (kExpTabSize - 1)));
+  const double sc = __hiloint2double((int)(e.y + ((unsigned)m << (20 - kExpBits))), (int)e.x);
+#else
+  const int m = (int)double_to_bits(t);
+  const unsigned long long e = tab[m & (kExpTabSize - 1)];
+  const unsigned hi = (unsigned)(e >> 32) + ((unsigned)m << (20 - kExpBits));
+  const double sc = bits_to_double((long long)(((unsigned long long)hi << 32) | (e & 0xffffffffull)));
+#endif
+  return fma(p, sc, addend);
 }
-BART_HD double fast_exp(double x, const double *t) { return fast_exp_t<true, true>(x, t); }
-BART_HD double fast_exp_neg(double x, const double *t) { return fast_exp_t<true, false>(x, t); }  // x <= 0
-BART_HD double fast_exp_pos(double x, const double *t) { return fast_exp_t<false, true>(x, t); }  // x >= 0
+// exp(x) for x <= 0, any magnitude (0 below -700 up to 1e-304: the argument is clamped)
+BART_HD double fast_exp_neg(double x, const unsigned long long *tab) {
+  return exp_core(x < -700.0 ? -700.0 : x, kExpScale, tab, 0.0);
+}
+// exp(x), saturating: |x| clamped to 700
+BART_HD double fast_exp(double x, const unsigned long long *tab) {
+  x = x < -700.0 ? -700.0 : x;
+  x = x > 700.0 ? 700.0 : x;
+  return exp_core(x, kExpScale, tab, 0.0);
+}
 
-// 1/d for finite d > 0: hardware seed (>= 20 bits) + three Newton steps (full fp64 precision); the compiler's IEEE divide
-// is ~3x the issue slots because of its special-case branches.
+// 1/d for finite d > 0: hardware seed (MUFU.RCP64H) + two Newton steps; the compiler's IEEE
+// divide is ~3x the issue slots because of its special-case branches.
 BART_HD double fast_rcp(double d) {
 #ifdef __CUDA_ARCH__
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
-  double e = fma(-d, r, 1.0);
-  r = fma(r, e, r);
+  double e = fma(-d, r, 1.0);      // seed: >= 20 bits
+  r = fma(r, e, r);                // 2^-40
   e = fma(-d, r, 1.0);
-  r = fma(r, e, r);
-  e = fma(-d, r, 1.0);
-  r = fma(r, e, r);
+  r = fma(r, e, r);                // below rounding
   return r;
 #else
   return 1.0 / d;
 #endif
+}
+
+// Angle constants of the eclipse geometry (filled on the host at init):
+//   D(tau) = sum_a wgt[a] exp(-tau inv_mu[a]), the hemispheric transmission that weights the
+//   Planck function (eclipse_intens + flux, eclipse.c:117-160,242-287, are linear in the
+//   per-angle intensities, so the angle sum can be taken before the layer integral).
+//   taylor[k] = sum_a wgt[a] (-inv_mu[a])^k / k!  serves tau <= tau_small, where the truncation
+//   error (0.3^12/12! = 1e-15) is below rounding.
+inline void fill_angle_consts(DevConfig &c) {
+  double smax = 0.0;
+  for (int a = 0; a < c.nang; a++) {
+    c.exp_a[a] = c.inv_mu[a] * kExpScale;
+    if (c.inv_mu[a] > smax) smax = c.inv_mu[a];
+  }
+  double fact = 1.0;
+  for (int k = 0; k < kTaylorN; k++) {
+    if (k > 0) fact *= k;
+    long double acc = 0.0L;
+    for (int a = 0; a < c.nang; a++) {
+      long double pw = 1.0L;
+      for (int i = 0; i < k; i++) pw *= -(long double)c.inv_mu[a];
+      acc += (long double)c.wgt[a] * pw;
+    }
+    c.taylor[k] = (double)(acc / fact);
+  }
+  // D(0) is evaluated by both branches: make them agree to the bit (sequential sum, like the loop)
+  double d0 = 0.0;
+  for (int a = 0; a < c.nang; a++) d0 = fma(1.0, c.wgt[a], d0);
+  c.taylor[0] = d0;
+  c.tau_small = smax > 0 ? 0.3 / smax : 0.0;
+  c.tau_clamp = smax > 0 ? 700.0 / smax : 700.0;
 }
 
 struct KnobVals {
@@ -227,7 +286,7 @@ BART_HD int prep_table_row(const DevConfig &c, const KnobVals &kv, int d, const 
   if (T < c.gtemp[0] || T > c.gtemp[c.ntemp - 1]) status |= REJ_TGRID;
   const int it = bracket(c.gtemp, c.ntemp, T);
   const double t0 = c.gtemp[it], t1 = c.gtemp[it + 1];
-  row[L.GOFF] = bits_to_double((((long long)l * c.ntemp + it) * c.ngmol) * (long long)c.nwave);
+  row[L.GOFF] = bits_to_double((((long long)l * c.ntemp + it) * c.gms) * (long long)c.nwave * 8);
   for (int m = 0; m < c.ngmol; m++) {
     const double r = rho[(size_t)c.gmol_spec[m] * rho_stride + l];
     row[L.W + 2 * m] = r * (t1 - T) / (t1 - t0);
@@ -257,7 +316,7 @@ BART_HD int prep_table_row(const DevConfig &c, const KnobVals &kv, int d, const 
       cz1 = dx * (-h / 6.0 + dx * dx / (6.0 * h));
     }
     double *cr = row + L.cia(f);
-    cr[0] = bits_to_double((long long)k * c.nwave);
+    cr[0] = bits_to_double((long long)k * c.nwave * 16);
     cr[1] = (double)k;
     cr[2] = cy0 * dens;
     cr[3] = cy1 * dens;
@@ -308,47 +367,81 @@ BART_HD int prep_table_row(const DevConfig &c, const KnobVals &kv, int d, const 
 }
 
 // ---------------------------------------------------------------------------------------
+// Per-column base addresses into the grid and the CIA tables (byte pointers: the table records
+// carry byte offsets, so a cell address is one 64-bit add).
+struct ColPtrs {
+  const char *g;
+  const char *cia[kMaxCia];
+};
+template <int NCIA>
+BART_HD ColPtrs col_ptrs(const DevConfig &c, int w) {
+  ColPtrs P;
+  P.g = reinterpret_cast<const char *>(c.grid) + (size_t)w * c.gms * 8;
+#pragma unroll
+  for (int f = 0; f < (NCIA >= 0 ? NCIA : kMaxCia); f++)
+    P.cia[f] = f < c.ncia ? reinterpret_cast<const char *>(c.ciaPQ[f]) + (size_t)w * 16 : nullptr;
+  return P;
+}
+
 // Total extinction of one (depth, wavenumber) cell: opacity-grid lookup with temperature
 // interpolation and abundance scaling (extinction.c:534-581), + scattering + cloud + CIA in the
 // reference's summation order (tau.c:231-232).  `row` is the depth's table record.  NMOL / NCIA
-// are compile-time counts (0 = take them from the configuration at run time).
+// are compile-time counts (NMOL 0 / NCIA -1 = take them from the configuration at run time).
+// With NMOL > 1 a sample's molecules arrive as 16-byte pairs (LDG.128) from each of the two
+// bracketing temperature planes.
 template <int NMOL, int NCIA>
-BART_HD double cell_extinction(const DevConfig &c, const double *row, int w, double wn4,
+BART_HD double cell_extinction(const DevConfig &c, const ColPtrs &P, const double *row, double wn4,
                                bool mol_only) {
   typedef TabLayout L;
   const int ngmol = NMOL > 0 ? NMOL : c.ngmol;
   const int ncia = NCIA >= 0 ? NCIA : c.ncia;
-  const size_t nw = (size_t)c.nwave;
-  const D2 head = ld2(row + L::INVT);                        // (1/T, grid offset)
-  const double *lo = c.grid + double_to_bits(head.y) + w;
-  const double *hi = lo + (size_t)ngmol * nw;
-  double e;
-  {
+  const size_t plane = (size_t)c.nwave * c.gms * 8;
+  const char *lo = P.g + double_to_bits(row[L::GOFF]);
+  const char *hi = lo + plane;
+  double e = 0.0;
+  if (NMOL == 1) {
     const D2 wt = ld2(row + L::W);
-    e = wt.x * lo[0] + wt.y * hi[0];
-  }
+    e = wt.x * ld1b(lo);
+    e = fma(wt.y, ld1b(hi), e);
+  } else if (NMOL > 1) {
 #pragma unroll
-  for (int m = 1; m < (NMOL > 0 ? NMOL : kMaxGridMol); m++)
-    if (m < ngmol) {
-      const D2 wt = ld2(row + L::W + 2 * m);
-      e += wt.x * lo[m * nw] + wt.y * hi[m * nw];
+    for (int q = 0; q < (NMOL + 1) / 2; q++) {
+      const D2 a = ld2b(lo + 16 * q), b = ld2b(hi + 16 * q);
+      const D2 w0 = ld2(row + L::W + 4 * q);
+      e = q == 0 ? w0.x * a.x : fma(w0.x, a.x, e);
+      e = fma(w0.y, b.x, e);
+      if (2 * q + 1 < NMOL) {
+        const D2 w1 = ld2(row + L::W + 4 * q + 2);
+        e = fma(w1.x, a.y, e);
+        e = fma(w1.y, b.y, e);
+      }
     }
+  } else {
+    for (int m = 0; m < ngmol; m++) {
+      const D2 wt = ld2(row + L::W + 2 * m);
+      e = fma(wt.x, ld1b(lo + 8 * m), e);
+      e = fma(wt.y, ld1b(hi + 8 * m), e);
+    }
+  }
   if (mol_only) return e;
   double ecs = 0.0;
   const double *cr = row + L::W + 2 * ngmol;
+  const size_t cplane = (size_t)c.nwave * 16;
 #pragma unroll
   for (int f = 0; f < (NCIA >= 0 ? NCIA : kMaxCia); f++) {
     if (f < ncia) {
-      const long long off = double_to_bits(cr[6 * f]) + w;
-      const double *P = c.ciaP[f] + off;
-      const double *Q = c.ciaQ[f] + off;
+      const char *pq = P.cia[f] + double_to_bits(cr[6 * f]);
+      const D2 k0 = ld2b(pq), k1 = ld2b(pq + cplane);          // (value, d2/dT2) at T_k, T_k+1
       const D2 cy = ld2(cr + 6 * f + 2), cz = ld2(cr + 6 * f + 4);
-      const double v = cy.x * P[0] + cy.y * P[nw] + cz.x * Q[0] + cz.y * Q[nw];
-      if (v > 0) ecs += v;
+      double v = cy.x * k0.x;
+      v = fma(cy.y, k1.x, v);
+      v = fma(cz.x, k0.y, v);
+      v = fma(cz.y, k1.y, v);
+      if (hi_word(v) > 0) ecs += v;                            // v > 0 (crosssec.c:330)
     }
   }
-  const D2 sc = ld2(row + L::SCAT);                          // (scattering coefficient, cloud)
-  return e + sc.x * wn4 + sc.y + ecs;
+  const D2 sc = ld2(row + L::SCAT);                            // (scattering coefficient, cloud)
+  return fma(sc.x, wn4, e) + sc.y + ecs;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -358,10 +451,17 @@ BART_HD double cell_extinction(const DevConfig &c, const double *row, int w, dou
 //        reference re-integrates from each depth to the top; its panels are always aligned to
 //        the top sample, numerical.c:454-525, so tau(d) = sum of completed panels (+ one
 //        trapezoid when d is odd));  stop at the first tau > toomuch (tau.c:277-287).
-//   intensity: eclipse_intens eclipse.c:117-160; flux eclipse.c:242-287.
+//   intensity + flux: eclipse_intens eclipse.c:117-160 and flux eclipse.c:242-287 are
+//        F = pi sum_a wgt_a [B_L d_L^a - 1/2 sum_i (d_{i+1}^a - d_i^a)(B_{i+1} + B_i)], d_i^a =
+//        exp(-tau_i/mu_a).  The angle sum commutes with the layer sum, so the column carries
+//        D_i = sum_a wgt_a d_i^a: F = pi [B_L D_L - 1/2 sum_i (D_{i+1} - D_i)(B_{i+1} + B_i)].
+//        While every column of the warp has tau <= tau_small, D comes from its Maclaurin series
+//        (one polynomial instead of one exp per angle).
+// All 32 lanes of a warp must enter together (warp votes); a column that has passed its `last`
+// layer idles until the warp's deepest column is done.
 template <int NMOL, int NCIA, int NANG, bool KEEP>
-BART_HD double eclipse_column(const DevConfig &c, const double *tab, const double *etab, int w,
-                              double *tau_keep, int *last_keep) {
+BART_HD double eclipse_column(const DevConfig &c, const double *tab, const unsigned long long *etab,
+                              int w, double *tau_keep, int *last_keep) {
   typedef TabLayout L;
   const int nl = c.nlayer;
   const int nf = c.lay.nf();
@@ -369,46 +469,67 @@ BART_HD double eclipse_column(const DevConfig &c, const double *tab, const doubl
   const double wn = c.wn[w];
   const double wn4 = (wn * wn) * (wn * wn);
   const double c1 = 2.0 * cH * (wn * wn * wn) * cLS * cLS;
-  const double c2 = cH * wn * cLS / cKB;
-  double trap[NANG > 0 ? NANG : kMaxAng], dprev[NANG > 0 ? NANG : kMaxAng];
-#pragma unroll
-  for (int a = 0; a < (NANG > 0 ? NANG : kMaxAng); a++) { trap[a] = 0.0; dprev[a] = 1.0; }
-  double S = 0.0, er1 = 0.0, er2 = 0.0, Bprev = 0.0;
+  const double c2n = cH * wn * cLS / cKB * kExpScale;          // Planck exponent x N/ln2, per 1/T
+  const double invt_cap = kExpYmax / c2n;                      // keeps the exponent below 700
+  const int invt_cap_hi = hi_word(invt_cap);
+  const int small_hi = hi_word(c.tau_small), clamp_hi = hi_word(c.tau_clamp);
+  const ColPtrs P = col_ptrs<NCIA>(c, w);
+
+  // depth 0 (top): tau = 0, D = D(0)
+  double er1 = cell_extinction<NMOL, NCIA>(c, P, tab, wn4, false), er2 = 0.0;
+  double S = 0.0, trap = 0.0, Dprev = c.taylor[0], Bprev;
+  {
+    double it = tab[L::INVT];
+    if (hi_word(it) > invt_cap_hi) it = invt_cap;
+    Bprev = c1 * fast_rcp(exp_core(c2n, it, etab, -1.0));
+  }
+  if (KEEP) tau_keep[0] = 0.0;
   int last = nl - 1;
-  const double *row = tab;
-  for (int d = 0; d < nl; d++, row += nf) {
-    const double er = cell_extinction<NMOL, NCIA>(c, row, w, wn4, false);
+  bool alive = !(0.0 > c.toomuch);
+  if (!alive) last = 0;
+
+  auto step = [&](const double *row, int d, bool odd) {
+    const double er = cell_extinction<NMOL, NCIA>(c, P, row, wn4, false);
     double tau;
-    if (d == 0) tau = 0.0;
+    if (odd) tau = fma(row[L::TR], er + er1, S);
     else {
-      const D2 s1 = ld2(row + L::SA), s2 = ld2(row + L::SC);   // (SA, SB), (SC, TR)
-      if (d & 1) tau = S + s2.y * (er + er1);
-      else {
-        S += s1.x * er + s1.y * er1 + s2.x * er2;
-        tau = S;
-      }
+      const D2 s1 = ld2(row + L::SA);                          // (SA, SB)
+      S = fma(s1.x, er, fma(s1.y, er1, fma(row[L::SC], er2, S)));
+      tau = S;
     }
     er2 = er1; er1 = er;
-    if (KEEP) tau_keep[d] = tau;
-    const double B = c1 * fast_rcp(fast_exp_pos(c2 * row[L::INVT], etab) - 1.0);
-    const double Bs = B + Bprev;
+    double it = row[L::INVT];
+    if (hi_word(it) > invt_cap_hi) it = invt_cap;
+    const double B = c1 * fast_rcp(exp_core(c2n, it, etab, -1.0));
+    double D;
+    if (BART_WARP_ALL(!alive || hi_word(tau) < small_hi)) {
+      D = c.taylor[kTaylorN - 1];
 #pragma unroll
-    for (int a = 0; a < (NANG > 0 ? NANG : kMaxAng); a++) {
-      if (a < nang) {
-        const double dt = fast_exp_neg(-tau * c.inv_mu[a], etab);
-        trap[a] += (dt - dprev[a]) * Bs;       // d = 0: dprev = 1 = dt, contributes exactly 0
-        dprev[a] = dt;
-      }
+      for (int k = kTaylorN - 2; k >= 0; k--) D = fma(D, tau, c.taylor[k]);
+    } else {
+      const double tc = hi_word(tau) >= clamp_hi ? c.tau_clamp : tau;
+      D = 0.0;
+#pragma unroll
+      for (int a = 0; a < (NANG > 0 ? NANG : kMaxAng); a++)
+        if (a < nang) D = fma(exp_core(tc, -c.exp_a[a], etab, 0.0), c.wgt[a], D);
     }
-    Bprev = B;
-    if (tau > c.toomuch) { last = d; break; }
+    if (alive) {
+      if (KEEP) tau_keep[d] = tau;
+      trap = fma(D - Dprev, B + Bprev, trap);
+      Dprev = D; Bprev = B;
+      if (tau > c.toomuch) { last = d; alive = false; }
+    }
+  };
+
+  const double *row = tab + nf;
+  for (int d = 1; d < nl; d += 2, row += 2 * nf) {
+    if (!BART_WARP_ANY(alive)) break;
+    step(row, d, true);
+    if (d + 1 >= nl || !BART_WARP_ANY(alive)) break;
+    step(row + nf, d + 1, false);
   }
   if (KEEP) *last_keep = last;
-  double flux = 0.0;
-#pragma unroll
-  for (int a = 0; a < (NANG > 0 ? NANG : kMaxAng); a++)
-    if (a < nang) flux += cPI * (Bprev * dprev[a] - 0.5 * trap[a]) * c.wgt[a];
-  return flux;
+  return cPI * (Bprev * Dprev - 0.5 * trap);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -456,7 +577,7 @@ BART_HD void transit_weight_row(const DevConfig &c, const double *tab, int d, do
 // (modulation1, slantpath.c:350-436) as a top-aligned Simpson scan over impact parameter.
 // `er` is per-thread scratch with stride `es` (shared memory in the kernel).
 template <int NMOL, int NCIA, bool KEEP>
-BART_HD double transit_column(const DevConfig &c, const double *tab, const double *etab,
+BART_HD double transit_column(const DevConfig &c, const double *tab, const unsigned long long *etab,
                               const double *wts, int w, double *er, int es, double *tau_keep,
                               int *last_keep, int *status) {
   typedef TabLayout L;
@@ -467,9 +588,10 @@ BART_HD double transit_column(const DevConfig &c, const double *tab, const doubl
   double S = 0.0, f1 = 0.0, f2 = 0.0, tau = 0.0;
   int last = nl - 1;
   int d;
+  const ColPtrs P = col_ptrs<NCIA>(c, w);
   for (d = 0; d < nl; d++) {
     const double *row = tab + (size_t)d * nf;
-    er[(size_t)d * es] = cell_extinction<NMOL, NCIA>(c, row, w, wn4, false);
+    er[(size_t)d * es] = cell_extinction<NMOL, NCIA>(c, P, row, wn4, false);
     const double *wr = wts + (size_t)d * (d + 1) / 2;
     tau = 0.0;
     for (int i = 0; i <= d; i++) tau += wr[i] * er[(size_t)i * es];

@@ -1,10 +1,14 @@
 // device.cuh -- device-side data model shared by kernels.cu / builder.cu / transit.cu.
 //
 // HBM layout (all fp64 unless stated):
-//   grid   o[layer][temp][mol][wave]   the opacity file's own order (opacity.c:418-421): the
-//                                      wavenumber axis is contiguous, so thread <-> wavenumber
-//                                      gives perfectly coalesced streams with no transpose.
-//   ciaP/ciaQ[file][temp][wave]        CIA tables pre-folded through the wavenumber spline.
+//   grid   o[layer][temp][wave][gms]   the opacity file (o[layer][temp][mol][wave],
+//                                      opacity.c:418-421) with the molecule axis moved innermost
+//                                      at upload time (gms = molecules per sample, padded to an
+//                                      even count when > 1): thread <-> wavenumber reads one
+//                                      (layer, temperature) plane as a contiguous stream of
+//                                      16-byte vector loads carrying all molecules of a sample.
+//   ciaPQ[file][temp][wave][2]         CIA tables pre-folded through the wavenumber spline
+//                                      (value, temperature second derivative) interleaved.
 //   profiles[model][(1+nspec)*nlayer]  the caller's per-model input, verbatim.
 //   tab[model][field][depth]           per-model, per-layer coefficients written by atm_prep and
 //                                      staged into shared memory (one bulk-async copy) by the
@@ -25,15 +29,16 @@ constexpr int kMaxGridMol = 16;
 constexpr int kMaxCia = 4;
 constexpr int kMaxAng = 16;
 constexpr int kMaxSpec = 64;
+constexpr int kTaylorN = 12;   // series degree 11
 
 // One model table = nlayer records of `nf()` doubles, one record per depth (0 = top layer), so a
 // column kernel reads everything it needs for a layer from one contiguous, 16-byte aligned
 // shared-memory record with compile-time offsets (warp-wide broadcast loads, LDS.128 for pairs).
-//   [0] 1/T      [1] grid offset (int64 bits) of plane (layer, it)   [2] scattering coef (x wn^4)
+//   [0] 1/T      [1] byte offset (int64 bits) of grid plane (layer, it)   [2] scattering coef (x wn^4)
 //   [3] cloud    [4..6] Simpson panel coefficients   [7] trapezoid half-width
 //   [8] T        [9] radius (file units)
 //   [10+2m, 11+2m]  W0, W1 of grid molecule m:  rho*(t1-T)/(t1-t0), rho*(T-t0)/(t1-t0)
-//   [cia(f) .. +5]  CIA file f: table offset (int64 bits), bracket index, 4 cubic coefficients
+//   [cia(f) .. +5]  CIA file f: table byte offset (int64 bits), bracket index, 4 cubic coefficients
 struct TabLayout {
   int nl, ngmol, ncia;
   static constexpr int INVT = 0, GOFF = 1, SCAT = 2, CLOUD = 3, SA = 4, SB = 5, SC = 6, TR = 7,
@@ -45,6 +50,7 @@ struct TabLayout {
 
 struct DevConfig {
   int nlayer, nspec, nwave, ntemp, ngmol, ncia, nang;
+  int gms;                  // grid doubles per wavenumber sample (ngmol, padded to even when > 1)
   int eclipse, transparent;
   const double *grid;
   const double *gtemp;
@@ -53,8 +59,7 @@ struct DevConfig {
   const double *mass;       // [nspec]
   const double *pol;        // [nspec]
   int gmol_spec[kMaxGridMol];
-  const double *ciaP[kMaxCia];
-  const double *ciaQ[kMaxCia];
+  const double *ciaPQ[kMaxCia];
   const double *ciaT[kMaxCia];
   int cia_nt[kMaxCia];
   int cia_nspec[kMaxCia];
@@ -63,6 +68,11 @@ struct DevConfig {
   double inv_mu[kMaxAng];   // 1/cos(angle)
   double wgt[kMaxAng];      // sin^2(g_{a+1}) - sin^2(g_a)
   double inv_srad2;         // 1/R*^2 (cm^-2)
+  // hemispheric transmission D(tau) = sum_a wgt[a] exp(-tau inv_mu[a]) (column_math.cuh):
+  double exp_a[kMaxAng];    // inv_mu[a] * N/ln2, the exponent in units of the exp table
+  double taylor[kTaylorN];  // Maclaurin coefficients of D, used while tau <= tau_small
+  double tau_small;         // warp-uniform switch to the series
+  double tau_clamp;         // exp arguments stay above -700
   TabLayout lay;
 };
 

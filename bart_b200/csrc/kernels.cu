@@ -58,9 +58,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 
 // Stage one model's table into shared memory.  Bulk-async when the size allows (multiple of 16 B,
 // always true by TabLayout::stride), else a cooperative copy.
+// exp table entries (column_math.cuh exp_table_entry) in global memory, copied to shared per CTA
+__device__ unsigned long long g_exp_table[kExpTabSize];
+
 __device__ __forceinline__ void stage_table(double *s_tab, const double *g_tab, int ndoubles,
-                                            uint64_t *bar, bool use_tma, double *s_etab = nullptr) {
-  if (s_etab && threadIdx.x == 32) fill_exp_table(s_etab);
+                                            uint64_t *bar, bool use_tma,
+                                            unsigned long long *s_etab = nullptr) {
+  if (s_etab)
+    for (int j = threadIdx.x; j < kExpTabSize; j += blockDim.x) s_etab[j] = g_exp_table[j];
   if (use_tma) {
     if (threadIdx.x == 0) { mbar_init(bar, 1); fence_mbar_init(); }
     __syncthreads();
@@ -125,8 +130,8 @@ eclipse_column_kernel(DevConfig c, const double *__restrict__ tabs, const int *_
                       int *__restrict__ last_keep, int nmodels, int use_tma) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar;
-  double *s_etab = reinterpret_cast<double *>(smem_raw);       // 2^(j/16), one 128-byte bank row
-  double *s_tab = s_etab + kExpTabSize;
+  unsigned long long *s_etab = reinterpret_cast<unsigned long long *>(smem_raw);   // exp table, 1 KB
+  double *s_tab = reinterpret_cast<double *>(s_etab + kExpTabSize);
   const int m = blockIdx.x % nmodels;           // model-fastest: neighbours share grid columns
   const int tile = blockIdx.x / nmodels;
   const int w = tile * kColThreads + threadIdx.x;
@@ -136,11 +141,13 @@ eclipse_column_kernel(DevConfig c, const double *__restrict__ tabs, const int *_
     return;
   }
   stage_table(s_tab, tabs + (size_t)m * nd, nd, &bar, use_tma != 0, s_etab);
-  if (w >= c.nwave) return;
-  double *tk = KEEP ? tau_keep + ((size_t)m * c.nwave + w) * c.nlayer : nullptr;
-  int *lk = KEEP ? last_keep + (size_t)m * c.nwave + w : nullptr;
-  spectra[(size_t)m * c.nwave + w] =
-      eclipse_column<NMOL, NCIA, NANG, KEEP>(c, s_tab, s_etab, w, tk, lk);
+  // lanes past the end of the spectrum shadow the last sample: the column's warp votes need all
+  // 32 lanes
+  const int wl = min(w, c.nwave - 1);
+  double *tk = KEEP ? tau_keep + ((size_t)m * c.nwave + wl) * c.nlayer : nullptr;
+  int *lk = KEEP ? last_keep + (size_t)m * c.nwave + wl : nullptr;
+  const double f = eclipse_column<NMOL, NCIA, NANG, KEEP>(c, s_tab, s_etab, wl, tk, lk);
+  if (w < c.nwave) spectra[(size_t)m * c.nwave + w] = f;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -167,8 +174,8 @@ transit_column_kernel(DevConfig c, const double *__restrict__ tabs, const double
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar;
   const int nd = c.lay.stride();
-  double *s_etab = reinterpret_cast<double *>(smem_raw);
-  double *s_tab = s_etab + kExpTabSize;
+  unsigned long long *s_etab = reinterpret_cast<unsigned long long *>(smem_raw);
+  double *s_tab = reinterpret_cast<double *>(s_etab + kExpTabSize);
   double *s_er = s_tab + nd;                                   // [nl][kTransitThreads]
   const int m = blockIdx.x % nmodels;
   const int tile = blockIdx.x / nmodels;
@@ -195,6 +202,7 @@ __global__ void merge_status_kernel(int *status, const int *status_col, int n) {
 
 // ---------------------------------------------------------------------------------------
 // K1 stand-alone lookup: ext[m][layer][w], layer index bottom -> top like the reference's e[r][w]
+template <int NMOL>
 __global__ void __launch_bounds__(kColThreads)
 extinction_kernel(DevConfig c, const double *__restrict__ tabs, double *__restrict__ ext,
                   int nmodels, int mol_only, int use_tma) {
@@ -214,9 +222,25 @@ extinction_kernel(DevConfig c, const double *__restrict__ tabs, double *__restri
   const int per = (nl + gridDim.y - 1) / gridDim.y;
   const int d0 = blockIdx.y * per, d1 = min(nl, d0 + per);
   double *out = ext + (size_t)m * nl * c.nwave + w;
+  const ColPtrs P = col_ptrs<-1>(c, w);
+#pragma unroll 4
   for (int d = d0; d < d1; d++)
     out[(size_t)(nl - 1 - d) * c.nwave] =
-        cell_extinction<0, -1>(c, s_tab + (size_t)d * c.lay.nf(), w, wn4, mol_only != 0);
+        cell_extinction<NMOL, -1>(c, P, s_tab + (size_t)d * c.lay.nf(), wn4, mol_only != 0);
+}
+
+// Grid upload: one chunk of (layer, temperature) cells in file order [cell][mol][wave] ->
+// device layout [cell][wave][gms] (molecule innermost, zero padding when gms > nmol).
+__global__ void grid_relayout_kernel(const double *__restrict__ in, double *__restrict__ out,
+                                     int ncells, int nmol, int gms, int nwave) {
+  const size_t total = (size_t)ncells * nwave;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const size_t cell = i / nwave, w = i % nwave;
+    const double *src = in + cell * (size_t)nmol * nwave + w;
+    double *dst = out + i * gms;
+    for (int m = 0; m < gms; m++) dst[m] = m < nmol ? src[(size_t)m * nwave] : 0.0;
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -260,6 +284,18 @@ __global__ void fill_kernel(double *p, size_t n, double v) {
 // launchers
 static size_t table_smem(const DevConfig &c) {
   return ((size_t)c.lay.stride() + kExpTabSize) * sizeof(double);
+}
+
+void upload_exp_table(cudaStream_t s) {
+  unsigned long long h[kExpTabSize];
+  fill_exp_table(h);
+  cudaMemcpyToSymbolAsync(g_exp_table, h, sizeof(h), 0, cudaMemcpyHostToDevice, s);
+  cudaStreamSynchronize(s);
+}
+
+void launch_grid_relayout(const double *in, double *out, int ncells, int nmol, int gms, int nwave,
+                          cudaStream_t s) {
+  grid_relayout_kernel<<<148 * 8, 256, 0, s>>>(in, out, ncells, nmol, gms, nwave);
 }
 
 void launch_atm_prep(const DevConfig &c, const Knobs &k, const double *profiles, int n_in,
@@ -355,15 +391,21 @@ void launch_transit(const DevConfig &c, const double *tabs, double *wts, const i
 
 void launch_extinction(const DevConfig &c, const double *tabs, double *ext, int nmodels,
                        bool mol_only, int layer_splits, int use_tma, cudaStream_t s) {
-  const size_t smem = table_smem(c);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaFuncSetAttribute(extinction_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
-  }
+  const size_t smem = (size_t)c.lay.stride() * sizeof(double);
   const int tiles = (c.nwave + kColThreads - 1) / kColThreads;
   dim3 grid((unsigned)((size_t)tiles * nmodels), (unsigned)layer_splits);
-  extinction_kernel<<<grid, kColThreads, smem, s>>>(c, tabs, ext, nmodels, mol_only ? 1 : 0, use_tma);
+  auto go = [&](auto kern) {
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<grid, kColThreads, smem, s>>>(c, tabs, ext, nmodels, mol_only ? 1 : 0, use_tma);
+  };
+  switch (c.ngmol) {
+    case 1: go(extinction_kernel<1>); break;
+    case 2: go(extinction_kernel<2>); break;
+    case 3: go(extinction_kernel<3>); break;
+    case 4: go(extinction_kernel<4>); break;
+    default: go(extinction_kernel<0>);
+  }
 }
 
 void launch_band_integrate(const double *spectra, const double *wn, const int *fstart,

@@ -25,5 +25,9 @@ void launch_band_integrate(const double *spectra, const double *wn, const int *f
                            const double *star, double rprs2, const int *status, double *bandflux,
                            int nfilters, int nwave, int nmodels, cudaStream_t s);
 void launch_fill(double *p, size_t n, double v, cudaStream_t s);
+void upload_exp_table(cudaStream_t s);
+// [cell][mol][wave] (file order) -> [cell][wave][gms] (device order), ncells (layer, T) cells
+void launch_grid_relayout(const double *in, double *out, int ncells, int nmol, int gms, int nwave,
+                          cudaStream_t s);
 
 }  // namespace bart

@@ -109,7 +109,7 @@ struct State {
   Knobs knobs{};
   // static device arrays
   DevBuf<double> d_grid, d_gtemp, d_wn, d_press, d_mass, d_pol;
-  DevBuf<double> d_ciaP[kMaxCia], d_ciaQ[kMaxCia], d_ciaT[kMaxCia];
+  DevBuf<double> d_ciaPQ[kMaxCia], d_ciaT[kMaxCia];
   // batch buffers
   DevBuf<double> d_prof, d_tabs, d_spec, d_wts, d_tau, d_band, d_ext, d_flush;
   DevBuf<int> d_status, d_status_col, d_last;
@@ -256,8 +256,10 @@ static void setup_cia() {
            c.file.c_str(), G.wn[0], G.wn[nw - 1]);
     std::vector<double> P, Q;
     fold_cia_table(c, G.wn, P, Q);
-    upload(G.d_ciaP[f], P); upload(G.d_ciaQ[f], Q); upload(G.d_ciaT[f], c.temp);
-    G.dc.ciaP[f] = G.d_ciaP[f].p; G.dc.ciaQ[f] = G.d_ciaQ[f].p; G.dc.ciaT[f] = G.d_ciaT[f].p;
+    std::vector<double> PQ(2 * P.size());                  // [T_k][wave][value, d2/dT2]
+    for (size_t i = 0; i < P.size(); i++) { PQ[2 * i] = P[i]; PQ[2 * i + 1] = Q[i]; }
+    upload(G.d_ciaPQ[f], PQ); upload(G.d_ciaT[f], c.temp);
+    G.dc.ciaPQ[f] = G.d_ciaPQ[f].p; G.dc.ciaT[f] = G.d_ciaT[f].p;
     G.dc.cia_nt[f] = nt;
     G.dc.cia_nspec[f] = (int)c.species.size();
     for (size_t s = 0; s < c.species.size(); s++) {
@@ -277,25 +279,47 @@ static void load_grid_to_device(const std::string &path) {
     fail("Opacity grid has %ld layers but the atmosphere has %d.", g.nlayer, G.atm.nlayer());
   if (g.nwave != (long)G.wn.size())
     fail("Opacity grid has %ld wavenumber samples but the configuration asks for %zu.", g.nwave, G.wn.size());
-  const size_t n = (size_t)g.nlayer * g.ntemp * g.nmol * g.nwave;
-  G.d_grid.ensure(n);
+  // device layout: [layer][temp][wave][gms], molecule axis innermost (device.cuh)
+  const int gms = g.nmol == 1 ? 1 : (int)((g.nmol + 1) / 2 * 2);
+  G.dc.gms = gms;
+  const size_t ncell = (size_t)g.nlayer * g.ntemp;
+  const size_t cell_in = (size_t)g.nmol * g.nwave, cell_out = (size_t)gms * g.nwave;
+  G.d_grid.ensure(ncell * cell_out);
   FILE *f = fopen(path.c_str(), "rb");
   if (!f) fail("Opening opacity file '%s' failed.", path.c_str());
   fseek(f, g.data_offset, SEEK_SET);
-  // stream the file through a pinned staging buffer (files reach tens of GB at high resolution)
-  const size_t chunk = 64u << 20;
-  void *stage = nullptr;
-  CUDA_OK(cudaMallocHost(&stage, chunk));
-  size_t done = 0, total = n * sizeof(double);
-  while (done < total) {
-    size_t want = std::min(chunk, total - done);
-    size_t got = fread(stage, 1, want, f);
-    if (got != want) { cudaFreeHost(stage); fclose(f); fail("Opacity file '%s' is truncated.", path.c_str()); }
-    CUDA_OK(cudaMemcpy((char *)G.d_grid.p + done, stage, got, cudaMemcpyHostToDevice));
-    done += got;
+  // stream whole (layer, temperature) cells through two pinned staging buffers (files reach tens
+  // of GB at high resolution); each chunk is re-laid out on the device while the next is read
+  const size_t cells_per_chunk = std::max<size_t>(1, (size_t)(64u << 20) / (cell_in * 8));
+  const size_t chunk = cells_per_chunk * cell_in * 8;
+  void *stage[2] = {nullptr, nullptr};
+  DevBuf<double> d_stage[2];
+  cudaEvent_t done_ev[2];
+  for (int i = 0; i < 2; i++) {
+    CUDA_OK(cudaMallocHost(&stage[i], chunk));
+    d_stage[i].ensure(cells_per_chunk * cell_in);
+    CUDA_OK(cudaEventCreate(&done_ev[i]));
   }
-  cudaFreeHost(stage);
+  size_t cell = 0;
+  int which = 0;
+  bool bad = false;
+  while (cell < ncell && !bad) {
+    const size_t nc = std::min(cells_per_chunk, ncell - cell);
+    const size_t want = nc * cell_in * 8;
+    CUDA_OK(cudaEventSynchronize(done_ev[which]));           // staging buffer free again
+    if (fread(stage[which], 1, want, f) != want) { bad = true; break; }
+    CUDA_OK(cudaMemcpyAsync(d_stage[which].p, stage[which], want, cudaMemcpyHostToDevice, G.stream));
+    launch_grid_relayout(d_stage[which].p, G.d_grid.p + cell * cell_out, (int)nc, (int)g.nmol, gms,
+                         (int)g.nwave, G.stream);
+    CUDA_OK(cudaEventRecord(done_ev[which], G.stream));
+    cell += nc;
+    which ^= 1;
+  }
+  cudaStreamSynchronize(G.stream);
+  for (int i = 0; i < 2; i++) { cudaFreeHost(stage[i]); d_stage[i].release(); cudaEventDestroy(done_ev[i]); }
   fclose(f);
+  if (bad) fail("Opacity file '%s' is truncated.", path.c_str());
+  check_launch("grid_relayout");
 }
 
 static void finish_grid_config() {
@@ -316,7 +340,7 @@ static void finish_grid_config() {
 static void reset_state() {
   G.d_grid.release(); G.d_gtemp.release(); G.d_wn.release(); G.d_press.release();
   G.d_mass.release(); G.d_pol.release();
-  for (int f = 0; f < kMaxCia; f++) { G.d_ciaP[f].release(); G.d_ciaQ[f].release(); G.d_ciaT[f].release(); }
+  for (int f = 0; f < kMaxCia; f++) { G.d_ciaPQ[f].release(); G.d_ciaT[f].release(); }
   G.d_prof.release(); G.d_tabs.release(); G.d_spec.release(); G.d_wts.release(); G.d_tau.release();
   G.d_band.release(); G.d_ext.release(); G.d_status.release(); G.d_status_col.release();
   G.d_last.release(); G.d_kr0.release(); G.d_kcloud.release(); G.d_klogext.release(); G.d_kflag.release();
@@ -394,7 +418,9 @@ static void do_init(int argc, char **argv) {
       c.inv_mu[a] = 1.0 / cos(G.angles[a] * kDEG);
       c.wgt[a] = pow(sin(area[a + 1]), 2.0) - pow(sin(area[a]), 2.0);
     }
+    fill_angle_consts(c);
   }
+  upload_exp_table(G.stream);
   const double srad = o.starrad * kSUNRADIUS;                      // geometry.c:36,50
   c.inv_srad2 = 1.0 / (srad * srad);
 

@@ -29,7 +29,7 @@ using namespace bart;
 struct Emu {
   Options opt; Atmosphere atm; Molecules mol; Tli tli; OpacityGrid og;
   std::vector<CiaTable> cia;
-  std::vector<double> wn, grid, P[kMaxCia], Q[kMaxCia];
+  std::vector<double> wn, grid, PQ[kMaxCia];
   DevConfig c{};
   Knobs k{};
 };
@@ -54,12 +54,19 @@ int emu_init(const char *cfg) {
     if (!read_opacity_header(o.opacityfile, E->og)) fail("no opacity file");
     OpacityGrid &g = E->og;
     size_t n = (size_t)g.nlayer * g.ntemp * g.nmol * g.nwave;
-    E->grid.resize(n);
+    std::vector<double> filegrid(n);
     FILE *f = fopen(o.opacityfile.c_str(), "rb");
     fseek(f, g.data_offset, SEEK_SET);
-    if (fread(E->grid.data(), 8, n, f) != n) fail("short grid");
+    if (fread(filegrid.data(), 8, n, f) != n) fail("short grid");
     fclose(f);
     DevConfig &c = E->c;
+    // the device layout of the grid: [layer][temp][wave][gms] (device.cuh)
+    c.gms = g.nmol == 1 ? 1 : (int)((g.nmol + 1) / 2 * 2);
+    E->grid.assign((size_t)g.nlayer * g.ntemp * g.nwave * c.gms, 0.0);
+    for (size_t cell = 0; cell < (size_t)(g.nlayer * g.ntemp); cell++)
+      for (long m = 0; m < g.nmol; m++)
+        for (long w = 0; w < g.nwave; w++)
+          E->grid[(cell * g.nwave + w) * c.gms + m] = filegrid[(cell * g.nmol + m) * g.nwave + w];
     c.nlayer = E->atm.nlayer(); c.nspec = E->atm.nspec(); c.nwave = (int)E->wn.size();
     c.ntemp = (int)g.ntemp; c.ngmol = (int)g.nmol;
     c.eclipse = o.solution == "eclipse"; c.transparent = o.transparent;
@@ -71,8 +78,11 @@ int emu_init(const char *cfg) {
     c.ncia = (int)o.csfiles.size();
     for (int i = 0; i < c.ncia; i++) {
       read_cia(o.csfiles[i], E->cia[i]);
-      fold_cia_table(E->cia[i], E->wn, E->P[i], E->Q[i]);
-      c.ciaP[i] = E->P[i].data(); c.ciaQ[i] = E->Q[i].data(); c.ciaT[i] = E->cia[i].temp.data();
+      std::vector<double> P, Q;
+      fold_cia_table(E->cia[i], E->wn, P, Q);
+      E->PQ[i].resize(2 * P.size());
+      for (size_t k = 0; k < P.size(); k++) { E->PQ[i][2 * k] = P[k]; E->PQ[i][2 * k + 1] = Q[k]; }
+      c.ciaPQ[i] = E->PQ[i].data(); c.ciaT[i] = E->cia[i].temp.data();
       c.cia_nt[i] = (int)E->cia[i].temp.size();
       c.cia_nspec[i] = (int)E->cia[i].species.size();
       for (size_t s = 0; s < E->cia[i].species.size(); s++)
@@ -91,6 +101,7 @@ int emu_init(const char *cfg) {
       c.inv_mu[a] = 1.0 / cos(ang[a] * kDEG);
       c.wgt[a] = pow(sin(area[a + 1]), 2.0) - pow(sin(area[a]), 2.0);
     }
+    fill_angle_consts(c);
     double srad = o.starrad * kSUNRADIUS;
     c.inv_srad2 = 1.0 / (srad * srad);
     c.lay.nl = c.nlayer; c.lay.ngmol = c.ngmol; c.lay.ncia = c.ncia;
@@ -124,7 +135,7 @@ int emu_run(const double *in, double *spectrum, double *tau, int *last, double *
   if (radius) for (int l = 0; l < nl; l++) radius[l] = rad[l];
   if (status) { for (int w = 0; w < nw; w++) spectrum[w] = -1; return status; }
   std::vector<double> tk(nl), wts((size_t)nl * (nl + 1) / 2), er(nl);
-  alignas(16) double etab[kExpTabSize];
+  alignas(16) unsigned long long etab[kExpTabSize];
   fill_exp_table(etab);
   if (!c.eclipse) for (int d = 0; d < nl; d++) transit_weight_row(c, tab.data(), d, &wts[(size_t)d * (d + 1) / 2]);
   for (int w = 0; w < nw; w++) {
@@ -142,13 +153,14 @@ int emu_run(const double *in, double *spectrum, double *tau, int *last, double *
     if (last) last[w] = lk;
     if (ext_total) {
       const double wn = c.wn[w], wn4 = (wn * wn) * (wn * wn);
+      const ColPtrs P = col_ptrs<-1>(c, w);
       for (int d = 0; d < nl; d++)
-        ext_total[(size_t)(nl - 1 - d) * nw + w] = cell_extinction<0, -1>(c, tab.data() + (size_t)d * c.lay.nf(), w, wn4, true);
+        ext_total[(size_t)(nl - 1 - d) * nw + w] = cell_extinction<0, -1>(c, P, tab.data() + (size_t)d * c.lay.nf(), wn4, true);
     }
   }
   return status;
 }
 
-double emu_fast_exp(double x) { double t[kExpTabSize]; fill_exp_table(t); return fast_exp(x, t); }
+double emu_fast_exp(double x) { unsigned long long t[kExpTabSize]; fill_exp_table(t); return fast_exp(x, t); }
 
 }  // extern "C"

@@ -46,20 +46,24 @@ def test_rejection_status(built, get_case):
 
 
 def test_fast_exp_accuracy(built):
-    """The kernels' exp (column_math.cuh fast_exp) against libm: <= 1e-15 relative over the ranges
-    the forward model uses (-tau/mu down to the clamp, Planck exponents up to ~150)."""
+    """The kernels' exp (column_math.cuh exp_core / fast_exp) against libm over the ranges the
+    forward model uses (-tau/mu down to the clamp at -700, Planck exponents up to the clamp at
+    +700): relative error <= 2e-15 + 2e-17 |x| (the one-constant argument reduction carries the
+    rounding of N/ln2 into the exponent; 1e-14 at the clamps, 8 orders below the 1e-6 budget)."""
     import ctypes as C
     lib = C.CDLL(__import__("os").path.join(cases.ROOT, "tests", "cpu_emu", "libemu.so"))
     lib.emu_fast_exp.restype = C.c_double
     lib.emu_fast_exp.argtypes = [C.c_double]
     rng = np.random.default_rng(1)
-    xs = np.concatenate([-10.0 ** rng.uniform(-12, 2.8, 20000), rng.uniform(0, 150, 5000),
-                         [0.0, -0.0, -1e-300, -708.0, 1.0, -1.0, 0.5 * np.log(2), -0.5 * np.log(2)]])
+    xs = np.concatenate([-10.0 ** rng.uniform(-12, 2.845, 20000), rng.uniform(0, 700, 5000),
+                         [0.0, -0.0, -1e-300, -700.0, 700.0, 1.0, -1.0, 0.5 * np.log(2),
+                          -0.5 * np.log(2), np.log(2) / 256, -np.log(2) / 256]])
     worst = 0.0
     for x in xs:
         got, ref = lib.emu_fast_exp(float(x)), float(np.exp(x))
-        worst = max(worst, abs(got - ref) / ref)
-    assert worst < 1e-15, worst
+        worst = max(worst, abs(got - ref) / ref / (2e-15 + 2e-17 * abs(x)))
+    assert worst < 1.0, worst
     assert lib.emu_fast_exp(0.0) == 1.0
-    assert lib.emu_fast_exp(-1e9) == 0.0 and lib.emu_fast_exp(-709.0) == 0.0   # opaque deck
-    assert lib.emu_fast_exp(1e5) == 1e308 and np.isfinite(lib.emu_fast_exp(709.0))
+    # arguments are clamped to [-700, 700]: an opaque deck transmits e^-700 ~ 1e-304, not NaN
+    assert lib.emu_fast_exp(-1e9) == lib.emu_fast_exp(-700.0) < 1e-300
+    assert lib.emu_fast_exp(1e5) == lib.emu_fast_exp(700.0) and np.isfinite(lib.emu_fast_exp(1e5))
