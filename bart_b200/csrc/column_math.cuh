@@ -48,6 +48,40 @@ struct alignas(16) D2 { double x, y; };
 BART_HD D2 ld2(const double *p) { return *reinterpret_cast<const D2 *>(p); }
 BART_HD D2 ld2b(const char *p) { return *reinterpret_cast<const D2 *>(p); }
 BART_HD double ld1b(const char *p) { return *reinterpret_cast<const double *>(p); }
+// Global loads of cell_load: volatile asm, so that they stay where the software pipeline of the
+// column kernels puts them (after the consumption of the previous depth's data).
+BART_HD D2 ldg2b(const char *p) {
+#ifdef __CUDA_ARCH__
+  D2 v;
+  asm volatile("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+#else
+  return *reinterpret_cast<const D2 *>(p);
+#endif
+}
+BART_HD double ldg1b(const char *p) {
+#ifdef __CUDA_ARCH__
+  double v;
+  asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+#else
+  return *reinterpret_cast<const double *>(p);
+#endif
+}
+// 32-byte load of a 4-molecule grid sample: one LDG.256 per lane, so a warp's request is 1 KB of
+// contiguous memory (two LDG.128 per lane would each touch every other 16 bytes of that span and
+// cost twice the L1 wavefronts).
+struct alignas(32) D4 { double x, y, z, w; };
+BART_HD D4 ld4b(const char *p) {
+#ifdef __CUDA_ARCH__
+  D4 v;
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+               : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+  return v;
+#else
+  D4 v; memcpy(&v, p, sizeof(v)); return v;
+#endif
+}
 
 // Warp-uniform decisions of the column kernels.  On the host (tests/cpu_emu, one column at a
 // time) they degenerate to the column's own predicate.
@@ -59,22 +93,27 @@ BART_HD double ld1b(const char *p) { return *reinterpret_cast<const double *>(p)
 #define BART_WARP_ANY(p) (p)
 #endif
 
-// exp(x) = 2^n 2^(j/N) e^(r ln2/N) with y = x N/ln2 = (N n + j) + r, |r| <= 1/2, N = 128:
-// |r ln2/N| <= 2.7e-3, so a degree-4 polynomial is exact to 1.2e-15.  The caller supplies y as a
+// exp(x) = 2^n 2^(j/N) e^(r ln2/N) with y = x N/ln2 = (N n + j) + r, |r| <= 1/2, N = 16:
+// |r ln2/N| <= 0.0217, so a degree-6 polynomial is exact to 4.5e-16.  The caller supplies y as a
 // product a*b (one factor usually a constant that already carries N/ln2), so the reduction is two
 // FMAs with the SAME exact product: t = a b + 1.5 2^52 rounds y to the nearest integer m (low
-// word of t), r = a b - m is exact.  8 fp64 instructions per exp in all.
-// The table (shared memory, 1 KB) holds the bit patterns of 2^(j/N) with (j << 13) subtracted
-// from the high word, so that adding (m << 13) -- one integer multiply-add -- yields the high word
-// of 2^n 2^(j/N) without masking j out of m.  Arguments must satisfy |x| <= 708 (callers clamp).
-constexpr int kExpBits = 7;
+// word of t), r = a b - m is exact.  10 fp64 instructions per exp in all.
+// The table (shared memory) holds the bit patterns of 2^(j/N) with (j << 16) subtracted from the
+// high word, so that adding (m << 16) -- one integer multiply-add -- yields the high word of
+// 2^n 2^(j/N) without masking j out of m.  N = 16 keeps the table inside ONE 128-byte bank row:
+// divergent lanes never conflict (the column kernels are bound by shared/L1 wavefronts, not by
+// the fp64 pipe; a 128-entry table with a degree-4 polynomial measured slower).
+// Arguments must satisfy |x| <= 708 (callers clamp).
+constexpr int kExpBits = 4;
 constexpr int kExpTabSize = 1 << kExpBits;
-constexpr double kExpScale = 184.6649652337873;                 // N / ln2
+constexpr double kExpScale = 23.083120654223414;                 // N / ln2
 constexpr double kExpYmax = 700.0 * kExpScale;                   // clamp for y
-constexpr double kExpQ1 = 0.0054152123481245725;                 // (ln2/N)^k / k!
-constexpr double kExpQ2 = 1.4662262387640425e-05;
-constexpr double kExpQ3 = 2.646642144433097e-08;
-constexpr double kExpQ4 = 3.583032305400251e-11;
+constexpr double kExpQ1 = 0.04332169878499658;                   // (ln2/N)^k / k!
+constexpr double kExpQ2 = 0.0009383847928089872;
+constexpr double kExpQ3 = 1.3550807779497457e-05;
+constexpr double kExpQ4 = 1.467610032291943e-07;
+constexpr double kExpQ5 = 1.2715871950558131e-09;
+constexpr double kExpQ6 = 9.181219573844438e-12;
 
 static const unsigned long long kExpTabBits[kExpTabSize] = {
 #include "exp_table.inc"
@@ -93,7 +132,9 @@ BART_HD double exp_core(double a, double b, const unsigned long long *tab, doubl
   const double t = fma(a, b, MAGIC);
   const double kf = t - MAGIC;
   const double r = fma(a, b, -kf);
-  double p = kExpQ4;
+  double p = kExpQ6;
+  p = fma(p, r, kExpQ5);
+  p = fma(p, r, kExpQ4);
   p = fma(p, r, kExpQ3);
   p = fma(p, r, kExpQ2);
   p = fma(p, r, kExpQ1);
@@ -164,6 +205,10 @@ inline void fill_angle_consts(DevConfig &c) {
   double d0 = 0.0;
   for (int a = 0; a < c.nang; a++) d0 = fma(1.0, c.wgt[a], d0);
   c.taylor[0] = d0;
+  c.sq_src = c.sq_dst = -1;
+  for (int b = 0; b < c.nang && c.sq_dst < 0; b++)
+    for (int a = 0; a < b; a++)
+      if (fabs(c.inv_mu[b] - 2.0 * c.inv_mu[a]) <= 4e-16 * c.inv_mu[b]) { c.sq_src = a; c.sq_dst = b; break; }
   c.tau_small = smax > 0 ? 0.3 / smax : 0.0;
   c.tau_clamp = smax > 0 ? 700.0 / smax : 700.0;
 }
@@ -281,6 +326,8 @@ BART_HD int prep_table_row(const DevConfig &c, const KnobVals &kv, int d, const 
   row[L.T] = T;
   row[L.INVT] = 1.0 / T;
   row[L.RAD] = radius[l];
+  row[L.PF] = c.planck_cols > 0 ? exp(c.planck_step / T) : 1.0;
+  row[L.PF + 1] = 0.0;
 
   // opacity-grid bracket and folded weights (interpolmolext, extinction.c:534-581)
   if (T < c.gtemp[0] || T > c.gtemp[c.ntemp - 1]) status |= REJ_TGRID;
@@ -387,39 +434,68 @@ BART_HD ColPtrs col_ptrs(const DevConfig &c, int w) {
 // interpolation and abundance scaling (extinction.c:534-581), + scattering + cloud + CIA in the
 // reference's summation order (tau.c:231-232).  `row` is the depth's table record.  NMOL / NCIA
 // are compile-time counts (NMOL 0 / NCIA -1 = take them from the configuration at run time).
-// With NMOL > 1 a sample's molecules arrive as 16-byte pairs (LDG.128) from each of the two
-// bracketing temperature planes.
+// The lookup is split into cell_load (issues the global loads: one 8/16/32-byte vector per
+// bracketing temperature plane carrying all molecules of the sample, one 16-byte pair per CIA
+// temperature node) and cell_combine (the arithmetic), so that a column kernel can issue the
+// loads of the next depth before it works on the current one.
 template <int NMOL, int NCIA>
-BART_HD double cell_extinction(const DevConfig &c, const ColPtrs &P, const double *row, double wn4,
-                               bool mol_only) {
+struct CellData {
+  static constexpr bool kStatic = NMOL >= 1 && NMOL <= 4 && NCIA >= 0;
+  static constexpr int NG = !kStatic ? 1 : (NMOL == 1 ? 1 : (NMOL == 2 ? 2 : 4));
+  static constexpr int NC = kStatic && NCIA > 0 ? NCIA : 1;
+  double lo[NG], hi[NG];
+  D2 k0[NC], k1[NC];
+};
+
+template <int NMOL, int NCIA>
+BART_HD void cell_load(const DevConfig &c, const ColPtrs &P, const double *row,
+                       CellData<NMOL, NCIA> &x) {
   typedef TabLayout L;
-  const int ngmol = NMOL > 0 ? NMOL : c.ngmol;
-  const int ncia = NCIA >= 0 ? NCIA : c.ncia;
+  if (!CellData<NMOL, NCIA>::kStatic) return;                  // run-time counts: loaded in cell_combine
   const size_t plane = (size_t)c.nwave * c.gms * 8;
   const char *lo = P.g + double_to_bits(row[L::GOFF]);
   const char *hi = lo + plane;
-  double e = 0.0;
-  if (NMOL == 1) {
-    const D2 wt = ld2(row + L::W);
-    e = wt.x * ld1b(lo);
-    e = fma(wt.y, ld1b(hi), e);
-  } else if (NMOL > 1) {
+  if (NMOL == 1) { x.lo[0] = ldg1b(lo); x.hi[0] = ldg1b(hi); }
+  else if (NMOL == 2) {
+    const D2 a = ldg2b(lo), b = ldg2b(hi);
+    x.lo[0] = a.x; x.lo[1] = a.y; x.hi[0] = b.x; x.hi[1] = b.y;
+  } else {
+    const D4 a = ld4b(lo), b = ld4b(hi);
+    x.lo[0] = a.x; x.lo[1] = a.y; x.lo[2] = a.z; x.lo[3] = a.w;
+    x.hi[0] = b.x; x.hi[1] = b.y; x.hi[2] = b.z; x.hi[3] = b.w;
+  }
+  const double *cr = row + L::W + 2 * NMOL;
+  const size_t cplane = (size_t)c.nwave * 16;
 #pragma unroll
-    for (int q = 0; q < (NMOL + 1) / 2; q++) {
-      const D2 a = ld2b(lo + 16 * q), b = ld2b(hi + 16 * q);
-      const D2 w0 = ld2(row + L::W + 4 * q);
-      e = q == 0 ? w0.x * a.x : fma(w0.x, a.x, e);
-      e = fma(w0.y, b.x, e);
-      if (2 * q + 1 < NMOL) {
-        const D2 w1 = ld2(row + L::W + 4 * q + 2);
-        e = fma(w1.x, a.y, e);
-        e = fma(w1.y, b.y, e);
-      }
+  for (int f = 0; f < (NCIA > 0 ? NCIA : 0); f++) {
+    const char *pq = P.cia[f] + double_to_bits(cr[6 * f]);
+    x.k0[f] = ldg2b(pq);                                       // (value, d2/dT2) at T_k
+    x.k1[f] = ldg2b(pq + cplane);                              //                    T_k+1
+  }
+}
+
+template <int NMOL, int NCIA>
+BART_HD double cell_combine(const DevConfig &c, const ColPtrs &P, const double *row,
+                            const CellData<NMOL, NCIA> &x, double wn4, bool mol_only) {
+  typedef TabLayout L;
+  const int ngmol = NMOL > 0 ? NMOL : c.ngmol;
+  const int ncia = NCIA >= 0 ? NCIA : c.ncia;
+  constexpr bool kStatic = CellData<NMOL, NCIA>::kStatic;
+  double e = 0.0;
+  if (kStatic) {
+#pragma unroll
+    for (int m = 0; m < (kStatic ? NMOL : 0); m++) {
+      const D2 wt = ld2(row + L::W + 2 * m);
+      e = m == 0 ? wt.x * x.lo[0] : fma(wt.x, x.lo[m < CellData<NMOL, NCIA>::NG ? m : 0], e);
+      e = fma(wt.y, x.hi[m < CellData<NMOL, NCIA>::NG ? m : 0], e);
     }
   } else {
+    const size_t plane = (size_t)c.nwave * c.gms * 8;
+    const char *lo = P.g + double_to_bits(row[L::GOFF]);
+    const char *hi = lo + plane;
     for (int m = 0; m < ngmol; m++) {
       const D2 wt = ld2(row + L::W + 2 * m);
-      e = fma(wt.x, ld1b(lo + 8 * m), e);
+      e = m == 0 ? wt.x * ld1b(lo) : fma(wt.x, ld1b(lo + 8 * m), e);
       e = fma(wt.y, ld1b(hi + 8 * m), e);
     }
   }
@@ -430,8 +506,12 @@ BART_HD double cell_extinction(const DevConfig &c, const ColPtrs &P, const doubl
 #pragma unroll
   for (int f = 0; f < (NCIA >= 0 ? NCIA : kMaxCia); f++) {
     if (f < ncia) {
-      const char *pq = P.cia[f] + double_to_bits(cr[6 * f]);
-      const D2 k0 = ld2b(pq), k1 = ld2b(pq + cplane);          // (value, d2/dT2) at T_k, T_k+1
+      D2 k0, k1;
+      if (kStatic) { k0 = x.k0[f < CellData<NMOL, NCIA>::NC ? f : 0]; k1 = x.k1[f < CellData<NMOL, NCIA>::NC ? f : 0]; }
+      else {
+        const char *pq = P.cia[f] + double_to_bits(cr[6 * f]);
+        k0 = ld2b(pq); k1 = ld2b(pq + cplane);
+      }
       const D2 cy = ld2(cr + 6 * f + 2), cz = ld2(cr + 6 * f + 4);
       double v = cy.x * k0.x;
       v = fma(cy.y, k1.x, v);
@@ -442,6 +522,14 @@ BART_HD double cell_extinction(const DevConfig &c, const ColPtrs &P, const doubl
   }
   const D2 sc = ld2(row + L::SCAT);                            // (scattering coefficient, cloud)
   return fma(sc.x, wn4, e) + sc.y + ecs;
+}
+
+template <int NMOL, int NCIA>
+BART_HD double cell_extinction(const DevConfig &c, const ColPtrs &P, const double *row, double wn4,
+                               bool mol_only) {
+  CellData<NMOL, NCIA> x;
+  cell_load<NMOL, NCIA>(c, P, row, x);
+  return cell_combine<NMOL, NCIA>(c, P, row, x, wn4, mol_only);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -458,78 +546,166 @@ BART_HD double cell_extinction(const DevConfig &c, const ColPtrs &P, const doubl
 //        While every column of the warp has tau <= tau_small, D comes from its Maclaurin series
 //        (one polynomial instead of one exp per angle).
 // All 32 lanes of a warp must enter together (warp votes); a column that has passed its `last`
-// layer idles until the warp's deepest column is done.
-template <int NMOL, int NCIA, int NANG, bool KEEP>
-BART_HD double eclipse_column(const DevConfig &c, const double *tab, const unsigned long long *etab,
-                              int w, double *tau_keep, int *last_keep) {
+// layer idles until the warp's deepest column is done.  A thread carries NCOL independent
+// columns of the same model (the table record of a depth is read once for all of them, and the
+// independent dependency chains overlap); a column with valid[k] false idles from the start.
+// SQ >= 0 encodes (src << 4 | dst): the exponential of angle dst is the square of that of src
+// (1/mu_dst = 2/mu_src, e.g. 60 and 0 degrees of the default ray grid); CHAIN: Planck chaining.
+template <int NMOL, int NCIA, int NANG, bool KEEP, int NCOL, int SQ = -1, bool CHAIN = false>
+BART_HD void eclipse_columns(const DevConfig &c, const double *tab, const unsigned long long *etab,
+                             const int (&w)[NCOL], const bool (&valid)[NCOL],
+                             double *const (&tau_keep)[NCOL], int *const (&last_keep)[NCOL],
+                             double (&flux)[NCOL]) {
   typedef TabLayout L;
   const int nl = c.nlayer;
   const int nf = c.lay.nf();
   const int nang = NANG > 0 ? NANG : c.nang;
-  const double wn = c.wn[w];
-  const double wn4 = (wn * wn) * (wn * wn);
-  const double c1 = 2.0 * cH * (wn * wn * wn) * cLS * cLS;
-  const double c2n = cH * wn * cLS / cKB * kExpScale;          // Planck exponent x N/ln2, per 1/T
-  const double invt_cap = kExpYmax / c2n;                      // keeps the exponent below 700
-  const int invt_cap_hi = hi_word(invt_cap);
   const int small_hi = hi_word(c.tau_small), clamp_hi = hi_word(c.tau_clamp);
-  const ColPtrs P = col_ptrs<NCIA>(c, w);
+  double wn4[NCOL], c1[NCOL], c2n[NCOL], invt_cap[NCOL];
+  double er1[NCOL], er2[NCOL], S[NCOL], trap[NCOL], Dprev[NCOL], Bprev[NCOL];
+  int last[NCOL];
+  bool alive[NCOL];
+  ColPtrs P[NCOL];
 
   // depth 0 (top): tau = 0, D = D(0)
-  double er1 = cell_extinction<NMOL, NCIA>(c, P, tab, wn4, false), er2 = 0.0;
-  double S = 0.0, trap = 0.0, Dprev = c.taylor[0], Bprev;
-  {
-    double it = tab[L::INVT];
-    if (hi_word(it) > invt_cap_hi) it = invt_cap;
-    Bprev = c1 * fast_rcp(exp_core(c2n, it, etab, -1.0));
+#pragma unroll
+  for (int k = 0; k < NCOL; k++) {
+    const double wn = c.wn[w[k]];
+    wn4[k] = (wn * wn) * (wn * wn);
+    c1[k] = 2.0 * cH * (wn * wn * wn) * cLS * cLS;
+    c2n[k] = cH * wn * cLS / cKB * kExpScale;                  // Planck exponent x N/ln2, per 1/T
+    invt_cap[k] = kExpYmax / c2n[k];                           // keeps the exponent below 700
+    P[k] = col_ptrs<NCIA>(c, w[k]);
+    er1[k] = cell_extinction<NMOL, NCIA>(c, P[k], tab, wn4[k], false);
+    er2[k] = 0.0; S[k] = 0.0; trap[k] = 0.0; Dprev[k] = c.taylor[0];
+    alive[k] = valid[k] && !(0.0 > c.toomuch);
+    last[k] = alive[k] ? nl - 1 : 0;
+    if (KEEP && valid[k]) tau_keep[k][0] = 0.0;
   }
-  if (KEEP) tau_keep[0] = 0.0;
-  int last = nl - 1;
-  bool alive = !(0.0 > c.toomuch);
-  if (!alive) last = 0;
+
+  // Planck function of every column at one depth (eclipse_intens, eclipse.c:130-140)
+  auto planck = [&](const double *row, double (&B)[NCOL]) {
+    double E = 0.0;
+#pragma unroll
+    for (int k = 0; k < NCOL; k++) {
+      double em1;
+      if (CHAIN && k > 0) {
+        const double pf = row[L::PF];
+        em1 = fma(E, pf, -1.0);
+        if (k + 1 < NCOL) E *= pf;
+      } else {
+        double it = row[L::INVT];
+        if (hi_word(it) > hi_word(invt_cap[k])) it = invt_cap[k];
+        if (CHAIN && NCOL > 1) { E = exp_core(c2n[k], it, etab, 0.0); em1 = E - 1.0; }
+        else em1 = exp_core(c2n[k], it, etab, -1.0);
+      }
+      B[k] = c1[k] * fast_rcp(em1);
+    }
+  };
+  planck(tab, Bprev);
+
+  auto any_alive = [&]() {
+    bool a = false;
+#pragma unroll
+    for (int k = 0; k < NCOL; k++) a = a || alive[k];
+    return BART_WARP_ANY(a);
+  };
+
+  // software pipeline: the loads of depth d + 1 are issued as soon as the data of depth d has
+  // been folded into its extinction (same registers), and complete under the ~100 fp64
+  // instructions of the rest of the step
+  CellData<NMOL, NCIA> cur[NCOL];
+  const double *row_last = tab + (size_t)(nl - 1) * nf;
+#pragma unroll
+  for (int k = 0; k < NCOL; k++) cell_load<NMOL, NCIA>(c, P[k], nl > 1 ? tab + nf : tab, cur[k]);
 
   auto step = [&](const double *row, int d, bool odd) {
-    const double er = cell_extinction<NMOL, NCIA>(c, P, row, wn4, false);
-    double tau;
-    if (odd) tau = fma(row[L::TR], er + er1, S);
-    else {
-      const D2 s1 = ld2(row + L::SA);                          // (SA, SB)
-      S = fma(s1.x, er, fma(s1.y, er1, fma(row[L::SC], er2, S)));
-      tau = S;
-    }
-    er2 = er1; er1 = er;
-    double it = row[L::INVT];
-    if (hi_word(it) > invt_cap_hi) it = invt_cap;
-    const double B = c1 * fast_rcp(exp_core(c2n, it, etab, -1.0));
-    double D;
-    if (BART_WARP_ALL(!alive || hi_word(tau) < small_hi)) {
-      D = c.taylor[kTaylorN - 1];
+    double tau[NCOL], B[NCOL], D[NCOL];
+    bool small = true;
+    const double *rown = row < row_last ? row + nf : row;      // the bottom depth re-reads itself
+    double erk[NCOL];
 #pragma unroll
-      for (int k = kTaylorN - 2; k >= 0; k--) D = fma(D, tau, c.taylor[k]);
+    for (int k = 0; k < NCOL; k++) {
+      erk[k] = cell_combine<NMOL, NCIA>(c, P[k], row, cur[k], wn4[k], false);
+      cell_load<NMOL, NCIA>(c, P[k], rown, cur[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < NCOL; k++) {
+      const double er = erk[k];
+      if (odd) tau[k] = fma(row[L::TR], er + er1[k], S[k]);
+      else {
+        const D2 s1 = ld2(row + L::SA);                        // (SA, SB)
+        S[k] = fma(s1.x, er, fma(s1.y, er1[k], fma(row[L::SC], er2[k], S[k])));
+        tau[k] = S[k];
+      }
+      er2[k] = er1[k]; er1[k] = er;
+      small = small && (!alive[k] || hi_word(tau[k]) < small_hi);
+    }
+    planck(row, B);
+    if (BART_WARP_ALL(small)) {
+#pragma unroll
+      for (int k = 0; k < NCOL; k++) {
+        double p = c.taylor[kTaylorN - 1];
+#pragma unroll
+        for (int i = kTaylorN - 2; i >= 0; i--) p = fma(p, tau[k], c.taylor[i]);
+        D[k] = p;
+      }
     } else {
-      const double tc = hi_word(tau) >= clamp_hi ? c.tau_clamp : tau;
-      D = 0.0;
+      double tc[NCOL];
+#pragma unroll
+      for (int k = 0; k < NCOL; k++) {
+        tc[k] = hi_word(tau[k]) >= clamp_hi ? c.tau_clamp : tau[k];
+        D[k] = 0.0;
+      }
+      double esq[NCOL];
 #pragma unroll
       for (int a = 0; a < (NANG > 0 ? NANG : kMaxAng); a++)
-        if (a < nang) D = fma(exp_core(tc, -c.exp_a[a], etab, 0.0), c.wgt[a], D);
+        if (a < nang) {
+#pragma unroll
+          for (int k = 0; k < NCOL; k++) {
+            double e;
+            if (SQ >= 0 && a == (SQ & 15)) e = esq[k] * esq[k];
+            else e = exp_core(tc[k], -c.exp_a[a], etab, 0.0);
+            if (SQ >= 0 && a == (SQ >> 4)) esq[k] = e;
+            D[k] = fma(e, c.wgt[a], D[k]);
+          }
+        }
     }
-    if (alive) {
-      if (KEEP) tau_keep[d] = tau;
-      trap = fma(D - Dprev, B + Bprev, trap);
-      Dprev = D; Bprev = B;
-      if (tau > c.toomuch) { last = d; alive = false; }
-    }
+#pragma unroll
+    for (int k = 0; k < NCOL; k++)
+      if (alive[k]) {
+        if (KEEP) tau_keep[k][d] = tau[k];
+        trap[k] = fma(D[k] - Dprev[k], B[k] + Bprev[k], trap[k]);
+        Dprev[k] = D[k]; Bprev[k] = B[k];
+        if (tau[k] > c.toomuch) { last[k] = d; alive[k] = false; }
+      }
   };
 
   const double *row = tab + nf;
   for (int d = 1; d < nl; d += 2, row += 2 * nf) {
-    if (!BART_WARP_ANY(alive)) break;
+    if (!any_alive()) break;
     step(row, d, true);
-    if (d + 1 >= nl || !BART_WARP_ANY(alive)) break;
+    if (d + 1 >= nl || !any_alive()) break;
     step(row + nf, d + 1, false);
   }
-  if (KEEP) *last_keep = last;
-  return cPI * (Bprev * Dprev - 0.5 * trap);
+#pragma unroll
+  for (int k = 0; k < NCOL; k++) {
+    if (KEEP && valid[k]) *last_keep[k] = last[k];
+    flux[k] = cPI * (Bprev[k] * Dprev[k] - 0.5 * trap[k]);
+  }
+}
+
+// single-column form (host emulation, tests)
+template <int NMOL, int NCIA, int NANG, bool KEEP>
+BART_HD double eclipse_column(const DevConfig &c, const double *tab, const unsigned long long *etab,
+                              int w, double *tau_keep, int *last_keep) {
+  const int ws[1] = {w};
+  const bool valid[1] = {true};
+  double *const tk[1] = {tau_keep};
+  int *const lk[1] = {last_keep};
+  double flux[1];
+  eclipse_columns<NMOL, NCIA, NANG, KEEP, 1>(c, tab, etab, ws, valid, tk, lk, flux);
+  return flux[0];
 }
 
 // ---------------------------------------------------------------------------------------

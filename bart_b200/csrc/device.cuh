@@ -37,12 +37,14 @@ constexpr int kTaylorN = 12;   // series degree 11
 //   [0] 1/T      [1] byte offset (int64 bits) of grid plane (layer, it)   [2] scattering coef (x wn^4)
 //   [3] cloud    [4..6] Simpson panel coefficients   [7] trapezoid half-width
 //   [8] T        [9] radius (file units)
-//   [10+2m, 11+2m]  W0, W1 of grid molecule m:  rho*(t1-T)/(t1-t0), rho*(T-t0)/(t1-t0)
+//   [10] exp(planck_step/T): ratio of the Planck exponentials of two columns planck_cols apart
+//   [11] spare
+//   [12+2m, 13+2m]  W0, W1 of grid molecule m:  rho*(t1-T)/(t1-t0), rho*(T-t0)/(t1-t0)
 //   [cia(f) .. +5]  CIA file f: table byte offset (int64 bits), bracket index, 4 cubic coefficients
 struct TabLayout {
   int nl, ngmol, ncia;
   static constexpr int INVT = 0, GOFF = 1, SCAT = 2, CLOUD = 3, SA = 4, SB = 5, SC = 6, TR = 7,
-                       T = 8, RAD = 9, W = 10;
+                       T = 8, RAD = 9, PF = 10, W = 12;
   BART_HD int cia(int f) const { return W + 2 * ngmol + 6 * f; }
   BART_HD int nf() const { return W + 2 * ngmol + 6 * ncia; }
   BART_HD int stride() const { return nf() * nl; }   // nf() is even: 16-byte granularity holds
@@ -73,6 +75,11 @@ struct DevConfig {
   double taylor[kTaylorN];  // Maclaurin coefficients of D, used while tau <= tau_small
   double tau_small;         // warp-uniform switch to the series
   double tau_clamp;         // exp arguments stay above -700
+  int sq_src, sq_dst;       // angles with inv_mu[sq_dst] = 2 inv_mu[sq_src] (exp by squaring), or -1
+  // Planck chaining: a thread's columns are planck_cols samples apart on the uniform wavenumber
+  // grid, so exp(c2 wn'/T) = exp(c2 wn/T) * exp(planck_step/T), planck_step = (hc/k) planck_cols dwn
+  int planck_cols;          // 0 = no chaining
+  double planck_step;
   TabLayout lay;
 };
 

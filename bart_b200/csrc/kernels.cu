@@ -123,31 +123,46 @@ atm_prep_kernel(DevConfig c, Knobs knobs, const double *__restrict__ profiles, i
 
 // ---------------------------------------------------------------------------------------
 // fused eclipse column kernel
-template <int NMOL, int NCIA, int NANG, bool KEEP>
-__global__ void __launch_bounds__(kColThreads)
+template <int NMOL, int NCIA, int NANG, bool KEEP, int SQ>
+__global__ void __launch_bounds__(kEclThreads, 8)
 eclipse_column_kernel(DevConfig c, const double *__restrict__ tabs, const int *__restrict__ status,
                       double *__restrict__ spectra, double *__restrict__ tau_keep,
                       int *__restrict__ last_keep, int nmodels, int use_tma) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar;
-  unsigned long long *s_etab = reinterpret_cast<unsigned long long *>(smem_raw);   // exp table, 1 KB
+  unsigned long long *s_etab = reinterpret_cast<unsigned long long *>(smem_raw);   // exp table, one bank row
   double *s_tab = reinterpret_cast<double *>(s_etab + kExpTabSize);
   const int m = blockIdx.x % nmodels;           // model-fastest: neighbours share grid columns
   const int tile = blockIdx.x / nmodels;
-  const int w = tile * kColThreads + threadIdx.x;
+  const int w0 = tile * (kEclThreads * kEclCols) + threadIdx.x;
   const int nd = c.lay.stride();
+  double *out = spectra + (size_t)m * c.nwave;
   if (status[m] != 0) {                          // rejected model: -1 fill (BARTfunc.py:327-330)
-    if (w < c.nwave) spectra[(size_t)m * c.nwave + w] = -1.0;
+#pragma unroll
+    for (int k = 0; k < kEclCols; k++)
+      if (w0 + k * kEclThreads < c.nwave) out[w0 + k * kEclThreads] = -1.0;
     return;
   }
   stage_table(s_tab, tabs + (size_t)m * nd, nd, &bar, use_tma != 0, s_etab);
-  // lanes past the end of the spectrum shadow the last sample: the column's warp votes need all
-  // 32 lanes
-  const int wl = min(w, c.nwave - 1);
-  double *tk = KEEP ? tau_keep + ((size_t)m * c.nwave + wl) * c.nlayer : nullptr;
-  int *lk = KEEP ? last_keep + (size_t)m * c.nwave + wl : nullptr;
-  const double f = eclipse_column<NMOL, NCIA, NANG, KEEP>(c, s_tab, s_etab, wl, tk, lk);
-  if (w < c.nwave) spectra[(size_t)m * c.nwave + w] = f;
+  // thread t carries columns w0 + t and w0 + 64 + t: each is its own coalesced stream.  Columns
+  // past the end of the spectrum shadow the last sample and idle (the warp votes need all lanes).
+  int w[kEclCols];
+  bool valid[kEclCols];
+  double *tk[kEclCols];
+  int *lk[kEclCols];
+  double flux[kEclCols];
+#pragma unroll
+  for (int k = 0; k < kEclCols; k++) {
+    const int wk = w0 + k * kEclThreads;
+    valid[k] = wk < c.nwave;
+    w[k] = min(wk, c.nwave - 1);
+    tk[k] = KEEP ? tau_keep + ((size_t)m * c.nwave + w[k]) * c.nlayer : nullptr;
+    lk[k] = KEEP ? last_keep + (size_t)m * c.nwave + w[k] : nullptr;
+  }
+  eclipse_columns<NMOL, NCIA, NANG, KEEP, kEclCols, SQ, true>(c, s_tab, s_etab, w, valid, tk, lk, flux);
+#pragma unroll
+  for (int k = 0; k < kEclCols; k++)
+    if (valid[k]) out[w[k]] = flux[k];
 }
 
 // ---------------------------------------------------------------------------------------
@@ -309,20 +324,21 @@ void launch_atm_prep(const DevConfig &c, const Knobs &k, const double *profiles,
   atm_prep_kernel<<<nmodels, 128, smem, s>>>(c, k, profiles, n_in, tabs, status, nmodels);
 }
 
-template <int NMOL, int NCIA, int NANG, bool KEEP>
+template <int NMOL, int NCIA, int NANG, bool KEEP, int SQ = -1>
 static void launch_eclipse_t(const DevConfig &c, const double *tabs, const int *status,
                              double *spectra, double *tau_keep, int *last_keep, int nmodels,
                              int use_tma, cudaStream_t s) {
   const size_t smem = table_smem(c);
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
-    cudaFuncSetAttribute(eclipse_column_kernel<NMOL, NCIA, NANG, KEEP>,
+    cudaFuncSetAttribute(eclipse_column_kernel<NMOL, NCIA, NANG, KEEP, SQ>,
                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = smem;
   }
-  const int tiles = (c.nwave + kColThreads - 1) / kColThreads;
-  eclipse_column_kernel<NMOL, NCIA, NANG, KEEP>
-      <<<(unsigned)((size_t)tiles * nmodels), kColThreads, smem, s>>>(
+  const int per = kEclThreads * kEclCols;
+  const int tiles = (c.nwave + per - 1) / per;
+  eclipse_column_kernel<NMOL, NCIA, NANG, KEEP, SQ>
+      <<<(unsigned)((size_t)tiles * nmodels), kEclThreads, smem, s>>>(
           c, tabs, status, spectra, tau_keep, last_keep, nmodels, use_tma);
 }
 
@@ -331,7 +347,10 @@ static void launch_eclipse_t(const DevConfig &c, const double *tabs, const int *
 template <int NMOL, int NCIA>
 static void launch_eclipse_nang(const DevConfig &c, const double *tabs, const int *status,
                                 double *spectra, int nmodels, int use_tma, cudaStream_t s) {
-  if (c.nang == 5) launch_eclipse_t<NMOL, NCIA, 5, false>(c, tabs, status, spectra, nullptr, nullptr, nmodels, use_tma, s);
+  // the default ray grid (0 20 40 60 80 degrees): exp(-tau/cos 60) = exp(-tau/cos 0)^2
+  if (c.nang == 5 && c.sq_src == 0 && c.sq_dst == 3)
+    launch_eclipse_t<NMOL, NCIA, 5, false, 0x03>(c, tabs, status, spectra, nullptr, nullptr, nmodels, use_tma, s);
+  else if (c.nang == 5) launch_eclipse_t<NMOL, NCIA, 5, false>(c, tabs, status, spectra, nullptr, nullptr, nmodels, use_tma, s);
   else launch_eclipse_t<NMOL, NCIA, 0, false>(c, tabs, status, spectra, nullptr, nullptr, nmodels, use_tma, s);
 }
 

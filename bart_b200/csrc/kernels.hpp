@@ -6,7 +6,9 @@
 
 namespace bart {
 
-constexpr int kColThreads = 128;      // wavenumbers per CTA, eclipse / lookup kernels
+constexpr int kColThreads = 128;      // wavenumbers per CTA, lookup kernel
+constexpr int kEclThreads = 64;       // eclipse kernel: 64 threads x kEclCols columns = 128 wavenumbers per CTA
+constexpr int kEclCols = 2;
 constexpr int kTransitThreads = 64;   // wavenumbers per CTA, transit kernel (smem: nlayer x 64 x 8 B)
 
 void launch_atm_prep(const DevConfig &c, const Knobs &k, const double *profiles, int n_in,

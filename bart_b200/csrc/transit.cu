@@ -419,6 +419,17 @@ static void do_init(int argc, char **argv) {
       c.wgt[a] = pow(sin(area[a + 1]), 2.0) - pow(sin(area[a]), 2.0);
     }
     fill_angle_consts(c);
+    // Planck chaining between the columns of one thread (device.cuh): needs the uniform grid that
+    // makewnsample always produces (makesample.c:97-104)
+    c.planck_cols = 0;
+    if (nw > kEclThreads) {
+      const double dwn = (G.wn[nw - 1] - G.wn[0]) / (nw - 1);
+      double dev = 0.0;
+      for (int i = 1; i < nw; i++) dev = std::max(dev, fabs((G.wn[i] - G.wn[i - 1]) - dwn));
+      if (dev > 1e-9 * dwn) fail("internal: the wavenumber grid is not uniform (max deviation %g)", dev);
+      c.planck_cols = kEclThreads;
+      c.planck_step = cH * cLS / cKB * kEclThreads * dwn;
+    }
   }
   upload_exp_table(G.stream);
   const double srad = o.starrad * kSUNRADIUS;                      // geometry.c:36,50

@@ -49,12 +49,16 @@ def test_spectra_vs_oracle_and_golden(name, api, get_case):
         assert relerr(spectra[m], o["spectrum"]) < TOL
         assert relerr(spectra[m], g["spectra"][m]) < TOL
     tr.debug_keep(False)
+    spectra2, _ = tr.run_batch(models)
+    # the production kernel is specialised (compile-time counts, exp(-tau/cos 60) by squaring); the
+    # introspection kernel above is the run-time-count instantiation of the same code
+    assert relerr(spectra2, spectra) < 1e-13, "keep/no-keep kernels disagree"
     for m in range(models.shape[0]):
+        assert relerr(spectra2[m], o["spectrum"]) < TOL if m == models.shape[0] - 1 else True
+        assert relerr(spectra2[m], g["spectra"][m]) < TOL
         # the reference's own single-model entry point gives the same numbers as the batch
         one = tr.run_transit(models[m])
-        assert np.array_equal(one, spectra[m])
-    spectra2, _ = tr.run_batch(models)
-    assert np.array_equal(spectra2, spectra), "keep/no-keep kernels disagree"
+        assert np.array_equal(one, spectra2[m])
     tr.free_memory()
 
 
