@@ -440,9 +440,10 @@ BART_HD ColPtrs col_ptrs(const DevConfig &c, int w) {
 // loads of the next depth before it works on the current one.
 template <int NMOL, int NCIA>
 struct CellData {
-  static constexpr bool kStatic = NMOL >= 1 && NMOL <= 4 && NCIA >= 0;
+  static constexpr bool kStatic = NMOL >= 1 && NMOL <= 4;      // grid sample preloaded (vector load)
+  static constexpr bool kStaticCia = kStatic && NCIA >= 0;     // CIA pairs preloaded too
   static constexpr int NG = !kStatic ? 1 : (NMOL == 1 ? 1 : (NMOL == 2 ? 2 : 4));
-  static constexpr int NC = kStatic && NCIA > 0 ? NCIA : 1;
+  static constexpr int NC = kStaticCia && NCIA > 0 ? NCIA : 1;
   double lo[NG], hi[NG];
   D2 k0[NC], k1[NC];
 };
@@ -464,6 +465,7 @@ BART_HD void cell_load(const DevConfig &c, const ColPtrs &P, const double *row,
     x.lo[0] = a.x; x.lo[1] = a.y; x.lo[2] = a.z; x.lo[3] = a.w;
     x.hi[0] = b.x; x.hi[1] = b.y; x.hi[2] = b.z; x.hi[3] = b.w;
   }
+  if (!CellData<NMOL, NCIA>::kStaticCia) return;
   const double *cr = row + L::W + 2 * NMOL;
   const size_t cplane = (size_t)c.nwave * 16;
 #pragma unroll
@@ -507,7 +509,7 @@ BART_HD double cell_combine(const DevConfig &c, const ColPtrs &P, const double *
   for (int f = 0; f < (NCIA >= 0 ? NCIA : kMaxCia); f++) {
     if (f < ncia) {
       D2 k0, k1;
-      if (kStatic) { k0 = x.k0[f < CellData<NMOL, NCIA>::NC ? f : 0]; k1 = x.k1[f < CellData<NMOL, NCIA>::NC ? f : 0]; }
+      if (CellData<NMOL, NCIA>::kStaticCia) { k0 = x.k0[f < CellData<NMOL, NCIA>::NC ? f : 0]; k1 = x.k1[f < CellData<NMOL, NCIA>::NC ? f : 0]; }
       else {
         const char *pq = P.cia[f] + double_to_bits(cr[6 * f]);
         k0 = ld2b(pq); k1 = ld2b(pq + cplane);

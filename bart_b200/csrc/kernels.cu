@@ -217,6 +217,7 @@ __global__ void merge_status_kernel(int *status, const int *status_col, int n) {
 
 // ---------------------------------------------------------------------------------------
 // K1 stand-alone lookup: ext[m][layer][w], layer index bottom -> top like the reference's e[r][w]
+constexpr int kLookupBatch = 8;
 template <int NMOL>
 __global__ void __launch_bounds__(kColThreads)
 extinction_kernel(DevConfig c, const double *__restrict__ tabs, double *__restrict__ ext,
@@ -238,10 +239,20 @@ extinction_kernel(DevConfig c, const double *__restrict__ tabs, double *__restri
   const int d0 = blockIdx.y * per, d1 = min(nl, d0 + per);
   double *out = ext + (size_t)m * nl * c.nwave + w;
   const ColPtrs P = col_ptrs<-1>(c, w);
-#pragma unroll 4
-  for (int d = d0; d < d1; d++)
-    out[(size_t)(nl - 1 - d) * c.nwave] =
-        cell_extinction<NMOL, -1>(c, P, s_tab + (size_t)d * c.lay.nf(), wn4, mol_only != 0);
+  // batches of kLookupBatch depths: all global loads of a batch are issued before the first is
+  // consumed (the kernel is a pure stream: what bounds it is the number of bytes in flight)
+  const int nf = c.lay.nf();
+  for (int d = d0; d < d1; d += kLookupBatch) {
+    CellData<NMOL, -1> x[kLookupBatch];
+#pragma unroll
+    for (int j = 0; j < kLookupBatch; j++)
+      if (d + j < d1) cell_load<NMOL, -1>(c, P, s_tab + (size_t)(d + j) * nf, x[j]);
+#pragma unroll
+    for (int j = 0; j < kLookupBatch; j++)
+      if (d + j < d1)
+        out[(size_t)(nl - 1 - d - j) * c.nwave] =
+            cell_combine<NMOL, -1>(c, P, s_tab + (size_t)(d + j) * nf, x[j], wn4, mol_only != 0);
+  }
 }
 
 // Grid upload: one chunk of (layer, temperature) cells in file order [cell][mol][wave] ->

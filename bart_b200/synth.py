@@ -391,3 +391,49 @@ def make_models(case, M, seed=99, molfit=("CH4",), tmin=400.0, tmax=3000.0, radi
         prof = np.vstack([T[None, :], q.T])
         out[m] = prof.ravel()
     return out
+
+
+def write_synth_opacity_stream(path, nlayer, temps, molids, wn, press_bar, seed=2026):
+    """Large grids (the high-resolution sweep: 1e5-1e6 wavenumbers, several GB): the same
+    envelope/spike/hot-band model as synth_opacity_grid without the per-cell noise, written layer
+    by layer so that the array never has to sit in host memory."""
+    rng = np.random.default_rng(seed)
+    nT, nmol, nw = len(temps), len(molids), len(wn)
+    x = (wn - wn[0]) / max(wn[-1] - wn[0], 1.0)
+    tt = (np.asarray(temps) / 1000.0)[:, None]
+    logo = np.empty((nmol, nT, nw))
+    for m in range(nmol):
+        centers = rng.uniform(0.0, 1.0, 4)
+        widths = rng.uniform(0.05, 0.2, 4)
+        amps = rng.uniform(-1.0, 2.0, 4)
+        env = np.full(nw, -4.0)
+        for c, w, a in zip(centers, widths, amps):
+            env = np.maximum(env, a - 3.0 * ((x - c) / w) ** 2)
+        base = env + rng.uniform(-1.5, 1.0, nw)
+        hot = rng.uniform(0.2, 1.5, nw)
+        logo[m] = base[None, :] + hot[None, :] * (tt - 1.0)
+    with open(path, "wb") as f:
+        f.write(struct.pack("4l", nmol, nT, nlayer, nw))
+        f.write(np.asarray(molids, dtype=np.int32).tobytes())
+        f.write(np.asarray(temps, dtype=np.float64).tobytes())
+        f.write((np.asarray(press_bar) * 1e6).astype(np.float64).tobytes())
+        f.write(np.asarray(wn, dtype=np.float64).tobytes())
+        for r in range(nlayer):
+            pfac = 0.15 * np.log10(press_bar[r] / 1e-5) / 7.0
+            # [T][mol][wave] for this layer
+            f.write(np.ascontiguousarray(np.transpose(10.0 ** (logo * (1.0 - pfac)), (1, 0, 2))).tobytes())
+    return path
+
+
+def make_hr_case(workdir, nwave=100001, ntemp=20, solution="eclipse", seed=2026):
+    """High-resolution sweep shape (BASELINE.json configs[4]): nwave samples over 910-3333 cm-1,
+    100 layers, ntemp grid temperatures from 400 K in 100 K steps, 4 molecules + H2-H2 CIA."""
+    wnlow, wnhigh = 910.0, 3333.0
+    wndelt = (wnhigh - wnlow) / (nwave - 1)
+    thigh = 400.0 + 100.0 * (ntemp - 1)
+    sh = dict(wnlow=wnlow, wnhigh=wnhigh, wndelt=wndelt, mols=["H2O", "CO2", "CO", "CH4"], toomuch=10.0)
+    case = make_case(workdir, shape=sh, solution=solution, seed=seed, thigh=thigh, with_grid=False)
+    wn = case["wn"]
+    write_synth_opacity_stream(case["opacity"], case["nlayer"], case["grid_temps"], case["grid_molids"],
+                               wn, case["press_bar"], seed=seed + 1)
+    return case
