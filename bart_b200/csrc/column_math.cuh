@@ -254,10 +254,20 @@ BART_HD int prep_layer(const DevConfig &c, const double *in, int l, double *rho,
   return sumq > 1.001 ? REJ_SUMQ : 0;
 }
 
-// atm_prep stage 2: hydrostatic radii, sequential in the layer index.
-// Reference: radpress readatm.c:787-865 (same expression order).
+// atm_prep stage 2: hydrostatic radii.  Reference: radpress readatm.c:787-865 integrates
+//   r_i = r_{i+1} - 1/2 (T_i/mu_i + T_{i+1}/mu_{i+1}) (KB/AMU ln(p_i/p_{i+1}) / g_{i+1}) / rfct
+// with the gravity carried along as g <- g (r_{i+1}/r_i)^2, i.e. g_i = g0 (r0/r_i)^2.  Here the
+// layer-only factor hc_i = 1/2 (T_i/mu_i + T_{i+1}/mu_{i+1}) KB/AMU ln(p_i/p_{i+1}) / rfct is
+// computed in parallel over layers (hydro_coef) and the sequential part is the two-instruction
+// recurrence r_i = r_{i+1} - hc_i r_{i+1}^2 / (g0 r0^2) (hydrostatic_radii); the gravity product
+// telescopes, so the results agree with the reference's running product to rounding (1e-15).
+BART_HD double hydro_coef(const DevConfig &c, const double *temp, const double *mu, int i) {
+  return 0.5 * (temp[i] / mu[i] + temp[i + 1] / mu[i + 1]) *
+         (cKB / cAMU * log(c.press[i] / c.press[i + 1])) / c.rfct;
+}
+
 BART_HD void hydrostatic_radii(const DevConfig &c, double r0, const double *temp, const double *mu,
-                               double *radius) {
+                               const double *hc, double *radius) {
   const int nl = c.nlayer;
   const double *pr = c.press;
   const double p0 = c.p0, g0 = c.gsurf, rfct = c.rfct;
@@ -280,21 +290,16 @@ BART_HD void hydrostatic_radii(const DevConfig &c, double r0, const double *temp
     const double m0 = mu[i0] + ((mu[i1] - mu[i0]) / lr) * lp;
     radius[i0] = r0 - 0.5 * (temp[i0] / mu[i0] + t0 / m0) * (cKB / cAMU * log(pr[i0] / p0) / g0) / rfct;
   }
-  double ratio = r0 / radius[i0];
-  double g = g0 * (ratio * ratio);
+  const double q = 1.0 / (g0 * r0 * r0);
+  double r = radius[i0];
   for (int i = i0 - 1; i >= 0; i--) {
-    radius[i] = radius[i + 1] - 0.5 * (temp[i] / mu[i] + temp[i + 1] / mu[i + 1]) *
-                (cKB / cAMU * log(pr[i] / pr[i + 1]) / g) / rfct;
-    ratio = radius[i + 1] / radius[i];
-    g = g * (ratio * ratio);
+    r = fma(-(hc[i] * q), r * r, r);
+    radius[i] = r;
   }
-  ratio = r0 / radius[i0];
-  g = g0 * (ratio * ratio);
+  r = radius[i0];
   for (int i = i0 + 1; i < nl; i++) {
-    radius[i] = radius[i - 1] + 0.5 * (temp[i] / mu[i] + temp[i - 1] / mu[i - 1]) *
-                (cKB / cAMU * log(pr[i - 1] / pr[i]) / g) / rfct;
-    ratio = radius[i - 1] / radius[i];
-    g = g * (ratio * ratio);
+    r = fma(hc[i - 1] * q, r * r, r);
+    radius[i] = r;
   }
 }
 

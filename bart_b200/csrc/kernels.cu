@@ -101,6 +101,7 @@ atm_prep_kernel(DevConfig c, Knobs knobs, const double *__restrict__ profiles, i
   double *s_rho = reinterpret_cast<double *>(smem_raw);        // [nspec][nl]
   double *s_mu = s_rho + (size_t)c.nspec * nl;                 // [nl]
   double *s_rad = s_mu + nl;                                   // [nl]
+  double *s_hc = s_rad + nl;                                   // [nl]
   __shared__ int s_status;
   if (threadIdx.x == 0) s_status = 0;
   __syncthreads();
@@ -110,7 +111,9 @@ atm_prep_kernel(DevConfig c, Knobs knobs, const double *__restrict__ profiles, i
   if (st) atomicOr(&s_status, st);
   __syncthreads();
   const KnobVals kv = knobs_for(knobs, m);
-  if (threadIdx.x == 0) hydrostatic_radii(c, kv.r0, in, s_mu, s_rad);
+  for (int l = threadIdx.x; l < nl - 1; l += blockDim.x) s_hc[l] = hydro_coef(c, in, s_mu, l);
+  __syncthreads();
+  if (threadIdx.x == 0) hydrostatic_radii(c, kv.r0, in, s_mu, s_hc, s_rad);
   __syncthreads();
   double *tab = tabs + (size_t)m * c.lay.stride();
   st = 0;
@@ -326,7 +329,7 @@ void launch_grid_relayout(const double *in, double *out, int ncells, int nmol, i
 
 void launch_atm_prep(const DevConfig &c, const Knobs &k, const double *profiles, int n_in,
                      double *tabs, int *status, int nmodels, cudaStream_t s) {
-  const size_t smem = ((size_t)c.nspec + 2) * c.nlayer * sizeof(double);
+  const size_t smem = ((size_t)c.nspec + 3) * c.nlayer * sizeof(double);
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
     cudaFuncSetAttribute(atm_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

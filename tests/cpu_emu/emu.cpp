@@ -130,7 +130,9 @@ int emu_run(const double *in, double *spectrum, double *tau, int *last, double *
   int status = 0;
   for (int l = 0; l < nl; l++) status |= prep_layer(c, in, l, rho.data() + l, nl, &mu[l]);
   KnobVals kv = knobs_for(E->k, 0);
-  hydrostatic_radii(c, kv.r0, in, mu.data(), rad.data());
+  std::vector<double> hc(nl);
+  for (int l = 0; l + 1 < nl; l++) hc[l] = hydro_coef(c, in, mu.data(), l);
+  hydrostatic_radii(c, kv.r0, in, mu.data(), hc.data(), rad.data());
   for (int d = 0; d < nl; d++) status |= prep_table_row(c, kv, d, in, rho.data(), nl, rad.data(), tab.data());
   if (radius) for (int l = 0; l < nl; l++) radius[l] = rad[l];
   if (status) { for (int w = 0; w < nw; w++) spectrum[w] = -1; return status; }
