@@ -74,6 +74,8 @@ def lib():
     L.bart_build_opacity_slice.argtypes = [C.c_int, C.c_int, dp]
     L.bart_builder_stats.restype = C.c_longlong
     L.bart_builder_stats.argtypes = [C.POINTER(C.c_longlong)] * 3
+    L.bart_builder_phase_ms.restype = C.c_double
+    L.bart_builder_phase_ms.argtypes = [C.c_char_p]
     L.bart_line_bins.restype = C.c_longlong
     L.bart_line_bins.argtypes = [C.POINTER(C.c_longlong), C.c_longlong]
     L.bart_voigt_profile.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_float), C.c_longlong,

@@ -30,6 +30,9 @@
 #include <cstring>
 #include <algorithm>
 #include <vector>
+#include <map>
+#include <string>
+#include <chrono>
 #include <unistd.h>
 #include <fcntl.h>
 
@@ -81,6 +84,23 @@ struct BuilderState {
   double *d_out = nullptr;                  // [nlayer][ngmol][nwave] for the current temperature
   void *d_cellinfo = nullptr;
   bool lines_loaded = false, profiles_ready = false;
+  // per-phase wall/device milliseconds (bart_builder_phase_ms)
+  std::map<std::string, double> phase_ms;
+};
+
+// Times a phase of the build on stream `s` with CUDA events (the builder synchronises between
+// phases anyway, so this costs nothing on the data path).
+struct PhaseTimer {
+  BuilderState *b; const char *name; cudaStream_t s; cudaEvent_t e0, e1;
+  PhaseTimer(BuilderState *b_, const char *n, cudaStream_t s_) : b(b_), name(n), s(s_) {
+    cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, s);
+  }
+  ~PhaseTimer() {
+    cudaEventRecord(e1, s); cudaEventSynchronize(e1);
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    b->phase_ms[name] += ms;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+  }
 };
 
 // ---------------------------------------------------------------------------------------
@@ -510,6 +530,7 @@ static void build_profiles(BuilderState *b, const Options &o, cudaStream_t s) {
   for (auto &j : jobs) maxn = std::max(maxn, j.nwn);
   // grid.y is limited to 65535 jobs; 60x60 profiles fit
   const int chunk = 32768;
+  PhaseTimer pt(b, "voigt_table", s);
   for (size_t j0 = 0; j0 < jobs.size(); j0 += chunk) {
     const int nj = (int)std::min<size_t>(chunk, jobs.size() - j0);
     dim3 grid((maxn + 127) / 128, nj);
@@ -531,7 +552,10 @@ static void load_lines(BuilderState *b, const Options &o, Tli &t, const std::vec
   double lo = wn.front(), hi_hint;
   // readdatarng selects with the HINTED limits wns.i / wns.f (readlineinfo.c:435-436)
   hi_hint = o.wnhigh > 0 ? o.wnhigh * o.wnfct : 1.0 / (o.wllow * o.wlfct);
+  auto tp0 = std::chrono::steady_clock::now();
   read_tli_lines(o.linedb, t, lo, hi_hint);
+  auto tp1 = std::chrono::steady_clock::now();
+  b->phase_ms["read_tli_host"] += std::chrono::duration<double, std::milli>(tp1 - tp0).count();
   const long long n = (long long)t.wl.size();
   b->nlines = n;
   b->d_wl = dev_upload(t.wl); b->d_elow = dev_upload(t.elow); b->d_gf = dev_upload(t.gf);
@@ -561,6 +585,7 @@ static void load_lines(BuilderState *b, const Options &o, Tli &t, const std::vec
   // isotope while |wavn - owns[iown_leader]| < odwn.  Out-of-range lines never lead, but are
   // absorbed when they follow a leader (the reference does not re-test the range in its while
   // loop).  The grouping does not depend on temperature or layer, so it is done once, here.
+  auto tg0 = std::chrono::steady_clock::now();
   std::vector<long long> bounds;            // [ngroups+1] into the grouped line arrays
   std::vector<int> giown, gidwn;
   std::vector<short> giso;
@@ -594,6 +619,8 @@ static void load_lines(BuilderState *b, const Options &o, Tli &t, const std::vec
   bounds.push_back((long long)c_wavn.size());
   for (int k = prev_iso + 1; k <= b->niso; k++) b->iso_gbeg[k] = (long long)giown.size();
   b->ngroups = (long long)giown.size();
+  b->phase_ms["grouping_host"] += std::chrono::duration<double, std::milli>(
+      std::chrono::steady_clock::now() - tg0).count();
   b->d_gstart = dev_upload(bounds);
   b->d_giown = dev_upload(giown); b->d_gidwn = dev_upload(gidwn); b->d_giso = dev_upload(giso);
   b->d_gwavn = dev_upload(gwavn);
@@ -630,21 +657,27 @@ static void build_temperature(BuilderState *b, const Options &o, const Atmospher
   double *d_facfull = dev_upload(facfull), *d_fac2 = dev_upload(fac2);
   BCUDA(cudaMemsetAsync(b->d_kmax, 0, kMaxGridMol * 8, s));
   if (b->nlines > 0) {
+    PhaseTimer pt(b, "kmax", s);
     kmax_kernel<<<148 * 4, 256, 0, s>>>(b->d_wavn, b->d_elow, b->d_gf, b->d_isoid, b->d_inrange, b->nlines,
                                         T, d_facfull, d_iso_gmol, (unsigned long long *)b->d_kmax, b->ngmol);
     BCUDA(cudaGetLastError());
   }
   if (b->ngroups > 0) {
+    PhaseTimer pt(b, "strength", s);
     strength_kernel<<<(unsigned)((b->ngroups + 255) / 256), 256, 0, s>>>(
         b->d_gstart, b->d_giso, b->d_c_wavn, b->d_c_elow, b->d_c_gf, b->ngroups, T, d_fac2, b->d_gS);
     BCUDA(cudaGetLastError());
   }
   CellIso *cells = (CellIso *)b->d_cellinfo;
+  {
+  PhaseTimer pt(b, "widths", s);
   widths_kernel<<<nl, std::max(32, b->niso), 0, s>>>(
       cells, nl, b->niso, ns, T, b->d_density, d_spec_mass, d_spec_radius, d_iso_mass, d_iso_spec,
       d_iso_gmol, b->d_aDop, b->d_aLor, b->nDop, b->nLor, b->d_prof_size, b->osamp, b->wn_lo,
       d_iso_gbeg, b->d_gwavn, b->d_gS, b->d_kmax, o.ethreshold);
   BCUDA(cudaGetLastError());
+  }
+  PhaseTimer pt(b, "accumulate", s);
   BCUDA(cudaMemsetAsync(b->d_out, 0, (size_t)nl * b->ngmol * b->nwave * 8, s));
   dim3 grid((b->nwave + kAccThreads - 1) / kAccThreads, nl);
   accumulate_kernel<<<grid, kAccThreads, 0, s>>>(
@@ -690,9 +723,12 @@ void builder_slice(BuilderState *&b, const Options &o, const Atmosphere &a, cons
   for (int it = t_begin; it < t_end; it++) {
     build_temperature(b, o, a, m, t, it, s, d_iso_spec, d_iso_gmol, d_iso_mass, d_spec_mass,
                       d_spec_radius, d_iso_gbeg, d_neval);
+    auto td0 = std::chrono::steady_clock::now();
     BCUDA(cudaMemcpy(tmp.data(), b->d_out, tmp.size() * 8, cudaMemcpyDeviceToHost));
     for (int r = 0; r < nl; r++)
       memcpy(host_out + ((size_t)r * nt + (it - t_begin)) * plane, tmp.data() + (size_t)r * plane, plane * 8);
+    b->phase_ms["d2h"] += std::chrono::duration<double, std::milli>(
+        std::chrono::steady_clock::now() - td0).count();
   }
   unsigned long long ne = 0;
   BCUDA(cudaMemcpy(&ne, d_neval, 8, cudaMemcpyDeviceToHost));
@@ -754,6 +790,12 @@ long long builder_stats(BuilderState *b, long long *nlines, long long *ngroups, 
   if (ngroups) *ngroups = b->ngroups;
   if (neval) *neval = b->neval;
   return b->nlines;
+}
+
+double builder_phase_ms(BuilderState *b, const char *name) {
+  if (!b) return -1.0;
+  auto it = b->phase_ms.find(name);
+  return it == b->phase_ms.end() ? 0.0 : it->second;
 }
 
 long long builder_line_bins(BuilderState *b, long long *iown_out, long long capacity) {

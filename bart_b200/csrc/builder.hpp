@@ -18,6 +18,9 @@ void builder_slice(BuilderState *&b, const Options &o, const Atmosphere &a, cons
                    Tli &t, const std::vector<double> &wn, cudaStream_t s, int t_begin, int t_end,
                    double *host_out);
 long long builder_stats(BuilderState *b, long long *nlines, long long *ngroups, long long *neval);
+// milliseconds spent in a build phase so far: "voigt_table","line_index","grouping_host","kmax",
+// "strength","widths","accumulate","d2h"
+double builder_phase_ms(BuilderState *b, const char *name);
 long long builder_line_bins(BuilderState *b, long long *iown_out, long long capacity);
 int builder_profile(BuilderState *b, int idop, int ilor, float *out, long long capacity,
                     long long *halfsize);

@@ -721,10 +721,13 @@ BART_HD double eclipse_column(const DevConfig &c, const double *tab, const unsig
 // impact parameter b = r(depth d), top-aligned Simpson panels with a trapezoid on the bottom
 // interval when the count is even, the two-point case through the reference's 3-point
 // construction, result x2 (both halves of the chord) and x rfct (tau.c:274).
-BART_HD void transit_weight_row(const DevConfig &c, const double *tab, int d, double *wt) {
+// `W(i)` returns a reference to where the weight of depth i lives (packed row, or the tiled layout
+// below).
+template <class Acc>
+BART_HD void transit_weight_row_acc(const DevConfig &c, const double *tab, int d, Acc W) {
   const int nf = c.lay.nf();
   auto rad = [&](int i) { return tab[(size_t)i * nf + TabLayout::RAD]; };   // depth-indexed radii
-  for (int i = 0; i <= d; i++) wt[i] = 0.0;
+  for (int i = 0; i <= d; i++) W(i) = 0.0;
   if (d == 0) return;
   const double b = rad(d);
   const double f = 2.0 * c.rfct;
@@ -735,8 +738,8 @@ BART_HD void transit_weight_row(const DevConfig &c, const double *tab, int d, do
     const double hsum = h0 + h1, hratio = h1 / h0, hfactor = hsum * hsum / (h0 * h1);
     const double a0 = (2.0 - hratio) * hsum / 6.0, a1 = hfactor * hsum / 6.0,
                  a2 = (2.0 - 1.0 / hratio) * hsum / 6.0;
-    wt[1] = f * (a0 + 0.5 * a1);                             // bottom sample (depth 1)
-    wt[0] = f * (a2 + 0.5 * a1);
+    W(1) = f * (a0 + 0.5 * a1);                              // bottom sample (depth 1)
+    W(0) = f * (a2 + 0.5 * a1);
     return;
   }
   // s at depth i
@@ -745,15 +748,41 @@ BART_HD void transit_weight_row(const DevConfig &c, const double *tab, int d, do
     const double sB = sdep(2 * p + 2), sM = sdep(2 * p + 1), sT = sdep(2 * p);
     const double h0 = sM - sB, h1 = sT - sM;
     const double hsum = h0 + h1, hratio = h1 / h0, hfactor = hsum * hsum / (h0 * h1);
-    wt[2 * p + 2] += f * (2.0 - hratio) * hsum / 6.0;
-    wt[2 * p + 1] += f * hfactor * hsum / 6.0;
-    wt[2 * p]     += f * (2.0 - 1.0 / hratio) * hsum / 6.0;
+    W(2 * p + 2) += f * (2.0 - hratio) * hsum / 6.0;
+    W(2 * p + 1) += f * hfactor * hsum / 6.0;
+    W(2 * p)     += f * (2.0 - 1.0 / hratio) * hsum / 6.0;
   }
   if (d & 1) {                                               // even count: bottom trapezoid
     const double h = sdep(d - 1);
-    wt[d]     += f * h / 2.0;
-    wt[d - 1] += f * h / 2.0;
+    W(d)     += f * h / 2.0;
+    W(d - 1) += f * h / 2.0;
   }
+}
+
+// packed row: wt[i], i = 0..d
+BART_HD void transit_weight_row(const DevConfig &c, const double *tab, int d, double *wt) {
+  transit_weight_row_acc(c, tab, d, [wt](int i) -> double & { return wt[i]; });
+}
+
+// Tiled layout of one model's chord weights for the tile kernel: depth chunks of kTrChunk; chunk
+// ch holds rows i = 0 .. min(kTrChunk (ch+1), nl) - 1 (the layers a chord of that chunk can cross),
+// each row kTrRow doubles = kTrChunk / kTrTD groups of (kTrTD weights + padding to 16 bytes):
+// element (depth d, layer i) sits at chunk d / kTrChunk, row i, group (d % kTrChunk) / kTrTD,
+// slot d % kTrTD; weights with i > d are zero.  One chunk is one contiguous block (one bulk copy)
+// and a warp's kTrTD weights for layer i are one aligned 48-byte broadcast read.
+constexpr int kTrChunk = 20, kTrTD = 5, kTrGroup = 6, kTrRow = (kTrChunk / kTrTD) * kTrGroup;
+BART_HD int tr_rows(int nl, int ch) { const int r = kTrChunk * (ch + 1); return r < nl ? r : nl; }
+BART_HD size_t tr_chunk_off(int nl, int ch) {
+  size_t rows = 0;
+  for (int k = 0; k < ch; k++) rows += tr_rows(nl, k);
+  return rows * kTrRow;
+}
+BART_HD int tr_nchunks(int nl) { return (nl + kTrChunk - 1) / kTrChunk; }
+BART_HD size_t tr_stride(int nl) { return tr_chunk_off(nl, tr_nchunks(nl)); }
+BART_HD void transit_weight_row_tiled(const DevConfig &c, const double *tab, int d, double *wm) {
+  const int ch = d / kTrChunk, dl = d % kTrChunk;
+  double *base = wm + tr_chunk_off(c.nlayer, ch) + (dl / kTrTD) * kTrGroup + dl % kTrTD;
+  transit_weight_row_acc(c, tab, d, [base](int i) -> double & { return base[(size_t)i * kTrRow]; });
 }
 
 // Transit column: tau(d) by the chord weights, stop at toomuch, then the modulation integral

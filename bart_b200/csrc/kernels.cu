@@ -170,47 +170,179 @@ eclipse_column_kernel(DevConfig c, const double *__restrict__ tabs, const int *_
 
 // ---------------------------------------------------------------------------------------
 // transit geometry
+//
+// transit_weights_kernel: one CTA per model, thread <-> depth; writes the chord weights in the
+// tiled layout of column_math.cuh (zero-filled first: weights above the diagonal are zero).
 __global__ void __launch_bounds__(128)
 transit_weights_kernel(DevConfig c, const double *__restrict__ tabs, double *__restrict__ wts,
                        int nmodels) {
   const int m = blockIdx.x;
   if (m >= nmodels) return;
   const int nl = c.nlayer;
+  const size_t stride = tr_stride(nl);
   const double *tab = tabs + (size_t)m * c.lay.stride();
-  double *wm = wts + (size_t)m * ((size_t)nl * (nl + 1) / 2);
-  for (int d = threadIdx.x; d < nl; d += blockDim.x)
-    transit_weight_row(c, tab, d, wm + (size_t)d * (d + 1) / 2);
+  double *wm = wts + (size_t)m * stride;
+  for (size_t i = threadIdx.x; i < stride; i += blockDim.x) wm[i] = 0.0;
+  __syncthreads();
+  for (int d = threadIdx.x; d < nl; d += blockDim.x) transit_weight_row_tiled(c, tab, d, wm);
 }
 
-template <bool KEEP>
-__global__ void __launch_bounds__(kTransitThreads)
-transit_column_kernel(DevConfig c, const double *__restrict__ tabs, const double *__restrict__ wts,
-                      const int *__restrict__ status, int *__restrict__ status_col,
-                      double *__restrict__ spectra,
-                      double *__restrict__ tau_keep, int *__restrict__ last_keep, int nmodels,
-                      int use_tma) {
+// transit_tile_kernel: CTA = one model x 64 wavenumbers, 4 warps.  The chord optical depth
+// tau(d, w) = sum_{i<=d} W[d][i] er[i][w] (totaltau1, slantpath.c:18-108) is a triangular
+// matrix product per model; it is evaluated in depth chunks of kTrChunk with a register tile
+// (lane: 2 wavenumbers x 5 depths; warp: 64 wavenumbers x 5 depths; CTA: the chunk's 20 depths):
+//   phase A  all threads: opacity lookup of the chunk's 20 layers -> er[layer][64] in shared memory
+//   phase B  tau of the chunk: er rows as conflict-free 16-byte reads, the chunk's weights (bulk-
+//            async copy into shared memory, issued before phase A) as warp-wide broadcasts
+//   phase C  threads 0..63, one column each: exp(-tau), Simpson scan over impact parameter
+//            (modulation1, slantpath.c:350-436), first tau > toomuch -> last
+// and the CTA leaves the chunk loop when every column has passed toomuch (tau.c:277-287), so the
+// work follows the deepest column of the tile.  Summation order per (d, w) is i = 0..d, the same
+// as the single-column form transit_column (tests/cpu_emu).
+constexpr int kTrW = 64, kTrThreads = 128, kTrLoadBatch = 5;
+
+template <int NMOL, int NCIA, bool KEEP>
+__global__ void __launch_bounds__(kTrThreads, 2)
+transit_tile_kernel(DevConfig c, const double *__restrict__ tabs, const double *__restrict__ wts,
+                    const int *__restrict__ status, int *__restrict__ status_col,
+                    double *__restrict__ spectra, double *__restrict__ tau_keep,
+                    int *__restrict__ last_keep, int nmodels, int use_tma) {
+  typedef TabLayout L;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ __align__(8) uint64_t bar;
-  const int nd = c.lay.stride();
+  __shared__ __align__(8) uint64_t bar, bar_w;
+  const int nl = c.nlayer, nf = c.lay.nf(), nd = c.lay.stride();
   unsigned long long *s_etab = reinterpret_cast<unsigned long long *>(smem_raw);
   double *s_tab = reinterpret_cast<double *>(s_etab + kExpTabSize);
-  double *s_er = s_tab + nd;                                   // [nl][kTransitThreads]
+  double *s_wt = s_tab + nd;                                   // [<= nl][kTrRow]
+  double *s_er = s_wt + (size_t)nl * kTrRow;                   // [nl][kTrW]
+  double *s_tau = s_er + (size_t)nl * kTrW;                    // [kTrChunk][kTrW]
   const int m = blockIdx.x % nmodels;
   const int tile = blockIdx.x / nmodels;
-  const int w = tile * kTransitThreads + threadIdx.x;
-  if (status[m] != 0) {
-    if (w < c.nwave) spectra[(size_t)m * c.nwave + w] = -1.0;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int wl = t & (kTrW - 1), dh = t >> 6;                  // lookup mapping: column, depth parity
+  const int wcol = tile * kTrW + wl;
+  const bool valid = wcol < c.nwave;
+  const int w = valid ? wcol : c.nwave - 1;                    // columns past the end shadow the last one
+  if (status[m] != 0) {                                        // rejected model: -1 fill
+    if (t < kTrW && valid) spectra[(size_t)m * c.nwave + w] = -1.0;
     return;
   }
+  if (t == 0) mbar_init(&bar_w, 1);
   stage_table(s_tab, tabs + (size_t)m * nd, nd, &bar, use_tma != 0, s_etab);
-  if (w >= c.nwave) return;
-  const double *wm = wts + (size_t)m * ((size_t)c.nlayer * (c.nlayer + 1) / 2);
-  double *tk = KEEP ? tau_keep + ((size_t)m * c.nwave + w) * c.nlayer : nullptr;
-  int *lk = KEEP ? last_keep + (size_t)m * c.nwave + w : nullptr;
-  int st = 0;
-  const double r = transit_column<0, -1, KEEP>(c, s_tab, s_etab, wm, w, s_er + threadIdx.x, kTransitThreads, tk, lk, &st);
-  spectra[(size_t)m * c.nwave + w] = r;
-  if (st) atomicOr(&status_col[m], st);
+  const double *wm = wts + (size_t)m * tr_stride(nl);
+  const ColPtrs P = col_ptrs<NCIA>(c, w);
+  const double wn = c.wn[w];
+  const double wn4 = (wn * wn) * (wn * wn);
+  double *tk = KEEP ? tau_keep + ((size_t)m * c.nwave + w) * nl : nullptr;
+  // per-column state of phase C (threads 0..63)
+  double S = 0.0, f1 = 0.0, f2 = 0.0, tau = 0.0;
+  int last = nl - 1;
+  bool done = false;
+  uint32_t wphase = 0;
+  const int nchunks = tr_nchunks(nl);
+  for (int ch = 0; ch < nchunks; ch++) {
+    const int d0 = ch * kTrChunk;
+    const int dn = min(kTrChunk, nl - d0);
+    const int rows = tr_rows(nl, ch);
+    const double *wsrc = wm + tr_chunk_off(nl, ch);
+    if (use_tma) {
+      if (t == 0) {
+        const uint32_t bytes = (uint32_t)rows * kTrRow * 8u;
+        mbar_expect_tx(&bar_w, bytes);
+        bulk_g2s(s_wt, wsrc, bytes, &bar_w);
+      }
+    } else {
+      for (int i = t; i < rows * kTrRow; i += kTrThreads) s_wt[i] = wsrc[i];
+    }
+    // ---- phase A: lookup, kTrChunk / 2 layers per thread in batches of independent loads
+#pragma unroll
+    for (int j0 = 0; j0 < kTrChunk / 2; j0 += kTrLoadBatch) {
+      CellData<NMOL, NCIA> x[kTrLoadBatch];
+#pragma unroll
+      for (int j = 0; j < kTrLoadBatch; j++) {
+        const int d = d0 + dh + 2 * (j0 + j);
+        if (d < nl) cell_load<NMOL, NCIA>(c, P, s_tab + (size_t)d * nf, x[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < kTrLoadBatch; j++) {
+        const int d = d0 + dh + 2 * (j0 + j);
+        if (d < nl)
+          s_er[(size_t)d * kTrW + wl] = cell_combine<NMOL, NCIA>(c, P, s_tab + (size_t)d * nf, x[j], wn4, false);
+      }
+    }
+    __syncthreads();
+    if (use_tma) { mbar_wait(&bar_w, wphase); wphase ^= 1u; }
+    // ---- phase B: tau of depths d0 + 5 warp .. + 4 for columns 2 lane, 2 lane + 1
+    {
+      const int dg = d0 + kTrTD * warp;
+      if (dg < nl) {
+        const int kmax = min(dg + kTrTD - 1, nl - 1);
+        double a0[kTrTD], a1[kTrTD];
+#pragma unroll
+        for (int j = 0; j < kTrTD; j++) { a0[j] = 0.0; a1[j] = 0.0; }
+        const double *wr = s_wt + warp * kTrGroup;
+        const double *ep = s_er + 2 * lane;
+#pragma unroll 4
+        for (int i = 0; i <= kmax; i++) {
+          const D2 e = ld2(ep + (size_t)i * kTrW);
+          const D2 w01 = ld2(wr + (size_t)i * kTrRow), w23 = ld2(wr + (size_t)i * kTrRow + 2);
+          const double w4 = wr[(size_t)i * kTrRow + 4];
+          a0[0] = fma(w01.x, e.x, a0[0]); a1[0] = fma(w01.x, e.y, a1[0]);
+          a0[1] = fma(w01.y, e.x, a0[1]); a1[1] = fma(w01.y, e.y, a1[1]);
+          a0[2] = fma(w23.x, e.x, a0[2]); a1[2] = fma(w23.x, e.y, a1[2]);
+          a0[3] = fma(w23.y, e.x, a0[3]); a1[3] = fma(w23.y, e.y, a1[3]);
+          a0[4] = fma(w4, e.x, a0[4]);    a1[4] = fma(w4, e.y, a1[4]);
+        }
+#pragma unroll
+        for (int j = 0; j < kTrTD; j++)
+          if (dg + j < nl) {
+            D2 v; v.x = a0[j]; v.y = a1[j];
+            *reinterpret_cast<D2 *>(s_tau + (size_t)(kTrTD * warp + j) * kTrW + 2 * lane) = v;
+          }
+      }
+    }
+    __syncthreads();
+    // ---- phase C: one thread per column
+    if (t < kTrW && !done) {
+      for (int j = 0; j < dn; j++) {
+        const int d = d0 + j;
+        const double *row = s_tab + (size_t)d * nf;
+        tau = s_tau[(size_t)j * kTrW + t];
+        if (KEEP && valid) tk[d] = tau;
+        const double bd = row[L::RAD] * c.rfct;
+        const double fd = fast_exp_neg(-tau, s_etab) * bd;
+        if (d >= 2 && !(d & 1)) S += row[L::SA] * fd + row[L::SB] * f1 + row[L::SC] * f2;
+        f2 = f1; f1 = fd;
+        if (tau > c.toomuch) { last = d; done = true; break; }
+      }
+    }
+    if (__syncthreads_and(t >= kTrW || done)) break;
+  }
+  if (t >= kTrW || !valid) return;
+  if (KEEP) last_keep[(size_t)m * c.nwave + w] = last;
+  // modulation1 (slantpath.c:350-436): same tail as transit_column
+  int n;
+  if (last < nl - 1) {
+    const int dd = last + 1;                                   // appended zero-integrand point
+    const double *row = s_tab + (size_t)dd * nf;
+    if (dd >= 2 && !(dd & 1)) S += row[L::SB] * f1 + row[L::SC] * f2;
+    f2 = f1; f1 = 0.0;
+    n = dd + 1;
+  } else n = nl;
+  double res;
+  if (n < 3) { atomicOr(&status_col[m], REJ_FEWPTS); res = -1.0; }
+  else {
+    if (!(n & 1)) S += s_tab[(size_t)(n - 1) * nf + L::TR] * (f1 + f2);
+    const double btop = s_tab[L::RAD] * c.rfct;
+    res = btop * btop - 2.0 * S;
+    if (c.transparent) {
+      const double maxtau = tau > c.toomuch ? tau : c.toomuch;
+      const double bl = s_tab[(size_t)(n - 1) * nf + L::RAD] * c.rfct;
+      res -= fast_exp_neg(-maxtau, s_etab) * bl * bl;
+    }
+    res *= c.inv_srad2;
+  }
+  spectra[(size_t)m * c.nwave + w] = res;
 }
 
 __global__ void merge_status_kernel(int *status, const int *status_col, int n) {
@@ -399,27 +531,55 @@ void launch_merge_status(int *status, const int *status_col, int nmodels, cudaSt
   merge_status_kernel<<<(nmodels + 255) / 256, 256, 0, s>>>(status, status_col, nmodels);
 }
 
-void launch_transit(const DevConfig &c, const double *tabs, double *wts, const int *status,
-                    int *status_col, double *spectra, double *tau_keep, int *last_keep,
-                    int nmodels, bool keep, int use_tma, cudaStream_t s) {
-  transit_weights_kernel<<<nmodels, 128, 0, s>>>(c, tabs, wts, nmodels);
-  const size_t smem = table_smem(c) + (size_t)c.nlayer * kTransitThreads * sizeof(double);
+size_t transit_weights_stride(int nlayer) { return tr_stride(nlayer); }
+
+template <int NMOL, int NCIA, bool KEEP>
+static void launch_transit_t(const DevConfig &c, const double *tabs, const double *wts,
+                             const int *status, int *status_col, double *spectra, double *tau_keep,
+                             int *last_keep, int nmodels, int use_tma, cudaStream_t s) {
+  const size_t smem = table_smem(c) + ((size_t)c.nlayer * (kTrRow + kTrW) + (size_t)kTrChunk * kTrW) * sizeof(double);
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
-    cudaFuncSetAttribute(transit_column_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)smem);
-    cudaFuncSetAttribute(transit_column_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)smem);
+    cudaFuncSetAttribute(transit_tile_kernel<NMOL, NCIA, KEEP>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = smem;
   }
-  const int tiles = (c.nwave + kTransitThreads - 1) / kTransitThreads;
-  const unsigned grid = (unsigned)((size_t)tiles * nmodels);
-  if (keep)
-    transit_column_kernel<true><<<grid, kTransitThreads, smem, s>>>(
-        c, tabs, wts, status, status_col, spectra, tau_keep, last_keep, nmodels, use_tma);
-  else
-    transit_column_kernel<false><<<grid, kTransitThreads, smem, s>>>(
-        c, tabs, wts, status, status_col, spectra, tau_keep, last_keep, nmodels, use_tma);
+  const int tiles = (c.nwave + kTrW - 1) / kTrW;
+  transit_tile_kernel<NMOL, NCIA, KEEP><<<(unsigned)((size_t)tiles * nmodels), kTrThreads, smem, s>>>(
+      c, tabs, wts, status, status_col, spectra, tau_keep, last_keep, nmodels, use_tma);
+}
+
+template <int NMOL>
+static void launch_transit_ncia(const DevConfig &c, const double *tabs, const double *wts,
+                                const int *status, int *status_col, double *spectra, int nmodels,
+                                int use_tma, cudaStream_t s) {
+  switch (c.ncia) {
+    case 0: launch_transit_t<NMOL, 0, false>(c, tabs, wts, status, status_col, spectra, nullptr, nullptr, nmodels, use_tma, s); break;
+    case 1: launch_transit_t<NMOL, 1, false>(c, tabs, wts, status, status_col, spectra, nullptr, nullptr, nmodels, use_tma, s); break;
+    case 2: launch_transit_t<NMOL, 2, false>(c, tabs, wts, status, status_col, spectra, nullptr, nullptr, nmodels, use_tma, s); break;
+    default: launch_transit_t<0, -1, false>(c, tabs, wts, status, status_col, spectra, nullptr, nullptr, nmodels, use_tma, s);
+  }
+}
+
+void launch_transit_weights(const DevConfig &c, const double *tabs, double *wts, int nmodels,
+                            cudaStream_t s) {
+  transit_weights_kernel<<<nmodels, 128, 0, s>>>(c, tabs, wts, nmodels);
+}
+
+void launch_transit(const DevConfig &c, const double *tabs, const double *wts, const int *status,
+                    int *status_col, double *spectra, double *tau_keep, int *last_keep,
+                    int nmodels, bool keep, int use_tma, cudaStream_t s) {
+  if (keep) {   // introspection path: run-time counts, stores tau[] and last[]
+    launch_transit_t<0, -1, true>(c, tabs, wts, status, status_col, spectra, tau_keep, last_keep, nmodels, use_tma, s);
+    return;
+  }
+  switch (c.ngmol) {
+    case 1: launch_transit_ncia<1>(c, tabs, wts, status, status_col, spectra, nmodels, use_tma, s); break;
+    case 2: launch_transit_ncia<2>(c, tabs, wts, status, status_col, spectra, nmodels, use_tma, s); break;
+    case 3: launch_transit_ncia<3>(c, tabs, wts, status, status_col, spectra, nmodels, use_tma, s); break;
+    case 4: launch_transit_ncia<4>(c, tabs, wts, status, status_col, spectra, nmodels, use_tma, s); break;
+    default: launch_transit_t<0, -1, false>(c, tabs, wts, status, status_col, spectra, nullptr, nullptr, nmodels, use_tma, s);
+  }
 }
 
 void launch_extinction(const DevConfig &c, const double *tabs, double *ext, int nmodels,

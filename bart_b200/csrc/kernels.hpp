@@ -9,14 +9,17 @@ namespace bart {
 constexpr int kColThreads = 128;      // wavenumbers per CTA, lookup kernel
 constexpr int kEclThreads = 64;       // eclipse kernel: 64 threads x kEclCols columns = 128 wavenumbers per CTA
 constexpr int kEclCols = 2;
-constexpr int kTransitThreads = 64;   // wavenumbers per CTA, transit kernel (smem: nlayer x 64 x 8 B)
 
 void launch_atm_prep(const DevConfig &c, const Knobs &k, const double *profiles, int n_in,
                      double *tabs, int *status, int nmodels, cudaStream_t s);
 void launch_eclipse(const DevConfig &c, const double *tabs, const int *status, double *spectra,
                     double *tau_keep, int *last_keep, int nmodels, bool keep, int use_tma,
                     cudaStream_t s);
-void launch_transit(const DevConfig &c, const double *tabs, double *wts, const int *status,
+// chord weights of one model in the tiled layout (doubles per model), K2t, and the tile kernel
+size_t transit_weights_stride(int nlayer);
+void launch_transit_weights(const DevConfig &c, const double *tabs, double *wts, int nmodels,
+                            cudaStream_t s);
+void launch_transit(const DevConfig &c, const double *tabs, const double *wts, const int *status,
                     int *status_col, double *spectra, double *tau_keep, int *last_keep,
                     int nmodels, bool keep, int use_tma, cudaStream_t s);
 void launch_merge_status(int *status, const int *status_col, int nmodels, cudaStream_t s);

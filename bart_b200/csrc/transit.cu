@@ -501,7 +501,7 @@ static void prepare_batch(int total, int n_in) {
     G.d_last.ensure((size_t)total * c.nwave);
     CUDA_OK(cudaMemsetAsync(G.d_tau.p, 0, (size_t)total * c.nwave * c.nlayer * sizeof(double), G.stream));
   }
-  if (!c.eclipse) G.d_wts.ensure((size_t)total * c.nlayer * (c.nlayer + 1) / 2);
+  if (!c.eclipse) G.d_wts.ensure((size_t)total * transit_weights_stride(c.nlayer));
 }
 
 static void launch_models(const double *d_prof, int off, int count, int total, int n_in, double *d_spec) {
@@ -528,14 +528,19 @@ static void launch_models(const double *d_prof, int off, int count, int total, i
   } else {
     int *scol = G.d_status_col.p + off;
     CUDA_OK(cudaMemsetAsync(scol, 0, count * sizeof(int), G.stream));
+    double *wts = G.d_wts.p + (size_t)off * transit_weights_stride(c.nlayer);
+    {
+      KernelScope ks("transit_weights");
+      launch_transit_weights(c, tabs, wts, count, G.stream);
+      check_launch("transit_weights");
+    }
     {
       KernelScope ks("transit_column");
-      launch_transit(c, tabs, G.d_wts.p + (size_t)off * c.nlayer * (c.nlayer + 1) / 2, status, scol,
-                     d_spec, tau, last, count, G.keep, G.use_tma, G.stream);
+      launch_transit(c, tabs, wts, status, scol, d_spec, tau, last, count, G.keep, G.use_tma, G.stream);
       check_launch("transit_column");
     }
     launch_merge_status(status, scol, count, G.stream);
-    G.launches += 2;                 // transit_weights + merge_status
+    G.launches += 1;                 // merge_status
   }
 }
 
@@ -1099,6 +1104,8 @@ int bart_build_opacity_slice(int t_begin, int t_end, double *host_out) {
   return 0;
   API_END_INT
 }
+
+double bart_builder_phase_ms(const char *name) { return builder_phase_ms(G.builder, name); }
 
 long long bart_builder_stats(long long *nlines, long long *ngroups, long long *neval) {
   if (!G.builder) return -1;

@@ -160,6 +160,9 @@ int  bart_comm_finalize(void);
  * the pieces: t_begin/t_end select a slice of the temperature axis (T-sharded multi-GPU build). */
 int  bart_build_opacity_slice(int t_begin, int t_end, double *host_out /*[layer][t][mol][wn]*/);
 long long bart_builder_stats(long long *nlines, long long *ngroups, long long *neval);
+/* milliseconds spent so far in a build phase: "read_tli_host", "grouping_host", "voigt_table",
+ * "kmax", "strength", "widths", "accumulate", "d2h" (CUDA events on the build stream).      */
+double bart_builder_phase_ms(const char *name);
 long long bart_line_bins(long long *iown_out, long long capacity);  /* bit-exact bin trace   */
 int  bart_voigt_profile(int idop, int ilor, float *out, long long capacity, long long *halfsize);
 
