@@ -216,6 +216,7 @@ transit_tile_kernel(DevConfig c, const double *__restrict__ tabs, const double *
   double *s_wt = s_tab + nd;                                   // [<= nl][kTrRow]
   double *s_er = s_wt + (size_t)nl * kTrRow;                   // [nl][kTrW]
   double *s_tau = s_er + (size_t)nl * kTrW;                    // [kTrChunk][kTrW]
+  double *s_fd = s_tau + (size_t)kTrChunk * kTrW;              // [kTrChunk][kTrW] exp(-tau) b
   const int m = blockIdx.x % nmodels;
   const int tile = blockIdx.x / nmodels;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -293,28 +294,46 @@ transit_tile_kernel(DevConfig c, const double *__restrict__ tabs, const double *
           a0[3] = fma(w23.y, e.x, a0[3]); a1[3] = fma(w23.y, e.y, a1[3]);
           a0[4] = fma(w4, e.x, a0[4]);    a1[4] = fma(w4, e.y, a1[4]);
         }
+        // epilogue: the transmission integrand exp(-tau) b of every (depth, column) of the tile, all
+        // threads, independent exponentials (phase C only scans)
 #pragma unroll
         for (int j = 0; j < kTrTD; j++)
           if (dg + j < nl) {
+            const double bd = s_tab[(size_t)(dg + j) * nf + L::RAD] * c.rfct;
             D2 v; v.x = a0[j]; v.y = a1[j];
+            D2 f;
+            f.x = fast_exp_neg(-v.x, s_etab) * bd;
+            f.y = fast_exp_neg(-v.y, s_etab) * bd;
             *reinterpret_cast<D2 *>(s_tau + (size_t)(kTrTD * warp + j) * kTrW + 2 * lane) = v;
+            *reinterpret_cast<D2 *>(s_fd + (size_t)(kTrTD * warp + j) * kTrW + 2 * lane) = f;
           }
       }
     }
     __syncthreads();
-    // ---- phase C: one thread per column
+    // ---- phase C: one thread per column; branch-free so the loads and the panel products of the
+    // chunk overlap (only the running sum S is a dependent chain, in the reference's order)
     if (t < kTrW && !done) {
-      for (int j = 0; j < dn; j++) {
-        const int d = d0 + j;
-        const double *row = s_tab + (size_t)d * nf;
-        tau = s_tau[(size_t)j * kTrW + t];
-        if (KEEP && valid) tk[d] = tau;
-        const double bd = row[L::RAD] * c.rfct;
-        const double fd = fast_exp_neg(-tau, s_etab) * bd;
-        if (d >= 2 && !(d & 1)) S += row[L::SA] * fd + row[L::SB] * f1 + row[L::SC] * f2;
-        f2 = f1; f1 = fd;
-        if (tau > c.toomuch) { last = d; done = true; break; }
+      const double *tc = s_tau + t, *fc = s_fd + t;
+      int jstop = kTrChunk;                                      // first depth of the chunk beyond toomuch
+#pragma unroll
+      for (int j = kTrChunk - 1; j >= 0; j--)
+        if (j < dn && tc[(size_t)j * kTrW] > c.toomuch) jstop = j;
+      const int jl = jstop < dn ? jstop : dn - 1;                // last depth processed in this chunk
+      if (KEEP && valid)
+        for (int j = 0; j <= jl; j++) tk[d0 + j] = tc[(size_t)j * kTrW];
+#pragma unroll
+      for (int j = 0; j < kTrChunk; j++) {
+        const double fd = fc[(size_t)j * kTrW];
+        if (j <= jl) {
+          if (!(j & 1) && d0 + j >= 2) {                         // d0 is even: parity of d = parity of j
+            const double *row = s_tab + (size_t)(d0 + j) * nf;
+            S += row[L::SA] * fd + row[L::SB] * f1 + row[L::SC] * f2;
+          }
+          f2 = f1; f1 = fd;
+        }
       }
+      tau = tc[(size_t)jl * kTrW];
+      if (jstop < dn) { last = d0 + jstop; done = true; }
     }
     if (__syncthreads_and(t >= kTrW || done)) break;
   }
@@ -537,7 +556,7 @@ template <int NMOL, int NCIA, bool KEEP>
 static void launch_transit_t(const DevConfig &c, const double *tabs, const double *wts,
                              const int *status, int *status_col, double *spectra, double *tau_keep,
                              int *last_keep, int nmodels, int use_tma, cudaStream_t s) {
-  const size_t smem = table_smem(c) + ((size_t)c.nlayer * (kTrRow + kTrW) + (size_t)kTrChunk * kTrW) * sizeof(double);
+  const size_t smem = table_smem(c) + ((size_t)c.nlayer * (kTrRow + kTrW) + (size_t)2 * kTrChunk * kTrW) * sizeof(double);
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
     cudaFuncSetAttribute(transit_tile_kernel<NMOL, NCIA, KEEP>,
