@@ -1,0 +1,345 @@
+"""TEST INFRASTRUCTURE -- CPU restatement of the retrieval loop AROUND the forward model
+(SURVEY.md section 8f rows 1 and 2).  Only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline leg may import this; the product (bart_b200/) never does.
+
+What is restated, in numpy, the literal way:
+
+* input converter  code/BARTfunc.py:309-360  (PT profile, abundance scaling, H2/He
+  renormalisation, the temperature-bounds and sum-of-metals rejections, the per-model knobs)
+* PT models        code/PT.py:589-739 PT_line + xi (Line et al. 2013 eq. 13-14), PT.py:700-716
+  PT_iso, PT.py:741-750 PT_adiabatic
+* E_2(x)           third-party: scipy.special.expn (scipy 1.18.1 here; cephes `expn.c`, Moshier):
+  power series for x <= 1, continued fraction for x > 1, restated from the published algorithm
+* chi-squared      modules/MCcubed/src_c/chisq.c:111-142 + include/stats.h:72-103 (priors)
+* DE-MC loop       modules/MCcubed/MCcubed/mc/mcmc.py:296-345 (initial state), 484-507 (random
+  streams, drawn in MC3's order so a seeded run reproduces MC3's chains), 518-660 (proposal,
+  boundary clamp, shared parameters, Metropolis rule, best fit, trace), MPI-mode semantics (every
+  chain is evaluated each generation, as BART runs it)
+
+Pinned against the reference itself: tests/golden/retrieval_*.npz are produced by
+tests/golden/make_golden_retrieval.py, which imports the reference's code/PT.py and runs the
+reference's MCcubed.mc.mcmc (C extensions compiled from a /tmp copy) with fixed seeds.
+"""
+import numpy as np
+
+EUL = 0.57721566490153286060
+MACHEP = 1.11022302462515654042e-16
+BIG = 1.44115188075855872e17
+MAXLOG = 7.09782712893383996843e2
+STEFAN_BOLTZMANN = 5.6703744191844314e-08     # scipy.constants.Stefan_Boltzmann (scipy 1.18)
+
+
+def expn_scalar(n, x):
+    """E_n(x), cephes expn.c algorithm (n small)."""
+    if x > MAXLOG:
+        return 0.0
+    if x == 0.0:
+        return np.inf if n < 2 else 1.0 / (n - 1.0)
+    if n == 0:
+        return np.exp(-x) / x
+    if x > 1.0:
+        k = 1
+        pkm2, qkm2, pkm1, qkm1 = 1.0, x, 1.0, x + n
+        ans = pkm1 / qkm1
+        while True:
+            k += 1
+            if k & 1:
+                yk, xk = 1.0, n + (k - 1) // 2
+            else:
+                yk, xk = x, k // 2
+            pk = pkm1 * yk + pkm2 * xk
+            qk = qkm1 * yk + qkm2 * xk
+            if qk != 0:
+                r = pk / qk
+                t = abs((ans - r) / r)
+                ans = r
+            else:
+                t = 1.0
+            pkm2, pkm1, qkm2, qkm1 = pkm1, pk, qkm1, qk
+            if abs(pk) > BIG:
+                pkm2 /= BIG; pkm1 /= BIG; qkm2 /= BIG; qkm1 /= BIG
+            if t <= MACHEP:
+                break
+        return ans * np.exp(-x)
+    psi = -EUL - np.log(x)
+    for i in range(1, n):
+        psi += 1.0 / i
+    z = -x
+    xk, yk, pk = 0.0, 1.0, 1.0 - n
+    ans = 0.0 if n == 1 else 1.0 / pk
+    while True:
+        xk += 1.0
+        yk *= z / xk
+        pk += 1.0
+        if pk != 0.0:
+            ans += yk / pk
+        t = abs(yk / ans) if ans != 0.0 else 1.0
+        if t <= MACHEP:
+            break
+    fact = 1.0
+    for i in range(2, n):
+        fact *= i
+    return z ** (n - 1) * psi / fact - ans
+
+
+def expn(n, x):
+    x = np.asarray(x, dtype=float)
+    return np.array([expn_scalar(n, float(v)) for v in x.ravel()]).reshape(x.shape)
+
+
+def xi(gamma, tau):
+    """PT.py:719-737 (eq. 14 of Line et al. 2013)."""
+    return (2.0 / 3) * (1 + (1. / gamma) * (1 + (0.5 * gamma * tau - 1) * np.exp(-gamma * tau)) +
+                        gamma * (1 - 0.5 * tau ** 2) * expn(2, gamma * tau))
+
+
+def thorngren_tint(R_star, T_star, sma):
+    """PT.py:671-676."""
+    T_eq = (R_star / (2.0 * sma)) ** 0.5 * T_star
+    F = 4.0 * STEFAN_BOLTZMANN * T_eq ** 4
+    return 1.24 * T_eq * np.exp(-(np.log(F) - 0.14) ** 2 / 2.96)
+
+
+def PT_line(pressure, kappa, gamma1, gamma2, alpha, beta, R_star, T_star, T_int, sma, grav,
+            T_int_type="const"):
+    """PT.py:589-697."""
+    kappa, gamma1, gamma2 = 10 ** kappa, 10 ** gamma1, 10 ** gamma2
+    if T_int_type == "thorngren":
+        T_int = thorngren_tint(R_star, T_star, sma)
+    T_irr = beta * (R_star / (2.0 * sma)) ** 0.5 * T_star
+    tau = kappa * (pressure * 1e6) / grav
+    xi1, xi2 = xi(gamma1, tau), xi(gamma2, tau)
+    return (0.75 * (T_int ** 4 * (2.0 / 3.0 + tau) + T_irr ** 4 * (1 - alpha) * xi1 +
+                    T_irr ** 4 * alpha * xi2)) ** 0.25
+
+
+def PT_iso(p, T):
+    return np.ones(len(p)) * T
+
+
+def PT_adiabatic(p, T0, gamma, logp0):
+    p0 = 10 ** logp0
+    return T0 / (1 + (gamma - 1) / gamma * np.log(p0 / p))
+
+
+PT_TYPES = {"iso": 0, "line": 1, "adiabatic": 2}
+
+
+class Converter:
+    """Input converter of BARTfunc.py:139-222 (set-up) and 320-360 (per proposal)."""
+
+    def __init__(self, pressure_bar, species, abundances, molfit, pt_type, pt_args=None,
+                 tint_type="const", tmin=400.0, tmax=3000.0, nrad=0, ncloud=0, nray=0):
+        self.press = np.asarray(pressure_bar, dtype=float)          # atmosphere-file order
+        self.species = list(species)
+        self.base = np.asarray(abundances, dtype=float)             # [layer][species]
+        self.nlayer, self.nspec = self.base.shape
+        self.imol = [self.species.index(m) for m in molfit]
+        self.iH2, self.iHe = self.species.index("H2"), self.species.index("He")
+        self.imetals = [i for i, s in enumerate(self.species) if s not in ("H2", "He", "H-", "e-")]
+        self.ratio = self.base[:, self.iH2] / self.base[:, self.iHe]
+        self.pt_type, self.pt_args, self.tint_type = pt_type, pt_args, tint_type
+        self.tmin, self.tmax = tmin, tmax
+        self.nrad, self.ncloud, self.nray = nrad, ncloud, nray
+        self.npt = {"iso": 1, "line": 5, "adiabatic": 3}[pt_type]
+        self.npars = self.npt + nrad + ncloud + nray + len(self.imol)
+
+    def temperature(self, ptpars):
+        p = self.press[::-1]                                          # BARTfunc.py:176
+        if self.pt_type == "line":
+            rstar, tstar, tint, sma, grav = self.pt_args
+            T = PT_line(p, *ptpars, rstar, tstar, tint, sma, grav, self.tint_type)
+        elif self.pt_type == "iso":
+            T = PT_iso(p, *ptpars)
+        else:
+            T = PT_adiabatic(p, *ptpars)
+        return T[::-1]
+
+    def profiles(self, params):
+        """params[M][npars] -> profiles[M][(1+nspec) nlayer], status[M] (0 ok, 16 temperature
+        bounds, 32 sum of metals > 1), knobs dict."""
+        params = np.atleast_2d(np.asarray(params, dtype=float))
+        M = params.shape[0]
+        nl, ns = self.nlayer, self.nspec
+        prof = np.zeros((M, (ns + 1) * nl))
+        status = np.zeros(M, dtype=np.int32)
+        off = self.npt + self.nrad + self.ncloud + self.nray
+        for m in range(M):
+            T = self.temperature(params[m, :self.npt])
+            if np.any(T < self.tmin) or np.any(T > self.tmax) or not np.all(np.isfinite(T)):
+                status[m] = 16
+                continue
+            a = self.base.T.copy()                                    # aprofiles[species][layer]
+            for k, i in enumerate(self.imol):
+                a[i] = self.base[:, i] * 10.0 ** params[m, off + k]
+            q = 1.0 - np.sum(a[self.imetals], axis=0)
+            if np.any(q < 0.0):
+                status[m] = 32
+                continue
+            a[self.iH2] = self.ratio * q / (1.0 + self.ratio)
+            a[self.iHe] = q / (1.0 + self.ratio)
+            prof[m, :nl] = T
+            prof[m, nl:] = a.ravel()
+        knobs = {}
+        c = self.npt
+        if self.nrad:
+            knobs["refradius"] = params[:, c].copy(); c += 1
+        if self.ncloud:
+            knobs["cloudtop"] = params[:, c].copy(); c += 1
+        if self.nray == 1:
+            knobs["scat_flag"] = np.ones(M, dtype=np.int32)
+            knobs["scat_logext"] = params[:, c].copy()
+        elif self.nray == 2:
+            knobs["scat_flag"] = 2 * np.ones(M, dtype=np.int32)
+            knobs["scat_logext"] = np.zeros(M)
+        return prof, status, knobs
+
+
+def chisq(model, data, uncert, prioroff=None, priorlow=None, priorup=None):
+    """chisq.c:111-142 + stats.h:72-103: sequential sums, pow(.,2)."""
+    c = 0.0
+    for i in range(len(model)):
+        c += ((model[i] - data[i]) / uncert[i]) ** 2
+    jc = 0.0
+    if prioroff is not None:
+        for i in range(len(prioroff)):
+            if priorlow[i] == -1:
+                c += 2.0 * np.log(prioroff[i]); jc += 2.0 * np.log(prioroff[i])
+            elif prioroff[i] > 0:
+                c += (prioroff[i] / priorup[i]) ** 2
+            else:
+                c += (prioroff[i] / priorlow[i]) ** 2
+    return c, c - jc
+
+
+def demc(func, data, uncert, params, pmin, pmax, stepsize, numit, nchains, prior=None,
+         priorlow=None, priorup=None, burnin=0, fgamma=1.0, fepsilon=0.0, rng=np.random,
+         draws=None):
+    """walk='demc' of mcmc.py, MPI-mode semantics.  `func(params[nchains][npars]) ->
+    models[nchains][ndata]`.  Random numbers are drawn from `rng` in MC3's order (mcmc.py:300,
+    484-507) unless `draws` supplies them.  Returns a dict with MC3's arrays."""
+    data, uncert = np.asarray(data, float), np.asarray(uncert, float)
+    params = np.atleast_2d(np.array(params, dtype=float))
+    nparams, ndata = params.shape[1], len(data)
+    pmin, pmax, stepsize = (np.asarray(a, float) for a in (pmin, pmax, stepsize))
+    if prior is None or priorlow is None or priorup is None:
+        prior = priorup = priorlow = np.zeros(nparams)
+    prior, priorlow, priorup = (np.asarray(a, float) for a in (prior, priorlow, priorup))
+    iprior = np.where(priorlow != 0)[0]
+    nfree = int(np.sum(stepsize > 0))
+    chainsize = int(np.ceil(numit / nchains))
+    ifree = np.where(stepsize > 0)[0]
+    ishare = np.where(stepsize < 0)[0]
+    gamma = fgamma * 2.4 / np.sqrt(2 * nfree)
+    if params.shape[0] != nchains:                                   # mcmc.py:296-306
+        params = np.repeat(params, nchains, 0)
+        for p in ifree:
+            params[1:, p] = (draws["init"][p] if draws else
+                             rng.normal(params[0, p], stepsize[p], nchains - 1))
+            params[np.where(params[:, p] < pmin[p]), p] = pmin[p]
+            params[np.where(params[:, p] > pmax[p]), p] = pmax[p]
+    for s in ishare:
+        params[:, s] = params[:, -int(stepsize[s]) - 1]
+    params0 = params.copy()
+    models = np.array(func(params), dtype=float).reshape(nchains, ndata)
+    currchisq, c2 = np.zeros(nchains), np.zeros(nchains)
+    for c in range(nchains):
+        currchisq[c], c2[c] = chisq(models[c], data, uncert, (params[c] - prior)[iprior],
+                                    priorlow[iprior], priorlow[iprior])
+    bestchisq = np.amin(c2)
+    bestp = params[np.argmin(c2)].copy()
+    bestmodel = models[np.argmin(c2)].copy()
+    if draws:
+        support, r1, r2, unif, ugamma = (draws[k] for k in ("support", "r1", "r2", "unif", "ugamma"))
+    else:                                                            # mcmc.py:484-507
+        support = rng.normal(0, stepsize[ifree], (chainsize, nchains, nfree))
+        r1 = rng.randint(0, nchains - 1, (nchains, chainsize))
+        for c in range(nchains):
+            r1[c][np.where(r1[c] == c)] = nchains - 1
+        r2 = np.zeros((nchains, chainsize), int)
+        for c in range(nchains):
+            r2[c] = (c + rng.randint(1, nchains - 1, chainsize)) % nchains
+            r2[c][np.where(r2[c] == r1[c])] = (c - 1) % nchains
+        unif = rng.uniform(0, 1, (chainsize, nchains))
+        ugamma = rng.uniform(0, 1, (chainsize, nchains))
+    gamma1 = np.tile(gamma, (nchains, 1))
+    nextp = params.copy()
+    nextchisq = np.zeros(nchains)
+    numaccept = np.zeros(nchains)
+    outbounds = np.zeros((nchains, nfree), int)
+    allparams = np.zeros((nchains, nfree, chainsize))
+    allmodels = np.zeros((chainsize, nchains, ndata))
+    for i in range(chainsize):
+        gamma1[ugamma[i] >= 0.1] = gamma
+        gamma1[ugamma[i] < 0.1] = 0.98
+        jump = gamma1 * (params[r1[:, i]] - params[r2[:, i]])[:, ifree] + fepsilon * support[i]
+        nextp[:, ifree] = params[:, ifree] + jump
+        outpars = np.asarray(((nextp < pmin) | (nextp > pmax))[:, ifree])
+        outflag = np.any(outpars, axis=1)
+        outbounds += outpars
+        for p in ifree:
+            nextp[np.where(nextp[:, p] < pmin[p]), p] = pmin[p]
+            nextp[np.where(nextp[:, p] > pmax[p]), p] = pmax[p]
+        for s in ishare:
+            nextp[:, s] = nextp[:, -int(stepsize[s]) - 1]
+        models = np.array(func(nextp), dtype=float).reshape(nchains, ndata)
+        allmodels[i] = models
+        for c in np.where(~outflag)[0]:
+            nextchisq[c], c2[c] = chisq(models[c], data, uncert, (nextp[c] - prior)[iprior],
+                                        priorlow[iprior], priorlow[iprior])
+        nextchisq[outflag] = np.inf
+        with np.errstate(over="ignore", invalid="ignore"):
+            accept = np.exp(0.5 * (currchisq - nextchisq))
+        accepted = accept >= unif[i]
+        if i >= burnin:
+            numaccept += accepted
+        params[accepted] = nextp[accepted]
+        currchisq[accepted] = nextchisq[accepted]
+        if np.amin(c2) < bestchisq:
+            bestp = params[np.argmin(c2)].copy()
+            bestmodel = models[np.argmin(c2)].copy()
+            bestchisq = np.amin(c2)
+        allparams[:, :, i] = params[:, ifree]
+    return dict(allparams=allparams, params=params, currchisq=currchisq, numaccept=numaccept,
+                outbounds=outbounds, bestp=bestp, bestchisq=bestchisq, bestmodel=bestmodel,
+                params0=params0, allmodels=allmodels,
+                draws=dict(support=support, r1=r1, r2=r2, unif=unif, ugamma=ugamma))
+
+
+class BandOracle:
+    """params[M][npars] -> band fluxes[M][nfilters]: Converter + forward-model oracle
+    (oracle.Oracle, transit_oracle.c) + band integration (oracle.bandflux), i.e. what one
+    BARTfunc.py worker returns to MC3 per proposal (BARTfunc.py:309-399), rejected proposals -1."""
+
+    def __init__(self, cfg, converter, filter_files, starwn=None, starfl=None, rprs=1.0):
+        from oracle import oracle as orc
+        self.orc = orc
+        self.O = orc.Oracle(cfg)
+        self.conv = converter
+        self.wn = self.O.wn
+        self.star = starwn is not None
+        swn = starwn if self.star else self.wn
+        sfl = starfl if self.star else np.ones_like(self.wn)
+        self.filters = []
+        for f in filter_files:
+            fwn, ftr = orc.readfilter(f)
+            self.filters.append(orc.resample(self.wn, fwn, ftr, swn, sfl))
+        self.rprs = rprs
+        self.nfilters = len(self.filters)
+
+    def __call__(self, params):
+        params = np.atleast_2d(params)
+        prof, status, knobs = self.conv.profiles(params)
+        out = -np.ones((params.shape[0], self.nfilters))
+        for m in range(params.shape[0]):
+            if status[m]:
+                continue
+            if "refradius" in knobs:
+                self.O.set_radius(knobs["refradius"][m])
+            if "cloudtop" in knobs:
+                self.O.set_cloudtop(knobs["cloudtop"][m])
+            if "scat_flag" in knobs:
+                self.O.set_scattering(int(knobs["scat_flag"][m]), knobs["scat_logext"][m])
+            spec = self.O.run(prof[m])
+            out[m] = self.orc.bandflux(spec, self.wn, self.filters, star=self.star, rprs=self.rprs)
+        return out

@@ -68,3 +68,43 @@ def build_case(name, workdir):
 
 def golden_path(name):
     return os.path.join(GOLDEN_DIR, name + ".npz")
+
+
+# Retrieval-loop cases: input converter + DE-MC around the forward model.
+# WASP-12b system constants (examples/WASP-12b/WASP-12b.tep; code/constants.py; BARTfunc.py:159-211)
+RSUN, RJUP, MJUP, AU, GNEWT = 6.96e8, 7.1492e7, 1.8983e27, 149597870700.0, 6.6743e-11
+W12_PTARGS = (1.57 * RSUN, 6300.0, 100.0, 0.0229 * AU,
+              100.0 * GNEWT * 1.41 * MJUP / (1.79 * RJUP) ** 2)    # rstar, tstar, tint, sma, gplanet
+RETRIEVAL = {
+    # name -> forward-model case, PT model, knob parameters, MC3 set-up
+    "retr_tiny_eclipse": dict(
+        case=dict(shape="tiny", solution="eclipse", seed=2031), molfit=("CH4",), pt="line",
+        nrad=0, ncloud=0, nray=0,
+        params=[-0.5, -0.2, 1.0, 0.0, 1.1, 0.5],
+        pmin=[-5.0, -3.0, -2.0, 0.0, 0.55, -9.0], pmax=[2.0, 2.0, 3.0, 1.0, 1.4, 3.0],
+        stepsize=[0.05, 0.05, 0.0, 0.0, 0.01, 0.3], truth=[-0.7, -0.1, 1.0, 0.0, 1.05, 1.0],
+        nchains=6, numit=180, burnin=5, seed=314),
+    "retr_small4_transit": dict(
+        case=dict(shape="small4", solution="transit", seed=2032, refradius_km=95000.0),
+        molfit=("H2O", "CO2", "CO", "CH4"), pt="line", nrad=1, ncloud=1, nray=1,
+        params=[-0.5, -0.2, 1.0, 0.0, 1.1, 94000.0, -1.0, 0.5, 0.0, 0.5, -0.5, 0.2],
+        pmin=[-5.0, -3.0, -2.0, 0.0, 0.55, 90000.0, -4.0, -3.0, -9.0, -9.0, -9.0, -9.0],
+        pmax=[2.0, 2.0, 3.0, 1.0, 1.4, 99000.0, 1.5, 3.0, 3.0, 3.0, 3.0, 3.0],
+        stepsize=[0.05, 0.05, 0.0, 0.0, 0.01, 100.0, 0.2, 0.2, 0.3, 0.3, -9, 0.3],
+        truth=[-0.6, -0.15, 1.0, 0.0, 1.08, 94300.0, -0.8, 0.8, 0.3, 0.2, 0.3, 0.0],
+        nchains=5, numit=100, burnin=0, seed=2718),
+}
+
+
+def build_retrieval(name, workdir):
+    """-> (case, spec, dict(pt_args, star, rprs)) for a RETRIEVAL entry."""
+    spec = RETRIEVAL[name]
+    case = synth.make_case(os.path.join(workdir, name), **spec["case"])
+    wn = case["wn"]
+    starwn = np.linspace(wn[0] - 10, wn[-1] + 10, 3000)
+    hc_k = 6.6260755e-27 * 2.99792458e10 / 1.380658e-16
+    starfl = 2 * 6.6260755e-27 * 2.99792458e10 ** 2 * starwn ** 3 / np.expm1(hc_k * starwn / 6300.0) * np.pi
+    eclipse = spec["case"]["solution"] == "eclipse"
+    extra = dict(pt_args=W12_PTARGS, starwn=starwn if eclipse else None,
+                 starfl=starfl if eclipse else None, rprs=0.117 if eclipse else 1.0)
+    return case, spec, extra

@@ -1,0 +1,191 @@
+#!/usr/bin/env python
+"""Generate tests/golden/retrieval_*.npz from the REFERENCE's own Python code, in the build
+container (neither /root/reference nor the /tmp build exist on the GPU box):
+
+  * retrieval_pt.npz      code/PT.py PT_line / PT_iso / PT_adiabatic (imported from
+                          /root/reference/code) on seeded parameter draws, incl. scipy's expn(2, x)
+  * retrieval_conv_*.npz  the per-proposal input converter: the statements of
+                          code/BARTfunc.py:320-347 executed verbatim in numpy around the
+                          reference's PT_generator
+  * retrieval_mc3_*.npz   a seeded run of the reference's MCcubed.mc.mcmc (walk='demc'; C
+                          extensions compiled from a copy under /tmp/bart_mc3_ref with the
+                          reference's own setup.py) whose model function is the forward-model
+                          oracle: the chain trace, best fit, acceptance counts
+
+Shims applied from the outside, none to the reference sources: `numpy.int/float` aliases (removed
+from numpy 2), stub `matplotlib` and `dwt` modules (absent / built on a removed numpy C API; neither
+is used on this path).
+
+    python tests/golden/make_golden_retrieval.py
+"""
+import glob
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import types
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference"
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import cases  # noqa: E402
+from oracle import retrieval_oracle as ro  # noqa: E402
+
+
+def shim():
+    np.int = int
+    np.float = float
+    for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.patches", "dwt"):
+        sys.modules[name] = types.ModuleType(name)
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    sys.modules["matplotlib"].patches = sys.modules["matplotlib.patches"]
+    sys.modules["matplotlib"].use = lambda *a, **k: None
+
+
+def build_mc3():
+    dst = "/tmp/bart_mc3_ref"
+    if not glob.glob(os.path.join(dst, "MCcubed", "lib", "chisq*.so")):
+        shutil.rmtree(dst, ignore_errors=True)
+        shutil.copytree(os.path.join(REF, "modules", "MCcubed"), dst)
+        subprocess.check_call([sys.executable, "setup.py", "build"], cwd=dst,
+                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        for so in glob.glob(os.path.join(dst, "build", "lib.*", "*.so")):
+            if "dwt" not in so:
+                shutil.copy(so, os.path.join(dst, "MCcubed", "lib"))
+    sys.path.insert(0, dst)
+    import MCcubed
+    return MCcubed
+
+
+def golden_pt(pt):
+    rng = np.random.default_rng(12345)
+    p = np.logspace(2, -5, 100)
+    rstar, tstar, tint, sma, grav = cases.W12_PTARGS
+    lo = np.array([-5.0, -3.0, -2.0, 0.0, 0.55])
+    hi = np.array([2.0, 2.0, 3.0, 1.0, 1.4])
+    pars = rng.uniform(lo, hi, (64, 5))
+    pars[0] = [-0.5, -0.2, 1.0, 0.0, 1.1]                    # examples/WASP-12b/BART.cfg:104
+    T_const = np.array([pt.PT_line(p, *q, rstar, tstar, tint, sma, grav, "const") for q in pars])
+    T_thorn = np.array([pt.PT_line(p, *q, rstar, tstar, tint, sma, grav, "thorngren") for q in pars])
+    apars = np.column_stack([rng.uniform(800, 2500, 16), rng.uniform(1.1, 1.67, 16),
+                             rng.uniform(-1, 2, 16)])
+    T_adia = np.array([pt.PT_adiabatic(p, *q) for q in apars])
+    import scipy.special as sp
+    x = np.concatenate([10 ** rng.uniform(-10, 2.85, 400), [1.0, 0.999999, 1.000001, 709.0, 720.0]])
+    np.savez_compressed(os.path.join(HERE, "retrieval_pt.npz"), pressure=p, ptargs=cases.W12_PTARGS,
+                        pars=pars, T_const=T_const, T_thorngren=T_thorn, apars=apars, T_adiabatic=T_adia,
+                        x=x, expn2=sp.expn(2, x))
+    print("retrieval_pt.npz: T range %.0f..%.0f K" % (T_const.min(), T_const.max()))
+
+
+def golden_converter(pt, name, tmp):
+    case, spec, extra = cases.build_retrieval(name, tmp)
+    rng = np.random.default_rng(777)
+    lo, hi = np.array(spec["pmin"]), np.array(spec["pmax"])
+    M = 48
+    params = rng.uniform(lo, hi, (M, len(lo)))
+    params[0] = spec["params"]
+    params[1] = spec["truth"]
+    params[2:12, :5] = np.array(spec["params"][:5]) + rng.normal(0, 0.05, (10, 5))
+    params[8:12, -1] = 4.2                                   # sum of metals > 1 (BARTfunc.py:339-344)
+    # --- BARTfunc.py:139-222 set-up, verbatim
+    species = np.asarray(case["species"])
+    pressure = case["press_bar"][::-1]
+    abundances = case["abund"]
+    nlayers, nspecies = len(pressure), len(species)
+    iH2 = np.where(species == "H2")[0]
+    iHe = np.where(species == "He")[0]
+    ratio = (abundances[:, iH2] / abundances[:, iHe]).squeeze()
+    imetals = np.where((species != "He") & (species != "H2") & (species != "H-") & (species != "e-"))[0]
+    molfit = spec["molfit"]
+    nmolfit = len(molfit)
+    imol = np.zeros(nmolfit, dtype="i")
+    for i in np.arange(nmolfit):
+        imol[i] = np.where(np.asarray(species) == molfit[i])[0][0]
+    nradfit, ncloud, nray = spec["nrad"], spec["ncloud"], spec["nray"]
+    nPT = len(lo) - nmolfit - ncloud - nray - nradfit
+    PTargs = list(extra["pt_args"]) + ["const"]
+    profiles = np.zeros((nspecies + 1, nlayers), dtype="d")
+    tprofile, aprofiles = profiles[0, :], profiles[1:, :]
+    for i in np.arange(nspecies):
+        aprofiles[i] = abundances[:, i]
+    Tmin, Tmax = 400.0, 3000.0
+    out = np.zeros((M, (nspecies + 1) * nlayers))
+    status = np.zeros(M, dtype=np.int32)
+    for m in range(M):
+        par = params[m]
+        # --- BARTfunc.py:320-347, verbatim
+        tprofile[:] = pt.PT_generator(pressure, par[0:nPT], pt.PT_line, PTargs)[::-1]
+        if np.any(tprofile < Tmin) or np.any(tprofile > Tmax):
+            status[m] = 16
+            continue
+        for i in np.arange(nmolfit):
+            mm = imol[i]
+            aprofiles[mm] = abundances[:, mm] * 10.0 ** par[nPT + nradfit + ncloud + nray + i]
+        q = 1.0 - np.sum(aprofiles[imetals], axis=0)
+        if np.any(q < 0.0):
+            status[m] = 32
+            continue
+        aprofiles[iH2] = ratio * q / (1.0 + ratio)
+        aprofiles[iHe] = q / (1.0 + ratio)
+        out[m] = profiles.flatten()
+    np.savez_compressed(os.path.join(HERE, "retrieval_conv_%s.npz" % name), params=params,
+                        profiles=out, status=status)
+    print("retrieval_conv_%s.npz: %d ok, %d T-rejected, %d abundance-rejected" % (
+        name, (status == 0).sum(), (status == 16).sum(), (status == 32).sum()))
+
+
+def make_band_oracle(name, tmp):
+    case, spec, extra = cases.build_retrieval(name, tmp)
+    conv = ro.Converter(case["press_bar"], case["species"], case["abund"], spec["molfit"], spec["pt"],
+                        pt_args=extra["pt_args"], nrad=spec["nrad"], ncloud=spec["ncloud"],
+                        nray=spec["nray"])
+    band = ro.BandOracle(case["cfg"], conv, case["filters"], extra["starwn"], extra["starfl"],
+                         extra["rprs"])
+    return case, spec, band
+
+
+def retrieval_data(spec, band):
+    """Synthetic observation: band fluxes at `truth` + seeded 1 % noise."""
+    truth = band(np.array(spec["truth"]))[0]
+    rng = np.random.default_rng(spec["seed"])
+    uncert = 0.01 * np.abs(truth)
+    return truth + rng.normal(0, 1, truth.shape) * uncert, uncert
+
+
+def golden_mc3(mc3, name, tmp):
+    case, spec, band = make_band_oracle(name, tmp)
+    data, uncert = retrieval_data(spec, band)
+    sav = os.path.join(tmp, name + "_trace.npy")
+    log = open(os.path.join(tmp, name + ".log"), "w")
+    np.random.seed(spec["seed"])
+    out = mc3.mc.mcmc(data, uncert, band, [], params=np.array(spec["params"]),
+                      pmin=np.array(spec["pmin"]), pmax=np.array(spec["pmax"]),
+                      stepsize=np.array(spec["stepsize"], dtype=float), numit=spec["numit"],
+                      nchains=spec["nchains"], walk="demc", leastsq=False, grtest=False,
+                      burnin=spec["burnin"], plots=False, savefile=sav, log=log)
+    allparams = np.load(sav)                       # [nchains][nfree][chainsize] (mcmc.py:842-843)
+    np.savez_compressed(os.path.join(HERE, "retrieval_mc3_%s.npz" % name), data=data, uncert=uncert,
+                        allparams=allparams, allstack=out[0], bestp=out[1])
+    print("retrieval_mc3_%s.npz: trace %s, posterior %s, best %s" % (
+        name, allparams.shape, out[0].shape, np.array2string(out[1], precision=4)))
+
+
+def main():
+    shim()
+    sys.path.insert(0, os.path.join(REF, "code"))
+    import PT as pt
+    mc3 = build_mc3()
+    golden_pt(pt)
+    with tempfile.TemporaryDirectory() as tmp:
+        for name in cases.RETRIEVAL:
+            golden_converter(pt, name, tmp)
+            golden_mc3(mc3, name, tmp)
+
+
+if __name__ == "__main__":
+    main()
