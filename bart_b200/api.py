@@ -80,6 +80,19 @@ def lib():
     L.bart_line_bins.argtypes = [C.POINTER(C.c_longlong), C.c_longlong]
     L.bart_voigt_profile.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_float), C.c_longlong,
                                      C.POINTER(C.c_longlong)]
+    L.bart_converter_init.argtypes = [C.c_int, C.c_int, dp, C.c_int, dp, dp, C.c_int, ip, C.c_int, ip,
+                                      C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int,
+                                      C.c_int]
+    L.bart_profiles_from_params.argtypes = [dp, C.c_int, C.c_int, dp, C.c_int, ip, dp]
+    L.bart_bandflux_from_params.argtypes = [dp, C.c_int, C.c_int, dp, ip]
+    L.bart_bandflux_from_params_device.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.bart_chain_block.argtypes = [C.c_int, C.c_int, C.c_int, ip, ip]
+    L.bart_chain_block.restype = None
+    L.bart_mcmc_init.argtypes = [C.c_int, C.c_int, dp, dp, dp, dp, dp, dp, C.c_int, dp, dp,
+                                 C.c_double, C.c_double, C.c_int]
+    L.bart_mcmc_run.argtypes = [C.c_int, dp, ip, ip, dp, dp]
+    L.bart_mcmc_get.restype = C.c_longlong
+    L.bart_mcmc_get.argtypes = [C.c_char_p, dp, C.c_longlong]
     L.bart_set_error_mode(1)
     _lib = L
     return L
@@ -231,6 +244,99 @@ class Transit:
         out = np.empty((M, self.nlayer, self.nwave)) if fetch else None
         _check(lib().bart_extinction_batch(_d(p), M, p.shape[1],
                                            None if out is None else _d(out), 1 if total else 0))
+        return out
+
+    # ---- retrieval loop on the device (include/bart_b200.h part 3) -------------------------
+    PT_TYPES = {"iso": 0, "line": 1, "adiabatic": 2}
+
+    def converter_init(self, pressure_bar, species, abundances, molfit, pt_type="line", pt_args=None,
+                       tint_type="const", tmin=400.0, tmax=3000.0, nrad=None, ncloud=0, nray=0):
+        """Input-converter set-up of code/BARTfunc.py:139-222: `abundances[layer][species]`,
+        `pressure_bar[layer]` and `species` as makeatm.readatm returns them; `molfit` the fitted
+        molecule names; pt_args = (R_star, T_star, T_int, sma, gravity) for PT_line."""
+        species = list(species)
+        press = np.ascontiguousarray(pressure_bar, dtype=np.float64)
+        ab = np.ascontiguousarray(abundances, dtype=np.float64)
+        if ab.shape != (self.nlayer, self.nspec) or press.shape != (self.nlayer,):
+            raise BartError("abundances must be [%d layers][%d species]" % (self.nlayer, self.nspec))
+        imol = np.array([species.index(m) for m in molfit], dtype=np.int32)
+        imetals = np.array([i for i, s in enumerate(species) if s not in ("H2", "He", "H-", "e-")],
+                           dtype=np.int32)
+        npt = {"iso": 1, "line": 5, "adiabatic": 3}[pt_type]
+        if nrad is None:
+            nrad = 0 if self.eclipse else 1
+        args = np.ascontiguousarray(pt_args if pt_args is not None else np.zeros(5), dtype=np.float64)
+        _check(lib().bart_converter_init(self.PT_TYPES[pt_type], npt, _d(args),
+                                         int(tint_type == "thorngren"), _d(press), _d(ab), len(imol),
+                                         imol.ctypes.data_as(ip), len(imetals),
+                                         imetals.ctypes.data_as(ip), species.index("H2"),
+                                         species.index("He"), float(tmin), float(tmax), int(nrad),
+                                         int(ncloud), int(nray)))
+        self.npars = lib().bart_converter_npars()
+        return self.npars
+
+    def profiles_from_params(self, params):
+        """params[M][npars] -> (profiles[M][n_in], status[M], knobs[3][M]) (parity/debug)."""
+        params = np.ascontiguousarray(np.atleast_2d(params), dtype=np.float64)
+        M = params.shape[0]
+        prof = np.zeros((M, self.n_in))
+        status = np.zeros(M, dtype=np.int32)
+        knobs = np.zeros((3, M))
+        _check(lib().bart_profiles_from_params(_d(params), M, params.shape[1], _d(prof), self.n_in,
+                                               status.ctypes.data_as(ip), _d(knobs)))
+        return prof, status, knobs
+
+    def bandflux_from_params(self, params, out=None, status=None):
+        """One BARTfunc.py worker iteration (309-399) for a batch of proposals."""
+        params = np.ascontiguousarray(np.atleast_2d(params), dtype=np.float64)
+        M = params.shape[0]
+        if out is None:
+            out = np.empty((M, self.nfilters))
+        if status is None:
+            status = np.zeros(M, dtype=np.int32)
+        _check(lib().bart_bandflux_from_params(_d(params), M, params.shape[1], _d(out),
+                                               status.ctypes.data_as(ip)))
+        return out, status
+
+    def mcmc_init(self, params, pmin, pmax, stepsize, data, uncert, prior=None, priorlow=None,
+                  fgamma=1.0, fepsilon=0.0, burnin=0):
+        params = np.ascontiguousarray(np.atleast_2d(params), dtype=np.float64)
+        nchains, npars = params.shape
+        f = lambda a: np.ascontiguousarray(a if a is not None else np.zeros(npars), dtype=np.float64)
+        pmin, pmax, stepsize, prior, priorlow = (f(a) for a in (pmin, pmax, stepsize, prior, priorlow))
+        data = np.ascontiguousarray(data, dtype=np.float64)
+        uncert = np.ascontiguousarray(uncert, dtype=np.float64)
+        _check(lib().bart_mcmc_init(nchains, npars, _d(params), _d(pmin), _d(pmax), _d(stepsize),
+                                    _d(prior), _d(priorlow), len(data), _d(data), _d(uncert),
+                                    float(fgamma), float(fepsilon), int(burnin)))
+        self._mc_shape = (nchains, npars, int(np.sum(stepsize > 0)), len(data))
+
+    def mcmc_run(self, support, r1, r2, unif, ugamma):
+        support = np.ascontiguousarray(support, dtype=np.float64)
+        unif = np.ascontiguousarray(unif, dtype=np.float64)
+        ugamma = np.ascontiguousarray(ugamma, dtype=np.float64)
+        r1 = np.ascontiguousarray(r1, dtype=np.int32)
+        r2 = np.ascontiguousarray(r2, dtype=np.int32)
+        niter = unif.shape[0]
+        nchains, npars, nfree, ndata = self._mc_shape
+        if support.shape != (niter, nchains, nfree) or r1.shape != (nchains, niter) or \
+                r2.shape != (nchains, niter) or unif.shape != (niter, nchains) or \
+                ugamma.shape != (niter, nchains):
+            raise BartError("random streams do not have MC3's shapes for %d chains x %d iterations"
+                            % (nchains, niter))
+        _check(lib().bart_mcmc_run(niter, _d(support), r1.ctypes.data_as(ip), r2.ctypes.data_as(ip),
+                                   _d(unif), _d(ugamma)))
+        self._mc_niter = niter
+
+    def mcmc_get(self, name):
+        nchains, npars, nfree, ndata = self._mc_shape
+        shapes = {"allparams": (nchains, nfree, getattr(self, "_mc_niter", 0)),
+                  "params": (nchains, npars), "currchisq": (nchains,), "numaccept": (nchains,),
+                  "outbounds": (nchains, nfree), "bestp": (npars,), "bestchisq": (1,),
+                  "bestmodel": (ndata,), "models": (nchains, ndata)}
+        out = np.zeros(shapes[name])
+        n = lib().bart_mcmc_get(name.encode(), _d(out), out.size)
+        _check(0 if n >= 0 else -1)
         return out
 
     def debug_keep(self, on=True):

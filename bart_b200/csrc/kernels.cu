@@ -93,10 +93,15 @@ __device__ __forceinline__ void stage_table(double *s_tab, const double *g_tab, 
 // K0
 __global__ void __launch_bounds__(128)
 atm_prep_kernel(DevConfig c, Knobs knobs, const double *__restrict__ profiles, int n_in,
-                double *__restrict__ tabs, int *__restrict__ status, int nmodels) {
+                double *__restrict__ tabs, int *__restrict__ status,
+                const int *__restrict__ pre_status, int nmodels) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int m = blockIdx.x;
   if (m >= nmodels) return;
+  if (pre_status && pre_status[m] != 0) {        // rejected by the input converter already
+    if (threadIdx.x == 0) status[m] = pre_status[m];
+    return;
+  }
   const int nl = c.nlayer;
   double *s_rho = reinterpret_cast<double *>(smem_raw);        // [nspec][nl]
   double *s_mu = s_rho + (size_t)c.nspec * nl;                 // [nl]
@@ -479,14 +484,15 @@ void launch_grid_relayout(const double *in, double *out, int ncells, int nmol, i
 }
 
 void launch_atm_prep(const DevConfig &c, const Knobs &k, const double *profiles, int n_in,
-                     double *tabs, int *status, int nmodels, cudaStream_t s) {
+                     double *tabs, int *status, const int *pre_status, int nmodels,
+                     cudaStream_t s) {
   const size_t smem = ((size_t)c.nspec + 3) * c.nlayer * sizeof(double);
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
     cudaFuncSetAttribute(atm_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = smem;
   }
-  atm_prep_kernel<<<nmodels, 128, smem, s>>>(c, k, profiles, n_in, tabs, status, nmodels);
+  atm_prep_kernel<<<nmodels, 128, smem, s>>>(c, k, profiles, n_in, tabs, status, pre_status, nmodels);
 }
 
 template <int NMOL, int NCIA, int NANG, bool KEEP, int SQ = -1>

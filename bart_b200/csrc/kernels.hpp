@@ -11,7 +11,8 @@ constexpr int kEclThreads = 64;       // eclipse kernel: 64 threads x kEclCols c
 constexpr int kEclCols = 2;
 
 void launch_atm_prep(const DevConfig &c, const Knobs &k, const double *profiles, int n_in,
-                     double *tabs, int *status, int nmodels, cudaStream_t s);
+                     double *tabs, int *status, const int *pre_status, int nmodels,
+                     cudaStream_t s);
 void launch_eclipse(const DevConfig &c, const double *tabs, const int *status, double *spectra,
                     double *tau_keep, int *last_keep, int nmodels, bool keep, int use_tma,
                     cudaStream_t s);

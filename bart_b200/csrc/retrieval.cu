@@ -1,0 +1,270 @@
+// retrieval.cu -- sm_100a kernels of the retrieval loop around the forward model (SURVEY.md 8f
+// rows 1-2): a generation goes parameters -> profiles -> spectra -> band fluxes -> chi-squared ->
+// Metropolis step without leaving the device.
+//
+//   convert_params_kernel  one CTA per proposal, thread <-> layer: temperature profile (PT_line of
+//                          Line et al. 2013 with E_2 by series / continued fraction, PT_iso,
+//                          PT_adiabatic), abundance scaling 10^p, H2/He renormalisation, the two
+//                          rejection tests, per-model radius / cloud-top / scattering knobs.
+//                          Writes the profiles buffer in run_transit's layout, so atm_prep reads it
+//                          unchanged.
+//   demc_propose_kernel    thread <-> chain: DE-MC jump from two other chains' current states,
+//                          boundary clamp, shared parameters.  Products and sums are rounded
+//                          separately (no FMA contraction) so chains are bit-identical to numpy.
+//   chisq_accept_kernel    one CTA: per-chain chi-squared with priors, Metropolis rule, state
+//                          update, trace, running best fit (first-index argmin like numpy).
+//
+// These are latency-bound kernels over [nchains x npars] doubles: no roofline claim; they exist so
+// that the per-generation host round trip (MPI scatter/gather in the reference) disappears.
+#include "retrieval.hpp"
+#include <cmath>
+
+namespace bart {
+
+// ---------------------------------------------------------------------------------------
+// E_2(x): exponential integral of order 2 (scipy.special.expn(2, x) in code/PT.py:736; cephes
+// expn: power series for x <= 1, continued fraction above).
+__device__ double expint2(double x) {
+  const double EUL = 0.57721566490153286060, MACHEP = 1.11022302462515654042e-16;
+  const double BIG = 1.44115188075855872e17, MAXLOG = 7.09782712893383996843e2;
+  const int n = 2;
+  if (!(x <= MAXLOG)) return x != x ? x : 0.0;
+  if (x == 0.0) return 1.0;
+  if (x > 1.0) {
+    int k = 1;
+    double pkm2 = 1.0, qkm2 = x, pkm1 = 1.0, qkm1 = x + n, ans = pkm1 / qkm1, t;
+    do {
+      k++;
+      double yk, xk;
+      if (k & 1) { yk = 1.0; xk = n + (k - 1) / 2; }
+      else { yk = x; xk = k / 2; }
+      const double pk = __dadd_rn(__dmul_rn(pkm1, yk), __dmul_rn(pkm2, xk));
+      const double qk = __dadd_rn(__dmul_rn(qkm1, yk), __dmul_rn(qkm2, xk));
+      if (qk != 0.0) { const double r = pk / qk; t = fabs((ans - r) / r); ans = r; }
+      else t = 1.0;
+      pkm2 = pkm1; pkm1 = pk; qkm2 = qkm1; qkm1 = qk;
+      if (fabs(pk) > BIG) { pkm2 /= BIG; pkm1 /= BIG; qkm2 /= BIG; qkm1 /= BIG; }
+    } while (t > MACHEP && k < 100000);
+    return ans * exp(-x);
+  }
+  double psi = -EUL - log(x);
+  psi += 1.0;                                   // sum_{i=1}^{n-1} 1/i
+  const double z = -x;
+  double xk = 0.0, yk = 1.0, pk = 1.0 - n, ans = 1.0 / pk, t;
+  int it = 0;
+  do {
+    xk += 1.0;
+    yk *= z / xk;
+    pk += 1.0;
+    if (pk != 0.0) ans += yk / pk;
+    t = ans != 0.0 ? fabs(yk / ans) : 1.0;
+  } while (t > MACHEP && ++it < 100000);
+  return __dmul_rn(z, psi) - ans;               // z^(n-1) psi / Gamma(n) - series
+}
+
+// eq. 14 of Line et al. 2013 (PT.py:719-737)
+__device__ double line_xi(double gamma, double tau) {
+  const double gt = gamma * tau;
+  return (2.0 / 3) * (1 + (1. / gamma) * (1 + (0.5 * gamma * tau - 1) * exp(-gt)) +
+                      gamma * (1 - 0.5 * (tau * tau)) * expint2(gt));
+}
+
+__device__ double pt_temperature(const ConvConfig &cc, const double *par, double p_bar) {
+  if (cc.pt_type == PT_ISO) return par[0];
+  if (cc.pt_type == PT_ADIABATIC) {             // PT.py:741-750
+    const double p0 = pow(10.0, par[2]);
+    return par[0] / (1 + (par[1] - 1) / par[1] * log(p0 / p_bar));
+  }
+  // PT_line (PT.py:664-697)
+  const double kappa = pow(10.0, par[0]), g1 = pow(10.0, par[1]), g2 = pow(10.0, par[2]);
+  const double alpha = par[3], beta = par[4];
+  const double tirr = beta * sqrt(cc.rstar / (2.0 * cc.sma)) * cc.tstar;
+  const double tau = kappa * (p_bar * 1e6) / cc.grav;
+  const double xi1 = line_xi(g1, tau), xi2 = line_xi(g2, tau);
+  const double ti4 = pow(cc.tint, 4.0), tr4 = pow(tirr, 4.0);
+  return pow(0.75 * (ti4 * (2.0 / 3.0 + tau) + tr4 * (1 - alpha) * xi1 + tr4 * alpha * xi2), 0.25);
+}
+
+__global__ void __launch_bounds__(128)
+convert_params_kernel(ConvConfig cc, const double *__restrict__ params, int npars,
+                      double *__restrict__ profiles, int n_in, int *__restrict__ status,
+                      ConvKnobs kn, int nmodels) {
+  const int m = blockIdx.x;
+  if (m >= nmodels) return;
+  __shared__ int s_bad;
+  __shared__ double s_par[kMaxPars];
+  if (threadIdx.x == 0) s_bad = 0;
+  for (int i = threadIdx.x; i < npars; i += blockDim.x) s_par[i] = params[(size_t)m * npars + i];
+  __syncthreads();
+  const int nl = cc.nlayer;
+  const int off = cc.npt + cc.nrad + cc.ncloud + cc.nray;
+  double *out = profiles + (size_t)m * n_in;
+  int bad = 0;
+  for (int l = threadIdx.x; l < nl; l += blockDim.x) {
+    const double T = pt_temperature(cc, s_par, cc.press_bar[l]);
+    if (!(T >= cc.tmin) || !(T <= cc.tmax)) bad |= REJ_TBOUNDS;   // also catches NaN
+    out[l] = T;
+    // scaled abundances and the metal sum in the reference's order (BARTfunc.py:333-338)
+    double metals = 0.0;
+    for (int j = 0; j < cc.nspec; j++) {
+      double a = cc.base[(size_t)j * nl + l];
+      for (int k = 0; k < cc.nmolfit; k++)
+        if (cc.imol[k] == j) a = a * pow(10.0, s_par[off + k]);
+      if (j != cc.iH2 && j != cc.iHe) out[(size_t)(j + 1) * nl + l] = a;
+    }
+    for (int k = 0; k < cc.nmetals; k++) {
+      const double a = out[(size_t)(cc.imetals[k] + 1) * nl + l];
+      metals = k == 0 ? a : metals + a;
+    }
+    const double q = 1.0 - metals;
+    if (q < 0.0) bad |= REJ_ABUND;
+    const double ratio = cc.ratio[l];
+    out[(size_t)(cc.iH2 + 1) * nl + l] = ratio * q / (1.0 + ratio);
+    out[(size_t)(cc.iHe + 1) * nl + l] = q / (1.0 + ratio);
+  }
+  if (bad) atomicOr(&s_bad, bad);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // the temperature test comes first and wins (BARTfunc.py:327-330 before 339-344)
+    status[m] = (s_bad & REJ_TBOUNDS) ? REJ_TBOUNDS : s_bad;
+    int c = cc.npt;
+    if (cc.nrad) kn.r0[m] = s_par[c++];
+    if (cc.ncloud) kn.cloudtop[m] = s_par[c++];
+    if (cc.nray == 1) { kn.scat_flag[m] = 1; kn.scat_logext[m] = s_par[c]; }
+    else if (cc.nray == 2) { kn.scat_flag[m] = 2; kn.scat_logext[m] = 0.0; }
+  }
+}
+
+void launch_convert_params(const ConvConfig &cc, const double *params, int npars, double *profiles,
+                           int n_in, int *status, const ConvKnobs &kn, int nmodels, cudaStream_t s) {
+  if (nmodels <= 0) return;
+  convert_params_kernel<<<nmodels, 128, 0, s>>>(cc, params, npars, profiles, n_in, status, kn, nmodels);
+}
+
+// ---------------------------------------------------------------------------------------
+// DE-MC proposal (mcmc.py:524-575): jump = gamma1 (x_r1 - x_r2) + fepsilon * support
+__global__ void demc_propose_kernel(McmcDev mc) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= mc.nchains) return;
+  const int i = *mc.iter;
+  const int np = mc.npars;
+  const double *cur = mc.params + (size_t)c * np;
+  double *nx = mc.nextp + (size_t)c * np;
+  const double *a = mc.params + (size_t)mc.r1[(size_t)c * mc.chainsize + i] * np;
+  const double *b = mc.params + (size_t)mc.r2[(size_t)c * mc.chainsize + i] * np;
+  const double g = mc.ugamma[(size_t)i * mc.nchains + c] < 0.1 ? 0.98 : mc.gamma;
+  const double *sup = mc.support + ((size_t)i * mc.nchains + c) * mc.nfree;
+  int out = 0;
+  for (int f = 0; f < mc.nfree; f++) {
+    const int p = mc.ifree[f];
+    const double jump = __dadd_rn(__dmul_rn(g, __dsub_rn(a[p], b[p])), __dmul_rn(mc.fepsilon, sup[f]));
+    double v = __dadd_rn(cur[p], jump);
+    const int o = (v < mc.pmin[p]) || (v > mc.pmax[p]);
+    out |= o;
+    mc.outbounds[(size_t)c * mc.nfree + f] += o;
+    if (v < mc.pmin[p]) v = mc.pmin[p];
+    if (v > mc.pmax[p]) v = mc.pmax[p];
+    nx[p] = v;
+  }
+  for (int s = 0; s < mc.nshare; s++) nx[mc.share_dst[s]] = nx[mc.share_src[s]];
+  mc.outflag[c] = out;
+}
+
+void launch_demc_propose(const McmcDev &mc, cudaStream_t s) {
+  const int threads = 128;
+  demc_propose_kernel<<<(mc.nchains + threads - 1) / threads, threads, 0, s>>>(mc);
+}
+
+// ---------------------------------------------------------------------------------------
+__device__ const double *chain_model(const double *models, const ModelMap &mp, int c, int ndata) {
+  // contiguous blocks: the first `extra` ranks own base+1 chains (driver.partition)
+  const int cut = mp.extra * (mp.base + 1);
+  int r, j;
+  if (c < cut) { r = c / (mp.base + 1); j = c - r * (mp.base + 1); }
+  else { r = mp.extra + (mp.base > 0 ? (c - cut) / mp.base : 0); j = c - cut - (r - mp.extra) * mp.base; }
+  return models + ((size_t)r * mp.pad + j) * ndata;
+}
+
+// chisq.c:111-142 + stats.h:72-103: sequential sums; priorup is priorlow at the call sites
+// (mcmc.py:338-339,596-597 pass priorlow twice)
+__device__ void chain_chisq(const McmcDev &mc, const double *model, const double *p, double *chisq,
+                            double *c2) {
+  double c = 0.0;
+  for (int i = 0; i < mc.ndata; i++) {
+    const double r = (model[i] - mc.data[i]) / mc.uncert[i];
+    c = __dadd_rn(c, __dmul_rn(r, r));
+  }
+  double jc = 0.0;
+  for (int k = 0; k < mc.nprior; k++) {
+    const int ip = mc.iprior[k];
+    const double off = p[ip] - mc.prior[ip], lo = mc.priorlow[ip];
+    if (lo == -1) { const double t = 2.0 * log(off); c += t; jc += t; }
+    else { const double r = off / lo; c = __dadd_rn(c, __dmul_rn(r, r)); }
+  }
+  *chisq = c;
+  *c2 = c - jc;
+}
+
+__global__ void __launch_bounds__(256)
+chisq_accept_kernel(McmcDev mc, const double *__restrict__ models, ModelMap mp, int first) {
+  const int np = mc.npars;
+  const int i = *mc.iter;
+  for (int c = threadIdx.x; c < mc.nchains; c += blockDim.x) {
+    const double *model = chain_model(models, mp, c, mc.ndata);
+    double *cur = mc.params + (size_t)c * np;
+    if (first) {
+      chain_chisq(mc, model, cur, &mc.currchisq[c], &mc.c2[c]);
+      continue;
+    }
+    const double *nx = mc.nextp + (size_t)c * np;
+    double next;
+    if (!mc.outflag[c]) {
+      chain_chisq(mc, model, nx, &next, &mc.c2[c]);
+    } else next = INFINITY;                                  // mcmc.py:598
+    mc.nextchisq[c] = next;
+    const double accept = exp(0.5 * (mc.currchisq[c] - next));
+    const bool ok = accept >= mc.unif[(size_t)i * mc.nchains + c];
+    if (ok) {
+      for (int p = 0; p < np; p++) cur[p] = nx[p];
+      mc.currchisq[c] = next;
+      if (mc.nold + i >= mc.burnin) mc.numaccept[c] += 1.0;
+    }
+    for (int f = 0; f < mc.nfree; f++)
+      mc.allparams[((size_t)c * mc.nfree + f) * mc.chainsize + i] = cur[mc.ifree[f]];
+  }
+  __syncthreads();
+  // running best fit: first index of the minimum no-Jeffreys chi-squared (np.argmin)
+  if (threadIdx.x < 32) {
+    double best = INFINITY;
+    int arg = 0x7fffffff;
+    for (int c = threadIdx.x; c < mc.nchains; c += 32) {
+      const double v = mc.c2[c];
+      if (v < best || (v == best && c < arg)) { best = v; arg = c; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ob = __shfl_down_sync(0xffffffffu, best, o);
+      const int oa = __shfl_down_sync(0xffffffffu, arg, o);
+      if (ob < best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+    }
+    best = __shfl_sync(0xffffffffu, best, 0);
+    arg = __shfl_sync(0xffffffffu, arg, 0);
+    const bool take = arg < mc.nchains && (first || best < *mc.bestchisq);
+    if (take) {
+      const double *model = chain_model(models, mp, arg, mc.ndata);
+      for (int p = threadIdx.x; p < np; p += 32) mc.bestp[p] = mc.params[(size_t)arg * np + p];
+      for (int d = threadIdx.x; d < mc.ndata; d += 32) mc.bestmodel[d] = model[d];
+    }
+    __syncwarp();
+    if (threadIdx.x == 0) {
+      if (take) *mc.bestchisq = best;
+      if (!first) *mc.iter = i + 1;
+    }
+  }
+}
+
+void launch_chisq_accept(const McmcDev &mc, const double *models, ModelMap map, int first,
+                         cudaStream_t s) {
+  chisq_accept_kernel<<<1, 256, 0, s>>>(mc, models, map, first);
+}
+
+}  // namespace bart

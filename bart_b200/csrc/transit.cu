@@ -11,6 +11,7 @@
 #include "kernels.hpp"
 #include "column_math.cuh"
 #include "builder.hpp"
+#include "retrieval.hpp"
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <cstdarg>
@@ -140,6 +141,19 @@ struct State {
   int rank = 0, world = 1;
   // builder
   BuilderState *builder = nullptr;
+  // input converter (retrieval.hpp)
+  ConvConfig conv{};
+  DevBuf<double> d_cpress, d_cbase, d_cratio, d_cparams;
+  DevBuf<int> d_cstatus;
+  const int *pre_status = nullptr;         // converter rejections of the batch being launched
+  // DE-MC loop
+  McmcDev mc{};
+  bool mc_ready = false;
+  int mc_lo = 0, mc_hi = 0, mc_pad = 0;
+  DevBuf<double> d_mcd[20];
+  DevBuf<int> d_mci[8];
+  DevBuf<double> d_mcband, d_mcgather;
+  cudaGraphExec_t mc_graph = nullptr;
 };
 static State G;
 
@@ -347,6 +361,12 @@ static void reset_state() {
   G.d_fstart.release(); G.d_fcount.release(); G.d_foffset.release(); G.d_fweight.release();
   G.d_fstar.release(); G.d_flush.release();
   if (G.builder) { builder_free(G.builder); G.builder = nullptr; }
+  G.d_cpress.release(); G.d_cbase.release(); G.d_cratio.release(); G.d_cparams.release();
+  G.d_cstatus.release(); G.d_mcband.release(); G.d_mcgather.release();
+  for (auto &b : G.d_mcd) b.release();
+  for (auto &b : G.d_mci) b.release();
+  if (G.mc_graph) { cudaGraphExecDestroy(G.mc_graph); G.mc_graph = nullptr; }
+  G.conv = ConvConfig(); G.mc = McmcDev(); G.mc_ready = false; G.pre_status = nullptr;
   G.nfilters = 0; G.knob_models = 0; G.last_batch = 0;
   G.cia.clear(); G.wn.clear(); G.angles.clear();
   G.init = false;
@@ -518,7 +538,7 @@ static void launch_models(const double *d_prof, int off, int count, int total, i
   int *last = G.keep ? G.d_last.p + (size_t)off * c.nwave : nullptr;
   {
     KernelScope ks("atm_prep");
-    launch_atm_prep(c, k, d_prof, n_in, tabs, status, count, G.stream);
+    launch_atm_prep(c, k, d_prof, n_in, tabs, status, G.pre_status ? G.pre_status + off : nullptr, count, G.stream);
     check_launch("atm_prep");
   }
   if (c.eclipse) {
@@ -558,6 +578,90 @@ static void band_device(const double *d_spec, int nmodels, const int *d_status, 
                         G.have_star ? G.d_fstar.p : nullptr, G.rprs2, d_status, d_band, G.nfilters,
                         G.dc.nwave, nmodels, G.stream);
   check_launch("band_integrate");
+}
+
+
+// ---------------------------------------------------------------------------------------
+// retrieval loop (retrieval.cu): parameters -> band fluxes on the device
+static void chain_block(int nchains, int world, int rank, int *lo, int *hi) {
+  const int base = nchains / world, extra = nchains % world;
+  *lo = rank * base + std::min(rank, extra);
+  *hi = *lo + base + (rank < extra ? 1 : 0);
+}
+
+// converter + forward model + band integration for `nmodels` parameter vectors on the device.
+// No synchronisation: everything is queued on G.stream.
+static void ensure_params_buffers(int nmodels) {
+  const DevConfig &c = G.dc;
+  if (!G.init || G.opt.justOpacity) fail("Transit init not run, please initialize transit.");
+  if (!G.conv.ready) fail("bart_converter_init has not been called");
+  if (G.nfilters <= 0) fail("bart_set_filters has not been called");
+  const int n_in = (c.nspec + 1) * c.nlayer;
+  G.d_prof.ensure((size_t)std::max(1, nmodels) * n_in);
+  G.d_spec.ensure((size_t)std::max(1, nmodels) * c.nwave);
+  G.d_cstatus.ensure(std::max(1, nmodels));
+  G.d_kr0.ensure(std::max(1, nmodels)); G.d_kcloud.ensure(std::max(1, nmodels));
+  G.d_klogext.ensure(std::max(1, nmodels)); G.d_kflag.ensure(std::max(1, nmodels));
+  prepare_batch(nmodels, n_in);
+}
+
+static void params_to_bandflux_queued(const double *d_params, int nmodels, int npars, double *d_band) {
+  const DevConfig &c = G.dc;
+  const ConvConfig &cc = G.conv;
+  if (npars != cc.npars) fail("parameter vectors have %d entries, the converter expects %d", npars, cc.npars);
+  if (nmodels <= 0) return;
+  const int n_in = (c.nspec + 1) * c.nlayer;
+  ConvKnobs kn{G.d_kr0.p, G.d_kcloud.p, G.d_klogext.p, G.d_kflag.p};
+  {
+    KernelScope ks("convert_params");
+    launch_convert_params(cc, d_params, npars, G.d_prof.p, n_in, G.d_cstatus.p, kn, nmodels, G.stream);
+    check_launch("convert_params");
+  }
+  // per-model knobs written by the converter (BARTfunc.py:350-360)
+  Knobs saved = G.knobs;
+  const int saved_models = G.knob_models;
+  G.knobs.r0 = cc.nrad ? G.d_kr0.p : nullptr;
+  G.knobs.cloudtop = cc.ncloud ? G.d_kcloud.p : nullptr;
+  G.knobs.scat_flag = cc.nray ? G.d_kflag.p : nullptr;
+  G.knobs.scat_logext = cc.nray ? G.d_klogext.p : nullptr;
+  G.knob_models = nmodels;
+  G.pre_status = G.d_cstatus.p;
+  launch_models(G.d_prof.p, 0, nmodels, nmodels, n_in, G.d_spec.p);
+  G.pre_status = nullptr;
+  G.knobs = saved;
+  G.knob_models = saved_models;
+  G.last_batch = nmodels;
+  band_device(G.d_spec.p, nmodels, G.d_status.p, d_band);
+}
+
+// one DE-MC generation, queued on G.stream (first: the initial evaluation, mcmc.py:310-345)
+static void mcmc_generation_queued(int first) {
+  McmcDev &mc = G.mc;
+  const int nloc = G.mc_hi - G.mc_lo;
+  if (!first) {
+    KernelScope ks("demc_propose");
+    launch_demc_propose(mc, G.stream);
+    check_launch("demc_propose");
+  }
+  const double *src = (first ? mc.params : mc.nextp) + (size_t)G.mc_lo * mc.npars;
+  params_to_bandflux_queued(src, nloc, mc.npars, G.d_mcband.p);
+  const double *models = G.d_mcband.p;
+  if (G.world > 1) {
+    typedef int (*fn_allgather)(const void *, void *, size_t, int, void *, cudaStream_t);
+    fn_allgather ag = (fn_allgather)dlsym(G.nccl_lib, "ncclAllGather");
+    if (!ag || !G.nccl_comm) fail("multi-rank DE-MC needs bart_comm_init first");
+    int rc = ag(G.d_mcband.p, G.d_mcgather.p, (size_t)G.mc_pad * mc.ndata, 8 /*ncclFloat64*/,
+                G.nccl_comm, G.stream);
+    if (rc != 0) fail("ncclAllGather failed (%d)", rc);
+    G.launches++;
+    models = G.d_mcgather.p;
+  }
+  ModelMap mp{G.world, mc.nchains / G.world, mc.nchains % G.world, G.mc_pad};
+  {
+    KernelScope ks("chisq_accept");
+    launch_chisq_accept(mc, models, mp, first, G.stream);
+    check_launch("chisq_accept");
+  }
 }
 
 static void finish_stream() {
@@ -854,7 +958,7 @@ int bart_extinction_batch(const double *profiles, int nmodels, int n_in, double 
   CUDA_OK(cudaMemcpyAsync(G.d_prof.p, profiles, (size_t)nmodels * n_in * 8, cudaMemcpyHostToDevice, G.stream));
   Knobs k = effective_knobs(nmodels);
   { KernelScope ks("atm_prep");
-    launch_atm_prep(c, k, G.d_prof.p, n_in, G.d_tabs.p, G.d_status.p, nmodels, G.stream); check_launch("atm_prep"); }
+    launch_atm_prep(c, k, G.d_prof.p, n_in, G.d_tabs.p, G.d_status.p, nullptr, nmodels, G.stream); check_launch("atm_prep"); }
   const int tiles = (c.nwave + kColThreads - 1) / kColThreads;
   int splits = 1;
   while ((long long)tiles * nmodels * splits < 148 * 8 && splits < c.nlayer) splits *= 2;
@@ -1060,6 +1164,313 @@ int bart_comm_finalize(void) {
   API_BEGIN
   if (G.nccl_comm) { ((fn_destroy)nccl_sym("ncclCommDestroy"))(G.nccl_comm); G.nccl_comm = nullptr; }
   return 0;
+  API_END_INT
+}
+
+
+// =========================================================================================
+// Retrieval loop on the device
+
+// replaces the input-converter set-up of code/BARTfunc.py:139-222
+int bart_converter_init(int pt_type, int npt, const double *pt_args, int tint_thorngren,
+                        const double *pressure_bar, const double *abundances, int nmolfit,
+                        const int *imol, int nmetals, const int *imetals, int iH2, int iHe,
+                        double tmin, double tmax, int nrad, int ncloud, int nray) {
+  API_BEGIN
+  if (!G.init || G.opt.justOpacity) fail("Transit init not run, please initialize transit.");
+  const DevConfig &c = G.dc;
+  ConvConfig cc{};
+  const int want = pt_type == PT_ISO ? 1 : pt_type == PT_LINE ? 5 : pt_type == PT_ADIABATIC ? 3 : -1;
+  if (want < 0) fail("unknown PT model %d (0 iso, 1 line, 2 adiabatic)", pt_type);
+  if (npt != want) fail("PT model %d takes %d parameters, got %d", pt_type, want, npt);
+  if (nmolfit < 0 || nmolfit > kMaxGridMol) fail("too many fitted molecules (%d)", nmolfit);
+  if (nmetals < 0 || nmetals > kMaxSpec) fail("too many metal species (%d)", nmetals);
+  if (iH2 < 0 || iH2 >= c.nspec || iHe < 0 || iHe >= c.nspec) fail("H2/He species index out of range");
+  if (nray < 0 || nray > 2 || nrad < 0 || nrad > 1 || ncloud < 0 || ncloud > 1) fail("bad knob counts");
+  cc.pt_type = pt_type; cc.npt = npt; cc.nrad = nrad; cc.ncloud = ncloud; cc.nray = nray;
+  cc.nmolfit = nmolfit; cc.nmetals = nmetals;
+  cc.npars = npt + nrad + ncloud + (nray ? 1 : 0) + nmolfit;
+  if (cc.npars > kMaxPars) fail("too many parameters (%d)", cc.npars);
+  cc.nlayer = c.nlayer; cc.nspec = c.nspec;
+  for (int i = 0; i < nmolfit; i++) {
+    if (imol[i] < 0 || imol[i] >= c.nspec) fail("fitted molecule index %d out of range", imol[i]);
+    cc.imol[i] = imol[i];
+  }
+  for (int i = 0; i < nmetals; i++) {
+    if (imetals[i] < 0 || imetals[i] >= c.nspec) fail("metal index %d out of range", imetals[i]);
+    cc.imetals[i] = imetals[i];
+  }
+  cc.iH2 = iH2; cc.iHe = iHe; cc.tmin = tmin; cc.tmax = tmax;
+  if (pt_type == PT_LINE) {
+    if (!pt_args) fail("PT_line needs pt_args = {R_star, T_star, T_int, sma, gravity}");
+    cc.rstar = pt_args[0]; cc.tstar = pt_args[1]; cc.tint = pt_args[2]; cc.sma = pt_args[3];
+    cc.grav = pt_args[4];
+    if (tint_thorngren) {          // Thorngren et al. 2019, code/PT.py:671-676
+      const double teq = sqrt(cc.rstar / (2.0 * cc.sma)) * cc.tstar;
+      const double F = 4.0 * 5.6703744191844314e-08 * pow(teq, 4.0);
+      cc.tint = 1.24 * teq * exp(-pow(log(F) - 0.14, 2.0) / 2.96);
+    }
+  }
+  const int nl = c.nlayer, ns = c.nspec;
+  std::vector<double> press(pressure_bar, pressure_bar + nl), base((size_t)ns * nl), ratio(nl);
+  for (int l = 0; l < nl; l++) {
+    for (int j = 0; j < ns; j++) base[(size_t)j * nl + l] = abundances[(size_t)l * ns + j];
+    ratio[l] = abundances[(size_t)l * ns + iH2] / abundances[(size_t)l * ns + iHe];
+  }
+  upload(G.d_cpress, press); upload(G.d_cbase, base); upload(G.d_cratio, ratio);
+  cc.press_bar = G.d_cpress.p; cc.base = G.d_cbase.p; cc.ratio = G.d_cratio.p;
+  cc.ready = 1;
+  G.conv = cc;
+  return 0;
+  API_END_INT
+}
+
+int bart_converter_npars(void) { return G.conv.ready ? G.conv.npars : -1; }
+
+int bart_profiles_from_params(const double *params, int nmodels, int npars, double *profiles,
+                              int n_in, int *status, double *knobs_out) {
+  API_BEGIN
+  if (!G.conv.ready) fail("bart_converter_init has not been called");
+  const ConvConfig &cc = G.conv;
+  if (npars != cc.npars) fail("parameter vectors have %d entries, the converter expects %d", npars, cc.npars);
+  const int need = (G.dc.nspec + 1) * G.dc.nlayer;
+  if (n_in != need) fail("profiles hold %d values per model, %d needed", n_in, need);
+  if (nmodels <= 0) return 0;
+  G.d_cparams.ensure((size_t)nmodels * npars);
+  G.d_prof.ensure((size_t)nmodels * n_in);
+  G.d_cstatus.ensure(nmodels);
+  G.d_kr0.ensure(nmodels); G.d_kcloud.ensure(nmodels); G.d_klogext.ensure(nmodels); G.d_kflag.ensure(nmodels);
+  CUDA_OK(cudaMemcpyAsync(G.d_cparams.p, params, (size_t)nmodels * npars * 8, cudaMemcpyHostToDevice, G.stream));
+  CUDA_OK(cudaMemsetAsync(G.d_prof.p, 0, (size_t)nmodels * n_in * 8, G.stream));
+  ConvKnobs kn{G.d_kr0.p, G.d_kcloud.p, G.d_klogext.p, G.d_kflag.p};
+  {
+    KernelScope ks("convert_params");
+    launch_convert_params(cc, G.d_cparams.p, npars, G.d_prof.p, n_in, G.d_cstatus.p, kn, nmodels, G.stream);
+    check_launch("convert_params");
+  }
+  CUDA_OK(cudaMemcpyAsync(profiles, G.d_prof.p, (size_t)nmodels * n_in * 8, cudaMemcpyDeviceToHost, G.stream));
+  if (status) CUDA_OK(cudaMemcpyAsync(status, G.d_cstatus.p, nmodels * sizeof(int), cudaMemcpyDeviceToHost, G.stream));
+  finish_stream();
+  if (knobs_out) {                       // [3][nmodels]: radius, cloudtop, scattering logext
+    std::vector<double> tmp(nmodels);
+    for (int k = 0; k < 3; k++) {
+      const bool on = k == 0 ? cc.nrad : k == 1 ? cc.ncloud : cc.nray == 1;
+      const double *src = k == 0 ? G.d_kr0.p : k == 1 ? G.d_kcloud.p : G.d_klogext.p;
+      if (on) CUDA_OK(cudaMemcpy(knobs_out + (size_t)k * nmodels, src, nmodels * 8, cudaMemcpyDeviceToHost));
+      else for (int m = 0; m < nmodels; m++) knobs_out[(size_t)k * nmodels + m] = 0.0;
+    }
+  }
+  return 0;
+  API_END_INT
+}
+
+int bart_bandflux_from_params_device(const double *d_params, int nmodels, int npars, double *d_bandflux,
+                                     int *d_status) {
+  API_BEGIN
+  ensure_params_buffers(nmodels);
+  params_to_bandflux_queued(d_params, nmodels, npars, d_bandflux);
+  if (d_status && nmodels > 0)
+    CUDA_OK(cudaMemcpyAsync(d_status, G.d_status.p, nmodels * sizeof(int), cudaMemcpyDeviceToDevice, G.stream));
+  finish_stream();
+  return 0;
+  API_END_INT
+}
+
+int bart_bandflux_from_params(const double *params, int nmodels, int npars, double *bandflux, int *status) {
+  API_BEGIN
+  if (nmodels <= 0) return 0;
+  ensure_params_buffers(nmodels);
+  G.d_cparams.ensure((size_t)nmodels * npars);
+  G.d_band.ensure((size_t)nmodels * G.nfilters);
+  CUDA_OK(cudaMemcpyAsync(G.d_cparams.p, params, (size_t)nmodels * npars * 8, cudaMemcpyHostToDevice, G.stream));
+  params_to_bandflux_queued(G.d_cparams.p, nmodels, npars, G.d_band.p);
+  CUDA_OK(cudaMemcpyAsync(bandflux, G.d_band.p, (size_t)nmodels * G.nfilters * 8, cudaMemcpyDeviceToHost, G.stream));
+  if (status) CUDA_OK(cudaMemcpyAsync(status, G.d_status.p, nmodels * sizeof(int), cudaMemcpyDeviceToHost, G.stream));
+  finish_stream();
+  return 0;
+  API_END_INT
+}
+
+void bart_chain_block(int nchains, int world, int rank, int *lo, int *hi) {
+  chain_block(nchains, world, rank, lo, hi);
+}
+
+// replaces the set-up and initial evaluation of MCcubed.mc.mcmc (mcmc.py:196-345) for walk='demc'
+int bart_mcmc_init(int nchains, int npars, const double *params, const double *pmin,
+                   const double *pmax, const double *stepsize, const double *prior,
+                   const double *priorlow, int ndata, const double *data, const double *uncert,
+                   double fgamma, double fepsilon, int burnin) {
+  API_BEGIN
+  if (!G.conv.ready) fail("bart_converter_init has not been called");
+  if (npars != G.conv.npars) fail("bart_mcmc_init: %d parameters, the converter expects %d", npars, G.conv.npars);
+  if (ndata != G.nfilters) fail("bart_mcmc_init: %d data points but %d filters", ndata, G.nfilters);
+  if (nchains < 3) fail("DE-MC needs at least 3 chains (got %d)", nchains);
+  McmcDev mc{};
+  mc.nchains = nchains; mc.npars = npars; mc.ndata = ndata; mc.burnin = burnin; mc.nold = 0;
+  mc.fepsilon = fepsilon;
+  for (int p = 0; p < npars; p++) {
+    if (stepsize[p] > 0) mc.ifree[mc.nfree++] = p;
+    else if (stepsize[p] < 0) {
+      // a shared parameter copies parameter number -stepsize (1-based) (mcmc.py:307-308):
+      // nextp[:, s] = nextp[:, -int(stepsize[s])-1]
+      const int src = -(int)stepsize[p] - 1;
+      if (src < 0 || src >= npars) fail("shared parameter %d points at %d", p, src);
+      mc.share_dst[mc.nshare] = p; mc.share_src[mc.nshare] = src; mc.nshare++;
+    }
+    if (priorlow && priorlow[p] != 0) mc.iprior[mc.nprior++] = p;
+  }
+  if (mc.nfree < 1) fail("no free parameters");
+  mc.gamma = fgamma * 2.4 / sqrt(2.0 * mc.nfree);
+  auto up = [&](int slot, const double *src, size_t n) -> double * {
+    std::vector<double> v(n, 0.0);
+    if (src) v.assign(src, src + n);
+    upload(G.d_mcd[slot], v);
+    return G.d_mcd[slot].p;
+  };
+  mc.pmin = up(0, pmin, npars); mc.pmax = up(1, pmax, npars);
+  mc.prior = up(2, prior, npars); mc.priorlow = up(3, priorlow, npars);
+  mc.data = up(4, data, ndata); mc.uncert = up(5, uncert, ndata);
+  std::vector<double> p0(params, params + (size_t)nchains * npars);
+  for (int c = 0; c < nchains; c++)
+    for (int s = 0; s < mc.nshare; s++)
+      p0[(size_t)c * npars + mc.share_dst[s]] = p0[(size_t)c * npars + mc.share_src[s]];
+  mc.params = up(6, p0.data(), p0.size());
+  mc.nextp = up(7, p0.data(), p0.size());
+  mc.currchisq = up(8, nullptr, nchains); mc.nextchisq = up(9, nullptr, nchains);
+  mc.c2 = up(10, nullptr, nchains); mc.bestp = up(11, nullptr, npars);
+  mc.bestchisq = up(12, nullptr, 1); mc.bestmodel = up(13, nullptr, ndata);
+  mc.numaccept = up(14, nullptr, nchains);
+  std::vector<int> zi((size_t)nchains * mc.nfree, 0);
+  upload(G.d_mci[0], zi); mc.outbounds = G.d_mci[0].p;
+  zi.assign(nchains, 0); upload(G.d_mci[1], zi); mc.outflag = G.d_mci[1].p;
+  zi.assign(1, 0); upload(G.d_mci[2], zi); mc.iter = G.d_mci[2].p;
+  G.mc = mc;
+  chain_block(nchains, G.world, G.rank, &G.mc_lo, &G.mc_hi);
+  G.mc_pad = nchains / G.world + (nchains % G.world ? 1 : 0);
+  G.d_mcband.ensure((size_t)G.mc_pad * ndata);
+  G.d_mcgather.ensure((size_t)G.mc_pad * ndata * G.world);
+  CUDA_OK(cudaMemsetAsync(G.d_mcband.p, 0, (size_t)G.mc_pad * ndata * 8, G.stream));
+  if (G.mc_graph) { cudaGraphExecDestroy(G.mc_graph); G.mc_graph = nullptr; }
+  ensure_params_buffers(G.mc_hi - G.mc_lo);
+  mcmc_generation_queued(1);
+  finish_stream();
+  G.mc_ready = true;
+  return 0;
+  API_END_INT
+}
+
+// replaces the generation loop of MCcubed.mc.mcmc (mcmc.py:518-625) for walk='demc'.  The random
+// streams come from the caller in MC3's own shapes (mcmc.py:484-507), chainsize = niter.
+int bart_mcmc_run(int niter, const double *support, const int *r1, const int *r2,
+                  const double *unif, const double *ugamma) {
+  API_BEGIN
+  if (!G.mc_ready) fail("bart_mcmc_init has not been called");
+  if (niter <= 0) return 0;
+  McmcDev &mc = G.mc;
+  const int nc = mc.nchains;
+  for (size_t k = 0; k < (size_t)nc * niter; k++)
+    if (r1[k] < 0 || r1[k] >= nc || r2[k] < 0 || r2[k] >= nc) fail("chain index out of range in r1/r2");
+  mc.nold += mc.chainsize;               // iterations of earlier calls count towards burn-in
+  mc.chainsize = niter;
+  auto upd = [&](DevBuf<double> &b, const double *src, size_t n) {
+    b.ensure(n);
+    CUDA_OK(cudaMemcpyAsync(b.p, src, n * 8, cudaMemcpyHostToDevice, G.stream));
+    return (const double *)b.p;
+  };
+  auto upi = [&](DevBuf<int> &b, const int *src, size_t n) {
+    b.ensure(n);
+    CUDA_OK(cudaMemcpyAsync(b.p, src, n * 4, cudaMemcpyHostToDevice, G.stream));
+    return (const int *)b.p;
+  };
+  DevBuf<double> &d_support = G.d_mcd[15], &d_unif = G.d_mcd[16], &d_ugamma = G.d_mcd[17],
+                 &d_trace = G.d_mcd[18];
+  DevBuf<int> &d_r1 = G.d_mci[3], &d_r2 = G.d_mci[4];
+  mc.support = upd(d_support, support, (size_t)niter * nc * mc.nfree);
+  mc.unif = upd(d_unif, unif, (size_t)niter * nc);
+  mc.ugamma = upd(d_ugamma, ugamma, (size_t)niter * nc);
+  mc.r1 = upi(d_r1, r1, (size_t)nc * niter);
+  mc.r2 = upi(d_r2, r2, (size_t)nc * niter);
+  d_trace.ensure((size_t)nc * mc.nfree * niter);
+  mc.allparams = d_trace.p;
+  CUDA_OK(cudaMemsetAsync(mc.iter, 0, sizeof(int), G.stream));
+  if (G.mc_graph) { cudaGraphExecDestroy(G.mc_graph); G.mc_graph = nullptr; }
+  ensure_params_buffers(G.mc_hi - G.mc_lo);
+  // One generation is a fixed sequence of launches whose only varying input, the iteration
+  // number, lives on the device: capture it once and replay it (launch-latency bound at MC3's
+  // usual 10-chain populations).  Per-kernel timing and multi-rank runs use plain launches unless
+  // BART_MCMC_GRAPH=1.
+  const char *genv = getenv("BART_MCMC_GRAPH");
+  bool use_graph = genv ? atoi(genv) != 0 : (G.world == 1);
+  if (G.profile || niter < 3) use_graph = false;
+  int done = 0;
+  if (use_graph) {
+    mcmc_generation_queued(0); done = 1;          // warms every lazily configured launch
+    const long long before = G.launches;
+    cudaGraph_t graph = nullptr;
+    CUDA_OK(cudaStreamBeginCapture(G.stream, cudaStreamCaptureModeThreadLocal));
+    bool ok = true;
+    try { mcmc_generation_queued(0); } catch (BartError &) { ok = false; }
+    cudaError_t e = cudaStreamEndCapture(G.stream, &graph);
+    const long long per_gen = G.launches - before;
+    if (ok && e == cudaSuccess && graph &&
+        cudaGraphInstantiate(&G.mc_graph, graph, 0) == cudaSuccess) {
+      for (; done < niter; done++) CUDA_OK(cudaGraphLaunch(G.mc_graph, G.stream));
+      G.launches += per_gen * (niter - 2);
+    } else {
+      cudaGetLastError();
+      G.launches = before;
+      if (!ok) { g_error_pending = false; g_error_msg[0] = 0; }
+    }
+    if (graph) cudaGraphDestroy(graph);
+  }
+  for (; done < niter; done++) mcmc_generation_queued(0);
+  finish_stream();
+  return 0;
+  API_END_INT
+}
+
+// results of the DE-MC loop: "allparams" [nchains][nfree][niter of the last run] (MC3's trace
+// layout), "params" [nchains][npars], "currchisq", "numaccept" [nchains], "outbounds"
+// [nchains][nfree], "bestp" [npars], "bestchisq" [1], "bestmodel" [ndata], "models" (band fluxes of
+// the last generation, [nchains][ndata]).  Returns the number of doubles written, or < 0.
+long long bart_mcmc_get(const char *name, double *out, long long capacity) {
+  API_BEGIN
+  if (!G.mc_ready) fail("bart_mcmc_init has not been called");
+  const McmcDev &mc = G.mc;
+  std::string n(name);
+  const double *src = nullptr;
+  long long cnt = 0;
+  if (n == "allparams") { src = mc.allparams; cnt = (long long)mc.nchains * mc.nfree * mc.chainsize; }
+  else if (n == "params") { src = mc.params; cnt = (long long)mc.nchains * mc.npars; }
+  else if (n == "currchisq") { src = mc.currchisq; cnt = mc.nchains; }
+  else if (n == "numaccept") { src = mc.numaccept; cnt = mc.nchains; }
+  else if (n == "bestp") { src = mc.bestp; cnt = mc.npars; }
+  else if (n == "bestchisq") { src = mc.bestchisq; cnt = 1; }
+  else if (n == "bestmodel") { src = mc.bestmodel; cnt = mc.ndata; }
+  else if (n == "outbounds") {
+    cnt = (long long)mc.nchains * mc.nfree;
+    if (cnt > capacity) fail("bart_mcmc_get(%s): capacity %lld < %lld", name, capacity, cnt);
+    std::vector<int> tmp(cnt);
+    CUDA_OK(cudaMemcpy(tmp.data(), mc.outbounds, cnt * 4, cudaMemcpyDeviceToHost));
+    for (long long i = 0; i < cnt; i++) out[i] = tmp[i];
+    return cnt;
+  } else if (n == "models") {
+    cnt = (long long)mc.nchains * mc.ndata;
+    if (cnt > capacity) fail("bart_mcmc_get(%s): capacity %lld < %lld", name, capacity, cnt);
+    const double *base = G.world > 1 ? G.d_mcgather.p : G.d_mcband.p;
+    for (int r = 0; r < G.world; r++) {
+      int lo, hi;
+      chain_block(mc.nchains, G.world, r, &lo, &hi);
+      if (hi > lo)
+        CUDA_OK(cudaMemcpy(out + (size_t)lo * mc.ndata, base + (size_t)r * G.mc_pad * mc.ndata,
+                           (size_t)(hi - lo) * mc.ndata * 8, cudaMemcpyDeviceToHost));
+    }
+    return cnt;
+  } else fail("bart_mcmc_get: unknown name '%s'", name);
+  if (!src) return 0;
+  if (cnt > capacity) fail("bart_mcmc_get(%s): capacity %lld < %lld", name, capacity, cnt);
+  CUDA_OK(cudaMemcpy(out, src, cnt * 8, cudaMemcpyDeviceToHost));
+  return cnt;
   API_END_INT
 }
 

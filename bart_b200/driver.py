@@ -12,8 +12,10 @@
   The communicator is pluggable: `TorchComm` (torch.distributed, gloo on CPU in the tests, nccl
   on GPUs) or `LibComm` (the library's own NCCL communicator on device buffers).
 
-The temperature-profile generator (code/PT.py) stays on the caller's side (SURVEY.md section
-8f, "next"): pass any callable `pt_func(pressure_bar, pt_params) -> T[layers]`.
+`BandModel` takes any callable `pt_func(pressure_bar, pt_params) -> T[layers]` (Madhusudhan and
+Piette profiles smooth over layers and stay on the caller's side); for the pointwise PT models
+(line, iso, adiabatic) the whole converter runs on the device: `Transit.converter_init` +
+`Transit.bandflux_from_params`, and `run_demc` below keeps MC3's DE-MC generation loop there too.
 """
 import numpy as np
 
@@ -156,3 +158,53 @@ def evaluate_generation(evaluate, params_all, comm):
     counts = [partition(nchains, comm.world, r)[1] - partition(nchains, comm.world, r)[0]
               for r in range(comm.world)]
     return comm.allgather(local, counts)
+
+
+# ---------------------------------------------------------------------------------------------
+# MC3's DE-MC sampler around the device-resident generation loop (include/bart_b200.h part 3)
+def demc_draws(rng, nchains, chainsize, step_free):
+    """The random streams of one run, drawn in MC3's order and shapes
+    (modules/MCcubed/MCcubed/mc/mcmc.py:484-507) so that a seeded `rng` (numpy's legacy
+    RandomState interface, `numpy.random` itself included) reproduces MC3's chains."""
+    nfree = len(step_free)
+    support = rng.normal(0, step_free, (chainsize, nchains, nfree))
+    r1 = rng.randint(0, nchains - 1, (nchains, chainsize))
+    for c in range(nchains):
+        r1[c][np.where(r1[c] == c)] = nchains - 1
+    r2 = np.zeros((nchains, chainsize), int)
+    for c in range(nchains):
+        r2[c] = (c + rng.randint(1, nchains - 1, chainsize)) % nchains
+        r2[c][np.where(r2[c] == r1[c])] = (c - 1) % nchains
+    unif = rng.uniform(0, 1, (chainsize, nchains))
+    ugamma = rng.uniform(0, 1, (chainsize, nchains))
+    return dict(support=support, r1=r1, r2=r2, unif=unif, ugamma=ugamma)
+
+
+def run_demc(transit, data, uncert, params, pmin, pmax, stepsize, numit, nchains, prior=None,
+             priorlow=None, burnin=0, fgamma=1.0, fepsilon=0.0, rng=np.random, draws=None):
+    """`MCcubed.mc.mcmc(..., walk='demc', leastsq=False)` with the whole generation loop on the
+    GPU: the host only draws the random streams (once, up front, exactly like mcmc.py does) and
+    reads the trace back at the end.  `transit` must have its converter and filters set
+    (Transit.converter_init / set_filters).  Returns MC3's arrays: allparams
+    [nchains][nfree][chainsize], the stacked posterior after burn-in, bestp, numaccept, ..."""
+    params = np.atleast_2d(np.array(params, dtype=float))
+    pmin, pmax, stepsize = (np.asarray(a, dtype=float) for a in (pmin, pmax, stepsize))
+    ifree = np.where(stepsize > 0)[0]
+    chainsize = int(np.ceil(numit / nchains))
+    if params.shape[0] != nchains:                                   # mcmc.py:296-306
+        params = np.repeat(params, nchains, 0)
+        for p in ifree:
+            params[1:, p] = rng.normal(params[0, p], stepsize[p], nchains - 1)
+            params[np.where(params[:, p] < pmin[p]), p] = pmin[p]
+            params[np.where(params[:, p] > pmax[p]), p] = pmax[p]
+    transit.mcmc_init(params, pmin, pmax, stepsize, data, uncert, prior=prior, priorlow=priorlow,
+                      fgamma=fgamma, fepsilon=fepsilon, burnin=burnin)
+    if draws is None:
+        draws = demc_draws(rng, nchains, chainsize, stepsize[ifree])
+    transit.mcmc_run(draws["support"], draws["r1"], draws["r2"], draws["unif"], draws["ugamma"])
+    out = {k: transit.mcmc_get(k) for k in ("allparams", "params", "currchisq", "numaccept",
+                                            "outbounds", "bestp", "bestmodel", "models")}
+    out["bestchisq"] = float(transit.mcmc_get("bestchisq")[0])
+    allp = out["allparams"]
+    out["allstack"] = np.hstack([allp[c, :, burnin:chainsize] for c in range(nchains)])  # mcmc.py:692-695
+    return out

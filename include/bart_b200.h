@@ -166,6 +166,67 @@ double bart_builder_phase_ms(const char *name);
 long long bart_line_bins(long long *iown_out, long long capacity);  /* bit-exact bin trace   */
 int  bart_voigt_profile(int idop, int ilor, float *out, long long capacity, long long *halfsize);
 
+/* ===================================================================================== */
+/* Part 3 -- the retrieval loop around the forward model, on the device (additive).
+ * In the reference these run in Python on the host, once per proposal and per chain:
+ * code/BARTfunc.py:309-399 (one MPI worker per chain) and modules/MCcubed/MCcubed/mc/mcmc.py.   */
+
+#define BART_REJ_TBOUNDS 16  /* temperature profile outside [Tmin, Tmax] (BARTfunc.py:327-330)   */
+#define BART_REJ_ABUND   32  /* sum of metal abundances > 1 (BARTfunc.py:339-344)                */
+
+/* replaces the input-converter set-up of code/BARTfunc.py:139-222.
+ * pt_type: 0 PT_iso (1 parameter), 1 PT_line (5: log kappa, log gamma1, log gamma2, alpha, beta;
+ * code/PT.py:589-697), 2 PT_adiabatic (3; PT.py:741-750).  pt_args[5] = {R_star m, T_star K,
+ * T_int K, sma m, gravity cm s-2} for PT_line (BARTfunc.py:206-211); tint_thorngren != 0 computes
+ * T_int after Thorngren et al. 2019 (PT.py:671-676).  pressure_bar[nlayer] and
+ * abundances[nlayer][nspecies] as read from the atmosphere file (bottom -> top).  imol: species
+ * indices of the fitted molecules; imetals: every species but H2, He, H-, e-.  Parameter vector
+ * layout (BARTfunc.py:176-181): [PT (npt) | radius (nrad) | cloud top (ncloud) | scattering
+ * (nray: 0 none; 1 Lecavelier log-extinction; 2 polar, whose slot is unused as in BARTfunc) |
+ * log10 abundance factors (nmolfit)].                                                           */
+int  bart_converter_init(int pt_type, int npt, const double *pt_args, int tint_thorngren,
+                         const double *pressure_bar, const double *abundances, int nmolfit,
+                         const int *imol, int nmetals, const int *imetals, int iH2, int iHe,
+                         double tmin, double tmax, int nrad, int ncloud, int nray);
+int  bart_converter_npars(void);
+
+/* replaces code/BARTfunc.py:320-360 for a batch: params[nmodels][npars] -> profiles in
+ * run_transit's layout (host buffers; parity/debug use).  status: 0, BART_REJ_TBOUNDS or
+ * BART_REJ_ABUND.  knobs_out (may be NULL) [3][nmodels]: radius, cloud top, scattering.          */
+int  bart_profiles_from_params(const double *params, int nmodels, int npars, double *profiles,
+                               int n_in, int *status, double *knobs_out);
+
+/* replaces one BARTfunc.py worker iteration (309-399) for a batch of proposals:
+ * parameters -> band fluxes; profiles and spectra never leave the device.  Rejected proposals
+ * get -1 in every band.                                                                         */
+int  bart_bandflux_from_params(const double *params, int nmodels, int npars, double *bandflux,
+                               int *status);
+int  bart_bandflux_from_params_device(const double *d_params, int nmodels, int npars,
+                                      double *d_bandflux, int *d_status);
+
+/* contiguous block of chains owned by `rank` (sizes differ by at most one)                      */
+void bart_chain_block(int nchains, int world, int rank, int *lo, int *hi);
+
+/* replaces MCcubed.mc.mcmc for walk='demc' (mcmc.py:196-345 set-up and initial chi-squared,
+ * 518-625 generation loop; chi-squared and priors of src_c/chisq.c:111-142,
+ * src_c/include/stats.h:72-103; MC3 passes priorlow for both prior widths).  params[nchains][npars]
+ * are the chains' starting points; stepsize > 0 free, 0 fixed, < 0 shared with parameter
+ * -stepsize (1-based).  ndata must equal the number of filters.  With a communicator
+ * (bart_comm_init) every rank evaluates its block of chains and one all-gather per generation
+ * shares the band fluxes; the proposal and Metropolis steps run redundantly on every rank.       */
+int  bart_mcmc_init(int nchains, int npars, const double *params, const double *pmin,
+                    const double *pmax, const double *stepsize, const double *prior,
+                    const double *priorlow, int ndata, const double *data, const double *uncert,
+                    double fgamma, double fepsilon, int burnin);
+/* niter generations without a host round trip.  The random streams are the caller's, in MC3's
+ * shapes with chainsize = niter (mcmc.py:484-507): support[niter][nchains][nfree],
+ * r1/r2[nchains][niter], unif/ugamma[niter][nchains].                                            */
+int  bart_mcmc_run(int niter, const double *support, const int *r1, const int *r2,
+                   const double *unif, const double *ugamma);
+/* "allparams" [nchains][nfree][niter], "params", "currchisq", "numaccept", "outbounds", "bestp",
+ * "bestchisq", "bestmodel", "models"; returns the number of doubles written or < 0.             */
+long long bart_mcmc_get(const char *name, double *out, long long capacity);
+
 #ifdef __cplusplus
 }
 #endif

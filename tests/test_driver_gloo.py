@@ -95,3 +95,21 @@ def test_bandmodel_input_converter():
     flux = bm.evaluate(params)
     assert flux.shape == (3, 3) and (flux[1:] == -1).all() and (flux[0] == 1500.0).all()
     assert tr.calls == [("batch", (1, (len(species) + 1) * nl))]
+
+
+def test_library_chain_block_matches_partition(built):
+    """The device DE-MC loop's chain -> rank map (bart_chain_block, pure host arithmetic) is the
+    driver's `partition`; blocks tile [0, nchains) for every world size."""
+    import ctypes as C
+    from bart_b200 import api
+    L = api.lib()
+    for nchains in (3, 10, 17, 4096):
+        for world in (1, 2, 3, 4, 8):
+            nxt = 0
+            for rank in range(world):
+                lo, hi = C.c_int(), C.c_int()
+                L.bart_chain_block(nchains, world, rank, C.byref(lo), C.byref(hi))
+                assert (lo.value, hi.value) == driver.partition(nchains, world, rank)
+                assert lo.value == nxt
+                nxt = hi.value
+            assert nxt == nchains

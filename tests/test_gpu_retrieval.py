@@ -1,0 +1,163 @@
+"""GPU: the retrieval loop on the device (include/bart_b200.h part 3) through the C ABI, against
+the retrieval oracle and the golden vectors made by the reference's own Python code."""
+import os
+import numpy as np
+import pytest
+import cases
+from util import relerr
+
+pytestmark = pytest.mark.gpu
+G = cases.GOLDEN_DIR
+
+
+@pytest.fixture(scope="module")
+def api():
+    from bart_b200 import api as a
+    a.lib()
+    return a
+
+
+def setup(api, name, workdir):
+    case, spec, extra = cases.build_retrieval(name, workdir)
+    tr = api.Transit(case["cfg"])
+    wn = tr.get_waveno_arr()
+    start, count, weight, star = api.filters_from_files(wn, case["filters"], extra["starwn"], extra["starfl"])
+    tr.set_filters(start, count, weight, star, extra["rprs"])
+    tr.converter_init(case["press_bar"], case["species"], case["abund"], spec["molfit"], spec["pt"],
+                      pt_args=extra["pt_args"], nrad=spec["nrad"], ncloud=spec["ncloud"],
+                      nray=spec["nray"])
+    return case, spec, extra, tr
+
+
+def band_oracle(case, spec, extra):
+    from oracle import retrieval_oracle as ro
+    conv = ro.Converter(case["press_bar"], case["species"], case["abund"], spec["molfit"], spec["pt"],
+                        pt_args=extra["pt_args"], nrad=spec["nrad"], ncloud=spec["ncloud"],
+                        nray=spec["nray"])
+    return ro.BandOracle(case["cfg"], conv, case["filters"], extra["starwn"], extra["starfl"],
+                         extra["rprs"])
+
+
+@pytest.mark.parametrize("name", list(cases.RETRIEVAL))
+def test_converter_vs_reference_golden(name, api, workdir):
+    """K-1 against the profiles the reference's BARTfunc statements + PT.py produce."""
+    case, spec, extra, tr = setup(api, name, workdir)
+    d = np.load(os.path.join(G, "retrieval_conv_%s.npz" % name))
+    prof, status, knobs = tr.profiles_from_params(d["params"])
+    assert np.array_equal(status, d["status"])
+    ok = status == 0
+    assert ok.sum() >= 10 and (status == 16).any() and (status == 32).any()
+    assert np.max(np.abs(prof[ok] - d["profiles"][ok]) / np.abs(d["profiles"][ok])) < 1e-12
+    c = 5
+    for k, on in enumerate((spec["nrad"], spec["ncloud"], spec["nray"])):
+        if on:
+            assert np.array_equal(knobs[k], d["params"][:, c]); c += 1
+    tr.free_memory()
+
+
+def test_pt_line_thorngren_and_adiabatic(api, workdir):
+    case, spec, extra, tr = setup(api, "retr_tiny_eclipse", workdir)
+    d = np.load(os.path.join(G, "retrieval_pt.npz"))
+    assert np.array_equal(d["pressure"], case["press_bar"]) or np.allclose(d["pressure"], case["press_bar"], rtol=1e-14)
+    nl = tr.nlayer
+    for tint_type, key in (("const", "T_const"), ("thorngren", "T_thorngren")):
+        tr.converter_init(case["press_bar"], case["species"], case["abund"], (), "line",
+                          pt_args=extra["pt_args"], tint_type=tint_type, tmin=0.0, tmax=1e9, nrad=0)
+        prof, status, _ = tr.profiles_from_params(d["pars"])
+        assert (status == 0).all()
+        assert np.max(np.abs(prof[:, :nl] / d[key] - 1)) < 1e-12
+    tr.converter_init(case["press_bar"], case["species"], case["abund"], (), "adiabatic", tmin=-1e9,
+                      tmax=1e9, nrad=0)
+    prof, status, _ = tr.profiles_from_params(d["apars"])
+    assert np.max(np.abs(prof[:, :nl] / d["T_adiabatic"] - 1)) < 1e-13
+    tr.converter_init(case["press_bar"], case["species"], case["abund"], (), "iso", nrad=0)
+    prof, status, _ = tr.profiles_from_params(np.array([[1500.0], [399.0]]))
+    assert np.all(prof[0, :nl] == 1500.0) and list(status) == [0, 16]
+    tr.free_memory()
+
+
+@pytest.mark.parametrize("name", list(cases.RETRIEVAL))
+def test_bandflux_from_params_vs_oracle(name, api, workdir):
+    """parameters -> band fluxes in one call (one BARTfunc worker iteration) against the oracle
+    chain converter -> forward model -> band integration; rejected proposals are -1."""
+    case, spec, extra, tr = setup(api, name, workdir)
+    d = np.load(os.path.join(G, "retrieval_conv_%s.npz" % name))
+    params = d["params"]
+    bf, status = tr.bandflux_from_params(params)
+    ref = band_oracle(case, spec, extra)(params)
+    rej = d["status"] != 0
+    assert np.all(bf[rej] == -1.0) and np.all(ref[rej] == -1.0)
+    assert np.array_equal(status[rej], d["status"][rej])
+    ok = ~rej & (status == 0)
+    assert ok.sum() >= 8
+    assert relerr(bf[ok], ref[ok]) < 1e-6
+    # the same through the host-converter path (profiles -> band fluxes)
+    prof, st2, knobs = tr.profiles_from_params(params[ok])
+    kw = {}
+    if spec["nrad"]: kw["refradius"] = knobs[0]
+    if spec["ncloud"]: kw["cloudtop"] = knobs[1]
+    if spec["nray"]: kw["scat_flag"] = np.ones(ok.sum(), dtype=np.int32); kw["scat_logext"] = knobs[2]
+    if kw:
+        tr.set_batch_knobs(int(ok.sum()), **kw)
+    bf2, _ = tr.bandflux_batch(prof)
+    tr.set_batch_knobs(0)
+    assert np.array_equal(bf2, bf[ok])
+    tr.free_memory()
+
+
+@pytest.mark.parametrize("graph", ["1", "0"])
+@pytest.mark.parametrize("name", list(cases.RETRIEVAL))
+def test_demc_on_device_reproduces_reference_mc3(name, graph, api, workdir, monkeypatch):
+    """The seeded run of the reference's MCcubed.mc.mcmc (golden) chain for chain: same random
+    streams, the generation loop on the GPU (CUDA-graph replay and plain launches)."""
+    from bart_b200 import driver
+    monkeypatch.setenv("BART_MCMC_GRAPH", graph)
+    case, spec, extra, tr = setup(api, name, workdir)
+    d = np.load(os.path.join(G, "retrieval_mc3_%s.npz" % name))
+    np.random.seed(spec["seed"])
+    n0 = api.lib().bart_launch_count()
+    out = driver.run_demc(tr, d["data"], d["uncert"], spec["params"], spec["pmin"], spec["pmax"],
+                          spec["stepsize"], spec["numit"], spec["nchains"], burnin=spec["burnin"])
+    assert np.array_equal(out["allparams"], d["allparams"])          # every chain, every iteration
+    assert np.array_equal(out["allstack"], d["allstack"])
+    assert np.array_equal(out["bestp"], d["bestp"])
+    chainsize = d["allparams"].shape[2]
+    per_gen = 5 if tr.eclipse else 7
+    assert api.lib().bart_launch_count() - n0 >= per_gen * chainsize
+    # the oracle loop on the same streams: acceptance counts, chi-squared, best model
+    from oracle import retrieval_oracle as ro
+    np.random.seed(spec["seed"])
+    ref = ro.demc(band_oracle(case, spec, extra), d["data"], d["uncert"], spec["params"], spec["pmin"],
+                  spec["pmax"], spec["stepsize"], spec["numit"], spec["nchains"], burnin=spec["burnin"])
+    assert np.array_equal(out["numaccept"], ref["numaccept"])
+    assert np.array_equal(out["outbounds"], ref["outbounds"])
+    assert np.array_equal(out["params"], ref["params"])
+    assert relerr(out["currchisq"], ref["currchisq"]) < 1e-6
+    assert abs(out["bestchisq"] / ref["bestchisq"] - 1) < 1e-6
+    assert relerr(out["bestmodel"], ref["bestmodel"]) < 1e-6
+    assert relerr(out["models"], ref["allmodels"][-1]) < 1e-6
+    tr.free_memory()
+
+
+def test_demc_continues_across_calls(api, workdir):
+    """Two bart_mcmc_run calls of n/2 generations == one call of n (state stays on the device)."""
+    from bart_b200 import driver
+    name = "retr_tiny_eclipse"
+    case, spec, extra, tr = setup(api, name, workdir)
+    d = np.load(os.path.join(G, "retrieval_mc3_%s.npz" % name))
+    nch = spec["nchains"]
+    stepsize = np.array(spec["stepsize"])
+    rng = np.random.RandomState(5)
+    p0 = np.repeat(np.atleast_2d(spec["params"]), nch, 0)
+    p0[:, stepsize > 0] += rng.normal(0, 0.01, (nch, int((stepsize > 0).sum())))
+    dr = driver.demc_draws(rng, nch, 16, stepsize[stepsize > 0])
+    one = driver.run_demc(tr, d["data"], d["uncert"], p0, spec["pmin"], spec["pmax"], stepsize,
+                          16 * nch, nch, draws=dr)
+    tr.mcmc_init(p0, spec["pmin"], spec["pmax"], stepsize, d["data"], d["uncert"])
+    halves = []
+    for h in (slice(0, 8), slice(8, 16)):
+        tr.mcmc_run(dr["support"][h], dr["r1"][:, h], dr["r2"][:, h], dr["unif"][h], dr["ugamma"][h])
+        halves.append(tr.mcmc_get("allparams"))
+    assert np.array_equal(np.concatenate(halves, axis=2), one["allparams"])
+    assert np.array_equal(tr.mcmc_get("params"), one["params"])
+    tr.free_memory()
