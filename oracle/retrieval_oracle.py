@@ -306,6 +306,185 @@ def demc(func, data, uncert, params, pmin, pmax, stepsize, numit, nchains, prior
                 draws=dict(support=support, r1=r1, r2=r2, unif=unif, ugamma=ugamma))
 
 
+def snooker_draws(rng, nchains, nfree, chainsize, hsize, thinning, stepsize_free, pmin_free,
+                  pmax_free):
+    """The random numbers walk='snooker' consumes, drawn from `rng` in MC3's order: the M0
+    initial Z samples (mcmc.py:421-424), support/unif/ugamma (mcmc.py:490-497), then inside
+    the loop, per generation, i1, i2 (+ collision redraws), iz, ic (mcmc.py:529-539) and the
+    uniform(1.2, 2.2) factors of that generation's snooker chains (mcmc.py:545-556: the two
+    calls together take [number of chains with ugamma < 0.1][nfree] values whatever the split
+    between projected and unprojected jumps is).  None of it depends on the chain states."""
+    z0 = np.zeros((hsize, nchains, nfree))
+    for f in range(nfree):
+        z0[:, :, f] = rng.uniform(pmin_free[f], pmax_free[f], (hsize, nchains))
+    support = rng.normal(0, stepsize_free, (chainsize, nchains, nfree))
+    unif = rng.uniform(0, 1, (chainsize, nchains))
+    ugamma = rng.uniform(0, 1, (chainsize, nchains))
+    sjump = ugamma < 0.1
+    i1 = np.zeros((chainsize, nchains), np.int64)
+    i2 = np.zeros((chainsize, nchains), np.int64)
+    iz = np.zeros((chainsize, nchains), np.int64)
+    ic = np.zeros((chainsize, nchains), np.int64)
+    usnooker, offset = [], np.zeros(chainsize + 1, np.int64)
+    zsize = hsize
+    for i in range(chainsize):
+        a = rng.randint(0, (zsize - 1) * nchains, nchains)
+        b = rng.randint(0, (zsize - 1) * nchains, nchains)
+        for j in range(nchains):
+            while a[j] == b[j]:
+                b[j] = rng.randint(0, (zsize - 1) * nchains)
+        i1[i], i2[i] = a, b
+        iz[i] = rng.randint(0, zsize - 1, nchains)
+        ic[i] = rng.randint(0, nchains, nchains)
+        n = int(sjump[i].sum())
+        if n:
+            usnooker.append(rng.uniform(1.2, 2.2, (n, nfree)))
+        offset[i + 1] = offset[i] + n
+        if i % thinning == 0:
+            zsize += 1
+    usn = np.concatenate(usnooker) if usnooker else np.zeros((0, nfree))
+    return dict(z0=z0, support=support, unif=unif, ugamma=ugamma, i1=i1, i2=i2, iz=iz, ic=ic,
+                usnooker=usn, usn_offset=offset)
+
+
+def snooker(func, data, uncert, params, pmin, pmax, stepsize, numit, nchains, prior=None,
+            priorlow=None, priorup=None, burnin=0, thinning=1, fgamma=1.0, fepsilon=0.0, hsize=1,
+            rng=np.random, draws=None):
+    """walk='snooker' of mcmc.py (ter Braak & Vrugt 2008 as MC3 implements it), MPI-mode
+    semantics (every proposal is evaluated, mcmc.py:582-585), `params` [nchains][npars] given
+    per chain.  Random numbers come from `rng` in MC3's order (see snooker_draws) unless
+    `draws` supplies them.  Quirks kept: Z rows carry the chains' INITIAL non-free columns
+    (mcmc.py:419,425); the Metropolis factor of projected jumps is one Frobenius-norm ratio
+    over all such chains of the generation (mcmc.py:606-609)."""
+    data, uncert = np.asarray(data, float), np.asarray(uncert, float)
+    params = np.atleast_2d(np.array(params, dtype=float))
+    nparams, ndata = params.shape[1], len(data)
+    pmin, pmax, stepsize = (np.asarray(a, float) for a in (pmin, pmax, stepsize))
+    if prior is None or priorlow is None or priorup is None:
+        prior = priorup = priorlow = np.zeros(nparams)
+    prior, priorlow, priorup = (np.asarray(a, float) for a in (prior, priorlow, priorup))
+    iprior = np.where(priorlow != 0)[0]
+    nfree = int(np.sum(stepsize > 0))
+    chainsize = int(np.ceil(numit / nchains))
+    ifree = np.where(stepsize > 0)[0]
+    ishare = np.where(stepsize < 0)[0]
+    if hsize < nchains:                                              # mcmc.py:233-235
+        hsize = nchains + 1
+    gamma = fgamma * 2.4 / np.sqrt(2 * nfree)
+    if params.shape[0] != nchains:                                   # mcmc.py:296-306
+        params = np.repeat(params, nchains, 0)
+        for p in ifree:
+            params[1:, p] = rng.normal(params[0, p], stepsize[p], nchains - 1)
+            params[np.where(params[:, p] < pmin[p]), p] = pmin[p]
+            params[np.where(params[:, p] > pmax[p]), p] = pmax[p]
+    for s in ishare:
+        params[:, s] = params[:, -int(stepsize[s]) - 1]
+    params0 = params.copy()
+    models = np.array(func(params), dtype=float).reshape(nchains, ndata)
+    currchisq, c2 = np.zeros(nchains), np.zeros(nchains)
+
+    def chi(model, p):
+        return chisq(model, data, uncert, (p - prior)[iprior], priorlow[iprior], priorlow[iprior])
+
+    for c in range(nchains):
+        currchisq[c], c2[c] = chi(models[c], params[c])
+    # --- Z set-up, mcmc.py:357-460
+    nZchain = int(np.ceil(numit / nchains / thinning))
+    Zsize = hsize
+    Z = np.zeros((hsize + nZchain, nchains, nparams))
+    Zchisq = np.zeros((hsize + nZchain, nchains))
+    Z[:, :, :] = params
+    if draws is None:
+        draws = snooker_draws(rng, nchains, nfree, chainsize, hsize, thinning, stepsize[ifree],
+                              pmin[ifree], pmax[ifree])
+    for f in range(nfree):
+        Z[:hsize, :, ifree[f]] = draws["z0"][:, :, f]
+    Z[:, :, stepsize == 0] = params[0, stepsize == 0]
+    Zmodels0 = np.zeros((hsize, nchains, ndata))
+    for i in range(hsize):
+        Zmodels0[i] = np.array(func(Z[i]), dtype=float).reshape(nchains, ndata)
+        for c in range(nchains):
+            Zchisq[i, c], _ = chi(Zmodels0[i, c], Z[i, c])
+    Zibest = np.unravel_index(np.argmin(Zchisq[:hsize]), Zchisq[:hsize].shape)
+    bestchisq = np.amin(c2)
+    bestp = params[np.argmin(c2)].copy()
+    bestmodel = models[np.argmin(c2)].copy()
+    if Zchisq[Zibest] < bestchisq:
+        bestchisq, bestp, bestmodel = Zchisq[Zibest], Z[Zibest].copy(), Zmodels0[Zibest].copy()
+    support, unif, ugamma = draws["support"], draws["unif"], draws["ugamma"]
+    sjump = ugamma < 0.1
+    nextp = params.copy()
+    nextchisq = np.zeros(nchains)
+    numaccept = np.zeros(nchains)
+    outbounds = np.zeros((nchains, nfree), int)
+    allparams = np.zeros((nchains, nfree, chainsize))
+    allmodels = np.zeros((chainsize, nchains, ndata))
+    mrfactor = np.zeros(nchains)
+    mrtrace = np.ones((chainsize, nchains))
+    for i in range(chainsize):
+        i1, i2 = draws["i1"][i], draws["i2"][i]
+        iz1, ic1 = np.unravel_index(i1, (Zsize, nchains))
+        iz2, ic2 = np.unravel_index(i2, (Zsize, nchains))
+        z = Z[draws["iz"][i], draws["ic"][i]]
+        jump = np.zeros((nchains, nfree))
+        noproj = np.all(z == params, axis=1)
+        usn = draws["usnooker"][draws["usn_offset"][i]:draws["usn_offset"][i + 1]]
+        n_np = int(np.sum(noproj * sjump[i]))
+        if n_np != 0:                                                # mcmc.py:544-547
+            jump[noproj * sjump[i]] = usn[:n_np] * (Z[iz2, ic2] - Z[iz1, ic1])[noproj * sjump[i]][:, ifree]
+        if np.sum(~noproj * sjump[i]) != 0:                          # mcmc.py:549-557
+            dz = (params - z)[:, ifree][~noproj * sjump[i]]
+            zp1 = np.sum(Z[iz1, ic1][:, ifree][~noproj * sjump[i]] * dz, axis=1)
+            zp2 = np.sum(Z[iz2, ic2][:, ifree][~noproj * sjump[i]] * dz, axis=1)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                jump[~noproj * sjump[i]] = usn[n_np:] * \
+                    (zp1 - zp2).reshape(zp1.shape[0], 1) / \
+                    np.sum(dz ** 2, axis=1).reshape(zp1.shape[0], 1) * \
+                    dz
+        jump[~sjump[i]] = gamma * (Z[iz1, ic1] - Z[iz2, ic2])[~sjump[i]][:, ifree] \
+            + fepsilon * support[i][~sjump[i]]
+        nextp[:, ifree] = params[:, ifree] + jump
+        outpars = np.asarray(((nextp < pmin) | (nextp > pmax))[:, ifree])
+        outflag = np.any(outpars, axis=1)
+        outbounds += outpars
+        for p in ifree:
+            nextp[np.where(nextp[:, p] < pmin[p]), p] = pmin[p]
+            nextp[np.where(nextp[:, p] > pmax[p]), p] = pmax[p]
+        for s in ishare:
+            nextp[:, s] = nextp[:, -int(stepsize[s]) - 1]
+        models = np.array(func(nextp), dtype=float).reshape(nchains, ndata)
+        allmodels[i] = models
+        for c in np.where(~outflag)[0]:
+            nextchisq[c], c2[c] = chi(models[c], nextp[c])
+        nextchisq[outflag] = np.inf
+        mrfactor[:] = 1.0
+        if np.any(sjump[i] * ~noproj * ~outflag):                    # mcmc.py:603-609
+            asj = sjump[i] * ~noproj * ~outflag
+            mrfactor[asj] = (np.linalg.norm((nextp - z)[:, ifree][asj]) /
+                             np.linalg.norm((params - z)[:, ifree][asj])) ** (nfree - 1)
+        mrtrace[i] = mrfactor
+        with np.errstate(over="ignore", invalid="ignore"):
+            accept = np.exp(0.5 * (currchisq - nextchisq)) * mrfactor
+        accepted = accept >= unif[i]
+        if i >= burnin:
+            numaccept += accepted
+        params[accepted] = nextp[accepted]
+        currchisq[accepted] = nextchisq[accepted]
+        if np.amin(c2) < bestchisq:
+            bestp = params[np.argmin(c2)].copy()
+            bestmodel = models[np.argmin(c2)].copy()
+            bestchisq = np.amin(c2)
+        allparams[:, :, i] = params[:, ifree]
+        if i % thinning == 0:                                        # mcmc.py:653-660
+            Z[hsize + i // thinning][:, ifree] = params[:, ifree]
+            Zchisq[hsize + i // thinning] = currchisq
+            Zsize += 1
+    return dict(allparams=allparams, params=params, currchisq=currchisq, numaccept=numaccept,
+                outbounds=outbounds, bestp=bestp, bestchisq=bestchisq, bestmodel=bestmodel,
+                params0=params0, allmodels=allmodels, Z=Z, Zchisq=Zchisq, Zsize=Zsize, hsize=hsize,
+                mrfactor=mrtrace, draws=draws)
+
+
 class BandOracle:
     """params[M][npars] -> band fluxes[M][nfilters]: Converter + forward-model oracle
     (oracle.Oracle, transit_oracle.c) + band integration (oracle.bandflux), i.e. what one

@@ -11,12 +11,14 @@ container (neither /root/reference nor the /tmp build exist on the GPU box):
                           extensions compiled from a copy under /tmp/bart_mc3_ref with the
                           reference's own setup.py) whose model function is the forward-model
                           oracle: the chain trace, best fit, acceptance counts
+  * retrieval_snooker_*.npz  the same with walk='snooker' (BART's configured walk) in MC3's MPI
+                          mode, the worker side played by an in-process stand-in (FakeWorkers)
 
 Shims applied from the outside, none to the reference sources: `numpy.int/float` aliases (removed
 from numpy 2), stub `matplotlib` and `dwt` modules (absent / built on a removed numpy C API; neither
 is used on this path).
 
-    python tests/golden/make_golden_retrieval.py
+    python tests/golden/make_golden_retrieval.py [pt] [conv] [demc] [snooker]
 """
 import glob
 import os
@@ -175,16 +177,77 @@ def golden_mc3(mc3, name, tmp):
         name, allparams.shape, out[0].shape, np.array2string(out[1], precision=4)))
 
 
+class FakeWorkers:
+    """Stands in for the MPI intercommunicator MC3 talks to in BART (mcmc.py:277-286,317-322,
+    582-585; MCcubed/utils/mcutils.py:208-281): Scatter hands over the proposals of all chains,
+    Gather returns the workers' models.  Test-side shim so that the reference takes its MPI-mode
+    branches (every proposal evaluated, no early `continue`) without mpi4py/mpiexec."""
+
+    def __init__(self, func, nchains):
+        self.func, self.nchains, self.pending = func, nchains, None
+
+    def Barrier(self):
+        pass
+
+    def Bcast(self, buf, root=0):
+        pass
+
+    def Scatter(self, send, recv, root=0):
+        arr = np.asarray(send[0], dtype=float)
+        self.pending = arr.reshape(self.nchains, -1).copy()
+
+    def Gather(self, send, recv, root=0):
+        recv[:] = np.asarray(self.func(self.pending), dtype=float).ravel()
+
+    def Disconnect(self):
+        pass
+
+
+def golden_snooker(mc3, name, tmp):
+    case, spec, band = make_band_oracle(name, tmp)
+    data, uncert = retrieval_data(spec, band)
+    mpi4py = types.ModuleType("mpi4py")
+    mpi4py.MPI = types.SimpleNamespace(DOUBLE="d", INT="i", ROOT=-3)
+    sys.modules["mpi4py"] = mpi4py
+    sys.modules["mpi4py.MPI"] = mpi4py.MPI
+    import MCcubed.utils.mcutils as mcu
+    mcu.MPI = mpi4py.MPI
+    for thinning in (1, 3):
+        sav = os.path.join(tmp, "%s_snk%d_trace.npy" % (name, thinning))
+        log = open(os.path.join(tmp, "%s_snk%d.log" % (name, thinning)), "w")
+        np.random.seed(spec["seed"] + thinning)
+        comm = FakeWorkers(band, spec["nchains"])
+        out = mc3.mc.mcmc(data, uncert, band, [], params=np.array(spec["params"]),
+                          pmin=np.array(spec["pmin"]), pmax=np.array(spec["pmax"]),
+                          stepsize=np.array(spec["stepsize"], dtype=float), numit=spec["numit"],
+                          nchains=spec["nchains"], walk="snooker", leastsq=False, grtest=False,
+                          burnin=spec["burnin"], thinning=thinning, plots=False, savefile=sav,
+                          log=log, comm=comm)
+        allparams = np.load(sav)
+        np.savez_compressed(os.path.join(HERE, "retrieval_snooker_%s_thin%d.npz" % (name, thinning)),
+                            data=data, uncert=uncert, allparams=allparams, allstack=out[0],
+                            bestp=out[1], thinning=thinning)
+        print("retrieval_snooker_%s_thin%d.npz: trace %s, best %s" % (
+            name, thinning, allparams.shape, np.array2string(out[1], precision=4)))
+
+
 def main():
+    only = set(sys.argv[1:])                     # e.g. `make_golden_retrieval.py snooker`
+    want = lambda k: not only or k in only
     shim()
     sys.path.insert(0, os.path.join(REF, "code"))
     import PT as pt
     mc3 = build_mc3()
-    golden_pt(pt)
+    if want("pt"):
+        golden_pt(pt)
     with tempfile.TemporaryDirectory() as tmp:
         for name in cases.RETRIEVAL:
-            golden_converter(pt, name, tmp)
-            golden_mc3(mc3, name, tmp)
+            if want("conv"):
+                golden_converter(pt, name, tmp)
+            if want("demc"):
+                golden_mc3(mc3, name, tmp)
+            if want("snooker"):
+                golden_snooker(mc3, name, tmp)
 
 
 if __name__ == "__main__":

@@ -63,3 +63,29 @@ def test_demc_oracle_reproduces_reference_mc3(name, built, workdir):
     assert np.array_equal(out["bestp"], d["bestp"])
     nacc = out["numaccept"].sum()
     assert 0 < nacc < spec["numit"]
+
+
+@pytest.mark.parametrize("thinning", [1, 3])
+@pytest.mark.parametrize("name", list(cases.RETRIEVAL))
+def test_snooker_oracle_reproduces_reference_mc3(name, thinning, built, workdir):
+    """walk='snooker' (the walk every BART example configures), MC3's MPI mode: same seed, same
+    model function -> the reference's chain trace bit for bit."""
+    case, spec, extra = cases.build_retrieval(name, workdir)
+    d = np.load(os.path.join(G, "retrieval_snooker_%s_thin%d.npz" % (name, thinning)))
+    conv = ro.Converter(case["press_bar"], case["species"], case["abund"], spec["molfit"], spec["pt"],
+                        pt_args=extra["pt_args"], nrad=spec["nrad"], ncloud=spec["ncloud"],
+                        nray=spec["nray"])
+    band = ro.BandOracle(case["cfg"], conv, case["filters"], extra["starwn"], extra["starfl"],
+                         extra["rprs"])
+    np.random.seed(spec["seed"] + thinning)
+    out = ro.snooker(band, d["data"], d["uncert"], spec["params"], spec["pmin"], spec["pmax"],
+                     spec["stepsize"], spec["numit"], spec["nchains"], burnin=spec["burnin"],
+                     thinning=thinning)
+    assert np.array_equal(out["allparams"], d["allparams"])
+    assert np.array_equal(out["bestp"], d["bestp"])
+    assert out["hsize"] == spec["nchains"] + 1
+    assert out["Zsize"] == out["hsize"] + len(range(0, out["allparams"].shape[2], thinning))
+    # the walk exercised projected snooker jumps and their Metropolis factor
+    assert np.any(out["mrfactor"] != 1.0)
+    nacc = out["numaccept"].sum()
+    assert 0 < nacc < spec["numit"]
