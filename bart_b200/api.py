@@ -91,6 +91,8 @@ def lib():
     L.bart_mcmc_init.argtypes = [C.c_int, C.c_int, dp, dp, dp, dp, dp, dp, C.c_int, dp, dp,
                                  C.c_double, C.c_double, C.c_int]
     L.bart_mcmc_run.argtypes = [C.c_int, dp, ip, ip, dp, dp]
+    L.bart_mcmc_snooker_init.argtypes = [C.c_int, C.c_int, dp]
+    L.bart_mcmc_run_snooker.argtypes = [C.c_int, dp, ip, ip, ip, ip, dp, ip, dp, dp]
     L.bart_mcmc_get.restype = C.c_longlong
     L.bart_mcmc_get.argtypes = [C.c_char_p, dp, C.c_longlong]
     L.bart_set_error_mode(1)
@@ -328,8 +330,40 @@ class Transit:
                                    _d(unif), _d(ugamma)))
         self._mc_niter = niter
 
+    def mcmc_snooker_init(self, z0, thinning=1):
+        """z0[hsize][nchains][nfree]: MC3's M0 initial history samples (mcmc.py:421-424)."""
+        nchains, npars, nfree, ndata = self._mc_shape
+        z0 = np.ascontiguousarray(z0, dtype=np.float64)
+        if z0.ndim != 3 or z0.shape[1:] != (nchains, nfree):
+            raise BartError("z0 must be [hsize][%d][%d]" % (nchains, nfree))
+        _check(lib().bart_mcmc_snooker_init(z0.shape[0], int(thinning), _d(z0)))
+        self._mc_zsize, self._mc_thinning = z0.shape[0], int(thinning)
+
+    def mcmc_run_snooker(self, support, i1, i2, iz, ic, usnooker, usn_offset, unif, ugamma):
+        nchains, npars, nfree, ndata = self._mc_shape
+        support, unif, ugamma, usnooker = (np.ascontiguousarray(a, dtype=np.float64)
+                                           for a in (support, unif, ugamma, usnooker))
+        i1, i2, iz, ic, usn_offset = (np.ascontiguousarray(a, dtype=np.int32)
+                                      for a in (i1, i2, iz, ic, usn_offset))
+        niter = unif.shape[0]
+        if support.shape != (niter, nchains, nfree) or ugamma.shape != (niter, nchains) or \
+                any(a.shape != (niter, nchains) for a in (i1, i2, iz, ic)) or \
+                usn_offset.shape != (niter + 1,) or usnooker.shape != (usn_offset[-1], nfree):
+            raise BartError("random streams do not have MC3's shapes for %d chains x %d iterations"
+                            % (nchains, niter))
+        _check(lib().bart_mcmc_run_snooker(
+            niter, _d(support), i1.ctypes.data_as(ip), i2.ctypes.data_as(ip), iz.ctypes.data_as(ip),
+            ic.ctypes.data_as(ip), _d(usnooker), usn_offset.ctypes.data_as(ip), _d(unif), _d(ugamma)))
+        self._mc_niter = niter
+        self._mc_zsize += len(range(0, niter, self._mc_thinning))
+
     def mcmc_get(self, name):
         nchains, npars, nfree, ndata = self._mc_shape
+        if name in ("Z", "Zchisq"):
+            out = np.zeros((self._mc_zsize, nchains, npars) if name == "Z" else (self._mc_zsize, nchains))
+            n = lib().bart_mcmc_get(name.encode(), _d(out), out.size)
+            _check(0 if n >= 0 else -1)
+            return out
         shapes = {"allparams": (nchains, nfree, getattr(self, "_mc_niter", 0)),
                   "params": (nchains, npars), "currchisq": (nchains,), "numaccept": (nchains,),
                   "outbounds": (nchains, nfree), "bestp": (npars,), "bestchisq": (1,),

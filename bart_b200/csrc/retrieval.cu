@@ -176,6 +176,108 @@ void launch_demc_propose(const McmcDev &mc, cudaStream_t s) {
 }
 
 // ---------------------------------------------------------------------------------------
+// numpy's pairwise summation (numpy/_core/src/umath/loops_utils.h.src, n <= 128), i.e. what
+// np.sum(x, axis=1) computes along a contiguous axis: the snooker projection's dot products
+// (mcmc.py:551-556) are reproduced bit for bit
+__device__ double np_pairwise_sum(const double *a, int n) {
+  if (n < 8) {
+    double r = 0.0;
+    for (int k = 0; k < n; k++) r = __dadd_rn(r, a[k]);
+    return r;
+  }
+  double r[8];
+  for (int j = 0; j < 8; j++) r[j] = a[j];
+  int k = 8;
+  for (; k < n - (n % 8); k += 8)
+    for (int j = 0; j < 8; j++) r[j] = __dadd_rn(r[j], a[k + j]);
+  double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                         __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+  for (; k < n; k++) res = __dadd_rn(res, a[k]);
+  return res;
+}
+
+// Snooker proposal (mcmc.py:527-575).  Per chain: two history samples z1 = Z[i1], z2 = Z[i2] and
+// a projection anchor z = Z[iz][ic].  With probability 0.9 (ugamma >= 0.1) a DE-MC jump
+// gamma (z1 - z2) + fepsilon support; otherwise a snooker jump u (zp1 - zp2)/|x - z|^2 (x - z)
+// along x - z (zp = projections of z1, z2), or u (z2 - z1) when z coincides with the chain's
+// state.  The uniform factors u come in the reference from two calls whose sizes depend on the
+// states (unprojected chains first): `slot` reproduces that assignment.
+__global__ void __launch_bounds__(256) snooker_propose_kernel(McmcDev mc) {
+  const int i = *mc.iter;
+  const int np = mc.npars, nc = mc.nchains;
+  const int *gi1 = mc.i1 + (size_t)i * nc, *gi2 = mc.i2 + (size_t)i * nc;
+  const int *giz = mc.iz + (size_t)i * nc, *gic = mc.ic + (size_t)i * nc;
+  const double *ug = mc.ugamma + (size_t)i * nc;
+  for (int c = threadIdx.x; c < nc; c += blockDim.x) {
+    const double *z = mc.Z + ((size_t)giz[c] * nc + gic[c]) * np;
+    const double *cur = mc.params + (size_t)c * np;
+    int same = 1;
+    for (int p = 0; p < np; p++) same &= (z[p] == cur[p]);   // np.all(z == params, axis=1)
+    mc.noproj[c] = same;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int k = mc.usn_off[i];
+    for (int c = 0; c < nc; c++) if (ug[c] < 0.1 && mc.noproj[c]) mc.slot[c] = k++;
+    for (int c = 0; c < nc; c++) if (ug[c] < 0.1 && !mc.noproj[c]) mc.slot[c] = k++;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < nc; c += blockDim.x) {
+    const double *cur = mc.params + (size_t)c * np;
+    double *nx = mc.nextp + (size_t)c * np;
+    const double *z1 = mc.Z + (size_t)gi1[c] * np;
+    const double *z2 = mc.Z + (size_t)gi2[c] * np;
+    const double *z = mc.Z + ((size_t)giz[c] * nc + gic[c]) * np;
+    const bool sj = ug[c] < 0.1;
+    const double *sup = mc.support + ((size_t)i * nc + c) * mc.nfree;
+    double jump[kMaxPars];
+    if (!sj) {
+      for (int f = 0; f < mc.nfree; f++) {
+        const int p = mc.ifree[f];
+        jump[f] = __dadd_rn(__dmul_rn(mc.gamma, __dsub_rn(z1[p], z2[p])), __dmul_rn(mc.fepsilon, sup[f]));
+      }
+    } else {
+      const double *u = mc.usn + (size_t)mc.slot[c] * mc.nfree;
+      if (mc.noproj[c]) {
+        for (int f = 0; f < mc.nfree; f++) {
+          const int p = mc.ifree[f];
+          jump[f] = __dmul_rn(u[f], __dsub_rn(z2[p], z1[p]));
+        }
+      } else {
+        double dz[kMaxPars], t[kMaxPars];
+        for (int f = 0; f < mc.nfree; f++) dz[f] = __dsub_rn(cur[mc.ifree[f]], z[mc.ifree[f]]);
+        for (int f = 0; f < mc.nfree; f++) t[f] = __dmul_rn(z1[mc.ifree[f]], dz[f]);
+        const double zp1 = np_pairwise_sum(t, mc.nfree);
+        for (int f = 0; f < mc.nfree; f++) t[f] = __dmul_rn(z2[mc.ifree[f]], dz[f]);
+        const double zp2 = np_pairwise_sum(t, mc.nfree);
+        for (int f = 0; f < mc.nfree; f++) t[f] = __dmul_rn(dz[f], dz[f]);
+        const double d2 = np_pairwise_sum(t, mc.nfree);
+        const double dzp = __dsub_rn(zp1, zp2);
+        for (int f = 0; f < mc.nfree; f++)
+          jump[f] = __dmul_rn(__ddiv_rn(__dmul_rn(u[f], dzp), d2), dz[f]);
+      }
+    }
+    int out = 0;
+    for (int f = 0; f < mc.nfree; f++) {
+      const int p = mc.ifree[f];
+      double v = __dadd_rn(cur[p], jump[f]);
+      const int o = (v < mc.pmin[p]) || (v > mc.pmax[p]);
+      out |= o;
+      mc.outbounds[(size_t)c * mc.nfree + f] += o;
+      if (v < mc.pmin[p]) v = mc.pmin[p];
+      if (v > mc.pmax[p]) v = mc.pmax[p];
+      nx[p] = v;
+    }
+    for (int s = 0; s < mc.nshare; s++) nx[mc.share_dst[s]] = nx[mc.share_src[s]];
+    mc.outflag[c] = out;
+  }
+}
+
+void launch_snooker_propose(const McmcDev &mc, cudaStream_t s) {
+  snooker_propose_kernel<<<1, 256, 0, s>>>(mc);
+}
+
+// ---------------------------------------------------------------------------------------
 __device__ const double *chain_model(const double *models, const ModelMap &mp, int c, int ndata) {
   // contiguous blocks: the first `extra` ranks own base+1 chains (driver.partition)
   const int cut = mp.extra * (mp.base + 1);
@@ -209,6 +311,37 @@ __global__ void __launch_bounds__(256)
 chisq_accept_kernel(McmcDev mc, const double *__restrict__ models, ModelMap mp, int first) {
   const int np = mc.npars;
   const int i = *mc.iter;
+  const bool snooker = mc.walk == 1 && !first;
+  const int zrow = snooker ? *mc.zsize : 0;
+  // Metropolis factor of the projected snooker jumps (mcmc.py:603-609): ONE ratio of Frobenius
+  // norms over all such chains of this generation, to the power nfree-1 (the reference's
+  // np.linalg.norm over the stacked rows; its BLAS summation order is not reproduced, so the
+  // factor may differ in the last bit, which only matters for a proposal exactly on the
+  // acceptance threshold)
+  __shared__ double s_n1[256], s_n2[256];
+  double mrf = 1.0;
+  if (snooker) {
+    double a1 = 0.0, a2 = 0.0;
+    for (int c = threadIdx.x; c < mc.nchains; c += blockDim.x) {
+      const bool sj = mc.ugamma[(size_t)i * mc.nchains + c] < 0.1;
+      if (!sj || mc.noproj[c] || mc.outflag[c]) continue;
+      const double *z = mc.Z + ((size_t)mc.iz[(size_t)i * mc.nchains + c] * mc.nchains +
+                                mc.ic[(size_t)i * mc.nchains + c]) * np;
+      const double *cur = mc.params + (size_t)c * np, *nx = mc.nextp + (size_t)c * np;
+      for (int f = 0; f < mc.nfree; f++) {
+        const int p = mc.ifree[f];
+        const double d1 = nx[p] - z[p], d2 = cur[p] - z[p];
+        a1 += d1 * d1; a2 += d2 * d2;
+      }
+    }
+    s_n1[threadIdx.x] = a1; s_n2[threadIdx.x] = a2;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if ((int)threadIdx.x < o) { s_n1[threadIdx.x] += s_n1[threadIdx.x + o]; s_n2[threadIdx.x] += s_n2[threadIdx.x + o]; }
+      __syncthreads();
+    }
+    mrf = pow(sqrt(s_n1[0]) / sqrt(s_n2[0]), (double)(mc.nfree - 1));
+  }
   for (int c = threadIdx.x; c < mc.nchains; c += blockDim.x) {
     const double *model = chain_model(models, mp, c, mc.ndata);
     double *cur = mc.params + (size_t)c * np;
@@ -222,7 +355,9 @@ chisq_accept_kernel(McmcDev mc, const double *__restrict__ models, ModelMap mp, 
       chain_chisq(mc, model, nx, &next, &mc.c2[c]);
     } else next = INFINITY;                                  // mcmc.py:598
     mc.nextchisq[c] = next;
-    const double accept = exp(0.5 * (mc.currchisq[c] - next));
+    double accept = exp(0.5 * (mc.currchisq[c] - next));
+    if (snooker && mc.ugamma[(size_t)i * mc.nchains + c] < 0.1 && !mc.noproj[c] && !mc.outflag[c])
+      accept = __dmul_rn(accept, mrf);
     const bool ok = accept >= mc.unif[(size_t)i * mc.nchains + c];
     if (ok) {
       for (int p = 0; p < np; p++) cur[p] = nx[p];
@@ -231,6 +366,11 @@ chisq_accept_kernel(McmcDev mc, const double *__restrict__ models, ModelMap mp, 
     }
     for (int f = 0; f < mc.nfree; f++)
       mc.allparams[((size_t)c * mc.nfree + f) * mc.chainsize + i] = cur[mc.ifree[f]];
+    if (snooker && i % mc.thinning == 0) {                   // mcmc.py:653-660
+      double *zr = mc.Z + ((size_t)zrow * mc.nchains + c) * np;
+      for (int f = 0; f < mc.nfree; f++) zr[mc.ifree[f]] = cur[mc.ifree[f]];
+      mc.Zchisq[(size_t)zrow * mc.nchains + c] = mc.currchisq[c];
+    }
   }
   __syncthreads();
   // running best fit: first index of the minimum no-Jeffreys chi-squared (np.argmin)
@@ -258,8 +398,59 @@ chisq_accept_kernel(McmcDev mc, const double *__restrict__ models, ModelMap mp, 
     if (threadIdx.x == 0) {
       if (take) *mc.bestchisq = best;
       if (!first) *mc.iter = i + 1;
+      if (snooker && i % mc.thinning == 0) *mc.zsize = zrow + 1;
     }
   }
+}
+
+// chi-squared of the initial Z samples of row `row` and the running best over rows in flattened
+// (row, chain) order, first minimum wins like np.argmin (mcmc.py:441-460); Zchisq keeps the value
+// WITH the Jeffreys term, which is also what the reference compares to the chains' best (462-470)
+__global__ void __launch_bounds__(256)
+zrow_chisq_kernel(McmcDev mc, const double *__restrict__ models, ModelMap mp, int row, int last) {
+  const int np = mc.npars;
+  double *zc = mc.Zchisq + (size_t)row * mc.nchains;
+  for (int c = threadIdx.x; c < mc.nchains; c += blockDim.x) {
+    double unused;
+    chain_chisq(mc, chain_model(models, mp, c, mc.ndata), mc.Z + ((size_t)row * mc.nchains + c) * np,
+                &zc[c], &unused);
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double best = INFINITY;
+    int arg = 0x7fffffff;
+    for (int c = threadIdx.x; c < mc.nchains; c += 32) {
+      const double v = zc[c];
+      if (v < best || (v == best && c < arg)) { best = v; arg = c; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ob = __shfl_down_sync(0xffffffffu, best, o);
+      const int oa = __shfl_down_sync(0xffffffffu, arg, o);
+      if (ob < best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+    }
+    best = __shfl_sync(0xffffffffu, best, 0);
+    arg = __shfl_sync(0xffffffffu, arg, 0);
+    const bool take = arg < mc.nchains && (row == 0 || best < mc.zbest[0]);
+    if (take) {
+      const double *model = chain_model(models, mp, arg, mc.ndata);
+      for (int p = threadIdx.x; p < np; p += 32) mc.zbest[1 + p] = mc.Z[((size_t)row * mc.nchains + arg) * np + p];
+      for (int d = threadIdx.x; d < mc.ndata; d += 32) mc.zbest[1 + np + d] = model[d];
+    }
+    __syncwarp();
+    if (threadIdx.x == 0 && take) mc.zbest[0] = best;
+    __syncwarp();
+    if (last && mc.zbest[0] < *mc.bestchisq) {
+      for (int p = threadIdx.x; p < np; p += 32) mc.bestp[p] = mc.zbest[1 + p];
+      for (int d = threadIdx.x; d < mc.ndata; d += 32) mc.bestmodel[d] = mc.zbest[1 + np + d];
+      __syncwarp();
+      if (threadIdx.x == 0) *mc.bestchisq = mc.zbest[0];
+    }
+  }
+}
+
+void launch_zrow_chisq(const McmcDev &mc, const double *models, ModelMap map, int row, int last,
+                       cudaStream_t s) {
+  zrow_chisq_kernel<<<1, 256, 0, s>>>(mc, models, map, row, last);
 }
 
 void launch_chisq_accept(const McmcDev &mc, const double *models, ModelMap map, int first,

@@ -2,7 +2,11 @@
 //   K-1 convert_params_kernel   input converter, code/BARTfunc.py:320-360 + code/PT.py:589-750
 //   K7  demc_propose_kernel     DE-MC proposal, modules/MCcubed/MCcubed/mc/mcmc.py:524-575
 //   K8  chisq_accept_kernel     chi-squared (src_c/chisq.c:111-142, include/stats.h:72-103),
-//                               Metropolis rule, best fit, trace (mcmc.py:590-625)
+//                               Metropolis rule, best fit, trace (mcmc.py:590-625), snooker
+//                               Metropolis factor (603-609) and Z update (653-660)
+//   K9  snooker_propose_kernel  DE-MC-with-snooker proposal from the sample history Z
+//                               (ter Braak & Vrugt 2008; mcmc.py:527-561)
+//   K10 zrow_chisq_kernel       chi-squared of the initial Z samples (mcmc.py:426-460)
 #pragma once
 #include "device.cuh"
 #include <cuda_runtime.h>
@@ -53,12 +57,30 @@ struct McmcDev {
   const int *r1, *r2;      // [nchains][chainsize]
   const double *unif;      // [chainsize][nchains]
   const double *ugamma;    // [chainsize][nchains]
+  // walk = 1: snooker (mcmc.py:357-460,527-561,603-609,653-660)
+  int walk, hsize, thinning;
+  double *Z;               // [zcap][nchains][npars] sample history; rows carry the chains'
+                           // initial non-free columns like the reference's (mcmc.py:419,425)
+  double *Zchisq;          // [zcap][nchains]
+  int *zsize;              // rows filled so far (device counter, advances with the generations)
+  double *zbest;           // [1 + npars + ndata] best initial Z sample: chisq, params, model
+  const int *i1, *i2;      // [chainsize][nchains] flat (row, chain) indices into Z
+  const int *iz, *ic;      // [chainsize][nchains]
+  const double *usn;       // [sum of snooker chains][nfree] uniform(1.2, 2.2) factors
+  const int *usn_off;      // [chainsize + 1] first row of generation i in usn
+  int *noproj;             // [nchains] scratch: z == current state (mcmc.py:543)
+  int *slot;               // [nchains] scratch: row of the chain's factors in usn
 };
 
 // where chain c's model sits in the gathered band-flux buffer: rank blocks of `pad` rows
 struct ModelMap { int world, base, extra, pad; };
 
 void launch_demc_propose(const McmcDev &mc, cudaStream_t s);
+void launch_snooker_propose(const McmcDev &mc, cudaStream_t s);
+// chi-squared of Z row `row` (models of its nchains samples); keeps the running best in mc.zbest.
+// last != 0: afterwards adopt zbest as the best fit when it beats the chains' (mcmc.py:462-470)
+void launch_zrow_chisq(const McmcDev &mc, const double *models, ModelMap map, int row, int last,
+                       cudaStream_t s);
 // first = 1: initial state (mcmc.py:310-345): chi-squared of the current parameters, best fit
 void launch_chisq_accept(const McmcDev &mc, const double *models, ModelMap map, int first,
                          cudaStream_t s);

@@ -154,6 +154,12 @@ struct State {
   DevBuf<int> d_mci[8];
   DevBuf<double> d_mcband, d_mcgather;
   cudaGraphExec_t mc_graph = nullptr;
+  // snooker walk: sample history Z
+  DevBuf<double> d_Z, d_Zchisq, d_snk_usn;
+  DevBuf<int> d_snk_idx, d_snk_off;
+  int mc_zsize = 0;                        // host mirror of the device row counter
+  size_t mc_zcap = 0;                      // rows allocated
+  std::vector<double> mc_ztemplate;        // [nchains][npars] what an unfilled row holds
 };
 static State G;
 
@@ -365,6 +371,8 @@ static void reset_state() {
   G.d_cstatus.release(); G.d_mcband.release(); G.d_mcgather.release();
   for (auto &b : G.d_mcd) b.release();
   for (auto &b : G.d_mci) b.release();
+  G.d_snk_usn.release(); G.d_snk_idx.release(); G.d_snk_off.release();
+  G.d_Z.release(); G.d_Zchisq.release(); G.mc_zsize = 0; G.mc_zcap = 0; G.mc_ztemplate.clear();
   if (G.mc_graph) { cudaGraphExecDestroy(G.mc_graph); G.mc_graph = nullptr; }
   G.conv = ConvConfig(); G.mc = McmcDev(); G.mc_ready = false; G.pre_status = nullptr;
   G.nfilters = 0; G.knob_models = 0; G.last_batch = 0;
@@ -634,16 +642,36 @@ static void params_to_bandflux_queued(const double *d_params, int nmodels, int n
   band_device(G.d_spec.p, nmodels, G.d_status.p, d_band);
 }
 
-// one DE-MC generation, queued on G.stream (first: the initial evaluation, mcmc.py:310-345)
+static const double *mcmc_evaluate_queued(const double *d_params);
+
+// one DE-MC / snooker generation, queued on G.stream (first: the initial evaluation,
+// mcmc.py:310-345)
 static void mcmc_generation_queued(int first) {
   McmcDev &mc = G.mc;
-  const int nloc = G.mc_hi - G.mc_lo;
-  if (!first) {
+  if (!first && mc.walk == 1) {
+    KernelScope ks("snooker_propose");
+    launch_snooker_propose(mc, G.stream);
+    check_launch("snooker_propose");
+  } else if (!first) {
     KernelScope ks("demc_propose");
     launch_demc_propose(mc, G.stream);
     check_launch("demc_propose");
   }
-  const double *src = (first ? mc.params : mc.nextp) + (size_t)G.mc_lo * mc.npars;
+  const double *models = mcmc_evaluate_queued(first ? mc.params : mc.nextp);
+  ModelMap mp{G.world, mc.nchains / G.world, mc.nchains % G.world, G.mc_pad};
+  {
+    KernelScope ks("chisq_accept");
+    launch_chisq_accept(mc, models, mp, first, G.stream);
+    check_launch("chisq_accept");
+  }
+}
+
+// band fluxes of one population `d_params` [nchains][npars] (device): this rank's block of chains
+// through the forward model, then the all-gather; returns the buffer chain_model() indexes
+static const double *mcmc_evaluate_queued(const double *d_params) {
+  McmcDev &mc = G.mc;
+  const int nloc = G.mc_hi - G.mc_lo;
+  const double *src = d_params + (size_t)G.mc_lo * mc.npars;
   params_to_bandflux_queued(src, nloc, mc.npars, G.d_mcband.p);
   const double *models = G.d_mcband.p;
   if (G.world > 1) {
@@ -656,18 +684,51 @@ static void mcmc_generation_queued(int first) {
     G.launches++;
     models = G.d_mcgather.p;
   }
-  ModelMap mp{G.world, mc.nchains / G.world, mc.nchains % G.world, G.mc_pad};
-  {
-    KernelScope ks("chisq_accept");
-    launch_chisq_accept(mc, models, mp, first, G.stream);
-    check_launch("chisq_accept");
-  }
+  return models;
 }
 
 static void finish_stream() {
   cudaError_t e = cudaStreamSynchronize(G.stream);
   if (e != cudaSuccess) fail("CUDA execution failed: %s", cudaGetErrorString(e));
   if (G.profile) drain_profile();
+}
+
+// niter generations of the walk set up in G.mc, queued and awaited
+static void mcmc_run_generations(int niter) {
+  McmcDev &mc = G.mc;
+  CUDA_OK(cudaMemsetAsync(mc.iter, 0, sizeof(int), G.stream));
+  if (G.mc_graph) { cudaGraphExecDestroy(G.mc_graph); G.mc_graph = nullptr; }
+  ensure_params_buffers(G.mc_hi - G.mc_lo);
+  // One generation is a fixed sequence of launches whose only varying input, the iteration
+  // number, lives on the device: capture it once and replay it (launch-latency bound at MC3's
+  // usual 10-chain populations).  Per-kernel timing and multi-rank runs use plain launches unless
+  // BART_MCMC_GRAPH=1.
+  const char *genv = getenv("BART_MCMC_GRAPH");
+  bool use_graph = genv ? atoi(genv) != 0 : (G.world == 1);
+  if (G.profile || niter < 3) use_graph = false;
+  int done = 0;
+  if (use_graph) {
+    mcmc_generation_queued(0); done = 1;          // warms every lazily configured launch
+    const long long before = G.launches;
+    cudaGraph_t graph = nullptr;
+    CUDA_OK(cudaStreamBeginCapture(G.stream, cudaStreamCaptureModeThreadLocal));
+    bool ok = true;
+    try { mcmc_generation_queued(0); } catch (BartError &) { ok = false; }
+    cudaError_t e = cudaStreamEndCapture(G.stream, &graph);
+    const long long per_gen = G.launches - before;
+    if (ok && e == cudaSuccess && graph &&
+        cudaGraphInstantiate(&G.mc_graph, graph, 0) == cudaSuccess) {
+      for (; done < niter; done++) CUDA_OK(cudaGraphLaunch(G.mc_graph, G.stream));
+      G.launches += per_gen * (niter - 2);
+    } else {
+      cudaGetLastError();
+      G.launches = before;
+      if (!ok) { g_error_pending = false; g_error_msg[0] = 0; }
+    }
+    if (graph) cudaGraphDestroy(graph);
+  }
+  for (; done < niter; done++) mcmc_generation_queued(0);
+  finish_stream();
 }
 
 }  // namespace bart
@@ -1345,6 +1406,8 @@ int bart_mcmc_init(int nchains, int npars, const double *params, const double *p
   zi.assign(nchains, 0); upload(G.d_mci[1], zi); mc.outflag = G.d_mci[1].p;
   zi.assign(1, 0); upload(G.d_mci[2], zi); mc.iter = G.d_mci[2].p;
   G.mc = mc;
+  G.mc_ztemplate = p0;
+  G.mc_zsize = 0;
   chain_block(nchains, G.world, G.rank, &G.mc_lo, &G.mc_hi);
   G.mc_pad = nchains / G.world + (nchains % G.world ? 1 : 0);
   G.d_mcband.ensure((size_t)G.mc_pad * ndata);
@@ -1392,39 +1455,158 @@ int bart_mcmc_run(int niter, const double *support, const int *r1, const int *r2
   mc.r2 = upi(d_r2, r2, (size_t)nc * niter);
   d_trace.ensure((size_t)nc * mc.nfree * niter);
   mc.allparams = d_trace.p;
-  CUDA_OK(cudaMemsetAsync(mc.iter, 0, sizeof(int), G.stream));
-  if (G.mc_graph) { cudaGraphExecDestroy(G.mc_graph); G.mc_graph = nullptr; }
-  ensure_params_buffers(G.mc_hi - G.mc_lo);
-  // One generation is a fixed sequence of launches whose only varying input, the iteration
-  // number, lives on the device: capture it once and replay it (launch-latency bound at MC3's
-  // usual 10-chain populations).  Per-kernel timing and multi-rank runs use plain launches unless
-  // BART_MCMC_GRAPH=1.
-  const char *genv = getenv("BART_MCMC_GRAPH");
-  bool use_graph = genv ? atoi(genv) != 0 : (G.world == 1);
-  if (G.profile || niter < 3) use_graph = false;
-  int done = 0;
-  if (use_graph) {
-    mcmc_generation_queued(0); done = 1;          // warms every lazily configured launch
-    const long long before = G.launches;
-    cudaGraph_t graph = nullptr;
-    CUDA_OK(cudaStreamBeginCapture(G.stream, cudaStreamCaptureModeThreadLocal));
-    bool ok = true;
-    try { mcmc_generation_queued(0); } catch (BartError &) { ok = false; }
-    cudaError_t e = cudaStreamEndCapture(G.stream, &graph);
-    const long long per_gen = G.launches - before;
-    if (ok && e == cudaSuccess && graph &&
-        cudaGraphInstantiate(&G.mc_graph, graph, 0) == cudaSuccess) {
-      for (; done < niter; done++) CUDA_OK(cudaGraphLaunch(G.mc_graph, G.stream));
-      G.launches += per_gen * (niter - 2);
-    } else {
-      cudaGetLastError();
-      G.launches = before;
-      if (!ok) { g_error_pending = false; g_error_msg[0] = 0; }
-    }
-    if (graph) cudaGraphDestroy(graph);
+  mc.walk = 0;
+  mcmc_run_generations(niter);
+  return 0;
+  API_END_INT
+}
+
+
+// ---- snooker walk (BART's configured walk; ter Braak & Vrugt 2008 as in mcmc.py) ----
+// (re)allocate the history for `rows` rows, keeping the filled ones; an unfilled row holds the
+// chains' initial parameters (mcmc.py:419: Z[:, :, 0:mpars] = params; the generation loop only
+// ever overwrites the free columns, 656)
+static void snooker_reserve_rows(size_t rows) {
+  McmcDev &mc = G.mc;
+  if (rows <= G.mc_zcap) return;
+  const size_t rowlen = (size_t)mc.nchains * mc.npars;
+  rows += rows / 2 + 16;
+  DevBuf<double> nz, nc;
+  nz.ensure(rows * rowlen); nc.ensure(rows * mc.nchains);
+  std::vector<double> fill(rows * rowlen);
+  for (size_t r = 0; r < rows; r++) std::copy(G.mc_ztemplate.begin(), G.mc_ztemplate.end(), fill.begin() + r * rowlen);
+  CUDA_OK(cudaMemcpyAsync(nz.p, fill.data(), fill.size() * 8, cudaMemcpyHostToDevice, G.stream));
+  CUDA_OK(cudaMemsetAsync(nc.p, 0, rows * mc.nchains * 8, G.stream));
+  if (G.mc_zsize > 0) {
+    CUDA_OK(cudaMemcpyAsync(nz.p, G.d_Z.p, (size_t)G.mc_zsize * rowlen * 8, cudaMemcpyDeviceToDevice, G.stream));
+    CUDA_OK(cudaMemcpyAsync(nc.p, G.d_Zchisq.p, (size_t)G.mc_zsize * mc.nchains * 8, cudaMemcpyDeviceToDevice, G.stream));
   }
-  for (; done < niter; done++) mcmc_generation_queued(0);
+  CUDA_OK(cudaStreamSynchronize(G.stream));
+  G.d_Z.release(); G.d_Zchisq.release();
+  G.d_Z = nz; G.d_Zchisq = nc;
+  G.mc_zcap = rows;
+  mc.Z = G.d_Z.p; mc.Zchisq = G.d_Zchisq.p;
+}
+
+// replaces the Z set-up of MCcubed.mc.mcmc for walk='snooker' (mcmc.py:357-470): after
+// bart_mcmc_init.  z0[hsize][nchains][nfree]: the M0 = hsize*nchains initial samples of the free
+// parameters (the reference draws them uniformly in [pmin, pmax], 421-424; hsize must already be
+// > nchains as mcmc.py:233-235 enforces); their models are evaluated here (429-447) and the best
+// of them competes with the chains' best fit (449-470).
+int bart_mcmc_snooker_init(int hsize, int thinning, const double *z0) {
+  API_BEGIN
+  if (!G.mc_ready) fail("bart_mcmc_init has not been called");
+  McmcDev &mc = G.mc;
+  if (hsize < 2) fail("snooker needs hsize >= 2 (got %d)", hsize);
+  if (thinning < 1) fail("thinning must be >= 1 (got %d)", thinning);
+  const int nc = mc.nchains, np = mc.npars;
+  // fixed parameters of every Z sample are chain 0's (mcmc.py:425)
+  for (int c = 0; c < nc; c++)
+    for (int p = 0; p < np; p++) {
+      bool fixed = true;
+      for (int f = 0; f < mc.nfree; f++) fixed &= mc.ifree[f] != p;
+      for (int k = 0; k < mc.nshare; k++) fixed &= mc.share_dst[k] != p;
+      if (fixed) G.mc_ztemplate[(size_t)c * np + p] = G.mc_ztemplate[p];
+    }
+  G.mc_zsize = 0; G.mc_zcap = 0;
+  snooker_reserve_rows((size_t)hsize + 64);
+  std::vector<double> rows((size_t)hsize * nc * np);
+  for (int r = 0; r < hsize; r++)
+    for (int c = 0; c < nc; c++) {
+      double *dst = &rows[((size_t)r * nc + c) * np];
+      std::copy(&G.mc_ztemplate[(size_t)c * np], &G.mc_ztemplate[(size_t)c * np] + np, dst);
+      for (int f = 0; f < mc.nfree; f++) dst[mc.ifree[f]] = z0[((size_t)r * nc + c) * mc.nfree + f];
+    }
+  CUDA_OK(cudaMemcpyAsync(mc.Z, rows.data(), rows.size() * 8, cudaMemcpyHostToDevice, G.stream));
+  std::vector<int> zi(1, hsize);
+  upload(G.d_mci[5], zi); mc.zsize = G.d_mci[5].p;
+  zi.assign(nc, 0);
+  upload(G.d_mci[6], zi); mc.noproj = G.d_mci[6].p;
+  upload(G.d_mci[7], zi); mc.slot = G.d_mci[7].p;
+  G.d_mcd[19].ensure(1 + np + mc.ndata); mc.zbest = G.d_mcd[19].p;
+  mc.hsize = hsize; mc.thinning = thinning; mc.walk = 1;
+  ensure_params_buffers(G.mc_hi - G.mc_lo);
+  ModelMap mp{G.world, nc / G.world, nc % G.world, G.mc_pad};
+  for (int r = 0; r < hsize; r++) {
+    const double *models = mcmc_evaluate_queued(mc.Z + (size_t)r * nc * np);
+    KernelScope ks("zrow_chisq");
+    launch_zrow_chisq(mc, models, mp, r, r == hsize - 1, G.stream);
+    check_launch("zrow_chisq");
+  }
   finish_stream();
+  G.mc_zsize = hsize;
+  return 0;
+  API_END_INT
+}
+
+// replaces the generation loop of MCcubed.mc.mcmc for walk='snooker' (mcmc.py:518-660).  Random
+// streams from the caller, in the order and shapes mcmc.py consumes them (chainsize = niter):
+// support[niter][nchains][nfree], unif/ugamma[niter][nchains] (490-497); per generation i1, i2
+// (flat indices into the first Zsize-1 rows x nchains, i1 != i2), iz (row < Zsize-1), ic (chain)
+// [niter][nchains] (529-539); usnooker[usn_offset[niter]][nfree] the uniform(1.2, 2.2) factors
+// of the chains with ugamma < 0.1, generation i owning rows usn_offset[i]..usn_offset[i+1]
+// (545-556).  Zsize starts at hsize and grows by one after every generation with
+// i % thinning == 0 (653-660).
+int bart_mcmc_run_snooker(int niter, const double *support, const int *i1, const int *i2,
+                          const int *iz, const int *ic, const double *usnooker,
+                          const int *usn_offset, const double *unif, const double *ugamma) {
+  API_BEGIN
+  if (!G.mc_ready || G.mc_zsize < 2) fail("bart_mcmc_snooker_init has not been called");
+  if (niter <= 0) return 0;
+  McmcDev &mc = G.mc;
+  const int nc = mc.nchains;
+  // validate the indices against the history size each generation will see
+  {
+    int zs = G.mc_zsize;
+    for (int i = 0; i < niter; i++) {
+      int nsj = 0;
+      for (int c = 0; c < nc; c++) {
+        const size_t k = (size_t)i * nc + c;
+        const long long lim = (long long)(zs - 1) * nc;
+        if (i1[k] < 0 || i1[k] >= lim || i2[k] < 0 || i2[k] >= lim || iz[k] < 0 || iz[k] >= zs - 1 ||
+            ic[k] < 0 || ic[k] >= nc)
+          fail("snooker index out of range at generation %d, chain %d (history rows %d)", i, c, zs);
+        nsj += ugamma[k] < 0.1;
+      }
+      if (usn_offset[i + 1] - usn_offset[i] != nsj || usn_offset[i] < 0)
+        fail("usn_offset: generation %d has %d snooker chains but %d rows of factors", i, nsj,
+             usn_offset[i + 1] - usn_offset[i]);
+      if (i % mc.thinning == 0) zs++;
+    }
+    snooker_reserve_rows((size_t)zs + 1);
+    G.mc_zsize = zs;
+  }
+  mc.nold += mc.chainsize;
+  mc.chainsize = niter;
+  auto upd = [&](DevBuf<double> &b, const double *src, size_t n) {
+    b.ensure(std::max<size_t>(n, 1));
+    if (n) CUDA_OK(cudaMemcpyAsync(b.p, src, n * 8, cudaMemcpyHostToDevice, G.stream));
+    return (const double *)b.p;
+  };
+  auto upi = [&](DevBuf<int> &b, const int *src, size_t n) {
+    b.ensure(n);
+    CUDA_OK(cudaMemcpyAsync(b.p, src, n * 4, cudaMemcpyHostToDevice, G.stream));
+    return (const int *)b.p;
+  };
+  // i1, i2, iz, ic packed in one buffer; usn_offset in another
+  DevBuf<int> &d_idx = G.d_snk_idx, &d_off = G.d_snk_off;
+  DevBuf<double> &d_usn = G.d_snk_usn;
+  const size_t n1 = (size_t)niter * nc;
+  std::vector<int> packed(4 * n1);
+  std::copy(i1, i1 + n1, packed.begin()); std::copy(i2, i2 + n1, packed.begin() + n1);
+  std::copy(iz, iz + n1, packed.begin() + 2 * n1); std::copy(ic, ic + n1, packed.begin() + 3 * n1);
+  const int *pk = upi(d_idx, packed.data(), packed.size());
+  CUDA_OK(cudaStreamSynchronize(G.stream));
+  mc.i1 = pk; mc.i2 = pk + n1; mc.iz = pk + 2 * n1; mc.ic = pk + 3 * n1;
+  mc.usn_off = upi(d_off, usn_offset, (size_t)niter + 1);
+  mc.usn = upd(d_usn, usnooker, (size_t)usn_offset[niter] * mc.nfree);
+  mc.support = upd(G.d_mcd[15], support, n1 * mc.nfree);
+  mc.unif = upd(G.d_mcd[16], unif, n1);
+  mc.ugamma = upd(G.d_mcd[17], ugamma, n1);
+  G.d_mcd[18].ensure((size_t)nc * mc.nfree * niter);
+  mc.allparams = G.d_mcd[18].p;
+  mc.walk = 1;
+  mcmc_run_generations(niter);
   return 0;
   API_END_INT
 }
@@ -1447,6 +1629,8 @@ long long bart_mcmc_get(const char *name, double *out, long long capacity) {
   else if (n == "bestp") { src = mc.bestp; cnt = mc.npars; }
   else if (n == "bestchisq") { src = mc.bestchisq; cnt = 1; }
   else if (n == "bestmodel") { src = mc.bestmodel; cnt = mc.ndata; }
+  else if (n == "Z") { src = mc.Z; cnt = (long long)G.mc_zsize * mc.nchains * mc.npars; }
+  else if (n == "Zchisq") { src = mc.Zchisq; cnt = (long long)G.mc_zsize * mc.nchains; }
   else if (n == "outbounds") {
     cnt = (long long)mc.nchains * mc.nfree;
     if (cnt > capacity) fail("bart_mcmc_get(%s): capacity %lld < %lld", name, capacity, cnt);

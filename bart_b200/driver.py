@@ -208,3 +208,74 @@ def run_demc(transit, data, uncert, params, pmin, pmax, stepsize, numit, nchains
     allp = out["allparams"]
     out["allstack"] = np.hstack([allp[c, :, burnin:chainsize] for c in range(nchains)])  # mcmc.py:692-695
     return out
+
+
+def snooker_draws(rng, nchains, nfree, chainsize, hsize, thinning, step_free, pmin_free, pmax_free):
+    """The random numbers MC3's walk='snooker' consumes, in its order: the M0 initial history
+    samples (mcmc.py:421-424), support / unif / ugamma (490-497), then per generation i1, i2 with
+    their collision redraws, iz, ic (529-539) and the uniform(1.2, 2.2) factors of that
+    generation's snooker chains (545-556; the reference's two calls take, together,
+    [chains with ugamma < 0.1][nfree] values however they split).  None of these depends on the
+    chain states, so the host draws them up front and the generation loop stays on the device."""
+    z0 = np.zeros((hsize, nchains, nfree))
+    for f in range(nfree):
+        z0[:, :, f] = rng.uniform(pmin_free[f], pmax_free[f], (hsize, nchains))
+    support = rng.normal(0, step_free, (chainsize, nchains, nfree))
+    unif = rng.uniform(0, 1, (chainsize, nchains))
+    ugamma = rng.uniform(0, 1, (chainsize, nchains))
+    sjump = ugamma < 0.1
+    idx = np.zeros((4, chainsize, nchains), np.int64)
+    usn, offset = [], np.zeros(chainsize + 1, np.int64)
+    zsize = hsize
+    for i in range(chainsize):
+        a = rng.randint(0, (zsize - 1) * nchains, nchains)
+        b = rng.randint(0, (zsize - 1) * nchains, nchains)
+        for j in range(nchains):
+            while a[j] == b[j]:
+                b[j] = rng.randint(0, (zsize - 1) * nchains)
+        idx[0, i], idx[1, i] = a, b
+        idx[2, i] = rng.randint(0, zsize - 1, nchains)
+        idx[3, i] = rng.randint(0, nchains, nchains)
+        n = int(sjump[i].sum())
+        if n:
+            usn.append(rng.uniform(1.2, 2.2, (n, nfree)))
+        offset[i + 1] = offset[i] + n
+        if i % thinning == 0:
+            zsize += 1
+    return dict(z0=z0, support=support, unif=unif, ugamma=ugamma, i1=idx[0], i2=idx[1], iz=idx[2],
+                ic=idx[3], usnooker=np.concatenate(usn) if usn else np.zeros((0, nfree)),
+                usn_offset=offset)
+
+
+def run_snooker(transit, data, uncert, params, pmin, pmax, stepsize, numit, nchains, prior=None,
+                priorlow=None, burnin=0, thinning=1, fgamma=1.0, fepsilon=0.0, hsize=1,
+                rng=np.random, draws=None):
+    """`MCcubed.mc.mcmc(..., walk='snooker', leastsq=False)` -- the walk BART's examples configure
+    -- with the sample history Z, the proposals, the Metropolis rule and the forward models all on
+    the GPU.  Returns MC3's arrays (see run_demc) plus Z and Zchisq."""
+    params = np.atleast_2d(np.array(params, dtype=float))
+    pmin, pmax, stepsize = (np.asarray(a, dtype=float) for a in (pmin, pmax, stepsize))
+    ifree = np.where(stepsize > 0)[0]
+    chainsize = int(np.ceil(numit / nchains))
+    if hsize < nchains:                                              # mcmc.py:233-235
+        hsize = nchains + 1
+    if params.shape[0] != nchains:                                   # mcmc.py:296-306
+        params = np.repeat(params, nchains, 0)
+        for p in ifree:
+            params[1:, p] = rng.normal(params[0, p], stepsize[p], nchains - 1)
+            params[np.where(params[:, p] < pmin[p]), p] = pmin[p]
+            params[np.where(params[:, p] > pmax[p]), p] = pmax[p]
+    transit.mcmc_init(params, pmin, pmax, stepsize, data, uncert, prior=prior, priorlow=priorlow,
+                      fgamma=fgamma, fepsilon=fepsilon, burnin=burnin)
+    if draws is None:
+        draws = snooker_draws(rng, nchains, len(ifree), chainsize, hsize, thinning, stepsize[ifree],
+                              pmin[ifree], pmax[ifree])
+    transit.mcmc_snooker_init(draws["z0"], thinning)
+    transit.mcmc_run_snooker(*(draws[k] for k in ("support", "i1", "i2", "iz", "ic", "usnooker",
+                                                  "usn_offset", "unif", "ugamma")))
+    out = {k: transit.mcmc_get(k) for k in ("allparams", "params", "currchisq", "numaccept",
+                                            "outbounds", "bestp", "bestmodel", "models", "Z", "Zchisq")}
+    out["bestchisq"] = float(transit.mcmc_get("bestchisq")[0])
+    allp = out["allparams"]
+    out["allstack"] = np.hstack([allp[c, :, burnin:chainsize] for c in range(nchains)])
+    return out

@@ -223,8 +223,26 @@ int  bart_mcmc_init(int nchains, int npars, const double *params, const double *
  * r1/r2[nchains][niter], unif/ugamma[niter][nchains].                                            */
 int  bart_mcmc_run(int niter, const double *support, const int *r1, const int *r2,
                    const double *unif, const double *ugamma);
+/* replaces MCcubed.mc.mcmc for walk='snooker' -- the walk every BART example configures
+ * (examples/WASP-12b/BART.cfg:118) -- DE-MC with snooker updates drawn from the sample history Z
+ * (ter Braak & Vrugt 2008): Z set-up and evaluation of the hsize*nchains initial samples
+ * (mcmc.py:357-470), proposals (527-561), Metropolis factor of projected jumps (603-609), Z
+ * update every `thinning` generations (653-660).  Call after bart_mcmc_init.
+ * z0[hsize][nchains][nfree]: initial samples of the free parameters (the reference draws them
+ * uniformly in [pmin, pmax]); hsize > nchains as mcmc.py:233-235 enforces is the caller's job.   */
+int  bart_mcmc_snooker_init(int hsize, int thinning, const double *z0);
+/* niter snooker generations without a host round trip.  Random streams in the order mcmc.py
+ * consumes them: support[niter][nchains][nfree], unif/ugamma[niter][nchains] (490-497); per
+ * generation i1, i2 (flat indices into Z's first Zsize-1 rows x nchains), iz (row), ic (chain),
+ * each [niter][nchains] (529-539); usnooker[usn_offset[niter]][nfree]: the uniform(1.2, 2.2)
+ * factors of the chains with ugamma < 0.1, generation i owning rows usn_offset[i] ..
+ * usn_offset[i+1] in the reference's draw order (545-556).                                       */
+int  bart_mcmc_run_snooker(int niter, const double *support, const int *i1, const int *i2,
+                           const int *iz, const int *ic, const double *usnooker,
+                           const int *usn_offset, const double *unif, const double *ugamma);
 /* "allparams" [nchains][nfree][niter], "params", "currchisq", "numaccept", "outbounds", "bestp",
- * "bestchisq", "bestmodel", "models"; returns the number of doubles written or < 0.             */
+ * "bestchisq", "bestmodel", "models", and for snooker "Z" [Zsize][nchains][npars], "Zchisq"
+ * [Zsize][nchains]; returns the number of doubles written or < 0.                               */
 long long bart_mcmc_get(const char *name, double *out, long long capacity);
 
 #ifdef __cplusplus

@@ -161,3 +161,77 @@ def test_demc_continues_across_calls(api, workdir):
     assert np.array_equal(np.concatenate(halves, axis=2), one["allparams"])
     assert np.array_equal(tr.mcmc_get("params"), one["params"])
     tr.free_memory()
+
+
+@pytest.mark.parametrize("graph", ["1", "0"])
+@pytest.mark.parametrize("thinning", [1, 3])
+@pytest.mark.parametrize("name", list(cases.RETRIEVAL))
+def test_snooker_on_device_reproduces_reference_mc3(name, thinning, graph, api, workdir, monkeypatch):
+    """walk='snooker' (BART's configured walk): the seeded reference MCcubed run (MPI mode) chain
+    for chain, with history Z, proposals, Metropolis rule and forward models on the GPU."""
+    from bart_b200 import driver
+    monkeypatch.setenv("BART_MCMC_GRAPH", graph)
+    case, spec, extra, tr = setup(api, name, workdir)
+    d = np.load(os.path.join(G, "retrieval_snooker_%s_thin%d.npz" % (name, thinning)))
+    np.random.seed(spec["seed"] + thinning)
+    out = driver.run_snooker(tr, d["data"], d["uncert"], spec["params"], spec["pmin"], spec["pmax"],
+                             spec["stepsize"], spec["numit"], spec["nchains"], burnin=spec["burnin"],
+                             thinning=thinning)
+    assert np.array_equal(out["allparams"], d["allparams"])          # every chain, every iteration
+    assert np.array_equal(out["allstack"], d["allstack"])
+    assert np.array_equal(out["bestp"], d["bestp"])
+    from oracle import retrieval_oracle as ro
+    np.random.seed(spec["seed"] + thinning)
+    ref = ro.snooker(band_oracle(case, spec, extra), d["data"], d["uncert"], spec["params"],
+                     spec["pmin"], spec["pmax"], spec["stepsize"], spec["numit"], spec["nchains"],
+                     burnin=spec["burnin"], thinning=thinning)
+    assert np.array_equal(out["numaccept"], ref["numaccept"])
+    assert np.array_equal(out["outbounds"], ref["outbounds"])
+    assert np.array_equal(out["params"], ref["params"])
+    assert out["Z"].shape[0] == ref["Zsize"]
+    assert np.array_equal(out["Z"], ref["Z"][:ref["Zsize"]])
+    assert relerr(out["Zchisq"], ref["Zchisq"][:ref["Zsize"]]) < 1e-6
+    assert relerr(out["currchisq"], ref["currchisq"]) < 1e-6
+    assert abs(out["bestchisq"] / ref["bestchisq"] - 1) < 1e-6
+    assert relerr(out["bestmodel"], ref["bestmodel"]) < 1e-6
+    tr.free_memory()
+
+
+def test_snooker_large_population_and_continuation(api, workdir):
+    """64 chains x 11 free parameters (numpy's 8-way pairwise sums in the projection), split over
+    two bart_mcmc_run_snooker calls, against the oracle on the same streams."""
+    from bart_b200 import driver
+    from oracle import retrieval_oracle as ro
+    name = "retr_small4_transit"
+    case, spec, extra, tr = setup(api, name, workdir)
+    d = np.load(os.path.join(G, "retrieval_mc3_%s.npz" % name))
+    nch, niter, thin = 64, 12, 2
+    stepsize = np.array(spec["stepsize"], dtype=float)
+    stepsize[2], stepsize[3] = 0.05, 0.02                           # free all but the shared one
+    pmin, pmax = np.array(spec["pmin"]), np.array(spec["pmax"])
+    ifree = np.where(stepsize > 0)[0]
+    assert len(ifree) == 11
+    rng = np.random.RandomState(11)
+    p0 = np.repeat(np.atleast_2d(spec["params"]), nch, 0)
+    p0[:, ifree] += rng.normal(0, 0.2, (nch, len(ifree))) * stepsize[ifree]
+    hsize = nch + 1
+    dr = driver.snooker_draws(rng, nch, len(ifree), niter, hsize, thin, stepsize[ifree], pmin[ifree], pmax[ifree])
+    dr["ugamma"][:, ::3] *= 0.2                                      # more snooker jumps than 10 %
+    sj = dr["ugamma"] < 0.1
+    dr["usn_offset"] = np.concatenate([[0], np.cumsum(sj.sum(axis=1))])
+    dr["usnooker"] = rng.uniform(1.2, 2.2, (dr["usn_offset"][-1], len(ifree)))
+    ref = ro.snooker(band_oracle(case, spec, extra), d["data"], d["uncert"], p0, pmin, pmax, stepsize,
+                     niter * nch, nch, thinning=thin, draws=dr)
+    tr.mcmc_init(p0, pmin, pmax, stepsize, d["data"], d["uncert"])
+    tr.mcmc_snooker_init(dr["z0"], thin)
+    halves = []
+    for h in (slice(0, 6), slice(6, 12)):
+        off = dr["usn_offset"][h.start:h.stop + 1]
+        tr.mcmc_run_snooker(dr["support"][h], dr["i1"][h], dr["i2"][h], dr["iz"][h], dr["ic"][h],
+                            dr["usnooker"][off[0]:off[-1]], off - off[0], dr["unif"][h], dr["ugamma"][h])
+        halves.append(tr.mcmc_get("allparams"))
+    got = np.concatenate(halves, axis=2)
+    assert np.array_equal(got, ref["allparams"])
+    assert np.array_equal(tr.mcmc_get("Z"), ref["Z"][:ref["Zsize"]])
+    assert np.any(ref["mrfactor"] != 1.0)
+    tr.free_memory()
