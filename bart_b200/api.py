@@ -17,6 +17,7 @@ dp = C.POINTER(C.c_double)
 ip = C.POINTER(C.c_int)
 
 REJ_TGRID, REJ_TCIA, REJ_SUMQ, REJ_FEWPTS = 1, 2, 4, 8
+REJ_NOTOOMUCH = 64
 
 
 class BartError(RuntimeError):

@@ -21,7 +21,7 @@ constexpr double cE0H2 = 4.911e-23;
 constexpr double cNAVO = 6.02214076e23;
 constexpr double cMICRON = 1e-4;
 
-enum { REJ_TGRID = 1, REJ_TCIA = 2, REJ_SUMQ = 4, REJ_FEWPTS = 8 };
+enum { REJ_TGRID = 1, REJ_TCIA = 2, REJ_SUMQ = 4, REJ_FEWPTS = 8, REJ_NOTOOMUCH = 64 };
 
 // ---------------------------------------------------------------------------------------
 // fp64 exp and reciprocal for the column kernels.  libdevice's exp() costs ~45 issue slots per
@@ -785,6 +785,20 @@ BART_HD void transit_weight_row_tiled(const DevConfig &c, const double *tab, int
   transit_weight_row_acc(c, tab, d, [base](int i) -> double & { return base[(size_t)i * kTrRow]; });
 }
 
+// modulationm1 (slantpath.c:446-473), modlevel -1: the planet as an opaque disc whose radius is
+// where tau reaches toomuch, by linear interpolation (interp_line, pu/src/numerical.c:203-211)
+// between the last two impact parameters.  tau0/tau1: optical depths at depths last-1 and last,
+// b0/b1 their impact parameters (cm).  Returns -1 when toomuch was not reached (the reference
+// exits, slantpath.c:308-316).
+BART_HD double modulation_m1(double tau0, double tau1, double b0, double b1, double toomuch,
+                             double inv_srad2, int *status) {
+  if (tau1 < toomuch) { *status |= REJ_NOTOOMUCH; return -1.0; }
+  const double dx = tau1 - tau0;
+  const double m = (b1 - b0) / dx;
+  const double muchrad = b0 + (toomuch - tau0) * m;
+  return muchrad * muchrad * inv_srad2;
+}
+
 // Transit column: tau(d) by the chord weights, stop at toomuch, then the modulation integral
 // (modulation1, slantpath.c:350-436) as a top-aligned Simpson scan over impact parameter.
 // `er` is per-thread scratch with stride `es` (shared memory in the kernel).
@@ -797,7 +811,7 @@ BART_HD double transit_column(const DevConfig &c, const double *tab, const unsig
   const int nf = c.lay.nf();
   const double wn = c.wn[w];
   const double wn4 = (wn * wn) * (wn * wn);
-  double S = 0.0, f1 = 0.0, f2 = 0.0, tau = 0.0;
+  double S = 0.0, f1 = 0.0, f2 = 0.0, tau = 0.0, tau_prev = 0.0;
   int last = nl - 1;
   int d;
   const ColPtrs P = col_ptrs<NCIA>(c, w);
@@ -805,6 +819,7 @@ BART_HD double transit_column(const DevConfig &c, const double *tab, const unsig
     const double *row = tab + (size_t)d * nf;
     er[(size_t)d * es] = cell_extinction<NMOL, NCIA>(c, P, row, wn4, false);
     const double *wr = wts + (size_t)d * (d + 1) / 2;
+    tau_prev = tau;
     tau = 0.0;
     for (int i = 0; i <= d; i++) tau += wr[i] * er[(size_t)i * es];
     if (KEEP) tau_keep[d] = tau;
@@ -815,6 +830,12 @@ BART_HD double transit_column(const DevConfig &c, const double *tab, const unsig
     if (tau > c.toomuch) { last = d; break; }
   }
   if (KEEP) *last_keep = last;
+  if (c.modlevel == -1) {
+    const int i0 = last > 0 ? last - 1 : 0;
+    return modulation_m1(tau_prev, tau, tab[(size_t)i0 * nf + L::RAD] * c.rfct,
+                         tab[(size_t)(i0 + 1) * nf + L::RAD] * c.rfct, c.toomuch,
+                         c.inv_srad2, status);
+  }
   int n;                                                       // number of integration points
   if (last < nl - 1) {
     const int dd = last + 1;                                   // appended zero-integrand point

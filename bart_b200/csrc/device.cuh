@@ -53,7 +53,7 @@ struct TabLayout {
 struct DevConfig {
   int nlayer, nspec, nwave, ntemp, ngmol, ncia, nang;
   int gms;                  // grid doubles per wavenumber sample (ngmol, padded to even when > 1)
-  int eclipse, transparent;
+  int eclipse, transparent, modlevel;
   const double *grid;
   const double *gtemp;
   const double *wn;

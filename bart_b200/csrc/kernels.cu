@@ -241,7 +241,7 @@ transit_tile_kernel(DevConfig c, const double *__restrict__ tabs, const double *
   const double wn4 = (wn * wn) * (wn * wn);
   double *tk = KEEP ? tau_keep + ((size_t)m * c.nwave + w) * nl : nullptr;
   // per-column state of phase C (threads 0..63)
-  double S = 0.0, f1 = 0.0, f2 = 0.0, tau = 0.0;
+  double S = 0.0, f1 = 0.0, f2 = 0.0, tau = 0.0, tau_prev = 0.0;
   int last = nl - 1;
   bool done = false;
   uint32_t wphase = 0;
@@ -337,6 +337,7 @@ transit_tile_kernel(DevConfig c, const double *__restrict__ tabs, const double *
           f2 = f1; f1 = fd;
         }
       }
+      tau_prev = jl > 0 ? tc[(size_t)(jl - 1) * kTrW] : tau;     // tau still holds depth d0-1's
       tau = tc[(size_t)jl * kTrW];
       if (jstop < dn) { last = d0 + jstop; done = true; }
     }
@@ -344,6 +345,16 @@ transit_tile_kernel(DevConfig c, const double *__restrict__ tabs, const double *
   }
   if (t >= kTrW || !valid) return;
   if (KEEP) last_keep[(size_t)m * c.nwave + w] = last;
+  if (c.modlevel == -1) {                                      // modulationm1 (slantpath.c:446-473)
+    const int i0 = last > 0 ? last - 1 : 0;
+    int st = 0;
+    const double r = modulation_m1(tau_prev, tau, s_tab[(size_t)i0 * nf + L::RAD] * c.rfct,
+                                   s_tab[(size_t)(i0 + 1) * nf + L::RAD] * c.rfct, c.toomuch,
+                                   c.inv_srad2, &st);
+    if (st) atomicOr(&status_col[m], st);
+    spectra[(size_t)m * c.nwave + w] = r;
+    return;
+  }
   // modulation1 (slantpath.c:350-436): same tail as transit_column
   int n;
   if (last < nl - 1) {

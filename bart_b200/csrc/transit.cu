@@ -397,7 +397,9 @@ static void do_init(int argc, char **argv) {
                             "not supported (BART always uses the atmosphere-file layers)", o.raddelt);
   if (o.taulevel != 1) fail("slantpath:: totaltau:: Level %i of detail has not been implemented to "
                             "compute optical depth.", o.taulevel);
-  if (o.modlevel != 1) fail("modlevel %d is not supported (only 1)", o.modlevel);
+  if (o.modlevel != 1 && o.modlevel != -1)          // slantpath.c:497-503
+    fail("slantpath:: modulationperwn:: Level %i of detail has not been implemented to compute "
+         "modulation.", o.modlevel);
   ensure_device();
 
   info(2, "--------------------------------------------------\n"
@@ -424,6 +426,7 @@ static void do_init(int argc, char **argv) {
   c.nlayer = nl; c.nspec = ns; c.nwave = nw;
   c.eclipse = o.solution == "eclipse";
   c.transparent = o.transparent ? 1 : 0;
+  c.modlevel = o.modlevel;
   c.pfct = G.atm.pfct; c.rfct = G.atm.rfct; c.gsurf = o.gsurf; c.p0 = o.refpress;
   c.toomuch = o.toomuch;
   upload(G.d_wn, G.wn); c.wn = G.d_wn.p;
@@ -793,6 +796,8 @@ void run_transit(double *re_input, int transint, double *transit_out, int transi
   if (status & REJ_TGRID) fail("A layer in the atmospheric model has a temperature outside the "
                                "opacity-grid temperature range [%g, %g] K.", G.og.temp.front(), G.og.temp.back());
   if (status & REJ_FEWPTS) fail("Condition failed, less than 3 items for radial integration.");
+  if (status & REJ_NOTOOMUCH) fail("Optical depth didn't reach limiting %g at some wavenumber.  Cannot "
+                                   "use critical radius technique (-1).", G.opt.toomuch);
   API_END_VOID
 }
 

@@ -91,6 +91,8 @@ int  bart_run_batch(const double *profiles, int nmodels, int n_in, double *spect
 #define BART_REJ_TCIA    2   /* outside a CIA table's range (src/crosssec.c:293-309)        */
 #define BART_REJ_SUMQ    4   /* sum of abundances > 1.001 (src/readatm.c:152-156)           */
 #define BART_REJ_FEWPTS  8   /* transit: fewer than 3 points for the modulation integral    */
+#define BART_REJ_NOTOOMUCH 64 /* transit, modlevel -1: tau never reached toomuch at some
+                                wavenumber (src/slantpath.c:308-316,458-460)                  */
 
 /* Per-model knobs for the batched calls (the reference's setters are per-process state that
  * BARTfunc.py sets before each run_transit, code/BARTfunc.py:350-360).  Any pointer may be

@@ -49,6 +49,7 @@ class OrcConfig(C.Structure):
         ("cloud_flag", C.c_int), ("cloudext", C.c_double), ("cloudtop", C.c_double),
         ("cloudbot", C.c_double),
         ("scat_flag", C.c_int), ("scat_logext", C.c_double),
+        ("modlevel", C.c_int),
     ]
 
 
@@ -243,6 +244,7 @@ class Oracle:
         c.nangle, c.angles_deg = len(self.angles), _d(self.angles)
         c.starrad_cm = float(cfg.get("starrad", 1.125)) * 6.957e10
         c.transparent = 0
+        c.modlevel = int(cfg.get("modlevel", 1))
         c.cloud_flag, c.cloudext, c.cloudtop, c.cloudbot = 0, 0.0, 0.0, 0.0
         if "cloudtop" in cfg:
             self.set_cloudtop(float(cfg["cloudtop"]), c)

@@ -234,6 +234,26 @@ double orc_totaltau1(double b, double *rad_all, double *ex_all, long nrad){
   return 2*res;
 }
 
+/* transit/src/slantpath.c:446-473 + pu/src/numerical.c:203-211 (interp_line): modlevel -1, the
+   radius where tau = toomuch by linear interpolation; -1 when toomuch was not reached (the
+   reference then exits, slantpath.c:308-316) */
+double orc_modulationm1(const double *tau, long last, double toomuch, const double *ipv_in,
+                        double ipfct, double srad){
+  long i, ini;
+  double ipv[2] = {0.0, 0.0};
+  if (tau[last] < toomuch) return -1;
+  ini = ++last - 2;
+  if (ini < 0) ini = 0;
+  for (i=ini; i<last; i++) ipv[i-ini] = ipv_in[i]*ipfct;
+  {
+    const double *x = tau + ini;
+    const double dx = x[1] - x[0];
+    const double m = (ipv[1] - ipv[0]) / dx;
+    const double muchrad = ipv[0] + (toomuch - x[0]) * m;
+    return muchrad * muchrad / (srad*srad);
+  }
+}
+
 /* transit/src/slantpath.c:350-436 */
 double orc_modulation1(const double *tau, long last, double toomuch, const double *ipv_in,
                        long ipn, double ipfct, double srad, int transparent){
@@ -457,8 +477,10 @@ int orc_forward(const orc_config *c, int eclipse, const double *input, double *s
     double *ipv = malloc(sizeof(double)*nl);
     for (i=0; i<nl; i++) ipv[i] = rad[nl-1-i];          /* makesample.c:564-574 */
     for (w=0; w<nw; w++)
-      spectrum[w] = orc_modulation1(tau+(size_t)w*nl, last[w], c->toomuch, ipv, nl, c->rfct,
-                                    c->starrad_cm, c->transparent);
+      spectrum[w] = c->modlevel == -1 ?
+        orc_modulationm1(tau+(size_t)w*nl, last[w], c->toomuch, ipv, c->rfct, c->starrad_cm) :
+        orc_modulation1(tau+(size_t)w*nl, last[w], c->toomuch, ipv, nl, c->rfct,
+                        c->starrad_cm, c->transparent);
     free(ipv);
   }
 

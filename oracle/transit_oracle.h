@@ -38,6 +38,7 @@ typedef struct {
   /* per-call knobs (set_cloudtop / set_scattering state)                               */
   int cloud_flag; double cloudext, cloudtop, cloudbot;
   int scat_flag;  double scat_logext;
+  int modlevel;             /* transit: 1 (modulation1) or -1 (modulationm1)            */
 } orc_config;
 
 /* Optional intermediates; any pointer may be NULL. */
@@ -67,6 +68,8 @@ void   orc_radpress(double g0, double p0, double r0, const double *temp, const d
 double orc_simps_path(const double *s, const double *y, int n);
 double orc_eclipsetau(const double *rad, double *ex, int nlayer, int rs);
 double orc_totaltau1(double b, double *rad, double *ex, long nrad);
+double orc_modulationm1(const double *tau, long last, double toomuch, const double *ipv,
+                        double ipfct, double srad);
 double orc_modulation1(const double *tau, long last, double toomuch, const double *ipv,
                        long ipn, double ipfct, double srad, int transparent);
 

@@ -28,6 +28,8 @@ CASES = {
     "demo_eclipse": (dict(shape="demo", solution="eclipse", seed=12345), 2, 95, {}),
     "demo_transit": (dict(shape="demo", solution="transit", seed=12345, refradius_km=95000.0),
                      2, 94, {"radius": 94000.0}),
+    "tiny_transit_m1": (dict(shape="tiny", solution="transit", seed=12346, refradius_km=95000.0,
+                             extra_cfg=["modlevel -1"]), 3, 91, {"radius": 94200.0}),
     "tiny_eclipse_3ang": (dict(shape="tiny", solution="eclipse", seed=4242,
                                extra_cfg=["raygrid 0 30 70"]), 2, 93, {}),
     "tiny_eclipse_t20": (dict(shape="tiny", solution="eclipse", seed=4243,

@@ -69,7 +69,7 @@ int emu_init(const char *cfg) {
           E->grid[(cell * g.nwave + w) * c.gms + m] = filegrid[(cell * g.nmol + m) * g.nwave + w];
     c.nlayer = E->atm.nlayer(); c.nspec = E->atm.nspec(); c.nwave = (int)E->wn.size();
     c.ntemp = (int)g.ntemp; c.ngmol = (int)g.nmol;
-    c.eclipse = o.solution == "eclipse"; c.transparent = o.transparent;
+    c.eclipse = o.solution == "eclipse"; c.transparent = o.transparent; c.modlevel = o.modlevel;
     c.grid = E->grid.data(); c.gtemp = g.temp.data(); c.wn = E->wn.data();
     c.press = E->atm.press.data(); c.mass = E->mol.mass.data(); c.pol = E->mol.pol.data();
     for (int m = 0; m < c.ngmol; m++)

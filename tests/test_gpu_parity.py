@@ -3,6 +3,7 @@
 (3) size-independent properties at the full BASELINE shapes.  Tolerance for spectra and band
 fluxes: 1e-6 relative in fp64 (BASELINE.json north star); `last[]` (the layer index where the
 optical depth exceeds toomuch) must be identical."""
+import os
 import numpy as np
 import pytest
 
@@ -131,6 +132,22 @@ def test_rejected_models_are_flagged(api, get_case):
     assert np.array_equal(spectra[0], spectra[3])
     with pytest.raises(api.BartError):                     # the reference exit()s; we raise
         tr.run_transit(batch[1])
+    tr.free_memory()
+
+
+def test_modlevel_m1_needs_toomuch(api, workdir):
+    """modlevel -1 (slantpath.c:446-473): a column whose optical depth never reaches toomuch makes
+    the reference exit (slantpath.c:308-316); here the model is flagged and -1-filled."""
+    from bart_b200 import synth
+    case = synth.make_case(os.path.join(workdir, "m1_thin"), shape="tiny", solution="transit",
+                           seed=12346, refradius_km=95000.0, extra_cfg=["modlevel -1"],
+                           overrides={"toomuch": 1e30})
+    models = synth.make_models(case, 2, seed=91, molfit=("CH4",))
+    tr = api.Transit(case["cfg"])
+    spectra, status = tr.run_batch(models)
+    assert (status & api.REJ_NOTOOMUCH).all() and (spectra == -1).all()
+    with pytest.raises(api.BartError):
+        tr.run_transit(models[0])
     tr.free_memory()
 
 
