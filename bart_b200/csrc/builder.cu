@@ -45,6 +45,20 @@ namespace bart {
                                 __FILE__, __LINE__, #call);                                \
   } while (0)
 
+struct DevBuf {           // grow-only device buffer
+  void *p = nullptr; size_t cap = 0;
+  template <class T> T *get(size_t n) {
+    const size_t bytes = std::max<size_t>(1, n) * sizeof(T);
+    if (bytes > cap) {
+      if (p) cudaFree(p);
+      cap = bytes + bytes / 4;
+      BCUDA(cudaMalloc(&p, cap));
+    }
+    return (T *)p;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
 constexpr int kMaxIso = 64;
 constexpr int kAccThreads = 128;
 
@@ -67,7 +81,7 @@ struct BuilderState {
   long long *d_gstart = nullptr;            // [ngroups+1]
   int *d_giown = nullptr, *d_gidwn = nullptr;
   short *d_giso = nullptr;
-  double *d_gwavn = nullptr, *d_gS = nullptr;
+  double *d_gwavn = nullptr;
   std::vector<long long> iso_gbeg;          // [niso+1] group range per isotope
   std::vector<int> h_iown;                  // per-line trace (leader bin, or -2-bin when co-added)
   // Voigt table
@@ -78,12 +92,11 @@ struct BuilderState {
   long long prof_total = 0;
   double *d_aDop = nullptr, *d_aLor = nullptr;
   long long *d_prof_off = nullptr, *d_prof_size = nullptr;
-  // per-layer state
-  double *d_density = nullptr;              // [nlayer][nspec] for the current temperature
-  double *d_kmax = nullptr;                 // [ngmol]
-  double *d_out = nullptr;                  // [nlayer][ngmol][nwave] for the current temperature
-  void *d_cellinfo = nullptr;
-  bool lines_loaded = false, profiles_ready = false;
+  // plane / cell work buffers (run_planes)
+  struct PlaneWork *work = nullptr;
+  DevBuf dens, out;                              // grid build: [cell][nspec], [cell][ngmol][nwave]
+  std::vector<std::vector<double>> zspline; // [niso] second derivatives of Z(T) (line-by-line mode)
+  bool lines_loaded = false, profiles_ready = false, grid_ready = false;
   // per-phase wall/device milliseconds (bart_builder_phase_ms)
   std::map<std::string, double> phase_ms;
 };
@@ -203,12 +216,25 @@ __global__ void line_index_kernel(const double *wl, long long n, double wn_lo, d
   idwn_out[i] = idwn;
 }
 
-// K6a: strongest individual line per output molecule at temperature T (extinction.c:400-427)
+// A PLANE is one temperature: per-isotope factors, the strongest line per output molecule, and
+// the ordered list of co-added groups that pass the weak-line cut at that temperature (the cut
+// depends on T only, so it is taken once per plane and every layer of the plane walks the short
+// list).  A CELL is one (plane, layer): densities -> widths -> one extinction row per output
+// molecule.  The grid build has one plane per grid temperature with nlayer cells each; the
+// line-by-line forward mode (tau.c:163-175,253-264 -> computemolext(permol=0)) has one plane per
+// (model, layer) with a single cell.
+
+// K6a: strongest individual line per output molecule at the plane's temperature
+// (extinction.c:400-427).  grid = (blocks, planes).
 __global__ void kmax_kernel(const double *wavn, const double *elow, const double *gf,
-                            const short *isoid, const unsigned char *inrange, long long n, double T,
-                            const double *iso_fac /*[niso] ratio*SIGCTE/(mass*Z)*/,
-                            const int *iso_gmol, unsigned long long *kmax_bits, int ngmol) {
+                            const short *isoid, const unsigned char *inrange, long long n,
+                            const double *plane_T, const double *plane_facfull /*[P][niso]*/, int niso,
+                            const int *iso_out, unsigned long long *kmax_bits /*[P][kMaxGridMol]*/,
+                            int nout) {
   __shared__ double s_max[kMaxGridMol];
+  const int p = blockIdx.y;
+  const double T = plane_T[p];
+  const double *iso_fac = plane_facfull + (size_t)p * niso;
   if (threadIdx.x < kMaxGridMol) s_max[threadIdx.x] = 0.0;
   __syncthreads();
   double loc[kMaxGridMol];
@@ -220,42 +246,139 @@ __global__ void kmax_kernel(const double *wavn, const double *elow, const double
     const int iso = isoid[i];
     const double pk = iso_fac[iso] * gf[i] * exp(-kEXPCTE * elow[i] / T) *
                       (1 - exp(-kEXPCTE * wavn[i] / T));
-    const int m = iso_gmol[iso];
+    const int m = iso_out[iso];
 #pragma unroll
     for (int q = 0; q < kMaxGridMol; q++) if (q == m) loc[q] = fmax(loc[q], pk);
   }
 #pragma unroll
   for (int m = 0; m < kMaxGridMol; m++)
-    if (m < ngmol && loc[m] > 0)
+    if (m < nout && loc[m] > 0)
       atomicMax((unsigned long long *)&s_max[m], (unsigned long long)__double_as_longlong(loc[m]));
   __syncthreads();
-  if (threadIdx.x < ngmol && s_max[threadIdx.x] > 0)
-    atomicMax(&kmax_bits[threadIdx.x], (unsigned long long)__double_as_longlong(s_max[threadIdx.x]));
+  if (threadIdx.x < nout && s_max[threadIdx.x] > 0)
+    atomicMax(&kmax_bits[(size_t)p * kMaxGridMol + threadIdx.x],
+              (unsigned long long)__double_as_longlong(s_max[threadIdx.x]));
 }
 
-// K6b: co-added group strength at temperature T (extinction.c:439-464), thread per group,
-// lines of a group summed in file order.
-__global__ void strength_kernel(const long long *gstart, const short *giso, const double *wavn,
-                                const double *elow, const double *gf, long long ngroups, double T,
-                                const double *iso_fac2 /*[niso] SIGCTE*ratio/(mass*Z)*/,
-                                double *gS) {
-  const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (g >= ngroups) return;
+// Co-added group strength at temperature T (extinction.c:439-464): lines of a group summed in
+// file order, then the isotope factor.
+__device__ __forceinline__ double group_strength(const long long *gstart, const double *wavn,
+                                                 const double *elow, const double *gf, long long g,
+                                                 double T, double fac) {
   const long long b = gstart[g], e = gstart[g + 1];
   double pk = 0.0;
   for (long long i = b; i < e; i++) {
     const double term = gf[i] * exp(-kEXPCTE * elow[i] / T) * (1 - exp(-kEXPCTE * wavn[i] / T));
     pk = (i == b) ? term : pk + term;
   }
-  gS[g] = pk * iso_fac2[giso[g]];
+  return pk * fac;
 }
 
-struct CellIso {          // per (layer, isotope) for the current temperature
+constexpr int kCompactThreads = 256;
+
+struct PlaneArgs {
+  const long long *gstart; const short *giso; const double *wavn, *elow, *gf;
+  long long ngroups;
+  const double *plane_T, *plane_fac2 /*[P][niso]*/, *kmax /*[P][kMaxGridMol]*/;
+  const int *iso_out;
+  int niso;
+  double ethresh;
+  int nblk;
+};
+
+// K6b pass 1: survivors of the weak-line cut (extinction.c:467-470) per block of 256 groups.
+__global__ void __launch_bounds__(kCompactThreads)
+strength_count_kernel(PlaneArgs a, int *blkcnt /*[P][nblk]*/) {
+  const int p = blockIdx.y;
+  const long long g = blockIdx.x * (long long)kCompactThreads + threadIdx.x;
+  bool alive = false;
+  if (g < a.ngroups) {
+    const int iso = a.giso[g];
+    const double S = group_strength(a.gstart, a.wavn, a.elow, a.gf, g, a.plane_T[p],
+                                    a.plane_fac2[(size_t)p * a.niso + iso]);
+    alive = !(S < a.ethresh * a.kmax[(size_t)p * kMaxGridMol + a.iso_out[iso]]);
+  }
+  const int cnt = __syncthreads_count(alive);
+  if (threadIdx.x == 0) blkcnt[(size_t)p * a.nblk + blockIdx.x] = cnt;
+}
+
+// exclusive scan of a plane's block counts (in place) and the plane total; block per plane
+__global__ void __launch_bounds__(1024)
+block_scan_kernel(int *blkcnt, int nblk, long long *total) {
+  __shared__ int s_warp[32];
+  __shared__ int s_carry;
+  int *v = blkcnt + (size_t)blockIdx.x * nblk;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int base = 0; base < nblk; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int x = i < nblk ? v[i] : 0;
+    int inc = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
+    if (lane == 31) s_warp[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+      int w = s_warp[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
+      s_warp[lane] = w;
+    }
+    __syncthreads();
+    const int carry = s_carry;
+    const int excl = carry + (wid > 0 ? s_warp[wid - 1] : 0) + inc - x;
+    if (i < nblk) v[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry = carry + s_warp[31];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) total[blockIdx.x] = s_carry;
+}
+
+// K6b pass 2: ordered compaction of the surviving groups of every plane into the pool, and the
+// per-isotope ranges of the compact list.
+__global__ void __launch_bounds__(kCompactThreads)
+strength_fill_kernel(PlaneArgs a, const int *blkoff /*[P][nblk]*/, const long long *plane_base,
+                     const int *giown, const int *gidwn, const double *gwavn,
+                     int *c_iown, int *c_idwn, double *c_wavn, double *c_S,
+                     long long *cisobeg /*[P][niso+1]*/) {
+  __shared__ int s_warp[kCompactThreads / 32];
+  const int p = blockIdx.y;
+  const long long g = blockIdx.x * (long long)kCompactThreads + threadIdx.x;
+  bool alive = false;
+  double S = 0.0;
+  int iso = 0;
+  if (g < a.ngroups) {
+    iso = a.giso[g];
+    S = group_strength(a.gstart, a.wavn, a.elow, a.gf, g, a.plane_T[p],
+                       a.plane_fac2[(size_t)p * a.niso + iso]);
+    alive = !(S < a.ethresh * a.kmax[(size_t)p * kMaxGridMol + a.iso_out[iso]]);
+  }
+  const unsigned bal = __ballot_sync(0xffffffffu, alive);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) s_warp[wid] = __popc(bal);
+  __syncthreads();
+  int pos = blkoff[(size_t)p * a.nblk + blockIdx.x] + __popc(bal & ((1u << lane) - 1u));
+  for (int w = 0; w < wid; w++) pos += s_warp[w];
+  if (g >= a.ngroups) return;
+  if (alive) {
+    const long long q = plane_base[p] + pos;
+    c_iown[q] = giown[g]; c_idwn[q] = gidwn[g]; c_wavn[q] = gwavn[g]; c_S[q] = S;
+  }
+  long long *cb = cisobeg + (size_t)p * (a.niso + 1);
+  const int prev = g > 0 ? a.giso[g - 1] : -1;
+  for (int i = prev + 1; i <= iso; i++) cb[i] = pos;
+  if (g == a.ngroups - 1)
+    for (int i = iso + 1; i <= a.niso; i++) cb[i] = pos + (alive ? 1 : 0);
+}
+
+struct CellIso {          // per (cell, isotope)
   double alphal, alphad;  // Lorentz width; Doppler width / wavenumber
   int ilor, idop0;        // table indices (idop0: at wn[0])
   int idop_carry;         // Doppler index used by lines below the re-pick threshold
-  int hwbins;             // max profile half-width in coarse bins (+2)
-  long long gsplit;       // first group (in the isotope's range) with alphad*wavn/alphal < 0.1
+  int hwbins;             // max profile half-width in coarse bins (+2) any group of the cell can have
+  long long gsplit;       // first compact entry (absolute) with alphad*wavn/alphal < 0.1
 };
 
 __device__ int nearest_dev(const double *a, double v, int lo, int hi) {
@@ -267,23 +390,36 @@ __device__ int nearest_dev(const double *a, double v, int lo, int hi) {
   return fabs(a[hi] - v) < fabs(a[lo] - v) ? hi : lo;
 }
 
-// K6c: widths and table indices per (layer, isotope) (extinction.c:365-396, 478-483).
-__global__ void widths_kernel(CellIso *cells, int nlayer, int niso, int nspec, double T,
-                              const double *density /*[nlayer][nspec]*/, const double *spec_mass,
-                              const double *spec_radius, const double *iso_mass, const int *iso_spec,
-                              const int *iso_gmol, const double *aDop, const double *aLor, int nDop,
-                              int nLor, const long long *prof_size, int osamp, double wn0,
-                              const long long *iso_gbeg, const double *gwavn, const double *gS,
-                              const double *kmax, double ethresh) {
-  const int r = blockIdx.x, i = threadIdx.x;
-  if (r >= nlayer || i >= niso) return;
+struct CellArgs {
+  const int *cell_plane;            // [ncell]
+  const double *cell_dens;          // [ncell][nspec] mass densities
+  const long long *cell_out;        // [ncell] offset (doubles) of the cell's [nout][nwave] block
+  const double *plane_T;
+  const long long *plane_base, *cisobeg;
+  const int *c_iown, *c_idwn; const double *c_wavn, *c_S;
+  int niso, nspec, nout, nwave, osamp, nDop, nLor;
+  const int *iso_spec, *iso_out;
+  const double *aDop, *aLor;
+  const long long *prof_off, *prof_size;
+  const float *pool;
+  double wn0, own_last, dwn;
+  int total_mode;                   // permol = 0: strengths times the isotope's species density
+};
+
+// K6c: widths and table indices per (cell, isotope) (extinction.c:365-396, 478-483).
+__global__ void widths_kernel(CellArgs a, CellIso *cells, const double *spec_mass,
+                              const double *spec_radius, const double *iso_mass) {
+  const int ci = blockIdx.x, i = threadIdx.x;
+  if (i >= a.niso) return;
+  const int p = a.cell_plane[ci];
+  const double T = a.plane_T[p];
+  const double *density = a.cell_dens + (size_t)ci * a.nspec;
   const double fdoppler = sqrt(2 * kKB * T / kAMU) * kSQRTLN2 / kLS;
   const double florentz = sqrt(2 * kKB * T / kPI / kAMU) / (kAMU * kLS);
   double al = 0.0;
-  for (int j = 0; j < nspec; j++) {
-    const double cs = spec_radius[j] + spec_radius[iso_spec[i]];
-    al += density[(size_t)r * nspec + j] / spec_mass[j] * cs * cs *
-          sqrt(1 / iso_mass[i] + 1 / spec_mass[j]);
+  for (int j = 0; j < a.nspec; j++) {
+    const double cs = spec_radius[j] + spec_radius[a.iso_spec[i]];
+    al += density[j] / spec_mass[j] * cs * cs * sqrt(1 / iso_mass[i] + 1 / spec_mass[j]);
   }
   al *= florentz;
   const double ad = fdoppler / sqrt(iso_mass[i]);
@@ -291,119 +427,164 @@ __global__ void widths_kernel(CellIso *cells, int nlayer, int niso, int nspec, d
   c.alphal = al; c.alphad = ad;
   // the reference searches with hi = nDop / nLor (one past the end, extinction.c:394-395);
   // clamped to the last valid entry here
-  c.idop0 = nearest_dev(aDop, ad * wn0, 0, nDop - 1);
-  c.ilor = nearest_dev(aLor, al, 0, nLor - 1);
+  c.idop0 = nearest_dev(a.aDop, ad * a.wn0, 0, a.nDop - 1);
+  c.ilor = nearest_dev(a.aLor, al, 0, a.nLor - 1);
   // lines are sorted by decreasing wavenumber inside an isotope, so "alphad*wavn/alphal >= 0.1"
-  // holds for a prefix of the isotope's groups
-  const long long gb = iso_gbeg[i], ge = iso_gbeg[i + 1];
+  // holds for a prefix of the isotope's (compact) groups
+  const long long base = a.plane_base[p];
+  const long long *cb = a.cisobeg + (size_t)p * (a.niso + 1);
+  const long long gb = base + cb[i], ge = base + cb[i + 1];
   long long lo = gb, hi = ge;
   while (lo < hi) {
     const long long mid = (lo + hi) >> 1;
-    if (ad * gwavn[mid] / al >= 1e-1) lo = mid + 1; else hi = mid;
+    if (ad * a.c_wavn[mid] / al >= 1e-1) lo = mid + 1; else hi = mid;
   }
   c.gsplit = lo;
   // the sequential loop keeps the Doppler index of the last line that was re-picked AND evaluated
-  // (weak lines `continue` before the re-pick, extinction.c:467-483)
-  int carry = c.idop0;
-  const double thr = ethresh * kmax[iso_gmol[i]];
-  for (long long g = lo - 1; g >= gb; g--)
-    if (!(gS[g] < thr)) { carry = nearest_dev(aDop, ad * gwavn[g], 0, nDop - 1); break; }
-  c.idop_carry = carry;
-  long long hw = 0;
-  for (int d = 0; d < nDop; d++) hw = max(hw, prof_size[(size_t)d * nLor + c.ilor]);
-  c.hwbins = (int)(hw / osamp) + 2;
-  cells[(size_t)r * niso + i] = c;
+  // (weak lines `continue` before the re-pick, extinction.c:467-483): the last compact entry of
+  // the prefix
+  c.idop_carry = lo > gb ? nearest_dev(a.aDop, ad * a.c_wavn[lo - 1], 0, a.nDop - 1) : c.idop0;
+  // widest profile any group of the cell can pick: Doppler indices between those of the two
+  // ends of the spectrum (nearest_dev is monotonic), or the carried one
+  const int dhi = nearest_dev(a.aDop, ad * a.own_last, 0, a.nDop - 1);
+  long long hw = a.prof_size[(size_t)c.idop_carry * a.nLor + c.ilor];
+  for (int d = c.idop0; d <= dhi; d++) hw = max(hw, a.prof_size[(size_t)d * a.nLor + c.ilor]);
+  c.hwbins = (int)(hw / a.osamp) + 2;
+  cells[(size_t)ci * a.niso + i] = c;
 }
 
-// K6d: gather-accumulate.  Block = (128-bin tile, layer); thread <-> coarse bin j.  For every
-// isotope the candidate groups (leaders whose coarse bin lies within the widest profile of the
-// tile) are staged 128 at a time into shared memory -- one group per thread: Doppler index,
-// profile pointer, bin range -- and then every thread walks the staged groups in line order,
-// adding S * profile[wnosamp*j - offset] when its bin is inside the group's range
-// (extinction.c:486-509).
+// K6d: accumulate.  CTA = (128-bin tile, cell), 4 warps.  For every isotope the candidate groups
+// (compact entries whose leader bin lies within the widest profile the tile can see) are dealt to
+// the warps in batches of 32, one group per lane: Doppler index, profile pointer, bin range
+// clipped to the tile (extinction.c:476-497).  A batch whose groups span few bins (the usual
+// case above ~1 bar: Doppler cores of 1-3 bins, ~1e3 lines per bin) is reduced LANE-PER-GROUP:
+// for each bin of the span every lane evaluates its own group's sample and a shuffle butterfly
+// sums the 32 values.  A batch that spans many bins (pressure-broadened layers) is walked
+// LANE-PER-BIN: the groups are staged in shared memory and each one is spread over the lanes,
+// bin = first + lane + 32 k.  Every warp adds into its own shared-memory row of 128 partial sums
+// (no atomics); the rows are combined in warp order when the output molecule changes.  The
+// result is deterministic and independent of how planes are batched; the order in which the
+// terms of a bin are added differs from the reference's line order (relative effect ~1e-16).
 struct StagedGroup {
   const float *prof;
   double S;
   int offset, ps2, minj, maxj;
 };
+constexpr int kAccWarps = kAccThreads / 32;
+constexpr int kNarrowSpan = 12;
 
 __global__ void __launch_bounds__(kAccThreads)
-accumulate_kernel(const CellIso *cells, int niso, int ngmol, int nwave, int osamp,
-                  const int *iso_gmol, const long long *iso_gbeg, const int *giown,
-                  const int *gidwn, const double *gwavn, const double *gS, const double *kmax,
-                  double ethresh, const double *aDop, int nDop, int nLor,
-                  const long long *prof_off, const long long *prof_size, const float *pool,
-                  double *out /*[nlayer][ngmol][nwave]*/, unsigned long long *neval) {
-  __shared__ StagedGroup s_g[kAccThreads];
+accumulate_kernel(CellArgs a, const CellIso *cells, double *out) {
+  __shared__ double s_acc[kAccWarps][kAccThreads];
+  __shared__ StagedGroup s_g[kAccWarps][32];
   __shared__ double s_aDop[128];
-  const int r = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ci = blockIdx.y;
   const int j0 = blockIdx.x * kAccThreads;
   const int j = j0 + threadIdx.x;
-  for (int k = threadIdx.x; k < nDop && k < 128; k += blockDim.x) s_aDop[k] = aDop[k];
+  const int jt_hi = min(j0 + kAccThreads - 1, a.nwave - 1);
+  const int p = a.cell_plane[ci];
+  const long long base0 = a.plane_base[p];
+  const long long *cb = a.cisobeg + (size_t)p * (a.niso + 1);
+  double *o = out + a.cell_out[ci];
+  for (int k = threadIdx.x; k < a.nDop && k < 128; k += blockDim.x) s_aDop[k] = a.aDop[k];
+#pragma unroll
+  for (int w = 0; w < kAccWarps; w++) s_acc[w][threadIdx.x] = 0.0;
   __syncthreads();
+  // isotopes of one molecule are contiguous (TLI database order); a molecule that re-appears
+  // continues from what was stored
+  auto flush = [&](int m) {
+    __syncthreads();
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < kAccWarps; w++) { v += s_acc[w][threadIdx.x]; s_acc[w][threadIdx.x] = 0.0; }
+    if (j < a.nwave) o[(size_t)m * a.nwave + j] += v;
+    __syncthreads();
+  };
   int cur_mol = -1;
-  double acc = 0.0;
-  unsigned long long my_eval = 0;
-  for (int iso = 0; iso < niso; iso++) {
-    const int m = iso_gmol[iso];
+  double *acc = s_acc[warp];
+  for (int iso = 0; iso < a.niso; iso++) {
+    const int m = a.iso_out[iso];
     if (m != cur_mol) {
-      if (cur_mol >= 0 && j < nwave) out[((size_t)r * ngmol + cur_mol) * nwave + j] = acc;
-      // isotopes of one molecule are contiguous (TLI database order); a molecule that re-appears
-      // continues from what was stored
-      acc = (j < nwave && m >= 0) ? out[((size_t)r * ngmol + m) * nwave + j] : 0.0;
+      if (cur_mol >= 0) flush(cur_mol);
       cur_mol = m;
     }
-    const CellIso c = cells[(size_t)r * niso + iso];
-    const long long gb = iso_gbeg[iso], ge = iso_gbeg[iso + 1];
+    const long long gb = base0 + cb[iso], ge = base0 + cb[iso + 1];
     if (gb == ge) continue;
-    // candidate range: leader coarse bins in [j0 - hw, j0 + 127 + hw]; gidwn is non-increasing
-    const int hi_bin = j0 + kAccThreads - 1 + c.hwbins, lo_bin = j0 - c.hwbins;
-    long long a = gb, b = ge;
-    while (a < b) { const long long mid = (a + b) >> 1; if (gidwn[mid] > hi_bin) a = mid + 1; else b = mid; }
-    const long long first = a;
-    b = ge;
-    while (a < b) { const long long mid = (a + b) >> 1; if (gidwn[mid] >= lo_bin) a = mid + 1; else b = mid; }
-    const long long last = a;                                   // exclusive
-    const double thr = ethresh * kmax[m];
-    for (long long base = first; base < last; base += kAccThreads) {
-      const long long g = base + threadIdx.x;
+    const CellIso c = cells[(size_t)ci * a.niso + iso];
+    const double dens = a.total_mode ? a.cell_dens[(size_t)ci * a.nspec + a.iso_spec[iso]] : 1.0;
+    // tile-local half-width: candidates of the cell-level window have wavenumbers inside it, so
+    // their Doppler indices lie between those of the window's ends
+    int hwb = c.hwbins;
+    {
+      double wlo = a.wn0 + (double)(j0 - c.hwbins - 1) * a.dwn;
+      double whi = a.wn0 + (double)(j0 + kAccThreads + c.hwbins + 1) * a.dwn;
+      if (wlo < a.wn0) wlo = a.wn0;
+      if (whi > a.own_last) whi = a.own_last;
+      const int dl = nearest_dev(s_aDop, c.alphad * wlo, 0, a.nDop - 1);
+      const int dh = nearest_dev(s_aDop, c.alphad * whi, 0, a.nDop - 1);
+      long long hw = a.prof_size[(size_t)c.idop_carry * a.nLor + c.ilor];
+      for (int d = dl; d <= dh; d++) hw = max(hw, a.prof_size[(size_t)d * a.nLor + c.ilor]);
+      hwb = min(hwb, (int)(hw / a.osamp) + 2);
+    }
+    // candidate range: leader coarse bins in [j0 - hw, j0 + 127 + hw]; idwn is non-increasing
+    const int hi_bin = j0 + kAccThreads - 1 + hwb, lo_bin = j0 - hwb;
+    long long x = gb, y = ge;
+    while (x < y) { const long long mid = (x + y) >> 1; if (a.c_idwn[mid] > hi_bin) x = mid + 1; else y = mid; }
+    const long long first = x;
+    y = ge;
+    while (x < y) { const long long mid = (x + y) >> 1; if (a.c_idwn[mid] >= lo_bin) x = mid + 1; else y = mid; }
+    const long long last = x;                                   // exclusive
+    for (long long base = first + 32 * warp; base < last; base += 32 * kAccWarps) {
+      const long long g = base + lane;
       StagedGroup sg;
-      sg.prof = nullptr; sg.S = 0.0; sg.offset = 0; sg.ps2 = -1; sg.minj = 1; sg.maxj = 0;
+      sg.prof = a.pool; sg.S = 0.0; sg.offset = 0; sg.ps2 = -1; sg.minj = (1 << 30); sg.maxj = -(1 << 30);
       if (g < last) {
-        const double S = gS[g];
-        if (!(S < thr)) {                                       // weak-line cut (467-470)
-          int idop = c.idop_carry;
-          if (g < c.gsplit) idop = nearest_dev(s_aDop, c.alphad * gwavn[g], 0, nDop - 1);
-          const size_t pi = (size_t)idop * nLor + c.ilor;
-          const int ps = (int)prof_size[pi];
-          const int iown = giown[g], idwn = gidwn[g];
-          const int subw = iown - idwn * osamp;
-          sg.offset = iown - ps;
-          sg.minj = idwn - (ps - subw) / osamp;
-          sg.maxj = idwn + (ps + subw) / osamp;
-          if (sg.minj < 0) sg.minj = 0;
-          if (sg.maxj >= nwave) sg.maxj = nwave - 1;
-          sg.ps2 = 2 * ps;
-          sg.prof = pool + prof_off[pi];
-          sg.S = S;
-          if (blockIdx.x == 0) my_eval++;                       // counted once per layer
-        }
+        int idop = c.idop_carry;
+        if (g < c.gsplit) idop = nearest_dev(s_aDop, c.alphad * a.c_wavn[g], 0, a.nDop - 1);
+        const size_t pi = (size_t)idop * a.nLor + c.ilor;
+        const int ps = (int)a.prof_size[pi];
+        const int iown = a.c_iown[g], idwn = a.c_idwn[g];
+        const int subw = iown - idwn * a.osamp;
+        sg.offset = iown - ps;
+        // bins whose profile index osamp*j - offset lies in [0, 2 ps] (extinction.c:486-509),
+        // clipped to the tile
+        int mn = idwn - (ps - subw) / a.osamp, mx = idwn + (ps + subw) / a.osamp;
+        while (a.osamp * mn - sg.offset < 0) mn++;
+        while (a.osamp * mx - sg.offset > 2 * ps) mx--;
+        sg.minj = max(mn, j0);
+        sg.maxj = min(mx, jt_hi);
+        if (sg.minj > sg.maxj) { sg.minj = (1 << 30); sg.maxj = -(1 << 30); }
+        sg.ps2 = 2 * ps;
+        sg.prof = a.pool + a.prof_off[pi];
+        sg.S = a.total_mode ? a.c_S[g] * dens : a.c_S[g];       // extinction.c:472-473
       }
-      __syncthreads();
-      s_g[threadIdx.x] = sg;
-      __syncthreads();
-      const int cnt = (int)min((long long)kAccThreads, last - base);
-      for (int q = 0; q < cnt; q++) {
-        const StagedGroup &t = s_g[q];
-        if (j >= t.minj && j <= t.maxj) {
-          const int bj = osamp * j - t.offset;
-          if (bj >= 0 && bj <= t.ps2) acc += t.S * (double)t.prof[bj];
+      const int lo = __reduce_min_sync(0xffffffffu, sg.minj);
+      const int hi = __reduce_max_sync(0xffffffffu, sg.maxj);
+      if (hi < lo) continue;
+      if (hi - lo < kNarrowSpan) {
+        for (int bb = lo; bb <= hi; bb++) {
+          double v = 0.0;
+          if (bb >= sg.minj && bb <= sg.maxj) v = sg.S * (double)sg.prof[a.osamp * bb - sg.offset];
+#pragma unroll
+          for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+          if (lane == 0) acc[bb - j0] += v;
         }
+        __syncwarp();
+      } else {
+        s_g[warp][lane] = sg;
+        __syncwarp();
+        const int cnt = (int)min((long long)32, last - base);
+        for (int q = 0; q < cnt; q++) {
+          const StagedGroup &t = s_g[warp][q];
+          for (int bb = t.minj + lane; bb <= t.maxj; bb += 32)
+            acc[bb - j0] += t.S * (double)t.prof[a.osamp * bb - t.offset];
+        }
+        __syncwarp();
       }
     }
   }
-  if (cur_mol >= 0 && j < nwave) out[((size_t)r * ngmol + cur_mol) * nwave + j] = acc;
-  if (neval && my_eval) atomicAdd(neval, my_eval);
+  if (cur_mol >= 0) flush(cur_mol);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -425,14 +606,6 @@ static void setup_static(BuilderState *b, const Options &o, const Atmosphere &a,
   b->dwn = o.wndelt;
   b->odwn = o.wndelt / o.wnosamp;                                  // owns.d / owns.o
   b->nowns = (long long)(b->nwave - 1) * o.wnosamp + 1;            // makesample1, makesample.c:93
-  b->temps = make_sampling(o.tlow, o.thigh, o.tempdelt, 1);        // maketempsample
-  b->ntemp = (int)b->temps.size();
-  if (b->temps.front() < t.tmin)
-    fail("The opacity file attempted to sample a temperature (%.1f K) below the lowest allowed TLI "
-         "temperature (%.1f K).", b->temps.front(), t.tmin);
-  if (b->temps.back() > t.tmax)
-    fail("The opacity file attempted to sample a temperature (%.1f K) beyond the highest allowed "
-         "TLI temperature (%.1f K).", b->temps.back(), t.tmax);
   b->niso = t.niso();
   if (b->niso > kMaxIso) fail("at most %d isotopes are supported", kMaxIso);
   // setimol (readlineinfo.c:249-278) and the molID list of calcopacity (opacity.c:353-361)
@@ -451,7 +624,18 @@ static void setup_static(BuilderState *b, const Options &o, const Atmosphere &a,
   }
   b->ngmol = (int)b->gmol_id.size();
   if (b->ngmol > kMaxGridMol) fail("at most %d line-list molecules are supported", kMaxGridMol);
-  // partition functions on the temperature grid (opacity.c:325-339)
+}
+
+// temperature grid of the opacity file and the partition functions on it (opacity.c:297-339)
+static void setup_grid_temps(BuilderState *b, const Options &o, const Tli &t) {
+  b->temps = make_sampling(o.tlow, o.thigh, o.tempdelt, 1);        // maketempsample
+  b->ntemp = (int)b->temps.size();
+  if (b->temps.front() < t.tmin)
+    fail("The opacity file attempted to sample a temperature (%.1f K) below the lowest allowed TLI "
+         "temperature (%.1f K).", b->temps.front(), t.tmin);
+  if (b->temps.back() > t.tmax)
+    fail("The opacity file attempted to sample a temperature (%.1f K) beyond the highest allowed "
+         "TLI temperature (%.1f K).", b->temps.back(), t.tmax);
   b->ziso.assign((size_t)b->niso * b->ntemp, 0.0);
   for (int i = 0; i < b->niso; i++) {
     const std::vector<double> &T = t.db[t.iso_db[i]].T;
@@ -461,6 +645,7 @@ static void setup_static(BuilderState *b, const Options &o, const Atmosphere &a,
       b->ziso[(size_t)i * b->ntemp + k] = spline_eval(z.data(), (long)T.size(), T.data(),
                                                       t.iso_Z[i].data(), b->temps[k]);
   }
+  b->grid_ready = true;
 }
 
 // calcprofiles (opacity.c:218-277) + getprofile (extinction.c:8-57)
@@ -625,122 +810,242 @@ static void load_lines(BuilderState *b, const Options &o, Tli &t, const std::vec
   b->d_giown = dev_upload(giown); b->d_gidwn = dev_upload(gidwn); b->d_giso = dev_upload(giso);
   b->d_gwavn = dev_upload(gwavn);
   b->d_c_wavn = dev_upload(c_wavn); b->d_c_elow = dev_upload(c_elow); b->d_c_gf = dev_upload(c_gf);
-  BCUDA(cudaMalloc((void **)&b->d_gS, std::max<long long>(1, b->ngroups) * 8));
   cudaFree(b->d_wl); b->d_wl = nullptr;     // wavelengths are no longer needed on the device
   b->lines_loaded = true;
 }
 
-// One temperature plane for all layers: out[layer][mol][wave] on the device.
-static void build_temperature(BuilderState *b, const Options &o, const Atmosphere &a,
-                              const Molecules &mol, const Tli &t, int it, cudaStream_t s,
-                              const int *d_iso_spec, const int *d_iso_gmol, const double *d_iso_mass,
-                              const double *d_spec_mass, const double *d_spec_radius,
-                              const long long *d_iso_gbeg, unsigned long long *d_neval) {
-  const double T = b->temps[it];
-  const int nl = b->nlayer, ns = b->nspec;
-  // densities: stateeqnford with number abundances (transit.h:58-69, opacity.c:390-394)
-  std::vector<double> dens((size_t)nl * ns);
-  for (int r = 0; r < nl; r++)
-    for (int j = 0; j < ns; j++) {
-      const double rho = kAMU * a.q[(size_t)j * nl + r] * (a.press[r] * a.pfct) / kKB / T;
-      dens[(size_t)r * ns + j] = rho * mol.mass[j];
+// ---------------------------------------------------------------------------------------
+// Plane / cell driver shared by the grid build and the line-by-line forward mode.
+struct PlaneWork {
+  DevBuf T, facfull, fac2, kmax, blk, total, base, cisobeg;           // per plane
+  DevBuf c_iown, c_idwn, c_wavn, c_S;                                  // compact pool
+  DevBuf cell_plane, cell_out, cellinfo;                               // per cell
+  DevBuf iso_spec, iso_out, iso_mass, spec_mass, spec_radius;          // static tables
+  bool statics = false;
+};
+
+static void upload_statics(BuilderState *b, const Molecules &mol, const Tli &t, bool total_mode,
+                           cudaStream_t s) {
+  PlaneWork &w = *b->work;
+  std::vector<int> iso_out = b->iso_gmol;
+  if (total_mode) std::fill(iso_out.begin(), iso_out.end(), 0);      // permol = 0: m stays 0
+  BCUDA(cudaMemcpyAsync(w.iso_spec.get<int>(b->niso), b->iso_spec.data(), b->niso * 4, cudaMemcpyHostToDevice, s));
+  BCUDA(cudaMemcpyAsync(w.iso_out.get<int>(b->niso), iso_out.data(), b->niso * 4, cudaMemcpyHostToDevice, s));
+  BCUDA(cudaMemcpyAsync(w.iso_mass.get<double>(b->niso), t.iso_mass.data(), b->niso * 8, cudaMemcpyHostToDevice, s));
+  BCUDA(cudaMemcpyAsync(w.spec_mass.get<double>(b->nspec), mol.mass.data(), b->nspec * 8, cudaMemcpyHostToDevice, s));
+  BCUDA(cudaMemcpyAsync(w.spec_radius.get<double>(b->nspec), mol.radius_cm.data(), b->nspec * 8, cudaMemcpyHostToDevice, s));
+  BCUDA(cudaStreamSynchronize(s));
+}
+
+// Runs nplanes planes / ncell cells.  plane_T[P]; plane_Z[P][niso] partition functions;
+// cell_plane[ncell] (non-decreasing); d_cell_dens[ncell][nspec] (device, mass densities);
+// cell_out[ncell] offsets (doubles) into d_out of each cell's [nout][nwave] block, nout = ngmol
+// (grid build) or 1 (total_mode).  Returns the number of evaluated (group, cell) pairs.
+static long long run_planes(BuilderState *b, const Options &o, const Molecules &mol, const Tli &t,
+                            int nplanes, const double *plane_T, const double *plane_Z, int ncell,
+                            const int *cell_plane, const double *d_cell_dens,
+                            const long long *cell_out, double *d_out, bool total_mode,
+                            cudaStream_t s) {
+  if (!b->work) b->work = new PlaneWork();
+  PlaneWork &w = *b->work;
+  upload_statics(b, mol, t, total_mode, s);
+  const int niso = b->niso, nout = total_mode ? 1 : b->ngmol;
+  const int nblk = (int)((b->ngroups + kCompactThreads - 1) / kCompactThreads);
+  // per-isotope factors: pass 1 (extinction.c:412-418) uses ratio*SIGCTE*.../mass/Z per line,
+  // pass 2 (464) SIGCTE*ratio/(mass*Z) per group
+  std::vector<double> facfull((size_t)nplanes * niso), fac2((size_t)nplanes * niso);
+  for (int p = 0; p < nplanes; p++)
+    for (int i = 0; i < niso; i++) {
+      const double Z = plane_Z[(size_t)p * niso + i];
+      facfull[(size_t)p * niso + i] = t.iso_ratio[i] * kSIGCTE / t.iso_mass[i] / Z;
+      fac2[(size_t)p * niso + i] = kSIGCTE * t.iso_ratio[i] / (t.iso_mass[i] * Z);
     }
-  BCUDA(cudaMemcpyAsync(b->d_density, dens.data(), dens.size() * 8, cudaMemcpyHostToDevice, s));
-  // per-isotope factors at this temperature: pass 1 (extinction.c:412-418) uses
-  // ratio*SIGCTE*...*/mass/Z per line, pass 2 (464) SIGCTE*ratio/(mass*Z) per group
-  std::vector<double> facfull(b->niso), fac2(b->niso);
-  for (int i = 0; i < b->niso; i++) {
-    const double Z = b->ziso[(size_t)i * b->ntemp + it];
-    facfull[i] = t.iso_ratio[i] * kSIGCTE / t.iso_mass[i] / Z;
-    fac2[i] = kSIGCTE * t.iso_ratio[i] / (t.iso_mass[i] * Z);
-  }
-  double *d_facfull = dev_upload(facfull), *d_fac2 = dev_upload(fac2);
-  BCUDA(cudaMemsetAsync(b->d_kmax, 0, kMaxGridMol * 8, s));
+  double *d_T = w.T.get<double>(nplanes), *d_facfull = w.facfull.get<double>(facfull.size()),
+         *d_fac2 = w.fac2.get<double>(fac2.size()), *d_kmax = w.kmax.get<double>((size_t)nplanes * kMaxGridMol);
+  int *d_blk = w.blk.get<int>((size_t)nplanes * std::max(1, nblk));
+  long long *d_total = w.total.get<long long>(nplanes), *d_base = w.base.get<long long>(nplanes),
+            *d_cisobeg = w.cisobeg.get<long long>((size_t)nplanes * (niso + 1));
+  BCUDA(cudaMemcpyAsync(d_T, plane_T, nplanes * 8, cudaMemcpyHostToDevice, s));
+  BCUDA(cudaMemcpyAsync(d_facfull, facfull.data(), facfull.size() * 8, cudaMemcpyHostToDevice, s));
+  BCUDA(cudaMemcpyAsync(d_fac2, fac2.data(), fac2.size() * 8, cudaMemcpyHostToDevice, s));
+  BCUDA(cudaMemsetAsync(d_kmax, 0, (size_t)nplanes * kMaxGridMol * 8, s));
+  BCUDA(cudaMemsetAsync(d_cisobeg, 0, (size_t)nplanes * (niso + 1) * 8, s));
+  BCUDA(cudaMemsetAsync(d_total, 0, (size_t)nplanes * 8, s));
+  const int *d_iso_out = (const int *)w.iso_out.p;
   if (b->nlines > 0) {
     PhaseTimer pt(b, "kmax", s);
-    kmax_kernel<<<148 * 4, 256, 0, s>>>(b->d_wavn, b->d_elow, b->d_gf, b->d_isoid, b->d_inrange, b->nlines,
-                                        T, d_facfull, d_iso_gmol, (unsigned long long *)b->d_kmax, b->ngmol);
+    const int nb = (int)std::min<long long>(148 * 4, (b->nlines + 255) / 256);
+    kmax_kernel<<<dim3(nb, nplanes), 256, 0, s>>>(b->d_wavn, b->d_elow, b->d_gf, b->d_isoid, b->d_inrange,
+                                                  b->nlines, d_T, d_facfull, niso, d_iso_out,
+                                                  (unsigned long long *)d_kmax, nout);
     BCUDA(cudaGetLastError());
   }
+  PlaneArgs pa;
+  pa.gstart = b->d_gstart; pa.giso = b->d_giso; pa.wavn = b->d_c_wavn; pa.elow = b->d_c_elow; pa.gf = b->d_c_gf;
+  pa.ngroups = b->ngroups; pa.plane_T = d_T; pa.plane_fac2 = d_fac2; pa.kmax = d_kmax; pa.iso_out = d_iso_out;
+  pa.niso = niso; pa.ethresh = o.ethreshold; pa.nblk = nblk;
+  std::vector<long long> total(nplanes, 0), base(nplanes, 0);
+  long long pool = 0;
   if (b->ngroups > 0) {
     PhaseTimer pt(b, "strength", s);
-    strength_kernel<<<(unsigned)((b->ngroups + 255) / 256), 256, 0, s>>>(
-        b->d_gstart, b->d_giso, b->d_c_wavn, b->d_c_elow, b->d_c_gf, b->ngroups, T, d_fac2, b->d_gS);
+    strength_count_kernel<<<dim3(nblk, nplanes), kCompactThreads, 0, s>>>(pa, d_blk);
+    block_scan_kernel<<<nplanes, 1024, 0, s>>>(d_blk, nblk, d_total);
+    BCUDA(cudaGetLastError());
+    BCUDA(cudaMemcpyAsync(total.data(), d_total, nplanes * 8, cudaMemcpyDeviceToHost, s));
+    BCUDA(cudaStreamSynchronize(s));
+    for (int p = 0; p < nplanes; p++) { base[p] = pool; pool += total[p]; }
+    BCUDA(cudaMemcpyAsync(d_base, base.data(), nplanes * 8, cudaMemcpyHostToDevice, s));
+    int *ci = w.c_iown.get<int>(pool), *cd = w.c_idwn.get<int>(pool);
+    double *cw = w.c_wavn.get<double>(pool), *cS = w.c_S.get<double>(pool);
+    strength_fill_kernel<<<dim3(nblk, nplanes), kCompactThreads, 0, s>>>(
+        pa, d_blk, d_base, b->d_giown, b->d_gidwn, b->d_gwavn, ci, cd, cw, cS, d_cisobeg);
+    BCUDA(cudaGetLastError());
+  } else {
+    BCUDA(cudaMemsetAsync(d_base, 0, nplanes * 8, s));
+    w.c_iown.get<int>(1); w.c_idwn.get<int>(1); w.c_wavn.get<double>(1); w.c_S.get<double>(1);
+  }
+  int *d_cell_plane = w.cell_plane.get<int>(ncell);
+  long long *d_cell_out = w.cell_out.get<long long>(ncell);
+  CellIso *cells = w.cellinfo.get<CellIso>((size_t)ncell * niso);
+  BCUDA(cudaMemcpyAsync(d_cell_plane, cell_plane, ncell * 4, cudaMemcpyHostToDevice, s));
+  BCUDA(cudaMemcpyAsync(d_cell_out, cell_out, ncell * 8, cudaMemcpyHostToDevice, s));
+  CellArgs ca;
+  ca.cell_plane = d_cell_plane; ca.cell_dens = d_cell_dens; ca.cell_out = d_cell_out;
+  ca.plane_T = d_T; ca.plane_base = d_base; ca.cisobeg = d_cisobeg;
+  ca.c_iown = (const int *)w.c_iown.p; ca.c_idwn = (const int *)w.c_idwn.p;
+  ca.c_wavn = (const double *)w.c_wavn.p; ca.c_S = (const double *)w.c_S.p;
+  ca.niso = niso; ca.nspec = b->nspec; ca.nout = nout; ca.nwave = b->nwave; ca.osamp = b->osamp;
+  ca.nDop = b->nDop; ca.nLor = b->nLor;
+  ca.iso_spec = (const int *)w.iso_spec.p; ca.iso_out = d_iso_out;
+  ca.aDop = b->d_aDop; ca.aLor = b->d_aLor; ca.prof_off = b->d_prof_off; ca.prof_size = b->d_prof_size;
+  ca.pool = b->d_prof;
+  ca.wn0 = b->wn_lo; ca.own_last = b->wn_lo + (double)(b->nowns - 1) * b->odwn; ca.dwn = b->dwn;
+  ca.total_mode = total_mode ? 1 : 0;
+  {
+    PhaseTimer pt(b, "widths", s);
+    widths_kernel<<<ncell, std::max(32, niso), 0, s>>>(ca, cells, (const double *)w.spec_mass.p,
+                                                       (const double *)w.spec_radius.p,
+                                                       (const double *)w.iso_mass.p);
     BCUDA(cudaGetLastError());
   }
-  CellIso *cells = (CellIso *)b->d_cellinfo;
   {
-  PhaseTimer pt(b, "widths", s);
-  widths_kernel<<<nl, std::max(32, b->niso), 0, s>>>(
-      cells, nl, b->niso, ns, T, b->d_density, d_spec_mass, d_spec_radius, d_iso_mass, d_iso_spec,
-      d_iso_gmol, b->d_aDop, b->d_aLor, b->nDop, b->nLor, b->d_prof_size, b->osamp, b->wn_lo,
-      d_iso_gbeg, b->d_gwavn, b->d_gS, b->d_kmax, o.ethreshold);
-  BCUDA(cudaGetLastError());
+    PhaseTimer pt(b, "accumulate", s);
+    const int ntile = (b->nwave + kAccThreads - 1) / kAccThreads;
+    for (int c0 = 0; c0 < ncell; c0 += 32768) {                  // gridDim.y limit
+      const int nc = std::min(32768, ncell - c0);
+      CellArgs cb = ca;
+      cb.cell_plane += c0; cb.cell_dens += (size_t)c0 * b->nspec; cb.cell_out += c0;
+      accumulate_kernel<<<dim3(ntile, nc), kAccThreads, 0, s>>>(cb, cells + (size_t)c0 * niso, d_out);
+    }
+    BCUDA(cudaGetLastError());
   }
-  PhaseTimer pt(b, "accumulate", s);
-  BCUDA(cudaMemsetAsync(b->d_out, 0, (size_t)nl * b->ngmol * b->nwave * 8, s));
-  dim3 grid((b->nwave + kAccThreads - 1) / kAccThreads, nl);
-  accumulate_kernel<<<grid, kAccThreads, 0, s>>>(
-      cells, b->niso, b->ngmol, b->nwave, b->osamp, d_iso_gmol, d_iso_gbeg, b->d_giown, b->d_gidwn,
-      b->d_gwavn, b->d_gS, b->d_kmax, o.ethreshold, b->d_aDop, b->nDop, b->nLor, b->d_prof_off,
-      b->d_prof_size, b->d_prof, b->d_out, d_neval);
-  BCUDA(cudaGetLastError());
   BCUDA(cudaStreamSynchronize(s));
-  cudaFree(d_fac2); cudaFree(d_facfull);
+  long long ne = 0;
+  for (int c = 0; c < ncell; c++) ne += total[cell_plane[c]];
+  return ne;
 }
 
 static void ensure_builder(BuilderState *&b, const Options &o, const Atmosphere &a,
                            const Molecules &m, Tli &t, const std::vector<double> &wn, cudaStream_t s) {
   if (!b) b = new BuilderState();
-  if (!t.present) fail("the opacity-grid builder needs a TLI line list (linedb)");
+  if (!t.present) fail("the line-by-line opacity calculation needs a TLI line list (linedb)");
   if (b->nwave == 0) setup_static(b, o, a, m, t, wn);
   build_profiles(b, o, s);
   load_lines(b, o, t, wn, s);
-  if (!b->d_density) {
-    BCUDA(cudaMalloc((void **)&b->d_density, (size_t)b->nlayer * b->nspec * 8));
-    BCUDA(cudaMalloc((void **)&b->d_kmax, kMaxGridMol * 8));
-    BCUDA(cudaMalloc((void **)&b->d_out, (size_t)b->nlayer * b->ngmol * b->nwave * 8));
-    BCUDA(cudaMalloc((void **)&b->d_cellinfo, (size_t)b->nlayer * b->niso * sizeof(CellIso)));
-  }
 }
 
 void builder_slice(BuilderState *&b, const Options &o, const Atmosphere &a, const Molecules &m,
                    Tli &t, const std::vector<double> &wn, cudaStream_t s, int t_begin, int t_end,
                    double *host_out) {
   ensure_builder(b, o, a, m, t, wn, s);
+  if (!b->grid_ready) setup_grid_temps(b, o, t);
   if (t_begin < 0 || t_end > b->ntemp || t_begin > t_end)
     fail("temperature slice [%d, %d) outside the grid of %d temperatures", t_begin, t_end, b->ntemp);
-  int *d_iso_spec = dev_upload(b->iso_spec), *d_iso_gmol = dev_upload(b->iso_gmol);
-  double *d_iso_mass = dev_upload(t.iso_mass), *d_spec_mass = dev_upload(m.mass),
-         *d_spec_radius = dev_upload(m.radius_cm);
-  long long *d_iso_gbeg = dev_upload(b->iso_gbeg);
-  unsigned long long *d_neval = nullptr;
-  BCUDA(cudaMalloc((void **)&d_neval, 8));
-  BCUDA(cudaMemset(d_neval, 0, 8));
-  const int nt = t_end - t_begin, nl = b->nlayer;
+  const int nt = t_end - t_begin, nl = b->nlayer, ns = b->nspec;
   const size_t plane = (size_t)b->ngmol * b->nwave;
-  std::vector<double> tmp((size_t)nl * plane);
-  for (int it = t_begin; it < t_end; it++) {
-    build_temperature(b, o, a, m, t, it, s, d_iso_spec, d_iso_gmol, d_iso_mass, d_spec_mass,
-                      d_spec_radius, d_iso_gbeg, d_neval);
+  // planes per batch: bounded by the device output buffer (2 GB) -- one plane is nl * plane doubles
+  const int pb = (int)std::max<size_t>(1, std::min<size_t>(16, ((size_t)2 << 30) / (nl * plane * 8)));
+  std::vector<double> tmp;
+  for (int it0 = t_begin; it0 < t_end; it0 += pb) {
+    const int np = std::min(pb, t_end - it0), nc = np * nl;
+    std::vector<double> pT(np), pZ((size_t)np * b->niso), dens((size_t)nc * ns);
+    std::vector<int> cplane(nc);
+    std::vector<long long> cout_(nc);
+    for (int p = 0; p < np; p++) {
+      const int it = it0 + p;
+      pT[p] = b->temps[it];
+      for (int i = 0; i < b->niso; i++) pZ[(size_t)p * b->niso + i] = b->ziso[(size_t)i * b->ntemp + it];
+      // densities: stateeqnford with number abundances (transit.h:58-69, opacity.c:390-394)
+      for (int r = 0; r < nl; r++) {
+        const int c = p * nl + r;
+        cplane[c] = p;
+        cout_[c] = (long long)c * (long long)plane;
+        for (int j = 0; j < ns; j++) {
+          const double rho = kAMU * a.q[(size_t)j * nl + r] * (a.press[r] * a.pfct) / kKB / pT[p];
+          dens[(size_t)c * ns + j] = rho * m.mass[j];
+        }
+      }
+    }
+    double *d_dens = b->dens.get<double>(dens.size());
+    double *d_out = b->out.get<double>((size_t)nc * plane);
+    BCUDA(cudaMemcpyAsync(d_dens, dens.data(), dens.size() * 8, cudaMemcpyHostToDevice, s));
+    BCUDA(cudaMemsetAsync(d_out, 0, (size_t)nc * plane * 8, s));
+    b->neval += run_planes(b, o, m, t, np, pT.data(), pZ.data(), nc, cplane.data(), d_dens,
+                           cout_.data(), d_out, false, s);
     auto td0 = std::chrono::steady_clock::now();
-    BCUDA(cudaMemcpy(tmp.data(), b->d_out, tmp.size() * 8, cudaMemcpyDeviceToHost));
-    for (int r = 0; r < nl; r++)
-      memcpy(host_out + ((size_t)r * nt + (it - t_begin)) * plane, tmp.data() + (size_t)r * plane, plane * 8);
+    tmp.resize((size_t)nc * plane);
+    BCUDA(cudaMemcpy(tmp.data(), d_out, tmp.size() * 8, cudaMemcpyDeviceToHost));
+    for (int p = 0; p < np; p++)
+      for (int r = 0; r < nl; r++)
+        memcpy(host_out + ((size_t)r * nt + (it0 + p - t_begin)) * plane,
+               tmp.data() + ((size_t)p * nl + r) * plane, plane * 8);
     b->phase_ms["d2h"] += std::chrono::duration<double, std::milli>(
         std::chrono::steady_clock::now() - td0).count();
   }
-  unsigned long long ne = 0;
-  BCUDA(cudaMemcpy(&ne, d_neval, 8, cudaMemcpyDeviceToHost));
-  b->neval += (long long)ne;
-  cudaFree(d_iso_spec); cudaFree(d_iso_gmol); cudaFree(d_iso_mass); cudaFree(d_spec_mass);
-  cudaFree(d_spec_radius); cudaFree(d_iso_gbeg); cudaFree(d_neval);
+}
+
+// Line-by-line forward mode: total molecular extinction (all isotopes collapsed, times the
+// species densities) of ncell (model, layer) cells at their own temperatures, written to
+// d_out + cell_out[c] (nwave doubles each).  tau.c:163-175,253-264 -> computemolext(permol=0).
+void builder_lbl_cells(BuilderState *&b, const Options &o, const Atmosphere &a, const Molecules &m,
+                       Tli &t, const std::vector<double> &wn, cudaStream_t s, int ncell,
+                       const double *cell_T, const double *d_cell_dens, const long long *cell_out,
+                       double *d_out) {
+  ensure_builder(b, o, a, m, t, wn, s);
+  if (b->zspline.empty()) {                 // second derivatives of Z_iso(T), makesample.c:534-544
+    b->zspline.resize(b->niso);
+    for (int i = 0; i < b->niso; i++) {
+      const std::vector<double> &T = t.db[t.iso_db[i]].T;
+      b->zspline[i].resize(T.size());
+      spline_second_derivs(T.data(), t.iso_Z[i].data(), (long)T.size(), b->zspline[i].data());
+    }
+  }
+  // bound the per-batch work arrays: block counters are nblk ints per plane
+  const long long nblk = std::max<long long>(1, (b->ngroups + kCompactThreads - 1) / kCompactThreads);
+  const int maxp = (int)std::max<long long>(1, std::min<long long>(16384, ((long long)1 << 28) / nblk));
+  std::vector<int> cplane;
+  std::vector<double> pZ;
+  for (int c0 = 0; c0 < ncell; c0 += maxp) {
+    const int nc = std::min(maxp, ncell - c0);
+    cplane.resize(nc); pZ.resize((size_t)nc * b->niso);
+    for (int c = 0; c < nc; c++) {
+      cplane[c] = c;
+      for (int i = 0; i < b->niso; i++) {
+        const std::vector<double> &T = t.db[t.iso_db[i]].T;
+        pZ[(size_t)c * b->niso + i] = spline_eval(b->zspline[i].data(), (long)T.size(), T.data(),
+                                                  t.iso_Z[i].data(), cell_T[c0 + c]);
+      }
+    }
+    b->neval += run_planes(b, o, m, t, nc, cell_T + c0, pZ.data(), nc, cplane.data(),
+                           d_cell_dens + (size_t)c0 * b->nspec, cell_out + c0, d_out, true, s);
+  }
 }
 
 void builder_run_and_write(BuilderState *&b, const Options &o, const Atmosphere &a,
                            const Molecules &m, Tli &t, const std::vector<double> &wn,
                            cudaStream_t s, const std::string &path) {
   ensure_builder(b, o, a, m, t, wn, s);
+  if (!b->grid_ready) setup_grid_temps(b, o, t);
   OpacityGrid g;
   g.nmol = b->ngmol; g.ntemp = b->ntemp; g.nlayer = b->nlayer; g.nwave = b->nwave;
   g.molid = b->gmol_id; g.temp = b->temps; g.wn = wn;
@@ -822,9 +1127,17 @@ void builder_free(BuilderState *b) {
   if (!b) return;
   void *ptrs[] = {b->d_wl, b->d_elow, b->d_gf, b->d_wavn, b->d_c_wavn, b->d_c_elow, b->d_c_gf,
                   b->d_isoid, b->d_iown, b->d_idwn, b->d_inrange, b->d_gstart, b->d_giown,
-                  b->d_gidwn, b->d_giso, b->d_gwavn, b->d_gS, b->d_prof, b->d_aDop, b->d_aLor,
-                  b->d_prof_off, b->d_prof_size, b->d_density, b->d_kmax, b->d_out, b->d_cellinfo};
+                  b->d_gidwn, b->d_giso, b->d_gwavn, b->d_prof, b->d_aDop, b->d_aLor,
+                  b->d_prof_off, b->d_prof_size, b->dens.p, b->out.p};
   for (void *p : ptrs) if (p) cudaFree(p);
+  if (b->work) {
+    PlaneWork &w = *b->work;
+    DevBuf *bufs[] = {&w.T, &w.facfull, &w.fac2, &w.kmax, &w.blk, &w.total, &w.base, &w.cisobeg,
+                      &w.c_iown, &w.c_idwn, &w.c_wavn, &w.c_S, &w.cell_plane, &w.cell_out, &w.cellinfo,
+                      &w.iso_spec, &w.iso_out, &w.iso_mass, &w.spec_mass, &w.spec_radius};
+    for (DevBuf *d : bufs) d->release();
+    delete b->work;
+  }
   delete b;
 }
 

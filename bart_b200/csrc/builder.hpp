@@ -17,6 +17,14 @@ void builder_run_and_write(BuilderState *&b, const Options &o, const Atmosphere 
 void builder_slice(BuilderState *&b, const Options &o, const Atmosphere &a, const Molecules &m,
                    Tli &t, const std::vector<double> &wn, cudaStream_t s, int t_begin, int t_end,
                    double *host_out);
+// Line-by-line forward mode (no opacity file; tau.c:163-175,253-264 -> computemolext(permol=0)):
+// total molecular extinction of ncell (model, layer) cells, each at its own temperature
+// cell_T[c] with mass densities d_cell_dens[c][nspec] (device), written to d_out + cell_out[c]
+// (nwave doubles per cell, device).
+void builder_lbl_cells(BuilderState *&b, const Options &o, const Atmosphere &a, const Molecules &m,
+                       Tli &t, const std::vector<double> &wn, cudaStream_t s, int ncell,
+                       const double *cell_T, const double *d_cell_dens, const long long *cell_out,
+                       double *d_out);
 long long builder_stats(BuilderState *b, long long *nlines, long long *ngroups, long long *neval);
 // milliseconds spent in a build phase so far: "voigt_table","line_index","grouping_host","kmax",
 // "strength","widths","accumulate","d2h"

@@ -369,8 +369,11 @@ static void ext_cloud(const orc_config *c, const double *press, double *e){
 }
 
 /* ------------------------------------------------------------------------------------ */
-int orc_forward(const orc_config *c, int eclipse, const double *input, double *spectrum,
-                orc_inter *inter){
+static int computemolext_impl(const orc_lbl *L, double temp, const double *density, const double *Z,
+                              double *k, long *trace_iown, long *counts, int permol);
+
+static int forward_impl(const orc_config *c, const orc_lbl_fwd *F, int eclipse, const double *input,
+                        double *spectrum, orc_inter *inter){
   const int nl = c->nlayer, ns = c->nspec, nw = c->nwave;
   int i, j, w, m;
   double *t_in = malloc(sizeof(double)*nl), *mm_in = malloc(sizeof(double)*nl);
@@ -406,7 +409,20 @@ int orc_forward(const orc_config *c, int eclipse, const double *input, double *s
 
   /* molecular extinction for every layer: extinction.c:534-581                            */
   double *e = calloc((size_t)nl*nw, sizeof(double));
-  for (i=0; i<nl; i++){
+  if (F){
+    /* no opacity file: tau.c:163-175,253-264 computes each layer line by line at the layer's own
+       temperature, with Z_iso(T) splined from the TLI tables (makesample.c:534-544)         */
+    const orc_lbl *L = F->lbl;
+    double *dl = malloc(sizeof(double)*ns), *Zl = malloc(sizeof(double)*L->niso);
+    for (i=0; i<nl; i++){
+      for (j=0; j<ns; j++) dl[j] = dens[(size_t)j*nl+i];
+      for (j=0; j<L->niso; j++)
+        orc_splinterp(F->iso_nt[j], F->iso_T[j], F->iso_Z[j], 1, temp+i, Zl+j);
+      computemolext_impl(L, temp[i], dl, Zl, e+(size_t)i*nw, NULL, NULL, 0);
+    }
+    free(dl); free(Zl);
+  }
+  for (i=0; i<nl && !F; i++){
     double T = temp[i];
     int it = orc_binsearchapprox(c->gtemp, T, 0, c->ntemp-1);
     /* the reference passes hi = Ntemp (one past the end); identical for T < gtemp[Ntemp-1] */
@@ -498,6 +514,16 @@ int orc_forward(const orc_config *c, int eclipse, const double *input, double *s
   free(dens); free(e_cs); free(e); free(tau); free(last); free(er); free(e_s); free(e_c);
   free(radw);
   return 0;
+}
+
+int orc_forward(const orc_config *c, int eclipse, const double *input, double *spectrum,
+                orc_inter *inter){
+  return forward_impl(c, NULL, eclipse, input, spectrum, inter);
+}
+
+int orc_forward_lbl(const orc_config *c, const orc_lbl_fwd *F, int eclipse, const double *input,
+                    double *spectrum, orc_inter *inter){
+  return forward_impl(c, F, eclipse, input, spectrum, inter);
 }
 
 /* ====================================================================================== */
@@ -592,19 +618,24 @@ long orc_profile_halfsize(double dwn, double dop, double lor, float ta, long now
   return nvgt/2;
 }
 
-/* transit/src/extinction.c:281-529 with permol = 1 (the opacity-grid call, opacity.c:397)  */
-int orc_computemolext(const orc_lbl *L, double temp, const double *density, const double *Z,
-                      double *k, long *trace_iown, long *counts){
+/* transit/src/extinction.c:281-529.  permol = 1 is the opacity-grid call (opacity.c:397):
+   one row per line-list molecule, no density factor.  permol = 0 is the line-by-line forward
+   call (tau.c:163-175,253-264): the species index m stays 0 for every isotope (extinction.c:
+   296,405-406,433-434), so there is ONE strongest-line reference across all molecules, every
+   profile lands in row 0, and each strength is multiplied by its species' density (472-473). */
+static int computemolext_impl(const orc_lbl *L, double temp, const double *density, const double *Z,
+                              double *k, long *trace_iown, long *counts, int permol){
   int niso = L->niso, i, j;
   long ln, nl = L->nlines, nwn = L->nwave;
   double dwn = L->dwn, odwn = L->dwn/L->osamp;
   double *alphal = calloc(niso, sizeof(double)), *alphad = calloc(niso, sizeof(double));
   int *idop = calloc(niso, sizeof(int)), *ilor = calloc(niso, sizeof(int));
-  double *kmax = calloc(L->ngmol, sizeof(double));
+  int nout = permol ? L->ngmol : 1;
+  double *kmax = calloc(nout, sizeof(double));
   long nadd = 0, nskip = 0, neval = 0;
   double own_last = L->wn_lo + (L->nowns-1)*odwn;   /* owns.v[onwn-1], makesample.c:97-104 */
   double wn0 = L->wn_lo;                            /* wn[0] */
-  memset(k, 0, sizeof(double)*(size_t)L->ngmol*nwn);
+  memset(k, 0, sizeof(double)*(size_t)nout*nwn);
 
   double fdoppler = sqrt(2*O_KB*temp/O_AMU)*O_SQRTLN2/O_LS;
   double florentz = sqrt(2*O_KB*temp/O_PI/O_AMU)/(O_AMU*O_LS);
@@ -624,7 +655,7 @@ int orc_computemolext(const orc_lbl *L, double temp, const double *density, cons
   for (ln=0; ln<nl; ln++){
     double wavn = 1.0/(L->wl_um[ln]*1e-4);
     i = L->isoid[ln];
-    int m = L->iso_gmol[i];
+    int m = permol ? L->iso_gmol[i] : 0;
     if (wavn < L->wn_lo || wavn > own_last) continue;
     double pk = L->iso_ratio[i]*O_SIGCTE*L->gf[ln]*exp(-O_EXPCTE*L->elow[ln]/temp)*
                 (1-exp(-O_EXPCTE*wavn/temp))/L->iso_mass[i]/Z[i];
@@ -634,7 +665,7 @@ int orc_computemolext(const orc_lbl *L, double temp, const double *density, cons
   for (ln=0; ln<nl; ln++){
     double wavn = 1.0/(L->wl_um[ln]*1e-4);
     i = L->isoid[ln];
-    int m = L->iso_gmol[i];
+    int m = permol ? L->iso_gmol[i] : 0;
     if (trace_iown) trace_iown[ln] = -1;
     if (wavn < L->wn_lo || wavn > own_last) continue;
     double pk = L->gf[ln]*exp(-O_EXPCTE*L->elow[ln]/temp)*(1-exp(-O_EXPCTE*wavn/temp));
@@ -653,6 +684,7 @@ int orc_computemolext(const orc_lbl *L, double temp, const double *density, cons
     }
     pk *= O_SIGCTE*L->iso_ratio[i]/(L->iso_mass[i]*Z[i]);
     if (pk < L->ethresh*kmax[m]){ nskip++; continue; }
+    if (!permol) pk *= density[L->iso_spec[i]];
     int idwn = (int)((wavn - L->wn_lo)/dwn);
     if (alphad[i]*wavn/alphal[i] >= 1e-1)
       idop[i] = orc_binsearchapprox(L->aDop, alphad[i]*wavn, 0, L->nDop-1);
@@ -673,6 +705,17 @@ int orc_computemolext(const orc_lbl *L, double temp, const double *density, cons
     neval++;
   }
   if (counts){ counts[0] = nadd; counts[1] = nskip; counts[2] = neval; }
+
   free(alphal); free(alphad); free(idop); free(ilor); free(kmax);
   return 0;
+}
+
+int orc_computemolext(const orc_lbl *L, double temp, const double *density, const double *Z,
+                      double *k, long *trace_iown, long *counts){
+  return computemolext_impl(L, temp, density, Z, k, trace_iown, counts, 1);
+}
+
+int orc_computemolext_total(const orc_lbl *L, double temp, const double *density, const double *Z,
+                            double *k, long *counts){
+  return computemolext_impl(L, temp, density, Z, k, NULL, counts, 0);
 }

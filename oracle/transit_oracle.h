@@ -110,6 +110,21 @@ int orc_computemolext(const orc_lbl *L, double temp, const double *density, cons
                       double *k /*[ngmol][nwave]*/, long *trace_iown /*[nlines] or NULL*/,
                       long *counts /*[3] nadd,nskip,neval or NULL*/);
 
+/* permol = 0 (line-by-line forward mode): k[nwave], densities folded in */
+int orc_computemolext_total(const orc_lbl *L, double temp, const double *density, const double *Z,
+                            double *k /*[nwave]*/, long *counts);
+
+/* forward model without an opacity file (tau.c:163-175,253-264): the grid fields of orc_config
+   are ignored; molecular extinction comes from computemolext(permol=0) per layer */
+typedef struct {
+  const orc_lbl *lbl;
+  const int *iso_nt;             /* [niso] temperature nodes of the isotope's database   */
+  const double *const *iso_T;    /* [niso][nt]                                          */
+  const double *const *iso_Z;    /* [niso][nt] partition function                       */
+} orc_lbl_fwd;
+int orc_forward_lbl(const orc_config *cfg, const orc_lbl_fwd *F, int eclipse, const double *input,
+                    double *spectrum, orc_inter *inter);
+
 #ifdef __cplusplus
 }
 #endif
