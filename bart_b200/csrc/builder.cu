@@ -159,6 +159,7 @@ struct ProfJob {          // one unique profile
   int nwn;                // 2*halfsize+1
   int ipo;                // fine intervals per bin (1 => adjacent average / quick)
   int quick;
+  int osamp, K;           // pool layout: sample i of the profile is stored at (i % osamp) * K + i / osamp
   double dint, dwn_half, alphaL, alphaD;
 };
 
@@ -189,7 +190,9 @@ __global__ void voigt_table_kernel(const ProfJob *jobs, float *pool) {
     acc += sample(base) + sample(base + jb.ipo);
     out = (float)(acc / (jb.ipo * 3.0));
   }
-  pool[jb.off + k] = out;
+  // phase-major ("transposed") storage: the samples one line adds to consecutive coarse bins
+  // (stride osamp in the reference's array, extinction.c:499-507) are contiguous here
+  pool[jb.off + (long long)(k % jb.osamp) * jb.K + k / jb.osamp] = out;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -466,14 +469,17 @@ __global__ void widths_kernel(CellArgs a, CellIso *cells, const double *spec_mas
 // result is deterministic and independent of how planes are batched; the order in which the
 // terms of a bin are added differs from the reference's line order (relative effect ~1e-16).
 struct StagedGroup {
-  const float *prof;
+  const float *prof;      // prof[j] is the sample this group adds to coarse bin j
   double S;
-  int offset, ps2, minj, maxj;
+  int minj, maxj;         // bin range clipped to the tile (empty: minj > maxj)
+  int pad0, pad1;
 };
-constexpr int kAccWarps = kAccThreads / 32;
+constexpr int kAccWarps = 8;
+constexpr int kAccCta = 32 * kAccWarps;
 constexpr int kNarrowSpan = 12;
+constexpr int kBinsPerLane = kAccThreads / 32;
 
-__global__ void __launch_bounds__(kAccThreads)
+__global__ void __launch_bounds__(kAccCta)
 accumulate_kernel(CellArgs a, const CellIso *cells, double *out) {
   __shared__ double s_acc[kAccWarps][kAccThreads];
   __shared__ StagedGroup s_g[kAccWarps][32];
@@ -481,28 +487,34 @@ accumulate_kernel(CellArgs a, const CellIso *cells, double *out) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int ci = blockIdx.y;
   const int j0 = blockIdx.x * kAccThreads;
-  const int j = j0 + threadIdx.x;
   const int jt_hi = min(j0 + kAccThreads - 1, a.nwave - 1);
   const int p = a.cell_plane[ci];
   const long long base0 = a.plane_base[p];
   const long long *cb = a.cisobeg + (size_t)p * (a.niso + 1);
   double *o = out + a.cell_out[ci];
   for (int k = threadIdx.x; k < a.nDop && k < 128; k += blockDim.x) s_aDop[k] = a.aDop[k];
-#pragma unroll
-  for (int w = 0; w < kAccWarps; w++) s_acc[w][threadIdx.x] = 0.0;
+  for (int k = threadIdx.x; k < kAccWarps * kAccThreads; k += blockDim.x) (&s_acc[0][0])[k] = 0.0;
   __syncthreads();
+  double *acc = s_acc[warp];
+  double r[kBinsPerLane];                  // lane-per-bin partial sums of bins j0 + lane + 32 k
+#pragma unroll
+  for (int k = 0; k < kBinsPerLane; k++) r[k] = 0.0;
   // isotopes of one molecule are contiguous (TLI database order); a molecule that re-appears
   // continues from what was stored
   auto flush = [&](int m) {
-    __syncthreads();
-    double v = 0.0;
 #pragma unroll
-    for (int w = 0; w < kAccWarps; w++) { v += s_acc[w][threadIdx.x]; s_acc[w][threadIdx.x] = 0.0; }
-    if (j < a.nwave) o[(size_t)m * a.nwave + j] += v;
+    for (int k = 0; k < kBinsPerLane; k++) { acc[lane + 32 * k] += r[k]; r[k] = 0.0; }
+    __syncthreads();
+    if (threadIdx.x < kAccThreads) {
+      double v = 0.0;
+#pragma unroll
+      for (int w = 0; w < kAccWarps; w++) { v += s_acc[w][threadIdx.x]; s_acc[w][threadIdx.x] = 0.0; }
+      const int j = j0 + threadIdx.x;
+      if (j < a.nwave) o[(size_t)m * a.nwave + j] += v;
+    }
     __syncthreads();
   };
   int cur_mol = -1;
-  double *acc = s_acc[warp];
   for (int iso = 0; iso < a.niso; iso++) {
     const int m = a.iso_out[iso];
     if (m != cur_mol) {
@@ -538,7 +550,7 @@ accumulate_kernel(CellArgs a, const CellIso *cells, double *out) {
     for (long long base = first + 32 * warp; base < last; base += 32 * kAccWarps) {
       const long long g = base + lane;
       StagedGroup sg;
-      sg.prof = a.pool; sg.S = 0.0; sg.offset = 0; sg.ps2 = -1; sg.minj = (1 << 30); sg.maxj = -(1 << 30);
+      sg.prof = a.pool; sg.S = 0.0; sg.minj = (1 << 30); sg.maxj = -(1 << 30); sg.pad0 = sg.pad1 = 0;
       if (g < last) {
         int idop = c.idop_carry;
         if (g < c.gsplit) idop = nearest_dev(s_aDop, c.alphad * a.c_wavn[g], 0, a.nDop - 1);
@@ -546,17 +558,18 @@ accumulate_kernel(CellArgs a, const CellIso *cells, double *out) {
         const int ps = (int)a.prof_size[pi];
         const int iown = a.c_iown[g], idwn = a.c_idwn[g];
         const int subw = iown - idwn * a.osamp;
-        sg.offset = iown - ps;
-        // bins whose profile index osamp*j - offset lies in [0, 2 ps] (extinction.c:486-509),
-        // clipped to the tile
+        const int offset = iown - ps;
+        // bins whose profile index osamp*j - offset lies in [0, 2 ps] (extinction.c:486-509)
         int mn = idwn - (ps - subw) / a.osamp, mx = idwn + (ps + subw) / a.osamp;
-        while (a.osamp * mn - sg.offset < 0) mn++;
-        while (a.osamp * mx - sg.offset > 2 * ps) mx--;
+        while (a.osamp * mn - offset < 0) mn++;
+        while (a.osamp * mx - offset > 2 * ps) mx--;
+        // phase-major profile storage: index = phase * K + k, osamp*j - offset = k*osamp + phase
+        const int bj0 = a.osamp * mn - offset;
+        const int K = (2 * ps) / a.osamp + 1;
+        sg.prof = a.pool + a.prof_off[pi] + (long long)(bj0 % a.osamp) * K + (bj0 / a.osamp - mn);
         sg.minj = max(mn, j0);
         sg.maxj = min(mx, jt_hi);
         if (sg.minj > sg.maxj) { sg.minj = (1 << 30); sg.maxj = -(1 << 30); }
-        sg.ps2 = 2 * ps;
-        sg.prof = a.pool + a.prof_off[pi];
         sg.S = a.total_mode ? a.c_S[g] * dens : a.c_S[g];       // extinction.c:472-473
       }
       const int lo = __reduce_min_sync(0xffffffffu, sg.minj);
@@ -565,22 +578,25 @@ accumulate_kernel(CellArgs a, const CellIso *cells, double *out) {
       if (hi - lo < kNarrowSpan) {
         for (int bb = lo; bb <= hi; bb++) {
           double v = 0.0;
-          if (bb >= sg.minj && bb <= sg.maxj) v = sg.S * (double)sg.prof[a.osamp * bb - sg.offset];
+          if (bb >= sg.minj && bb <= sg.maxj) v = sg.S * (double)sg.prof[bb];
 #pragma unroll
           for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
           if (lane == 0) acc[bb - j0] += v;
         }
-        __syncwarp();
       } else {
+        __syncwarp();
         s_g[warp][lane] = sg;
         __syncwarp();
         const int cnt = (int)min((long long)32, last - base);
+#pragma unroll 4
         for (int q = 0; q < cnt; q++) {
-          const StagedGroup &t = s_g[warp][q];
-          for (int bb = t.minj + lane; bb <= t.maxj; bb += 32)
-            acc[bb - j0] += t.S * (double)t.prof[a.osamp * bb - t.offset];
+          const StagedGroup t = s_g[warp][q];
+#pragma unroll
+          for (int k = 0; k < kBinsPerLane; k++) {
+            const int bb = j0 + lane + 32 * k;
+            if (bb >= t.minj && bb <= t.maxj) r[k] += t.S * (double)t.prof[bb];
+          }
         }
-        __syncwarp();
       }
     }
   }
@@ -683,6 +699,7 @@ static void build_profiles(BuilderState *b, const Options &o, cudaStream_t s) {
       if (nvgt > 2 * b->nowns) nvgt = 2 * (int)b->nowns + 1;
       ProfJob jb;
       jb.off = total; jb.nwn = nvgt;
+      jb.osamp = b->osamp; jb.K = (nvgt - 1) / b->osamp + 1;
       jb.alphaL = lor; jb.alphaD = dop;
       jb.dwn_half = dwn * (long)(nvgt / 2);
       jb.quick = nvgt > 99999 ? 1 : 0;                            // _voigt_maxelements
@@ -699,11 +716,12 @@ static void build_profiles(BuilderState *b, const Options &o, cudaStream_t s) {
       }
       b->prof_off[p] = total;
       b->prof_size[p] = nvgt / 2;
-      total += nvgt;
+      total += (long long)jb.osamp * jb.K;
       jobs.push_back(jb);
     }
   b->prof_total = total;
   BCUDA(cudaMalloc((void **)&b->d_prof, std::max<long long>(1, total) * sizeof(float)));
+  BCUDA(cudaMemsetAsync(b->d_prof, 0, std::max<long long>(1, total) * sizeof(float), s));
   // series coefficients 1/(n!(2n+1)) (the table of voigt.c:47-108)
   double ferf[64];
   long double fac = 1.0L;
@@ -935,7 +953,7 @@ static long long run_planes(BuilderState *b, const Options &o, const Molecules &
       const int nc = std::min(32768, ncell - c0);
       CellArgs cb = ca;
       cb.cell_plane += c0; cb.cell_dens += (size_t)c0 * b->nspec; cb.cell_out += c0;
-      accumulate_kernel<<<dim3(ntile, nc), kAccThreads, 0, s>>>(cb, cells + (size_t)c0 * niso, d_out);
+      accumulate_kernel<<<dim3(ntile, nc), kAccCta, 0, s>>>(cb, cells + (size_t)c0 * niso, d_out);
     }
     BCUDA(cudaGetLastError());
   }
@@ -1118,7 +1136,10 @@ int builder_profile(BuilderState *b, int idop, int ilor, float *out, long long c
   if (halfsize) *halfsize = b->prof_size[p];
   if (out) {
     if (capacity < n) fail("profile buffer too small (%lld needed)", n);
-    BCUDA(cudaMemcpy(out, b->d_prof + b->prof_off[p], n * sizeof(float), cudaMemcpyDeviceToHost));
+    const long long K = (n - 1) / b->osamp + 1;
+    std::vector<float> tr((size_t)b->osamp * K);
+    BCUDA(cudaMemcpy(tr.data(), b->d_prof + b->prof_off[p], tr.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    for (long long i = 0; i < n; i++) out[i] = tr[(size_t)(i % b->osamp) * K + i / b->osamp];
   }
   return 0;
 }
