@@ -321,7 +321,8 @@ BART_HD int bracket(const double *x, int n, double v) {
 // written as one record (layout: TabLayout).  temp/radius are indexed by layer (bottom -> top);
 // rho[j*rho_stride + layer].
 BART_HD int prep_table_row(const DevConfig &c, const KnobVals &kv, int d, const double *temp,
-                           const double *rho, int rho_stride, const double *radius, double *tab) {
+                           const double *rho, int rho_stride, const double *radius, double *tab,
+                           int model = 0) {
   const TabLayout &L = c.lay;
   const int nl = c.nlayer;
   const int l = nl - 1 - d;
@@ -339,7 +340,14 @@ BART_HD int prep_table_row(const DevConfig &c, const KnobVals &kv, int d, const 
   const int it = bracket(c.gtemp, c.ntemp, T);
   const double t0 = c.gtemp[it], t1 = c.gtemp[it + 1];
   row[L.GOFF] = bits_to_double((((long long)l * c.ntemp + it) * c.gms) * (long long)c.nwave * 8);
-  for (int m = 0; m < c.ngmol; m++) {
+  if (c.lbl) {
+    // line-by-line mode: the "grid" is ext[model][layer][wave] with the densities folded in
+    // (computemolext permol = 0, extinction.c:472-473); gtemp = TLI range (makesample.c:488-503)
+    row[L.GOFF] = bits_to_double(((long long)model * nl + l) * (long long)c.nwave * 8);
+    row[L.W] = 1.0;
+    row[L.W + 1] = 0.0;
+  }
+  for (int m = 0; m < (c.lbl ? 0 : c.ngmol); m++) {
     const double r = rho[(size_t)c.gmol_spec[m] * rho_stride + l];
     row[L.W + 2 * m] = r * (t1 - T) / (t1 - t0);
     row[L.W + 2 * m + 1] = r * (T - t0) / (t1 - t0);

@@ -80,6 +80,12 @@ struct DevConfig {
   // grid, so exp(c2 wn'/T) = exp(c2 wn/T) * exp(planck_step/T), planck_step = (hc/k) planck_cols dwn
   int planck_cols;          // 0 = no chaining
   double planck_step;
+  // line-by-line mode (no opacity file, tau.c:163-175): `grid` is the per-batch buffer
+  // ext[model][layer][wave] filled by the builder kernels (one "molecule" with weight 1, second
+  // bracket weight 0); gtemp = {TLI tmin, TLI tmax}; atm_prep also stores the mass densities
+  int lbl;
+  int lbl_model0;           // global index of the launch's first model
+  double *lbl_dens;         // [model][layer][nspec]
   TabLayout lay;
 };
 

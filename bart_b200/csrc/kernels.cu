@@ -123,7 +123,12 @@ atm_prep_kernel(DevConfig c, Knobs knobs, const double *__restrict__ profiles, i
   double *tab = tabs + (size_t)m * c.lay.stride();
   st = 0;
   for (int d = threadIdx.x; d < nl; d += blockDim.x)
-    st |= prep_table_row(c, kv, d, in, s_rho, nl, s_rad, tab);
+    st |= prep_table_row(c, kv, d, in, s_rho, nl, s_rad, tab, c.lbl_model0 + m);
+  if (c.lbl)
+    for (int i = threadIdx.x; i < nl * c.nspec; i += blockDim.x) {
+      const int l = i / c.nspec, j = i - l * c.nspec;
+      c.lbl_dens[((size_t)(c.lbl_model0 + m) * nl + l) * c.nspec + j] = s_rho[(size_t)j * nl + l];
+    }
   if (st) atomicOr(&s_status, st);
   __syncthreads();
   if (threadIdx.x == 0) status[m] = s_status;

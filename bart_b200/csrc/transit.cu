@@ -141,6 +141,11 @@ struct State {
   int rank = 0, world = 1;
   // builder
   BuilderState *builder = nullptr;
+  // line-by-line forward mode (no opacity file)
+  bool lbl = false;
+  DevBuf<double> d_lbl_ext, d_lbl_dens;
+  std::vector<double> h_lbl_T;
+  std::vector<int> h_lbl_status;
   // input converter (retrieval.hpp)
   ConvConfig conv{};
   DevBuf<double> d_cpress, d_cbase, d_cratio, d_cparams;
@@ -367,6 +372,7 @@ static void reset_state() {
   G.d_fstart.release(); G.d_fcount.release(); G.d_foffset.release(); G.d_fweight.release();
   G.d_fstar.release(); G.d_flush.release();
   if (G.builder) { builder_free(G.builder); G.builder = nullptr; }
+  G.d_lbl_ext.release(); G.d_lbl_dens.release(); G.lbl = false;
   G.d_cpress.release(); G.d_cbase.release(); G.d_cratio.release(); G.d_cparams.release();
   G.d_cstatus.release(); G.d_mcband.release(); G.d_mcgather.release();
   for (auto &b : G.d_mcd) b.release();
@@ -480,9 +486,21 @@ static void do_init(int argc, char **argv) {
     struct stat st;
     have_file = stat(o.opacityfile.c_str(), &st) == 0 && S_ISREG(st.st_mode);
   }
-  if (o.opacityfile.empty())
-    fail("No opacity file given: the on-the-fly line-by-line mode of the reference (tau.c:163-175) "
-         "is not part of this library yet; set 'opacityfile' (it is built when missing).");
+  G.lbl = false;
+  if (o.opacityfile.empty()) {
+    // opacity.c:28-36: no opacity file -> Voigt profiles only; tau() computes every layer line by
+    // line at the layer's own temperature (tau.c:163-175,253-264)
+    if (!G.tli.present) fail("Neither an opacity file nor a TLI line list (linedb) was given.");
+    if (o.justOpacity) fail("--justOpacity needs 'opacityfile'.");
+    info(2, "No opacity file: line-by-line extinction at every run_transit call.\n");
+    G.lbl = true;
+    builder_lbl_cells(G.builder, G.opt, G.atm, G.mol, G.tli, G.wn, G.stream, 0, nullptr, nullptr,
+                      nullptr, nullptr);               // Voigt table + line list on the device
+    c.lbl = 1; c.ntemp = 2; c.ngmol = 1; c.gms = 1;
+    upload(G.d_gtemp, std::vector<double>{G.tli.tmin, G.tli.tmax});
+    c.gtemp = G.d_gtemp.p;
+    c.gmol_spec[0] = 0;
+  } else {
   if (!have_file) {
     if (!G.tli.present) fail("Cannot build the opacity grid '%s': no TLI line list (linedb) given.", o.opacityfile.c_str());
     info(2, "Calculating new grid of opacities: '%s'.\n", o.opacityfile.c_str());
@@ -495,6 +513,7 @@ static void do_init(int argc, char **argv) {
   if (!read_opacity_header(o.opacityfile, G.og)) fail("Opening opacity file failed.");
   load_grid_to_device(o.opacityfile);
   finish_grid_config();
+  }
 
   // readcs(): crosssec.c:9-268
   G.cia.resize(o.csfiles.size());
@@ -533,6 +552,48 @@ static void prepare_batch(int total, int n_in) {
     CUDA_OK(cudaMemsetAsync(G.d_tau.p, 0, (size_t)total * c.nwave * c.nlayer * sizeof(double), G.stream));
   }
   if (!c.eclipse) G.d_wts.ensure((size_t)total * transit_weights_stride(c.nlayer));
+  if (G.lbl) {
+    // one extra row: the column kernels also load the (zero-weighted) second bracket plane
+    G.d_lbl_ext.ensure(((size_t)total * c.nlayer + 1) * c.nwave);
+    G.d_lbl_dens.ensure((size_t)std::max(1, total) * c.nlayer * c.nspec);
+    c.grid = G.d_lbl_ext.p;
+    c.lbl_dens = G.d_lbl_dens.p;
+  }
+}
+
+// Line-by-line mode: molecular extinction of models [off, off+count) (those atm_prep accepted)
+// into ext[model][layer][wave], by the builder kernels with one plane per (model, layer).
+static void lbl_extinction(const double *d_prof, int off, int count, int n_in) {
+  DevConfig &c = G.dc;
+  const int nl = c.nlayer, nw = c.nwave;
+  G.h_lbl_T.resize((size_t)count * nl);
+  G.h_lbl_status.resize(count);
+  CUDA_OK(cudaMemsetAsync(G.d_lbl_ext.p + (size_t)off * nl * nw, 0,
+                          ((size_t)count * nl + 1) * nw * sizeof(double), G.stream));
+  CUDA_OK(cudaMemcpy2DAsync(G.h_lbl_T.data(), (size_t)nl * 8, d_prof, (size_t)n_in * 8, (size_t)nl * 8,
+                            count, cudaMemcpyDeviceToHost, G.stream));
+  CUDA_OK(cudaMemcpyAsync(G.h_lbl_status.data(), G.d_status.p + off, count * sizeof(int),
+                          cudaMemcpyDeviceToHost, G.stream));
+  CUDA_OK(cudaStreamSynchronize(G.stream));
+  std::vector<double> cT;
+  std::vector<long long> cout_;
+  for (int m0 = 0; m0 < count;) {                       // runs of accepted models
+    if (G.h_lbl_status[m0] != 0) { m0++; continue; }
+    int m1 = m0;
+    while (m1 < count && G.h_lbl_status[m1] == 0) m1++;
+    const int ncell = (m1 - m0) * nl;
+    cT.resize(ncell); cout_.resize(ncell);
+    for (int m = m0; m < m1; m++)
+      for (int l = 0; l < nl; l++) {
+        cT[(size_t)(m - m0) * nl + l] = G.h_lbl_T[(size_t)m * nl + l] * G.atm.tfct;
+        cout_[(size_t)(m - m0) * nl + l] = ((long long)(off + m) * nl + l) * nw;
+      }
+    KernelScope ks("lbl_extinction");
+    builder_lbl_cells(G.builder, G.opt, G.atm, G.mol, G.tli, G.wn, G.stream, ncell, cT.data(),
+                      G.d_lbl_dens.p + (size_t)(off + m0) * nl * c.nspec, cout_.data(), G.d_lbl_ext.p);
+    G.launches += 5;                                    // kmax, count, scan, fill, widths (+ accumulate)
+    m0 = m1;
+  }
 }
 
 static void launch_models(const double *d_prof, int off, int count, int total, int n_in, double *d_spec) {
@@ -549,9 +610,12 @@ static void launch_models(const double *d_prof, int off, int count, int total, i
   int *last = G.keep ? G.d_last.p + (size_t)off * c.nwave : nullptr;
   {
     KernelScope ks("atm_prep");
-    launch_atm_prep(c, k, d_prof, n_in, tabs, status, G.pre_status ? G.pre_status + off : nullptr, count, G.stream);
+    DevConfig cc = c;
+    cc.lbl_model0 = off;
+    launch_atm_prep(cc, k, d_prof, n_in, tabs, status, G.pre_status ? G.pre_status + off : nullptr, count, G.stream);
     check_launch("atm_prep");
   }
+  if (G.lbl) lbl_extinction(d_prof, off, count, n_in);
   if (c.eclipse) {
     KernelScope ks("eclipse_column");
     launch_eclipse(c, tabs, status, d_spec, tau, last, count, G.keep, G.use_tma, G.stream);
@@ -607,6 +671,8 @@ static void ensure_params_buffers(int nmodels) {
   if (!G.init || G.opt.justOpacity) fail("Transit init not run, please initialize transit.");
   if (!G.conv.ready) fail("bart_converter_init has not been called");
   if (G.nfilters <= 0) fail("bart_set_filters has not been called");
+  if (G.lbl) fail("the device-resident retrieval loop needs an opacity grid (set 'opacityfile'); the "
+                  "line-by-line mode serves run_transit / bart_run_batch only");
   const int n_in = (c.nspec + 1) * c.nlayer;
   G.d_prof.ensure((size_t)std::max(1, nmodels) * n_in);
   G.d_spec.ensure((size_t)std::max(1, nmodels) * c.nwave);
@@ -1023,8 +1089,12 @@ int bart_extinction_batch(const double *profiles, int nmodels, int n_in, double 
   G.d_ext.ensure(n);
   CUDA_OK(cudaMemcpyAsync(G.d_prof.p, profiles, (size_t)nmodels * n_in * 8, cudaMemcpyHostToDevice, G.stream));
   Knobs k = effective_knobs(nmodels);
+  if (G.lbl) prepare_batch(nmodels, n_in);
   { KernelScope ks("atm_prep");
-    launch_atm_prep(c, k, G.d_prof.p, n_in, G.d_tabs.p, G.d_status.p, nullptr, nmodels, G.stream); check_launch("atm_prep"); }
+    DevConfig cc = c;
+    cc.lbl_model0 = 0;
+    launch_atm_prep(cc, k, G.d_prof.p, n_in, G.d_tabs.p, G.d_status.p, nullptr, nmodels, G.stream); check_launch("atm_prep"); }
+  if (G.lbl) lbl_extinction(G.d_prof.p, 0, nmodels, n_in);
   const int tiles = (c.nwave + kColThreads - 1) / kColThreads;
   int splits = 1;
   while ((long long)tiles * nmodels * splits < 148 * 8 && splits < c.nlayer) splits *= 2;

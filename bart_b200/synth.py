@@ -282,7 +282,8 @@ def make_case(workdir, shape="demo", solution="eclipse", seed=12345, nlayer=100,
               tlow=400.0, thigh=3000.0, tempdelt=100.0, with_cia=True, with_grid=True,
               nlines=0, wnosamp=2160, extra_cfg=None, nfilters=None, overrides=None,
               cia_path=None, starrad=1.155, refpress=0.1, gsurf=1165.02,
-              refradius_km=123820.0, ethresh=1e-6, nwidth=20, outputs=False, verb=0):
+              refradius_km=123820.0, ethresh=1e-6, nwidth=20, outputs=False, verb=0,
+              no_opacity=False):
     """Create every input file of one configuration under `workdir`; returns paths + arrays."""
     os.makedirs(workdir, exist_ok=True)
     sh = dict(SHAPES[shape]) if isinstance(shape, str) else dict(shape)
@@ -329,8 +330,9 @@ def make_case(workdir, shape="demo", solution="eclipse", seed=12345, nlayer=100,
     case["filters"] = [write_filter(P("filter%02d.dat" % i), edges[i], edges[i + 1])
                        for i in range(nfilters)]
     # transit cfg (the file makecfg.makeTransit would write, makecfg.py:23-108)
-    lines = ["atm %s" % case["atm"], "molfile %s" % case["molfile"], "linedb %s" % case["tli"],
-             "opacityfile %s" % case["opacity"]]
+    lines = ["atm %s" % case["atm"], "molfile %s" % case["molfile"], "linedb %s" % case["tli"]]
+    if not no_opacity:      # without it transit computes the extinction line by line (tau.c:163-175)
+        lines.append("opacityfile %s" % case["opacity"])
     if with_cia:
         lines.append("csfile %s" % case["cia"])
     lines += ["wnlow %.10g" % sh["wnlow"], "wnhigh %.10g" % sh["wnhigh"],

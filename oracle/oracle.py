@@ -210,14 +210,32 @@ class Oracle:
         c.gsurf = float(cfg["gsurf"])
         c.p0 = float(cfg["refpress"])
         c.r0 = float(cfg["refradius"])
-        op = read_opacity(cfg["opacityfile"])
-        self.op = op
-        self.grid = np.ascontiguousarray(op["o"])
-        self.gtemp = op["temps"]
-        self.gmol_spec = np.array([self.ids.index(int(m)) for m in op["molids"]], dtype=np.int32)
-        c.ntemp, c.ngmol = len(self.gtemp), len(self.gmol_spec)
-        c.gtemp, c.gmol_spec, c.grid = _d(self.gtemp), self.gmol_spec.ctypes.data_as(ip), \
-            _d(self.grid)
+        self.lbl = None
+        if cfg.get("opacityfile"):
+            op = read_opacity(cfg["opacityfile"])
+            self.op = op
+            self.grid = np.ascontiguousarray(op["o"])
+            self.gtemp = op["temps"]
+            self.gmol_spec = np.array([self.ids.index(int(m)) for m in op["molids"]], dtype=np.int32)
+            c.ntemp, c.ngmol = len(self.gtemp), len(self.gmol_spec)
+            c.gtemp, c.gmol_spec, c.grid = _d(self.gtemp), self.gmol_spec.ctypes.data_as(ip), \
+                _d(self.grid)
+        else:
+            # no opacity file (opacity.c:28-36): line-by-line extinction per layer, tau.c:163-175
+            self.B = BuilderOracle(cfgpath, grid_temps=False)
+            lb, keep = self.B.lbl_struct()
+            isos = self.B.tli["isos"]
+            self._iso_nt = np.array([len(i["T"]) for i in isos], dtype=np.int32)
+            self._iso_T = [np.ascontiguousarray(i["T"], dtype=np.float64) for i in isos]
+            self._iso_Z = [np.ascontiguousarray(i["Z"], dtype=np.float64) for i in isos]
+            f = OrcLblFwd()
+            f.lbl = C.pointer(lb)
+            f.iso_nt = self._iso_nt.ctypes.data_as(ip)
+            Tp = (dp * len(isos))(*[_d(t) for t in self._iso_T])
+            Zp = (dp * len(isos))(*[_d(z) for z in self._iso_Z])
+            f.iso_T, f.iso_Z = Tp, Zp
+            self._lblkeep = (lb, keep, Tp, Zp)
+            self.lbl = f
         files = [f for f in cfg.get("csfile", "").split(",") if f]
         self.cia = [read_cia(f) for f in files]
         n = len(self.cia)
@@ -272,7 +290,7 @@ class Oracle:
         nl, nw, ns = self.c.nlayer, self.c.nwave, self.c.nspec
         spec = np.zeros(nw)
         if not inter:
-            lib().orc_forward(C.byref(self.c), int(self.eclipse), _d(model), _d(spec), None)
+            self._forward(model, spec, None)
             return spec
         it = OrcInter()
         out = dict(radius=np.zeros(nl), temp=np.zeros(nl), mm=np.zeros(nl),
@@ -285,9 +303,19 @@ class Oracle:
         if self.eclipse:
             out["intens"] = np.zeros((self.c.nangle, nw))
             it.intens = _d(out["intens"])
-        lib().orc_forward(C.byref(self.c), int(self.eclipse), _d(model), _d(spec), C.byref(it))
+        self._forward(model, spec, C.byref(it))
         out["spectrum"] = spec
         return out
+
+    def _forward(self, model, spec, it):
+        if self.lbl is None:
+            lib().orc_forward(C.byref(self.c), int(self.eclipse), _d(model), _d(spec), it)
+        else:
+            L = lib()
+            L.orc_forward_lbl.argtypes = [C.POINTER(OrcConfig), C.POINTER(OrcLblFwd), C.c_int, dp, dp,
+                                          C.POINTER(OrcInter)]
+            L.orc_forward_lbl(C.byref(self.c), C.byref(self.lbl), int(self.eclipse), _d(model),
+                              _d(spec), it)
 
     def run_batch(self, models):
         return np.stack([self.run(m) for m in np.atleast_2d(models)])
@@ -346,6 +374,11 @@ class OrcLbl(C.Structure):
         ("profsize", C.POINTER(C.c_long)), ("profile", C.POINTER(C.POINTER(C.c_float))),
         ("ethresh", C.c_double),
     ]
+
+
+class OrcLblFwd(C.Structure):
+    _fields_ = [("lbl", C.POINTER(OrcLbl)), ("iso_nt", ip), ("iso_T", C.POINTER(dp)),
+                ("iso_Z", C.POINTER(dp))]
 
 
 def read_tli(path):
@@ -424,7 +457,7 @@ def select_lines(tli, wnlow, wnhigh):
 class BuilderOracle:
     """calcprofiles + calcopacity restated: builds o[layer][temp][mol][wave] on the CPU."""
 
-    def __init__(self, cfgpath, with_profiles=True):
+    def __init__(self, cfgpath, with_profiles=True, grid_temps=True):
         L = lib()
         L.orc_computemolext.argtypes = [C.POINTER(OrcLbl), C.c_double, dp, dp, dp,
                                         C.POINTER(C.c_long), C.POINTER(C.c_long)]
@@ -447,7 +480,7 @@ class BuilderOracle:
         self.odwn = d / self.osamp
         self.dwn = d
         self.temps = wn_grid(float(cfg.get("tlow", 500)), float(cfg.get("thigh", 3000)),
-                             float(cfg.get("tempdelt", 100)))
+                             float(cfg.get("tempdelt", 100))) if grid_temps else np.zeros(0)
         tli = read_tli(cfg["linedb"])
         self.tli = tli
         idx = select_lines(tli, lo, hi)
@@ -511,12 +544,8 @@ class BuilderOracle:
                      1 if n > 99999 else 0)
         return out, ps
 
-    def build(self, layers=None, temps=None, trace=False):
-        L = lib()
-        atm = self.atm
-        nl = len(atm["press"])
-        layers = range(nl) if layers is None else layers
-        temps = range(len(self.temps)) if temps is None else temps
+    def lbl_struct(self):
+        """(OrcLbl, objects to keep alive)"""
         nw = len(self.wn)
         ng = len(self.gmol_id)
         lb = OrcLbl()
@@ -535,6 +564,29 @@ class BuilderOracle:
             *[p.ctypes.data_as(C.POINTER(C.c_float)) for p in self.profiles])
         lb.profile = ptrs
         lb.ethresh = self.ethresh
+        return lb, (psz, ptrs)
+
+    def total(self, temp, density, Z):
+        """computemolext(permol=0) of one layer: k[nwave] (extinction.c:281-529)"""
+        L = lib()
+        L.orc_computemolext_total.argtypes = [C.POINTER(OrcLbl), C.c_double, dp, dp, dp,
+                                              C.POINTER(C.c_long)]
+        lb, keep = self.lbl_struct()
+        k = np.zeros(len(self.wn))
+        density = np.ascontiguousarray(density, dtype=np.float64)
+        Z = np.ascontiguousarray(Z, dtype=np.float64)
+        L.orc_computemolext_total(C.byref(lb), float(temp), _d(density), _d(Z), _d(k), None)
+        return k
+
+    def build(self, layers=None, temps=None, trace=False):
+        L = lib()
+        atm = self.atm
+        nl = len(atm["press"])
+        layers = range(nl) if layers is None else layers
+        temps = range(len(self.temps)) if temps is None else temps
+        nw = len(self.wn)
+        ng = len(self.gmol_id)
+        lb, _keep = self.lbl_struct()
         out = np.zeros((len(list(layers)), len(list(temps)), ng, nw))
         tr = np.zeros(len(self.wl), dtype=np.int64) if trace else None
         for a, r in enumerate(layers):

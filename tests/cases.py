@@ -48,6 +48,26 @@ BUILD_CASES = {
 }
 
 
+# Line-by-line forward mode (no opacity file: tau.c:163-175,253-264 -> computemolext(permol=0)):
+# name -> (make_case kwargs, n_models, model seed, molfit)
+LBL_CASES = {
+    "lbl_eclipse": (dict(shape="tiny", solution="eclipse", nlayer=24, with_grid=False, no_opacity=True,
+                         nlines=3000, seed=5150, ethresh=1e-6), 2, 61, ("CH4",)),
+    "lbl_transit_2mol": (dict(shape=dict(wnlow=2000.0, wnhigh=2120.0, wndelt=1.0, mols=["H2O", "CH4"],
+                                         toomuch=10.0),
+                              solution="transit", refradius_km=95000.0, nlayer=20, with_grid=False,
+                              no_opacity=True, nlines=5000, seed=5151, ethresh=1e-4, wnosamp=1080,
+                              nwidth=30), 2, 62, ("H2O", "CH4")),
+}
+
+
+def build_lbl_case(name, workdir):
+    kw, nm, mseed, molfit = LBL_CASES[name]
+    case = synth.make_case(os.path.join(workdir, name), **kw)
+    models = synth.make_models(case, nm, seed=mseed, molfit=molfit)
+    return case, models
+
+
 def build_builder_case(name, workdir):
     import os as _os
     case = synth.make_case(_os.path.join(workdir, name), **BUILD_CASES[name])

@@ -69,6 +69,34 @@ def builder_golden(only):
                 name, g["o"].shape, g["o"].max(), (g["o"] > 0).mean(), os.path.getsize(cases.golden_path(name))))
 
 
+def lbl_golden(only):
+    """Forward models of the reference WITHOUT an opacity file (line-by-line extinction at every
+    layer's own temperature, tau.c:163-175 -> computemolext(permol=0))."""
+    with tempfile.TemporaryDirectory() as tmp:
+        for name in cases.LBL_CASES:
+            if only and name not in only:
+                continue
+            case, models = cases.build_lbl_case(name, tmp)
+            mpath = os.path.join(case["workdir"], "models.npy")
+            opath = os.path.join(case["workdir"], "ref.npz")
+            np.save(mpath, models)
+            cmd = [sys.executable, os.path.join(ROOT, "oracle", "ref_driver.py"), case["cfg"], mpath,
+                   opath, "--inter"]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                raise SystemExit("reference failed on %s:\n%s\n%s" % (name, r.stdout[-2000:], r.stderr[-2000:]))
+            d = np.load(opath)
+            np.savez_compressed(
+                cases.golden_path(name), wn=d["wn"], spectra=d["spectra"], last=d["last"],
+                radius=d["radius"], ext=d["ext"], tau=d["tau"],
+                tli_sha=cases.sha(np.fromfile(case["tli"], dtype=np.uint8)),
+                models_sha=cases.sha(models), toomuch=d["toomuch"])
+            print("%-24s nwave %5d  models %d  last[min,max]=%d,%d  ext max %.3g -> %d bytes" % (
+                name, len(d["wn"]), models.shape[0], d["last"].min(), d["last"].max(), d["ext"].max(),
+                os.path.getsize(cases.golden_path(name))))
+
+
 if __name__ == "__main__":
     builder_golden(sys.argv[1:])
+    lbl_golden(sys.argv[1:])
     main()
