@@ -491,7 +491,8 @@ BART_HD void cell_load(const DevConfig &c, const ColPtrs &P, const double *row,
 
 template <int NMOL, int NCIA>
 BART_HD double cell_combine(const DevConfig &c, const ColPtrs &P, const double *row,
-                            const CellData<NMOL, NCIA> &x, double wn4, bool mol_only) {
+                            const CellData<NMOL, NCIA> &x, double wn4, int part) {
+  // part: 0 = total extinction, 1 = molecular lines only, 2 = collision-induced absorption only
   typedef TabLayout L;
   const int ngmol = NMOL > 0 ? NMOL : c.ngmol;
   const int ncia = NCIA >= 0 ? NCIA : c.ncia;
@@ -514,7 +515,7 @@ BART_HD double cell_combine(const DevConfig &c, const ColPtrs &P, const double *
       e = fma(wt.y, ld1b(hi + 8 * m), e);
     }
   }
-  if (mol_only) return e;
+  if (part == 1) return e;
   double ecs = 0.0;
   const double *cr = row + L::W + 2 * ngmol;
   const size_t cplane = (size_t)c.nwave * 16;
@@ -535,16 +536,17 @@ BART_HD double cell_combine(const DevConfig &c, const ColPtrs &P, const double *
       if (hi_word(v) > 0) ecs += v;                            // v > 0 (crosssec.c:330)
     }
   }
+  if (part == 2) return ecs;
   const D2 sc = ld2(row + L::SCAT);                            // (scattering coefficient, cloud)
   return fma(sc.x, wn4, e) + sc.y + ecs;
 }
 
 template <int NMOL, int NCIA>
 BART_HD double cell_extinction(const DevConfig &c, const ColPtrs &P, const double *row, double wn4,
-                               bool mol_only) {
+                               int part) {
   CellData<NMOL, NCIA> x;
   cell_load<NMOL, NCIA>(c, P, row, x);
-  return cell_combine<NMOL, NCIA>(c, P, row, x, wn4, mol_only);
+  return cell_combine<NMOL, NCIA>(c, P, row, x, wn4, part);
 }
 
 // ---------------------------------------------------------------------------------------

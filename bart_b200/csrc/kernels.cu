@@ -426,7 +426,7 @@ extinction_kernel(DevConfig c, const double *__restrict__ tabs, double *__restri
     for (int j = 0; j < kLookupBatch; j++)
       if (d + j < d1)
         out[(size_t)(nl - 1 - d - j) * c.nwave] =
-            cell_combine<NMOL, -1>(c, P, s_tab + (size_t)(d + j) * nf, x[j], wn4, mol_only != 0);
+            cell_combine<NMOL, -1>(c, P, s_tab + (size_t)(d + j) * nf, x[j], wn4, mol_only);
   }
 }
 
@@ -624,14 +624,14 @@ void launch_transit(const DevConfig &c, const double *tabs, const double *wts, c
 }
 
 void launch_extinction(const DevConfig &c, const double *tabs, double *ext, int nmodels,
-                       bool mol_only, int layer_splits, int use_tma, cudaStream_t s) {
+                       int mol_only, int layer_splits, int use_tma, cudaStream_t s) {
   const size_t smem = (size_t)c.lay.stride() * sizeof(double);
   const int tiles = (c.nwave + kColThreads - 1) / kColThreads;
   dim3 grid((unsigned)((size_t)tiles * nmodels), (unsigned)layer_splits);
   auto go = [&](auto kern) {
     if (smem > 48 * 1024)
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<grid, kColThreads, smem, s>>>(c, tabs, ext, nmodels, mol_only ? 1 : 0, use_tma);
+    kern<<<grid, kColThreads, smem, s>>>(c, tabs, ext, nmodels, mol_only, use_tma);
   };
   switch (c.ngmol) {
     case 1: go(extinction_kernel<1>); break;

@@ -24,8 +24,9 @@ void launch_transit(const DevConfig &c, const double *tabs, const double *wts, c
                     int *status_col, double *spectra, double *tau_keep, int *last_keep,
                     int nmodels, bool keep, int use_tma, cudaStream_t s);
 void launch_merge_status(int *status, const int *status_col, int nmodels, cudaStream_t s);
+// mol_only: 0 = total extinction, 1 = molecular lines only, 2 = CIA only
 void launch_extinction(const DevConfig &c, const double *tabs, double *ext, int nmodels,
-                       bool mol_only, int layer_splits, int use_tma, cudaStream_t s);
+                       int mol_only, int layer_splits, int use_tma, cudaStream_t s);
 void launch_band_integrate(const double *spectra, const double *wn, const int *fstart,
                            const int *fcount, const int *foffset, const double *weight,
                            const double *star, double rprs2, const int *status, double *bandflux,

@@ -846,21 +846,94 @@ void set_scattering(int flag, double scattering) {
   G.knobs.scat_flag_all = flag; G.knobs.scat_logext_all = scattering;
 }
 
+// `savefiles yes` (tau.c:179-190,308-329): the six text dumps of one run_transit call, written to
+// the working directory in the reference's layouts (print2dArrayDouble / save1Darray /
+// savemolExtion, tau.c:360-518; format %-20.10g).  code/cf.py:68-135 reads tau.dat.
+static void write_savefiles(const double *re_input, int n_in) {
+  const DevConfig &c = G.dc;
+  const int nl = c.nlayer, nw = c.nwave, nf = c.lay.nf();
+  std::vector<double> tau((size_t)nw * nl), tab((size_t)c.lay.stride());
+  CUDA_OK(cudaMemcpy(tau.data(), G.d_tau.p, tau.size() * 8, cudaMemcpyDeviceToHost));
+  CUDA_OK(cudaMemcpy(tab.data(), G.d_tabs.p, tab.size() * 8, cudaMemcpyDeviceToHost));
+  std::vector<double> mol((size_t)nl * nw), tot((size_t)nl * nw), cia((size_t)nl * nw);
+  if (bart_extinction_batch(re_input, 1, n_in, mol.data(), 0) != 0) return;
+  if (bart_extinction_batch(re_input, 1, n_in, tot.data(), 1) != 0) return;
+  if (bart_extinction_batch(re_input, 1, n_in, cia.data(), 2) != 0) return;
+  const char *fmt = "%-20.10g";
+  auto open_dump = [](const char *name, const char *header) {
+    FILE *f = fopen(name, "w");
+    if (!f) fail("cannot open '%s' for writing (savefiles)", name);
+    fprintf(f, "\n");
+    fputs(header, f);
+    return f;
+  };
+  // per-wavenumber rows [wn][rad], rad[0] = bottom: total, cloud, scattering (save1Darray)
+  FILE *ft = open_dump("total_extion.dat", "# 2D total extinction\n# er [wn][rad]; wn[0]=min(wn), row[0]=bottom (max(p))\n");
+  FILE *fc = open_dump("cloud_extion.dat", "# 2D cloud extinction\n# e_c [wn][rad]; wn[0]=min(wn), row[0]=bottom (max(p))\n");
+  FILE *fs = open_dump("scatt_extion.dat", "# 2D scatt extinction\n# e_s [wn][rad]; wn[0]=min(wn), row[0]=bottom (max(p))\n");
+  for (int w = 0; w < nw; w++) {
+    const double wn = G.wn[w], wn4 = (wn * wn) * (wn * wn);
+    FILE *fl[3] = {ft, fc, fs};
+    for (int k = 0; k < 3; k++) {
+      fprintf(fl[k], "\nwavenumber: ");
+      fprintf(fl[k], fmt, wn);
+      fprintf(fl[k], "\n");
+      for (int r = 0; r < nl; r++) {
+        const double *row = tab.data() + (size_t)(nl - 1 - r) * nf;
+        const double v = k == 0 ? tot[(size_t)r * nw + w] : (k == 1 ? row[TabLayout::CLOUD] : row[TabLayout::SCAT] * wn4);
+        fprintf(fl[k], fmt, v);
+      }
+      fprintf(fl[k], "\n");
+    }
+  }
+  fclose(ft); fclose(fc); fclose(fs);
+  // tau.dat [wn][rad], rad[0] = top; CIA.dat [wn][rad], rad[0] = bottom (print2dArrayDouble)
+  FILE *f = open_dump("tau.dat", "# 2D optical depth\n# tau [wn][rad]; wn[0]=min(wn); rad[0]=top (min(p))\n\n");
+  FILE *g = open_dump("CIA.dat", "# 2D CIA extinction\n# e_cs [wn][rad]; wn[0]=min(wn); row[0]=bottom (max(p))\n\n");
+  for (int w = 0; w < nw; w++) {
+    FILE *fl[2] = {f, g};
+    for (int k = 0; k < 2; k++) {
+      fprintf(fl[k], "wavenumber: ");
+      fprintf(fl[k], fmt, G.wn[w]);
+      fprintf(fl[k], "\n");
+      for (int r = 0; r < nl; r++) fprintf(fl[k], fmt, k == 0 ? tau[(size_t)w * nl + r] : cia[(size_t)r * nw + w]);
+      fprintf(fl[k], "\n\n");
+    }
+  }
+  fclose(f); fclose(g);
+  // mol_extion.dat [rad][wn], rad[0] = bottom (savemolExtion)
+  f = open_dump("mol_extion.dat", "# mol-line extinction\n# e [rad][wn]; rad[0]=bottom (max(p)); wn[0]=min(wn)\n\n");
+  for (int r = 0; r < nl; r++) {
+    fprintf(f, "radius: %-20.10g\n", tab[(size_t)(nl - 1 - r) * nf + TabLayout::RAD]);
+    for (int w = 0; w < nw; w++) fprintf(f, fmt, mol[(size_t)r * nw + w]);
+    fprintf(f, "\n\n");
+  }
+  fclose(f);
+}
+
 void run_transit(double *re_input, int transint, double *transit_out, int transit_out_size) {
   API_BEGIN
   if (!G.init) { printf("Transit init not run, please initialize transit.\n"); return; }
   int status = 0;
   const int saved = G.knob_models;
   G.knob_models = 0;                         // the single-model call uses the process-wide setters
+  const bool saved_keep = G.keep;
+  if (G.opt.savefiles) G.keep = true;
   int rc = bart_run_batch(re_input, 1, transint, transit_out, transit_out_size, &status);
+  if (rc == 0 && status == 0 && G.opt.savefiles) write_savefiles(re_input, transint);
+  G.keep = saved_keep;
   G.knob_models = saved;
   if (rc != 0) return;
   // the reference exit()s where the batched path reports a per-model status
   if (status & REJ_SUMQ) fail("Sum of abundances of isotopes adds up to more than 1");
   if (status & REJ_TCIA) fail("A layer in the atmospheric model has a temperature outside the allowed "
                               "cross-section temperature range.");
-  if (status & REJ_TGRID) fail("A layer in the atmospheric model has a temperature outside the "
-                               "opacity-grid temperature range [%g, %g] K.", G.og.temp.front(), G.og.temp.back());
+  if (status & REJ_TGRID) {
+    if (G.lbl) fail("A layer in the atmospheric model has a temperature outside the allowed TLI "
+                    "temperature range [%.1f, %.1f] K.", G.tli.tmin, G.tli.tmax);
+    fail("A layer in the atmospheric model has a temperature outside the "
+         "opacity-grid temperature range [%g, %g] K.", G.og.temp.front(), G.og.temp.back());
+  }
   if (status & REJ_FEWPTS) fail("Condition failed, less than 3 items for radial integration.");
   if (status & REJ_NOTOOMUCH) fail("Optical depth didn't reach limiting %g at some wavenumber.  Cannot "
                                    "use critical radius technique (-1).", G.opt.toomuch);
@@ -1099,7 +1172,7 @@ int bart_extinction_batch(const double *profiles, int nmodels, int n_in, double 
   int splits = 1;
   while ((long long)tiles * nmodels * splits < 148 * 8 && splits < c.nlayer) splits *= 2;
   { KernelScope ks("opacity_lookup");
-    launch_extinction(c, G.d_tabs.p, G.d_ext.p, nmodels, what == 0, splits, G.use_tma, G.stream);
+    launch_extinction(c, G.d_tabs.p, G.d_ext.p, nmodels, what == 0 ? 1 : (what == 2 ? 2 : 0), splits, G.use_tma, G.stream);
     check_launch("opacity_lookup"); }
   if (ext_out)
     CUDA_OK(cudaMemcpyAsync(ext_out, G.d_ext.p, n * 8, cudaMemcpyDeviceToHost, G.stream));

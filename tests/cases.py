@@ -68,6 +68,17 @@ def build_lbl_case(name, workdir):
     return case, models
 
 
+# `savefiles yes` dumps (tau.c:179-190,308-329; tau.dat feeds code/cf.py)
+SAVEFILES_CASE = (dict(shape="tiny", solution="eclipse", seed=6001, nlayer=30,
+                       extra_cfg=["savefiles yes", "cloudtop -1.0", "scattering 1.5"]), 1, 60)
+
+
+def build_savefiles_case(workdir):
+    kw, nm, mseed = SAVEFILES_CASE
+    case = synth.make_case(os.path.join(workdir, "savefiles"), **kw)
+    return case, synth.make_models(case, nm, seed=mseed)
+
+
 def build_builder_case(name, workdir):
     import os as _os
     case = synth.make_case(_os.path.join(workdir, name), **BUILD_CASES[name])

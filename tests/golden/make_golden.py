@@ -96,7 +96,36 @@ def lbl_golden(only):
                 os.path.getsize(cases.golden_path(name))))
 
 
+def savefiles_golden(only):
+    """The six `savefiles yes` text dumps written by the reference for one model, parsed."""
+    if only and "savefiles" not in only:
+        return
+    from util import parse_dump, DUMPS
+    with tempfile.TemporaryDirectory() as tmp:
+        case, models = cases.build_savefiles_case(tmp)
+        mpath = os.path.join(case["workdir"], "models.npy")
+        opath = os.path.join(case["workdir"], "ref.npz")
+        np.save(mpath, models)
+        cmd = [sys.executable, os.path.join(ROOT, "oracle", "ref_driver.py"), case["cfg"], mpath, opath]
+        r = subprocess.run(cmd, capture_output=True, text=True, cwd=case["workdir"])
+        if r.returncode != 0:
+            raise SystemExit("reference failed:\n%s\n%s" % (r.stdout[-2000:], r.stderr[-2000:]))
+        out = dict(models_sha=cases.sha(models), grid_sha=cases.sha(case["grid"]),
+                   spectra=np.load(opath)["spectra"])
+        for name in DUMPS:
+            path = os.path.join(case["workdir"], name)
+            keys, rows = parse_dump(path)
+            key = name.split(".")[0]
+            out[key + "_keys"], out[key] = keys, rows
+            with open(path) as f:
+                out[key + "_head"] = f.read(300)
+        np.savez_compressed(cases.golden_path("savefiles"), **out)
+        print("savefiles: tau %s, mol %s -> %d bytes" % (out["tau"].shape, out["mol_extion"].shape,
+                                                          os.path.getsize(cases.golden_path("savefiles"))))
+
+
 if __name__ == "__main__":
+    savefiles_golden(sys.argv[1:])
     builder_golden(sys.argv[1:])
     lbl_golden(sys.argv[1:])
     main()

@@ -1,0 +1,55 @@
+"""GPU (B200): `savefiles yes` (tau.c:179-190,308-329) -- run_transit writes the reference's six
+text dumps into the working directory; tau.dat is what code/cf.py:68-135 reads for the contribution
+functions.  Compared with the files the UNMODIFIED reference wrote for the same model
+(tests/golden/savefiles.npz)."""
+import os
+import numpy as np
+import pytest
+
+import cases
+from util import relerr, parse_dump, DUMPS
+
+pytestmark = pytest.mark.gpu
+
+
+def test_savefiles_dumps_match_reference(built, workdir, monkeypatch):
+    from bart_b200 import api
+    case, models = cases.build_savefiles_case(workdir)
+    g = np.load(cases.golden_path("savefiles"))
+    assert cases.sha(models) == str(g["models_sha"]) and cases.sha(case["grid"]) == str(g["grid_sha"])
+    monkeypatch.chdir(case["workdir"])
+    for n in DUMPS:
+        if os.path.exists(n):
+            os.remove(n)
+    tr = api.Transit(case["cfg"])
+    spec = tr.run_transit(models[0])
+    assert relerr(spec, g["spectra"][0]) < 1e-6
+    got = {}
+    for n in DUMPS:
+        key = n.split(".")[0]
+        assert os.path.exists(n), n
+        keys, rows = parse_dump(n)
+        got[key] = rows
+        assert np.array_equal(keys, g[key + "_keys"]) or relerr(keys, g[key + "_keys"]) < 1e-9
+        assert rows.shape == g[key].shape
+        with open(n) as f:
+            head = f.read(300)
+        # identical header block and first record label (layout of print2dArrayDouble / save1Darray)
+        ref_head = str(g[key + "_head"])
+        nhead = ref_head.index("\n", ref_head.index(":")) + 1
+        assert head[:nhead] == ref_head[:nhead], (head[:nhead], ref_head[:nhead])
+    # values: 10 significant digits are printed
+    tau, tau_ref = got["tau"], g["tau"]
+    assert np.array_equal(tau > 0, tau_ref > 0)          # zero beyond `last`, like the reference
+    assert relerr(tau, tau_ref) < 1e-8
+    assert relerr(got["CIA"], g["CIA"]) < 1e-9
+    assert relerr(got["cloud_extion"], g["cloud_extion"]) < 1e-9
+    assert relerr(got["scatt_extion"], g["scatt_extion"]) < 1e-9
+    mol_ref = g["mol_extion"]
+    comp = np.abs(mol_ref).sum(axis=1) > 0               # the reference computes layers lazily
+    assert comp.sum() > 5
+    assert relerr(got["mol_extion"][comp], mol_ref[comp]) < 1e-9
+    assert relerr(got["total_extion"][:, comp], g["total_extion"][:, comp]) < 1e-9
+    # what cf.py does with tau.dat (cf.py:68-96): rows are wavenumbers, transposed to [layer][wn]
+    assert got["tau"].T.shape == (tr.nlayer, tr.nwave)
+    tr.free_memory()

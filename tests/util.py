@@ -25,3 +25,26 @@ def apply_setters(obj, setters):
         obj.set_cloudtop(setters["cloudtop"])
     if "scattering" in setters:
         obj.set_scattering(1, setters["scattering"])
+
+
+def parse_dump(path):
+    """One of transit's `savefiles` text dumps (tau.c:360-518) -> (keys, rows): every record is a
+    'wavenumber: x' / 'radius: x' line followed by one line of values.  tau.dat parsed this way is
+    what code/cf.py:68-96 (readTauDat) extracts."""
+    keys, rows = [], []
+    with open(path) as f:
+        lines = f.readlines()
+    i = 0
+    while i < len(lines):
+        s = lines[i].strip()
+        if s.startswith("wavenumber:") or s.startswith("radius:"):
+            keys.append(float(s.split()[1]))
+            rows.append([float(v) for v in lines[i + 1].split()])
+            i += 2
+        else:
+            i += 1
+    return np.array(keys), np.array(rows)
+
+
+DUMPS = ("tau.dat", "CIA.dat", "mol_extion.dat", "total_extion.dat", "cloud_extion.dat",
+         "scatt_extion.dat")
