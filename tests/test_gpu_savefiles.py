@@ -30,7 +30,7 @@ def test_savefiles_dumps_match_reference(built, workdir, monkeypatch):
         assert os.path.exists(n), n
         keys, rows = parse_dump(n)
         got[key] = rows
-        assert np.array_equal(keys, g[key + "_keys"]) or relerr(keys, g[key + "_keys"]) < 1e-9
+        assert np.array_equal(keys, g[key + "_keys"]) or relerr(keys, g[key + "_keys"]) < 2e-9
         assert rows.shape == g[key].shape
         with open(n) as f:
             head = f.read(300)
@@ -38,18 +38,18 @@ def test_savefiles_dumps_match_reference(built, workdir, monkeypatch):
         ref_head = str(g[key + "_head"])
         nhead = ref_head.index("\n", ref_head.index(":")) + 1
         assert head[:nhead] == ref_head[:nhead], (head[:nhead], ref_head[:nhead])
-    # values: 10 significant digits are printed
+    # values: 10 significant digits are printed; 2e-9 = one unit in the last printed digit
     tau, tau_ref = got["tau"], g["tau"]
     assert np.array_equal(tau > 0, tau_ref > 0)          # zero beyond `last`, like the reference
     assert relerr(tau, tau_ref) < 1e-8
-    assert relerr(got["CIA"], g["CIA"]) < 1e-9
-    assert relerr(got["cloud_extion"], g["cloud_extion"]) < 1e-9
-    assert relerr(got["scatt_extion"], g["scatt_extion"]) < 1e-9
+    assert relerr(got["CIA"], g["CIA"]) < 2e-9
+    assert relerr(got["cloud_extion"], g["cloud_extion"]) < 2e-9
+    assert relerr(got["scatt_extion"], g["scatt_extion"]) < 2e-9
     mol_ref = g["mol_extion"]
     comp = np.abs(mol_ref).sum(axis=1) > 0               # the reference computes layers lazily
     assert comp.sum() > 5
-    assert relerr(got["mol_extion"][comp], mol_ref[comp]) < 1e-9
-    assert relerr(got["total_extion"][:, comp], g["total_extion"][:, comp]) < 1e-9
+    assert relerr(got["mol_extion"][comp], mol_ref[comp]) < 2e-9
+    assert relerr(got["total_extion"][:, comp], g["total_extion"][:, comp]) < 2e-9
     # what cf.py does with tau.dat (cf.py:68-96): rows are wavenumbers, transposed to [layer][wn]
     assert got["tau"].T.shape == (tr.nlayer, tr.nwave)
     tr.free_memory()
