@@ -963,6 +963,12 @@ static long long run_planes(BuilderState *b, const Options &o, const Molecules &
   return ne;
 }
 
+// planes per batch: bounded by the output buffer (2 GB) -- one plane is nlayer * ngmol * nwave doubles
+static int planes_per_batch(const BuilderState *b) {
+  const size_t plane_bytes = (size_t)b->nlayer * b->ngmol * b->nwave * 8;
+  return (int)std::max<size_t>(1, std::min<size_t>(16, ((size_t)2 << 30) / std::max<size_t>(1, plane_bytes)));
+}
+
 static void ensure_builder(BuilderState *&b, const Options &o, const Atmosphere &a,
                            const Molecules &m, Tli &t, const std::vector<double> &wn, cudaStream_t s) {
   if (!b) b = new BuilderState();
@@ -981,9 +987,7 @@ void builder_slice(BuilderState *&b, const Options &o, const Atmosphere &a, cons
     fail("temperature slice [%d, %d) outside the grid of %d temperatures", t_begin, t_end, b->ntemp);
   const int nt = t_end - t_begin, nl = b->nlayer, ns = b->nspec;
   const size_t plane = (size_t)b->ngmol * b->nwave;
-  // planes per batch: bounded by the device output buffer (2 GB) -- one plane is nl * plane doubles
-  const int pb = (int)std::max<size_t>(1, std::min<size_t>(16, ((size_t)2 << 30) / (nl * plane * 8)));
-  std::vector<double> tmp;
+  const int pb = planes_per_batch(b);
   for (int it0 = t_begin; it0 < t_end; it0 += pb) {
     const int np = std::min(pb, t_end - it0), nc = np * nl;
     std::vector<double> pT(np), pZ((size_t)np * b->niso), dens((size_t)nc * ns);
@@ -1011,12 +1015,13 @@ void builder_slice(BuilderState *&b, const Options &o, const Atmosphere &a, cons
     b->neval += run_planes(b, o, m, t, np, pT.data(), pZ.data(), nc, cplane.data(), d_dens,
                            cout_.data(), d_out, false, s);
     auto td0 = std::chrono::steady_clock::now();
-    tmp.resize((size_t)nc * plane);
-    BCUDA(cudaMemcpy(tmp.data(), d_out, tmp.size() * 8, cudaMemcpyDeviceToHost));
+    // device [plane][layer][mol][wave] -> host [layer][t - t_begin][mol][wave]: one strided copy
+    // per plane straight into the caller's buffer (fast when it is pinned, as the file writer's is)
     for (int p = 0; p < np; p++)
-      for (int r = 0; r < nl; r++)
-        memcpy(host_out + ((size_t)r * nt + (it0 + p - t_begin)) * plane,
-               tmp.data() + ((size_t)p * nl + r) * plane, plane * 8);
+      BCUDA(cudaMemcpy2DAsync(host_out + (size_t)(it0 + p - t_begin) * plane, (size_t)nt * plane * 8,
+                              d_out + (size_t)p * nl * plane, plane * 8, plane * 8, nl,
+                              cudaMemcpyDeviceToHost, s));
+    BCUDA(cudaStreamSynchronize(s));
     b->phase_ms["d2h"] += std::chrono::duration<double, std::milli>(
         std::chrono::steady_clock::now() - td0).count();
   }
@@ -1080,10 +1085,10 @@ void builder_run_and_write(BuilderState *&b, const Options &o, const Atmosphere 
     header = t0 == 0;
   }
   const size_t plane = (size_t)b->ngmol * b->nwave;
-  std::vector<double> slab((size_t)b->nlayer * (t1 - t0) * plane);
-  builder_slice(b, o, a, m, t, wn, s, t0, t1, slab.data());
-  if (t0 == 0 && t1 == b->ntemp) { write_opacity_file(path, g, slab.data()); return; }
-  int fd = open(path.c_str(), O_WRONLY | O_CREAT, 0644);
+  // Streaming writer: the planes of a batch of temperatures are built, copied back and written in
+  // place (file order o[layer][temp][mol][wave], opacity.c:418-421), so host memory holds one
+  // batch (<= 2 GB) however large the grid is.  Rank 0 / the first slice writes the header.
+  int fd = open(path.c_str(), O_WRONLY | O_CREAT | (t0 == 0 && t1 == b->ntemp ? O_TRUNC : 0), 0644);
   if (fd < 0) fail("Opacity filename '%s' cannot be opened for writing.", path.c_str());
   const long long hdr = 4 * sizeof(long) + g.nmol * sizeof(int) + (g.ntemp + g.nlayer + g.nwave) * 8;
   if (header) {
@@ -1097,13 +1102,27 @@ void builder_run_and_write(BuilderState *&b, const Options &o, const Atmosphere 
     memcpy(p, g.wn.data(), g.nwave * 8);
     if (pwrite(fd, h.data(), hdr, 0) != hdr) fail("short write on '%s'", path.c_str());
   }
-  const int nt = t1 - t0;
-  for (int r = 0; r < b->nlayer; r++) {
-    const long long off = hdr + ((long long)r * g.ntemp + t0) * (long long)plane * 8;
-    const long long len = (long long)nt * plane * 8;
-    if (pwrite(fd, slab.data() + (size_t)r * nt * plane, len, off) != len)
-      fail("short write on '%s'", path.c_str());
+  const int pb = planes_per_batch(b);
+  double *slab = nullptr;                                   // pinned staging for one batch
+  if (t1 > t0) BCUDA(cudaMallocHost((void **)&slab, (size_t)b->nlayer * std::min(pb, t1 - t0) * plane * 8));
+  for (int it0 = t0; it0 < t1; it0 += pb) {
+    const int nt = std::min(pb, t1 - it0);
+    builder_slice(b, o, a, m, t, wn, s, it0, it0 + nt, slab);
+    auto tw0 = std::chrono::steady_clock::now();
+    for (int r = 0; r < b->nlayer; r++) {
+      const long long off = hdr + ((long long)r * g.ntemp + it0) * (long long)plane * 8;
+      const long long len = (long long)nt * plane * 8;
+      const char *src = (const char *)(slab + (size_t)r * nt * plane);
+      for (long long done = 0; done < len;) {               // pwrite may be partial above 2 GB
+        const ssize_t w = pwrite(fd, src + done, (size_t)std::min<long long>(len - done, 1LL << 30), off + done);
+        if (w <= 0) fail("short write on '%s'", path.c_str());
+        done += w;
+      }
+    }
+    b->phase_ms["file_write"] += std::chrono::duration<double, std::milli>(
+        std::chrono::steady_clock::now() - tw0).count();
   }
+  if (slab) cudaFreeHost(slab);
   close(fd);
 }
 

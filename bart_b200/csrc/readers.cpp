@@ -2,6 +2,10 @@
 // Each reader follows the byte/field layout the reference reads (cited per function); none of
 // this runs per model.
 #include "host.hpp"
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <fcntl.h>
+#include <unistd.h>
 #include <cmath>
 #include <cstring>
 #include <cstdlib>
@@ -218,52 +222,66 @@ void read_tli_header(const std::string &path, Tli &t) {
 // on-disk binary search + linear refinement (readlineinfo.c:16-77, 496-525): first record with
 // wl >= iniw ... last record with wl <= finw, but never an empty slice (the reference always
 // reads at least the record its search lands on).
+// The line block is memory-mapped: the per-isotope binary searches touch O(log n) pages of the
+// wavelength array and only the selected slices of the four columns are copied, so a 1e8-line TLI
+// (2.6 GB) costs what its in-range part costs.  Selection = readdatarng (readlineinfo.c:416-537).
 void read_tli_lines(const std::string &path, Tli &t, double wnlow, double wnhigh) {
-  FILE *f = fopen(path.c_str(), "rb");
-  if (!f) fail("Data file '%s' not found.", path.c_str());
-  fseek(f, t.data_offset, SEEK_SET);
-  long long nlines = rd<long long>(f);
-  int niso = rd<int>(f);
+  int fd = open(path.c_str(), O_RDONLY);
+  if (fd < 0) fail("Data file '%s' not found.", path.c_str());
+  struct stat st;
+  if (fstat(fd, &st) != 0) { close(fd); fail("Data file '%s': cannot stat.", path.c_str()); }
+  const size_t fsize = (size_t)st.st_size;
+  void *mp = mmap(nullptr, fsize, PROT_READ, MAP_PRIVATE, fd, 0);
+  close(fd);
+  if (mp == MAP_FAILED) fail("Data file '%s': mmap failed.", path.c_str());
+  const char *base = (const char *)mp;
+  auto need = [&](long long off, long long bytes) {
+    if (off < 0 || bytes < 0 || (size_t)(off + bytes) > fsize) { munmap(mp, fsize); fail("TLI file: truncated"); }
+  };
+  long long pos = t.data_offset;
+  need(pos, 12);
+  long long nlines; int niso;
+  memcpy(&nlines, base + pos, 8); pos += 8;
+  memcpy(&niso, base + pos, 4); pos += 4;
+  need(pos, (long long)niso * 8);
   std::vector<long long> per(niso);
-  if (fread(per.data(), sizeof(long long), niso, f) != (size_t)niso) fail("TLI file: truncated");
-  long long start = ftell(f);
-  std::vector<double> wl(nlines);
-  if (fread(wl.data(), sizeof(double), nlines, f) != (size_t)nlines) fail("TLI file: truncated");
-  const double iniw = 1.0 / wnhigh / 1e-4, finw = 1.0 / wnlow / 1e-4;   // micron
+  memcpy(per.data(), base + pos, (size_t)niso * 8); pos += (long long)niso * 8;
+  const long long start = pos;
   const long long iso_loc = start + nlines * 8, el_loc = iso_loc + nlines * 2,
                   gf_loc = el_loc + nlines * 8;
+  need(gf_loc, nlines * 8);
+  // the columns are not 8-byte aligned in the file in general: copy through memcpy
+  auto wl_at = [&](long long i) { double v; memcpy(&v, base + start + i * 8, 8); return v; };
+  const double iniw = 1.0 / wnhigh / 1e-4, finw = 1.0 / wnlow / 1e-4;   // micron
   t.wl.clear(); t.elow.clear(); t.gf.clear(); t.isoid.clear();
   long long off = 0;
   for (int i = 0; i < niso; i++) {
-    const double *w = wl.data() + off;
-    long long n = per[i];
+    const long long n = per[i];
     if (n > 0) {
+      auto w = [&](long long k) { return wl_at(off + k); };
       // datafileBS(..., up=0): binary search then walk down while the previous record >= target
       long long lo = 0, hi = n - 1;
-      do { long long loc = (hi + lo) / 2; if (iniw > w[loc]) lo = loc; else hi = loc; } while (hi - lo > 1);
+      do { long long loc = (hi + lo) / 2; if (iniw > w(loc)) lo = loc; else hi = loc; } while (hi - lo > 1);
       long long first = hi;
-      while (first > 0 && !(w[first - 1] < iniw)) first--;
+      while (first > 0 && !(w(first - 1) < iniw)) first--;
       // datafileBS(..., up=1): walk up while the next record <= target
       lo = 0; hi = n - 1;
-      do { long long loc = (hi + lo) / 2; if (finw > w[loc]) lo = loc; else hi = loc; } while (hi - lo > 1);
+      do { long long loc = (hi + lo) / 2; if (finw > w(loc)) lo = loc; else hi = loc; } while (hi - lo > 1);
       long long last = lo;
-      while (last < n - 1 && !(w[last + 1] > finw)) last++;
-      long long nread = last - first + 1;
+      while (last < n - 1 && !(w(last + 1) > finw)) last++;
+      const long long nread = last - first + 1;
       if (nread > 0) {
-        size_t base = t.wl.size();
-        t.wl.insert(t.wl.end(), w + first, w + first + nread);
-        t.isoid.resize(base + nread); t.elow.resize(base + nread); t.gf.resize(base + nread);
-        fseek(f, iso_loc + (off + first) * 2, SEEK_SET);
-        if (fread(t.isoid.data() + base, 2, nread, f) != (size_t)nread) fail("TLI file: truncated");
-        fseek(f, el_loc + (off + first) * 8, SEEK_SET);
-        if (fread(t.elow.data() + base, 8, nread, f) != (size_t)nread) fail("TLI file: truncated");
-        fseek(f, gf_loc + (off + first) * 8, SEEK_SET);
-        if (fread(t.gf.data() + base, 8, nread, f) != (size_t)nread) fail("TLI file: truncated");
+        const size_t b0 = t.wl.size();
+        t.wl.resize(b0 + nread); t.isoid.resize(b0 + nread); t.elow.resize(b0 + nread); t.gf.resize(b0 + nread);
+        memcpy(t.wl.data() + b0, base + start + (off + first) * 8, (size_t)nread * 8);
+        memcpy(t.isoid.data() + b0, base + iso_loc + (off + first) * 2, (size_t)nread * 2);
+        memcpy(t.elow.data() + b0, base + el_loc + (off + first) * 8, (size_t)nread * 8);
+        memcpy(t.gf.data() + b0, base + gf_loc + (off + first) * 8, (size_t)nread * 8);
       }
     }
     off += n;
   }
-  fclose(f);
+  munmap(mp, fsize);
 }
 
 // ---------------------------------------------------------------------------------------

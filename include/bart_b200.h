@@ -25,7 +25,12 @@ extern "C" {
  * option table of src/argum.c:112-320, `key value` file grammar of pu/src/procopt.c:649-704),
  * read atmosphere / molecules / TLI header / CIA files, read -- or, when the named opacity
  * file does not exist, BUILD (Voigt line-by-line, src/opacity.c:218-427) and write -- the
- * opacity grid, and make everything resident in HBM.                                     */
+ * opacity grid, and make everything resident in HBM.  Without an `opacityfile` key the
+ * reference keeps only the Voigt table (src/opacity.c:28-36) and computes every layer's
+ * extinction line by line inside tau() (src/tau.c:163-175,253-264 -> computemolext with
+ * permol = 0, src/extinction.c:281-529): same here, the TLI lines and the Voigt table are made
+ * resident and every run_transit / bart_run_batch call evaluates its (model, layer) cells with
+ * the builder kernels at the layers' own temperatures.                                    */
 void transit_init(int argc, char **argv);
 
 /* replaces get_no_samples (src/transit.c:77-80): number of spectrum wavenumbers.         */
@@ -48,7 +53,11 @@ void set_scattering(int flag, double scattering);
 /* replaces run_transit (src/transit.c:118-122): one forward model.
  * re_input[(1+nspecies)*nlayers] = [T(layers) | q_species0(layers) | ...], layers bottom ->
  * top in atmosphere-file order (src/readatm.c:735-744); transit_out[nwave] receives the
- * emergent flux (eclipse, erg s-1 cm-1) or the modulation (transit, (Rp/Rs)^2).          */
+ * emergent flux (eclipse, erg s-1 cm-1) or the modulation (transit, (Rp/Rs)^2).
+ * With `savefiles yes` in the configuration (src/tau.c:179-190,308-329) the call also writes
+ * tau.dat, CIA.dat, mol_extion.dat, total_extion.dat, cloud_extion.dat and scatt_extion.dat
+ * into the working directory in the reference's text layouts (src/tau.c:360-518); tau.dat
+ * is what code/cf.py:68-135 reads for the contribution functions.                        */
 void run_transit(double *re_input, int transint, double *transit_out, int transit_out_size);
 
 /* replaces free_memory (src/transit.c:216-228).                                          */
@@ -121,7 +130,7 @@ int  bart_bandflux_batch_device(const double *d_profiles, int nmodels, int n_in,
 /* Stand-alone opacity lookup (src/extinction.c:534-581 + the sum of src/tau.c:231-232):
  * materialises ext[nmodels][nlayer][nwave] on the device (debug/roofline use).            */
 int  bart_extinction_batch(const double *profiles, int nmodels, int n_in, double *ext_out,
-                           int what /*0 molecular, 1 total incl. CIA/scattering/cloud*/);
+                           int what /*0 molecular, 1 total incl. CIA/scattering/cloud, 2 CIA only*/);
 
 /* Device memory helpers for callers without a CUDA runtime of their own.                  */
 void *bart_dev_alloc(long long bytes);
