@@ -12,9 +12,12 @@
 //                              non-contracted IEEE ops (bit-exact indices).
 //   (host)                     co-add grouping of neighbouring lines -- temperature independent,
 //                              sequential by construction (extinction.c:450-462), done once.
-//   K6a kmax_kernel            per temperature: strongest line per molecule (extinction.c:400-427)
-//   K6b strength_kernel        per temperature: co-added strength per group; these do not depend
-//                              on the layer, so they are computed once per T, not per cell.
+//   K6a+b strength_kmax_kernel per plane (temperature): ONE pass over the lines evaluates the two
+//                              exponentials that serve both the strongest line per molecule
+//                              (extinction.c:400-427) and the co-added group strengths (439-464);
+//                              strength_count / block_scan / strength_fill then compact the
+//                              groups that pass the weak-line cut (467-470), in order.  These
+//                              do not depend on the layer: once per T, not per cell.
 //   K6c widths_kernel          per (layer, isotope): Lorentz/Doppler widths, table indices, the
 //                              carried Doppler index of the reference's sequential loop.
 //   K6d accumulate_kernel      per (layer, 128-bin wavenumber tile): GATHER over the candidate
@@ -227,80 +230,63 @@ __global__ void line_index_kernel(const double *wl, long long n, double wn_lo, d
 // line-by-line forward mode (tau.c:163-175,253-264 -> computemolext(permol=0)) has one plane per
 // (model, layer) with a single cell.
 
-// K6a: strongest individual line per output molecule at the plane's temperature
-// (extinction.c:400-427).  grid = (blocks, planes).
-__global__ void kmax_kernel(const double *wavn, const double *elow, const double *gf,
-                            const short *isoid, const unsigned char *inrange, long long n,
-                            const double *plane_T, const double *plane_facfull /*[P][niso]*/, int niso,
-                            const int *iso_out, unsigned long long *kmax_bits /*[P][kMaxGridMol]*/,
-                            int nout) {
-  __shared__ double s_max[kMaxGridMol];
-  const int p = blockIdx.y;
-  const double T = plane_T[p];
-  const double *iso_fac = plane_facfull + (size_t)p * niso;
-  if (threadIdx.x < kMaxGridMol) s_max[threadIdx.x] = 0.0;
-  __syncthreads();
-  double loc[kMaxGridMol];
-#pragma unroll
-  for (int m = 0; m < kMaxGridMol; m++) loc[m] = 0.0;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
-       i += (long long)gridDim.x * blockDim.x) {
-    if (!inrange[i]) continue;
-    const int iso = isoid[i];
-    const double pk = iso_fac[iso] * gf[i] * exp(-kEXPCTE * elow[i] / T) *
-                      (1 - exp(-kEXPCTE * wavn[i] / T));
-    const int m = iso_out[iso];
-#pragma unroll
-    for (int q = 0; q < kMaxGridMol; q++) if (q == m) loc[q] = fmax(loc[q], pk);
-  }
-#pragma unroll
-  for (int m = 0; m < kMaxGridMol; m++)
-    if (m < nout && loc[m] > 0)
-      atomicMax((unsigned long long *)&s_max[m], (unsigned long long)__double_as_longlong(loc[m]));
-  __syncthreads();
-  if (threadIdx.x < nout && s_max[threadIdx.x] > 0)
-    atomicMax(&kmax_bits[(size_t)p * kMaxGridMol + threadIdx.x],
-              (unsigned long long)__double_as_longlong(s_max[threadIdx.x]));
-}
-
-// Co-added group strength at temperature T (extinction.c:439-464): lines of a group summed in
-// file order, then the isotope factor.
-__device__ __forceinline__ double group_strength(const long long *gstart, const double *wavn,
-                                                 const double *elow, const double *gf, long long g,
-                                                 double T, double fac) {
-  const long long b = gstart[g], e = gstart[g + 1];
-  double pk = 0.0;
-  for (long long i = b; i < e; i++) {
-    const double term = gf[i] * exp(-kEXPCTE * elow[i] / T) * (1 - exp(-kEXPCTE * wavn[i] / T));
-    pk = (i == b) ? term : pk + term;
-  }
-  return pk * fac;
-}
-
 constexpr int kCompactThreads = 256;
 
 struct PlaneArgs {
   const long long *gstart; const short *giso; const double *wavn, *elow, *gf;
   long long ngroups;
-  const double *plane_T, *plane_fac2 /*[P][niso]*/, *kmax /*[P][kMaxGridMol]*/;
+  const double *plane_T, *plane_fac2 /*[P][niso]*/, *plane_facfull /*[P][niso]*/;
+  double *kmax /*[P][kMaxGridMol]*/;
+  double *S /*[P][ngroups]*/;
   const int *iso_out;
-  int niso;
-  double ethresh;
+  int niso, nout;
+  double ethresh, wn_lo, own_last;
   int nblk;
 };
 
-// K6b pass 1: survivors of the weak-line cut (extinction.c:467-470) per block of 256 groups.
+// K6a+b pass 1, grid = (blocks of 256 groups, planes): ONE evaluation of the two exponentials of
+// every line serves both reference passes -- the strongest individual in-range line per output
+// molecule (extinction.c:400-427, expression order kept) and the co-added group strength
+// (extinction.c:439-464: lines of a group summed in file order, then the isotope factor).
+__global__ void __launch_bounds__(kCompactThreads)
+strength_kmax_kernel(PlaneArgs a) {
+  __shared__ double s_max[kMaxGridMol];
+  const int p = blockIdx.y;
+  const long long g = blockIdx.x * (long long)kCompactThreads + threadIdx.x;
+  if (threadIdx.x < kMaxGridMol) s_max[threadIdx.x] = 0.0;
+  __syncthreads();
+  if (g < a.ngroups) {
+    const double T = a.plane_T[p];
+    const int iso = a.giso[g];
+    const double ff = a.plane_facfull[(size_t)p * a.niso + iso];
+    const long long b = a.gstart[g], e = a.gstart[g + 1];
+    double pk = 0.0, lmax = 0.0;
+    for (long long i = b; i < e; i++) {
+      const double w = a.wavn[i], gf = a.gf[i];
+      const double e1 = exp(-kEXPCTE * a.elow[i] / T), e2 = 1 - exp(-kEXPCTE * w / T);
+      const double term = gf * e1 * e2;
+      pk = (i == b) ? term : pk + term;
+      if (!(w < a.wn_lo || w > a.own_last)) lmax = fmax(lmax, ff * gf * e1 * e2);
+    }
+    a.S[(size_t)p * a.ngroups + g] = pk * a.plane_fac2[(size_t)p * a.niso + iso];
+    if (lmax > 0)
+      atomicMax((unsigned long long *)&s_max[a.iso_out[iso]], (unsigned long long)__double_as_longlong(lmax));
+  }
+  __syncthreads();
+  if (threadIdx.x < a.nout && s_max[threadIdx.x] > 0)
+    atomicMax((unsigned long long *)&a.kmax[(size_t)p * kMaxGridMol + threadIdx.x],
+              (unsigned long long)__double_as_longlong(s_max[threadIdx.x]));
+}
+
+// K6b pass 2: survivors of the weak-line cut (extinction.c:467-470) per block of 256 groups.
 __global__ void __launch_bounds__(kCompactThreads)
 strength_count_kernel(PlaneArgs a, int *blkcnt /*[P][nblk]*/) {
   const int p = blockIdx.y;
   const long long g = blockIdx.x * (long long)kCompactThreads + threadIdx.x;
   bool alive = false;
-  if (g < a.ngroups) {
-    const int iso = a.giso[g];
-    const double S = group_strength(a.gstart, a.wavn, a.elow, a.gf, g, a.plane_T[p],
-                                    a.plane_fac2[(size_t)p * a.niso + iso]);
-    alive = !(S < a.ethresh * a.kmax[(size_t)p * kMaxGridMol + a.iso_out[iso]]);
-  }
+  if (g < a.ngroups)
+    alive = !(a.S[(size_t)p * a.ngroups + g] <
+              a.ethresh * a.kmax[(size_t)p * kMaxGridMol + a.iso_out[a.giso[g]]]);
   const int cnt = __syncthreads_count(alive);
   if (threadIdx.x == 0) blkcnt[(size_t)p * a.nblk + blockIdx.x] = cnt;
 }
@@ -339,7 +325,7 @@ block_scan_kernel(int *blkcnt, int nblk, long long *total) {
   if (threadIdx.x == 0) total[blockIdx.x] = s_carry;
 }
 
-// K6b pass 2: ordered compaction of the surviving groups of every plane into the pool, and the
+// K6b pass 3: ordered compaction of the surviving groups of every plane into the pool, and the
 // per-isotope ranges of the compact list.
 __global__ void __launch_bounds__(kCompactThreads)
 strength_fill_kernel(PlaneArgs a, const int *blkoff /*[P][nblk]*/, const long long *plane_base,
@@ -354,8 +340,7 @@ strength_fill_kernel(PlaneArgs a, const int *blkoff /*[P][nblk]*/, const long lo
   int iso = 0;
   if (g < a.ngroups) {
     iso = a.giso[g];
-    S = group_strength(a.gstart, a.wavn, a.elow, a.gf, g, a.plane_T[p],
-                       a.plane_fac2[(size_t)p * a.niso + iso]);
+    S = a.S[(size_t)p * a.ngroups + g];
     alive = !(S < a.ethresh * a.kmax[(size_t)p * kMaxGridMol + a.iso_out[iso]]);
   }
   const unsigned bal = __ballot_sync(0xffffffffu, alive);
@@ -622,6 +607,9 @@ static void setup_static(BuilderState *b, const Options &o, const Atmosphere &a,
   b->dwn = o.wndelt;
   b->odwn = o.wndelt / o.wnosamp;                                  // owns.d / owns.o
   b->nowns = (long long)(b->nwave - 1) * o.wnosamp + 1;            // makesample1, makesample.c:93
+  if (b->nowns > 0x7fffffffLL)                                     // the reference's `int iown` too
+    fail("wavenumber oversampling: %d samples x wnosamp %d exceeds the 32-bit line-bin index "
+         "(extinction.c:322); lower wnosamp", b->nwave, o.wnosamp);
   b->niso = t.niso();
   if (b->niso > kMaxIso) fail("at most %d isotopes are supported", kMaxIso);
   // setimol (readlineinfo.c:249-278) and the molID list of calcopacity (opacity.c:353-361)
@@ -828,14 +816,19 @@ static void load_lines(BuilderState *b, const Options &o, Tli &t, const std::vec
   b->d_giown = dev_upload(giown); b->d_gidwn = dev_upload(gidwn); b->d_giso = dev_upload(giso);
   b->d_gwavn = dev_upload(gwavn);
   b->d_c_wavn = dev_upload(c_wavn); b->d_c_elow = dev_upload(c_elow); b->d_c_gf = dev_upload(c_gf);
-  cudaFree(b->d_wl); b->d_wl = nullptr;     // wavelengths are no longer needed on the device
+  // the raw per-line arrays are no longer needed on the device: everything downstream works on
+  // the grouped copies
+  for (void **q : {(void **)&b->d_wl, (void **)&b->d_elow, (void **)&b->d_gf, (void **)&b->d_wavn,
+                   (void **)&b->d_isoid, (void **)&b->d_iown, (void **)&b->d_idwn, (void **)&b->d_inrange}) {
+    cudaFree(*q); *q = nullptr;
+  }
   b->lines_loaded = true;
 }
 
 // ---------------------------------------------------------------------------------------
 // Plane / cell driver shared by the grid build and the line-by-line forward mode.
 struct PlaneWork {
-  DevBuf T, facfull, fac2, kmax, blk, total, base, cisobeg;           // per plane
+  DevBuf T, facfull, fac2, kmax, blk, total, base, cisobeg, S;        // per plane
   DevBuf c_iown, c_idwn, c_wavn, c_S;                                  // compact pool
   DevBuf cell_plane, cell_out, cellinfo;                               // per cell
   DevBuf iso_spec, iso_out, iso_mass, spec_mass, spec_radius;          // static tables
@@ -890,22 +883,17 @@ static long long run_planes(BuilderState *b, const Options &o, const Molecules &
   BCUDA(cudaMemsetAsync(d_cisobeg, 0, (size_t)nplanes * (niso + 1) * 8, s));
   BCUDA(cudaMemsetAsync(d_total, 0, (size_t)nplanes * 8, s));
   const int *d_iso_out = (const int *)w.iso_out.p;
-  if (b->nlines > 0) {
-    PhaseTimer pt(b, "kmax", s);
-    const int nb = (int)std::min<long long>(148 * 4, (b->nlines + 255) / 256);
-    kmax_kernel<<<dim3(nb, nplanes), 256, 0, s>>>(b->d_wavn, b->d_elow, b->d_gf, b->d_isoid, b->d_inrange,
-                                                  b->nlines, d_T, d_facfull, niso, d_iso_out,
-                                                  (unsigned long long *)d_kmax, nout);
-    BCUDA(cudaGetLastError());
-  }
   PlaneArgs pa;
   pa.gstart = b->d_gstart; pa.giso = b->d_giso; pa.wavn = b->d_c_wavn; pa.elow = b->d_c_elow; pa.gf = b->d_c_gf;
-  pa.ngroups = b->ngroups; pa.plane_T = d_T; pa.plane_fac2 = d_fac2; pa.kmax = d_kmax; pa.iso_out = d_iso_out;
-  pa.niso = niso; pa.ethresh = o.ethreshold; pa.nblk = nblk;
+  pa.ngroups = b->ngroups; pa.plane_T = d_T; pa.plane_fac2 = d_fac2; pa.plane_facfull = d_facfull;
+  pa.kmax = d_kmax; pa.S = w.S.get<double>((size_t)nplanes * std::max<long long>(1, b->ngroups));
+  pa.iso_out = d_iso_out; pa.niso = niso; pa.nout = nout; pa.ethresh = o.ethreshold; pa.nblk = nblk;
+  pa.wn_lo = b->wn_lo; pa.own_last = b->wn_lo + (double)(b->nowns - 1) * b->odwn;
   std::vector<long long> total(nplanes, 0), base(nplanes, 0);
   long long pool = 0;
   if (b->ngroups > 0) {
     PhaseTimer pt(b, "strength", s);
+    strength_kmax_kernel<<<dim3(nblk, nplanes), kCompactThreads, 0, s>>>(pa);
     strength_count_kernel<<<dim3(nblk, nplanes), kCompactThreads, 0, s>>>(pa, d_blk);
     block_scan_kernel<<<nplanes, 1024, 0, s>>>(d_blk, nblk, d_total);
     BCUDA(cudaGetLastError());
@@ -966,7 +954,9 @@ static long long run_planes(BuilderState *b, const Options &o, const Molecules &
 // planes per batch: bounded by the output buffer (2 GB) -- one plane is nlayer * ngmol * nwave doubles
 static int planes_per_batch(const BuilderState *b) {
   const size_t plane_bytes = (size_t)b->nlayer * b->ngmol * b->nwave * 8;
-  return (int)std::max<size_t>(1, std::min<size_t>(16, ((size_t)2 << 30) / std::max<size_t>(1, plane_bytes)));
+  const size_t by_out = ((size_t)2 << 30) / std::max<size_t>(1, plane_bytes);
+  const size_t by_S = ((size_t)8 << 30) / std::max<size_t>(1, (size_t)b->ngroups * 8);   // strengths [plane][group]
+  return (int)std::max<size_t>(1, std::min<size_t>(16, std::min(by_out, by_S)));
 }
 
 static void ensure_builder(BuilderState *&b, const Options &o, const Atmosphere &a,
@@ -1045,7 +1035,8 @@ void builder_lbl_cells(BuilderState *&b, const Options &o, const Atmosphere &a, 
   }
   // bound the per-batch work arrays: block counters are nblk ints per plane
   const long long nblk = std::max<long long>(1, (b->ngroups + kCompactThreads - 1) / kCompactThreads);
-  const int maxp = (int)std::max<long long>(1, std::min<long long>(16384, ((long long)1 << 28) / nblk));
+  const long long by_S = ((long long)8 << 30) / std::max<long long>(1, b->ngroups * 8);     // strengths [plane][group]
+  const int maxp = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(16384, by_S), ((long long)1 << 28) / nblk));
   std::vector<int> cplane;
   std::vector<double> pZ;
   for (int c0 = 0; c0 < ncell; c0 += maxp) {
@@ -1172,7 +1163,7 @@ void builder_free(BuilderState *b) {
   for (void *p : ptrs) if (p) cudaFree(p);
   if (b->work) {
     PlaneWork &w = *b->work;
-    DevBuf *bufs[] = {&w.T, &w.facfull, &w.fac2, &w.kmax, &w.blk, &w.total, &w.base, &w.cisobeg,
+    DevBuf *bufs[] = {&w.T, &w.facfull, &w.fac2, &w.kmax, &w.S, &w.blk, &w.total, &w.base, &w.cisobeg,
                       &w.c_iown, &w.c_idwn, &w.c_wavn, &w.c_S, &w.cell_plane, &w.cell_out, &w.cellinfo,
                       &w.iso_spec, &w.iso_out, &w.iso_mass, &w.spec_mass, &w.spec_radius};
     for (DevBuf *d : bufs) d->release();
