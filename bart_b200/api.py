@@ -72,6 +72,8 @@ def lib():
     L.bart_comm_unique_id.argtypes = [C.c_char_p]
     L.bart_comm_init.argtypes = [C.c_int, C.c_int, C.c_char_p]
     L.bart_comm_allgather.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong]
+    L.bart_bandflux_allgather_device.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.bart_comm_p2p.restype = C.c_int
     L.bart_build_opacity_slice.argtypes = [C.c_int, C.c_int, dp]
     L.bart_builder_stats.restype = C.c_longlong
     L.bart_builder_stats.argtypes = [C.POINTER(C.c_longlong)] * 3

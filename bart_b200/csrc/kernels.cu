@@ -17,6 +17,7 @@
 #include "column_math.cuh"
 #include "kernels.hpp"
 #include <cuda_runtime.h>
+#include <cstring>
 
 namespace bart {
 
@@ -447,32 +448,98 @@ __global__ void grid_relayout_kernel(const double *__restrict__ in, double *__re
 // ---------------------------------------------------------------------------------------
 // K4 band integration: one CTA per (model, filter); trapezoid of (spectrum/star*rprs^2)*weight
 // over the filter's contiguous sample range (wine.py:177-199, BARTfunc.py:386-396).
+//
+// Fused all-gather: with a peer window the CTA also stores its band flux straight into
+// every rank's window over NVLink (slot = generation parity, block = this rank), and the last CTA
+// of the launch -- after a system-scope fence -- releases this rank's arrival flag on every peer.
+// No NCCL call, no extra launch on the producer side; peer_wait_copy_kernel is the consumer.
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+__device__ __forceinline__ void peer_announce(const PeerOut &po) {
+  __threadfence_system();
+  const unsigned long long g = *po.gen;
+  for (int r = 0; r < po.world; r++) st_release_sys(po.flags[r] + po.rank, g + 1);
+}
+
 __global__ void __launch_bounds__(128)
 band_integrate_kernel(const double *__restrict__ spectra, const double *__restrict__ wn,
                       const int *__restrict__ fstart, const int *__restrict__ fcount,
                       const int *__restrict__ foffset, const double *__restrict__ weight,
                       const double *__restrict__ star, double rprs2, const int *__restrict__ status,
-                      double *__restrict__ bandflux, int nfilters, int nwave) {
+                      double *__restrict__ bandflux, int nfilters, int nwave, PeerOut po) {
   const int m = blockIdx.x, f = blockIdx.y;
-  double *out = bandflux + (size_t)m * nfilters + f;
-  if (status && status[m] != 0) { if (threadIdx.x == 0) *out = -1.0; return; }
-  const int s0 = fstart[f], n = fcount[f], off = foffset[f];
-  const double *sp = spectra + (size_t)m * nwave + s0;
-  const double *x = wn + s0;
-  const double *wt = weight + off;
-  const double *st = star ? star + off : nullptr;
+  const bool rejected = status && status[m] != 0;        // CTA-uniform
   double acc = 0.0;
-  for (int k = threadIdx.x; k < n - 1; k += blockDim.x) {
-    double y0 = sp[k], y1 = sp[k + 1];
-    if (st) { y0 = y0 / st[k] * rprs2; y1 = y1 / st[k + 1] * rprs2; }
-    acc += (x[k + 1] - x[k]) * (y1 * wt[k + 1] + y0 * wt[k]);
+  if (!rejected) {
+    const int s0 = fstart[f], n = fcount[f], off = foffset[f];
+    const double *sp = spectra + (size_t)m * nwave + s0;
+    const double *x = wn + s0;
+    const double *wt = weight + off;
+    const double *st = star ? star + off : nullptr;
+    for (int k = threadIdx.x; k < n - 1; k += blockDim.x) {
+      double y0 = sp[k], y1 = sp[k + 1];
+      if (st) { y0 = y0 / st[k] * rprs2; y1 = y1 / st[k + 1] * rprs2; }
+      acc += (x[k + 1] - x[k]) * (y1 * wt[k + 1] + y0 * wt[k]);
+    }
   }
   // fixed-shape reduction: deterministic for a given launch configuration
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
   __shared__ double s_part[4];
   if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
   __syncthreads();
-  if (threadIdx.x == 0) *out = 0.5 * ((s_part[0] + s_part[1]) + (s_part[2] + s_part[3]));
+  if (threadIdx.x != 0) return;
+  const double v = rejected ? -1.0 : 0.5 * ((s_part[0] + s_part[1]) + (s_part[2] + s_part[3]));
+  const size_t idx = (size_t)m * nfilters + f;
+  bandflux[idx] = v;
+  if (po.world <= 0) return;
+  const size_t slot = (size_t)(*po.gen & 1ull) * po.world * po.cap + (size_t)po.rank * po.cap;
+  for (int r = 0; r < po.world; r++) po.win[r][slot + idx] = v;
+  __threadfence_system();
+  const unsigned int total = gridDim.x * gridDim.y;
+  if (atomicAdd(po.done, 1u) == total - 1) {             // last CTA: every store above is visible
+    *po.done = 0;
+    peer_announce(po);
+  }
+}
+
+__global__ void peer_signal_kernel(PeerOut po) { peer_announce(po); }
+
+__global__ void __launch_bounds__(256)
+peer_wait_copy_kernel(const double *__restrict__ win, unsigned long long *flags,
+                      unsigned long long *gen, int world, long long cap, long long count,
+                      double *__restrict__ out, int *err) {
+  __shared__ int s_bad;
+  const unsigned long long g = *gen;
+  if (threadIdx.x == 0) s_bad = 0;
+  __syncthreads();
+  if (threadIdx.x < world) {
+    const unsigned long long t0 = global_ns();
+    while (ld_acquire_sys(flags + threadIdx.x) < g + 1) {
+      if (global_ns() - t0 > 10000000000ull) { s_bad = 1; break; }      // 10 s: a peer died
+      __nanosleep(200);
+    }
+  }
+  __syncthreads();
+  if (s_bad) { if (threadIdx.x == 0) *err = 1; }
+  const double *src = win + (size_t)(g & 1ull) * world * cap;
+  for (long long i = threadIdx.x; i < (long long)world * count; i += blockDim.x) {
+    const long long r = i / count, k = i - r * count;
+    out[i] = __ldcg(src + r * cap + k);                   // written by peers: bypass L1
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *gen = g + 1;
 }
 
 // L2 flush helper: stream-write a buffer larger than the L2
@@ -645,10 +712,21 @@ void launch_extinction(const DevConfig &c, const double *tabs, double *ext, int 
 void launch_band_integrate(const double *spectra, const double *wn, const int *fstart,
                            const int *fcount, const int *foffset, const double *weight,
                            const double *star, double rprs2, const int *status, double *bandflux,
-                           int nfilters, int nwave, int nmodels, cudaStream_t s) {
+                           int nfilters, int nwave, int nmodels, cudaStream_t s,
+                           const PeerOut *peers) {
+  PeerOut po;
+  if (peers) po = *peers; else { memset(&po, 0, sizeof(po)); }
   dim3 grid((unsigned)nmodels, (unsigned)nfilters);
   band_integrate_kernel<<<grid, 128, 0, s>>>(spectra, wn, fstart, fcount, foffset, weight, star,
-                                             rprs2, status, bandflux, nfilters, nwave);
+                                             rprs2, status, bandflux, nfilters, nwave, po);
+}
+
+void launch_peer_signal(const PeerOut &po, cudaStream_t s) { peer_signal_kernel<<<1, 1, 0, s>>>(po); }
+
+void launch_peer_wait_copy(const double *win_local, unsigned long long *flags_local,
+                           unsigned long long *gen, int world, long long cap, long long count,
+                           double *out, int *err, cudaStream_t s) {
+  peer_wait_copy_kernel<<<1, 256, 0, s>>>(win_local, flags_local, gen, world, cap, count, out, err);
 }
 
 void launch_fill(double *p, size_t n, double v, cudaStream_t s) {

@@ -27,10 +27,30 @@ void launch_merge_status(int *status, const int *status_col, int nmodels, cudaSt
 // mol_only: 0 = total extinction, 1 = molecular lines only, 2 = CIA only
 void launch_extinction(const DevConfig &c, const double *tabs, double *ext, int nmodels,
                        int mol_only, int layer_splits, int use_tma, cudaStream_t s);
+// Peer window of the fused band-integration + all-gather (one process per GPU, windows mapped
+// through CUDA IPC over NVLink/NVSwitch).  win[r] / flags[r] are rank r's window and arrival
+// flags as seen from this process; a window holds 2 slots x world x cap doubles.
+constexpr int kMaxPeers = 8;
+struct PeerOut {
+  double *win[kMaxPeers];
+  unsigned long long *flags[kMaxPeers];
+  int world, rank;                    // world == 0: no peers (plain band integration)
+  long long cap;                      // doubles per rank per slot
+  const unsigned long long *gen;      // generation counter (device; advanced by the wait kernel)
+  unsigned int *done;                 // CTA completion counter of the launch
+};
+// waits until every rank's block of generation *gen has arrived in the local window, copies
+// world x count doubles to `out` ([rank][count]) and advances *gen; *err is set on a time-out
+void launch_peer_wait_copy(const double *win_local, unsigned long long *flags_local,
+                           unsigned long long *gen, int world, long long cap, long long count,
+                           double *out, int *err, cudaStream_t s);
+// a rank with no model in this generation still has to announce itself
+void launch_peer_signal(const PeerOut &po, cudaStream_t s);
 void launch_band_integrate(const double *spectra, const double *wn, const int *fstart,
                            const int *fcount, const int *foffset, const double *weight,
                            const double *star, double rprs2, const int *status, double *bandflux,
-                           int nfilters, int nwave, int nmodels, cudaStream_t s);
+                           int nfilters, int nwave, int nmodels, cudaStream_t s,
+                           const PeerOut *peers = nullptr);
 void launch_fill(double *p, size_t n, double v, cudaStream_t s);
 void upload_exp_table(cudaStream_t s);
 // [cell][mol][wave] (file order) -> [cell][wave][gms] (device order), ncells (layer, T) cells

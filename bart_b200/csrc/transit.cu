@@ -139,6 +139,14 @@ struct State {
   void *nccl_lib = nullptr;
   void *nccl_comm = nullptr;
   int rank = 0, world = 1;
+  // peer window of the fused band-integration + all-gather (kernels.hpp PeerOut)
+  bool p2p = false;
+  char *pw_base = nullptr;                 // local allocation: window | flags | gen | done | err
+  void *pw_peer[kMaxPeers] = {};           // peers' allocations mapped through CUDA IPC
+  long long pw_cap = 0;
+  PeerOut pw{};
+  unsigned long long *pw_gen = nullptr, *pw_flags = nullptr;
+  int *pw_err = nullptr;
   // builder
   BuilderState *builder = nullptr;
   // line-by-line forward mode (no opacity file)
@@ -646,13 +654,32 @@ static void run_models_device(const double *d_prof, int nmodels, int n_in, doubl
   G.last_batch = nmodels;
 }
 
-static void band_device(const double *d_spec, int nmodels, const int *d_status, double *d_band) {
+static void band_device(const double *d_spec, int nmodels, const int *d_status, double *d_band,
+                        bool to_peers = false) {
   if (G.nfilters <= 0) fail("bart_set_filters has not been called");
+  if (to_peers && nmodels <= 0) {          // nothing to integrate: still announce this rank
+    KernelScope ks("peer_signal");
+    launch_peer_signal(G.pw, G.stream);
+    check_launch("peer_signal");
+    return;
+  }
   KernelScope ks("band_integrate");
   launch_band_integrate(d_spec, G.d_wn.p, G.d_fstart.p, G.d_fcount.p, G.d_foffset.p, G.d_fweight.p,
                         G.have_star ? G.d_fstar.p : nullptr, G.rprs2, d_status, d_band, G.nfilters,
-                        G.dc.nwave, nmodels, G.stream);
+                        G.dc.nwave, nmodels, G.stream, to_peers ? &G.pw : nullptr);
   check_launch("band_integrate");
+}
+
+// consumer side of the fused all-gather: wait for every rank's block, copy to d_all[rank][count]
+static void peer_gather(long long count_per_rank, double *d_all) {
+  KernelScope ks("peer_wait_copy");
+  launch_peer_wait_copy((const double *)G.pw_base, G.pw_flags, G.pw_gen, G.world, G.pw_cap,
+                        count_per_rank, d_all, G.pw_err, G.stream);
+  check_launch("peer_wait_copy");
+}
+
+static bool p2p_usable(long long count_per_rank) {
+  return G.p2p && G.world > 1 && count_per_rank <= G.pw_cap;
 }
 
 
@@ -682,11 +709,12 @@ static void ensure_params_buffers(int nmodels) {
   prepare_batch(nmodels, n_in);
 }
 
-static void params_to_bandflux_queued(const double *d_params, int nmodels, int npars, double *d_band) {
+static void params_to_bandflux_queued(const double *d_params, int nmodels, int npars, double *d_band,
+                                      bool to_peers = false) {
   const DevConfig &c = G.dc;
   const ConvConfig &cc = G.conv;
   if (npars != cc.npars) fail("parameter vectors have %d entries, the converter expects %d", npars, cc.npars);
-  if (nmodels <= 0) return;
+  if (nmodels <= 0) { if (to_peers) band_device(nullptr, 0, nullptr, d_band, true); return; }
   const int n_in = (c.nspec + 1) * c.nlayer;
   ConvKnobs kn{G.d_kr0.p, G.d_kcloud.p, G.d_klogext.p, G.d_kflag.p};
   {
@@ -708,7 +736,7 @@ static void params_to_bandflux_queued(const double *d_params, int nmodels, int n
   G.knobs = saved;
   G.knob_models = saved_models;
   G.last_batch = nmodels;
-  band_device(G.d_spec.p, nmodels, G.d_status.p, d_band);
+  band_device(G.d_spec.p, nmodels, G.d_status.p, d_band, to_peers);
 }
 
 static const double *mcmc_evaluate_queued(const double *d_params);
@@ -741,9 +769,15 @@ static const double *mcmc_evaluate_queued(const double *d_params) {
   McmcDev &mc = G.mc;
   const int nloc = G.mc_hi - G.mc_lo;
   const double *src = d_params + (size_t)G.mc_lo * mc.npars;
-  params_to_bandflux_queued(src, nloc, mc.npars, G.d_mcband.p);
+  const long long per_rank = (long long)G.mc_pad * mc.ndata;
+  const bool fused = p2p_usable(per_rank);
+  params_to_bandflux_queued(src, nloc, mc.npars, G.d_mcband.p, fused);
   const double *models = G.d_mcband.p;
-  if (G.world > 1) {
+  if (fused) {
+    // band fluxes went straight into every rank's window from the band-integration kernel
+    peer_gather(per_rank, G.d_mcgather.p);
+    models = G.d_mcgather.p;
+  } else if (G.world > 1) {
     typedef int (*fn_allgather)(const void *, void *, size_t, int, void *, cudaStream_t);
     fn_allgather ag = (fn_allgather)dlsym(G.nccl_lib, "ncclAllGather");
     if (!ag || !G.nccl_comm) fail("multi-rank DE-MC needs bart_comm_init first");
@@ -1334,6 +1368,75 @@ static void *nccl_sym(const char *name) {
   return s;
 }
 
+// Peer windows: every rank allocates [2 slots][world][cap] doubles + arrival flags, the handles are
+// exchanged with one ncclAllGather, and each rank maps the others' windows through CUDA IPC
+// (NVLink/NVSwitch peer memory).  Any failure, on any rank, leaves every rank on the NCCL path.
+static void setup_peer_window() {
+  G.p2p = false;
+  const char *env = getenv("BART_P2P");
+  if (env && atoi(env) == 0) return;
+  if (G.world < 2 || G.world > kMaxPeers) return;
+  const long long cap = 1 << 18;                              // doubles per rank per slot (2 MiB)
+  const size_t win_bytes = (size_t)2 * G.world * cap * 8;
+  const size_t tail = 4096;                                   // flags[world] | gen | done | err
+  int ok = 1;
+  if (!G.pw_base) {
+    if (cudaMalloc((void **)&G.pw_base, win_bytes + tail) != cudaSuccess) { cudaGetLastError(); ok = 0; G.pw_base = nullptr; }
+    else CUDA_OK(cudaMemset(G.pw_base, 0, win_bytes + tail));
+  }
+  struct Msg { cudaIpcMemHandle_t h; int ok; int pad[15]; };   // 128 bytes
+  Msg mine; memset(&mine, 0, sizeof(mine));
+  if (ok && cudaIpcGetMemHandle(&mine.h, G.pw_base) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+  mine.ok = ok;
+  Msg *d_msg = nullptr, *d_all = nullptr;
+  CUDA_OK(cudaMalloc((void **)&d_msg, sizeof(Msg)));
+  CUDA_OK(cudaMalloc((void **)&d_all, sizeof(Msg) * G.world));
+  std::vector<Msg> all(G.world);
+  auto exchange = [&]() {
+    CUDA_OK(cudaMemcpy(d_msg, &mine, sizeof(Msg), cudaMemcpyHostToDevice));
+    int rc = ((fn_allgather)nccl_sym("ncclAllGather"))(d_msg, d_all, sizeof(Msg), 0 /*ncclInt8*/, G.nccl_comm, G.stream);
+    if (rc != 0) fail("ncclAllGather failed: %s", ((fn_errstr)nccl_sym("ncclGetErrorString"))(rc));
+    CUDA_OK(cudaStreamSynchronize(G.stream));
+    CUDA_OK(cudaMemcpy(all.data(), d_all, sizeof(Msg) * G.world, cudaMemcpyDeviceToHost));
+  };
+  exchange();
+  for (int r = 0; r < G.world; r++) ok = ok && all[r].ok;
+  if (ok)
+    for (int r = 0; r < G.world; r++) {
+      if (r == G.rank) { G.pw_peer[r] = G.pw_base; continue; }
+      if (cudaIpcOpenMemHandle(&G.pw_peer[r], all[r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError(); G.pw_peer[r] = nullptr; ok = 0;
+      }
+    }
+  mine.ok = ok;
+  exchange();                                                 // everyone mapped everyone?
+  for (int r = 0; r < G.world; r++) ok = ok && all[r].ok;
+  cudaFree(d_msg); cudaFree(d_all);
+  if (!ok) { warn(1, "peer windows unavailable (CUDA IPC); using ncclAllGather\n"); return; }
+  G.pw_cap = cap;
+  G.pw_flags = (unsigned long long *)(G.pw_base + win_bytes);
+  G.pw_gen = G.pw_flags + kMaxPeers;
+  unsigned int *done = (unsigned int *)(G.pw_gen + 1);
+  G.pw_err = (int *)(done + 2);
+  PeerOut &po = G.pw;
+  memset(&po, 0, sizeof(po));
+  for (int r = 0; r < G.world; r++) {
+    po.win[r] = (double *)G.pw_peer[r];
+    po.flags[r] = (unsigned long long *)((char *)G.pw_peer[r] + win_bytes);
+  }
+  po.world = G.world; po.rank = G.rank; po.cap = cap; po.gen = G.pw_gen; po.done = done;
+  G.p2p = true;
+}
+
+static void release_peer_window() {
+  for (int r = 0; r < kMaxPeers; r++) {
+    if (G.pw_peer[r] && G.pw_peer[r] != (void *)G.pw_base) cudaIpcCloseMemHandle(G.pw_peer[r]);
+    G.pw_peer[r] = nullptr;
+  }
+  if (G.pw_base) { cudaFree(G.pw_base); G.pw_base = nullptr; }
+  G.p2p = false;
+}
+
 int bart_comm_unique_id(char *id128) {
   API_BEGIN
   nccl_uid_t id;
@@ -1352,6 +1455,38 @@ int bart_comm_init(int rank, int world, const char *id128) {
   int rc = ((fn_initrank)nccl_sym("ncclCommInitRank"))(&G.nccl_comm, world, id, rank);
   if (rc != 0) fail("ncclCommInitRank failed: %s", ((fn_errstr)nccl_sym("ncclGetErrorString"))(rc));
   G.rank = rank; G.world = world;
+  setup_peer_window();
+  return 0;
+  API_END_INT
+}
+
+int bart_comm_p2p(void) { return G.p2p ? 1 : 0; }
+
+// forward models -> band fluxes -> all ranks' band fluxes in d_all[world][nmodels*nfilters], every
+// rank with the same nmodels.  Fused path: the band-integration kernel stores into the peers'
+// windows; fallback: ncclAllGather.
+int bart_bandflux_allgather_device(const double *d_profiles, int nmodels, int n_in,
+                                   double *d_bandflux, double *d_all) {
+  API_BEGIN
+  if (G.world <= 1 || !G.nccl_comm) fail("bart_comm_init has not been called");
+  const long long per_rank = (long long)nmodels * G.nfilters;
+  const bool fused = p2p_usable(per_rank);
+  G.d_spec.ensure((size_t)std::max(1, nmodels) * G.dc.nwave);
+  run_models_device(d_profiles, nmodels, n_in, G.d_spec.p);
+  band_device(G.d_spec.p, nmodels, G.d_status.p, d_bandflux, fused);
+  if (fused) peer_gather(per_rank, d_all);
+  else {
+    int rc = ((fn_allgather)nccl_sym("ncclAllGather"))(d_bandflux, d_all, (size_t)per_rank, 8 /*ncclFloat64*/,
+                                                        G.nccl_comm, G.stream);
+    if (rc != 0) fail("ncclAllGather failed: %s", ((fn_errstr)nccl_sym("ncclGetErrorString"))(rc));
+    G.launches++;
+  }
+  finish_stream();
+  if (fused) {
+    int err = 0;
+    CUDA_OK(cudaMemcpy(&err, G.pw_err, sizeof(int), cudaMemcpyDeviceToHost));
+    if (err) fail("peer window: a rank did not deliver its band fluxes within 10 s");
+  }
   return 0;
   API_END_INT
 }
@@ -1371,7 +1506,12 @@ int bart_comm_allgather(const double *d_send, double *d_recv, long long count_pe
 
 int bart_comm_finalize(void) {
   API_BEGIN
-  if (G.nccl_comm) { ((fn_destroy)nccl_sym("ncclCommDestroy"))(G.nccl_comm); G.nccl_comm = nullptr; }
+  if (G.nccl_comm) {
+    // nobody may unmap a window a peer is still writing: agree first
+    if (G.p2p) { finish_stream(); }
+    ((fn_destroy)nccl_sym("ncclCommDestroy"))(G.nccl_comm); G.nccl_comm = nullptr;
+  }
+  release_peer_window();
   return 0;
   API_END_INT
 }

@@ -208,9 +208,12 @@ def main():
     api._check(L.bart_memcpy_h2d(d_prof, models.ctypes.data, M * n_in * 8))
 
     def step_device():
-        api._check(L.bart_bandflux_batch_device(d_prof, M, n_in, d_band, None))
         if world > 1:
-            api._check(L.bart_comm_allgather(d_band, d_all, M * nf))
+            # band integration fused with the all-gather (stores into the peers' NVLink windows;
+            # ncclAllGather when the windows could not be mapped)
+            api._check(L.bart_bandflux_allgather_device(d_prof, M, n_in, d_band, d_all))
+        else:
+            api._check(L.bart_bandflux_batch_device(d_prof, M, n_in, d_band, None))
 
     def barrier():
         L.bart_sync()
@@ -303,8 +306,11 @@ def main():
                 "warmup": W, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "models_per_gpu_per_step": M,
-                           "parallelism": "chains partitioned by rank (dp%d); per-generation NCCL "
-                                          "all-gather of band fluxes" % world,
+                           "parallelism": "chains partitioned by rank (dp%d); per-generation all-gather "
+                                          "of band fluxes %s" % (world, "fused into the band-integration "
+                                          "kernel (stores into peer windows over NVLink)"
+                                          if world > 1 and L.bart_comm_p2p() else "(ncclAllGather)"
+                                          if world > 1 else "(single rank: none)"),
                            "l2": "flushed between steps (256 MB write); grid 209 MB > L2",
                            "device": info["name"], "sm_count": info["sm_count"]},
                 "roofline": roofline, "cpu_baseline": cpu,

@@ -165,6 +165,18 @@ int  bart_comm_unique_id(char *id128);
 int  bart_comm_init(int rank, int world, const char *id128);
 int  bart_comm_allgather(const double *d_send, double *d_recv, long long count_per_rank);
 int  bart_comm_finalize(void);
+/* Fused band integration + all-gather.  bart_comm_init also maps a small window of every peer
+ * GPU through CUDA IPC (NVLink/NVSwitch peer memory); when that succeeded on every rank
+ * (bart_comm_p2p() == 1; $BART_P2P=0 disables it) the band-integration kernel stores each band
+ * flux directly into all ranks' windows and releases a per-rank arrival flag, and a one-CTA
+ * consumer kernel waits for the flags -- no NCCL call on the per-generation path.  Used by the
+ * device-resident retrieval loop (part 3) and by:
+ * forward models of this rank's `nmodels` proposals -> d_bandflux[nmodels][nfilters] and every
+ * rank's block in d_all[world][nmodels][nfilters] (same nmodels on every rank); falls back to
+ * ncclAllGather when the windows are unavailable or too small.                             */
+int  bart_comm_p2p(void);
+int  bart_bandflux_allgather_device(const double *d_profiles, int nmodels, int n_in,
+                                    double *d_bandflux, double *d_all);
 
 /* Opacity-grid builder (--justOpacity; src/opacity.c:218-427, src/extinction.c:281-529,
  * pu/src/voigt.c).  transit_init builds the grid itself when the file is missing; these expose
