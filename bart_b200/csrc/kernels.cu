@@ -499,18 +499,41 @@ band_integrate_kernel(const double *__restrict__ spectra, const double *__restri
   __shared__ double s_part[4];
   if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
   __syncthreads();
-  if (threadIdx.x != 0) return;
-  const double v = rejected ? -1.0 : 0.5 * ((s_part[0] + s_part[1]) + (s_part[2] + s_part[3]));
+  __shared__ int s_copier;
   const size_t idx = (size_t)m * nfilters + f;
-  bandflux[idx] = v;
-  if (po.world <= 0) return;
-  const size_t slot = (size_t)(*po.gen & 1ull) * po.world * po.cap + (size_t)po.rank * po.cap;
-  for (int r = 0; r < po.world; r++) po.win[r][slot + idx] = v;
-  __threadfence_system();
-  const unsigned int total = gridDim.x * gridDim.y;
-  if (atomicAdd(po.done, 1u) == total - 1) {             // last CTA: every store above is visible
-    *po.done = 0;
-    peer_announce(po);
+  if (threadIdx.x == 0) {
+    bandflux[idx] = rejected ? -1.0 : 0.5 * ((s_part[0] + s_part[1]) + (s_part[2] + s_part[3]));
+    s_copier = 0;
+    if (po.world > 0) {
+      // models are handed to the peers in groups of kPeerGroup: the CTA that completes a group
+      // ships it (so the system-scope fences are per group, not per band flux)
+      __threadfence();
+      const int grp = m / kPeerGroup;
+      const int in_grp = (min((grp + 1) * kPeerGroup, (int)gridDim.x) - grp * kPeerGroup) * nfilters;
+      if (atomicAdd(po.grpcnt + grp, 1u) == (unsigned)in_grp - 1) { s_copier = 1; __threadfence(); }
+    }
+  }
+  __syncthreads();
+  if (!s_copier) return;
+  {
+    const int grp = m / kPeerGroup;
+    const size_t lo = (size_t)grp * kPeerGroup * nfilters;
+    const size_t hi = (size_t)min((grp + 1) * kPeerGroup, (int)gridDim.x) * nfilters;
+    const size_t slot = (size_t)(*po.gen & 1ull) * po.world * po.cap + (size_t)po.rank * po.cap;
+    for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+      const double v = __ldcg(bandflux + i);              // written by other CTAs: read at L2
+      for (int r = 0; r < po.world; r++) po.win[r][slot + i] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      po.grpcnt[grp] = 0;
+      const unsigned int ngrp = (gridDim.x + kPeerGroup - 1) / kPeerGroup;
+      if (atomicAdd(po.done, 1u) == ngrp - 1) {           // last group: everything is on its way
+        *po.done = 0;
+        peer_announce(po);
+      }
+    }
   }
 }
 

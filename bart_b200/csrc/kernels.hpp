@@ -31,13 +31,15 @@ void launch_extinction(const DevConfig &c, const double *tabs, double *ext, int 
 // through CUDA IPC over NVLink/NVSwitch).  win[r] / flags[r] are rank r's window and arrival
 // flags as seen from this process; a window holds 2 slots x world x cap doubles.
 constexpr int kMaxPeers = 8;
+constexpr int kPeerGroup = 64;        // models shipped to the peers per copier CTA
 struct PeerOut {
   double *win[kMaxPeers];
   unsigned long long *flags[kMaxPeers];
   int world, rank;                    // world == 0: no peers (plain band integration)
   long long cap;                      // doubles per rank per slot
   const unsigned long long *gen;      // generation counter (device; advanced by the wait kernel)
-  unsigned int *done;                 // CTA completion counter of the launch
+  unsigned int *done;                 // completed groups of the launch
+  unsigned int *grpcnt;               // [groups] completed CTAs per group of kPeerGroup models
 };
 // waits until every rank's block of generation *gen has arrived in the local window, copies
 // world x count doubles to `out` ([rank][count]) and advances *gen; *err is set on a time-out

@@ -1378,7 +1378,7 @@ static void setup_peer_window() {
   if (G.world < 2 || G.world > kMaxPeers) return;
   const long long cap = 1 << 18;                              // doubles per rank per slot (2 MiB)
   const size_t win_bytes = (size_t)2 * G.world * cap * 8;
-  const size_t tail = 4096;                                   // flags[world] | gen | done | err
+  const size_t tail = 4096 + ((size_t)cap / kPeerGroup + 1) * 4;   // flags[world] | gen | done | err | group counters
   int ok = 1;
   if (!G.pw_base) {
     if (cudaMalloc((void **)&G.pw_base, win_bytes + tail) != cudaSuccess) { cudaGetLastError(); ok = 0; G.pw_base = nullptr; }
@@ -1425,6 +1425,7 @@ static void setup_peer_window() {
     po.flags[r] = (unsigned long long *)((char *)G.pw_peer[r] + win_bytes);
   }
   po.world = G.world; po.rank = G.rank; po.cap = cap; po.gen = G.pw_gen; po.done = done;
+  po.grpcnt = (unsigned int *)(G.pw_base + win_bytes + 4096);
   G.p2p = true;
 }
 

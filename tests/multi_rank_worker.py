@@ -42,7 +42,25 @@ def main():
         uid = f.read()
     api._check(L.bart_comm_init(rank, world, uid))
     out = {"p2p": L.bart_comm_p2p()}
-    if mode.startswith("demc"):
+    if mode == "time":
+        # generations per second of the device-resident loop (graph replay) at MC3's population size
+        d = np.load(os.path.join(cases.GOLDEN_DIR, "retrieval_mc3_%s.npz" % name))
+        nch, ngen = spec["nchains"], int(os.environ.get("BART_TIME_GENS", "2000"))
+        stepsize = np.array(spec["stepsize"])
+        rng = np.random.RandomState(5)
+        p0 = np.repeat(np.atleast_2d(spec["params"]), nch, 0)
+        p0[:, stepsize > 0] += rng.normal(0, 0.01, (nch, int((stepsize > 0).sum())))
+        dr = driver.demc_draws(rng, nch, ngen, stepsize[stepsize > 0])
+        tr.mcmc_init(p0, spec["pmin"], spec["pmax"], stepsize, d["data"], d["uncert"])
+        warm = slice(0, 50)
+        tr.mcmc_run(dr["support"][warm], dr["r1"][:, warm], dr["r2"][:, warm], dr["unif"][warm], dr["ugamma"][warm])
+        rest = slice(50, ngen)
+        t0 = time.perf_counter()
+        tr.mcmc_run(dr["support"][rest], dr["r1"][:, rest], dr["r2"][:, rest], dr["unif"][rest], dr["ugamma"][rest])
+        dt = time.perf_counter() - t0
+        out.update(gens=ngen - 50, seconds=dt, us_per_generation=1e6 * dt / (ngen - 50),
+                   params=tr.mcmc_get("params"))
+    elif mode.startswith("demc"):
         d = np.load(os.path.join(cases.GOLDEN_DIR, "retrieval_mc3_%s.npz" % name))
         np.random.seed(spec["seed"])
         r = driver.run_demc(tr, d["data"], d["uncert"], spec["params"], spec["pmin"], spec["pmax"],
