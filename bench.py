@@ -302,6 +302,24 @@ def main():
             cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": kind,
                    "sample": "%d processes x 6 models of the same batch (run_transit wall time after 2 "
                              "warm-ups; reference writes its output spectrum to /dev/null)" % nproc}
+        # the other named throughput of the north star: the --justOpacity grid builder, on a bounded
+        # sample (its own process: the library holds one configuration per process)
+        builder = None
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_builder.py")],
+                                   capture_output=True, text=True, timeout=300)
+                b = json.loads(r.stdout.strip().splitlines()[-1])
+                builder = {"metric": "opacity_grid_builder_line_cells_per_s",
+                           "value": b["line_cells_per_s_device"], "unit": "lines x (T,layer) cells / s",
+                           "wall_value": b["line_cells_per_s_wall"],
+                           "sample": "%d synthetic lines x %d layers x %d temperature planes on the W12 "
+                                     "wavenumber grid (%d samples, wnosamp %d)" % (
+                                         b["nlines_in_range"], b["shape"]["nlayer"], b["shape"]["ntemp_built"],
+                                         b["shape"]["nwave"], b["shape"]["wnosamp"]),
+                           "per_slice_ms": b["per_slice_ms"]}
+            except Exception as e:                    # the headline line must not depend on it
+                builder = {"error": repr(e)[:200]}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": W, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -318,6 +336,8 @@ def main():
                         "d2h_bytes_per_step": M * nw * 8 + M * 4,
                         "path": "bart_run_batch: pinned host profiles -> H2D -> kernels -> D2H spectra"},
                 "gpu_launches": int(launches), "kernels": stats, "clocks": clocks}
+        if builder is not None:
+            line["builder"] = builder
         print(json.dumps(line))
     if dist is not None:
         L.bart_comm_finalize()
