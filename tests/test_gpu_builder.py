@@ -91,3 +91,30 @@ def test_temperature_sharded_build(api, workdir):
     assert np.array_equal(np.concatenate(parts, axis=1), full)
     assert relerr(full, g["grid"]) < TOL
     tr.free_memory()
+
+
+def test_cli_temperature_slices_assemble_the_file(api, workdir):
+    """`transit -c cfg --justOpacity` run as separate processes with $BART_TSLICE (one per GPU on a
+    multi-GPU box; sequential here): every process streams its planes to their offsets in the SAME
+    file (opacity.c:418-421 order); the result equals the single-process file byte for byte."""
+    import subprocess
+    from bart_b200 import synth
+    case = cases.build_builder_case("build_h2o_ch4", workdir)
+    g = np.load(cases.golden_path("build_h2o_ch4"))
+    exe = os.path.join(cases.ROOT, "bart_b200", "bin", "transit")
+    nt = len(g["temps"])
+    env = dict(os.environ)
+    for sl in ("%d:%d" % (nt // 2, nt), "0:%d" % (nt // 2)):           # header written by the 0: slice
+        env["BART_TSLICE"] = sl
+        r = subprocess.run([exe, "-c", case["cfg"], "--justOpacity"], env=env, capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    sliced = np.fromfile(case["opacity"], dtype=np.uint8)
+    assert sliced.size == int(g["file_bytes"])
+    os.remove(case["opacity"])
+    env.pop("BART_TSLICE")
+    r = subprocess.run([exe, "-c", case["cfg"], "--justOpacity"], env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    whole = np.fromfile(case["opacity"], dtype=np.uint8)
+    assert np.array_equal(sliced, whole)
+    mine = synth.read_opacity(case["opacity"], mmap=False)
+    assert relerr(mine["o"], g["grid"]) < TOL
