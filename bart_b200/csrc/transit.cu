@@ -509,7 +509,10 @@ static void do_init(int argc, char **argv) {
     c.gtemp = G.d_gtemp.p;
     c.gmol_spec[0] = 0;
   } else {
-  if (!have_file) {
+  // a temperature-sliced build ($BART_TSLICE, one process per GPU) writes into the file the other
+  // slices are creating: its existence does not mean it is complete
+  const bool sliced = o.justOpacity && getenv("BART_TSLICE") != nullptr;
+  if (!have_file || sliced) {
     if (!G.tli.present) fail("Cannot build the opacity grid '%s': no TLI line list (linedb) given.", o.opacityfile.c_str());
     info(2, "Calculating new grid of opacities: '%s'.\n", o.opacityfile.c_str());
     builder_run_and_write(G.builder, G.opt, G.atm, G.mol, G.tli, G.wn, G.stream, o.opacityfile);
