@@ -3,6 +3,7 @@ bart_run_batch compute every layer's molecular extinction with the builder kerne
 own temperature (tau.c:163-175,253-264 -> computemolext(permol=0)) and feed the column kernels.
 Checked through the C ABI against the oracle and against golden vectors of the UNMODIFIED
 reference run without `opacityfile`."""
+import os
 import numpy as np
 import pytest
 
@@ -67,3 +68,35 @@ def test_lbl_rejects_out_of_range_temperature(api, workdir):
     ok, _ = tr.run_batch(models)
     assert np.array_equal(spectra[1], ok[1])
     tr.free_memory()
+
+
+def test_lbl_equals_grid_mode_at_a_grid_temperature(api, workdir):
+    """Cross-check of the two opacity paths: for an isothermal atmosphere whose temperature is a
+    node of the opacity grid the T-interpolation is exact, and with a single line-list molecule
+    computemolext(permol=0) = density x computemolext(permol=1) -- so the forward model without an
+    opacity file must reproduce the one that reads the grid built from the same line list."""
+    from bart_b200 import synth
+    kw = dict(shape="tiny", solution="eclipse", nlayer=16, with_grid=False, nlines=2500, seed=5152,
+              ethresh=1e-6, tlow=400.0, thigh=2800.0, tempdelt=600.0)
+    grid_case = synth.make_case(os.path.join(workdir, "lbl_vs_grid_g"), **kw)
+    if os.path.exists(grid_case["opacity"]):
+        os.remove(grid_case["opacity"])
+    lbl_case = synth.make_case(os.path.join(workdir, "lbl_vs_grid_l"), no_opacity=True, **kw)
+    models = synth.make_models(grid_case, 2, seed=63, molfit=("CH4",))
+    nl = grid_case["nlayer"]
+    models[0, :nl] = 1000.0                              # grid nodes: 400, 1000, 1600, 2200, 2800
+    models[1, :nl] = 1600.0
+    tr = api.Transit(grid_case["cfg"])                   # builds the grid file first (missing)
+    ext_g = tr.extinction_batch(models, total=False)
+    spec_g, st = tr.run_batch(models)
+    assert (st == 0).all()
+    tr.free_memory()
+    tr = api.Transit(lbl_case["cfg"])
+    ext_l = tr.extinction_batch(models, total=False)
+    spec_l, st = tr.run_batch(models)
+    assert (st == 0).all()
+    tr.free_memory()
+    assert (ext_l > 0).any()
+    assert np.array_equal(ext_l > 0, ext_g > 0)
+    assert relerr(ext_l, ext_g) < 1e-12
+    assert relerr(spec_l, spec_g) < 1e-12
