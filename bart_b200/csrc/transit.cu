@@ -98,6 +98,7 @@ struct State {
   int device = -1;
   cudaStream_t stream = nullptr;          // compute (and default copy) stream
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;   // copy streams of the pipelined host path
+  std::vector<cudaEvent_t> ev_pool;                // its events (created once)
   Options opt;
   Atmosphere atm;
   Molecules mol;
@@ -1067,21 +1068,33 @@ int bart_run_batch(const double *profiles, int nmodels, int n_in, double *spectr
   // Software pipeline over chunks of the batch: H2D of chunk k+1 and D2H of chunk k-1 run on
   // their own streams (both copy engines) while chunk k computes.  Buffers are indexed by the
   // global model number, so chunks never alias.
-  int nchunks = std::min(8, std::max(1, nmodels / 512));
-  if (G.keep || G.profile) nchunks = 1;
-  const int per = (nmodels + nchunks - 1) / nchunks;
-  std::vector<cudaEvent_t> ev_in(nchunks), ev_k(nchunks);
-  for (int c = 0; c < nchunks; c++) {
-    CUDA_OK(cudaEventCreateWithFlags(&ev_in[c], cudaEventDisableTiming));
-    CUDA_OK(cudaEventCreateWithFlags(&ev_k[c], cudaEventDisableTiming));
+  // Chunk schedule: small chunks at both ends keep the un-overlapped prologue (first H2D) and
+  // epilogue (last D2H) short, 512-model chunks in the middle keep the kernels' tails rare.
+  std::vector<int> sizes;
+  if (G.keep || G.profile || G.lbl || nmodels < 1024) sizes.push_back(nmodels);
+  else {
+    const int ramp[2] = {128, 256};
+    int left = nmodels;
+    std::vector<int> head, tail;
+    for (int k = 0; k < 2 && left >= 4 * ramp[k]; k++) { head.push_back(ramp[k]); tail.push_back(ramp[k]); left -= 2 * ramp[k]; }
+    int nmid = std::max(1, left / 512);
+    for (int k = 0; k < nmid; k++) sizes.push_back(left / nmid + (k < left % nmid ? 1 : 0));
+    sizes.insert(sizes.begin(), head.begin(), head.end());
+    sizes.insert(sizes.end(), tail.rbegin(), tail.rend());
   }
-  cudaEvent_t ev_start;
-  CUDA_OK(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
+  const int nchunks = (int)sizes.size();
+  while ((int)G.ev_pool.size() < 2 * nchunks + 1) {
+    cudaEvent_t e;
+    CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    G.ev_pool.push_back(e);
+  }
+  cudaEvent_t *ev_in = G.ev_pool.data(), *ev_k = G.ev_pool.data() + nchunks;
+  cudaEvent_t ev_start = G.ev_pool[2 * nchunks];
   CUDA_OK(cudaEventRecord(ev_start, G.stream));             // order after earlier work on the stream
   CUDA_OK(cudaStreamWaitEvent(G.s_h2d, ev_start, 0));
+  int off = 0;
   for (int c = 0; c < nchunks; c++) {
-    const int off = c * per, cnt = std::min(per, nmodels - off);
-    if (cnt <= 0) break;
+    const int cnt = sizes[c];
     CUDA_OK(cudaMemcpyAsync(G.d_prof.p + (size_t)off * n_in, profiles + (size_t)off * n_in,
                             (size_t)cnt * n_in * 8, cudaMemcpyHostToDevice, G.s_h2d));
     CUDA_OK(cudaEventRecord(ev_in[c], G.s_h2d));
@@ -1096,6 +1109,7 @@ int bart_run_batch(const double *profiles, int nmodels, int n_in, double *spectr
       CUDA_OK(cudaMemcpy2DAsync(spectra + (size_t)off * n_out, (size_t)n_out * 8,
                                 G.d_spec.p + (size_t)off * nw, (size_t)nw * 8, (size_t)nw * 8, cnt,
                                 cudaMemcpyDeviceToHost, G.s_d2h));
+    off += cnt;
   }
   if (status) {      // one small copy through pinned staging (a pageable target would block the loop)
     if ((size_t)nmodels > G.h_status_cap) {
@@ -1110,8 +1124,6 @@ int bart_run_batch(const double *profiles, int nmodels, int n_in, double *spectr
   if (e != cudaSuccess) fail("CUDA execution failed: %s", cudaGetErrorString(e));
   finish_stream();
   if (status) memcpy(status, G.h_status, nmodels * sizeof(int));
-  for (int c = 0; c < nchunks; c++) { cudaEventDestroy(ev_in[c]); cudaEventDestroy(ev_k[c]); }
-  cudaEventDestroy(ev_start);
   return 0;
   API_END_INT
 }
