@@ -210,7 +210,13 @@ transit_weights_kernel(DevConfig c, const double *__restrict__ tabs, double *__r
 // and the CTA leaves the chunk loop when every column has passed toomuch (tau.c:277-287), so the
 // work follows the deepest column of the tile.  Summation order per (d, w) is i = 0..d, the same
 // as the single-column form transit_column (tests/cpu_emu).
-constexpr int kTrW = 64, kTrThreads = 128, kTrLoadBatch = 5;
+// The CTA is warp-specialised: warps 4-7 (PRODUCERS) only do phase A and run ahead through the
+// chunks -- er[][] holds every layer, so they never wait for the consumers -- publishing each
+// chunk through a shared-memory counter; warps 0-3 (CONSUMERS) do phases B and C behind their own
+// named barrier.  The lookup's memory latency therefore overlaps the triangular product instead of
+// alternating with it, and the SM holds 16 warps instead of 8.
+constexpr int kTrW = 64, kTrThreads = 256, kTrCons = 128, kTrLoadBatch = 2, kTrMaxChunks = 16;
+__device__ __forceinline__ void bar_consumers() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 template <int NMOL, int NCIA, bool KEEP>
 __global__ void __launch_bounds__(kTrThreads, 2)
@@ -228,33 +234,67 @@ transit_tile_kernel(DevConfig c, const double *__restrict__ tabs, const double *
   double *s_er = s_wt + (size_t)nl * kTrRow;                   // [nl][kTrW]
   double *s_tau = s_er + (size_t)nl * kTrW;                    // [kTrChunk][kTrW]
   double *s_fd = s_tau + (size_t)kTrChunk * kTrW;              // [kTrChunk][kTrW] exp(-tau) b
+  __shared__ int s_ready[kTrMaxChunks];                        // producer warps that finished the chunk
+  __shared__ int s_stop, s_alive[2];                           // [chunk parity]
   const int m = blockIdx.x % nmodels;
   const int tile = blockIdx.x / nmodels;
-  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const bool producer = threadIdx.x >= kTrCons;
+  const int t = producer ? threadIdx.x - kTrCons : threadIdx.x;   // index inside the role
+  const int lane = t & 31, warp = t >> 5;
   const int wl = t & (kTrW - 1), dh = t >> 6;                  // lookup mapping: column, depth parity
   const int wcol = tile * kTrW + wl;
   const bool valid = wcol < c.nwave;
   const int w = valid ? wcol : c.nwave - 1;                    // columns past the end shadow the last one
   if (status[m] != 0) {                                        // rejected model: -1 fill
-    if (t < kTrW && valid) spectra[(size_t)m * c.nwave + w] = -1.0;
+    if (!producer && t < kTrW && valid) spectra[(size_t)m * c.nwave + w] = -1.0;
     return;
   }
-  if (t == 0) mbar_init(&bar_w, 1);
+  if (threadIdx.x == 0) { mbar_init(&bar_w, 1); s_stop = 0; s_alive[0] = s_alive[1] = 0; }
+  if (threadIdx.x < kTrMaxChunks) s_ready[threadIdx.x] = 0;
   stage_table(s_tab, tabs + (size_t)m * nd, nd, &bar, use_tma != 0, s_etab);
-  const double *wm = wts + (size_t)m * tr_stride(nl);
-  const ColPtrs P = col_ptrs<NCIA>(c, w);
+  __syncthreads();
+  const int nchunks = tr_nchunks(nl);
   const double wn = c.wn[w];
-  const double wn4 = (wn * wn) * (wn * wn);
+
+  if (producer) {
+    // ---- phase A for every chunk: kTrChunk / 2 layers per thread, batches of independent loads
+    const ColPtrs P = col_ptrs<NCIA>(c, w);
+    const double wn4 = (wn * wn) * (wn * wn);
+    for (int ch = 0; ch < nchunks; ch++) {
+      if (*(volatile int *)&s_stop) break;                     // every column is past toomuch
+      const int d0 = ch * kTrChunk;
+#pragma unroll
+      for (int j0 = 0; j0 < kTrChunk / 2; j0 += kTrLoadBatch) {
+        CellData<NMOL, NCIA> x[kTrLoadBatch];
+#pragma unroll
+        for (int j = 0; j < kTrLoadBatch; j++) {
+          const int d = d0 + dh + 2 * (j0 + j);
+          if (d < nl) cell_load<NMOL, NCIA>(c, P, s_tab + (size_t)d * nf, x[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < kTrLoadBatch; j++) {
+          const int d = d0 + dh + 2 * (j0 + j);
+          if (d < nl)
+            s_er[(size_t)d * kTrW + wl] = cell_combine<NMOL, NCIA>(c, P, s_tab + (size_t)d * nf, x[j], wn4, false);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) { __threadfence_block(); atomicAdd(&s_ready[ch], 1); }
+    }
+    return;
+  }
+
+  // ---- consumers
+  const double *wm = wts + (size_t)m * tr_stride(nl);
   double *tk = KEEP ? tau_keep + ((size_t)m * c.nwave + w) * nl : nullptr;
   // per-column state of phase C (threads 0..63)
   double S = 0.0, f1 = 0.0, f2 = 0.0, tau = 0.0, tau_prev = 0.0;
   int last = nl - 1;
   bool done = false;
   uint32_t wphase = 0;
-  const int nchunks = tr_nchunks(nl);
-  for (int ch = 0; ch < nchunks; ch++) {
-    const int d0 = ch * kTrChunk;
-    const int dn = min(kTrChunk, nl - d0);
+  bool pending = false;                                        // a weight copy is in flight
+  auto stage_weights = [&](int ch) {
+    pending = true;
     const int rows = tr_rows(nl, ch);
     const double *wsrc = wm + tr_chunk_off(nl, ch);
     if (use_tma) {
@@ -264,26 +304,19 @@ transit_tile_kernel(DevConfig c, const double *__restrict__ tabs, const double *
         bulk_g2s(s_wt, wsrc, bytes, &bar_w);
       }
     } else {
-      for (int i = t; i < rows * kTrRow; i += kTrThreads) s_wt[i] = wsrc[i];
+      for (int i = t; i < rows * kTrRow; i += kTrCons) s_wt[i] = wsrc[i];
     }
-    // ---- phase A: lookup, kTrChunk / 2 layers per thread in batches of independent loads
-#pragma unroll
-    for (int j0 = 0; j0 < kTrChunk / 2; j0 += kTrLoadBatch) {
-      CellData<NMOL, NCIA> x[kTrLoadBatch];
-#pragma unroll
-      for (int j = 0; j < kTrLoadBatch; j++) {
-        const int d = d0 + dh + 2 * (j0 + j);
-        if (d < nl) cell_load<NMOL, NCIA>(c, P, s_tab + (size_t)d * nf, x[j]);
-      }
-#pragma unroll
-      for (int j = 0; j < kTrLoadBatch; j++) {
-        const int d = d0 + dh + 2 * (j0 + j);
-        if (d < nl)
-          s_er[(size_t)d * kTrW + wl] = cell_combine<NMOL, NCIA>(c, P, s_tab + (size_t)d * nf, x[j], wn4, false);
-      }
-    }
-    __syncthreads();
+  };
+  stage_weights(0);
+  for (int ch = 0; ch < nchunks; ch++) {
+    const int d0 = ch * kTrChunk;
+    const int dn = min(kTrChunk, nl - d0);
+    // the chunk's extinction rows (and, by program order of the producers, all earlier ones)
+    while (*(volatile int *)&s_ready[ch] < kTrCons / 32) { }
+    __threadfence_block();
     if (use_tma) { mbar_wait(&bar_w, wphase); wphase ^= 1u; }
+    else bar_consumers();
+    pending = false;
     // ---- phase B: tau of depths d0 + 5 warp .. + 4 for columns 2 lane, 2 lane + 1
     {
       const int dg = d0 + kTrTD * warp;
@@ -320,7 +353,10 @@ transit_tile_kernel(DevConfig c, const double *__restrict__ tabs, const double *
           }
       }
     }
-    __syncthreads();
+    if (t == 0) s_alive[ch & 1] = 0;                           // last read two chunks ago
+    bar_consumers();
+    // the weight buffer is free: fetch the next chunk's while phase C runs
+    if (ch + 1 < nchunks) stage_weights(ch + 1);
     // ---- phase C: one thread per column; branch-free so the loads and the panel products of the
     // chunk overlap (only the running sum S is a dependent chain, in the reference's order)
     if (t < kTrW && !done) {
@@ -346,9 +382,13 @@ transit_tile_kernel(DevConfig c, const double *__restrict__ tabs, const double *
       tau_prev = jl > 0 ? tc[(size_t)(jl - 1) * kTrW] : tau;     // tau still holds depth d0-1's
       tau = tc[(size_t)jl * kTrW];
       if (jstop < dn) { last = d0 + jstop; done = true; }
+      if (!done) s_alive[ch & 1] = 1;
     }
-    if (__syncthreads_and(t >= kTrW || done)) break;
+    bar_consumers();
+    if (!*(volatile int *)&s_alive[ch & 1]) { if (t == 0) s_stop = 1; break; }
   }
+  // a bulk copy issued for a chunk that is never consumed must land before the CTA exits
+  if (use_tma && pending) mbar_wait(&bar_w, wphase);
   if (t >= kTrW || !valid) return;
   if (KEEP) last_keep[(size_t)m * c.nwave + w] = last;
   if (c.modlevel == -1) {                                      // modulationm1 (slantpath.c:446-473)
@@ -676,6 +716,7 @@ static void launch_transit_t(const DevConfig &c, const double *tabs, const doubl
     configured = smem;
   }
   const int tiles = (c.nwave + kTrW - 1) / kTrW;
+  if (tr_nchunks(c.nlayer) > kTrMaxChunks) return;             // launch_transit checks and reports
   transit_tile_kernel<NMOL, NCIA, KEEP><<<(unsigned)((size_t)tiles * nmodels), kTrThreads, smem, s>>>(
       c, tabs, wts, status, status_col, spectra, tau_keep, last_keep, nmodels, use_tma);
 }

@@ -426,6 +426,7 @@ static void do_init(int argc, char **argv) {
   read_tli_header(o.linedb, G.tli);
   const int nl = G.atm.nlayer(), ns = G.atm.nspec(), nw = (int)G.wn.size();
   if (ns > kMaxSpec) fail("at most %d atmospheric species are supported", kMaxSpec);
+  if (o.solution != "eclipse" && nl > 320) fail("transit geometry supports at most 320 layers (%d given)", nl);
   // makeradsample's temperature check against the TLI range (makesample.c:488-503)
   for (int i = 0; i < nl; i++) {
     if (G.atm.temp[i] * G.atm.tfct < G.tli.tmin)
