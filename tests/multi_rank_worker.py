@@ -18,7 +18,7 @@ def main():
     import cases
     from bart_b200 import api, driver
     L = api.lib()
-    name = "retr_small4_transit" if mode == "demc_transit" else "retr_tiny_eclipse"
+    name = "retr_small4_transit" if mode in ("demc_transit", "snooker_transit") else "retr_tiny_eclipse"
     case, spec, extra = cases.build_retrieval(name, os.path.join(workdir, "rank%d" % rank))
     tr = api.Transit(case["cfg"], device=rank)
     wn = tr.get_waveno_arr()
@@ -60,6 +60,14 @@ def main():
         dt = time.perf_counter() - t0
         out.update(gens=ngen - 50, seconds=dt, us_per_generation=1e6 * dt / (ngen - 50),
                    params=tr.mcmc_get("params"))
+    elif mode.startswith("snooker"):
+        thinning = 3
+        d = np.load(os.path.join(cases.GOLDEN_DIR, "retrieval_snooker_%s_thin%d.npz" % (name, thinning)))
+        np.random.seed(spec["seed"] + thinning)
+        r = driver.run_snooker(tr, d["data"], d["uncert"], spec["params"], spec["pmin"], spec["pmax"],
+                               spec["stepsize"], spec["numit"], spec["nchains"], burnin=spec["burnin"],
+                               thinning=thinning)
+        out.update(allparams=r["allparams"], bestp=r["bestp"], numaccept=r["numaccept"], Z=r["Z"])
     elif mode.startswith("demc"):
         d = np.load(os.path.join(cases.GOLDEN_DIR, "retrieval_mc3_%s.npz" % name))
         np.random.seed(spec["seed"])

@@ -65,6 +65,21 @@ def test_two_rank_demc_reproduces_reference(mode, p2p, built, workdir):
 
 
 @pytest.mark.skipif(ngpus() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("mode", ["snooker", "snooker_transit"])
+def test_two_rank_snooker_reproduces_reference(mode, built, workdir):
+    """walk='snooker' (history Z, projection proposals) with the chains split over two GPUs and the
+    fused all-gather: the seeded reference MCcubed chains bit for bit."""
+    name = "retr_small4_transit" if mode == "snooker_transit" else "retr_tiny_eclipse"
+    res = run_world(mode, workdir, 2, 1)
+    d = np.load(os.path.join(cases.GOLDEN_DIR, "retrieval_snooker_%s_thin3.npz" % name))
+    for r in res:
+        assert int(r["p2p"]) == 1
+        assert np.array_equal(r["allparams"], d["allparams"])
+        assert np.array_equal(r["bestp"], d["bestp"])
+    assert np.array_equal(res[0]["Z"], res[1]["Z"])
+
+
+@pytest.mark.skipif(ngpus() < 2, reason="needs 2 GPUs")
 @pytest.mark.parametrize("p2p", [1, 0])
 def test_fused_bandflux_allgather(p2p, built, workdir):
     res = run_world("gather", workdir, 2, p2p)
