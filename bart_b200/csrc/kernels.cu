@@ -18,6 +18,7 @@
 #include "kernels.hpp"
 #include <cuda_runtime.h>
 #include <cstring>
+#include <algorithm>
 
 namespace bart {
 
@@ -579,12 +580,14 @@ band_integrate_kernel(const double *__restrict__ spectra, const double *__restri
 
 __global__ void peer_signal_kernel(PeerOut po) { peer_announce(po); }
 
+// Consumer: every CTA acquires all arrival flags (they are only polled, never written here), copies
+// its slice of the generation's blocks, and the last CTA to finish advances the generation.
 __global__ void __launch_bounds__(256)
 peer_wait_copy_kernel(const double *__restrict__ win, unsigned long long *flags,
                       unsigned long long *gen, int world, long long cap, long long count,
-                      double *__restrict__ out, int *err) {
+                      double *__restrict__ out, int *err, unsigned int *finished) {
   __shared__ int s_bad;
-  const unsigned long long g = *gen;
+  const unsigned long long g = *gen;            // advanced only after every CTA has passed this read
   if (threadIdx.x == 0) s_bad = 0;
   __syncthreads();
   if (threadIdx.x < world) {
@@ -597,12 +600,17 @@ peer_wait_copy_kernel(const double *__restrict__ win, unsigned long long *flags,
   __syncthreads();
   if (s_bad) { if (threadIdx.x == 0) *err = 1; }
   const double *src = win + (size_t)(g & 1ull) * world * cap;
-  for (long long i = threadIdx.x; i < (long long)world * count; i += blockDim.x) {
+  const long long total = (long long)world * count;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / count, k = i - r * count;
     out[i] = __ldcg(src + r * cap + k);                   // written by peers: bypass L1
   }
   __syncthreads();
-  if (threadIdx.x == 0) *gen = g + 1;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(finished, 1u) == gridDim.x - 1) { *finished = 0; __threadfence(); *gen = g + 1; }
+  }
 }
 
 // L2 flush helper: stream-write a buffer larger than the L2
@@ -789,8 +797,10 @@ void launch_peer_signal(const PeerOut &po, cudaStream_t s) { peer_signal_kernel<
 
 void launch_peer_wait_copy(const double *win_local, unsigned long long *flags_local,
                            unsigned long long *gen, int world, long long cap, long long count,
-                           double *out, int *err, cudaStream_t s) {
-  peer_wait_copy_kernel<<<1, 256, 0, s>>>(win_local, flags_local, gen, world, cap, count, out, err);
+                           double *out, int *err, unsigned int *finished, cudaStream_t s) {
+  const long long total = (long long)world * count;
+  const int grid = (int)std::max<long long>(1, std::min<long long>(64, total / 2048));
+  peer_wait_copy_kernel<<<grid, 256, 0, s>>>(win_local, flags_local, gen, world, cap, count, out, err, finished);
 }
 
 void launch_fill(double *p, size_t n, double v, cudaStream_t s) {

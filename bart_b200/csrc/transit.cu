@@ -679,7 +679,7 @@ static void band_device(const double *d_spec, int nmodels, const int *d_status, 
 static void peer_gather(long long count_per_rank, double *d_all) {
   KernelScope ks("peer_wait_copy");
   launch_peer_wait_copy((const double *)G.pw_base, G.pw_flags, G.pw_gen, G.world, G.pw_cap,
-                        count_per_rank, d_all, G.pw_err, G.stream);
+                        count_per_rank, d_all, G.pw_err, G.pw.done + 1, G.stream);
   check_launch("peer_wait_copy");
 }
 

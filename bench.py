@@ -256,6 +256,12 @@ def main():
         tr.run_batch(h_in.array, out=h_out.array, status=st)
         e2e_ms.append(1e3 * (time.perf_counter() - t0))
     e2e_total = float(np.sum(e2e_ms))
+    # nvidia-smi can take longer to start than a short run lasts (8 ranks on one box): keep the
+    # same step running, untimed, until the sampler has seen the GPU under this load
+    t_wait = time.time()
+    while len(sampler.lines) < 5 and time.time() - t_wait < 8.0:
+        # rank-local work only: the number of iterations differs between ranks
+        api._check(L.bart_bandflux_batch_device(d_prof, M, n_in, d_band, None))
     clocks = sampler.stop()
 
     if dist is not None:
