@@ -28,6 +28,7 @@
 // The temperature axis is the sharding axis (bart_build_opacity_slice): planes are independent.
 #include "builder.hpp"
 #include "device.cuh"
+#include "column_math.cuh"
 #include <cuda_runtime.h>
 #include <cmath>
 #include <cstring>
@@ -248,34 +249,63 @@ struct PlaneArgs {
 // every line serves both reference passes -- the strongest individual in-range line per output
 // molecule (extinction.c:400-427, expression order kept) and the co-added group strength
 // (extinction.c:439-464: lines of a group summed in file order, then the isotope factor).
+// table of the fp64 exp of column_math.cuh (fast_exp_neg: <= 1e-15 relative, 11 instructions
+// instead of libdevice's ~30; the pass is 2 exponentials per line and nothing else)
+__device__ unsigned long long b_exp_table[kExpTabSize];
+
+constexpr int kPlanesPerThread = 4;   // planes that share one read of a line's (wavn, elow, gf)
+
 __global__ void __launch_bounds__(kCompactThreads)
-strength_kmax_kernel(PlaneArgs a) {
-  __shared__ double s_max[kMaxGridMol];
-  const int p = blockIdx.y;
+strength_kmax_kernel(PlaneArgs a, int nplanes) {
+  __shared__ double s_max[kPlanesPerThread][kMaxGridMol];
+  __shared__ unsigned long long s_etab[kExpTabSize];
+  if (threadIdx.x < kExpTabSize) s_etab[threadIdx.x] = b_exp_table[threadIdx.x];
+  const int p0 = blockIdx.y * kPlanesPerThread;
   const long long g = blockIdx.x * (long long)kCompactThreads + threadIdx.x;
-  if (threadIdx.x < kMaxGridMol) s_max[threadIdx.x] = 0.0;
+  if (threadIdx.x < kPlanesPerThread * kMaxGridMol) (&s_max[0][0])[threadIdx.x] = 0.0;
   __syncthreads();
   if (g < a.ngroups) {
-    const double T = a.plane_T[p];
     const int iso = a.giso[g];
-    const double ff = a.plane_facfull[(size_t)p * a.niso + iso];
-    const long long b = a.gstart[g], e = a.gstart[g + 1];
-    double pk = 0.0, lmax = 0.0;
-    for (long long i = b; i < e; i++) {
-      const double w = a.wavn[i], gf = a.gf[i];
-      const double e1 = exp(-kEXPCTE * a.elow[i] / T), e2 = 1 - exp(-kEXPCTE * w / T);
-      const double term = gf * e1 * e2;
-      pk = (i == b) ? term : pk + term;
-      if (!(w < a.wn_lo || w > a.own_last)) lmax = fmax(lmax, ff * gf * e1 * e2);
+    double Tq[kPlanesPerThread], ff[kPlanesPerThread], pk[kPlanesPerThread], lmax[kPlanesPerThread];
+#pragma unroll
+    for (int q = 0; q < kPlanesPerThread; q++) {
+      const int p = min(p0 + q, nplanes - 1);              // planes past the end shadow the last one
+      Tq[q] = a.plane_T[p];
+      ff[q] = a.plane_facfull[(size_t)p * a.niso + iso];
+      pk[q] = 0.0; lmax[q] = 0.0;
     }
-    a.S[(size_t)p * a.ngroups + g] = pk * a.plane_fac2[(size_t)p * a.niso + iso];
-    if (lmax > 0)
-      atomicMax((unsigned long long *)&s_max[a.iso_out[iso]], (unsigned long long)__double_as_longlong(lmax));
+    const long long b = a.gstart[g], e = a.gstart[g + 1];
+    for (long long i = b; i < e; i++) {
+      const double w = a.wavn[i], gf = a.gf[i], el = a.elow[i];
+      const bool inr = !(w < a.wn_lo || w > a.own_last);
+#pragma unroll
+      for (int q = 0; q < kPlanesPerThread; q++) {
+        const double T = Tq[q];
+        const double e1 = fast_exp_neg(-kEXPCTE * el / T, s_etab);
+        const double e2 = 1 - fast_exp_neg(-kEXPCTE * w / T, s_etab);
+        const double term = gf * e1 * e2;
+        pk[q] = (i == b) ? term : pk[q] + term;
+        if (inr) lmax[q] = fmax(lmax[q], ff[q] * gf * e1 * e2);
+      }
+    }
+    const int m = a.iso_out[iso];
+#pragma unroll
+    for (int q = 0; q < kPlanesPerThread; q++)
+      if (p0 + q < nplanes) {
+        const int p = p0 + q;
+        a.S[(size_t)p * a.ngroups + g] = pk[q] * a.plane_fac2[(size_t)p * a.niso + iso];
+        // the maximum only grows: a stale read can only cause a redundant atomic
+        if (lmax[q] > *(volatile double *)&s_max[q][m])
+          atomicMax((unsigned long long *)&s_max[q][m], (unsigned long long)__double_as_longlong(lmax[q]));
+      }
   }
   __syncthreads();
-  if (threadIdx.x < a.nout && s_max[threadIdx.x] > 0)
-    atomicMax((unsigned long long *)&a.kmax[(size_t)p * kMaxGridMol + threadIdx.x],
-              (unsigned long long)__double_as_longlong(s_max[threadIdx.x]));
+  if (threadIdx.x < kPlanesPerThread * kMaxGridMol) {
+    const int q = threadIdx.x / kMaxGridMol, m = threadIdx.x % kMaxGridMol;
+    if (p0 + q < nplanes && m < a.nout && s_max[q][m] > 0)
+      atomicMax((unsigned long long *)&a.kmax[(size_t)(p0 + q) * kMaxGridMol + m],
+                (unsigned long long)__double_as_longlong(s_max[q][m]));
+  }
 }
 
 // K6b pass 2: survivors of the weak-line cut (extinction.c:467-470) per block of 256 groups.
@@ -716,6 +746,9 @@ static void build_profiles(BuilderState *b, const Options &o, cudaStream_t s) {
   ferf[0] = 1.0;
   for (int n = 1; n < 64; n++) { fac *= n; ferf[n] = (double)(1.0L / (fac * (2 * n + 1))); }
   BCUDA(cudaMemcpyToSymbol(c_ferf, ferf, sizeof(ferf)));
+  unsigned long long etab[kExpTabSize];
+  fill_exp_table(etab);
+  BCUDA(cudaMemcpyToSymbol(b_exp_table, etab, sizeof(etab)));
   ProfJob *d_jobs = dev_upload(jobs);
   int maxn = 0;
   for (auto &j : jobs) maxn = std::max(maxn, j.nwn);
@@ -893,7 +926,7 @@ static long long run_planes(BuilderState *b, const Options &o, const Molecules &
   long long pool = 0;
   if (b->ngroups > 0) {
     PhaseTimer pt(b, "strength", s);
-    strength_kmax_kernel<<<dim3(nblk, nplanes), kCompactThreads, 0, s>>>(pa);
+    strength_kmax_kernel<<<dim3(nblk, (nplanes + kPlanesPerThread - 1) / kPlanesPerThread), kCompactThreads, 0, s>>>(pa, nplanes);
     strength_count_kernel<<<dim3(nblk, nplanes), kCompactThreads, 0, s>>>(pa, d_blk);
     block_scan_kernel<<<nplanes, 1024, 0, s>>>(d_blk, nblk, d_total);
     BCUDA(cudaGetLastError());
