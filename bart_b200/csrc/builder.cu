@@ -355,13 +355,12 @@ block_scan_kernel(int *blkcnt, int nblk, long long *total) {
   if (threadIdx.x == 0) total[blockIdx.x] = s_carry;
 }
 
-// K6b pass 3: ordered compaction of the surviving groups of every plane into the pool, and the
-// per-isotope ranges of the compact list.
+// K6b pass 3: ordered compaction of the surviving groups of every plane into the pool (group
+// numbers; bins, wavenumbers and strengths are read through them), and the per-isotope ranges of
+// the compact list.
 __global__ void __launch_bounds__(kCompactThreads)
 strength_fill_kernel(PlaneArgs a, const int *blkoff /*[P][nblk]*/, const long long *plane_base,
-                     const int *giown, const int *gidwn, const double *gwavn,
-                     int *c_iown, int *c_idwn, double *c_wavn, double *c_S,
-                     long long *cisobeg /*[P][niso+1]*/) {
+                     int *c_idx, long long *cisobeg /*[P][niso+1]*/) {
   __shared__ int s_warp[kCompactThreads / 32];
   const int p = blockIdx.y;
   const long long g = blockIdx.x * (long long)kCompactThreads + threadIdx.x;
@@ -382,7 +381,7 @@ strength_fill_kernel(PlaneArgs a, const int *blkoff /*[P][nblk]*/, const long lo
   if (g >= a.ngroups) return;
   if (alive) {
     const long long q = plane_base[p] + pos;
-    c_iown[q] = giown[g]; c_idwn[q] = gidwn[g]; c_wavn[q] = gwavn[g]; c_S[q] = S;
+    c_idx[q] = (int)g;       // the list holds group numbers only: 4 bytes per survivor and plane
   }
   long long *cb = cisobeg + (size_t)p * (a.niso + 1);
   const int prev = g > 0 ? a.giso[g - 1] : -1;
@@ -414,7 +413,10 @@ struct CellArgs {
   const long long *cell_out;        // [ncell] offset (doubles) of the cell's [nout][nwave] block
   const double *plane_T;
   const long long *plane_base, *cisobeg;
-  const int *c_iown, *c_idwn; const double *c_wavn, *c_S;
+  const int *c_idx;                 // compact lists of surviving group numbers (all planes)
+  const int *giown, *gidwn; const double *gwavn;   // per group: line-centre bins, wavenumber
+  const double *S;                  // [plane][ngroups] strengths
+  long long ngroups;
   int niso, nspec, nout, nwave, osamp, nDop, nLor;
   const int *iso_spec, *iso_out;
   const double *aDop, *aLor;
@@ -455,13 +457,13 @@ __global__ void widths_kernel(CellArgs a, CellIso *cells, const double *spec_mas
   long long lo = gb, hi = ge;
   while (lo < hi) {
     const long long mid = (lo + hi) >> 1;
-    if (ad * a.c_wavn[mid] / al >= 1e-1) lo = mid + 1; else hi = mid;
+    if (ad * a.gwavn[a.c_idx[mid]] / al >= 1e-1) lo = mid + 1; else hi = mid;
   }
   c.gsplit = lo;
   // the sequential loop keeps the Doppler index of the last line that was re-picked AND evaluated
   // (weak lines `continue` before the re-pick, extinction.c:467-483): the last compact entry of
   // the prefix
-  c.idop_carry = lo > gb ? nearest_dev(a.aDop, ad * a.c_wavn[lo - 1], 0, a.nDop - 1) : c.idop0;
+  c.idop_carry = lo > gb ? nearest_dev(a.aDop, ad * a.gwavn[a.c_idx[lo - 1]], 0, a.nDop - 1) : c.idop0;
   // widest profile any group of the cell can pick: Doppler indices between those of the two
   // ends of the spectrum (nearest_dev is monotonic), or the carried one
   const int dhi = nearest_dev(a.aDop, ad * a.own_last, 0, a.nDop - 1);
@@ -506,6 +508,7 @@ accumulate_kernel(CellArgs a, const CellIso *cells, double *out) {
   const int p = a.cell_plane[ci];
   const long long base0 = a.plane_base[p];
   const long long *cb = a.cisobeg + (size_t)p * (a.niso + 1);
+  const double *Sp = a.S + (size_t)p * a.ngroups;
   double *o = out + a.cell_out[ci];
   for (int k = threadIdx.x; k < a.nDop && k < 128; k += blockDim.x) s_aDop[k] = a.aDop[k];
   for (int k = threadIdx.x; k < kAccWarps * kAccThreads; k += blockDim.x) (&s_acc[0][0])[k] = 0.0;
@@ -557,21 +560,22 @@ accumulate_kernel(CellArgs a, const CellIso *cells, double *out) {
     // candidate range: leader coarse bins in [j0 - hw, j0 + 127 + hw]; idwn is non-increasing
     const int hi_bin = j0 + kAccThreads - 1 + hwb, lo_bin = j0 - hwb;
     long long x = gb, y = ge;
-    while (x < y) { const long long mid = (x + y) >> 1; if (a.c_idwn[mid] > hi_bin) x = mid + 1; else y = mid; }
+    while (x < y) { const long long mid = (x + y) >> 1; if (a.gidwn[a.c_idx[mid]] > hi_bin) x = mid + 1; else y = mid; }
     const long long first = x;
     y = ge;
-    while (x < y) { const long long mid = (x + y) >> 1; if (a.c_idwn[mid] >= lo_bin) x = mid + 1; else y = mid; }
+    while (x < y) { const long long mid = (x + y) >> 1; if (a.gidwn[a.c_idx[mid]] >= lo_bin) x = mid + 1; else y = mid; }
     const long long last = x;                                   // exclusive
     for (long long base = first + 32 * warp; base < last; base += 32 * kAccWarps) {
       const long long g = base + lane;
       StagedGroup sg;
       sg.prof = a.pool; sg.S = 0.0; sg.minj = (1 << 30); sg.maxj = -(1 << 30); sg.pad0 = sg.pad1 = 0;
       if (g < last) {
+        const int gi = a.c_idx[g];
         int idop = c.idop_carry;
-        if (g < c.gsplit) idop = nearest_dev(s_aDop, c.alphad * a.c_wavn[g], 0, a.nDop - 1);
+        if (g < c.gsplit) idop = nearest_dev(s_aDop, c.alphad * a.gwavn[gi], 0, a.nDop - 1);
         const size_t pi = (size_t)idop * a.nLor + c.ilor;
         const int ps = (int)a.prof_size[pi];
-        const int iown = a.c_iown[g], idwn = a.c_idwn[g];
+        const int iown = a.giown[gi], idwn = a.gidwn[gi];
         const int subw = iown - idwn * a.osamp;
         const int offset = iown - ps;
         // bins whose profile index osamp*j - offset lies in [0, 2 ps] (extinction.c:486-509)
@@ -585,7 +589,8 @@ accumulate_kernel(CellArgs a, const CellIso *cells, double *out) {
         sg.minj = max(mn, j0);
         sg.maxj = min(mx, jt_hi);
         if (sg.minj > sg.maxj) { sg.minj = (1 << 30); sg.maxj = -(1 << 30); }
-        sg.S = a.total_mode ? a.c_S[g] * dens : a.c_S[g];       // extinction.c:472-473
+        const double Sg = Sp[gi];
+        sg.S = a.total_mode ? Sg * dens : Sg;                   // extinction.c:472-473
       }
       const int lo = __reduce_min_sync(0xffffffffu, sg.minj);
       const int hi = __reduce_max_sync(0xffffffffu, sg.maxj);
@@ -862,7 +867,7 @@ static void load_lines(BuilderState *b, const Options &o, Tli &t, const std::vec
 // Plane / cell driver shared by the grid build and the line-by-line forward mode.
 struct PlaneWork {
   DevBuf T, facfull, fac2, kmax, blk, total, base, cisobeg, S;        // per plane
-  DevBuf c_iown, c_idwn, c_wavn, c_S;                                  // compact pool
+  DevBuf c_idx;                                                        // compact pool
   DevBuf cell_plane, cell_out, cellinfo;                               // per cell
   DevBuf iso_spec, iso_out, iso_mass, spec_mass, spec_radius;          // static tables
   bool statics = false;
@@ -934,14 +939,12 @@ static long long run_planes(BuilderState *b, const Options &o, const Molecules &
     BCUDA(cudaStreamSynchronize(s));
     for (int p = 0; p < nplanes; p++) { base[p] = pool; pool += total[p]; }
     BCUDA(cudaMemcpyAsync(d_base, base.data(), nplanes * 8, cudaMemcpyHostToDevice, s));
-    int *ci = w.c_iown.get<int>(pool), *cd = w.c_idwn.get<int>(pool);
-    double *cw = w.c_wavn.get<double>(pool), *cS = w.c_S.get<double>(pool);
-    strength_fill_kernel<<<dim3(nblk, nplanes), kCompactThreads, 0, s>>>(
-        pa, d_blk, d_base, b->d_giown, b->d_gidwn, b->d_gwavn, ci, cd, cw, cS, d_cisobeg);
+    int *ci = w.c_idx.get<int>(pool);
+    strength_fill_kernel<<<dim3(nblk, nplanes), kCompactThreads, 0, s>>>(pa, d_blk, d_base, ci, d_cisobeg);
     BCUDA(cudaGetLastError());
   } else {
     BCUDA(cudaMemsetAsync(d_base, 0, nplanes * 8, s));
-    w.c_iown.get<int>(1); w.c_idwn.get<int>(1); w.c_wavn.get<double>(1); w.c_S.get<double>(1);
+    w.c_idx.get<int>(1);
   }
   int *d_cell_plane = w.cell_plane.get<int>(ncell);
   long long *d_cell_out = w.cell_out.get<long long>(ncell);
@@ -951,8 +954,9 @@ static long long run_planes(BuilderState *b, const Options &o, const Molecules &
   CellArgs ca;
   ca.cell_plane = d_cell_plane; ca.cell_dens = d_cell_dens; ca.cell_out = d_cell_out;
   ca.plane_T = d_T; ca.plane_base = d_base; ca.cisobeg = d_cisobeg;
-  ca.c_iown = (const int *)w.c_iown.p; ca.c_idwn = (const int *)w.c_idwn.p;
-  ca.c_wavn = (const double *)w.c_wavn.p; ca.c_S = (const double *)w.c_S.p;
+  ca.c_idx = (const int *)w.c_idx.p;
+  ca.giown = b->d_giown; ca.gidwn = b->d_gidwn; ca.gwavn = b->d_gwavn;
+  ca.S = pa.S; ca.ngroups = std::max<long long>(1, b->ngroups);
   ca.niso = niso; ca.nspec = b->nspec; ca.nout = nout; ca.nwave = b->nwave; ca.osamp = b->osamp;
   ca.nDop = b->nDop; ca.nLor = b->nLor;
   ca.iso_spec = (const int *)w.iso_spec.p; ca.iso_out = d_iso_out;
@@ -1197,7 +1201,7 @@ void builder_free(BuilderState *b) {
   if (b->work) {
     PlaneWork &w = *b->work;
     DevBuf *bufs[] = {&w.T, &w.facfull, &w.fac2, &w.kmax, &w.S, &w.blk, &w.total, &w.base, &w.cisobeg,
-                      &w.c_iown, &w.c_idwn, &w.c_wavn, &w.c_S, &w.cell_plane, &w.cell_out, &w.cellinfo,
+                      &w.c_idx, &w.cell_plane, &w.cell_out, &w.cellinfo,
                       &w.iso_spec, &w.iso_out, &w.iso_mass, &w.spec_mass, &w.spec_radius};
     for (DevBuf *d : bufs) d->release();
     delete b->work;
