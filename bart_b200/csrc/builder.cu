@@ -270,7 +270,7 @@ strength_kmax_kernel(PlaneArgs a, int nplanes) {
 #pragma unroll
     for (int q = 0; q < kPlanesPerThread; q++) {
       const int p = min(p0 + q, nplanes - 1);              // planes past the end shadow the last one
-      Tq[q] = a.plane_T[p];
+      Tq[q] = -kEXPCTE / a.plane_T[p];                     // one division per plane, not two per line
       ff[q] = a.plane_facfull[(size_t)p * a.niso + iso];
       pk[q] = 0.0; lmax[q] = 0.0;
     }
@@ -280,9 +280,8 @@ strength_kmax_kernel(PlaneArgs a, int nplanes) {
       const bool inr = !(w < a.wn_lo || w > a.own_last);
 #pragma unroll
       for (int q = 0; q < kPlanesPerThread; q++) {
-        const double T = Tq[q];
-        const double e1 = fast_exp_neg(-kEXPCTE * el / T, s_etab);
-        const double e2 = 1 - fast_exp_neg(-kEXPCTE * w / T, s_etab);
+        const double e1 = fast_exp_neg(Tq[q] * el, s_etab);
+        const double e2 = 1 - fast_exp_neg(Tq[q] * w, s_etab);
         const double term = gf * e1 * e2;
         pk[q] = (i == b) ? term : pk[q] + term;
         if (inr) lmax[q] = fmax(lmax[q], ff[q] * gf * e1 * e2);
