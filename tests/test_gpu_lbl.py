@@ -67,6 +67,14 @@ def test_lbl_rejects_out_of_range_temperature(api, workdir):
     assert status[1] == 0
     ok, _ = tr.run_batch(models)
     assert np.array_equal(spectra[1], ok[1])
+    # a rejected model in the middle of a batch: the accepted runs on both sides are unaffected
+    tri = np.concatenate([models[:1], bad[:1], models[1:2]])
+    s3, st3 = tr.run_batch(tri)
+    assert st3[0] == 0 and st3[1] != 0 and st3[2] == 0
+    assert np.array_equal(s3[0], ok[0]) and np.array_equal(s3[2], ok[1]) and (s3[1] == -1).all()
+    # the legacy single-model call fails like the reference (makesample.c:488-503)
+    with pytest.raises(api.BartError):
+        tr.run_transit(bad[0])
     tr.free_memory()
 
 
