@@ -32,6 +32,7 @@ struct Emu {
   std::vector<double> wn, grid, PQ[kMaxCia];
   DevConfig c{};
   Knobs k{};
+  bool lbl = false;
 };
 static Emu *E = nullptr;
 
@@ -51,19 +52,30 @@ int emu_init(const char *cfg) {
     read_atmosphere(o.atm, E->atm);
     read_molecules(o.molfile, E->atm, E->mol);
     read_tli_header(o.linedb, E->tli);
-    if (!read_opacity_header(o.opacityfile, E->og)) fail("no opacity file");
+    DevConfig &c = E->c;
+    E->lbl = o.opacityfile.empty();
+    if (E->lbl) {
+      // line-by-line mode (transit.cu do_init): the "grid" is the caller's ext[layer][wave]
+      E->og = OpacityGrid();
+      E->og.nmol = 1; E->og.ntemp = 2; E->og.nlayer = E->atm.nlayer(); E->og.nwave = (long)E->wn.size();
+      E->og.temp = {E->tli.tmin, E->tli.tmax};
+      E->og.molid = {E->mol.id[0]};
+    } else if (!read_opacity_header(o.opacityfile, E->og)) fail("no opacity file");
     OpacityGrid &g = E->og;
-    size_t n = (size_t)g.nlayer * g.ntemp * g.nmol * g.nwave;
+    size_t n = E->lbl ? 0 : (size_t)g.nlayer * g.ntemp * g.nmol * g.nwave;
     std::vector<double> filegrid(n);
+    if (!E->lbl) {
     FILE *f = fopen(o.opacityfile.c_str(), "rb");
     fseek(f, g.data_offset, SEEK_SET);
     if (fread(filegrid.data(), 8, n, f) != n) fail("short grid");
     fclose(f);
-    DevConfig &c = E->c;
+    }
     // the device layout of the grid: [layer][temp][wave][gms] (device.cuh)
     c.gms = g.nmol == 1 ? 1 : (int)((g.nmol + 1) / 2 * 2);
     E->grid.assign((size_t)g.nlayer * g.ntemp * g.nwave * c.gms, 0.0);
-    for (size_t cell = 0; cell < (size_t)(g.nlayer * g.ntemp); cell++)
+    c.lbl = E->lbl ? 1 : 0;
+    c.lbl_model0 = 0; c.lbl_dens = nullptr;
+    for (size_t cell = 0; !E->lbl && cell < (size_t)(g.nlayer * g.ntemp); cell++)
       for (long m = 0; m < g.nmol; m++)
         for (long w = 0; w < g.nwave; w++)
           E->grid[(cell * g.nwave + w) * c.gms + m] = filegrid[(cell * g.nmol + m) * g.nwave + w];
@@ -112,6 +124,15 @@ int emu_init(const char *cfg) {
     k.scat_flag_all = o.scat_flag; k.scat_logext_all = o.scat_logext;
     return 0;
   } catch (std::exception &) { return -1; }
+}
+
+// line-by-line mode: the molecular extinction ext[layer][wave] of the next emu_run calls (what the
+// builder kernels write for one model; one zero row of padding like transit.cu's buffer)
+void emu_set_lbl_ext(const double *ext) {
+  const size_t n = (size_t)E->c.nlayer * E->c.nwave;
+  E->grid.assign(n + E->c.nwave, 0.0);
+  memcpy(E->grid.data(), ext, n * 8);
+  E->c.grid = E->grid.data();
 }
 
 int emu_nwave() { return E ? E->c.nwave : 0; }

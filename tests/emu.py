@@ -27,6 +27,12 @@ class Emu:
     def set_scattering(self, f, v):
         self.lib.emu_set_scattering(f, v)
 
+    def set_lbl_ext(self, ext):
+        """line-by-line mode (cfg without opacityfile): ext[layer][wave] of the next run() calls"""
+        ext = np.ascontiguousarray(ext, dtype=np.float64)
+        assert ext.shape == (self.nlayer, self.nwave)
+        self.lib.emu_set_lbl_ext(ext.ctypes.data_as(dp))
+
     def wn(self):
         out = np.zeros(self.nwave)
         self.lib.emu_wn(out.ctypes.data_as(dp))

@@ -46,3 +46,31 @@ def test_total_mode_differs_from_permol(built, workdir):
     Z = np.array([np.interp(T, i["T"], i["Z"]) for i in B.tli["isos"]])
     k = B.total(T, dens, Z)
     assert k.shape == (len(B.wn),) and np.isfinite(k).all() and (k > 0).any()
+
+
+@pytest.mark.parametrize("name", list(cases.LBL_CASES))
+def test_column_math_in_lbl_mode(name, built, workdir):
+    """The device-side half of the line-by-line mode on the CPU emulator (tests/cpu_emu): atm_prep
+    with DevConfig::lbl presents ext[model][layer][wave] to the unchanged column code as a
+    one-molecule grid with bracket weights (1, 0).  Given the oracle's per-layer extinction the
+    emulated columns must reproduce the oracle's (= the reference's) spectra, tau and last[]."""
+    from oracle import oracle as orc
+    from emu import Emu
+    case, models = cases.build_lbl_case(name, workdir)
+    g = np.load(cases.golden_path(name))
+    O = orc.Oracle(case["cfg"])
+    E = Emu(case["cfg"])
+    for m in range(models.shape[0]):
+        o = O.run(models[m], inter=True)
+        E.set_lbl_ext(o["ext"])
+        e = E.run(models[m])
+        assert e["status"] == 0
+        assert np.array_equal(e["ext"], o["ext"])            # weight 1, second bracket weight 0: exact
+        assert np.array_equal(e["last"], g["last"][m])
+        assert tau_relerr(e["tau"], g["tau"][m], g["last"][m]) < 1e-6
+        assert relerr(e["spectrum"], o["spectrum"]) < 1e-9
+        assert relerr(e["spectrum"], g["spectra"][m]) < 1e-6
+    # a layer outside the TLI temperature range is rejected (makesample.c:488-503)
+    bad = models[0].copy()
+    bad[2] = 69.0
+    assert E.run(bad)["status"] != 0
