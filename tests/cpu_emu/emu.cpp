@@ -184,6 +184,20 @@ int emu_run(const double *in, double *spectrum, double *tau, int *last, double *
   return status;
 }
 
+// host readers of the product (readers.cpp): the memory-mapped TLI line selection.  Returns the
+// number of selected lines and copies up to `cap` of them.
+long long emu_read_tli(const char *path, double wnlow, double wnhigh, long long cap, double *wl,
+                       double *elow, double *gf, short *isoid) {
+  try {
+    Tli t;
+    read_tli_header(path, t);
+    read_tli_lines(path, t, wnlow, wnhigh);
+    const long long n = (long long)t.wl.size();
+    for (long long i = 0; i < n && i < cap; i++) { wl[i] = t.wl[i]; elow[i] = t.elow[i]; gf[i] = t.gf[i]; isoid[i] = t.isoid[i]; }
+    return n;
+  } catch (std::exception &) { return -1; }
+}
+
 double emu_fast_exp(double x) { unsigned long long t[kExpTabSize]; fill_exp_table(t); return fast_exp(x, t); }
 
 }  // extern "C"
