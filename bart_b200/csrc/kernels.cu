@@ -313,7 +313,7 @@ transit_tile_kernel(DevConfig c, const double *__restrict__ tabs, const double *
     const int d0 = ch * kTrChunk;
     const int dn = min(kTrChunk, nl - d0);
     // the chunk's extinction rows (and, by program order of the producers, all earlier ones)
-    while (*(volatile int *)&s_ready[ch] < kTrCons / 32) { }
+    while (*(volatile int *)&s_ready[ch] < kTrCons / 32) __nanosleep(32);
     __threadfence_block();
     if (use_tma) { mbar_wait(&bar_w, wphase); wphase ^= 1u; }
     else bar_consumers();
