@@ -368,6 +368,7 @@ class Transit:
             _check(0 if n >= 0 else -1)
             return out
         shapes = {"allparams": (nchains, nfree, getattr(self, "_mc_niter", 0)),
+                  "allmodel": (nchains, ndata, getattr(self, "_mc_niter", 0)),
                   "params": (nchains, npars), "currchisq": (nchains,), "numaccept": (nchains,),
                   "outbounds": (nchains, nfree), "bestp": (npars,), "bestchisq": (1,),
                   "bestmodel": (ndata,), "models": (nchains, ndata)}

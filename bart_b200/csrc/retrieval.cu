@@ -366,6 +366,13 @@ chisq_accept_kernel(McmcDev mc, const double *__restrict__ models, ModelMap mp, 
     }
     for (int f = 0; f < mc.nfree; f++)
       mc.allparams[((size_t)c * mc.nfree + f) * mc.chainsize + i] = cur[mc.ifree[f]];
+    {                                                          // mcmc.py:636-651
+      double *cm = mc.curmodel + (size_t)c * mc.ndata;
+      for (int d = 0; d < mc.ndata; d++) {
+        if (ok) cm[d] = model[d];
+        mc.allmodel[((size_t)c * mc.ndata + d) * mc.chainsize + i] = cm[d];
+      }
+    }
     if (snooker && i % mc.thinning == 0) {                   // mcmc.py:653-660
       double *zr = mc.Z + ((size_t)zrow * mc.nchains + c) * np;
       for (int f = 0; f < mc.nfree; f++) zr[mc.ifree[f]] = cur[mc.ifree[f]];

@@ -51,6 +51,10 @@ struct McmcDev {
   const double *pmin, *pmax, *prior, *priorlow, *data, *uncert;
   double *params, *nextp, *currchisq, *nextchisq, *c2, *bestp, *bestchisq, *bestmodel;
   double *numaccept, *allparams;
+  // MC3's `savemodel` trace (mcmc.py:636-651): the model of every chain's CURRENT state after each
+  // generation, allmodel[chain][datum][iteration].  curmodel starts as zeros, like the reference's
+  // `allmodel[~accepted,:,i+nold-1]` with i + nold - 1 = -1 at the first generation.
+  double *curmodel, *allmodel;
   int *outbounds, *outflag, *iter;
   // random streams of this run, MC3's shapes (mcmc.py:484-507)
   const double *support;   // [chainsize][nchains][nfree]

@@ -166,7 +166,7 @@ struct State {
   int mc_lo = 0, mc_hi = 0, mc_pad = 0;
   DevBuf<double> d_mcd[20];
   DevBuf<int> d_mci[8];
-  DevBuf<double> d_mcband, d_mcgather;
+  DevBuf<double> d_mcband, d_mcgather, d_mccur, d_mcallm;
   cudaGraphExec_t mc_graph = nullptr;
   // snooker walk: sample history Z
   DevBuf<double> d_Z, d_Zchisq, d_snk_usn;
@@ -384,6 +384,7 @@ static void reset_state() {
   G.d_lbl_ext.release(); G.d_lbl_dens.release(); G.lbl = false;
   G.d_cpress.release(); G.d_cbase.release(); G.d_cratio.release(); G.d_cparams.release();
   G.d_cstatus.release(); G.d_mcband.release(); G.d_mcgather.release();
+  G.d_mccur.release(); G.d_mcallm.release();
   for (auto &b : G.d_mcd) b.release();
   for (auto &b : G.d_mci) b.release();
   G.d_snk_usn.release(); G.d_snk_idx.release(); G.d_snk_off.release();
@@ -812,7 +813,8 @@ static void mcmc_run_generations(int niter) {
   // usual 10-chain populations).  Per-kernel timing and multi-rank runs use plain launches unless
   // BART_MCMC_GRAPH=1.
   const char *genv = getenv("BART_MCMC_GRAPH");
-  bool use_graph = genv ? atoi(genv) != 0 : (G.world == 1);
+  // (multi-rank: only when the all-gather is the fused peer-window one -- plain kernels, no NCCL node)
+  bool use_graph = genv ? atoi(genv) != 0 : (G.world == 1 || p2p_usable((long long)G.mc_pad * mc.ndata));
   if (G.profile || niter < 3) use_graph = false;
   int done = 0;
   if (use_graph) {
@@ -1718,6 +1720,11 @@ int bart_mcmc_init(int nchains, int npars, const double *params, const double *p
   G.d_mcband.ensure((size_t)G.mc_pad * ndata);
   G.d_mcgather.ensure((size_t)G.mc_pad * ndata * G.world);
   CUDA_OK(cudaMemsetAsync(G.d_mcband.p, 0, (size_t)G.mc_pad * ndata * 8, G.stream));
+  G.d_mccur.ensure((size_t)nchains * ndata);
+  CUDA_OK(cudaMemsetAsync(G.d_mccur.p, 0, (size_t)nchains * ndata * 8, G.stream));
+  G.mc.curmodel = G.d_mccur.p;
+  G.d_mcallm.ensure((size_t)nchains * ndata);              // the initial evaluation writes no trace
+  G.mc.allmodel = G.d_mcallm.p;
   if (G.mc_graph) { cudaGraphExecDestroy(G.mc_graph); G.mc_graph = nullptr; }
   ensure_params_buffers(G.mc_hi - G.mc_lo);
   mcmc_generation_queued(1);
@@ -1760,6 +1767,8 @@ int bart_mcmc_run(int niter, const double *support, const int *r1, const int *r2
   mc.r2 = upi(d_r2, r2, (size_t)nc * niter);
   d_trace.ensure((size_t)nc * mc.nfree * niter);
   mc.allparams = d_trace.p;
+  G.d_mcallm.ensure((size_t)nc * mc.ndata * niter);
+  mc.allmodel = G.d_mcallm.p;
   mc.walk = 0;
   mcmc_run_generations(niter);
   return 0;
@@ -1910,6 +1919,8 @@ int bart_mcmc_run_snooker(int niter, const double *support, const int *i1, const
   mc.ugamma = upd(G.d_mcd[17], ugamma, n1);
   G.d_mcd[18].ensure((size_t)nc * mc.nfree * niter);
   mc.allparams = G.d_mcd[18].p;
+  G.d_mcallm.ensure((size_t)nc * mc.ndata * niter);
+  mc.allmodel = G.d_mcallm.p;
   mc.walk = 1;
   mcmc_run_generations(niter);
   return 0;
@@ -1928,6 +1939,7 @@ long long bart_mcmc_get(const char *name, double *out, long long capacity) {
   const double *src = nullptr;
   long long cnt = 0;
   if (n == "allparams") { src = mc.allparams; cnt = (long long)mc.nchains * mc.nfree * mc.chainsize; }
+  else if (n == "allmodel") { src = mc.allmodel; cnt = (long long)mc.nchains * mc.ndata * mc.chainsize; }
   else if (n == "params") { src = mc.params; cnt = (long long)mc.nchains * mc.npars; }
   else if (n == "currchisq") { src = mc.currchisq; cnt = mc.nchains; }
   else if (n == "numaccept") { src = mc.numaccept; cnt = mc.nchains; }

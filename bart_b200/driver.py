@@ -181,7 +181,8 @@ def demc_draws(rng, nchains, chainsize, step_free):
 
 
 def run_demc(transit, data, uncert, params, pmin, pmax, stepsize, numit, nchains, prior=None,
-             priorlow=None, burnin=0, fgamma=1.0, fepsilon=0.0, rng=np.random, draws=None):
+             priorlow=None, burnin=0, fgamma=1.0, fepsilon=0.0, rng=np.random, draws=None,
+             savefile=None, savemodel=None):
     """`MCcubed.mc.mcmc(..., walk='demc', leastsq=False)` with the whole generation loop on the
     GPU: the host only draws the random streams (once, up front, exactly like mcmc.py does) and
     reads the trace back at the end.  `transit` must have its converter and filters set
@@ -202,12 +203,23 @@ def run_demc(transit, data, uncert, params, pmin, pmax, stepsize, numit, nchains
     if draws is None:
         draws = demc_draws(rng, nchains, chainsize, stepsize[ifree])
     transit.mcmc_run(draws["support"], draws["r1"], draws["r2"], draws["unif"], draws["ugamma"])
-    out = {k: transit.mcmc_get(k) for k in ("allparams", "params", "currchisq", "numaccept",
+    out = {k: transit.mcmc_get(k) for k in ("allparams", "allmodel", "params", "currchisq", "numaccept",
                                             "outbounds", "bestp", "bestmodel", "models")}
     out["bestchisq"] = float(transit.mcmc_get("bestchisq")[0])
     allp = out["allparams"]
     out["allstack"] = np.hstack([allp[c, :, burnin:chainsize] for c in range(nchains)])  # mcmc.py:692-695
+    _save_mc3_files(out, savefile, savemodel)
     return out
+
+
+def _save_mc3_files(out, savefile, savemodel):
+    """MC3's output files (mcmc.py:842-850): `savefile` (BART's output.npy, read by
+    code/bestFit.py:431 and code/mc3plots.py) = allparams[nchains][nfree][chainsize];
+    `savemodel` (BART.cfg: band_eclipse.npy) = allmodel[nchains][ndata][chainsize]."""
+    if savefile is not None:
+        np.save(savefile, out["allparams"])
+    if savemodel is not None:
+        np.save(savemodel, out["allmodel"])
 
 
 def snooker_draws(rng, nchains, nfree, chainsize, hsize, thinning, step_free, pmin_free, pmax_free):
@@ -249,7 +261,7 @@ def snooker_draws(rng, nchains, nfree, chainsize, hsize, thinning, step_free, pm
 
 def run_snooker(transit, data, uncert, params, pmin, pmax, stepsize, numit, nchains, prior=None,
                 priorlow=None, burnin=0, thinning=1, fgamma=1.0, fepsilon=0.0, hsize=1,
-                rng=np.random, draws=None):
+                rng=np.random, draws=None, savefile=None, savemodel=None):
     """`MCcubed.mc.mcmc(..., walk='snooker', leastsq=False)` -- the walk BART's examples configure
     -- with the sample history Z, the proposals, the Metropolis rule and the forward models all on
     the GPU.  Returns MC3's arrays (see run_demc) plus Z and Zchisq."""
@@ -273,9 +285,10 @@ def run_snooker(transit, data, uncert, params, pmin, pmax, stepsize, numit, ncha
     transit.mcmc_snooker_init(draws["z0"], thinning)
     transit.mcmc_run_snooker(*(draws[k] for k in ("support", "i1", "i2", "iz", "ic", "usnooker",
                                                   "usn_offset", "unif", "ugamma")))
-    out = {k: transit.mcmc_get(k) for k in ("allparams", "params", "currchisq", "numaccept",
+    out = {k: transit.mcmc_get(k) for k in ("allparams", "allmodel", "params", "currchisq", "numaccept",
                                             "outbounds", "bestp", "bestmodel", "models", "Z", "Zchisq")}
     out["bestchisq"] = float(transit.mcmc_get("bestchisq")[0])
     allp = out["allparams"]
     out["allstack"] = np.hstack([allp[c, :, burnin:chainsize] for c in range(nchains)])
+    _save_mc3_files(out, savefile, savemodel)
     return out

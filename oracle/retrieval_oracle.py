@@ -269,6 +269,7 @@ def demc(func, data, uncert, params, pmin, pmax, stepsize, numit, nchains, prior
     outbounds = np.zeros((nchains, nfree), int)
     allparams = np.zeros((nchains, nfree, chainsize))
     allmodels = np.zeros((chainsize, nchains, ndata))
+    allmodel = np.zeros((nchains, ndata, chainsize))          # MC3's savemodel array (mcmc.py:250-252)
     for i in range(chainsize):
         gamma1[ugamma[i] >= 0.1] = gamma
         gamma1[ugamma[i] < 0.1] = 0.98
@@ -300,9 +301,14 @@ def demc(func, data, uncert, params, pmin, pmax, stepsize, numit, nchains, prior
             bestmodel = models[np.argmin(c2)].copy()
             bestchisq = np.amin(c2)
         allparams[:, :, i] = params[:, ifree]
+        # mcmc.py:649-651 -- rejected chains keep the previous column; at i = 0 that is column -1,
+        # still zeros, so a chain shows zeros until its first accepted proposal
+        cur = models.copy()
+        cur[~accepted] = allmodel[~accepted, :, i - 1]
+        allmodel[:, :, i] = cur
     return dict(allparams=allparams, params=params, currchisq=currchisq, numaccept=numaccept,
                 outbounds=outbounds, bestp=bestp, bestchisq=bestchisq, bestmodel=bestmodel,
-                params0=params0, allmodels=allmodels,
+                params0=params0, allmodels=allmodels, allmodel=allmodel,
                 draws=dict(support=support, r1=r1, r2=r2, unif=unif, ugamma=ugamma))
 
 
@@ -419,6 +425,7 @@ def snooker(func, data, uncert, params, pmin, pmax, stepsize, numit, nchains, pr
     outbounds = np.zeros((nchains, nfree), int)
     allparams = np.zeros((nchains, nfree, chainsize))
     allmodels = np.zeros((chainsize, nchains, ndata))
+    allmodel = np.zeros((nchains, ndata, chainsize))          # MC3's savemodel array (mcmc.py:250-252)
     mrfactor = np.zeros(nchains)
     mrtrace = np.ones((chainsize, nchains))
     for i in range(chainsize):
@@ -475,13 +482,17 @@ def snooker(func, data, uncert, params, pmin, pmax, stepsize, numit, nchains, pr
             bestmodel = models[np.argmin(c2)].copy()
             bestchisq = np.amin(c2)
         allparams[:, :, i] = params[:, ifree]
+        cur = models.copy()                                          # mcmc.py:649-651 (see demc)
+        cur[~accepted] = allmodel[~accepted, :, i - 1]
+        allmodel[:, :, i] = cur
         if i % thinning == 0:                                        # mcmc.py:653-660
             Z[hsize + i // thinning][:, ifree] = params[:, ifree]
             Zchisq[hsize + i // thinning] = currchisq
             Zsize += 1
     return dict(allparams=allparams, params=params, currchisq=currchisq, numaccept=numaccept,
                 outbounds=outbounds, bestp=bestp, bestchisq=bestchisq, bestmodel=bestmodel,
-                params0=params0, allmodels=allmodels, Z=Z, Zchisq=Zchisq, Zsize=Zsize, hsize=hsize,
+                params0=params0, allmodels=allmodels, allmodel=allmodel, Z=Z, Zchisq=Zchisq, Zsize=Zsize,
+                hsize=hsize,
                 mrfactor=mrtrace, draws=draws)
 
 

@@ -163,16 +163,18 @@ def golden_mc3(mc3, name, tmp):
     case, spec, band = make_band_oracle(name, tmp)
     data, uncert = retrieval_data(spec, band)
     sav = os.path.join(tmp, name + "_trace.npy")
+    savm = os.path.join(tmp, name + "_models.npy")
     log = open(os.path.join(tmp, name + ".log"), "w")
     np.random.seed(spec["seed"])
     out = mc3.mc.mcmc(data, uncert, band, [], params=np.array(spec["params"]),
                       pmin=np.array(spec["pmin"]), pmax=np.array(spec["pmax"]),
                       stepsize=np.array(spec["stepsize"], dtype=float), numit=spec["numit"],
                       nchains=spec["nchains"], walk="demc", leastsq=False, grtest=False,
-                      burnin=spec["burnin"], plots=False, savefile=sav, log=log)
+                      burnin=spec["burnin"], plots=False, savefile=sav, savemodel=savm, log=log)
     allparams = np.load(sav)                       # [nchains][nfree][chainsize] (mcmc.py:842-843)
+    allmodel = np.load(savm)                       # [nchains][ndata][chainsize] (mcmc.py:647-651,849-850)
     np.savez_compressed(os.path.join(HERE, "retrieval_mc3_%s.npz" % name), data=data, uncert=uncert,
-                        allparams=allparams, allstack=out[0], bestp=out[1])
+                        allparams=allparams, allstack=out[0], bestp=out[1], allmodel=allmodel)
     print("retrieval_mc3_%s.npz: trace %s, posterior %s, best %s" % (
         name, allparams.shape, out[0].shape, np.array2string(out[1], precision=4)))
 
@@ -214,6 +216,7 @@ def golden_snooker(mc3, name, tmp):
     mcu.MPI = mpi4py.MPI
     for thinning in (1, 3):
         sav = os.path.join(tmp, "%s_snk%d_trace.npy" % (name, thinning))
+        savm = os.path.join(tmp, "%s_snk%d_models.npy" % (name, thinning))
         log = open(os.path.join(tmp, "%s_snk%d.log" % (name, thinning)), "w")
         np.random.seed(spec["seed"] + thinning)
         comm = FakeWorkers(band, spec["nchains"])
@@ -222,11 +225,12 @@ def golden_snooker(mc3, name, tmp):
                           stepsize=np.array(spec["stepsize"], dtype=float), numit=spec["numit"],
                           nchains=spec["nchains"], walk="snooker", leastsq=False, grtest=False,
                           burnin=spec["burnin"], thinning=thinning, plots=False, savefile=sav,
-                          log=log, comm=comm)
+                          savemodel=savm, log=log, comm=comm)
         allparams = np.load(sav)
+        allmodel = np.load(savm)
         np.savez_compressed(os.path.join(HERE, "retrieval_snooker_%s_thin%d.npz" % (name, thinning)),
                             data=data, uncert=uncert, allparams=allparams, allstack=out[0],
-                            bestp=out[1], thinning=thinning)
+                            bestp=out[1], thinning=thinning, allmodel=allmodel)
         print("retrieval_snooker_%s_thin%d.npz: trace %s, best %s" % (
             name, thinning, allparams.shape, np.array2string(out[1], precision=4)))
 

@@ -121,6 +121,12 @@ def test_demc_on_device_reproduces_reference_mc3(name, graph, api, workdir, monk
     assert np.array_equal(out["allparams"], d["allparams"])          # every chain, every iteration
     assert np.array_equal(out["allstack"], d["allstack"])
     assert np.array_equal(out["bestp"], d["bestp"])
+    # MC3's savemodel array (mcmc.py:636-651, 849-850) and its files
+    assert np.array_equal(out["allmodel"] == 0, d["allmodel"] == 0)
+    assert relerr(out["allmodel"], d["allmodel"]) < 1e-6
+    sf, sm = os.path.join(workdir, "output_%s.npy" % name), os.path.join(workdir, "band_%s.npy" % name)
+    driver._save_mc3_files(out, sf, sm)
+    assert np.array_equal(np.load(sf), d["allparams"]) and np.load(sm).shape == d["allmodel"].shape
     chainsize = d["allparams"].shape[2]
     per_gen = 5 if tr.eclipse else 7
     assert api.lib().bart_launch_count() - n0 >= per_gen * chainsize
@@ -180,6 +186,8 @@ def test_snooker_on_device_reproduces_reference_mc3(name, thinning, graph, api, 
     assert np.array_equal(out["allparams"], d["allparams"])          # every chain, every iteration
     assert np.array_equal(out["allstack"], d["allstack"])
     assert np.array_equal(out["bestp"], d["bestp"])
+    assert np.array_equal(out["allmodel"] == 0, d["allmodel"] == 0)
+    assert relerr(out["allmodel"], d["allmodel"]) < 1e-6
     from oracle import retrieval_oracle as ro
     np.random.seed(spec["seed"] + thinning)
     ref = ro.snooker(band_oracle(case, spec, extra), d["data"], d["uncert"], spec["params"],

@@ -61,6 +61,10 @@ def test_demc_oracle_reproduces_reference_mc3(name, built, workdir):
                   spec["stepsize"], spec["numit"], spec["nchains"], burnin=spec["burnin"])
     assert np.array_equal(out["allparams"], d["allparams"])
     assert np.array_equal(out["bestp"], d["bestp"])
+    # MC3's `savemodel` file (BART.cfg: band_eclipse.npy): models of the chains' current states,
+    # zeros until a chain's first acceptance (mcmc.py:649-651)
+    assert np.array_equal(out["allmodel"], d["allmodel"])
+    assert (d["allmodel"][:, :, 0] == 0).all(axis=1).any()
     nacc = out["numaccept"].sum()
     assert 0 < nacc < spec["numit"]
 
@@ -83,6 +87,7 @@ def test_snooker_oracle_reproduces_reference_mc3(name, thinning, built, workdir)
                      thinning=thinning)
     assert np.array_equal(out["allparams"], d["allparams"])
     assert np.array_equal(out["bestp"], d["bestp"])
+    assert np.array_equal(out["allmodel"], d["allmodel"])
     assert out["hsize"] == spec["nchains"] + 1
     assert out["Zsize"] == out["hsize"] + len(range(0, out["allparams"].shape[2], thinning))
     # the walk exercised projected snooker jumps and their Metropolis factor
