@@ -263,9 +263,12 @@ int  bart_mcmc_snooker_init(int hsize, int thinning, const double *z0);
 int  bart_mcmc_run_snooker(int niter, const double *support, const int *i1, const int *i2,
                            const int *iz, const int *ic, const double *usnooker,
                            const int *usn_offset, const double *unif, const double *ugamma);
-/* "allparams" [nchains][nfree][niter], "params", "currchisq", "numaccept", "outbounds", "bestp",
- * "bestchisq", "bestmodel", "models", and for snooker "Z" [Zsize][nchains][npars], "Zchisq"
- * [Zsize][nchains]; returns the number of doubles written or < 0.                               */
+/* "allparams" [nchains][nfree][niter] (MC3's `savefile` array, BART's output.npy), "allmodel"
+ * [nchains][ndata][niter] (MC3's `savemodel` array, mcmc.py:636-651,849-850: the model of every
+ * chain's current state, zeros until its first acceptance like the reference), "params",
+ * "currchisq", "numaccept", "outbounds", "bestp", "bestchisq", "bestmodel", "models", and for
+ * snooker "Z" [Zsize][nchains][npars], "Zchisq" [Zsize][nchains]; returns the number of doubles
+ * written or < 0.                                                                               */
 long long bart_mcmc_get(const char *name, double *out, long long capacity);
 
 #ifdef __cplusplus
