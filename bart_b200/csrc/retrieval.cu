@@ -373,7 +373,7 @@ chisq_accept_kernel(McmcDev mc, const double *__restrict__ models, ModelMap mp, 
         mc.allmodel[((size_t)c * mc.ndata + d) * mc.chainsize + i] = cm[d];
       }
     }
-    if (snooker && i % mc.thinning == 0) {                   // mcmc.py:653-660
+    if (snooker && (mc.nold + i) % mc.thinning == 0) {                   // mcmc.py:653-660
       double *zr = mc.Z + ((size_t)zrow * mc.nchains + c) * np;
       for (int f = 0; f < mc.nfree; f++) zr[mc.ifree[f]] = cur[mc.ifree[f]];
       mc.Zchisq[(size_t)zrow * mc.nchains + c] = mc.currchisq[c];
@@ -405,7 +405,7 @@ chisq_accept_kernel(McmcDev mc, const double *__restrict__ models, ModelMap mp, 
     if (threadIdx.x == 0) {
       if (take) *mc.bestchisq = best;
       if (!first) *mc.iter = i + 1;
-      if (snooker && i % mc.thinning == 0) *mc.zsize = zrow + 1;
+      if (snooker && (mc.nold + i) % mc.thinning == 0) *mc.zsize = zrow + 1;
     }
   }
 }

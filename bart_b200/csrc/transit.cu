@@ -1885,7 +1885,7 @@ int bart_mcmc_run_snooker(int niter, const double *support, const int *i1, const
       if (usn_offset[i + 1] - usn_offset[i] != nsj || usn_offset[i] < 0)
         fail("usn_offset: generation %d has %d snooker chains but %d rows of factors", i, nsj,
              usn_offset[i + 1] - usn_offset[i]);
-      if (i % mc.thinning == 0) zs++;
+      if ((mc.nold + mc.chainsize + i) % mc.thinning == 0) zs++;   // global iteration number
     }
     snooker_reserve_rows((size_t)zs + 1);
     G.mc_zsize = zs;

@@ -182,7 +182,7 @@ def demc_draws(rng, nchains, chainsize, step_free):
 
 def run_demc(transit, data, uncert, params, pmin, pmax, stepsize, numit, nchains, prior=None,
              priorlow=None, burnin=0, fgamma=1.0, fepsilon=0.0, rng=np.random, draws=None,
-             savefile=None, savemodel=None):
+             savefile=None, savemodel=None, grtest=False, grexit=False, thinning=1):
     """`MCcubed.mc.mcmc(..., walk='demc', leastsq=False)` with the whole generation loop on the
     GPU: the host only draws the random streams (once, up front, exactly like mcmc.py does) and
     reads the trace back at the end.  `transit` must have its converter and filters set
@@ -202,14 +202,68 @@ def run_demc(transit, data, uncert, params, pmin, pmax, stepsize, numit, nchains
                       fgamma=fgamma, fepsilon=fepsilon, burnin=burnin)
     if draws is None:
         draws = demc_draws(rng, nchains, chainsize, stepsize[ifree])
-    transit.mcmc_run(draws["support"], draws["r1"], draws["r2"], draws["unif"], draws["ugamma"])
-    out = {k: transit.mcmc_get(k) for k in ("allparams", "allmodel", "params", "currchisq", "numaccept",
+    def run(lo, hi):
+        h = slice(lo, hi)
+        transit.mcmc_run(draws["support"][h], draws["r1"][:, h], draws["r2"][:, h], draws["unif"][h],
+                         draws["ugamma"][h])
+    allp, allm, history, chainlen = run_segments(
+        run, lambda: (transit.mcmc_get("allparams"), transit.mcmc_get("allmodel")), chainsize,
+        burnin=burnin, thinning=thinning, grtest=grtest, grexit=grexit)
+    out = {k: transit.mcmc_get(k) for k in ("params", "currchisq", "numaccept",
                                             "outbounds", "bestp", "bestmodel", "models")}
+    out["allparams"], out["allmodel"], out["psrf"] = allp, allm, history
     out["bestchisq"] = float(transit.mcmc_get("bestchisq")[0])
-    allp = out["allparams"]
-    out["allstack"] = np.hstack([allp[c, :, burnin:chainsize] for c in range(nchains)])  # mcmc.py:692-695
+    out["allstack"] = np.hstack([allp[c, :, burnin:chainlen] for c in range(nchains)])  # mcmc.py:692-695
     _save_mc3_files(out, savefile, savemodel)
     return out
+
+
+def gelman_rubin(chains):
+    """MC3's convergence test (MCcubed/mc/gelman_rubin.py:8-70): potential scale reduction factor of
+    every free parameter of chains[nchains][nfree][chainlen]."""
+    chains = np.asarray(chains, dtype=float)
+    nchains, nfree, chainlen = chains.shape
+    W = np.mean(np.var(chains, axis=2), axis=0)
+    means = np.mean(chains, axis=2)
+    B = (chainlen / (nchains - 1.0)) * np.sum((means - np.mean(means, axis=0)) ** 2, axis=0)
+    V = W * ((chainlen - 1.0) / chainlen) + B * ((nchains + 1.0) / (chainlen * nchains))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return np.sqrt(V / W)
+
+
+def gr_checkpoints(chainsize):
+    """Iterations i after which MC3 reports / tests convergence: ((i+1) % intsteps == 0) and i > 0
+    with intsteps = chainsize / 10 (mcmc.py:238,663; a float in Python 3)."""
+    intsteps = chainsize / 10
+    return [i for i in range(1, chainsize) if (i + 1) % intsteps == 0]
+
+
+def run_segments(run, fetch, chainsize, burnin=0, thinning=1, grtest=False, grexit=False, nold=0):
+    """Drive a device-resident walk in the segments MC3's loop is observable in (mcmc.py:662-690).
+    `run(lo, hi)` advances generations [lo, hi) (state stays on the device); `fetch()` returns that
+    call's allparams / allmodel pieces.  Without grtest it is one segment.  Returns (allparams,
+    allmodel, psrf history [(iteration, psrf)], number of generations run)."""
+    cuts = gr_checkpoints(chainsize) if grtest else []
+    edges = sorted(set([c + 1 for c in cuts] + [chainsize]))
+    pieces_p, pieces_m, history = [], [], []
+    lo, grflag = 0, False
+    for hi in edges:
+        run(lo, hi)
+        pp, pm = fetch()
+        pieces_p.append(pp); pieces_m.append(pm)
+        lo = hi
+        i = hi - 1
+        if grtest and i in cuts and (i + nold) > burnin:
+            allp = np.concatenate(pieces_p, axis=2)
+            psrf = gelman_rubin(allp[:, :, burnin:i + nold + 1:thinning])
+            history.append((i, psrf))
+            if np.all(psrf < 1.01):
+                if grexit and grflag:                        # two consecutive passes (mcmc.py:676-683)
+                    break
+                grflag = True
+            else:
+                grflag = False
+    return np.concatenate(pieces_p, axis=2), np.concatenate(pieces_m, axis=2), history, lo
 
 
 def _save_mc3_files(out, savefile, savemodel):
@@ -261,7 +315,7 @@ def snooker_draws(rng, nchains, nfree, chainsize, hsize, thinning, step_free, pm
 
 def run_snooker(transit, data, uncert, params, pmin, pmax, stepsize, numit, nchains, prior=None,
                 priorlow=None, burnin=0, thinning=1, fgamma=1.0, fepsilon=0.0, hsize=1,
-                rng=np.random, draws=None, savefile=None, savemodel=None):
+                rng=np.random, draws=None, savefile=None, savemodel=None, grtest=False, grexit=False):
     """`MCcubed.mc.mcmc(..., walk='snooker', leastsq=False)` -- the walk BART's examples configure
     -- with the sample history Z, the proposals, the Metropolis rule and the forward models all on
     the GPU.  Returns MC3's arrays (see run_demc) plus Z and Zchisq."""
@@ -283,12 +337,19 @@ def run_snooker(transit, data, uncert, params, pmin, pmax, stepsize, numit, ncha
         draws = snooker_draws(rng, nchains, len(ifree), chainsize, hsize, thinning, stepsize[ifree],
                               pmin[ifree], pmax[ifree])
     transit.mcmc_snooker_init(draws["z0"], thinning)
-    transit.mcmc_run_snooker(*(draws[k] for k in ("support", "i1", "i2", "iz", "ic", "usnooker",
-                                                  "usn_offset", "unif", "ugamma")))
-    out = {k: transit.mcmc_get(k) for k in ("allparams", "allmodel", "params", "currchisq", "numaccept",
+    def run(lo, hi):
+        h = slice(lo, hi)
+        off = np.asarray(draws["usn_offset"])[lo:hi + 1]
+        transit.mcmc_run_snooker(draws["support"][h], draws["i1"][h], draws["i2"][h], draws["iz"][h],
+                                 draws["ic"][h], draws["usnooker"][off[0]:off[-1]], off - off[0],
+                                 draws["unif"][h], draws["ugamma"][h])
+    allp, allm, history, chainlen = run_segments(
+        run, lambda: (transit.mcmc_get("allparams"), transit.mcmc_get("allmodel")), chainsize,
+        burnin=burnin, thinning=thinning, grtest=grtest, grexit=grexit)
+    out = {k: transit.mcmc_get(k) for k in ("params", "currchisq", "numaccept",
                                             "outbounds", "bestp", "bestmodel", "models", "Z", "Zchisq")}
+    out["allparams"], out["allmodel"], out["psrf"] = allp, allm, history
     out["bestchisq"] = float(transit.mcmc_get("bestchisq")[0])
-    allp = out["allparams"]
-    out["allstack"] = np.hstack([allp[c, :, burnin:chainsize] for c in range(nchains)])
+    out["allstack"] = np.hstack([allp[c, :, burnin:chainlen] for c in range(nchains)])
     _save_mc3_files(out, savefile, savemodel)
     return out

@@ -235,6 +235,30 @@ def golden_snooker(mc3, name, tmp):
             name, thinning, allparams.shape, np.array2string(out[1], precision=4)))
 
 
+def golden_gr():
+    """Gelman-Rubin factors of the reference's MCcubed/mc/gelman_rubin.py at MC3's own checkpoints
+    (mcmc.py:238,663-686) on the stored DE-MC traces and on a synthetic converged population."""
+    import MCcubed.mc.gelman_rubin as gr
+    out = {}
+    for name in cases.RETRIEVAL:
+        d = np.load(os.path.join(HERE, "retrieval_mc3_%s.npz" % name))
+        allp, burnin = d["allparams"], cases.RETRIEVAL[name]["burnin"]
+        chainsize = allp.shape[2]
+        intsteps = chainsize / 10
+        its, vals = [], []
+        for i in range(chainsize):
+            if ((i + 1) % intsteps == 0) and (i > 0) and i > burnin:
+                its.append(i)
+                vals.append(gr.convergetest(allp[:, :, burnin:i + 1:1]))
+        out["its_" + name], out["psrf_" + name] = np.array(its), np.array(vals)
+    rng = np.random.RandomState(11)
+    conv = rng.normal(0.0, 1.0, (7, 3, 400)) + np.array([1.0, -2.0, 0.5])[None, :, None]
+    out["conv_chains"] = conv
+    out["conv_psrf_thin2"] = gr.convergetest(conv[:, :, 50:300:2])
+    np.savez_compressed(os.path.join(HERE, "retrieval_gr.npz"), **out)
+    print("retrieval_gr.npz:", {k: np.shape(v) for k, v in out.items()})
+
+
 def main():
     only = set(sys.argv[1:])                     # e.g. `make_golden_retrieval.py snooker`
     want = lambda k: not only or k in only
@@ -244,6 +268,8 @@ def main():
     mc3 = build_mc3()
     if want("pt"):
         golden_pt(pt)
+    if want("gr"):
+        golden_gr()
     with tempfile.TemporaryDirectory() as tmp:
         for name in cases.RETRIEVAL:
             if want("conv"):

@@ -243,3 +243,37 @@ def test_snooker_large_population_and_continuation(api, workdir):
     assert np.array_equal(tr.mcmc_get("Z"), ref["Z"][:ref["Zsize"]])
     assert np.any(ref["mrfactor"] != 1.0)
     tr.free_memory()
+
+
+@pytest.mark.parametrize("walk", ["demc", "snooker"])
+def test_grtest_segments_leave_the_chains_unchanged(walk, api, workdir):
+    """grtest=True runs the device loop in the segments between MC3's convergence checkpoints
+    (mcmc.py:238,663-686): same chains as the single-call run / the reference, PSRF history equal to
+    the reference's gelman_rubin at those checkpoints.  Snooker with thinning 3 and checkpoints every
+    2 generations exercises the global iteration numbering of the history update."""
+    from bart_b200 import driver
+    name = "retr_small4_transit"                                   # chainsize 20 -> checkpoints 1,3,5..
+    case, spec, extra, tr = setup(api, name, workdir)
+    if walk == "demc":
+        d = np.load(os.path.join(G, "retrieval_mc3_%s.npz" % name))
+        np.random.seed(spec["seed"])
+        out = driver.run_demc(tr, d["data"], d["uncert"], spec["params"], spec["pmin"], spec["pmax"],
+                              spec["stepsize"], spec["numit"], spec["nchains"], burnin=spec["burnin"],
+                              grtest=True)
+        g = np.load(os.path.join(G, "retrieval_gr.npz"))
+        assert [h[0] for h in out["psrf"]] == list(g["its_" + name])
+        for (i, psrf), ref in zip(out["psrf"], g["psrf_" + name]):
+            assert np.allclose(psrf, ref, rtol=1e-12, equal_nan=True)
+    else:
+        d = np.load(os.path.join(G, "retrieval_snooker_%s_thin3.npz" % name))
+        np.random.seed(spec["seed"] + 3)
+        out = driver.run_snooker(tr, d["data"], d["uncert"], spec["params"], spec["pmin"], spec["pmax"],
+                                 spec["stepsize"], spec["numit"], spec["nchains"], burnin=spec["burnin"],
+                                 thinning=3, grtest=True)
+        assert len(out["psrf"]) >= 5
+    assert np.array_equal(out["allparams"], d["allparams"])
+    assert np.array_equal(out["allstack"], d["allstack"])
+    assert np.array_equal(out["bestp"], d["bestp"])
+    assert np.array_equal(out["allmodel"] == 0, d["allmodel"] == 0)
+    assert relerr(out["allmodel"], d["allmodel"]) < 1e-6
+    tr.free_memory()

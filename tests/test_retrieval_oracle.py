@@ -94,3 +94,61 @@ def test_snooker_oracle_reproduces_reference_mc3(name, thinning, built, workdir)
     assert np.any(out["mrfactor"] != 1.0)
     nacc = out["numaccept"].sum()
     assert 0 < nacc < spec["numit"]
+
+
+def test_gelman_rubin_matches_reference(built):
+    """driver.gelman_rubin / gr_checkpoints against the reference's MCcubed/mc/gelman_rubin.py
+    evaluated at MC3's own checkpoints (mcmc.py:238,663-686)."""
+    from bart_b200 import driver
+    g = np.load(os.path.join(G, "retrieval_gr.npz"))
+    for name, spec in cases.RETRIEVAL.items():
+        d = np.load(os.path.join(G, "retrieval_mc3_%s.npz" % name))
+        allp, burnin = d["allparams"], spec["burnin"]
+        its = [i for i in driver.gr_checkpoints(allp.shape[2]) if i > burnin]
+        assert its == list(g["its_" + name]) and len(its) >= 3
+        for k, i in enumerate(its):
+            assert np.allclose(driver.gelman_rubin(allp[:, :, burnin:i + 1]), g["psrf_" + name][k],
+                               rtol=1e-12, atol=0, equal_nan=True)
+    assert np.allclose(driver.gelman_rubin(g["conv_chains"][:, :, 50:300:2]), g["conv_psrf_thin2"], rtol=1e-12)
+    assert np.all(g["conv_psrf_thin2"] < 1.01)
+
+
+def test_run_segments_follows_mc3_convergence_logic():
+    """The segment driver around the device-resident loop makes MC3's observable decisions
+    (mcmc.py:662-690): PSRF at the checkpoints past burn-in, exit after two consecutive passes."""
+    from bart_b200 import driver
+    rng = np.random.RandomState(3)
+    nch, nfree, chainsize, burnin, thinning = 6, 2, 200, 20, 1
+    trace = rng.normal(0, 1, (nch, nfree, chainsize))
+    trace[:, :, :60] += np.arange(nch)[:, None, None] * 3.0        # chains start far apart
+    models = rng.normal(0, 1, (nch, 4, chainsize))
+    state = {}
+
+    def run(lo, hi):
+        state["piece"] = (trace[:, :, lo:hi], models[:, :, lo:hi])
+
+    # MC3's loop restated literally
+    grflag, stop, hist = False, chainsize, []
+    intsteps = chainsize / 10
+    for i in range(chainsize):
+        if ((i + 1) % intsteps == 0) and (i > 0) and i > burnin:
+            psrf = driver.gelman_rubin(trace[:, :, burnin:i + 1:thinning])
+            hist.append(i)
+            if np.all(psrf < 1.01):
+                if grflag:
+                    stop = i + 1
+                    break
+                grflag = True
+            else:
+                grflag = False
+    allp, allm, history, n = driver.run_segments(run, lambda: state["piece"], chainsize, burnin=burnin,
+                                                 thinning=thinning, grtest=True, grexit=True)
+    assert n == stop and [h[0] for h in history] == hist
+    assert np.array_equal(allp, trace[:, :, :stop]) and np.array_equal(allm, models[:, :, :stop])
+    # without grexit the whole chain runs and every checkpoint is reported; without grtest: one call
+    allp2, _, history2, n2 = driver.run_segments(run, lambda: state["piece"], chainsize, burnin=burnin,
+                                                 grtest=True, grexit=False)
+    assert n2 == chainsize and np.array_equal(allp2, trace) and len(history2) >= len(history)
+    calls = []
+    driver.run_segments(lambda lo, hi: calls.append((lo, hi)) or run(lo, hi), lambda: state["piece"], chainsize)
+    assert calls == [(0, chainsize)]
