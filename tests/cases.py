@@ -79,6 +79,18 @@ def build_savefiles_case(workdir):
     return case, synth.make_models(case, nm, seed=mseed)
 
 
+# CLI runs (`transit -c cfg`, transit.c:230-242; BART.py:632-634 best-fit run): name -> make_case kwargs
+CLI_CASES = {
+    "cli_eclipse": dict(shape="tiny", solution="eclipse", seed=7001, nlayer=40, outputs=True),
+    "cli_transit": dict(shape="tiny", solution="transit", seed=7002, nlayer=40, outputs=True,
+                        refradius_km=95000.0),
+}
+
+
+def build_cli_case(name, workdir):
+    return synth.make_case(os.path.join(workdir, name), **CLI_CASES[name])
+
+
 def build_builder_case(name, workdir):
     import os as _os
     case = synth.make_case(_os.path.join(workdir, name), **BUILD_CASES[name])

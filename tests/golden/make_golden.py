@@ -96,6 +96,25 @@ def lbl_golden(only):
                 os.path.getsize(cases.golden_path(name))))
 
 
+def cli_golden(only):
+    """Spectrum files written by the reference's command-line program (printflux eclipse.c:355-380,
+    printmod slantpath.c:510-555) for the atmosphere file's own profiles."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "transit_ref")
+    with tempfile.TemporaryDirectory() as tmp:
+        for name in cases.CLI_CASES:
+            if only and name not in only:
+                continue
+            case = cases.build_cli_case(name, tmp)
+            out = os.path.join(case["workdir"], "outspec.dat")
+            r = subprocess.run([exe, "-c", case["cfg"]], capture_output=True, text=True, cwd=case["workdir"])
+            if r.returncode != 0 or not os.path.exists(out):
+                raise SystemExit("reference CLI failed on %s:\n%s\n%s" % (name, r.stdout[-2000:], r.stderr[-2000:]))
+            with open(out) as f:
+                text = f.read()
+            np.savez_compressed(cases.golden_path(name), text=text, grid_sha=cases.sha(case["grid"]))
+            print("%-24s %d lines: %r ..." % (name, text.count("\n"), text[:60]))
+
+
 def savefiles_golden(only):
     """The six `savefiles yes` text dumps written by the reference for one model, parsed."""
     if only and "savefiles" not in only:
@@ -125,6 +144,7 @@ def savefiles_golden(only):
 
 
 if __name__ == "__main__":
+    cli_golden(sys.argv[1:])
     savefiles_golden(sys.argv[1:])
     builder_golden(sys.argv[1:])
     lbl_golden(sys.argv[1:])
