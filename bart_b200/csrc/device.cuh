@@ -95,6 +95,10 @@ struct Knobs {
   const double *cloudtop;    // [M] or nullptr
   const int *scat_flag;      // [M] or nullptr
   const double *scat_logext; // [M] or nullptr
+  const double *radius_file; // [nlayer] or nullptr: use these radii (file units, bottom -> top)
+                             // instead of the hydrostatic ones -- the command-line program runs
+                             // do_transit on the atmosphere file as read, without reloadatm
+                             // (transit.c:230-242, readatm.c:499)
   double r0_all;
   int cloud_flag_all; double cloudext_all, cloudtop_all, cloudbot_all;
   int scat_flag_all; double scat_logext_all;

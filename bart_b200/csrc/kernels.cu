@@ -120,7 +120,9 @@ atm_prep_kernel(DevConfig c, Knobs knobs, const double *__restrict__ profiles, i
   const KnobVals kv = knobs_for(knobs, m);
   for (int l = threadIdx.x; l < nl - 1; l += blockDim.x) s_hc[l] = hydro_coef(c, in, s_mu, l);
   __syncthreads();
-  if (threadIdx.x == 0) hydrostatic_radii(c, kv.r0, in, s_mu, s_hc, s_rad);
+  if (knobs.radius_file) {
+    for (int l = threadIdx.x; l < nl; l += blockDim.x) s_rad[l] = knobs.radius_file[l];
+  } else if (threadIdx.x == 0) hydrostatic_radii(c, kv.r0, in, s_mu, s_hc, s_rad);
   __syncthreads();
   double *tab = tabs + (size_t)m * c.lay.stride();
   st = 0;

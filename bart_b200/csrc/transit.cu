@@ -1985,7 +1985,14 @@ int bart_cli_run(void) {
   for (int i = 0; i < nl; i++) in[i] = G.atm.temp[i];
   for (int j = 0; j < ns; j++)
     for (int i = 0; i < nl; i++) in[(size_t)(j + 1) * nl + i] = G.atm.q[(size_t)j * nl + i];
+  // main() runs do_transit on the atmosphere as read: the file's own radius column, no hydrostatic
+  // recomputation (that is reloadatm's, i.e. run_transit's, job)
+  DevBuf<double> d_rad;
+  upload(d_rad, G.atm.radius);
+  G.knobs.radius_file = d_rad.p;
   run_transit(in.data(), (int)in.size(), out.data(), nw);
+  G.knobs.radius_file = nullptr;
+  d_rad.release();
   if (bart_error_pending()) return -1;
   // printflux / printmod text format: eclipse.c:355-380, slantpath.c:510-555
   FILE *f = stdout;
