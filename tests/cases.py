@@ -73,6 +73,16 @@ SAVEFILES_CASE = (dict(shape="tiny", solution="eclipse", seed=6001, nlayer=30,
                        extra_cfg=["savefiles yes", "cloudtop -1.0", "scattering 1.5"]), 1, 60)
 
 
+# what code/cf.py:40-65 does for the contribution functions: the best-fit configuration with
+# `toomuch 1e100` (every layer is integrated) and `savefiles yes`, run through the executable
+SAVEFILES_CF_CASE = dict(shape="tiny", solution="eclipse", seed=6002, nlayer=30, outputs=True,
+                         overrides={"toomuch": 1e100}, extra_cfg=["savefiles yes"])
+
+
+def build_savefiles_cf_case(workdir):
+    return synth.make_case(os.path.join(workdir, "savefiles_cf"), **SAVEFILES_CF_CASE)
+
+
 def build_savefiles_case(workdir):
     kw, nm, mseed = SAVEFILES_CASE
     case = synth.make_case(os.path.join(workdir, "savefiles"), **kw)

@@ -115,6 +115,25 @@ def cli_golden(only):
             print("%-24s %d lines: %r ..." % (name, text.count("\n"), text[:60]))
 
 
+def savefiles_cf_golden(only):
+    """tau.dat of the reference EXECUTABLE for cf.py's configuration (toomuch 1e100, savefiles yes)."""
+    if only and "savefiles_cf" not in only:
+        return
+    from util import parse_dump
+    exe = os.path.join(ROOT, "oracle", "_ref", "transit_ref")
+    with tempfile.TemporaryDirectory() as tmp:
+        case = cases.build_savefiles_cf_case(tmp)
+        r = subprocess.run([exe, "-c", case["cfg"]], capture_output=True, text=True, cwd=case["workdir"])
+        if r.returncode != 0:
+            raise SystemExit("reference CLI failed:\n%s\n%s" % (r.stdout[-2000:], r.stderr[-2000:]))
+        keys, tau = parse_dump(os.path.join(case["workdir"], "tau.dat"))
+        with open(os.path.join(case["workdir"], "outspec.dat")) as f:
+            spec = f.read()
+        np.savez_compressed(cases.golden_path("savefiles_cf"), tau_keys=keys, tau=tau, outspec=spec,
+                            grid_sha=cases.sha(case["grid"]))
+        print("savefiles_cf: tau %s, all layers integrated: %s" % (tau.shape, bool((tau[:, 1:] > 0).all())))
+
+
 def savefiles_golden(only):
     """The six `savefiles yes` text dumps written by the reference for one model, parsed."""
     if only and "savefiles" not in only:
@@ -145,6 +164,7 @@ def savefiles_golden(only):
 
 if __name__ == "__main__":
     cli_golden(sys.argv[1:])
+    savefiles_cf_golden(sys.argv[1:])
     savefiles_golden(sys.argv[1:])
     builder_golden(sys.argv[1:])
     lbl_golden(sys.argv[1:])

@@ -53,3 +53,32 @@ def test_savefiles_dumps_match_reference(built, workdir, monkeypatch):
     # what cf.py does with tau.dat (cf.py:68-96): rows are wavenumbers, transposed to [layer][wn]
     assert got["tau"].T.shape == (tr.nlayer, tr.nwave)
     tr.free_memory()
+
+
+def test_contribution_function_run_like_cf_py(built, workdir):
+    """code/cf.py:40-65 re-runs the best-fit configuration through the transit EXECUTABLE with
+    `toomuch 1e100` (no early exit: every layer integrated) and `savefiles yes`, then reads tau.dat
+    (cf.py:68-96).  Same run with bart_b200/bin/transit against the reference executable's files."""
+    import subprocess
+    case = cases.build_savefiles_cf_case(workdir)
+    g = np.load(cases.golden_path("savefiles_cf"))
+    assert cases.sha(case["grid"]) == str(g["grid_sha"])
+    for n in DUMPS + ("outspec.dat",):
+        p = os.path.join(case["workdir"], n)
+        if os.path.exists(p):
+            os.remove(p)
+    exe = os.path.join(cases.ROOT, "bart_b200", "bin", "transit")
+    r = subprocess.run([exe, "-c", case["cfg"]], capture_output=True, text=True, cwd=case["workdir"])
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    keys, tau = parse_dump(os.path.join(case["workdir"], "tau.dat"))
+    assert np.array_equal(keys, g["tau_keys"]) and tau.shape == g["tau"].shape
+    assert (tau[:, 1:] > 0).all()                            # toomuch 1e100: down to the bottom layer
+    assert relerr(tau, g["tau"]) < 1e-8
+    # cf.readTauDat's view: tau[layer][wn] after the transpose
+    assert tau.T.shape == (case["nlayer"], len(case["wn"]))
+    ref = str(g["outspec"]).splitlines()
+    with open(os.path.join(case["workdir"], "outspec.dat")) as f:
+        mine = f.read().splitlines()
+    assert mine[0] == ref[0] and len(mine) == len(ref)
+    worst = max(abs(float(a[15:]) - float(b[15:])) / abs(float(b[15:])) for a, b in zip(mine[1:], ref[1:]))
+    assert worst < 2e-9
