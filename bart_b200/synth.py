@@ -96,7 +96,9 @@ def write_atm(path, press, temp, abund, species=SPECIES, gsurf=1000.0, r0_km=920
         f.write("#TEADATA\n")
         f.write("#Radius    Pressure   Temp       " + " ".join("%-10s" % s for s in species) + "\n")
         for i in range(len(press)):
-            f.write("%10.3f %.4e %7.2f " % (rad[i], press[i], temp[i])
+            # a leading blank like TEA's files: the reference's reader drops the first character of
+            # the first data row (readatm.c:425-470), which only the executable's path ever sees
+            f.write(" %10.3f %.4e %7.2f " % (rad[i], press[i], temp[i])
                     + " ".join("%.4e" % q for q in abund[i]) + " \n")
     return path
 
