@@ -77,6 +77,8 @@ def main():
             setters["cloudtop"] = float(f.split("=")[1])
         if f.startswith("--scattering="):
             setters["scattering"] = float(f.split("=")[1])
+        if f.startswith("--scatflag="):
+            setters["scatflag"] = int(f.split("=")[1])
     lib = load()
     t0 = time.perf_counter()
     init(lib, cfg)
@@ -88,8 +90,8 @@ def main():
         lib.set_radius(setters["radius"])
     if "cloudtop" in setters:
         lib.set_cloudtop(setters["cloudtop"])
-    if "scattering" in setters:
-        lib.set_scattering(1, setters["scattering"])
+    if "scattering" in setters or "scatflag" in setters:
+        lib.set_scattering(setters.get("scatflag", 1), setters.get("scattering", 0.0))
     models = np.ascontiguousarray(np.load(models_path), dtype=np.float64)
     if models.ndim == 1:
         models = models[None, :]
