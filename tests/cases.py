@@ -32,6 +32,9 @@ CASES = {
                              extra_cfg=["modlevel -1"]), 3, 91, {"radius": 94200.0}),
     "tiny_eclipse_3ang": (dict(shape="tiny", solution="eclipse", seed=4242,
                                extra_cfg=["raygrid 0 30 70"]), 2, 93, {}),
+    # set_scattering(2, .): polarizability (Rayleigh) scattering of every species, extinction.c:586-624
+    "small4_eclipse_polar": (dict(shape="small4", solution="eclipse", seed=881, nlayer=40), 2, 90,
+                             {"scatflag": 2}),
     "tiny_eclipse_t20": (dict(shape="tiny", solution="eclipse", seed=4243,
                               overrides={"toomuch": 20.0}, nlayer=60), 2, 92, {}),
 }

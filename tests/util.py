@@ -23,8 +23,8 @@ def apply_setters(obj, setters):
         obj.set_radius(setters["radius"])
     if "cloudtop" in setters:
         obj.set_cloudtop(setters["cloudtop"])
-    if "scattering" in setters:
-        obj.set_scattering(1, setters["scattering"])
+    if "scattering" in setters or "scatflag" in setters:
+        obj.set_scattering(setters.get("scatflag", 1), setters.get("scattering", 0.0))
 
 
 def parse_dump(path):
