@@ -285,7 +285,7 @@ def make_case(workdir, shape="demo", solution="eclipse", seed=12345, nlayer=100,
               nlines=0, wnosamp=2160, extra_cfg=None, nfilters=None, overrides=None,
               cia_path=None, starrad=1.155, refpress=0.1, gsurf=1165.02,
               refradius_km=123820.0, ethresh=1e-6, nwidth=20, outputs=False, verb=0,
-              no_opacity=False):
+              no_opacity=False, cia_h2he=False):
     """Create every input file of one configuration under `workdir`; returns paths + arrays."""
     os.makedirs(workdir, exist_ok=True)
     sh = dict(SHAPES[shape]) if isinstance(shape, str) else dict(shape)
@@ -304,6 +304,10 @@ def make_case(workdir, shape="demo", solution="eclipse", seed=12345, nlayer=100,
                             r0_km=refradius_km * 0.97)
     if with_cia:
         case["cia"] = cia_path or write_cia(P("CIA_H2H2_synth.dat"))
+        if cia_h2he:      # a second, two-species table like examples/WASP-12b/BART.cfg's H2-He file
+            t2 = np.array([1000, 1500, 2000, 2500, 3000, 4000, 5000], dtype=float)
+            case["cia"] += "," + write_cia(P("CIA_H2He_synth.dat"), pair=("H2", "He"), temps=t2,
+                                           wn=np.arange(50.0, 12001.0, 25.0), seed=8)
     molids = [MOL_BY_NAME[m][0] for m in sh["mols"]]
     temps = np.arange(tlow, thigh + 0.5 * tempdelt, tempdelt)
     case["grid_temps"] = temps

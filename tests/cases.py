@@ -35,6 +35,10 @@ CASES = {
     # set_scattering(2, .): polarizability (Rayleigh) scattering of every species, extinction.c:586-624
     "small4_eclipse_polar": (dict(shape="small4", solution="eclipse", seed=881, nlayer=40), 2, 90,
                              {"scatflag": 2}),
+    # two CIA tables, the second a two-species (H2-He) one with its own temperature range
+    # (examples/WASP-12b/BART.cfg: csfile CIA_H2H2..., CIA_H2He...)
+    "small4_eclipse_2cia": (dict(shape="small4", solution="eclipse", seed=882, nlayer=40, cia_h2he=True),
+                            2, 89, {}),
     "tiny_eclipse_t20": (dict(shape="tiny", solution="eclipse", seed=4243,
                               overrides={"toomuch": 20.0}, nlayer=60), 2, 92, {}),
 }
