@@ -108,6 +108,24 @@ def build_cli_case(name, workdir):
     return synth.make_case(os.path.join(workdir, name), **CLI_CASES[name])
 
 
+# spectral range given as wavelengths (wllow / wlhigh / wlfct: what code/makecfg.py writes from
+# BART.cfg), makewnsample makesample.c:282-404
+WL_CASES = [(3.0, 5.0, 1.0), (2.9, 4.77, 0.7), (3.3, 3.9, 0.25)]
+
+
+def build_wl_case(k, workdir):
+    lo, hi, d = WL_CASES[k]
+    case = synth.make_case(os.path.join(workdir, "wl%d" % k),
+                           shape=dict(wnlow=1e4 / hi, wnhigh=1e4 / lo, wndelt=d, mols=["CH4"], toomuch=10.0),
+                           solution="eclipse", seed=5, nlayer=20)
+    with open(case["cfg"]) as f:
+        txt = [l for l in f.read().splitlines() if not l.startswith("wnlow") and not l.startswith("wnhigh")]
+    txt += ["wllow %.10g" % lo, "wlhigh %.10g" % hi]
+    with open(case["cfg"], "w") as f:
+        f.write("\n".join(txt) + "\n")
+    return case
+
+
 def build_builder_case(name, workdir):
     import os as _os
     case = synth.make_case(_os.path.join(workdir, name), **BUILD_CASES[name])

@@ -96,6 +96,28 @@ def lbl_golden(only):
                 os.path.getsize(cases.golden_path(name))))
 
 
+def wl_golden(only):
+    """Wavenumber grids the reference derives from wavelength limits (get_waveno_arr)."""
+    if only and "wl" not in only:
+        return
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        for k in range(len(cases.WL_CASES)):
+            case = cases.build_wl_case(k, tmp)
+            from bart_b200 import synth
+            models = synth.make_models(case, 1, seed=6)
+            mpath, opath = os.path.join(case["workdir"], "m.npy"), os.path.join(case["workdir"], "o.npz")
+            np.save(mpath, models)
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "ref_driver.py"), case["cfg"], mpath, opath],
+                               capture_output=True, text=True)
+            if r.returncode != 0:
+                raise SystemExit("reference failed:\n%s\n%s" % (r.stdout[-2000:], r.stderr[-2000:]))
+            d = np.load(opath)
+            out["wn%d" % k], out["spec%d" % k] = d["wn"], d["spectra"][0]
+    np.savez_compressed(cases.golden_path("wl_ranges"), **out)
+    print("wl_ranges:", {k: v.shape for k, v in out.items()})
+
+
 def cli_golden(only):
     """Spectrum files written by the reference's command-line program (printflux eclipse.c:355-380,
     printmod slantpath.c:510-555) for the atmosphere file's own profiles."""
@@ -163,6 +185,7 @@ def savefiles_golden(only):
 
 
 if __name__ == "__main__":
+    wl_golden(sys.argv[1:])
     cli_golden(sys.argv[1:])
     savefiles_cf_golden(sys.argv[1:])
     savefiles_golden(sys.argv[1:])

@@ -67,3 +67,17 @@ def test_fast_exp_accuracy(built):
     # arguments are clamped to [-700, 700]: an opaque deck transmits e^-700 ~ 1e-304, not NaN
     assert lib.emu_fast_exp(-1e9) == lib.emu_fast_exp(-700.0) < 1e-300
     assert lib.emu_fast_exp(1e5) == lib.emu_fast_exp(700.0) and np.isfinite(lib.emu_fast_exp(1e5))
+
+
+def test_wavelength_limits_give_the_reference_grid(built, workdir):
+    """wllow / wlhigh / wlfct (what makecfg.py writes from BART.cfg) through the product's host code
+    (cfg.cpp, readers.cpp make_sampling) and through the oracle: the reference's wavenumber grid."""
+    import numpy as np
+    import cases
+    from emu import Emu
+    from oracle import oracle as orc
+    g = np.load(cases.golden_path("wl_ranges"))
+    for k in range(len(cases.WL_CASES)):
+        case = cases.build_wl_case(k, workdir)
+        assert np.array_equal(Emu(case["cfg"]).wn(), g["wn%d" % k])
+        assert np.array_equal(orc.Oracle(case["cfg"]).wn, g["wn%d" % k])

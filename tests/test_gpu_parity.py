@@ -257,3 +257,17 @@ def test_transit_module_drop_in(api, get_case):
     spectra, status = trm.run_transit_batch(models)
     assert np.array_equal(spectra[0], spectrum)
     trm.free_memory()
+
+
+def test_wavelength_specified_range(api, workdir):
+    """Spectral range given as wavelengths (makecfg.py's transit configuration): get_waveno_arr and
+    the spectrum against the reference's."""
+    from bart_b200 import synth
+    g = np.load(cases.golden_path("wl_ranges"))
+    for k in range(len(cases.WL_CASES)):
+        case = cases.build_wl_case(k, workdir)
+        tr = api.Transit(case["cfg"])
+        assert np.array_equal(tr.get_waveno_arr(), g["wn%d" % k])
+        spec = tr.run_transit(synth.make_models(case, 1, seed=6)[0])
+        assert relerr(spec, g["spec%d" % k]) < TOL
+        tr.free_memory()
