@@ -39,6 +39,13 @@ CASES = {
     # (examples/WASP-12b/BART.cfg: csfile CIA_H2H2..., CIA_H2He...)
     "small4_eclipse_2cia": (dict(shape="small4", solution="eclipse", seed=882, nlayer=40, cia_h2he=True),
                             2, 89, {}),
+    # layer counts that are not a multiple of the transit kernel's depth chunk (20), and fewer
+    # layers than one chunk
+    "tiny_transit_37": (dict(shape="tiny", solution="transit", seed=883, nlayer=37, refradius_km=95000.0),
+                        2, 88, {"radius": 94100.0}),
+    "tiny_transit_9": (dict(shape="tiny", solution="transit", seed=884, nlayer=9, refradius_km=95000.0),
+                       2, 87, {}),
+    "tiny_eclipse_9": (dict(shape="tiny", solution="eclipse", seed=885, nlayer=9), 2, 86, {}),
     "tiny_eclipse_t20": (dict(shape="tiny", solution="eclipse", seed=4243,
                               overrides={"toomuch": 20.0}, nlayer=60), 2, 92, {}),
 }

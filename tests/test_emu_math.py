@@ -26,7 +26,7 @@ def test_column_math_vs_oracle_and_golden(name, built, get_case):
         o = O.run(models[m], inter=True)
         assert e["status"] == 0
         assert relerr(e["radius"], o["radius"]) < 1e-13
-        assert relerr(e["ext"], o["ext"]) < 1e-13
+        assert relerr(e["ext"], o["ext"]) < 1e-12        # the oracle performs the identity spline resample
         assert np.array_equal(e["last"], g["last"][m]), "last[] differs from the reference"
         assert tau_relerr(e["tau"], o["tau"], o["last"]) < 5e-9
         assert relerr(e["spectrum"], o["spectrum"]) < 1e-9

@@ -24,9 +24,9 @@ def test_oracle_matches_reference_golden(name, built, get_case):
         assert relerr(o["radius"], g["radius"][m]) < 1e-13
         assert np.array_equal(o["last"], g["last"][m]), "last[] differs from the reference"
         assert tau_relerr(o["tau"][wsel], g["tau_sample"][m], g["last"][m][wsel]) < 5e-9
-        assert relerr(o["cia"][wsel], g["cia_sample"][m]) < 1e-12
+        assert relerr(o["cia"][wsel], g["cia_sample"][m]) < 2e-11    # -ffast-math reassociation in the 2-stage spline
         ext_ref = g["ext_sample"][m]
         comp = np.abs(ext_ref).sum(axis=1) > 0        # the reference evaluates layers lazily
-        assert relerr(o["ext"][:, wsel][comp], ext_ref[comp]) < 1e-13
+        assert relerr(o["ext"][:, wsel][comp], ext_ref[comp]) < 2e-12   # identity-resample splines, -ffast-math
         # 1e-6 is the north star's tolerance; the restatement is ~5 orders tighter
         assert relerr(o["spectrum"], g["spectra"][m]) < 1e-9
