@@ -30,3 +30,26 @@ def test_fresh_seed(solution, setters, built, workdir):
         o = O.run(models[m], inter=True)
         assert np.array_equal(o["last"], d["last"][m])
         assert relerr(o["spectrum"], d["spectra"][m]) < 1e-9
+
+
+@pytest.mark.parametrize("solution", ["eclipse", "transit"])
+def test_fresh_seed_line_by_line(solution, built, workdir):
+    """No opacity file: the reference computes every layer line by line (tau.c:163-175); the
+    oracle's restatement on a fresh line list and fresh models."""
+    from bart_b200 import synth
+    from oracle import oracle as orc
+    case = synth.make_case(os.path.join(workdir, "fresh_lbl_" + solution), shape="tiny", solution=solution,
+                           seed=4242, nlayer=18, with_grid=False, no_opacity=True, nlines=1500,
+                           ethresh=1e-5, refradius_km=95000.0 if solution == "transit" else 123820.0)
+    models = synth.make_models(case, 2, seed=1618)
+    mp, op = os.path.join(case["workdir"], "m.npy"), os.path.join(case["workdir"], "ref.npz")
+    np.save(mp, models)
+    conftest.run_reference(case["cfg"], mp, op, {})
+    d = np.load(op)
+    O = orc.Oracle(case["cfg"])
+    for m in range(2):
+        o = O.run(models[m], inter=True)
+        assert np.array_equal(o["last"], d["last"][m])
+        comp = np.abs(d["ext"][m]).sum(axis=1) > 0
+        assert relerr(o["ext"][comp], d["ext"][m][comp]) < 1e-6
+        assert relerr(o["spectrum"], d["spectra"][m]) < 1e-6
