@@ -133,6 +133,38 @@ def build_wl_case(k, workdir):
     return case
 
 
+def build_fuzz_case(k, workdir):
+    """Seeded random configuration k: geometry, layer count, toomuch, ray grid, knobs, spectral
+    window -> (case, models, setters)."""
+    rng = np.random.default_rng(9000 + k)
+    solution = ("eclipse", "transit")[k % 2]
+    nlayer = int(rng.integers(12, 70))
+    lo = float(rng.uniform(1800.0, 3000.0))
+    shape = dict(wnlow=lo, wnhigh=lo + float(rng.uniform(40.0, 160.0)), wndelt=float(rng.choice([0.5, 1.0, 2.0])),
+                 mols=[["CH4"], ["H2O", "CO2", "CO", "CH4"]][int(rng.integers(0, 2))],
+                 toomuch=float(rng.choice([5.0, 10.0, 20.0, 1e100])))
+    extra = []
+    if solution == "eclipse":
+        extra.append("raygrid " + ["0 20 40 60 80", "0 30 70", "0 15 30 45 60 75", "10 50"][int(rng.integers(0, 4))])
+    case = synth.make_case(os.path.join(workdir, "fuzz%d" % k), shape=shape, solution=solution,
+                           seed=7000 + k, nlayer=nlayer, extra_cfg=extra,
+                           refradius_km=95000.0 if solution == "transit" else 123820.0)
+    molfit = ("CH4",) if len(shape["mols"]) == 1 else ("H2O", "CO2", "CO", "CH4")
+    models = synth.make_models(case, 2, seed=100 + k, molfit=molfit)
+    setters = {}
+    if rng.uniform() < 0.5:
+        setters["cloudtop"] = float(rng.uniform(-3.0, 0.5))
+    if rng.uniform() < 0.5:
+        setters["scattering"] = float(rng.uniform(0.0, 2.5))
+    if solution == "transit":
+        setters["radius"] = float(rng.uniform(93500.0, 96000.0))
+    return case, models, setters
+
+
+FUZZ_CPU = range(6)          # against the compiled reference (build container)
+FUZZ_GPU = range(12)         # CUDA path against the oracle
+
+
 def build_builder_case(name, workdir):
     import os as _os
     case = synth.make_case(_os.path.join(workdir, name), **BUILD_CASES[name])

@@ -271,3 +271,27 @@ def test_wavelength_specified_range(api, workdir):
         spec = tr.run_transit(synth.make_models(case, 1, seed=6)[0])
         assert relerr(spec, g["spec%d" % k]) < TOL
         tr.free_memory()
+
+
+@pytest.mark.parametrize("k", list(cases.FUZZ_GPU))
+def test_randomised_configurations(k, api, workdir):
+    """The seeded random configurations of tests/cases.py build_fuzz_case (the oracle agrees with
+    the compiled reference on every one of them, tests/test_oracle_vs_reference.py) through the CUDA
+    path: spectra within the north-star tolerance, last[] identical."""
+    from oracle import oracle as orc
+    case, models, setters = cases.build_fuzz_case(k, workdir)
+    tr = api.Transit(case["cfg"])
+    O = orc.Oracle(case["cfg"])
+    apply_setters(tr, setters)
+    apply_setters(O, setters)
+    tr.debug_keep(True)
+    spectra, status = tr.run_batch(models)
+    assert (status == 0).all()
+    for m in range(models.shape[0]):
+        o = O.run(models[m], inter=True)
+        assert np.array_equal(tr.debug_get("last", m).astype(np.int64), o["last"])
+        assert relerr(spectra[m], o["spectrum"]) < TOL
+    tr.debug_keep(False)
+    fast, _ = tr.run_batch(models)
+    assert relerr(fast, spectra) < 1e-12
+    tr.free_memory()

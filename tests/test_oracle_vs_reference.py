@@ -53,3 +53,23 @@ def test_fresh_seed_line_by_line(solution, built, workdir):
         comp = np.abs(d["ext"][m]).sum(axis=1) > 0
         assert relerr(o["ext"][comp], d["ext"][m][comp]) < 1e-6
         assert relerr(o["spectrum"], d["spectra"][m]) < 1e-6
+
+
+@pytest.mark.parametrize("k", list(__import__("cases").FUZZ_GPU))
+def test_randomised_configurations(k, built, workdir):
+    """Seeded random configurations (geometry, layer count, toomuch incl. 1e100, ray grids of 2-6
+    angles, knobs, spectral window; tests/cases.py build_fuzz_case) through the compiled reference
+    and the oracle.  The GPU suite runs the same configurations through the CUDA path."""
+    import cases
+    from oracle import oracle as orc
+    case, models, setters = cases.build_fuzz_case(k, workdir)
+    mp, op = os.path.join(case["workdir"], "m.npy"), os.path.join(case["workdir"], "ref.npz")
+    np.save(mp, models)
+    conftest.run_reference(case["cfg"], mp, op, setters)
+    d = np.load(op)
+    O = orc.Oracle(case["cfg"])
+    apply_setters(O, setters)
+    for m in range(2):
+        o = O.run(models[m], inter=True)
+        assert np.array_equal(o["last"], d["last"][m])
+        assert relerr(o["spectrum"], d["spectra"][m]) < 1e-8
