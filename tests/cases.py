@@ -161,6 +161,25 @@ def build_fuzz_case(k, workdir):
     return case, models, setters
 
 
+def build_builder_fuzz_case(k, workdir):
+    """Seeded random builder configuration k (no opacity file on disk): molecules, layers, line
+    count, oversampling, profile width, weak-line threshold, spectral step, temperature grid."""
+    rng = np.random.default_rng(9500 + k)
+    mols = [["CH4"], ["H2O", "CH4"], ["H2O", "CO2", "CO", "CH4"], ["CO", "CH4"]][int(rng.integers(0, 4))]
+    lo = float(rng.uniform(1900.0, 2900.0))
+    shape = dict(wnlow=lo, wnhigh=lo + float(rng.uniform(60.0, 200.0)), wndelt=float(rng.choice([0.25, 0.5, 1.0, 2.0])),
+                 mols=mols, toomuch=10.0)
+    kw = dict(shape=shape, nlayer=int(rng.integers(6, 16)), with_grid=False, nlines=int(rng.integers(800, 6000)),
+              tempdelt=float(rng.choice([500.0, 650.0, 1300.0])), seed=9600 + k,
+              ethresh=float(rng.choice([1e-8, 1e-6, 1e-4, 1e-2])), wnosamp=int(rng.choice([360, 720, 1080, 2160])),
+              nwidth=int(rng.choice([10, 20, 40])))
+    case = synth.make_case(os.path.join(workdir, "bfuzz%d" % k), **kw)
+    if os.path.exists(case["opacity"]):
+        os.remove(case["opacity"])
+    return case
+
+
+FUZZ_BUILDER = range(6)
 FUZZ_CPU = range(6)          # against the compiled reference (build container)
 FUZZ_GPU = range(12)         # CUDA path against the oracle
 

@@ -24,6 +24,33 @@ def test_builder_oracle_vs_reference_grid(name, built, workdir):
     assert relerr(o, ref) < 1e-12          # float32 profiles are reproduced bit for bit
 
 
+@pytest.mark.parametrize("k", list(cases.FUZZ_BUILDER))
+def test_randomised_builder_configurations(k, built, workdir):
+    """Seeded random builder configurations (cases.build_builder_fuzz_case): the builder oracle
+    against the grid the compiled reference builds (`transit_ref --justOpacity`; build container
+    only).  The GPU suite runs the CUDA builder on the same configurations against the oracle."""
+    import os
+    import subprocess
+    import conftest
+    if not conftest.has_ref():
+        pytest.skip("oracle/_ref not built here")
+    from oracle import oracle as orc
+    from bart_b200 import synth
+    case = cases.build_builder_fuzz_case(k, workdir)
+    exe = os.path.join(cases.ROOT, "oracle", "_ref", "transit_ref")
+    r = subprocess.run([exe, "-c", case["cfg"], "--justOpacity"], capture_output=True, text=True)
+    assert r.returncode == 0 and os.path.exists(case["opacity"]), r.stdout[-1500:] + r.stderr[-1500:]
+    ref = synth.read_opacity(case["opacity"], mmap=False)
+    os.remove(case["opacity"])
+    B = orc.BuilderOracle(case["cfg"])
+    nl, nt = ref["o"].shape[0], ref["o"].shape[1]
+    layers, temps = sorted({0, nl // 2, nl - 1}), sorted({0, nt - 1})
+    o = B.build(layers=layers, temps=temps)
+    want = ref["o"][layers][:, temps]
+    assert np.array_equal(o > 0, want > 0)
+    assert relerr(o, want) < 1e-12
+
+
 def test_voigt_kat():
     """Known values of the Voigt function the profile table samples: pure-Doppler and
     pure-Lorentz limits (analytic), for the region formulas of voigt.c:132-200."""

@@ -118,3 +118,30 @@ def test_cli_temperature_slices_assemble_the_file(api, workdir):
     assert np.array_equal(sliced, whole)
     mine = synth.read_opacity(case["opacity"], mmap=False)
     assert relerr(mine["o"], g["grid"]) < TOL
+
+
+@pytest.mark.parametrize("k", list(cases.FUZZ_BUILDER))
+def test_randomised_builder_configurations(k, api, workdir):
+    """The seeded random builder configurations of cases.build_builder_fuzz_case (the oracle agrees
+    with the compiled reference's grids on all of them, tests/test_builder_oracle.py) through the
+    CUDA builder: whole file written, sampled cells against the oracle, line bins bit-exact."""
+    import ctypes as C
+    from oracle import oracle as orc
+    from bart_b200 import synth
+    case = cases.build_builder_fuzz_case(k, workdir)
+    tr = api.Transit(argv=["transit", "-c", case["cfg"], "--justOpacity"])
+    mine = synth.read_opacity(case["opacity"], mmap=False)
+    B = orc.BuilderOracle(case["cfg"])
+    nl, nt = mine["o"].shape[0], mine["o"].shape[1]
+    assert np.array_equal(mine["temps"], B.temps) and list(mine["molids"]) == list(B.gmol_id)
+    layers, temps = sorted({0, nl // 2, nl - 1}), sorted({0, nt - 1})
+    ref = B.build(layers=layers, temps=temps, trace=True)
+    got = mine["o"][layers][:, temps]
+    assert np.array_equal(got > 0, ref > 0)
+    assert relerr(got, ref) < TOL
+    n = len(B.wl)
+    bins = np.zeros(n, dtype=np.int64)
+    assert api.lib().bart_line_bins(bins.ctypes.data_as(C.POINTER(C.c_longlong)), n) == n
+    B.build(layers=[0], temps=[0], trace=True)           # the trace of the cell the library reports
+    assert np.array_equal(bins, B.trace)
+    tr.free_memory()
