@@ -179,6 +179,25 @@ def build_builder_fuzz_case(k, workdir):
     return case
 
 
+def build_lbl_fuzz_case(k, workdir):
+    """Seeded random line-by-line forward configuration k (no opacity file) -> (case, models)."""
+    rng = np.random.default_rng(9700 + k)
+    mols = [["CH4"], ["H2O", "CH4"], ["H2O", "CO2", "CO", "CH4"]][int(rng.integers(0, 3))]
+    lo = float(rng.uniform(1900.0, 2900.0))
+    solution = ("eclipse", "transit")[k % 2]
+    shape = dict(wnlow=lo, wnhigh=lo + float(rng.uniform(60.0, 180.0)), wndelt=float(rng.choice([0.5, 1.0, 2.0])),
+                 mols=mols, toomuch=float(rng.choice([10.0, 1e100])))
+    case = synth.make_case(os.path.join(workdir, "lfuzz%d" % k), shape=shape, solution=solution,
+                           nlayer=int(rng.integers(10, 30)), with_grid=False, no_opacity=True,
+                           nlines=int(rng.integers(800, 5000)), seed=9800 + k,
+                           ethresh=float(rng.choice([1e-8, 1e-5, 1e-3])), wnosamp=int(rng.choice([720, 1080, 2160])),
+                           nwidth=int(rng.choice([10, 20, 40])),
+                           refradius_km=95000.0 if solution == "transit" else 123820.0)
+    molfit = tuple(m for m in ("H2O", "CO2", "CO", "CH4") if m in mols)
+    return case, synth.make_models(case, 2, seed=300 + k, molfit=molfit)
+
+
+FUZZ_LBL = range(4)
 FUZZ_BUILDER = range(6)
 FUZZ_CPU = range(6)          # against the compiled reference (build container)
 FUZZ_GPU = range(12)         # CUDA path against the oracle

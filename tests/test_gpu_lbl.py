@@ -108,3 +108,24 @@ def test_lbl_equals_grid_mode_at_a_grid_temperature(api, workdir):
     assert np.array_equal(ext_l > 0, ext_g > 0)
     assert relerr(ext_l, ext_g) < 1e-12
     assert relerr(spec_l, spec_g) < 1e-12
+
+
+@pytest.mark.parametrize("k", list(cases.FUZZ_LBL))
+def test_randomised_line_by_line_configurations(k, api, workdir):
+    """cases.build_lbl_fuzz_case (the oracle agrees with the compiled reference on each,
+    tests/test_oracle_vs_reference.py) through the CUDA path."""
+    from oracle import oracle as orc
+    case, models = cases.build_lbl_fuzz_case(k, workdir)
+    tr = api.Transit(case["cfg"])
+    O = orc.Oracle(case["cfg"])
+    ext = tr.extinction_batch(models, total=False)
+    tr.debug_keep(True)
+    spectra, status = tr.run_batch(models)
+    assert (status == 0).all()
+    for m in range(models.shape[0]):
+        o = O.run(models[m], inter=True)
+        assert np.array_equal(ext[m] > 0, o["ext"] > 0)
+        assert relerr(ext[m], o["ext"]) < TOL
+        assert np.array_equal(tr.debug_get("last", m).astype(np.int64), o["last"])
+        assert relerr(spectra[m], o["spectrum"]) < TOL
+    tr.free_memory()

@@ -73,3 +73,25 @@ def test_randomised_configurations(k, built, workdir):
         o = O.run(models[m], inter=True)
         assert np.array_equal(o["last"], d["last"][m])
         assert relerr(o["spectrum"], d["spectra"][m]) < 1e-8
+
+
+@pytest.mark.parametrize("k", list(__import__("cases").FUZZ_LBL))
+def test_randomised_line_by_line_configurations(k, built, workdir):
+    """Seeded random configurations WITHOUT an opacity file (cases.build_lbl_fuzz_case): the oracle's
+    line-by-line forward mode against the compiled reference; the GPU suite runs the same through
+    the CUDA path."""
+    import cases
+    from oracle import oracle as orc
+    case, models = cases.build_lbl_fuzz_case(k, workdir)
+    mp, op = os.path.join(case["workdir"], "m.npy"), os.path.join(case["workdir"], "ref.npz")
+    np.save(mp, models)
+    conftest.run_reference(case["cfg"], mp, op, {})
+    d = np.load(op)
+    O = orc.Oracle(case["cfg"])
+    for m in range(2):
+        o = O.run(models[m], inter=True)
+        assert np.array_equal(o["last"], d["last"][m])
+        comp = np.abs(d["ext"][m]).sum(axis=1) > 0
+        assert np.array_equal(o["ext"][comp] > 0, d["ext"][m][comp] > 0)
+        assert relerr(o["ext"][comp], d["ext"][m][comp]) < 1e-6
+        assert relerr(o["spectrum"], d["spectra"][m]) < 1e-6
