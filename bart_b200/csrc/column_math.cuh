@@ -8,6 +8,7 @@
 #include "device.cuh"
 #include <cmath>
 #include <cstring>
+#include <vector>
 
 namespace bart {
 
@@ -162,6 +163,67 @@ BART_HD double fast_exp(double x, const unsigned long long *tab) {
   return exp_core(x, kExpScale, tab, 0.0);
 }
 
+// Reduced-degree variants for the eclipse column kernel, whose instruction count is what bounds it
+// (DESIGN.md section 4).  Coefficients interpolate e^(r ln2/N) at the Chebyshev nodes of
+// |r| <= 1/2: degree 4 is within 2.6e-12 relative, degree 5 within 9e-15 (tests/test_emu_math.py).
+constexpr double kExp4C1 = 0.043321698760160544, kExp4C2 = 0.0009383847926296646,
+                 kExp4C3 = 1.3551205154935067e-05, kExp4C4 = 1.4676387238435006e-07;
+constexpr double kExp5C1 = 0.04332169878499661, kExp5C2 = 0.000938384792486206,
+                 kExp5C3 = 1.355080777749983e-05, kExp5C4 = 1.467644462189871e-07,
+                 kExp5C5 = 1.2716085030349987e-09;
+constexpr double kExpMagic = 6755399441055744.0;                  // 1.5 * 2^52
+
+// table value for the low word m of the rounded sum t: 2^(m/N) (or wgt 2^(m/N) from an angle's
+// table) -- layout: exp_table_entry
+BART_HD double exp_scale(double t, const unsigned long long *tab) {
+#ifdef __CUDA_ARCH__
+  const int m = __double2loint(t);
+  const uint2 e = *reinterpret_cast<const uint2 *>(tab + (m & (kExpTabSize - 1)));
+  return __hiloint2double((int)(e.y + ((unsigned)m << (20 - kExpBits))), (int)e.x);
+#else
+  const int m = (int)double_to_bits(t);
+  const unsigned long long e = tab[m & (kExpTabSize - 1)];
+  const unsigned hi = (unsigned)(e >> 32) + ((unsigned)m << (20 - kExpBits));
+  return bits_to_double((long long)(((unsigned long long)hi << 32) | (e & 0xffffffffull)));
+#endif
+}
+// exp(a*b*ln2/N) + addend, degree 5
+BART_HD double exp_core5(double a, double b, const unsigned long long *tab, double addend) {
+  const double t = fma(a, b, kExpMagic);
+  const double r = fma(a, b, -(t - kExpMagic));
+  double p = kExp5C5;
+  p = fma(p, r, kExp5C4);
+  p = fma(p, r, kExp5C3);
+  p = fma(p, r, kExp5C2);
+  p = fma(p, r, kExp5C1);
+  p = fma(p, r, 1.0);
+  return fma(p, exp_scale(t, tab), addend);
+}
+// acc + s exp(a*b*ln2/N), degree 4, 8 fp64 instructions; s is whatever factor `tab` carries (1 for
+// the plain table, the angle's weight for its own table: fill_ecl_exp_table)
+BART_HD double exp_w(double a, double b, const unsigned long long *tab, double acc) {
+  const double t = fma(a, b, kExpMagic);
+  const double r = fma(a, b, -(t - kExpMagic));
+  double p = kExp4C4;
+  p = fma(p, r, kExp4C3);
+  p = fma(p, r, kExp4C2);
+  p = fma(p, r, kExp4C1);
+  p = fma(p, r, 1.0);
+  return fma(p, exp_scale(t, tab), acc);
+}
+
+// 1/d for finite d > 0 to 2^-44: hardware seed (MUFU.RCP64H, 2^-22) + one Newton step
+BART_HD double fast_rcp1(double d) {
+#ifdef __CUDA_ARCH__
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  const double e = fma(-d, r, 1.0);
+  return fma(r, e, r);
+#else
+  return 1.0 / d;
+#endif
+}
+
 // 1/d for finite d > 0: hardware seed (MUFU.RCP64H) + two Newton steps; the compiler's IEEE
 // divide is ~3x the issue slots because of its special-case branches.
 BART_HD double fast_rcp(double d) {
@@ -208,9 +270,50 @@ inline void fill_angle_consts(DevConfig &c) {
   c.sq_src = c.sq_dst = -1;
   for (int b = 0; b < c.nang && c.sq_dst < 0; b++)
     for (int a = 0; a < b; a++)
-      if (fabs(c.inv_mu[b] - 2.0 * c.inv_mu[a]) <= 4e-16 * c.inv_mu[b]) { c.sq_src = a; c.sq_dst = b; break; }
-  c.tau_small = smax > 0 ? 0.3 / smax : 0.0;
-  c.tau_clamp = smax > 0 ? 700.0 / smax : 700.0;
+      if (fabs(c.inv_mu[b] - 2.0 * c.inv_mu[a]) <= 4e-16 * c.inv_mu[b] && fabs(c.wgt[a]) > 1e-100) {
+        c.sq_src = a; c.sq_dst = b; break;
+      }
+  // the series has kTaylorN = 12 terms: at tau smax <= 0.5 its truncation error is 0.5^12/12! = 5e-13
+  c.tau_small = smax > 0 ? 0.5 / smax : 0.0;
+  // the clamp keeps wgt exp(-tau inv_mu) a normal number (the weights live in the angle tables)
+  double lnw_min = 0.0;
+  for (int a = 0; a < c.nang; a++)
+    if (fabs(c.wgt[a]) > 1e-100 && log(fabs(c.wgt[a])) < lnw_min) lnw_min = log(fabs(c.wgt[a]));
+  c.tau_clamp = (690.0 + lnw_min) / (smax > 0 ? smax : 1.0);
+  c.sq_coef = c.sq_dst >= 0 ? c.wgt[c.sq_dst] / (c.wgt[c.sq_src] * c.wgt[c.sq_src]) : 0.0;
+}
+
+// Shared-memory exp tables of the eclipse kernel: the plain 2^(j/N) table followed by one table per
+// ray angle holding wgt[a] 2^(j/N) (same biased layout), kEclTabEntries(nang) entries in all.  A
+// weight below 1e-100 in magnitude counts as zero: its table holds 2^-1000 2^(j/N).
+BART_HD int ecl_tab_entries(int nang) { return (1 + nang) * kExpTabSize; }
+inline void fill_ecl_exp_table(const DevConfig &c, unsigned long long *tab) {
+  fill_exp_table(tab);
+  for (int a = 0; a < c.nang; a++) {
+    const long double w = fabs(c.wgt[a]) > 1e-100 ? (long double)c.wgt[a] : ldexpl(1.0L, -1000);
+    for (int j = 0; j < kExpTabSize; j++) {
+      const double v = (double)(w * exp2l((long double)j / kExpTabSize));
+      tab[(1 + a) * kExpTabSize + j] =
+          (unsigned long long)double_to_bits(v) - ((unsigned long long)j << (32 + 20 - kExpBits));
+    }
+  }
+}
+
+// CIA tables for the device: [T_k][wave][4] = (P_k, Q_k, P_k+1, Q_k+1) (P = table column splined
+// onto the spectrum grid, Q = its temperature second derivative; the last node repeats itself),
+// followed by `pad` samples of zeros.
+inline std::vector<double> pack_cia_quads(const std::vector<double> &P, const std::vector<double> &Q,
+                                          int nt, int nw, int pad) {
+  std::vector<double> out((size_t)nt * nw * 4 + (size_t)pad * 4, 0.0);
+  for (int k = 0; k < nt; k++) {
+    const int k1 = k + 1 < nt ? k + 1 : k;
+    for (int w = 0; w < nw; w++) {
+      double *o = &out[((size_t)k * nw + w) * 4];
+      o[0] = P[(size_t)k * nw + w];  o[1] = Q[(size_t)k * nw + w];
+      o[2] = P[(size_t)k1 * nw + w]; o[3] = Q[(size_t)k1 * nw + w];
+    }
+  }
+  return out;
 }
 
 struct KnobVals {
@@ -333,7 +436,7 @@ BART_HD int prep_table_row(const DevConfig &c, const KnobVals &kv, int d, const 
   row[L.INVT] = 1.0 / T;
   row[L.RAD] = radius[l];
   row[L.PF] = c.planck_cols > 0 ? exp(c.planck_step / T) : 1.0;
-  row[L.PF + 1] = 0.0;
+  row[L.GOFF + 1] = 0.0;
 
   // opacity-grid bracket and folded weights (interpolmolext, extinction.c:534-581)
   if (T < c.gtemp[0] || T > c.gtemp[c.ntemp - 1]) status |= REJ_TGRID;
@@ -376,7 +479,7 @@ BART_HD int prep_table_row(const DevConfig &c, const KnobVals &kv, int d, const 
       cz1 = dx * (-h / 6.0 + dx * dx / (6.0 * h));
     }
     double *cr = row + L.cia(f);
-    cr[0] = bits_to_double((long long)k * c.nwave * 16);
+    cr[0] = bits_to_double((long long)k * c.nwave * 32);
     cr[1] = (double)k;
     cr[2] = cy0 * dens;
     cr[3] = cy1 * dens;
@@ -439,7 +542,7 @@ BART_HD ColPtrs col_ptrs(const DevConfig &c, int w) {
   P.g = reinterpret_cast<const char *>(c.grid) + (size_t)w * c.gms * 8;
 #pragma unroll
   for (int f = 0; f < (NCIA >= 0 ? NCIA : kMaxCia); f++)
-    P.cia[f] = f < c.ncia ? reinterpret_cast<const char *>(c.ciaPQ[f]) + (size_t)w * 16 : nullptr;
+    P.cia[f] = f < c.ncia ? reinterpret_cast<const char *>(c.ciaPQ[f]) + (size_t)w * 32 : nullptr;
   return P;
 }
 
@@ -448,51 +551,75 @@ BART_HD ColPtrs col_ptrs(const DevConfig &c, int w) {
 // reference's summation order (tau.c:231-232).  `row` is the depth's table record.  NMOL / NCIA
 // are compile-time counts (NMOL 0 / NCIA -1 = take them from the configuration at run time).
 // The lookup is split into cell_load (issues the global loads: one 8/16/32-byte vector per
-// bracketing temperature plane carrying all molecules of the sample, one 16-byte pair per CIA
-// temperature node) and cell_combine (the arithmetic), so that a column kernel can issue the
-// loads of the next depth before it works on the current one.
+// bracketing temperature plane carrying all molecules of the sample, one 32-byte vector per CIA
+// file carrying both temperature nodes) and cell_combine (the arithmetic), so that a column kernel
+// can issue the loads of the next depth before it works on the current one.
 template <int NMOL, int NCIA>
 struct CellData {
   static constexpr bool kStatic = NMOL >= 1 && NMOL <= 4;      // grid sample preloaded (vector load)
-  static constexpr bool kStaticCia = kStatic && NCIA >= 0;     // CIA pairs preloaded too
+  static constexpr bool kStaticCia = kStatic && NCIA >= 0;     // CIA samples preloaded too
   static constexpr int NG = !kStatic ? 1 : (NMOL == 1 ? 1 : (NMOL == 2 ? 2 : 4));
   static constexpr int NC = kStaticCia && NCIA > 0 ? NCIA : 1;
   double lo[NG], hi[NG];
-  D2 k0[NC], k1[NC];
+  D4 q[NC];                                                    // (P_k, Q_k, P_k+1, Q_k+1)
 };
 
+// Byte offsets of one depth's samples from the column pointers: grid plane (layer, it) and the CIA
+// bracket rows, as stored in the table record.
+template <int NCIA>
+struct CellOffs {
+  long long g;
+  long long cia[NCIA > 0 ? NCIA : 1];
+};
 template <int NMOL, int NCIA>
-BART_HD void cell_load(const DevConfig &c, const ColPtrs &P, const double *row,
-                       CellData<NMOL, NCIA> &x) {
+BART_HD CellOffs<NCIA> cell_offsets(const double *row) {
   typedef TabLayout L;
+  CellOffs<NCIA> o;
+  o.g = double_to_bits(row[L::GOFF]);
+#pragma unroll
+  for (int f = 0; f < (NCIA > 0 ? NCIA : 0); f++) o.cia[f] = double_to_bits(row[L::W + 2 * NMOL + 6 * f]);
+  return o;
+}
+
+// goff / coff: byte offsets of this column from the column P addresses (grid / CIA tables); as
+// compile-time constants they become the immediate offsets of the load instructions
+// with_cia false: only the grid samples are loaded and x.q keeps what it holds (a caller that
+// walks down a column reloads the CIA samples only when the layer's bracket row changes)
+template <int NMOL, int NCIA>
+BART_HD void cell_load_at(const DevConfig &c, const ColPtrs &P, const CellOffs<NCIA> &o,
+                          CellData<NMOL, NCIA> &x, size_t goff = 0, size_t coff = 0,
+                          bool with_cia = true) {
   if (!CellData<NMOL, NCIA>::kStatic) return;                  // run-time counts: loaded in cell_combine
   const size_t plane = (size_t)c.nwave * c.gms * 8;
-  const char *lo = P.g + double_to_bits(row[L::GOFF]);
+  const char *lo = P.g + o.g;
   const char *hi = lo + plane;
-  if (NMOL == 1) { x.lo[0] = ldg1b(lo); x.hi[0] = ldg1b(hi); }
+  if (NMOL == 1) { x.lo[0] = ldg1b(lo + goff); x.hi[0] = ldg1b(hi + goff); }
   else if (NMOL == 2) {
-    const D2 a = ldg2b(lo), b = ldg2b(hi);
+    const D2 a = ldg2b(lo + goff), b = ldg2b(hi + goff);
     x.lo[0] = a.x; x.lo[1] = a.y; x.hi[0] = b.x; x.hi[1] = b.y;
   } else {
-    const D4 a = ld4b(lo), b = ld4b(hi);
+    const D4 a = ld4b(lo + goff), b = ld4b(hi + goff);
     x.lo[0] = a.x; x.lo[1] = a.y; x.lo[2] = a.z; x.lo[3] = a.w;
     x.hi[0] = b.x; x.hi[1] = b.y; x.hi[2] = b.z; x.hi[3] = b.w;
   }
-  if (!CellData<NMOL, NCIA>::kStaticCia) return;
-  const double *cr = row + L::W + 2 * NMOL;
-  const size_t cplane = (size_t)c.nwave * 16;
+  if (!CellData<NMOL, NCIA>::kStaticCia || !with_cia) return;
 #pragma unroll
-  for (int f = 0; f < (NCIA > 0 ? NCIA : 0); f++) {
-    const char *pq = P.cia[f] + double_to_bits(cr[6 * f]);
-    x.k0[f] = ldg2b(pq);                                       // (value, d2/dT2) at T_k
-    x.k1[f] = ldg2b(pq + cplane);                              //                    T_k+1
-  }
+  for (int f = 0; f < (NCIA > 0 ? NCIA : 0); f++) x.q[f] = ld4b(P.cia[f] + o.cia[f] + coff);
 }
 
 template <int NMOL, int NCIA>
+BART_HD void cell_load(const DevConfig &c, const ColPtrs &P, const double *row,
+                       CellData<NMOL, NCIA> &x, size_t goff = 0, size_t coff = 0) {
+  if (!CellData<NMOL, NCIA>::kStatic) return;
+  cell_load_at<NMOL, NCIA>(c, P, cell_offsets<NMOL, NCIA>(row), x, goff, coff);
+}
+
+template <int NMOL, int NCIA, bool SC = true>
 BART_HD double cell_combine(const DevConfig &c, const ColPtrs &P, const double *row,
-                            const CellData<NMOL, NCIA> &x, double wn4, int part) {
+                            const CellData<NMOL, NCIA> &x, double wn4, int part,
+                            size_t goff = 0, size_t coff = 0) {
   // part: 0 = total extinction, 1 = molecular lines only, 2 = collision-induced absorption only
+  // SC false: the caller knows that the scattering and cloud terms of every record are zero
   typedef TabLayout L;
   const int ngmol = NMOL > 0 ? NMOL : c.ngmol;
   const int ncia = NCIA >= 0 ? NCIA : c.ncia;
@@ -507,7 +634,7 @@ BART_HD double cell_combine(const DevConfig &c, const ColPtrs &P, const double *
     }
   } else {
     const size_t plane = (size_t)c.nwave * c.gms * 8;
-    const char *lo = P.g + double_to_bits(row[L::GOFF]);
+    const char *lo = P.g + double_to_bits(row[L::GOFF]) + goff;
     const char *hi = lo + plane;
     for (int m = 0; m < ngmol; m++) {
       const D2 wt = ld2(row + L::W + 2 * m);
@@ -518,35 +645,36 @@ BART_HD double cell_combine(const DevConfig &c, const ColPtrs &P, const double *
   if (part == 1) return e;
   double ecs = 0.0;
   const double *cr = row + L::W + 2 * ngmol;
-  const size_t cplane = (size_t)c.nwave * 16;
 #pragma unroll
   for (int f = 0; f < (NCIA >= 0 ? NCIA : kMaxCia); f++) {
     if (f < ncia) {
-      D2 k0, k1;
-      if (CellData<NMOL, NCIA>::kStaticCia) { k0 = x.k0[f < CellData<NMOL, NCIA>::NC ? f : 0]; k1 = x.k1[f < CellData<NMOL, NCIA>::NC ? f : 0]; }
+      D4 q;
+      if (CellData<NMOL, NCIA>::kStaticCia) q = x.q[f < CellData<NMOL, NCIA>::NC ? f : 0];
       else {
-        const char *pq = P.cia[f] + double_to_bits(cr[6 * f]);
-        k0 = ld2b(pq); k1 = ld2b(pq + cplane);
+        const char *pq = P.cia[f] + double_to_bits(cr[6 * f]) + coff;
+        const D2 k0 = ld2b(pq), k1 = ld2b(pq + 16);
+        q.x = k0.x; q.y = k0.y; q.z = k1.x; q.w = k1.y;
       }
       const D2 cy = ld2(cr + 6 * f + 2), cz = ld2(cr + 6 * f + 4);
-      double v = cy.x * k0.x;
-      v = fma(cy.y, k1.x, v);
-      v = fma(cz.x, k0.y, v);
-      v = fma(cz.y, k1.y, v);
+      double v = cy.x * q.x;
+      v = fma(cy.y, q.z, v);
+      v = fma(cz.x, q.y, v);
+      v = fma(cz.y, q.w, v);
       if (hi_word(v) > 0) ecs += v;                            // v > 0 (crosssec.c:330)
     }
   }
   if (part == 2) return ecs;
+  if (!SC) return e + ecs;                                     // = (e + 0 wn4) + 0 + ecs, to the bit
   const D2 sc = ld2(row + L::SCAT);                            // (scattering coefficient, cloud)
   return fma(sc.x, wn4, e) + sc.y + ecs;
 }
 
-template <int NMOL, int NCIA>
+template <int NMOL, int NCIA, bool SC = true>
 BART_HD double cell_extinction(const DevConfig &c, const ColPtrs &P, const double *row, double wn4,
-                               int part) {
+                               int part, size_t goff = 0, size_t coff = 0) {
   CellData<NMOL, NCIA> x;
-  cell_load<NMOL, NCIA>(c, P, row, x);
-  return cell_combine<NMOL, NCIA>(c, P, row, x, wn4, part);
+  cell_load<NMOL, NCIA>(c, P, row, x, goff, coff);
+  return cell_combine<NMOL, NCIA, SC>(c, P, row, x, wn4, part, goff, coff);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -561,16 +689,28 @@ BART_HD double cell_extinction(const DevConfig &c, const ColPtrs &P, const doubl
 //        exp(-tau_i/mu_a).  The angle sum commutes with the layer sum, so the column carries
 //        D_i = sum_a wgt_a d_i^a: F = pi [B_L D_L - 1/2 sum_i (D_{i+1} - D_i)(B_{i+1} + B_i)].
 //        While every column of the warp has tau <= tau_small, D comes from its Maclaurin series
-//        (one polynomial instead of one exp per angle).
+//        (one polynomial instead of one exp per angle).  The Planck prefactor 2 h c^2 wn^3 is
+//        common to every layer of a column and is applied once, to the result.
+// fp64 instruction budget per (depth, column) on the exponential branch (W12: 4 molecules, 1 CIA
+// file, 5 angles with one squaring): extinction 15, tau 2.5, Planck 7 (one degree-4 exponential
+// per thread, chained to the thread's other columns; reciprocal by seed + one Newton step), D 34
+// (four degree-4 exponentials whose table factor carries the angle's weight, so the angle sum
+// rides on their last multiply-add), layer sum 3, toomuch test 1.
 // All 32 lanes of a warp must enter together (warp votes); a column that has passed its `last`
 // layer idles until the warp's deepest column is done.  A thread carries NCOL independent
-// columns of the same model (the table record of a depth is read once for all of them, and the
-// independent dependency chains overlap); a column with valid[k] false idles from the start.
+// columns of the same model, CSTRIDE samples apart starting at w0 (the table record of a depth is
+// read once for all of them, and the independent dependency chains overlap); a column with
+// valid[k] false idles from the start -- it may lie past the end of the spectrum: its loads are
+// issued all the same (the launcher pads the grid and the CIA tables by NCOL CSTRIDE samples).
+// etab: ecl_tab_entries(nang) entries (fill_ecl_exp_table).
 // SQ >= 0 encodes (src << 4 | dst): the exponential of angle dst is the square of that of src
-// (1/mu_dst = 2/mu_src, e.g. 60 and 0 degrees of the default ray grid); CHAIN: Planck chaining.
-template <int NMOL, int NCIA, int NANG, bool KEEP, int NCOL, int SQ = -1, bool CHAIN = false>
+// (1/mu_dst = 2/mu_src, e.g. 60 and 0 degrees of the default ray grid); CHAIN: Planck chaining;
+// PGEN: Planck exponent clamped per column and evaluated to degree 5 (DevConfig::planck_generic);
+// SC false: no scattering and no cloud in any record of the launch (the terms are skipped).
+template <int NMOL, int NCIA, int NANG, bool KEEP, int NCOL, int SQ = -1, bool CHAIN = false,
+          int CSTRIDE = 0, bool PGEN = true, bool SC = true>
 BART_HD void eclipse_columns(const DevConfig &c, const double *tab, const unsigned long long *etab,
-                             const int (&w)[NCOL], const bool (&valid)[NCOL],
+                             int w0, const bool (&valid)[NCOL],
                              double *const (&tau_keep)[NCOL], int *const (&last_keep)[NCOL],
                              double (&flux)[NCOL]) {
   typedef TabLayout L;
@@ -578,47 +718,51 @@ BART_HD void eclipse_columns(const DevConfig &c, const double *tab, const unsign
   const int nf = c.lay.nf();
   const int nang = NANG > 0 ? NANG : c.nang;
   const int small_hi = hi_word(c.tau_small), clamp_hi = hi_word(c.tau_clamp);
-  double wn4[NCOL], c1[NCOL], c2n[NCOL], invt_cap[NCOL];
+  constexpr bool kStatic = CellData<NMOL, NCIA>::kStatic;
+  const size_t gstep = (size_t)CSTRIDE * (kStatic ? CellData<NMOL, NCIA>::NG : c.gms) * 8;
+  const size_t cstep = (size_t)CSTRIDE * 32;
+  double wn4[NCOL], c2n[NCOL];
   double er1[NCOL], er2[NCOL], S[NCOL], trap[NCOL], Dprev[NCOL], Bprev[NCOL];
   int last[NCOL];
   bool alive[NCOL];
-  ColPtrs P[NCOL];
+  const ColPtrs P = col_ptrs<NCIA>(c, w0);
+
+  // Planck function without its prefactor, 1/(exp(hc wn/(k T)) - 1), of every column at one depth
+  // (eclipse_intens, eclipse.c:130-140)
+  auto planck = [&](const double *row, double (&B)[NCOL]) {
+    double E = 0.0;
+    const D2 tp = ld2(row + L::INVT);                          // (1/T, chaining factor)
+#pragma unroll
+    for (int k = 0; k < NCOL; k++) {
+      double em1;
+      if (CHAIN && k > 0) {
+        em1 = fma(E, tp.y, -1.0);
+        if (k + 1 < NCOL) E *= tp.y;
+      } else {
+        double it = tp.x;
+        if (PGEN && it * c2n[k] > kExpYmax) it = kExpYmax / c2n[k];           // exponent <= 700
+        if (CHAIN && NCOL > 1) {
+          E = PGEN ? exp_core5(c2n[k], it, etab, 0.0) : exp_w(c2n[k], it, etab, 0.0);
+          em1 = E - 1.0;
+        } else em1 = PGEN ? exp_core5(c2n[k], it, etab, -1.0) : exp_w(c2n[k], it, etab, -1.0);
+      }
+      B[k] = fast_rcp1(em1);
+    }
+  };
 
   // depth 0 (top): tau = 0, D = D(0)
 #pragma unroll
   for (int k = 0; k < NCOL; k++) {
-    const double wn = c.wn[w[k]];
+    const int wk = w0 + k * CSTRIDE;
+    const double wn = c.wn[wk < c.nwave ? wk : c.nwave - 1];
     wn4[k] = (wn * wn) * (wn * wn);
-    c1[k] = 2.0 * cH * (wn * wn * wn) * cLS * cLS;
     c2n[k] = cH * wn * cLS / cKB * kExpScale;                  // Planck exponent x N/ln2, per 1/T
-    invt_cap[k] = kExpYmax / c2n[k];                           // keeps the exponent below 700
-    P[k] = col_ptrs<NCIA>(c, w[k]);
-    er1[k] = cell_extinction<NMOL, NCIA>(c, P[k], tab, wn4[k], false);
+    er1[k] = cell_extinction<NMOL, NCIA, SC>(c, P, tab, wn4[k], false, k * gstep, k * cstep);
     er2[k] = 0.0; S[k] = 0.0; trap[k] = 0.0; Dprev[k] = c.taylor[0];
     alive[k] = valid[k] && !(0.0 > c.toomuch);
     last[k] = alive[k] ? nl - 1 : 0;
     if (KEEP && valid[k]) tau_keep[k][0] = 0.0;
   }
-
-  // Planck function of every column at one depth (eclipse_intens, eclipse.c:130-140)
-  auto planck = [&](const double *row, double (&B)[NCOL]) {
-    double E = 0.0;
-#pragma unroll
-    for (int k = 0; k < NCOL; k++) {
-      double em1;
-      if (CHAIN && k > 0) {
-        const double pf = row[L::PF];
-        em1 = fma(E, pf, -1.0);
-        if (k + 1 < NCOL) E *= pf;
-      } else {
-        double it = row[L::INVT];
-        if (hi_word(it) > hi_word(invt_cap[k])) it = invt_cap[k];
-        if (CHAIN && NCOL > 1) { E = exp_core(c2n[k], it, etab, 0.0); em1 = E - 1.0; }
-        else em1 = exp_core(c2n[k], it, etab, -1.0);
-      }
-      B[k] = c1[k] * fast_rcp(em1);
-    }
-  };
   planck(tab, Bprev);
 
   auto any_alive = [&]() {
@@ -629,23 +773,35 @@ BART_HD void eclipse_columns(const DevConfig &c, const double *tab, const unsign
   };
 
   // software pipeline: the loads of depth d + 1 are issued as soon as the data of depth d has
-  // been folded into its extinction (same registers), and complete under the ~100 fp64
-  // instructions of the rest of the step
+  // been folded into its extinction (same registers), and complete under the fp64 work of the
+  // rest of the step; their addresses come from offsets read one step earlier still, so that no
+  // load instruction waits on a shared-memory read
   CellData<NMOL, NCIA> cur[NCOL];
   const double *row_last = tab + (size_t)(nl - 1) * nf;
+  auto row_after = [&](const double *r) { return r < row_last ? r + nf : r; };   // the bottom depth re-reads itself
 #pragma unroll
-  for (int k = 0; k < NCOL; k++) cell_load<NMOL, NCIA>(c, P[k], nl > 1 ? tab + nf : tab, cur[k]);
+  for (int k = 0; k < NCOL; k++)
+    cell_load<NMOL, NCIA>(c, P, row_after(tab), cur[k], k * gstep, k * cstep);
+  CellOffs<NCIA> offs = cell_offsets<NMOL, NCIA>(row_after(row_after(tab)));    // of depth 2
+  // The CIA samples of a column depend on the depth only through the bracket row of the layer's
+  // temperature in the table's (coarse) temperature grid: consecutive layers mostly share it, so
+  // cur[k].q is kept and reloaded only when the next depth's row differs (warp-uniform test)
+  CellOffs<NCIA> have = cell_offsets<NMOL, NCIA>(row_after(tab));               // what cur[k].q holds
 
   auto step = [&](const double *row, int d, bool odd) {
     double tau[NCOL], B[NCOL], D[NCOL];
     bool small = true;
-    const double *rown = row < row_last ? row + nf : row;      // the bottom depth re-reads itself
     double erk[NCOL];
 #pragma unroll
     for (int k = 0; k < NCOL; k++) {
-      erk[k] = cell_combine<NMOL, NCIA>(c, P[k], row, cur[k], wn4[k], false);
-      cell_load<NMOL, NCIA>(c, P[k], rown, cur[k]);
+      erk[k] = cell_combine<NMOL, NCIA, SC>(c, P, row, cur[k], wn4[k], false, k * gstep, k * cstep);
     }
+    bool fresh = false;
+#pragma unroll
+    for (int f = 0; f < (NCIA > 0 ? NCIA : 0); f++) fresh = fresh || offs.cia[f] != have.cia[f];
+#pragma unroll
+    for (int k = 0; k < NCOL; k++) cell_load_at<NMOL, NCIA>(c, P, offs, cur[k], k * gstep, k * cstep, fresh);
+    if (kStatic) { have = offs; offs = cell_offsets<NMOL, NCIA>(row_after(row_after(row))); }
 #pragma unroll
     for (int k = 0; k < NCOL; k++) {
       const double er = erk[k];
@@ -668,24 +824,35 @@ BART_HD void eclipse_columns(const DevConfig &c, const double *tab, const unsign
         D[k] = p;
       }
     } else {
+      // exp arguments stay above -690: only the last depth of a column can exceed the clamp
+      bool big = false;
+#pragma unroll
+      for (int k = 0; k < NCOL; k++) big = big || hi_word(tau[k]) >= clamp_hi;
       double tc[NCOL];
 #pragma unroll
-      for (int k = 0; k < NCOL; k++) {
-        tc[k] = hi_word(tau[k]) >= clamp_hi ? c.tau_clamp : tau[k];
-        D[k] = 0.0;
+      for (int k = 0; k < NCOL; k++) tc[k] = tau[k];
+      if (BART_WARP_ANY(big)) {
+#pragma unroll
+        for (int k = 0; k < NCOL; k++) tc[k] = hi_word(tau[k]) >= clamp_hi ? c.tau_clamp : tau[k];
       }
-      double esq[NCOL];
+      if (SQ >= 0) {
+        // the source angle of the squaring first (its value is needed, not only its share of the
+        // sum), then the others ride on the running sum
+#pragma unroll
+        for (int k = 0; k < NCOL; k++) {
+          const double e = exp_w(tc[k], -c.exp_a[SQ >> 4], etab + (1 + (SQ >> 4)) * kExpTabSize, 0.0);
+          D[k] = fma(e * e, c.sq_coef, e);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < NCOL; k++) D[k] = 0.0;
+      }
 #pragma unroll
       for (int a = 0; a < (NANG > 0 ? NANG : kMaxAng); a++)
-        if (a < nang) {
+        if (a < nang && !(SQ >= 0 && (a == (SQ >> 4) || a == (SQ & 15)))) {
 #pragma unroll
-          for (int k = 0; k < NCOL; k++) {
-            double e;
-            if (SQ >= 0 && a == (SQ & 15)) e = esq[k] * esq[k];
-            else e = exp_core(tc[k], -c.exp_a[a], etab, 0.0);
-            if (SQ >= 0 && a == (SQ >> 4)) esq[k] = e;
-            D[k] = fma(e, c.wgt[a], D[k]);
-          }
+          for (int k = 0; k < NCOL; k++)
+            D[k] = exp_w(tc[k], -c.exp_a[a], etab + (1 + a) * kExpTabSize, D[k]);
         }
     }
 #pragma unroll
@@ -698,17 +865,22 @@ BART_HD void eclipse_columns(const DevConfig &c, const double *tab, const unsign
       }
   };
 
+  // the warp leaves the depth loop when all its columns have passed toomuch (checked every other
+  // depth: a step on a finished column changes nothing)
   const double *row = tab + nf;
   for (int d = 1; d < nl; d += 2, row += 2 * nf) {
     if (!any_alive()) break;
     step(row, d, true);
-    if (d + 1 >= nl || !any_alive()) break;
+    if (d + 1 >= nl) break;
     step(row + nf, d + 1, false);
   }
 #pragma unroll
   for (int k = 0; k < NCOL; k++) {
     if (KEEP && valid[k]) *last_keep[k] = last[k];
-    flux[k] = cPI * (Bprev[k] * Dprev[k] - 0.5 * trap[k]);
+    const int wk = w0 + k * CSTRIDE;
+    const double wn = c.wn[wk < c.nwave ? wk : c.nwave - 1];
+    const double c1 = 2.0 * cH * (wn * wn * wn) * cLS * cLS;
+    flux[k] = cPI * c1 * (Bprev[k] * Dprev[k] - 0.5 * trap[k]);
   }
 }
 
@@ -716,12 +888,11 @@ BART_HD void eclipse_columns(const DevConfig &c, const double *tab, const unsign
 template <int NMOL, int NCIA, int NANG, bool KEEP>
 BART_HD double eclipse_column(const DevConfig &c, const double *tab, const unsigned long long *etab,
                               int w, double *tau_keep, int *last_keep) {
-  const int ws[1] = {w};
   const bool valid[1] = {true};
   double *const tk[1] = {tau_keep};
   int *const lk[1] = {last_keep};
   double flux[1];
-  eclipse_columns<NMOL, NCIA, NANG, KEEP, 1>(c, tab, etab, ws, valid, tk, lk, flux);
+  eclipse_columns<NMOL, NCIA, NANG, KEEP, 1>(c, tab, etab, w, valid, tk, lk, flux);
   return flux[0];
 }
 

@@ -7,8 +7,9 @@
 //                                      even count when > 1): thread <-> wavenumber reads one
 //                                      (layer, temperature) plane as a contiguous stream of
 //                                      16-byte vector loads carrying all molecules of a sample.
-//   ciaPQ[file][temp][wave][2]         CIA tables pre-folded through the wavenumber spline
-//                                      (value, temperature second derivative) interleaved.
+//   ciaPQ[file][temp][wave][4]         CIA tables pre-folded through the wavenumber spline: (value,
+//                                      temperature second derivative) at node k and at node k+1,
+//                                      so one 32-byte load serves a (layer, wavenumber) cell.
 //   profiles[model][(1+nspec)*nlayer]  the caller's per-model input, verbatim.
 //   tab[model][field][depth]           per-model, per-layer coefficients written by atm_prep and
 //                                      staged into shared memory (one bulk-async copy) by the
@@ -34,17 +35,16 @@ constexpr int kTaylorN = 12;   // series degree 11
 // One model table = nlayer records of `nf()` doubles, one record per depth (0 = top layer), so a
 // column kernel reads everything it needs for a layer from one contiguous, 16-byte aligned
 // shared-memory record with compile-time offsets (warp-wide broadcast loads, LDS.128 for pairs).
-//   [0] 1/T      [1] byte offset (int64 bits) of grid plane (layer, it)   [2] scattering coef (x wn^4)
-//   [3] cloud    [4..6] Simpson panel coefficients   [7] trapezoid half-width
+//   [0] 1/T      [1] exp(planck_step/T): ratio of the Planck exponentials of two columns planck_cols apart
+//   [2] scattering coef (x wn^4)   [3] cloud    [4..6] Simpson panel coefficients   [7] trapezoid half-width
 //   [8] T        [9] radius (file units)
-//   [10] exp(planck_step/T): ratio of the Planck exponentials of two columns planck_cols apart
-//   [11] spare
+//   [10] byte offset (int64 bits) of grid plane (layer, it)   [11] spare
 //   [12+2m, 13+2m]  W0, W1 of grid molecule m:  rho*(t1-T)/(t1-t0), rho*(T-t0)/(t1-t0)
 //   [cia(f) .. +5]  CIA file f: table byte offset (int64 bits), bracket index, 4 cubic coefficients
 struct TabLayout {
   int nl, ngmol, ncia;
-  static constexpr int INVT = 0, GOFF = 1, SCAT = 2, CLOUD = 3, SA = 4, SB = 5, SC = 6, TR = 7,
-                       T = 8, RAD = 9, PF = 10, W = 12;
+  static constexpr int INVT = 0, PF = 1, SCAT = 2, CLOUD = 3, SA = 4, SB = 5, SC = 6, TR = 7,
+                       T = 8, RAD = 9, GOFF = 10, W = 12;
   BART_HD int cia(int f) const { return W + 2 * ngmol + 6 * f; }
   BART_HD int nf() const { return W + 2 * ngmol + 6 * ncia; }
   BART_HD int stride() const { return nf() * nl; }   // nf() is even: 16-byte granularity holds
@@ -76,6 +76,13 @@ struct DevConfig {
   double tau_small;         // warp-uniform switch to the series
   double tau_clamp;         // exp arguments stay above -700
   int sq_src, sq_dst;       // angles with inv_mu[sq_dst] = 2 inv_mu[sq_src] (exp by squaring), or -1
+  // weighted angle exponentials wgt[a] exp(-tau inv_mu[a]) (column_math.cuh exp_w): the weight is
+  // folded into a per-angle copy of the 2^(j/N) table (fill_ecl_exp_table), so the angle sum rides
+  // on the last multiply-add of each exponential
+  double sq_coef;           // wgt[sq_dst] / wgt[sq_src]^2
+  // 1: some layer/wavenumber of this configuration can have a Planck exponent hc wn/(k T) above 690
+  // or below 0.1 -> the column kernel with the per-column clamp and the degree-5 exponential
+  int planck_generic;
   // Planck chaining: a thread's columns are planck_cols samples apart on the uniform wavenumber
   // grid, so exp(c2 wn'/T) = exp(c2 wn/T) * exp(planck_step/T), planck_step = (hc/k) planck_cols dwn
   int planck_cols;          // 0 = no chaining

@@ -60,14 +60,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 
 // Stage one model's table into shared memory.  Bulk-async when the size allows (multiple of 16 B,
 // always true by TabLayout::stride), else a cooperative copy.
-// exp table entries (column_math.cuh exp_table_entry) in global memory, copied to shared per CTA
-__device__ unsigned long long g_exp_table[kExpTabSize];
+// exp table entries (column_math.cuh exp_table_entry; then one weighted copy per ray angle,
+// fill_ecl_exp_table) in global memory, copied to shared per CTA
+__device__ unsigned long long g_exp_table[(1 + kMaxAng) * kExpTabSize];
 
 __device__ __forceinline__ void stage_table(double *s_tab, const double *g_tab, int ndoubles,
                                             uint64_t *bar, bool use_tma,
-                                            unsigned long long *s_etab = nullptr) {
+                                            unsigned long long *s_etab = nullptr,
+                                            int n_etab = kExpTabSize) {
   if (s_etab)
-    for (int j = threadIdx.x; j < kExpTabSize; j += blockDim.x) s_etab[j] = g_exp_table[j];
+    for (int j = threadIdx.x; j < n_etab; j += blockDim.x) s_etab[j] = g_exp_table[j];
   if (use_tma) {
     if (threadIdx.x == 0) { mbar_init(bar, 1); fence_mbar_init(); }
     __syncthreads();
@@ -140,15 +142,17 @@ atm_prep_kernel(DevConfig c, Knobs knobs, const double *__restrict__ profiles, i
 
 // ---------------------------------------------------------------------------------------
 // fused eclipse column kernel
-template <int NMOL, int NCIA, int NANG, bool KEEP, int SQ>
+template <int NMOL, int NCIA, int NANG, bool KEEP, int SQ, bool SC>
 __global__ void __launch_bounds__(kEclThreads, 8)
 eclipse_column_kernel(DevConfig c, const double *__restrict__ tabs, const int *__restrict__ status,
                       double *__restrict__ spectra, double *__restrict__ tau_keep,
                       int *__restrict__ last_keep, int nmodels, int use_tma) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar;
-  unsigned long long *s_etab = reinterpret_cast<unsigned long long *>(smem_raw);   // exp table, one bank row
-  double *s_tab = reinterpret_cast<double *>(s_etab + kExpTabSize);
+  // exp tables (plain + one per ray angle), one 128-byte bank row each
+  unsigned long long *s_etab = reinterpret_cast<unsigned long long *>(smem_raw);
+  const int n_etab = ecl_tab_entries(NANG > 0 ? NANG : c.nang);
+  double *s_tab = reinterpret_cast<double *>(s_etab + n_etab);
   const int m = blockIdx.x % nmodels;           // model-fastest: neighbours share grid columns
   const int tile = blockIdx.x / nmodels;
   const int w0 = tile * (kEclThreads * kEclCols) + threadIdx.x;
@@ -160,10 +164,10 @@ eclipse_column_kernel(DevConfig c, const double *__restrict__ tabs, const int *_
       if (w0 + k * kEclThreads < c.nwave) out[w0 + k * kEclThreads] = -1.0;
     return;
   }
-  stage_table(s_tab, tabs + (size_t)m * nd, nd, &bar, use_tma != 0, s_etab);
-  // thread t carries columns w0 + t and w0 + 64 + t: each is its own coalesced stream.  Columns
-  // past the end of the spectrum shadow the last sample and idle (the warp votes need all lanes).
-  int w[kEclCols];
+  stage_table(s_tab, tabs + (size_t)m * nd, nd, &bar, use_tma != 0, s_etab, n_etab);
+  // thread t carries columns w0 and w0 + 64: each is its own coalesced stream, addressed from one
+  // base pointer with compile-time offsets.  Columns past the end of the spectrum idle (the warp
+  // votes need all lanes); their loads land in the padding behind the grid and the CIA tables.
   bool valid[kEclCols];
   double *tk[kEclCols];
   int *lk[kEclCols];
@@ -172,14 +176,18 @@ eclipse_column_kernel(DevConfig c, const double *__restrict__ tabs, const int *_
   for (int k = 0; k < kEclCols; k++) {
     const int wk = w0 + k * kEclThreads;
     valid[k] = wk < c.nwave;
-    w[k] = min(wk, c.nwave - 1);
-    tk[k] = KEEP ? tau_keep + ((size_t)m * c.nwave + w[k]) * c.nlayer : nullptr;
-    lk[k] = KEEP ? last_keep + (size_t)m * c.nwave + w[k] : nullptr;
+    const int wc = min(wk, c.nwave - 1);
+    tk[k] = KEEP ? tau_keep + ((size_t)m * c.nwave + wc) * c.nlayer : nullptr;
+    lk[k] = KEEP ? last_keep + (size_t)m * c.nwave + wc : nullptr;
   }
-  eclipse_columns<NMOL, NCIA, NANG, KEEP, kEclCols, SQ, true>(c, s_tab, s_etab, w, valid, tk, lk, flux);
+  // the specialised instantiations leave the Planck-exponent clamp out and evaluate the Planck
+  // exponential to degree 4 (launch_eclipse routes configurations that need more to the
+  // run-time-count kernel)
+  eclipse_columns<NMOL, NCIA, NANG, KEEP, kEclCols, SQ, true, kEclThreads, NMOL == 0, SC>(c, s_tab, s_etab, w0,
+                                                                                         valid, tk, lk, flux);
 #pragma unroll
   for (int k = 0; k < kEclCols; k++)
-    if (valid[k]) out[w[k]] = flux[k];
+    if (valid[k]) out[w0 + k * kEclThreads] = flux[k];
 }
 
 // ---------------------------------------------------------------------------------------
@@ -627,9 +635,9 @@ static size_t table_smem(const DevConfig &c) {
   return ((size_t)c.lay.stride() + kExpTabSize) * sizeof(double);
 }
 
-void upload_exp_table(cudaStream_t s) {
-  unsigned long long h[kExpTabSize];
-  fill_exp_table(h);
+void upload_exp_table(const DevConfig &c, cudaStream_t s) {
+  unsigned long long h[(1 + kMaxAng) * kExpTabSize] = {};
+  fill_ecl_exp_table(c, h);
   cudaMemcpyToSymbolAsync(g_exp_table, h, sizeof(h), 0, cudaMemcpyHostToDevice, s);
   cudaStreamSynchronize(s);
 }
@@ -651,61 +659,73 @@ void launch_atm_prep(const DevConfig &c, const Knobs &k, const double *profiles,
   atm_prep_kernel<<<nmodels, 128, smem, s>>>(c, k, profiles, n_in, tabs, status, pre_status, nmodels);
 }
 
-template <int NMOL, int NCIA, int NANG, bool KEEP, int SQ = -1>
+template <int NMOL, int NCIA, int NANG, bool KEEP, int SQ = -1, bool SC = true>
 static void launch_eclipse_t(const DevConfig &c, const double *tabs, const int *status,
                              double *spectra, double *tau_keep, int *last_keep, int nmodels,
                              int use_tma, cudaStream_t s) {
-  const size_t smem = table_smem(c);
+  const size_t smem = ((size_t)c.lay.stride() + ecl_tab_entries(c.nang)) * sizeof(double);
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
-    cudaFuncSetAttribute(eclipse_column_kernel<NMOL, NCIA, NANG, KEEP, SQ>,
+    cudaFuncSetAttribute(eclipse_column_kernel<NMOL, NCIA, NANG, KEEP, SQ, SC>,
                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = smem;
   }
   const int per = kEclThreads * kEclCols;
   const int tiles = (c.nwave + per - 1) / per;
-  eclipse_column_kernel<NMOL, NCIA, NANG, KEEP, SQ>
+  eclipse_column_kernel<NMOL, NCIA, NANG, KEEP, SQ, SC>
       <<<(unsigned)((size_t)tiles * nmodels), kEclThreads, smem, s>>>(
           c, tabs, status, spectra, tau_keep, last_keep, nmodels, use_tma);
 }
 
 // Specialised instantiations for the shapes BART runs (1-4 line-list molecules, 0-2 CIA files, the
-// default 5-angle ray grid); anything else takes the run-time-count kernel.
-template <int NMOL, int NCIA>
+// default 5-angle ray grid, with or without scattering / cloud terms); anything else takes the
+// run-time-count kernel.
+template <int NMOL, int NCIA, bool SC>
 static void launch_eclipse_nang(const DevConfig &c, const double *tabs, const int *status,
                                 double *spectra, int nmodels, int use_tma, cudaStream_t s) {
   // the default ray grid (0 20 40 60 80 degrees): exp(-tau/cos 60) = exp(-tau/cos 0)^2
   if (c.nang == 5 && c.sq_src == 0 && c.sq_dst == 3)
-    launch_eclipse_t<NMOL, NCIA, 5, false, 0x03>(c, tabs, status, spectra, nullptr, nullptr, nmodels, use_tma, s);
-  else if (c.nang == 5) launch_eclipse_t<NMOL, NCIA, 5, false>(c, tabs, status, spectra, nullptr, nullptr, nmodels, use_tma, s);
-  else launch_eclipse_t<NMOL, NCIA, 0, false>(c, tabs, status, spectra, nullptr, nullptr, nmodels, use_tma, s);
+    launch_eclipse_t<NMOL, NCIA, 5, false, 0x03, SC>(c, tabs, status, spectra, nullptr, nullptr, nmodels, use_tma, s);
+  else if (c.nang == 5) launch_eclipse_t<NMOL, NCIA, 5, false, -1, SC>(c, tabs, status, spectra, nullptr, nullptr, nmodels, use_tma, s);
+  else launch_eclipse_t<NMOL, NCIA, 0, false, -1, SC>(c, tabs, status, spectra, nullptr, nullptr, nmodels, use_tma, s);
 }
 
-template <int NMOL>
+template <int NMOL, bool SC>
 static void launch_eclipse_ncia(const DevConfig &c, const double *tabs, const int *status,
                                 double *spectra, int nmodels, int use_tma, cudaStream_t s) {
   switch (c.ncia) {
-    case 0: launch_eclipse_nang<NMOL, 0>(c, tabs, status, spectra, nmodels, use_tma, s); break;
-    case 1: launch_eclipse_nang<NMOL, 1>(c, tabs, status, spectra, nmodels, use_tma, s); break;
-    case 2: launch_eclipse_nang<NMOL, 2>(c, tabs, status, spectra, nmodels, use_tma, s); break;
+    case 0: launch_eclipse_nang<NMOL, 0, SC>(c, tabs, status, spectra, nmodels, use_tma, s); break;
+    case 1: launch_eclipse_nang<NMOL, 1, SC>(c, tabs, status, spectra, nmodels, use_tma, s); break;
+    case 2: launch_eclipse_nang<NMOL, 2, SC>(c, tabs, status, spectra, nmodels, use_tma, s); break;
+    default: launch_eclipse_t<0, -1, 0, false>(c, tabs, status, spectra, nullptr, nullptr, nmodels, use_tma, s);
+  }
+}
+
+template <bool SC>
+static void launch_eclipse_nmol(const DevConfig &c, const double *tabs, const int *status,
+                                double *spectra, int nmodels, int use_tma, cudaStream_t s) {
+  switch (c.ngmol) {
+    case 1: launch_eclipse_ncia<1, SC>(c, tabs, status, spectra, nmodels, use_tma, s); break;
+    case 2: launch_eclipse_ncia<2, SC>(c, tabs, status, spectra, nmodels, use_tma, s); break;
+    case 3: launch_eclipse_ncia<3, SC>(c, tabs, status, spectra, nmodels, use_tma, s); break;
+    case 4: launch_eclipse_ncia<4, SC>(c, tabs, status, spectra, nmodels, use_tma, s); break;
     default: launch_eclipse_t<0, -1, 0, false>(c, tabs, status, spectra, nullptr, nullptr, nmodels, use_tma, s);
   }
 }
 
 void launch_eclipse(const DevConfig &c, const double *tabs, const int *status, double *spectra,
-                    double *tau_keep, int *last_keep, int nmodels, bool keep, int use_tma,
+                    double *tau_keep, int *last_keep, int nmodels, bool keep, bool sc, int use_tma,
                     cudaStream_t s) {
   if (keep) {   // introspection path: run-time counts, stores tau[] and last[]
     launch_eclipse_t<0, -1, 0, true>(c, tabs, status, spectra, tau_keep, last_keep, nmodels, use_tma, s);
     return;
   }
-  switch (c.ngmol) {
-    case 1: launch_eclipse_ncia<1>(c, tabs, status, spectra, nmodels, use_tma, s); break;
-    case 2: launch_eclipse_ncia<2>(c, tabs, status, spectra, nmodels, use_tma, s); break;
-    case 3: launch_eclipse_ncia<3>(c, tabs, status, spectra, nmodels, use_tma, s); break;
-    case 4: launch_eclipse_ncia<4>(c, tabs, status, spectra, nmodels, use_tma, s); break;
-    default: launch_eclipse_t<0, -1, 0, false>(c, tabs, status, spectra, nullptr, nullptr, nmodels, use_tma, s);
+  if (c.planck_generic) {   // extreme Planck exponents: the kernel with the per-column clamp, degree 5
+    launch_eclipse_t<0, -1, 0, false>(c, tabs, status, spectra, nullptr, nullptr, nmodels, use_tma, s);
+    return;
   }
+  if (sc) launch_eclipse_nmol<true>(c, tabs, status, spectra, nmodels, use_tma, s);
+  else launch_eclipse_nmol<false>(c, tabs, status, spectra, nmodels, use_tma, s);
 }
 
 void launch_merge_status(int *status, const int *status_col, int nmodels, cudaStream_t s) {

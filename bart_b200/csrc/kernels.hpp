@@ -9,12 +9,17 @@ namespace bart {
 constexpr int kColThreads = 128;      // wavenumbers per CTA, lookup kernel
 constexpr int kEclThreads = 64;       // eclipse kernel: 64 threads x kEclCols columns = 128 wavenumbers per CTA
 constexpr int kEclCols = 2;
+// the eclipse kernel addresses a thread's columns from one base pointer and does not clamp the
+// columns past the end of the spectrum: the grid, the CIA tables and the line-by-line extinction
+// buffer carry this many samples of padding behind their last plane
+constexpr int kEclPad = kEclThreads * kEclCols;
 
 void launch_atm_prep(const DevConfig &c, const Knobs &k, const double *profiles, int n_in,
                      double *tabs, int *status, const int *pre_status, int nmodels,
                      cudaStream_t s);
+// sc: some record of the launch may carry a scattering or cloud term (false: skipped altogether)
 void launch_eclipse(const DevConfig &c, const double *tabs, const int *status, double *spectra,
-                    double *tau_keep, int *last_keep, int nmodels, bool keep, int use_tma,
+                    double *tau_keep, int *last_keep, int nmodels, bool keep, bool sc, int use_tma,
                     cudaStream_t s);
 // chord weights of one model in the tiled layout (doubles per model), K2t, and the tile kernel
 size_t transit_weights_stride(int nlayer);
@@ -54,7 +59,7 @@ void launch_band_integrate(const double *spectra, const double *wn, const int *f
                            int nfilters, int nwave, int nmodels, cudaStream_t s,
                            const PeerOut *peers = nullptr);
 void launch_fill(double *p, size_t n, double v, cudaStream_t s);
-void upload_exp_table(cudaStream_t s);
+void upload_exp_table(const DevConfig &c, cudaStream_t s);   // after fill_angle_consts
 // [cell][mol][wave] (file order) -> [cell][wave][gms] (device order), ncells (layer, T) cells
 void launch_grid_relayout(const double *in, double *out, int ncells, int nmol, int gms, int nwave,
                           cudaStream_t s);

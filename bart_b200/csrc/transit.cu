@@ -290,8 +290,7 @@ static void setup_cia() {
            c.file.c_str(), G.wn[0], G.wn[nw - 1]);
     std::vector<double> P, Q;
     fold_cia_table(c, G.wn, P, Q);
-    std::vector<double> PQ(2 * P.size());                  // [T_k][wave][value, d2/dT2]
-    for (size_t i = 0; i < P.size(); i++) { PQ[2 * i] = P[i]; PQ[2 * i + 1] = Q[i]; }
+    std::vector<double> PQ = pack_cia_quads(P, Q, nt, nw, kEclPad);   // [T_k][wave][4] + padding
     upload(G.d_ciaPQ[f], PQ); upload(G.d_ciaT[f], c.temp);
     G.dc.ciaPQ[f] = G.d_ciaPQ[f].p; G.dc.ciaT[f] = G.d_ciaT[f].p;
     G.dc.cia_nt[f] = nt;
@@ -318,7 +317,8 @@ static void load_grid_to_device(const std::string &path) {
   G.dc.gms = gms;
   const size_t ncell = (size_t)g.nlayer * g.ntemp;
   const size_t cell_in = (size_t)g.nmol * g.nwave, cell_out = (size_t)gms * g.nwave;
-  G.d_grid.ensure(ncell * cell_out);
+  G.d_grid.ensure(ncell * cell_out + (size_t)kEclPad * gms);   // + padding (kernels.hpp kEclPad)
+  CUDA_OK(cudaMemsetAsync(G.d_grid.p + ncell * cell_out, 0, (size_t)kEclPad * gms * sizeof(double), G.stream));
   FILE *f = fopen(path.c_str(), "rb");
   if (!f) fail("Opening opacity file '%s' failed.", path.c_str());
   fseek(f, g.data_offset, SEEK_SET);
@@ -479,7 +479,7 @@ static void do_init(int argc, char **argv) {
       c.planck_step = cH * cLS / cKB * kEclThreads * dwn;
     }
   }
-  upload_exp_table(G.stream);
+  upload_exp_table(c, G.stream);
   const double srad = o.starrad * kSUNRADIUS;                      // geometry.c:36,50
   c.inv_srad2 = 1.0 / (srad * srad);
 
@@ -529,6 +529,18 @@ static void do_init(int argc, char **argv) {
   finish_grid_config();
   }
 
+  // Models with a layer outside the grid's temperature range (line by line: the TLI range) are
+  // rejected before the column kernels run, so the Planck exponents x = hc wn/(k T) they can meet
+  // lie in [hc wn_min/(k Tmax), hc wn_max/(k Tmin)].  The specialised eclipse kernels evaluate
+  // e^x - 1 to degree 4 without a clamp: fine for 0.1 <= x <= 690 (relative error of e^x - 1 below
+  // 2.6e-12 e^x/(e^x - 1) <= 2.8e-11); anything wider takes the generic kernel.
+  {
+    const double tmin = G.lbl ? G.tli.tmin : G.og.temp[0];
+    const double tmax = G.lbl ? G.tli.tmax : G.og.temp[G.og.ntemp - 1];
+    const double c2 = cH * cLS / cKB;
+    c.planck_generic = !(tmin > 0) || c2 * G.wn[nw - 1] / tmin > 690.0 || c2 * G.wn[0] / tmax < 0.1;
+  }
+
   // readcs(): crosssec.c:9-268
   G.cia.resize(o.csfiles.size());
   for (size_t i = 0; i < o.csfiles.size(); i++) read_cia(o.csfiles[i], G.cia[i]);
@@ -568,7 +580,7 @@ static void prepare_batch(int total, int n_in) {
   if (!c.eclipse) G.d_wts.ensure((size_t)total * transit_weights_stride(c.nlayer));
   if (G.lbl) {
     // one extra row: the column kernels also load the (zero-weighted) second bracket plane
-    G.d_lbl_ext.ensure(((size_t)total * c.nlayer + 1) * c.nwave);
+    G.d_lbl_ext.ensure(((size_t)total * c.nlayer + 1) * c.nwave + kEclPad);
     G.d_lbl_dens.ensure((size_t)std::max(1, total) * c.nlayer * c.nspec);
     c.grid = G.d_lbl_ext.p;
     c.lbl_dens = G.d_lbl_dens.p;
@@ -632,7 +644,10 @@ static void launch_models(const double *d_prof, int off, int count, int total, i
   if (G.lbl) lbl_extinction(d_prof, off, count, n_in);
   if (c.eclipse) {
     KernelScope ks("eclipse_column");
-    launch_eclipse(c, tabs, status, d_spec, tau, last, count, G.keep, G.use_tma, G.stream);
+    // scattering / cloud terms of the table records (prep_table_row): all zero unless a flag is set
+    const bool sc = k.scat_flag || k.cloudtop || k.scat_flag_all != 0 ||
+                    (k.cloud_flag_all == 1 && k.cloudext_all != 0.0);
+    launch_eclipse(c, tabs, status, d_spec, tau, last, count, G.keep, sc, G.use_tma, G.stream);
     check_launch("eclipse_column");
   } else {
     int *scol = G.d_status_col.p + off;

@@ -92,8 +92,7 @@ int emu_init(const char *cfg) {
       read_cia(o.csfiles[i], E->cia[i]);
       std::vector<double> P, Q;
       fold_cia_table(E->cia[i], E->wn, P, Q);
-      E->PQ[i].resize(2 * P.size());
-      for (size_t k = 0; k < P.size(); k++) { E->PQ[i][2 * k] = P[k]; E->PQ[i][2 * k + 1] = Q[k]; }
+      E->PQ[i] = pack_cia_quads(P, Q, (int)E->cia[i].temp.size(), (int)E->wn.size(), 0);
       c.ciaPQ[i] = E->PQ[i].data(); c.ciaT[i] = E->cia[i].temp.data();
       c.cia_nt[i] = (int)E->cia[i].temp.size();
       c.cia_nspec[i] = (int)E->cia[i].species.size();
@@ -114,6 +113,7 @@ int emu_init(const char *cfg) {
       c.wgt[a] = pow(sin(area[a + 1]), 2.0) - pow(sin(area[a]), 2.0);
     }
     fill_angle_consts(c);
+    c.planck_generic = 1;
     double srad = o.starrad * kSUNRADIUS;
     c.inv_srad2 = 1.0 / (srad * srad);
     c.lay.nl = c.nlayer; c.lay.ngmol = c.ngmol; c.lay.ncia = c.ncia;
@@ -158,8 +158,8 @@ int emu_run(const double *in, double *spectrum, double *tau, int *last, double *
   if (radius) for (int l = 0; l < nl; l++) radius[l] = rad[l];
   if (status) { for (int w = 0; w < nw; w++) spectrum[w] = -1; return status; }
   std::vector<double> tk(nl), wts((size_t)nl * (nl + 1) / 2), er(nl);
-  alignas(16) unsigned long long etab[kExpTabSize];
-  fill_exp_table(etab);
+  alignas(16) unsigned long long etab[(1 + kMaxAng) * kExpTabSize];
+  fill_ecl_exp_table(c, etab);
   if (!c.eclipse) for (int d = 0; d < nl; d++) transit_weight_row(c, tab.data(), d, &wts[(size_t)d * (d + 1) / 2]);
   for (int w = 0; w < nw; w++) {
     int lk = 0;

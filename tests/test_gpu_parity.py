@@ -11,7 +11,8 @@ import cases
 from util import relerr, tau_relerr, apply_setters
 
 pytestmark = pytest.mark.gpu
-TOL = 1e-6            # north-star tolerance; observed differences are ~1e-11
+TOL = 1e-6            # north-star tolerance (against the reference's golden vectors)
+TIGHT = 1e-8          # what the CUDA path is held to against the oracle; observed ~1e-11
 
 
 @pytest.fixture(scope="module")
@@ -47,15 +48,17 @@ def test_spectra_vs_oracle_and_golden(name, api, get_case):
         tau = tr.debug_get("tau", m).reshape(tr.nwave, tr.nlayer)
         assert tau_relerr(tau, o["tau"], o["last"]) < 1e-8
         assert tau_relerr(tau[wsel], g["tau_sample"][m], g["last"][m][wsel]) < 1e-8
-        assert relerr(spectra[m], o["spectrum"]) < TOL
+        assert relerr(spectra[m], o["spectrum"]) < TIGHT
         assert relerr(spectra[m], g["spectra"][m]) < TOL
     tr.debug_keep(False)
     spectra2, _ = tr.run_batch(models)
     # the production kernel is specialised (compile-time counts, exp(-tau/cos 60) by squaring); the
-    # introspection kernel above is the run-time-count instantiation of the same code
-    assert relerr(spectra2, spectra) < 1e-13, "keep/no-keep kernels disagree"
+    # introspection kernel above is the run-time-count instantiation of the same code.  The angle
+    # exponentials are degree-4 (2.6e-12 each), so squaring one instead of evaluating it differs
+    # at that level
+    assert relerr(spectra2, spectra) < 1e-10, "keep/no-keep kernels disagree"
     for m in range(models.shape[0]):
-        assert relerr(spectra2[m], o["spectrum"]) < TOL if m == models.shape[0] - 1 else True
+        assert relerr(spectra2[m], o["spectrum"]) < TIGHT if m == models.shape[0] - 1 else True
         assert relerr(spectra2[m], g["spectra"][m]) < TOL
         # the reference's own single-model entry point gives the same numbers as the batch
         one = tr.run_transit(models[m])
@@ -199,7 +202,7 @@ def test_batch_properties_w12_shape(api, workdir):
     assert (status == 0).all() and np.isfinite(spectra).all() and (spectra > 0).all()
     O = orc.Oracle(case["cfg"])
     for m in (0, 17, 47):
-        assert relerr(spectra[m], O.run(models[m])) < TOL
+        assert relerr(spectra[m], O.run(models[m])) < TIGHT
     perm = np.random.default_rng(3).permutation(models.shape[0])
     sp2, _ = tr.run_batch(models[perm])
     assert np.array_equal(sp2, spectra[perm])
@@ -290,8 +293,8 @@ def test_randomised_configurations(k, api, workdir):
     for m in range(models.shape[0]):
         o = O.run(models[m], inter=True)
         assert np.array_equal(tr.debug_get("last", m).astype(np.int64), o["last"])
-        assert relerr(spectra[m], o["spectrum"]) < TOL
+        assert relerr(spectra[m], o["spectrum"]) < TIGHT
     tr.debug_keep(False)
     fast, _ = tr.run_batch(models)
-    assert relerr(fast, spectra) < 1e-12
+    assert relerr(fast, spectra) < 1e-10          # degree-4 angle exponentials, squared vs evaluated
     tr.free_memory()
