@@ -187,6 +187,32 @@ def test_band_integration(api, get_case):
     tr.free_memory()
 
 
+def test_band_integration_vs_wine_golden(api, get_case):
+    """K4 through the C ABI on the arrays the reference's own code/wine.py produced
+    (tests/golden/wine.npz: shipped demo filters + Kurucz star on the demo wavenumber grid):
+    band fluxes <= 1e-12 of wine.bandintegrate's."""
+    import os
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "wine.npz"))
+    case, models, _ = get_case("demo_eclipse")
+    tr = api.Transit(case["cfg"])
+    wn = tr.get_waveno_arr()
+    assert np.array_equal(wn, G["demo_specwn"])
+    n = 10
+    start = np.array([G["demo_%d_idx" % i][0] for i in range(n)], dtype=np.int32)
+    count = np.array([len(G["demo_%d_idx" % i]) for i in range(n)], dtype=np.int32)
+    weight = np.concatenate([G["demo_%d_nifilter" % i] for i in range(n)])
+    star = np.concatenate([G["demo_%d_istarfl" % i] for i in range(n)])
+    tr.set_filters(start, count, weight, star, 0.117)
+    bf = tr.band_integrate(G["demo_spectrum"])[0]
+    ref = np.array([float(G["demo_%d_band_eclipse" % i]) for i in range(n)])
+    assert relerr(bf, ref) < 1e-12
+    tr.set_filters(start, count, weight, None, 1.0)
+    bf = tr.band_integrate(G["demo_spectrum"])[0]
+    ref = np.array([float(G["demo_%d_band_transit" % i]) for i in range(n)])
+    assert relerr(bf, ref) < 1e-12
+    tr.free_memory()
+
+
 def test_batch_properties_w12_shape(api, workdir):
     """Full WASP-12b shape (2424 wn x 100 layers x 27 T x 4 molecules): (i) a sample of models
     against the oracle; (ii) permutation equivariance and batch-size independence, bit-exact;
