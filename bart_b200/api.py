@@ -50,6 +50,7 @@ def lib():
     L.bart_run_batch_device.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
     L.bart_set_filters.argtypes = [C.c_int, ip, ip, dp, dp, C.c_double]
     L.bart_band_integrate.argtypes = [dp, C.c_int, C.c_int, dp]
+    L.bart_nfilters.restype = C.c_int
     L.bart_bandflux_batch.argtypes = [dp, C.c_int, C.c_int, dp, ip]
     L.bart_bandflux_batch_device.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     L.bart_extinction_batch.argtypes = [dp, C.c_int, C.c_int, dp, C.c_int]
@@ -358,15 +359,18 @@ class Transit:
             niter, _d(support), i1.ctypes.data_as(ip), i2.ctypes.data_as(ip), iz.ctypes.data_as(ip),
             ic.ctypes.data_as(ip), _d(usnooker), usn_offset.ctypes.data_as(ip), _d(unif), _d(ugamma)))
         self._mc_niter = niter
-        self._mc_zsize += len(range(0, niter, self._mc_thinning))
+        self._mc_zsize += len(range(0, niter, self._mc_thinning)) + 1     # upper bound, see mcmc_get
 
     def mcmc_get(self, name):
         nchains, npars, nfree, ndata = self._mc_shape
         if name in ("Z", "Zchisq"):
+            # _mc_zsize is an upper bound (it counts thinned rows per call; the library grows Z on
+            # the GLOBAL iteration number, like MC3): size the result from what the library returns
             out = np.zeros((self._mc_zsize, nchains, npars) if name == "Z" else (self._mc_zsize, nchains))
             n = lib().bart_mcmc_get(name.encode(), _d(out), out.size)
             _check(0 if n >= 0 else -1)
-            return out
+            rows = n // (nchains * npars if name == "Z" else nchains)
+            return out[:rows]
         shapes = {"allparams": (nchains, nfree, getattr(self, "_mc_niter", 0)),
                   "allmodel": (nchains, ndata, getattr(self, "_mc_niter", 0)),
                   "params": (nchains, npars), "currchisq": (nchains,), "numaccept": (nchains,),

@@ -1107,8 +1107,12 @@ void builder_run_and_write(BuilderState *&b, const Options &o, const Atmosphere 
   // in place (one process per GPU shards the axis; rank 0 writes the header first)
   int t0 = 0, t1 = b->ntemp;
   bool header = true;
-  if (const char *e = getenv("BART_TSLICE")) {
+  // Honoured only under --justOpacity: a leftover variable in the environment of a normal run whose
+  // opacity file is missing must not leave a file with one temperature slice filled in.
+  if (const char *e = o.justOpacity ? getenv("BART_TSLICE") : nullptr) {
     if (sscanf(e, "%d:%d", &t0, &t1) != 2) fail("BART_TSLICE must be 'begin:end'");
+    if (t0 < 0 || t1 < t0 || t1 > b->ntemp)
+      fail("BART_TSLICE %d:%d is outside the temperature axis [0, %d]", t0, t1, b->ntemp);
     header = t0 == 0;
   }
   const size_t plane = (size_t)b->ngmol * b->nwave;
@@ -1118,6 +1122,10 @@ void builder_run_and_write(BuilderState *&b, const Options &o, const Atmosphere 
   int fd = open(path.c_str(), O_WRONLY | O_CREAT | (t0 == 0 && t1 == b->ntemp ? O_TRUNC : 0), 0644);
   if (fd < 0) fail("Opacity filename '%s' cannot be opened for writing.", path.c_str());
   const long long hdr = 4 * sizeof(long) + g.nmol * sizeof(int) + (g.ntemp + g.nlayer + g.nwave) * 8;
+  // every slice writer sets the file to its final size: a stale, larger file of other dimensions
+  // does not survive, and the slices can be written in any order
+  if (ftruncate(fd, hdr + (long long)g.nlayer * g.ntemp * (long long)plane * 8) != 0)
+    fail("Opacity filename '%s' cannot be sized.", path.c_str());
   if (header) {
     std::vector<char> h(hdr);
     char *p = h.data();

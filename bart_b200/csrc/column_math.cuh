@@ -93,6 +93,12 @@ BART_HD D4 ld4b(const char *p) {
 #define BART_WARP_ALL(p) (p)
 #define BART_WARP_ANY(p) (p)
 #endif
+// bitwise AND of a small flag word over the warp (one REDUX instead of one vote per flag)
+#ifdef __CUDA_ARCH__
+#define BART_WARP_AND_BITS(x) __reduce_and_sync(0xffffffffu, (unsigned)(x))
+#else
+#define BART_WARP_AND_BITS(x) ((unsigned)(x))
+#endif
 
 // exp(x) = 2^n 2^(j/N) e^(r ln2/N) with y = x N/ln2 = (N n + j) + r, |r| <= 1/2, N = 16:
 // |r ln2/N| <= 0.0217, so a degree-6 polynomial is exact to 4.5e-16.  The caller supplies y as a
@@ -369,17 +375,24 @@ BART_HD double hydro_coef(const DevConfig &c, const double *temp, const double *
          (cKB / cAMU * log(c.press[i] / c.press[i + 1])) / c.rfct;
 }
 
+// the layer nearest to the reference pressure p0 (first minimum of |p - p0|, radpress
+// readatm.c:809-813): a property of the configuration, found once on the host
+inline int ref_layer_of(const double *press, int nl, double p0) {
+  int i0 = 0;
+  double best = 1e37;
+  for (int i = 0; i < nl; i++) {
+    const double d = fabs(press[i] - p0);
+    if (d < best) { i0 = i; best = d; }
+  }
+  return i0;
+}
+
 BART_HD void hydrostatic_radii(const DevConfig &c, double r0, const double *temp, const double *mu,
                                const double *hc, double *radius) {
   const int nl = c.nlayer;
   const double *pr = c.press;
   const double p0 = c.p0, g0 = c.gsurf, rfct = c.rfct;
-  int i0 = 0;
-  double best = 1e37;
-  for (int i = 0; i < nl; i++) {
-    const double d = fabs(pr[i] - p0);
-    if (d < best) { i0 = i; best = d; }
-  }
+  const int i0 = c.ref_layer;                 // nearest layer to the reference pressure (ref_layer_of)
   if (pr[i0] > p0) {
     const int i1 = i0 + 1 < nl ? i0 + 1 : i0;
     const double lr = log(pr[i1] / pr[i0]), lp = log(p0 / pr[i0]);
@@ -705,6 +718,10 @@ BART_HD double cell_extinction(const DevConfig &c, const ColPtrs &P, const doubl
 // etab: ecl_tab_entries(nang) entries (fill_ecl_exp_table).
 // SQ >= 0 encodes (src << 4 | dst): the exponential of angle dst is the square of that of src
 // (1/mu_dst = 2/mu_src, e.g. 60 and 0 degrees of the default ray grid); CHAIN: Planck chaining;
+// With NCOL 1 and CHAIN, `upper` marks a column that the NCOL 2 form would carry as a thread's
+// second one: its Planck exponential is then chained from the column CSTRIDE below in the same
+// way, and -- the series-or-exponentials decision being taken per slot, i.e. per group of 32
+// consecutive columns -- the result equals the NCOL 2 form's to the bit (small-batch kernel).
 // PGEN: Planck exponent clamped per column and evaluated to degree 5 (DevConfig::planck_generic);
 // SC false: no scattering and no cloud in any record of the launch (the terms are skipped).
 template <int NMOL, int NCIA, int NANG, bool KEEP, int NCOL, int SQ = -1, bool CHAIN = false,
@@ -712,7 +729,7 @@ template <int NMOL, int NCIA, int NANG, bool KEEP, int NCOL, int SQ = -1, bool C
 BART_HD void eclipse_columns(const DevConfig &c, const double *tab, const unsigned long long *etab,
                              int w0, const bool (&valid)[NCOL],
                              double *const (&tau_keep)[NCOL], int *const (&last_keep)[NCOL],
-                             double (&flux)[NCOL]) {
+                             double (&flux)[NCOL], bool upper = false) {
   typedef TabLayout L;
   const int nl = c.nlayer;
   const int nf = c.lay.nf();
@@ -741,9 +758,9 @@ BART_HD void eclipse_columns(const DevConfig &c, const double *tab, const unsign
       } else {
         double it = tp.x;
         if (PGEN && it * c2n[k] > kExpYmax) it = kExpYmax / c2n[k];           // exponent <= 700
-        if (CHAIN && NCOL > 1) {
+        if (CHAIN) {
           E = PGEN ? exp_core5(c2n[k], it, etab, 0.0) : exp_w(c2n[k], it, etab, 0.0);
-          em1 = E - 1.0;
+          em1 = NCOL == 1 && upper ? fma(E, tp.y, -1.0) : E - 1.0;
         } else em1 = PGEN ? exp_core5(c2n[k], it, etab, -1.0) : exp_w(c2n[k], it, etab, -1.0);
       }
       B[k] = fast_rcp1(em1);
@@ -757,6 +774,7 @@ BART_HD void eclipse_columns(const DevConfig &c, const double *tab, const unsign
     const double wn = c.wn[wk < c.nwave ? wk : c.nwave - 1];
     wn4[k] = (wn * wn) * (wn * wn);
     c2n[k] = cH * wn * cLS / cKB * kExpScale;                  // Planck exponent x N/ln2, per 1/T
+    if (CHAIN && NCOL == 1 && upper) c2n[k] = cH * c.wn[wk - CSTRIDE] * cLS / cKB * kExpScale;
     er1[k] = cell_extinction<NMOL, NCIA, SC>(c, P, tab, wn4[k], false, k * gstep, k * cstep);
     er2[k] = 0.0; S[k] = 0.0; trap[k] = 0.0; Dprev[k] = c.taylor[0];
     alive[k] = valid[k] && !(0.0 > c.toomuch);
@@ -790,7 +808,7 @@ BART_HD void eclipse_columns(const DevConfig &c, const double *tab, const unsign
 
   auto step = [&](const double *row, int d, bool odd) {
     double tau[NCOL], B[NCOL], D[NCOL];
-    bool small = true;
+    bool small[NCOL];
     double erk[NCOL];
 #pragma unroll
     for (int k = 0; k < NCOL; k++) {
@@ -812,25 +830,27 @@ BART_HD void eclipse_columns(const DevConfig &c, const double *tab, const unsign
         tau[k] = S[k];
       }
       er2[k] = er1[k]; er1[k] = er;
-      small = small && (!alive[k] || hi_word(tau[k]) < small_hi);
+      small[k] = !alive[k] || hi_word(tau[k]) < small_hi;
     }
     planck(row, B);
-    if (BART_WARP_ALL(small)) {
+    // D(tau): Maclaurin series while every live column of a slot (32 consecutive columns: the
+    // warp's k-th) is below tau_small, weighted exponentials otherwise
+    auto series = [&](int k0, int k1) {
 #pragma unroll
-      for (int k = 0; k < NCOL; k++) {
-        double p = c.taylor[kTaylorN - 1];
+      for (int k = 0; k < NCOL; k++)
+        if (k >= k0 && k < k1) {
+          double p = c.taylor[kTaylorN - 1];
 #pragma unroll
-        for (int i = kTaylorN - 2; i >= 0; i--) p = fma(p, tau[k], c.taylor[i]);
-        D[k] = p;
-      }
-    } else {
+          for (int i = kTaylorN - 2; i >= 0; i--) p = fma(p, tau[k], c.taylor[i]);
+          D[k] = p;
+        }
+    };
+    auto exponentials = [&](int k0, int k1) {
       // exp arguments stay above -690: only the last depth of a column can exceed the clamp
       bool big = false;
-#pragma unroll
-      for (int k = 0; k < NCOL; k++) big = big || hi_word(tau[k]) >= clamp_hi;
       double tc[NCOL];
 #pragma unroll
-      for (int k = 0; k < NCOL; k++) tc[k] = tau[k];
+      for (int k = 0; k < NCOL; k++) { big = big || hi_word(tau[k]) >= clamp_hi; tc[k] = tau[k]; }
       if (BART_WARP_ANY(big)) {
 #pragma unroll
         for (int k = 0; k < NCOL; k++) tc[k] = hi_word(tau[k]) >= clamp_hi ? c.tau_clamp : tau[k];
@@ -839,21 +859,32 @@ BART_HD void eclipse_columns(const DevConfig &c, const double *tab, const unsign
         // the source angle of the squaring first (its value is needed, not only its share of the
         // sum), then the others ride on the running sum
 #pragma unroll
-        for (int k = 0; k < NCOL; k++) {
-          const double e = exp_w(tc[k], -c.exp_a[SQ >> 4], etab + (1 + (SQ >> 4)) * kExpTabSize, 0.0);
-          D[k] = fma(e * e, c.sq_coef, e);
-        }
+        for (int k = 0; k < NCOL; k++)
+          if (k >= k0 && k < k1) {
+            const double e = exp_w(tc[k], -c.exp_a[SQ >> 4], etab + (1 + (SQ >> 4)) * kExpTabSize, 0.0);
+            D[k] = fma(e * e, c.sq_coef, e);
+          }
       } else {
 #pragma unroll
-        for (int k = 0; k < NCOL; k++) D[k] = 0.0;
+        for (int k = 0; k < NCOL; k++) if (k >= k0 && k < k1) D[k] = 0.0;
       }
 #pragma unroll
       for (int a = 0; a < (NANG > 0 ? NANG : kMaxAng); a++)
         if (a < nang && !(SQ >= 0 && (a == (SQ >> 4) || a == (SQ & 15)))) {
 #pragma unroll
           for (int k = 0; k < NCOL; k++)
-            D[k] = exp_w(tc[k], -c.exp_a[a], etab + (1 + a) * kExpTabSize, D[k]);
+            if (k >= k0 && k < k1) D[k] = exp_w(tc[k], -c.exp_a[a], etab + (1 + a) * kExpTabSize, D[k]);
         }
+    };
+    unsigned bits = 0;
+#pragma unroll
+    for (int k = 0; k < NCOL; k++) bits |= small[k] ? 1u << k : 0u;
+    const unsigned sm = BART_WARP_AND_BITS(bits);              // bit k: slot k takes the series
+    if (sm == (1u << NCOL) - 1u) series(0, NCOL);
+    else if (sm == 0u) exponentials(0, NCOL);
+    else {                                                     // slots disagree (a few depths per column)
+#pragma unroll
+      for (int k = 0; k < NCOL; k++) { if (sm >> k & 1u) series(k, k + 1); else exponentials(k, k + 1); }
     }
 #pragma unroll
     for (int k = 0; k < NCOL; k++)

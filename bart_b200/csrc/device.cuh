@@ -67,6 +67,7 @@ struct DevConfig {
   int cia_nspec[kMaxCia];
   int cia_spec[kMaxCia][2];
   double pfct, rfct, gsurf, p0, toomuch;
+  int ref_layer;            // layer nearest to the reference pressure p0 (column_math.cuh ref_layer_of)
   double inv_mu[kMaxAng];   // 1/cos(angle)
   double wgt[kMaxAng];      // sin^2(g_{a+1}) - sin^2(g_a)
   double inv_srad2;         // 1/R*^2 (cm^-2)

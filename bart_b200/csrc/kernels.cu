@@ -18,6 +18,7 @@
 #include "kernels.hpp"
 #include <cuda_runtime.h>
 #include <cstring>
+#include <cstdlib>
 #include <algorithm>
 
 namespace bart {
@@ -191,6 +192,43 @@ eclipse_column_kernel(DevConfig c, const double *__restrict__ tabs, const int *_
 #pragma unroll
   for (int k = 0; k < kEclCols; k++)
     if (valid[k]) out[w0 + k * kEclThreads] = flux[k];
+}
+
+// Small batches (BART's own populations are ~10 chains): CTA = one warp = one slot of 32
+// consecutive columns of one model, one column per thread -- four times the CTAs of the kernel
+// above, each with a quarter of its work, so that a 10-model generation spreads over the whole
+// machine instead of occupying ~190 CTAs for 100 dependent depth steps.  Same column arithmetic
+// (eclipse_columns with NCOL 1; `upper` chains the Planck exponential exactly like the second
+// column of a thread above), so spectra are bit-identical whichever kernel a batch size selects.
+template <int NMOL, int NCIA, int NANG, int SQ, bool SC>
+__global__ void __launch_bounds__(32)
+eclipse_slot_kernel(DevConfig c, const double *__restrict__ tabs, const int *__restrict__ status,
+                    double *__restrict__ spectra, int nmodels, int use_tma) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t bar;
+  unsigned long long *s_etab = reinterpret_cast<unsigned long long *>(smem_raw);
+  const int n_etab = ecl_tab_entries(NANG > 0 ? NANG : c.nang);
+  double *s_tab = reinterpret_cast<double *>(s_etab + n_etab);
+  const int m = blockIdx.x % nmodels;
+  const int slot = blockIdx.x / nmodels;
+  const int w = slot * 32 + threadIdx.x;
+  const int nd = c.lay.stride();
+  double *out = spectra + (size_t)m * c.nwave;
+  if (status[m] != 0) {
+    if (w < c.nwave) out[w] = -1.0;
+    return;
+  }
+  stage_table(s_tab, tabs + (size_t)m * nd, nd, &bar, use_tma != 0, s_etab, n_etab);
+  // the slot's place in the 128-column tile of eclipse_column_kernel: second half = a thread's
+  // second column there
+  const bool upper = c.planck_cols > 0 && ((slot * 32) % (kEclThreads * kEclCols)) >= kEclThreads;
+  const bool valid[1] = {w < c.nwave};
+  double *tk[1] = {nullptr};
+  int *lk[1] = {nullptr};
+  double flux[1];
+  eclipse_columns<NMOL, NCIA, NANG, false, 1, SQ, true, kEclThreads, NMOL == 0, SC>(c, s_tab, s_etab, w, valid, tk,
+                                                                                    lk, flux, upper);
+  if (valid[0]) out[w] = flux[0];
 }
 
 // ---------------------------------------------------------------------------------------
@@ -598,7 +636,8 @@ __global__ void peer_signal_kernel(PeerOut po) { peer_announce(po); }
 __global__ void __launch_bounds__(256)
 peer_wait_copy_kernel(const double *__restrict__ win, unsigned long long *flags,
                       unsigned long long *gen, int world, long long cap, long long count,
-                      double *__restrict__ out, int *err, unsigned int *finished) {
+                      double *__restrict__ out, int *err, unsigned int *finished,
+                      unsigned long long timeout_ns) {
   __shared__ int s_bad;
   const unsigned long long g = *gen;            // advanced only after every CTA has passed this read
   if (threadIdx.x == 0) s_bad = 0;
@@ -606,7 +645,7 @@ peer_wait_copy_kernel(const double *__restrict__ win, unsigned long long *flags,
   if (threadIdx.x < world) {
     const unsigned long long t0 = global_ns();
     while (ld_acquire_sys(flags + threadIdx.x) < g + 1) {
-      if (global_ns() - t0 > 10000000000ull) { s_bad = 1; break; }      // 10 s: a peer died
+      if (global_ns() - t0 > timeout_ns) { s_bad = 1; break; }            // a peer died or lags badly
       __nanosleep(200);
     }
   }
@@ -665,8 +704,20 @@ void launch_atm_prep(const DevConfig &c, const Knobs &k, const double *profiles,
 template <int NMOL, int NCIA, int NANG, bool KEEP, int SQ = -1, bool SC = true>
 static void launch_eclipse_t(const DevConfig &c, const double *tabs, const int *status,
                              double *spectra, double *tau_keep, int *last_keep, int nmodels,
-                             int use_tma, cudaStream_t s) {
+                             int use_tma, bool slots, cudaStream_t s) {
   const size_t smem = ((size_t)c.lay.stride() + ecl_tab_entries(c.nang)) * sizeof(double);
+  if (slots && !KEEP) {
+    static size_t configured_s = 0;
+    if (smem > 48 * 1024 && smem > configured_s) {
+      cudaFuncSetAttribute(eclipse_slot_kernel<NMOL, NCIA, NANG, SQ, SC>,
+                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      configured_s = smem;
+    }
+    const int nslots = (c.nwave + 31) / 32;
+    eclipse_slot_kernel<NMOL, NCIA, NANG, SQ, SC><<<(unsigned)((size_t)nslots * nmodels), 32, smem, s>>>(
+        c, tabs, status, spectra, nmodels, use_tma);
+    return;
+  }
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
     cudaFuncSetAttribute(eclipse_column_kernel<NMOL, NCIA, NANG, KEEP, SQ, SC>,
@@ -685,50 +736,59 @@ static void launch_eclipse_t(const DevConfig &c, const double *tabs, const int *
 // run-time-count kernel.
 template <int NMOL, int NCIA, bool SC>
 static void launch_eclipse_nang(const DevConfig &c, const double *tabs, const int *status,
-                                double *spectra, int nmodels, int use_tma, cudaStream_t s) {
+                                double *spectra, int nmodels, int use_tma, bool slots, cudaStream_t s) {
   // the default ray grid (0 20 40 60 80 degrees): exp(-tau/cos 60) = exp(-tau/cos 0)^2
   if (c.nang == 5 && c.sq_src == 0 && c.sq_dst == 3)
-    launch_eclipse_t<NMOL, NCIA, 5, false, 0x03, SC>(c, tabs, status, spectra, nullptr, nullptr, nmodels, use_tma, s);
-  else if (c.nang == 5) launch_eclipse_t<NMOL, NCIA, 5, false, -1, SC>(c, tabs, status, spectra, nullptr, nullptr, nmodels, use_tma, s);
-  else launch_eclipse_t<NMOL, NCIA, 0, false, -1, SC>(c, tabs, status, spectra, nullptr, nullptr, nmodels, use_tma, s);
+    launch_eclipse_t<NMOL, NCIA, 5, false, 0x03, SC>(c, tabs, status, spectra, nullptr, nullptr, nmodels, use_tma, slots, s);
+  else launch_eclipse_t<NMOL, NCIA, 0, false, -1, SC>(c, tabs, status, spectra, nullptr, nullptr, nmodels, use_tma, slots, s);
 }
 
 template <int NMOL, bool SC>
 static void launch_eclipse_ncia(const DevConfig &c, const double *tabs, const int *status,
-                                double *spectra, int nmodels, int use_tma, cudaStream_t s) {
+                                double *spectra, int nmodels, int use_tma, bool slots, cudaStream_t s) {
   switch (c.ncia) {
-    case 0: launch_eclipse_nang<NMOL, 0, SC>(c, tabs, status, spectra, nmodels, use_tma, s); break;
-    case 1: launch_eclipse_nang<NMOL, 1, SC>(c, tabs, status, spectra, nmodels, use_tma, s); break;
-    case 2: launch_eclipse_nang<NMOL, 2, SC>(c, tabs, status, spectra, nmodels, use_tma, s); break;
-    default: launch_eclipse_t<0, -1, 0, false>(c, tabs, status, spectra, nullptr, nullptr, nmodels, use_tma, s);
+    case 0: launch_eclipse_nang<NMOL, 0, SC>(c, tabs, status, spectra, nmodels, use_tma, slots, s); break;
+    case 1: launch_eclipse_nang<NMOL, 1, SC>(c, tabs, status, spectra, nmodels, use_tma, slots, s); break;
+    case 2: launch_eclipse_nang<NMOL, 2, SC>(c, tabs, status, spectra, nmodels, use_tma, slots, s); break;
+    default: launch_eclipse_t<0, -1, 0, false>(c, tabs, status, spectra, nullptr, nullptr, nmodels, use_tma, slots, s);
   }
 }
 
 template <bool SC>
 static void launch_eclipse_nmol(const DevConfig &c, const double *tabs, const int *status,
-                                double *spectra, int nmodels, int use_tma, cudaStream_t s) {
+                                double *spectra, int nmodels, int use_tma, bool slots, cudaStream_t s) {
   switch (c.ngmol) {
-    case 1: launch_eclipse_ncia<1, SC>(c, tabs, status, spectra, nmodels, use_tma, s); break;
-    case 2: launch_eclipse_ncia<2, SC>(c, tabs, status, spectra, nmodels, use_tma, s); break;
-    case 3: launch_eclipse_ncia<3, SC>(c, tabs, status, spectra, nmodels, use_tma, s); break;
-    case 4: launch_eclipse_ncia<4, SC>(c, tabs, status, spectra, nmodels, use_tma, s); break;
-    default: launch_eclipse_t<0, -1, 0, false>(c, tabs, status, spectra, nullptr, nullptr, nmodels, use_tma, s);
+    case 1: launch_eclipse_ncia<1, SC>(c, tabs, status, spectra, nmodels, use_tma, slots, s); break;
+    case 2: launch_eclipse_ncia<2, SC>(c, tabs, status, spectra, nmodels, use_tma, slots, s); break;
+    case 3: launch_eclipse_ncia<3, SC>(c, tabs, status, spectra, nmodels, use_tma, slots, s); break;
+    case 4: launch_eclipse_ncia<4, SC>(c, tabs, status, spectra, nmodels, use_tma, slots, s); break;
+    default: launch_eclipse_t<0, -1, 0, false>(c, tabs, status, spectra, nullptr, nullptr, nmodels, use_tma, slots, s);
   }
+}
+
+bool eclipse_prefers_slots(const DevConfig &c, int nmodels) {
+  // the throughput kernel needs ~8 CTAs per SM to hide its latencies; below ~4 the slot kernel's
+  // fourfold CTA count wins (measured at the W12 shape: DESIGN.md section 4)
+  const char *e = getenv("BART_ECL_SMALL");
+  if (e && *e) return atoi(e) != 0;
+  const long long tiles = (c.nwave + kEclThreads * kEclCols - 1) / (kEclThreads * kEclCols);
+  return tiles * nmodels <= 4LL * 148;
 }
 
 void launch_eclipse(const DevConfig &c, const double *tabs, const int *status, double *spectra,
                     double *tau_keep, int *last_keep, int nmodels, bool keep, bool sc, int use_tma,
                     cudaStream_t s) {
   if (keep) {   // introspection path: run-time counts, stores tau[] and last[]
-    launch_eclipse_t<0, -1, 0, true>(c, tabs, status, spectra, tau_keep, last_keep, nmodels, use_tma, s);
+    launch_eclipse_t<0, -1, 0, true>(c, tabs, status, spectra, tau_keep, last_keep, nmodels, use_tma, false, s);
     return;
   }
+  const bool slots = eclipse_prefers_slots(c, nmodels);
   if (c.planck_generic) {   // extreme Planck exponents: the kernel with the per-column clamp, degree 5
-    launch_eclipse_t<0, -1, 0, false>(c, tabs, status, spectra, nullptr, nullptr, nmodels, use_tma, s);
+    launch_eclipse_t<0, -1, 0, false>(c, tabs, status, spectra, nullptr, nullptr, nmodels, use_tma, slots, s);
     return;
   }
-  if (sc) launch_eclipse_nmol<true>(c, tabs, status, spectra, nmodels, use_tma, s);
-  else launch_eclipse_nmol<false>(c, tabs, status, spectra, nmodels, use_tma, s);
+  if (sc) launch_eclipse_nmol<true>(c, tabs, status, spectra, nmodels, use_tma, slots, s);
+  else launch_eclipse_nmol<false>(c, tabs, status, spectra, nmodels, use_tma, slots, s);
 }
 
 void launch_merge_status(int *status, const int *status_col, int nmodels, cudaStream_t s) {
@@ -822,10 +882,12 @@ void launch_peer_signal(const PeerOut &po, cudaStream_t s) { peer_signal_kernel<
 
 void launch_peer_wait_copy(const double *win_local, unsigned long long *flags_local,
                            unsigned long long *gen, int world, long long cap, long long count,
-                           double *out, int *err, unsigned int *finished, cudaStream_t s) {
+                           double *out, int *err, unsigned int *finished,
+                           unsigned long long timeout_ns, cudaStream_t s) {
   const long long total = (long long)world * count;
   const int grid = (int)std::max<long long>(1, std::min<long long>(64, total / 2048));
-  peer_wait_copy_kernel<<<grid, 256, 0, s>>>(win_local, flags_local, gen, world, cap, count, out, err, finished);
+  peer_wait_copy_kernel<<<grid, 256, 0, s>>>(win_local, flags_local, gen, world, cap, count, out, err, finished,
+                                             timeout_ns);
 }
 
 void launch_fill(double *p, size_t n, double v, cudaStream_t s) {

@@ -47,10 +47,12 @@ struct PeerOut {
   unsigned int *grpcnt;               // [groups] completed CTAs per group of kPeerGroup models
 };
 // waits until every rank's block of generation *gen has arrived in the local window, copies
-// world x count doubles to `out` ([rank][count]) and advances *gen; *err is set on a time-out
+// world x count doubles to `out` ([rank][count]) and advances *gen; *err is set after timeout_ns
+// without a peer's arrival flag (the copy still proceeds: the caller must check *err)
 void launch_peer_wait_copy(const double *win_local, unsigned long long *flags_local,
                            unsigned long long *gen, int world, long long cap, long long count,
-                           double *out, int *err, unsigned int *finished, cudaStream_t s);
+                           double *out, int *err, unsigned int *finished,
+                           unsigned long long timeout_ns, cudaStream_t s);
 // a rank with no model in this generation still has to announce itself
 void launch_peer_signal(const PeerOut &po, cudaStream_t s);
 void launch_band_integrate(const double *spectra, const double *wn, const int *fstart,

@@ -23,7 +23,13 @@ namespace bart {
 
 // ---------------------------------------------------------------------------------------
 // E_2(x): exponential integral of order 2 (scipy.special.expn(2, x) in code/PT.py:736; cephes
-// expn: power series for x <= 1, continued fraction above).
+// expn: power series for x <= 1, continued fraction above).  Same recurrences and stopping rules as
+// cephes, restated without a division inside the loops (a generation at MC3's 10-chain populations
+// is latency-bound, and the two divisions per continued-fraction step were most of it): the
+// convergence test |ans - r| <= eps |r| on consecutive convergents p'/q', p/q is evaluated as
+// |p' q - p q'| <= eps |p q'|, and the series divides by the integers k through a reciprocal table.
+// Agreement with scipy: <= 4e-16 relative (tests/test_gpu_retrieval.py, against PT.py's profiles).
+__constant__ double c_recip[48];            // 1/k, k = 1..47 (entry 0 unused)
 __device__ double expint2(double x) {
   const double EUL = 0.57721566490153286060, MACHEP = 1.11022302462515654042e-16;
   const double BIG = 1.44115188075855872e17, MAXLOG = 7.09782712893383996843e2;
@@ -32,7 +38,8 @@ __device__ double expint2(double x) {
   if (x == 0.0) return 1.0;
   if (x > 1.0) {
     int k = 1;
-    double pkm2 = 1.0, qkm2 = x, pkm1 = 1.0, qkm1 = x + n, ans = pkm1 / qkm1, t;
+    double pkm2 = 1.0, qkm2 = x, pkm1 = 1.0, qkm1 = x + n;
+    bool more;
     do {
       k++;
       double yk, xk;
@@ -40,25 +47,26 @@ __device__ double expint2(double x) {
       else { yk = x; xk = k / 2; }
       const double pk = __dadd_rn(__dmul_rn(pkm1, yk), __dmul_rn(pkm2, xk));
       const double qk = __dadd_rn(__dmul_rn(qkm1, yk), __dmul_rn(qkm2, xk));
-      if (qk != 0.0) { const double r = pk / qk; t = fabs((ans - r) / r); ans = r; }
-      else t = 1.0;
+      // consecutive convergents pkm1/qkm1 and pk/qk
+      const double pq = pk * qkm1;
+      more = qk == 0.0 || fabs(fma(pkm1, qk, -pq)) > MACHEP * fabs(pq);
       pkm2 = pkm1; pkm1 = pk; qkm2 = qkm1; qkm1 = qk;
-      if (fabs(pk) > BIG) { pkm2 /= BIG; pkm1 /= BIG; qkm2 /= BIG; qkm1 /= BIG; }
-    } while (t > MACHEP && k < 100000);
-    return ans * exp(-x);
+      if (fabs(pk) > BIG) { pkm2 *= 1.0 / BIG; pkm1 *= 1.0 / BIG; qkm2 *= 1.0 / BIG; qkm1 *= 1.0 / BIG; }
+    } while (more && k < 100000);
+    return pkm1 / qkm1 * exp(-x);
   }
   double psi = -EUL - log(x);
   psi += 1.0;                                   // sum_{i=1}^{n-1} 1/i
   const double z = -x;
-  double xk = 0.0, yk = 1.0, pk = 1.0 - n, ans = 1.0 / pk, t;
-  int it = 0;
+  double yk = 1.0, ans = -1.0;                  // 1 / (1 - n)
+  int k = 0;
+  bool more;
   do {
-    xk += 1.0;
-    yk *= z / xk;
-    pk += 1.0;
-    if (pk != 0.0) ans += yk / pk;
-    t = ans != 0.0 ? fabs(yk / ans) : 1.0;
-  } while (t > MACHEP && ++it < 100000);
+    k++;
+    yk *= k < 48 ? z * c_recip[k] : z / k;
+    if (k != n - 1) ans += k - (n - 1) < 48 ? yk * c_recip[k - (n - 1)] : yk / (k - (n - 1));
+    more = ans != 0.0 ? fabs(yk) > MACHEP * fabs(ans) : true;
+  } while (more && k < 100000);
   return __dmul_rn(z, psi) - ans;               // z^(n-1) psi / Gamma(n) - series
 }
 
@@ -69,23 +77,27 @@ __device__ double line_xi(double gamma, double tau) {
                       gamma * (1 - 0.5 * (tau * tau)) * expint2(gt));
 }
 
-__device__ double pt_temperature(const ConvConfig &cc, const double *par, double p_bar) {
+// PT_line (PT.py:664-697) splits over a pair of adjacent lanes: each evaluates one of the two
+// visible streams' xi (the expensive part), lane 0 of the pair combines them.  `half` = lane & 1.
+__device__ double pt_temperature(const ConvConfig &cc, const double *par, double p_bar, int half) {
   if (cc.pt_type == PT_ISO) return par[0];
   if (cc.pt_type == PT_ADIABATIC) {             // PT.py:741-750
     const double p0 = pow(10.0, par[2]);
     return par[0] / (1 + (par[1] - 1) / par[1] * log(p0 / p_bar));
   }
-  // PT_line (PT.py:664-697)
-  const double kappa = pow(10.0, par[0]), g1 = pow(10.0, par[1]), g2 = pow(10.0, par[2]);
+  const double kappa = pow(10.0, par[0]), g = pow(10.0, par[1 + half]);
   const double alpha = par[3], beta = par[4];
   const double tirr = beta * sqrt(cc.rstar / (2.0 * cc.sma)) * cc.tstar;
   const double tau = kappa * (p_bar * 1e6) / cc.grav;
-  const double xi1 = line_xi(g1, tau), xi2 = line_xi(g2, tau);
+  const double xi_mine = line_xi(g, tau);
+  const double xi_other = __shfl_xor_sync(0xffffffffu, xi_mine, 1);
+  const double xi1 = half ? xi_other : xi_mine, xi2 = half ? xi_mine : xi_other;
   const double ti4 = pow(cc.tint, 4.0), tr4 = pow(tirr, 4.0);
   return pow(0.75 * (ti4 * (2.0 / 3.0 + tau) + tr4 * (1 - alpha) * xi1 + tr4 * alpha * xi2), 0.25);
 }
 
-__global__ void __launch_bounds__(128)
+constexpr int kConvThreads = 256;               // two lanes per layer
+__global__ void __launch_bounds__(kConvThreads)
 convert_params_kernel(ConvConfig cc, const double *__restrict__ params, int npars,
                       double *__restrict__ profiles, int n_in, int *__restrict__ status,
                       ConvKnobs kn, int nmodels) {
@@ -93,15 +105,26 @@ convert_params_kernel(ConvConfig cc, const double *__restrict__ params, int npar
   if (m >= nmodels) return;
   __shared__ int s_bad;
   __shared__ double s_par[kMaxPars];
+  __shared__ double s_fac[kMaxPars];            // 10^p of the abundance parameters
   if (threadIdx.x == 0) s_bad = 0;
-  for (int i = threadIdx.x; i < npars; i += blockDim.x) s_par[i] = params[(size_t)m * npars + i];
-  __syncthreads();
   const int nl = cc.nlayer;
   const int off = cc.npt + cc.nrad + cc.ncloud + cc.nray;
+  for (int i = threadIdx.x; i < npars; i += blockDim.x) {
+    const double v = params[(size_t)m * npars + i];
+    s_par[i] = v;
+    if (i >= off && i - off < cc.nmolfit) s_fac[i - off] = pow(10.0, v);
+  }
+  __syncthreads();
   double *out = profiles + (size_t)m * n_in;
   int bad = 0;
-  for (int l = threadIdx.x; l < nl; l += blockDim.x) {
-    const double T = pt_temperature(cc, s_par, cc.press_bar[l]);
+  const int half = threadIdx.x & 1;
+  // every lane of a warp runs the same number of passes (the pair exchange is a warp shuffle)
+  const int npass = (nl + kConvThreads / 2 - 1) / (kConvThreads / 2);
+  for (int pass = 0; pass < npass; pass++) {
+    const int l = pass * (kConvThreads / 2) + (threadIdx.x >> 1);
+    const bool live = l < nl;
+    const double T = pt_temperature(cc, s_par, cc.press_bar[live ? l : nl - 1], half);
+    if (!live || half) continue;
     if (!(T >= cc.tmin) || !(T <= cc.tmax)) bad |= REJ_TBOUNDS;   // also catches NaN
     out[l] = T;
     // scaled abundances and the metal sum in the reference's order (BARTfunc.py:333-338)
@@ -109,7 +132,7 @@ convert_params_kernel(ConvConfig cc, const double *__restrict__ params, int npar
     for (int j = 0; j < cc.nspec; j++) {
       double a = cc.base[(size_t)j * nl + l];
       for (int k = 0; k < cc.nmolfit; k++)
-        if (cc.imol[k] == j) a = a * pow(10.0, s_par[off + k]);
+        if (cc.imol[k] == j) a = a * s_fac[k];
       if (j != cc.iH2 && j != cc.iHe) out[(size_t)(j + 1) * nl + l] = a;
     }
     for (int k = 0; k < cc.nmetals; k++) {
@@ -138,7 +161,15 @@ convert_params_kernel(ConvConfig cc, const double *__restrict__ params, int npar
 void launch_convert_params(const ConvConfig &cc, const double *params, int npars, double *profiles,
                            int n_in, int *status, const ConvKnobs &kn, int nmodels, cudaStream_t s) {
   if (nmodels <= 0) return;
-  convert_params_kernel<<<nmodels, 128, 0, s>>>(cc, params, npars, profiles, n_in, status, kn, nmodels);
+  static bool table_ready = false;
+  if (!table_ready) {
+    double h[48];
+    h[0] = 0.0;
+    for (int k = 1; k < 48; k++) h[k] = 1.0 / k;
+    cudaMemcpyToSymbol(c_recip, h, sizeof(h));
+    table_ready = true;
+  }
+  convert_params_kernel<<<nmodels, kConvThreads, 0, s>>>(cc, params, npars, profiles, n_in, status, kn, nmodels);
 }
 
 // ---------------------------------------------------------------------------------------

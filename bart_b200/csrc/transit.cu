@@ -423,6 +423,16 @@ static void do_init(int argc, char **argv) {
           "--------------------------------------------------\n");
   setup_sampling();
   read_atmosphere(o.atm, G.atm);
+  // BART's atmosphere files carry number abundances ('q number', TEA / makeatm.py) and BARTfunc does
+  // its own abundance scaling: the reference's mass-abundance branch (readatm.c:122-159,
+  // transit.h:58-69 with at->mass) and its qmol/qscale hints are not built -- refuse them rather
+  // than compute densities from the wrong kind of abundance
+  if (G.atm.mass_abund)
+    fail("Atmosphere file '%s' gives abundances by mass ('q mass'); only number abundances "
+         "('q number') are supported.", o.atm.c_str());
+  if (!o.qmol.empty() || !o.qscale.empty())
+    fail("The 'qmol' / 'qscale' abundance-scaling options are not supported (scale the abundances "
+         "in the run_transit input, as BARTfunc.py does).");
   read_molecules(o.molfile, G.atm, G.mol);
   read_tli_header(o.linedb, G.tli);
   const int nl = G.atm.nlayer(), ns = G.atm.nspec(), nw = (int)G.wn.size();
@@ -448,6 +458,7 @@ static void do_init(int argc, char **argv) {
   c.toomuch = o.toomuch;
   upload(G.d_wn, G.wn); c.wn = G.d_wn.p;
   upload(G.d_press, G.atm.press); c.press = G.d_press.p;
+  c.ref_layer = ref_layer_of(G.atm.press.data(), nl, c.p0);
   upload(G.d_mass, G.mol.mass); c.mass = G.d_mass.p;
   upload(G.d_pol, G.mol.pol); c.pol = G.d_pol.p;
   // ray grid (acceptgenhints 878-881; flux(), eclipse.c:262-279)
@@ -691,11 +702,17 @@ static void band_device(const double *d_spec, int nmodels, const int *d_status, 
   check_launch("band_integrate");
 }
 
+static double peer_timeout_s() {
+  const char *e = getenv("BART_PEER_TIMEOUT_S");
+  const double v = e ? atof(e) : 120.0;
+  return v > 0 ? v : 120.0;
+}
 // consumer side of the fused all-gather: wait for every rank's block, copy to d_all[rank][count]
 static void peer_gather(long long count_per_rank, double *d_all) {
   KernelScope ks("peer_wait_copy");
   launch_peer_wait_copy((const double *)G.pw_base, G.pw_flags, G.pw_gen, G.world, G.pw_cap,
-                        count_per_rank, d_all, G.pw_err, G.pw.done + 1, G.stream);
+                        count_per_rank, d_all, G.pw_err, G.pw.done + 1,
+                        (unsigned long long)(peer_timeout_s() * 1e9), G.stream);
   check_launch("peer_wait_copy");
 }
 
@@ -817,6 +834,32 @@ static void finish_stream() {
   if (G.profile) drain_profile();
 }
 
+// The consumer of the fused all-gather (peer_wait_copy_kernel) gives up on a silent peer after
+// $BART_PEER_TIMEOUT_S (default 120 s) and raises this flag instead of hanging; whatever was computed
+// from that generation on is garbage, so every path that waited on the window must look at it.
+static void check_peer_window(const char *where) {
+  if (!G.p2p || G.world <= 1 || !G.pw_err) return;
+  int err = 0;
+  CUDA_OK(cudaMemcpy(&err, G.pw_err, sizeof(int), cudaMemcpyDeviceToHost));
+  if (!err) return;
+  CUDA_OK(cudaMemset(G.pw_err, 0, sizeof(int)));
+  fail("%s: a rank did not deliver its band fluxes to the peer window within %.0f s (dead or "
+       "lagging peer); the results of this call are invalid", where, peer_timeout_s());
+}
+// all ranks have reached this point (ranks load their grids at different speeds; the first fused
+// generation must not start its time-out clock before the slowest one is ready)
+static void rank_barrier() {
+  if (G.world <= 1 || !G.nccl_comm) return;
+  typedef int (*fn_allgather)(const void *, void *, size_t, int, void *, cudaStream_t);
+  fn_allgather ag = (fn_allgather)dlsym(G.nccl_lib, "ncclAllGather");
+  if (!ag) fail("ncclAllGather not found");
+  G.d_mcgather.ensure((size_t)G.world + 1);
+  int rc = ag(G.d_mcgather.p + G.world, G.d_mcgather.p, 1, 8 /*ncclFloat64*/, G.nccl_comm, G.stream);
+  if (rc != 0) fail("ncclAllGather (barrier) failed (%d)", rc);
+  cudaError_t e = cudaStreamSynchronize(G.stream);
+  if (e != cudaSuccess) fail("CUDA execution failed: %s", cudaGetErrorString(e));
+}
+
 // niter generations of the walk set up in G.mc, queued and awaited
 static void mcmc_run_generations(int niter) {
   McmcDev &mc = G.mc;
@@ -854,6 +897,7 @@ static void mcmc_run_generations(int niter) {
   }
   for (; done < niter; done++) mcmc_generation_queued(0);
   finish_stream();
+  check_peer_window("MCMC generations");
 }
 
 }  // namespace bart
@@ -1172,6 +1216,8 @@ int bart_set_filters(int nfilters, const int *start, const int *count, const dou
   return 0;
   API_END_INT
 }
+
+int bart_nfilters(void) { return G.nfilters; }
 
 int bart_band_integrate(const double *spectra, int nmodels, int nwave, double *bandflux) {
   API_BEGIN
@@ -1516,11 +1562,7 @@ int bart_bandflux_allgather_device(const double *d_profiles, int nmodels, int n_
     G.launches++;
   }
   finish_stream();
-  if (fused) {
-    int err = 0;
-    CUDA_OK(cudaMemcpy(&err, G.pw_err, sizeof(int), cudaMemcpyDeviceToHost));
-    if (err) fail("peer window: a rank did not deliver its band fluxes within 10 s");
-  }
+  if (fused) check_peer_window("bart_bandflux_allgather_device");
   return 0;
   API_END_INT
 }
@@ -1742,8 +1784,10 @@ int bart_mcmc_init(int nchains, int npars, const double *params, const double *p
   G.mc.allmodel = G.d_mcallm.p;
   if (G.mc_graph) { cudaGraphExecDestroy(G.mc_graph); G.mc_graph = nullptr; }
   ensure_params_buffers(G.mc_hi - G.mc_lo);
+  rank_barrier();
   mcmc_generation_queued(1);
   finish_stream();
+  check_peer_window("bart_mcmc_init");
   G.mc_ready = true;
   return 0;
   API_END_INT
@@ -1863,6 +1907,7 @@ int bart_mcmc_snooker_init(int hsize, int thinning, const double *z0) {
     check_launch("zrow_chisq");
   }
   finish_stream();
+  check_peer_window("bart_mcmc_snooker_init");
   G.mc_zsize = hsize;
   return 0;
   API_END_INT

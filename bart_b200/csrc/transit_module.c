@@ -157,6 +157,24 @@ static PyObject *py_set_filters(PyObject *self, PyObject *args) {
   PyArrayObject *st = NULL;
   if (ostar != Py_None) st = (PyArrayObject *)PyArray_FROM_OTF(ostar, NPY_DOUBLE, NPY_ARRAY_IN_ARRAY);
   if (!s || !c || !w || (ostar != Py_None && !st)) { Py_XDECREF(s); Py_XDECREF(c); Py_XDECREF(w); Py_XDECREF(st); return NULL; }
+  /* the library trusts the lengths: count[] as long as start[], weight[] / star[] as long as
+     the counts add up to */
+  {
+    const char *bad = NULL;
+    long long total = 0;
+    if (PyArray_SIZE(c) != PyArray_SIZE(s)) bad = "start and count differ in length";
+    else {
+      const int *pc = (const int *)PyArray_DATA(c);
+      for (npy_intp i = 0; i < PyArray_SIZE(c); i++) { if (pc[i] < 0) bad = "negative count"; total += pc[i]; }
+      if (!bad && PyArray_SIZE(w) != total) bad = "weight must hold sum(count) values";
+      if (!bad && st && PyArray_SIZE(st) != total) bad = "star must hold sum(count) values";
+    }
+    if (bad) {
+      Py_DECREF(s); Py_DECREF(c); Py_DECREF(w); Py_XDECREF(st);
+      PyErr_SetString(PyExc_ValueError, bad);
+      return NULL;
+    }
+  }
   bart_set_filters((int)PyArray_SIZE(s), (int *)PyArray_DATA(s), (int *)PyArray_DATA(c),
                    (double *)PyArray_DATA(w), st ? (double *)PyArray_DATA(st) : NULL, rprs);
   Py_DECREF(s); Py_DECREF(c); Py_DECREF(w); Py_XDECREF(st);
@@ -171,6 +189,13 @@ static PyObject *py_band_flux_batch(PyObject *self, PyObject *args) {
   if (!a) return NULL;
   if (PyArray_NDIM(a) != 2) { Py_DECREF(a); PyErr_SetString(PyExc_TypeError, "profiles must be 2-D"); return NULL; }
   int M = (int)PyArray_DIM(a, 0), n_in = (int)PyArray_DIM(a, 1);
+  /* the library writes M x (configured filters) doubles: the caller's count must be that one */
+  if (nfilt != bart_nfilters()) {
+    Py_DECREF(a);
+    PyErr_Format(PyExc_ValueError, "band_flux_batch: nfilters %d given, %d configured by set_filters",
+                 nfilt, bart_nfilters());
+    return NULL;
+  }
   npy_intp d2[2] = {M, nfilt}, d1[1] = {M};
   PyObject *bf = PyArray_ZEROS(2, d2, NPY_DOUBLE, 0);
   PyObject *st = PyArray_ZEROS(1, d1, NPY_INT32, 0);

@@ -119,6 +119,7 @@ int  bart_run_batch_device(const double *d_profiles, int nmodels, int n_in, doub
  * stellar flux (star may be NULL: no division, `transit`/`direct` modes); rprs = Rp/Rs.    */
 int  bart_set_filters(int nfilters, const int *start, const int *count, const double *weight,
                       const double *star, double rprs);
+int  bart_nfilters(void);            /* filters configured by bart_set_filters (0 before) */
 int  bart_band_integrate(const double *spectra, int nmodels, int nwave, double *bandflux);
 /* profiles -> band fluxes in one call; spectra never leave the device.
  * bandflux[nmodels][nfilters]; rejected models get -1 in every band (BARTfunc.py:327-330).  */

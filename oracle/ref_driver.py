@@ -7,11 +7,11 @@ modules/transit/transit/src/transit.c:14-22 with ctypes, exactly as the SWIG mod
 
 The reference keeps all state in process globals and its option parser is one-shot
 (pu/src/procopt.c:196-202), so every configuration needs its own process: this file is run as
-a subprocess (`python oracle/ref_driver.py cfg models.npy out.npz [--inter] [--time K]`).
+a subprocess (`python oracle/ref_driver.py cfg models.npy out.npz [--inter] [--last] [--time K]`).
 
 Outputs (npz): wn[nwave], spectra[M,nwave]; with --inter also, for every model, radius,
 density, ext[layer,wn], cia[wn,layer], tau[wn,depth], last[wn] read from the reference's
-globals through oracle/ref_shim.c.
+globals through oracle/ref_shim.c; with --last only last[wn] (bench.py's in-run parity gate).
 """
 import ctypes as C
 import os
@@ -68,6 +68,7 @@ def main():
     cfg, models_path, out_path = sys.argv[1:4]
     flags = sys.argv[4:]
     inter = "--inter" in flags
+    want_last = "--last" in flags
     ntime = int(flags[flags.index("--time") + 1]) if "--time" in flags else 0
     setters = {}
     for f in flags:
@@ -117,11 +118,17 @@ def main():
             inter_store["tau"].append(arr(lib.ref_tau(), nl * nwave).reshape(nwave, nl))
             inter_store["last"].append(
                 np.ctypeslib.as_array(lib.ref_last(), shape=(nwave,)).astype(np.int64))
+        elif want_last:
+            lib.ref_run_keep(models[m].ctypes.data_as(dp), spec.ctypes.data_as(dp))
+            inter_store["last"].append(
+                np.ctypeslib.as_array(lib.ref_last(), shape=(nwave,)).astype(np.int64))
         else:
             lib.run_transit(models[m].ctypes.data_as(dp), models.shape[1],
                             spec.ctypes.data_as(dp), nwave)
         spectra[m] = spec
     out["spectra"] = spectra
+    if want_last and not inter:
+        out["last"] = np.stack(inter_store["last"])
     if inter:
         for k, v in inter_store.items():
             if v:

@@ -100,6 +100,7 @@ int emu_init(const char *cfg) {
         for (int j = 0; j < c.nspec; j++) if (E->atm.species[j] == E->cia[i].species[s]) c.cia_spec[i][s] = j;
     }
     c.pfct = E->atm.pfct; c.rfct = E->atm.rfct; c.gsurf = o.gsurf; c.p0 = o.refpress; c.toomuch = o.toomuch;
+    c.ref_layer = ref_layer_of(c.press, c.nlayer, c.p0);
     std::vector<double> ang;
     char *dup = strdup(o.raygrid.c_str());
     for (char *t = strtok(dup, " \t"); t; t = strtok(nullptr, " \t")) ang.push_back(atof(t));

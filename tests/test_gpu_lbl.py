@@ -49,7 +49,8 @@ def test_lbl_forward_vs_oracle_and_reference(name, api, workdir):
         assert relerr(spectra[m], g["spectra"][m]) < TOL
     tr.debug_keep(False)
     spectra2, _ = tr.run_batch(models)
-    assert relerr(spectra2, spectra) < 1e-13
+    # specialised (exp(-tau/cos 60) by squaring) vs run-time-count kernel: degree-4 exponentials
+    assert relerr(spectra2, spectra) < 1e-10
     one = tr.run_transit(models[1])                      # the reference's own entry point
     assert np.array_equal(one, spectra2[1])
     tr.free_memory()
@@ -107,7 +108,7 @@ def test_lbl_equals_grid_mode_at_a_grid_temperature(api, workdir):
     assert (ext_l > 0).any()
     assert np.array_equal(ext_l > 0, ext_g > 0)
     assert relerr(ext_l, ext_g) < 1e-12
-    assert relerr(spec_l, spec_g) < 1e-12
+    assert relerr(spec_l, spec_g) < 1e-10
 
 
 @pytest.mark.parametrize("k", list(cases.FUZZ_LBL))

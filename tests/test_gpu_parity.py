@@ -187,6 +187,30 @@ def test_band_integration(api, get_case):
     tr.free_memory()
 
 
+@pytest.mark.parametrize("name", ["w12", "tiny_eclipse", "small4_eclipse_cloud"])
+def test_small_batch_kernel_bit_identical(name, api, get_case, workdir, monkeypatch):
+    """The slot kernel that small batches select (one warp per 32 columns, kernels.cu
+    eclipse_slot_kernel) against the throughput kernel on the same models: identical bits, so a
+    spectrum does not depend on the size of the batch it was computed in."""
+    import os
+    from bart_b200 import synth
+    if name == "w12":
+        case = synth.make_case(os.path.join(workdir, "w12"), shape="w12", solution="eclipse", seed=2026)
+        models = synth.make_models(case, 12, seed=11, molfit=("H2O", "CO2", "CO", "CH4"))
+        setters = {}
+    else:
+        case, models, setters = get_case(name)
+    tr = api.Transit(case["cfg"])
+    apply_setters(tr, setters)
+    monkeypatch.setenv("BART_ECL_SMALL", "0")
+    big, st = tr.run_batch(models)
+    monkeypatch.setenv("BART_ECL_SMALL", "1")
+    small, st2 = tr.run_batch(models)
+    assert (st == 0).all() and (st2 == 0).all()
+    assert np.array_equal(big, small)
+    tr.free_memory()
+
+
 def test_band_integration_vs_wine_golden(api, get_case):
     """K4 through the C ABI on the arrays the reference's own code/wine.py produced
     (tests/golden/wine.npz: shipped demo filters + Kurucz star on the demo wavenumber grid):
