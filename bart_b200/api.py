@@ -11,7 +11,7 @@ import numpy as np
 _trapz = getattr(np, "trapezoid", None) or np.trapz
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIBPATH = os.path.join(HERE, "libbart_b200.so")
+LIBPATH = os.environ.get("BART_B200_LIB") or os.path.join(HERE, "libbart_b200.so")   # override: A/B builds
 
 dp = C.POINTER(C.c_double)
 ip = C.POINTER(C.c_int)

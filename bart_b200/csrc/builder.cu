@@ -493,24 +493,47 @@ struct StagedGroup {
 constexpr int kAccWarps = 8;
 constexpr int kAccCta = 32 * kAccWarps;
 constexpr int kNarrowSpan = 12;
-constexpr int kBinsPerLane = kAccThreads / 32;
 
-__global__ void __launch_bounds__(kAccCta)
-accumulate_kernel(CellArgs a, const CellIso *cells, double *out) {
-  __shared__ double s_acc[kAccWarps][kAccThreads];
+__device__ __forceinline__ float ldg_f32(const float *p) {
+  float v;
+  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+
+// TILE = coarse bins per CTA (128, or 512 at high resolution: a pressure-broadened group then spans
+// dozens of tiles, and every tile it touches pays the group's staging -- Doppler index search, bin
+// range, profile pointer -- once; wider tiles pay it for four times the bin updates).
+// 4 CTAs (32 warps) per SM at 64 registers.  Measured at the high-resolution shape (1e7 lines onto 1e5
+// wavenumbers, ms per 2 planes): 1 CTA/SM 716, 2: 390, 3: 307, 4: 266, 5: 258, 6: 257, 8: 295 -- the
+// kernel lives on warps in flight (its inner loop waits on scattered 512-byte profile segments served
+// by the L2), while below 48 registers the spills eat the gain at the W12 shape (9.0 -> 9.3 -> 10.3 ms).
+#ifndef BART_ACC_MINB
+#define BART_ACC_MINB 4
+#endif
+template <int TILE>
+__global__ void __launch_bounds__(kAccCta, BART_ACC_MINB)
+accumulate_kernel(CellArgs a, const CellIso *cells, double *out, int fast) {
+  constexpr int kBinsPerLane = TILE / 32;
+  __shared__ double s_acc[kAccWarps][TILE];
   __shared__ StagedGroup s_g[kAccWarps][32];
   __shared__ double s_aDop[128];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // Tile-fastest launch order.  (Measured alternative, round 2: cell-fastest, so that the layers of
+  // one plane walk the same candidate groups together and the group list is read from HBM once
+  // instead of once per layer -- 49 GB -> <1 GB of DRAM reads per plane at 1e7 lines -- ran 1.6x
+  // SLOWER: the kernel is bound by instructions per bin update, not by DRAM, and co-resident CTAs of
+  // very different profile widths balance worse.)
   const int ci = blockIdx.y;
-  const int j0 = blockIdx.x * kAccThreads;
-  const int jt_hi = min(j0 + kAccThreads - 1, a.nwave - 1);
+  const int j0 = blockIdx.x * TILE;
+  const int jt_hi = min(j0 + TILE - 1, a.nwave - 1);
+  const bool full_tile = j0 + TILE - 1 < a.nwave;
   const int p = a.cell_plane[ci];
   const long long base0 = a.plane_base[p];
   const long long *cb = a.cisobeg + (size_t)p * (a.niso + 1);
   const double *Sp = a.S + (size_t)p * a.ngroups;
   double *o = out + a.cell_out[ci];
   for (int k = threadIdx.x; k < a.nDop && k < 128; k += blockDim.x) s_aDop[k] = a.aDop[k];
-  for (int k = threadIdx.x; k < kAccWarps * kAccThreads; k += blockDim.x) (&s_acc[0][0])[k] = 0.0;
+  for (int k = threadIdx.x; k < kAccWarps * TILE; k += blockDim.x) (&s_acc[0][0])[k] = 0.0;
   __syncthreads();
   double *acc = s_acc[warp];
   double r[kBinsPerLane];                  // lane-per-bin partial sums of bins j0 + lane + 32 k
@@ -522,11 +545,11 @@ accumulate_kernel(CellArgs a, const CellIso *cells, double *out) {
 #pragma unroll
     for (int k = 0; k < kBinsPerLane; k++) { acc[lane + 32 * k] += r[k]; r[k] = 0.0; }
     __syncthreads();
-    if (threadIdx.x < kAccThreads) {
+    for (int t = threadIdx.x; t < TILE; t += kAccCta) {
       double v = 0.0;
 #pragma unroll
-      for (int w = 0; w < kAccWarps; w++) { v += s_acc[w][threadIdx.x]; s_acc[w][threadIdx.x] = 0.0; }
-      const int j = j0 + threadIdx.x;
+      for (int w = 0; w < kAccWarps; w++) { v += s_acc[w][t]; s_acc[w][t] = 0.0; }
+      const int j = j0 + t;
       if (j < a.nwave) o[(size_t)m * a.nwave + j] += v;
     }
     __syncthreads();
@@ -547,7 +570,7 @@ accumulate_kernel(CellArgs a, const CellIso *cells, double *out) {
     int hwb = c.hwbins;
     {
       double wlo = a.wn0 + (double)(j0 - c.hwbins - 1) * a.dwn;
-      double whi = a.wn0 + (double)(j0 + kAccThreads + c.hwbins + 1) * a.dwn;
+      double whi = a.wn0 + (double)(j0 + TILE + c.hwbins + 1) * a.dwn;
       if (wlo < a.wn0) wlo = a.wn0;
       if (whi > a.own_last) whi = a.own_last;
       const int dl = nearest_dev(s_aDop, c.alphad * wlo, 0, a.nDop - 1);
@@ -556,8 +579,8 @@ accumulate_kernel(CellArgs a, const CellIso *cells, double *out) {
       for (int d = dl; d <= dh; d++) hw = max(hw, a.prof_size[(size_t)d * a.nLor + c.ilor]);
       hwb = min(hwb, (int)(hw / a.osamp) + 2);
     }
-    // candidate range: leader coarse bins in [j0 - hw, j0 + 127 + hw]; idwn is non-increasing
-    const int hi_bin = j0 + kAccThreads - 1 + hwb, lo_bin = j0 - hwb;
+    // candidate range: leader coarse bins in [j0 - hw, j0 + TILE - 1 + hw]; idwn is non-increasing
+    const int hi_bin = j0 + TILE - 1 + hwb, lo_bin = j0 - hwb;
     long long x = gb, y = ge;
     while (x < y) { const long long mid = (x + y) >> 1; if (a.gidwn[a.c_idx[mid]] > hi_bin) x = mid + 1; else y = mid; }
     const long long first = x;
@@ -607,13 +630,26 @@ accumulate_kernel(CellArgs a, const CellIso *cells, double *out) {
         s_g[warp][lane] = sg;
         __syncwarp();
         const int cnt = (int)min((long long)32, last - base);
-#pragma unroll 4
-        for (int q = 0; q < cnt; q++) {
-          const StagedGroup t = s_g[warp][q];
+        // every staged group covers the whole tile (the usual batch where profiles are wide): a
+        // counted loop without range tests, loads at immediate offsets from one pointer per group
+        const bool mine_full = g >= last || (sg.minj == j0 && sg.maxj == jt_hi);
+        if (fast && full_tile && __all_sync(0xffffffffu, mine_full)) {
+#pragma unroll 8
+          for (int q = 0; q < cnt; q++) {
+            const float *pp = s_g[warp][q].prof + (j0 + lane);
+            const double Sq = s_g[warp][q].S;
 #pragma unroll
-          for (int k = 0; k < kBinsPerLane; k++) {
-            const int bb = j0 + lane + 32 * k;
-            if (bb >= t.minj && bb <= t.maxj) r[k] += t.S * (double)t.prof[bb];
+            for (int k = 0; k < kBinsPerLane; k++) r[k] = fma(Sq, (double)__ldg(pp + 32 * k), r[k]);
+          }
+        } else {
+#pragma unroll 4
+          for (int q = 0; q < cnt; q++) {
+            const StagedGroup t = s_g[warp][q];
+#pragma unroll
+            for (int k = 0; k < kBinsPerLane; k++) {
+              const int bb = j0 + lane + 32 * k;
+              if (bb >= t.minj && bb <= t.maxj) r[k] += t.S * (double)t.prof[bb];
+            }
           }
         }
       }
@@ -972,12 +1008,20 @@ static long long run_planes(BuilderState *b, const Options &o, const Molecules &
   }
   {
     PhaseTimer pt(b, "accumulate", s);
-    const int ntile = (b->nwave + kAccThreads - 1) / kAccThreads;
+    // 512-bin tiles where the grid is fine enough for pressure-broadened profiles to span many
+    // tiles; 128-bin tiles otherwise (more CTAs for the small grids)
+    int tile = 128;
+    if (const char *e = getenv("BART_ACC_TILE")) tile = atoi(e) == 512 ? 512 : atoi(e) == 256 ? 256 : 128;
+    int fast = 1;
+    if (const char *e = getenv("BART_ACC_FAST")) fast = atoi(e);
+    const int ntile = (b->nwave + tile - 1) / tile;
     for (int c0 = 0; c0 < ncell; c0 += 32768) {                  // gridDim.y limit
       const int nc = std::min(32768, ncell - c0);
       CellArgs cb = ca;
       cb.cell_plane += c0; cb.cell_dens += (size_t)c0 * b->nspec; cb.cell_out += c0;
-      accumulate_kernel<<<dim3(ntile, nc), kAccCta, 0, s>>>(cb, cells + (size_t)c0 * niso, d_out);
+      if (tile == 512) accumulate_kernel<512><<<dim3(ntile, nc), kAccCta, 0, s>>>(cb, cells + (size_t)c0 * niso, d_out, fast);
+      else if (tile == 256) accumulate_kernel<256><<<dim3(ntile, nc), kAccCta, 0, s>>>(cb, cells + (size_t)c0 * niso, d_out, fast);
+      else accumulate_kernel<128><<<dim3(ntile, nc), kAccCta, 0, s>>>(cb, cells + (size_t)c0 * niso, d_out, fast);
     }
     BCUDA(cudaGetLastError());
   }
