@@ -995,6 +995,22 @@ BART_HD void transit_weight_row_tiled(const DevConfig &c, const double *tab, int
   transit_weight_row_acc(c, tab, d, [base](int i) -> double & { return base[(size_t)i * kTrRow]; });
 }
 
+// Layout of one model's chord weights for the tensor-core tile kernel (transit_mma_kernel): depth
+// chunks of 16 rows; chunk ch is a dense row-major 16 x mm_rs(ch) block holding W[d][i] for the
+// chunk's depths d and layers i = 0 .. 16 (ch + 1) - 1 (zero above the diagonal and in the rows past
+// the last layer).  The row stride is 4 modulo 16 doubles, which makes the A-fragment read of
+// mma.m8n8k4 (lane -> row lane/4, column lane%4) touch every bank pair exactly twice.
+constexpr int kMmChunk = 16;
+BART_HD int mm_nchunks(int nl) { return (nl + kMmChunk - 1) / kMmChunk; }
+BART_HD int mm_rs(int ch) { return kMmChunk * (ch + 1) + 4; }
+BART_HD size_t mm_chunk_off(int ch) { return (size_t)128 * ch * (ch + 1) + (size_t)64 * ch; }
+BART_HD size_t mm_stride(int nl) { return mm_chunk_off(mm_nchunks(nl)); }
+BART_HD void transit_weight_row_mm(const DevConfig &c, const double *tab, int d, double *wm) {
+  const int ch = d / kMmChunk;
+  double *base = wm + mm_chunk_off(ch) + (size_t)(d % kMmChunk) * mm_rs(ch);
+  transit_weight_row_acc(c, tab, d, [base](int i) -> double & { return base[i]; });
+}
+
 // modulationm1 (slantpath.c:446-473), modlevel -1: the planet as an opaque disc whose radius is
 // where tau reaches toomuch, by linear interpolation (interp_line, pu/src/numerical.c:203-211)
 // between the last two impact parameters.  tau0/tau1: optical depths at depths last-1 and last,

@@ -238,16 +238,19 @@ eclipse_slot_kernel(DevConfig c, const double *__restrict__ tabs, const int *__r
 // tiled layout of column_math.cuh (zero-filled first: weights above the diagonal are zero).
 __global__ void __launch_bounds__(128)
 transit_weights_kernel(DevConfig c, const double *__restrict__ tabs, double *__restrict__ wts,
-                       int nmodels) {
+                       int nmodels, int mma_layout) {
   const int m = blockIdx.x;
   if (m >= nmodels) return;
   const int nl = c.nlayer;
-  const size_t stride = tr_stride(nl);
+  const size_t stride = mma_layout ? mm_stride(nl) : tr_stride(nl);
   const double *tab = tabs + (size_t)m * c.lay.stride();
   double *wm = wts + (size_t)m * stride;
   for (size_t i = threadIdx.x; i < stride; i += blockDim.x) wm[i] = 0.0;
   __syncthreads();
-  for (int d = threadIdx.x; d < nl; d += blockDim.x) transit_weight_row_tiled(c, tab, d, wm);
+  for (int d = threadIdx.x; d < nl; d += blockDim.x) {
+    if (mma_layout) transit_weight_row_mm(c, tab, d, wm);
+    else transit_weight_row_tiled(c, tab, d, wm);
+  }
 }
 
 // transit_tile_kernel: CTA = one model x 64 wavenumbers, 4 warps.  The chord optical depth
@@ -457,6 +460,242 @@ transit_tile_kernel(DevConfig c, const double *__restrict__ tabs, const double *
   int n;
   if (last < nl - 1) {
     const int dd = last + 1;                                   // appended zero-integrand point
+    const double *row = s_tab + (size_t)dd * nf;
+    if (dd >= 2 && !(dd & 1)) S += row[L::SB] * f1 + row[L::SC] * f2;
+    f2 = f1; f1 = 0.0;
+    n = dd + 1;
+  } else n = nl;
+  double res;
+  if (n < 3) { atomicOr(&status_col[m], REJ_FEWPTS); res = -1.0; }
+  else {
+    if (!(n & 1)) S += s_tab[(size_t)(n - 1) * nf + L::TR] * (f1 + f2);
+    const double btop = s_tab[L::RAD] * c.rfct;
+    res = btop * btop - 2.0 * S;
+    if (c.transparent) {
+      const double maxtau = tau > c.toomuch ? tau : c.toomuch;
+      const double bl = s_tab[(size_t)(n - 1) * nf + L::RAD] * c.rfct;
+      res -= fast_exp_neg(-maxtau, s_etab) * bl * bl;
+    }
+    res *= c.inv_srad2;
+  }
+  spectra[(size_t)m * c.nwave + w] = res;
+}
+
+// transit_mma_kernel: the same CTA shape and producer / consumer split, with the chord optical
+// depth evaluated on the fp64 tensor cores.  tau(d, w) = sum_{i<=d} W[d][i] er[i][w] is, per model,
+// a lower-triangular 100 x 100 matrix times the 100 x 64 extinction tile -- the one dense
+// contraction of the forward model.  With DFMA the product is bound by the shared-memory pipe
+// (every 10 multiply-adds of a lane need one 16-byte extinction read and 40 bytes of weight
+// broadcasts: l1tex 82 %, fp64 29 %); mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4, 64 multiply-adds per
+// clock per SM like DFMA -- tools/dmma_microbench.cu) takes its operands as warp-wide fragments,
+// 1 shared-memory wavefront per 128 multiply-adds instead of 1 per 36.
+//   chunk = 16 depths; consumer warp w owns columns 16 w .. 16 w + 15: 2 x 2 accumulator
+//   fragments (depths x columns), K loop over the layers 0 .. d0 + 15 in steps of 4 (the upper
+//   depth block stops 8 layers earlier: its weights beyond the diagonal are zero);
+//   er[layer][64] is stored with columns XOR-swizzled by 8 on odd layers, so that the B-fragment
+//   read (lane -> layer lane%4, column lane/4) is conflict-free at a row stride of 64;
+//   the chunk's weights arrive by one bulk-async copy (TMA) issued while the previous chunk's
+//   scan runs (layout: column_math.cuh mm_rs / mm_chunk_off).
+// The sum over layers runs in ascending order in groups of four; it differs from the DFMA kernel's
+// (and the reference's) by rounding only.
+constexpr int kMmThreads = 256, kMmCons = 128, kMmW = 64, kMmLoadBatch = 2, kMmMaxChunks = 20;
+__device__ __forceinline__ void dmma884(double (&acc)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(acc[0]), "+d"(acc[1]) : "d"(a), "d"(b));
+}
+
+template <int NMOL, int NCIA, bool KEEP>
+__global__ void __launch_bounds__(kMmThreads, 2)
+transit_mma_kernel(DevConfig c, const double *__restrict__ tabs, const double *__restrict__ wts,
+                   const int *__restrict__ status, int *__restrict__ status_col,
+                   double *__restrict__ spectra, double *__restrict__ tau_keep,
+                   int *__restrict__ last_keep, int nmodels, int use_tma) {
+  typedef TabLayout L;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t bar, bar_w;
+  const int nl = c.nlayer, nf = c.lay.nf(), nd = c.lay.stride();
+  const int nchunks = mm_nchunks(nl), nlp = nchunks * kMmChunk;
+  unsigned long long *s_etab = reinterpret_cast<unsigned long long *>(smem_raw);
+  double *s_tab = reinterpret_cast<double *>(s_etab + kExpTabSize);
+  double *s_wt = s_tab + nd;                                   // [16][mm_rs(last chunk)]
+  double *s_er = s_wt + (size_t)kMmChunk * mm_rs(nchunks - 1); // [nlp][64], swizzled
+  double *s_tau = s_er + (size_t)nlp * kMmW;                   // [16][64]
+  double *s_fd = s_tau + (size_t)kMmChunk * kMmW;              // [16][64] exp(-tau) b
+  __shared__ int s_ready[kMmMaxChunks];
+  __shared__ int s_stop, s_alive[2];
+  const int m = blockIdx.x % nmodels;
+  const int tile = blockIdx.x / nmodels;
+  const bool producer = threadIdx.x >= kMmCons;
+  const int t = producer ? threadIdx.x - kMmCons : threadIdx.x;
+  const int lane = t & 31, warp = t >> 5;
+  const int wl = t & (kMmW - 1), dh = t >> 6;
+  const int wcol = tile * kMmW + wl;
+  const bool valid = wcol < c.nwave;
+  const int w = valid ? wcol : c.nwave - 1;
+  if (status[m] != 0) {
+    if (!producer && t < kMmW && valid) spectra[(size_t)m * c.nwave + w] = -1.0;
+    return;
+  }
+  if (threadIdx.x == 0) { mbar_init(&bar_w, 1); s_stop = 0; s_alive[0] = s_alive[1] = 0; }
+  if (threadIdx.x < kMmMaxChunks) s_ready[threadIdx.x] = 0;
+  // rows past the last layer: zero extinction (their weights are zero as well)
+  for (int i = nl * kMmW + threadIdx.x; i < nlp * kMmW; i += kMmThreads) s_er[i] = 0.0;
+  stage_table(s_tab, tabs + (size_t)m * nd, nd, &bar, use_tma != 0, s_etab);
+  __syncthreads();
+  const double wn = c.wn[w];
+
+  if (producer) {
+    const ColPtrs P = col_ptrs<NCIA>(c, w);
+    const double wn4 = (wn * wn) * (wn * wn);
+    for (int ch = 0; ch < nchunks; ch++) {
+      if (*(volatile int *)&s_stop) break;
+      const int d0 = ch * kMmChunk;
+#pragma unroll
+      for (int j0 = 0; j0 < kMmChunk / 2; j0 += kMmLoadBatch) {
+        CellData<NMOL, NCIA> x[kMmLoadBatch];
+#pragma unroll
+        for (int j = 0; j < kMmLoadBatch; j++) {
+          const int d = d0 + dh + 2 * (j0 + j);
+          if (d < nl) cell_load<NMOL, NCIA>(c, P, s_tab + (size_t)d * nf, x[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < kMmLoadBatch; j++) {
+          const int d = d0 + dh + 2 * (j0 + j);
+          if (d < nl)
+            s_er[(size_t)d * kMmW + (wl ^ ((d & 1) << 3))] =
+                cell_combine<NMOL, NCIA>(c, P, s_tab + (size_t)d * nf, x[j], wn4, false);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) { __threadfence_block(); atomicAdd(&s_ready[ch], 1); }
+    }
+    return;
+  }
+
+  // ---- consumers
+  const double *wm = wts + (size_t)m * mm_stride(nl);
+  double *tk = KEEP ? tau_keep + ((size_t)m * c.nwave + w) * nl : nullptr;
+  double S = 0.0, f1 = 0.0, f2 = 0.0, tau = 0.0, tau_prev = 0.0;
+  int last = nl - 1;
+  bool done = false;
+  uint32_t wphase = 0;
+  bool pending = false;
+  auto stage_weights = [&](int ch) {
+    pending = true;
+    const int n = kMmChunk * mm_rs(ch);
+    const double *wsrc = wm + mm_chunk_off(ch);
+    if (use_tma) {
+      if (t == 0) {
+        mbar_expect_tx(&bar_w, (uint32_t)n * 8u);
+        bulk_g2s(s_wt, wsrc, (uint32_t)n * 8u, &bar_w);
+      }
+    } else {
+      for (int i = t; i < n; i += kMmCons) s_wt[i] = wsrc[i];
+    }
+  };
+  stage_weights(0);
+  const int g = lane >> 2, tg = lane & 3;
+  for (int ch = 0; ch < nchunks; ch++) {
+    const int d0 = ch * kMmChunk;
+    const int dn = min(kMmChunk, nl - d0);
+    while (*(volatile int *)&s_ready[ch] < kMmCons / 32) __nanosleep(32);
+    __threadfence_block();
+    if (use_tma) { mbar_wait(&bar_w, wphase); wphase ^= 1u; }
+    else bar_consumers();
+    pending = false;
+    // ---- phase B: tau[16 depths][16 columns of this warp] on the tensor cores
+    {
+      const int rs = mm_rs(ch);
+      double acc[2][2][2];
+#pragma unroll
+      for (int a = 0; a < 2; a++)
+#pragma unroll
+        for (int b = 0; b < 2; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+      const double *ap = s_wt + (size_t)g * rs + tg;           // A: row g (+8), layer k0 + tg
+      const int sw = (tg & 1) << 3;                            // k0 is a multiple of 4: layer parity = tg parity
+      const double *bp = s_er + (size_t)tg * kMmW;             // B: layer k0 + tg, column 16 warp + g (+8)
+      const int cb0 = (16 * warp + g) ^ sw, cb1 = (16 * warp + g + 8) ^ sw;
+      const int kend0 = d0 + 8, kend1 = d0 + kMmChunk;
+      int k0 = 0;
+#pragma unroll 2
+      for (; k0 < kend0; k0 += 4) {
+        const double b0 = bp[(size_t)k0 * kMmW + cb0], b1 = bp[(size_t)k0 * kMmW + cb1];
+        const double a0 = ap[k0], a1 = ap[(size_t)8 * rs + k0];
+        dmma884(acc[0][0], a0, b0); dmma884(acc[0][1], a0, b1);
+        dmma884(acc[1][0], a1, b0); dmma884(acc[1][1], a1, b1);
+      }
+      for (; k0 < kend1; k0 += 4) {                            // lower depth block only
+        const double b0 = bp[(size_t)k0 * kMmW + cb0], b1 = bp[(size_t)k0 * kMmW + cb1];
+        const double a1 = ap[(size_t)8 * rs + k0];
+        dmma884(acc[1][0], a1, b0); dmma884(acc[1][1], a1, b1);
+      }
+      // epilogue: C fragment = rows g (+8), columns 2 tg, 2 tg + 1 of each 8-column block
+#pragma unroll
+      for (int a = 0; a < 2; a++) {
+        const int dl = 8 * a + g;
+        if (d0 + dl < nl) {
+          const double bd = s_tab[(size_t)(d0 + dl) * nf + L::RAD] * c.rfct;
+#pragma unroll
+          for (int b = 0; b < 2; b++) {
+            const int col = 16 * warp + 8 * b + 2 * tg;
+            D2 v; v.x = acc[a][b][0]; v.y = acc[a][b][1];
+            D2 f;
+            f.x = fast_exp_neg(-v.x, s_etab) * bd;
+            f.y = fast_exp_neg(-v.y, s_etab) * bd;
+            *reinterpret_cast<D2 *>(s_tau + (size_t)dl * kMmW + col) = v;
+            *reinterpret_cast<D2 *>(s_fd + (size_t)dl * kMmW + col) = f;
+          }
+        }
+      }
+    }
+    if (t == 0) s_alive[ch & 1] = 0;
+    bar_consumers();
+    if (ch + 1 < nchunks) stage_weights(ch + 1);
+    // ---- phase C: one thread per column (same scan as transit_tile_kernel)
+    if (t < kMmW && !done) {
+      const double *tc = s_tau + t, *fc = s_fd + t;
+      int jstop = kMmChunk;
+#pragma unroll
+      for (int j = kMmChunk - 1; j >= 0; j--)
+        if (j < dn && tc[(size_t)j * kMmW] > c.toomuch) jstop = j;
+      const int jl = jstop < dn ? jstop : dn - 1;
+      if (KEEP && valid)
+        for (int j = 0; j <= jl; j++) tk[d0 + j] = tc[(size_t)j * kMmW];
+#pragma unroll
+      for (int j = 0; j < kMmChunk; j++) {
+        const double fd = fc[(size_t)j * kMmW];
+        if (j <= jl) {
+          if (!(j & 1) && d0 + j >= 2) {
+            const double *row = s_tab + (size_t)(d0 + j) * nf;
+            S += row[L::SA] * fd + row[L::SB] * f1 + row[L::SC] * f2;
+          }
+          f2 = f1; f1 = fd;
+        }
+      }
+      tau_prev = jl > 0 ? tc[(size_t)(jl - 1) * kMmW] : tau;
+      tau = tc[(size_t)jl * kMmW];
+      if (jstop < dn) { last = d0 + jstop; done = true; }
+      if (!done) s_alive[ch & 1] = 1;
+    }
+    bar_consumers();
+    if (!*(volatile int *)&s_alive[ch & 1]) { if (t == 0) s_stop = 1; break; }
+  }
+  if (use_tma && pending) mbar_wait(&bar_w, wphase);
+  if (t >= kMmW || !valid) return;
+  if (KEEP) last_keep[(size_t)m * c.nwave + w] = last;
+  if (c.modlevel == -1) {
+    const int i0 = last > 0 ? last - 1 : 0;
+    int st = 0;
+    const double r = modulation_m1(tau_prev, tau, s_tab[(size_t)i0 * nf + L::RAD] * c.rfct,
+                                   s_tab[(size_t)(i0 + 1) * nf + L::RAD] * c.rfct, c.toomuch,
+                                   c.inv_srad2, &st);
+    if (st) atomicOr(&status_col[m], st);
+    spectra[(size_t)m * c.nwave + w] = r;
+    return;
+  }
+  int n;
+  if (last < nl - 1) {
+    const int dd = last + 1;
     const double *row = s_tab + (size_t)dd * nf;
     if (dd >= 2 && !(dd & 1)) S += row[L::SB] * f1 + row[L::SC] * f2;
     f2 = f1; f1 = 0.0;
@@ -795,7 +1034,20 @@ void launch_merge_status(int *status, const int *status_col, int nmodels, cudaSt
   merge_status_kernel<<<(nmodels + 255) / 256, 256, 0, s>>>(status, status_col, nmodels);
 }
 
-size_t transit_weights_stride(int nlayer) { return tr_stride(nlayer); }
+size_t transit_weights_stride(int nlayer) { return std::max(tr_stride(nlayer), mm_stride(nlayer)); }
+
+static size_t transit_mma_smem(const DevConfig &c) {
+  const int nch = mm_nchunks(c.nlayer);
+  return table_smem(c) + ((size_t)kMmChunk * mm_rs(nch - 1) + (size_t)nch * kMmChunk * kMmW +
+                          (size_t)2 * kMmChunk * kMmW) * sizeof(double);
+}
+// the tensor-core tile kernel serves every production launch it has the shared memory for (two CTAs
+// per SM up to ~100 layers, one up to ~200); $BART_TRANSIT_MMA=0 forces the DFMA kernel
+bool transit_uses_mma(const DevConfig &c, bool keep) {
+  if (keep) return false;
+  if (const char *e = getenv("BART_TRANSIT_MMA")) { if (*e && atoi(e) == 0) return false; }
+  return mm_nchunks(c.nlayer) <= kMmMaxChunks && transit_mma_smem(c) <= 200 * 1024;
+}
 
 template <int NMOL, int NCIA, bool KEEP>
 static void launch_transit_t(const DevConfig &c, const double *tabs, const double *wts,
@@ -814,10 +1066,33 @@ static void launch_transit_t(const DevConfig &c, const double *tabs, const doubl
       c, tabs, wts, status, status_col, spectra, tau_keep, last_keep, nmodels, use_tma);
 }
 
+template <int NMOL, int NCIA>
+static void launch_transit_mma_t(const DevConfig &c, const double *tabs, const double *wts,
+                                 const int *status, int *status_col, double *spectra, int nmodels,
+                                 int use_tma, cudaStream_t s) {
+  const size_t smem = transit_mma_smem(c);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaFuncSetAttribute(transit_mma_kernel<NMOL, NCIA, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = smem;
+  }
+  const int tiles = (c.nwave + kMmW - 1) / kMmW;
+  transit_mma_kernel<NMOL, NCIA, false><<<(unsigned)((size_t)tiles * nmodels), kMmThreads, smem, s>>>(
+      c, tabs, wts, status, status_col, spectra, nullptr, nullptr, nmodels, use_tma);
+}
+
 template <int NMOL>
 static void launch_transit_ncia(const DevConfig &c, const double *tabs, const double *wts,
                                 const int *status, int *status_col, double *spectra, int nmodels,
                                 int use_tma, cudaStream_t s) {
+  if (transit_uses_mma(c, false)) {
+    switch (c.ncia) {
+      case 0: launch_transit_mma_t<NMOL, 0>(c, tabs, wts, status, status_col, spectra, nmodels, use_tma, s); return;
+      case 1: launch_transit_mma_t<NMOL, 1>(c, tabs, wts, status, status_col, spectra, nmodels, use_tma, s); return;
+      case 2: launch_transit_mma_t<NMOL, 2>(c, tabs, wts, status, status_col, spectra, nmodels, use_tma, s); return;
+      default: launch_transit_mma_t<0, -1>(c, tabs, wts, status, status_col, spectra, nmodels, use_tma, s); return;
+    }
+  }
   switch (c.ncia) {
     case 0: launch_transit_t<NMOL, 0, false>(c, tabs, wts, status, status_col, spectra, nullptr, nullptr, nmodels, use_tma, s); break;
     case 1: launch_transit_t<NMOL, 1, false>(c, tabs, wts, status, status_col, spectra, nullptr, nullptr, nmodels, use_tma, s); break;
@@ -827,8 +1102,8 @@ static void launch_transit_ncia(const DevConfig &c, const double *tabs, const do
 }
 
 void launch_transit_weights(const DevConfig &c, const double *tabs, double *wts, int nmodels,
-                            cudaStream_t s) {
-  transit_weights_kernel<<<nmodels, 128, 0, s>>>(c, tabs, wts, nmodels);
+                            bool keep, cudaStream_t s) {
+  transit_weights_kernel<<<nmodels, 128, 0, s>>>(c, tabs, wts, nmodels, transit_uses_mma(c, keep) ? 1 : 0);
 }
 
 void launch_transit(const DevConfig &c, const double *tabs, const double *wts, const int *status,
@@ -843,7 +1118,9 @@ void launch_transit(const DevConfig &c, const double *tabs, const double *wts, c
     case 2: launch_transit_ncia<2>(c, tabs, wts, status, status_col, spectra, nmodels, use_tma, s); break;
     case 3: launch_transit_ncia<3>(c, tabs, wts, status, status_col, spectra, nmodels, use_tma, s); break;
     case 4: launch_transit_ncia<4>(c, tabs, wts, status, status_col, spectra, nmodels, use_tma, s); break;
-    default: launch_transit_t<0, -1, false>(c, tabs, wts, status, status_col, spectra, nullptr, nullptr, nmodels, use_tma, s);
+    default:
+      if (transit_uses_mma(c, false)) launch_transit_mma_t<0, -1>(c, tabs, wts, status, status_col, spectra, nmodels, use_tma, s);
+      else launch_transit_t<0, -1, false>(c, tabs, wts, status, status_col, spectra, nullptr, nullptr, nmodels, use_tma, s);
   }
 }
 

@@ -23,8 +23,9 @@ void launch_eclipse(const DevConfig &c, const double *tabs, const int *status, d
                     cudaStream_t s);
 // chord weights of one model in the tiled layout (doubles per model), K2t, and the tile kernel
 size_t transit_weights_stride(int nlayer);
+// keep: the launch that follows is the introspection one (it takes the DFMA kernel's layout)
 void launch_transit_weights(const DevConfig &c, const double *tabs, double *wts, int nmodels,
-                            cudaStream_t s);
+                            bool keep, cudaStream_t s);
 void launch_transit(const DevConfig &c, const double *tabs, const double *wts, const int *status,
                     int *status_col, double *spectra, double *tau_keep, int *last_keep,
                     int nmodels, bool keep, int use_tma, cudaStream_t s);

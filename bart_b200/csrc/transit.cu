@@ -666,7 +666,7 @@ static void launch_models(const double *d_prof, int off, int count, int total, i
     double *wts = G.d_wts.p + (size_t)off * transit_weights_stride(c.nlayer);
     {
       KernelScope ks("transit_weights");
-      launch_transit_weights(c, tabs, wts, count, G.stream);
+      launch_transit_weights(c, tabs, wts, count, G.keep, G.stream);
       check_launch("transit_weights");
     }
     {

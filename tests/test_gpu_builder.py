@@ -74,6 +74,37 @@ def test_bins_and_profiles_vs_oracle(api, workdir):
     tr.free_memory()
 
 
+def test_line_bins_million_lines(api, workdir, monkeypatch):
+    """a19 index hazards at scale (extinction.c:431-462: `(wavn - wns.i)/odwn` truncation, the
+    nearest-oversampled-node test, the co-add run): 1.2e6 random lines onto 601 x 1080 oversampled
+    bins through the CUDA path (line_index_kernel + host grouping) against the oracle's trace --
+    leader bin of every line, or the leader it was co-added into.  Disagreements are counted, and
+    the count must be zero."""
+    import ctypes as C
+    import os
+    from bart_b200 import synth
+    from oracle import oracle as orc
+    case = synth.make_case(os.path.join(workdir, "bins_1e6"),
+                           shape=dict(wnlow=2000.0, wnhigh=2600.0, wndelt=1.0, mols=["H2O", "CH4"], toomuch=10.0),
+                           nlayer=10, with_grid=False, nlines=1200000, tempdelt=800.0, seed=4713,
+                           ethresh=1e-4, wnosamp=1080, nwidth=30)
+    monkeypatch.setenv("BART_TSLICE", "0:0")             # load and index the lines, build no plane
+    tr = api.Transit(argv=["transit", "-c", case["cfg"], "--justOpacity"])
+    monkeypatch.delenv("BART_TSLICE")
+    B = orc.BuilderOracle(case["cfg"])
+    n = len(B.wl)
+    assert n >= 1000000
+    B.build(layers=[len(B.atm["press"]) - 1], temps=[0], trace=True)
+    bins = np.zeros(n, dtype=np.int64)
+    assert api.lib().bart_line_bins(bins.ctypes.data_as(C.POINTER(C.c_longlong)), n) == n
+    ndiff = int((bins != B.trace).sum())
+    nlead, nco = int((B.trace >= 0).sum()), int((B.trace <= -2).sum())
+    print("line bins: %d lines, %d leaders, %d co-added, %d disagreements" % (n, nlead, nco, ndiff))
+    assert nlead > 300000 and nco > 100000
+    assert ndiff == 0
+    tr.free_memory()
+
+
 def test_temperature_sharded_build(api, workdir):
     """T-sharded build (bart_build_opacity_slice): slices reassemble to the full grid bit for bit."""
     case = cases.build_builder_case("build_ch4", workdir)
