@@ -18,6 +18,7 @@ ip = C.POINTER(C.c_int)
 
 REJ_TGRID, REJ_TCIA, REJ_SUMQ, REJ_FEWPTS = 1, 2, 4, 8
 REJ_NOTOOMUCH = 64
+REJ_ENERGY = 128
 
 
 class BartError(RuntimeError):
@@ -51,6 +52,8 @@ def lib():
     L.bart_set_filters.argtypes = [C.c_int, ip, ip, dp, dp, C.c_double]
     L.bart_band_integrate.argtypes = [dp, C.c_int, C.c_int, dp]
     L.bart_nfilters.restype = C.c_int
+    L.bart_set_energy_balance.argtypes = [C.c_int, C.c_double, C.c_double]
+    L.bart_energy_balance.argtypes = [dp, C.c_int, C.c_int, ip]
     L.bart_bandflux_batch.argtypes = [dp, C.c_int, C.c_int, dp, ip]
     L.bart_bandflux_batch_device.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     L.bart_extinction_batch.argtypes = [dp, C.c_int, C.c_int, dp, C.c_int]
@@ -220,6 +223,20 @@ class Transit:
                                       count.ctypes.data_as(ip), _d(weight),
                                       None if st is None else _d(st), float(rprs)))
         self.nfilters = len(start)
+
+    def set_energy_balance(self, tstar, rstar_m, sma_m, rplanet_m, on=True):
+        """Switch on BARTfunc's energy-balance rejection (code/BARTfunc.py:366-383; arguments as it
+        reads them from the TEP file: Ts [K], Rs, a, Rp [m]) for every band-flux call."""
+        sig, j2erg = 5.670367e-8, 1e7                      # code/constants.py:19, BARTfunc.py:375
+        e_in = sig * tstar ** 4 * rstar_m ** 2 * np.pi * rplanet_m ** 2 / sma_m ** 2 * j2erg
+        _check(lib().bart_set_energy_balance(1 if on else 0, float(e_in), float(4 * (rplanet_m * 100) ** 2)))
+        return e_in
+
+    def energy_balance(self, spectra):
+        s = np.ascontiguousarray(np.atleast_2d(spectra), dtype=np.float64)
+        out = np.zeros(s.shape[0], dtype=np.int32)
+        _check(lib().bart_energy_balance(_d(s), s.shape[0], s.shape[1], out.ctypes.data_as(ip)))
+        return out
 
     def band_integrate(self, spectra):
         s = np.ascontiguousarray(spectra, dtype=np.float64)

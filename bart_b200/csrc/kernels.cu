@@ -492,19 +492,21 @@ transit_tile_kernel(DevConfig c, const double *__restrict__ tabs, const double *
 //   chunk = 16 depths; consumer warp w owns columns 16 w .. 16 w + 15: 2 x 2 accumulator
 //   fragments (depths x columns), K loop over the layers 0 .. d0 + 15 in steps of 4 (the upper
 //   depth block stops 8 layers earlier: its weights beyond the diagonal are zero);
-//   er[layer][64] is stored with columns XOR-swizzled by 8 on odd layers, so that the B-fragment
-//   read (lane -> layer lane%4, column lane/4) is conflict-free at a row stride of 64;
+//   er[layer][64] is stored with its columns XOR-swizzled by 4 (layer & 3), so that the B-fragment
+//   read (lane -> layer lane%4, column lane/4) is conflict-free within each half-warp at a row
+//   stride of 64; the tau / exp(-tau) b tiles are swizzled by 8 on odd depths for the C-fragment
+//   stores;
 //   the chunk's weights arrive by one bulk-async copy (TMA) issued while the previous chunk's
 //   scan runs (layout: column_math.cuh mm_rs / mm_chunk_off).
 // The sum over layers runs in ascending order in groups of four; it differs from the DFMA kernel's
 // (and the reference's) by rounding only.
-constexpr int kMmThreads = 256, kMmCons = 128, kMmW = 64, kMmLoadBatch = 2, kMmMaxChunks = 20;
+constexpr int kMmThreads = 256, kMmCons = 128, kMmW = 64, kMmLoadBatch = 1, kMmMaxChunks = 20;
 __device__ __forceinline__ void dmma884(double (&acc)[2], double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(acc[0]), "+d"(acc[1]) : "d"(a), "d"(b));
 }
 
-template <int NMOL, int NCIA, bool KEEP>
+template <int NMOL, int NCIA, bool KEEP, bool SC>
 __global__ void __launch_bounds__(kMmThreads, 2)
 transit_mma_kernel(DevConfig c, const double *__restrict__ tabs, const double *__restrict__ wts,
                    const int *__restrict__ status, int *__restrict__ status_col,
@@ -528,7 +530,7 @@ transit_mma_kernel(DevConfig c, const double *__restrict__ tabs, const double *_
   const bool producer = threadIdx.x >= kMmCons;
   const int t = producer ? threadIdx.x - kMmCons : threadIdx.x;
   const int lane = t & 31, warp = t >> 5;
-  const int wl = t & (kMmW - 1), dh = t >> 6;
+  const int wl = t & (kMmW - 1);
   const int wcol = tile * kMmW + wl;
   const bool valid = wcol < c.nwave;
   const int w = valid ? wcol : c.nwave - 1;
@@ -545,25 +547,64 @@ transit_mma_kernel(DevConfig c, const double *__restrict__ tabs, const double *_
   const double wn = c.wn[w];
 
   if (producer) {
-    const ColPtrs P = col_ptrs<NCIA>(c, w);
-    const double wn4 = (wn * wn) * (wn * wn);
+    // Lookup: producer warp pw fills the depths d = pw (mod 4) of every chunk for all 64 columns of
+    // the tile, two columns per lane (lane, lane + 32) addressed from one base pointer, so a depth's
+    // table record is read by one warp only.  The CIA samples are kept across the depths of one
+    // bracket row (as in eclipse_columns).  Columns past the end of the spectrum read the padding.
+    // (Measured alternative: two tensor-core warps with 16 x 32 tiles and six producer warps, the
+    // next depth's loads in flight while the current one is combined -- 12.3 ms against 8.3 ms: the
+    // second register stage spills.)
+    const int wa = tile * kMmW + lane;
+    const ColPtrs P = col_ptrs<NCIA>(c, wa);
+    constexpr bool kStatic = CellData<NMOL, NCIA>::kStatic;
+    const size_t gstep = (size_t)32 * (kStatic ? CellData<NMOL, NCIA>::NG : c.gms) * 8, cstep = (size_t)32 * 32;
+    double wn4[2];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+      const double v = c.wn[min(wa + 32 * k, c.nwave - 1)];
+      wn4[k] = (v * v) * (v * v);
+    }
+    CellData<NMOL, NCIA> x[kMmLoadBatch][2];
+    D4 pq[2][CellData<NMOL, NCIA>::NC];                        // CIA samples of the current bracket rows
+    CellOffs<NCIA> have;
+    bool first = true;
     for (int ch = 0; ch < nchunks; ch++) {
       if (*(volatile int *)&s_stop) break;
       const int d0 = ch * kMmChunk;
 #pragma unroll
-      for (int j0 = 0; j0 < kMmChunk / 2; j0 += kMmLoadBatch) {
-        CellData<NMOL, NCIA> x[kMmLoadBatch];
+      for (int j0 = 0; j0 < kMmChunk / 4; j0 += kMmLoadBatch) {
+        bool fresh[kMmLoadBatch];
 #pragma unroll
         for (int j = 0; j < kMmLoadBatch; j++) {
-          const int d = d0 + dh + 2 * (j0 + j);
-          if (d < nl) cell_load<NMOL, NCIA>(c, P, s_tab + (size_t)d * nf, x[j]);
+          const int d = d0 + 4 * (j0 + j) + warp;
+          fresh[j] = false;
+          if (d < nl) {
+            const CellOffs<NCIA> o = cell_offsets<NMOL, NCIA>(s_tab + (size_t)d * nf);
+            fresh[j] = first;
+#pragma unroll
+            for (int f = 0; f < (NCIA > 0 ? NCIA : 0); f++) fresh[j] = fresh[j] || o.cia[f] != have.cia[f];
+#pragma unroll
+            for (int k = 0; k < 2; k++) cell_load_at<NMOL, NCIA>(c, P, o, x[j][k], k * gstep, k * cstep, fresh[j]);
+            have = o;
+            first = false;
+          }
         }
 #pragma unroll
         for (int j = 0; j < kMmLoadBatch; j++) {
-          const int d = d0 + dh + 2 * (j0 + j);
-          if (d < nl)
-            s_er[(size_t)d * kMmW + (wl ^ ((d & 1) << 3))] =
-                cell_combine<NMOL, NCIA>(c, P, s_tab + (size_t)d * nf, x[j], wn4, false);
+          const int d = d0 + 4 * (j0 + j) + warp;
+          if (d < nl) {
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+              if (CellData<NMOL, NCIA>::kStaticCia) {
+#pragma unroll
+                for (int f = 0; f < (NCIA > 0 ? NCIA : 0); f++) {
+                  if (fresh[j]) pq[k][f] = x[j][k].q[f]; else x[j][k].q[f] = pq[k][f];
+                }
+              }
+              s_er[(size_t)d * kMmW + ((lane + 32 * k) ^ ((d & 3) << 2))] =
+                  cell_combine<NMOL, NCIA, SC>(c, P, s_tab + (size_t)d * nf, x[j][k], wn4[k], false, k * gstep, k * cstep);
+            }
+          }
         }
       }
       __syncwarp();
@@ -612,7 +653,7 @@ transit_mma_kernel(DevConfig c, const double *__restrict__ tabs, const double *_
 #pragma unroll
         for (int b = 0; b < 2; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
       const double *ap = s_wt + (size_t)g * rs + tg;           // A: row g (+8), layer k0 + tg
-      const int sw = (tg & 1) << 3;                            // k0 is a multiple of 4: layer parity = tg parity
+      const int sw = tg << 2;                                  // k0 is a multiple of 4: layer & 3 = tg
       const double *bp = s_er + (size_t)tg * kMmW;             // B: layer k0 + tg, column 16 warp + g (+8)
       const int cb0 = (16 * warp + g) ^ sw, cb1 = (16 * warp + g + 8) ^ sw;
       const int kend0 = d0 + 8, kend1 = d0 + kMmChunk;
@@ -642,8 +683,9 @@ transit_mma_kernel(DevConfig c, const double *__restrict__ tabs, const double *_
             D2 f;
             f.x = fast_exp_neg(-v.x, s_etab) * bd;
             f.y = fast_exp_neg(-v.y, s_etab) * bd;
-            *reinterpret_cast<D2 *>(s_tau + (size_t)dl * kMmW + col) = v;
-            *reinterpret_cast<D2 *>(s_fd + (size_t)dl * kMmW + col) = f;
+            const int cs = col ^ ((dl & 1) << 3);
+            *reinterpret_cast<D2 *>(s_tau + (size_t)dl * kMmW + cs) = v;
+            *reinterpret_cast<D2 *>(s_fd + (size_t)dl * kMmW + cs) = f;
           }
         }
       }
@@ -653,17 +695,18 @@ transit_mma_kernel(DevConfig c, const double *__restrict__ tabs, const double *_
     if (ch + 1 < nchunks) stage_weights(ch + 1);
     // ---- phase C: one thread per column (same scan as transit_tile_kernel)
     if (t < kMmW && !done) {
-      const double *tc = s_tau + t, *fc = s_fd + t;
+      const double *tc = s_tau, *fc = s_fd;
+      auto at = [&](int j) { return (size_t)j * kMmW + (t ^ ((j & 1) << 3)); };
       int jstop = kMmChunk;
 #pragma unroll
       for (int j = kMmChunk - 1; j >= 0; j--)
-        if (j < dn && tc[(size_t)j * kMmW] > c.toomuch) jstop = j;
+        if (j < dn && tc[at(j)] > c.toomuch) jstop = j;
       const int jl = jstop < dn ? jstop : dn - 1;
       if (KEEP && valid)
-        for (int j = 0; j <= jl; j++) tk[d0 + j] = tc[(size_t)j * kMmW];
+        for (int j = 0; j <= jl; j++) tk[d0 + j] = tc[at(j)];
 #pragma unroll
       for (int j = 0; j < kMmChunk; j++) {
-        const double fd = fc[(size_t)j * kMmW];
+        const double fd = fc[at(j)];
         if (j <= jl) {
           if (!(j & 1) && d0 + j >= 2) {
             const double *row = s_tab + (size_t)(d0 + j) * nf;
@@ -672,8 +715,8 @@ transit_mma_kernel(DevConfig c, const double *__restrict__ tabs, const double *_
           f2 = f1; f1 = fd;
         }
       }
-      tau_prev = jl > 0 ? tc[(size_t)(jl - 1) * kMmW] : tau;
-      tau = tc[(size_t)jl * kMmW];
+      tau_prev = jl > 0 ? tc[at(jl - 1)] : tau;
+      tau = tc[at(jl)];
       if (jstop < dn) { last = d0 + jstop; done = true; }
       if (!done) s_alive[ch & 1] = 1;
     }
@@ -1066,19 +1109,27 @@ static void launch_transit_t(const DevConfig &c, const double *tabs, const doubl
       c, tabs, wts, status, status_col, spectra, tau_keep, last_keep, nmodels, use_tma);
 }
 
+template <int NMOL, int NCIA, bool SC>
+static void launch_transit_mma_sc(const DevConfig &c, const double *tabs, const double *wts,
+                                  const int *status, int *status_col, double *spectra, int nmodels,
+                                  int use_tma, cudaStream_t s) {
+  const size_t smem = transit_mma_smem(c);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaFuncSetAttribute(transit_mma_kernel<NMOL, NCIA, false, SC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = smem;
+  }
+  const int tiles = (c.nwave + kMmW - 1) / kMmW;
+  transit_mma_kernel<NMOL, NCIA, false, SC><<<(unsigned)((size_t)tiles * nmodels), kMmThreads, smem, s>>>(
+      c, tabs, wts, status, status_col, spectra, nullptr, nullptr, nmodels, use_tma);
+}
+static bool g_transit_sc = true;       // set by launch_transit for the launch in progress
 template <int NMOL, int NCIA>
 static void launch_transit_mma_t(const DevConfig &c, const double *tabs, const double *wts,
                                  const int *status, int *status_col, double *spectra, int nmodels,
                                  int use_tma, cudaStream_t s) {
-  const size_t smem = transit_mma_smem(c);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaFuncSetAttribute(transit_mma_kernel<NMOL, NCIA, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
-  }
-  const int tiles = (c.nwave + kMmW - 1) / kMmW;
-  transit_mma_kernel<NMOL, NCIA, false><<<(unsigned)((size_t)tiles * nmodels), kMmThreads, smem, s>>>(
-      c, tabs, wts, status, status_col, spectra, nullptr, nullptr, nmodels, use_tma);
+  if (g_transit_sc) launch_transit_mma_sc<NMOL, NCIA, true>(c, tabs, wts, status, status_col, spectra, nmodels, use_tma, s);
+  else launch_transit_mma_sc<NMOL, NCIA, false>(c, tabs, wts, status, status_col, spectra, nmodels, use_tma, s);
 }
 
 template <int NMOL>
@@ -1108,7 +1159,8 @@ void launch_transit_weights(const DevConfig &c, const double *tabs, double *wts,
 
 void launch_transit(const DevConfig &c, const double *tabs, const double *wts, const int *status,
                     int *status_col, double *spectra, double *tau_keep, int *last_keep,
-                    int nmodels, bool keep, int use_tma, cudaStream_t s) {
+                    int nmodels, bool keep, bool sc, int use_tma, cudaStream_t s) {
+  g_transit_sc = sc;
   if (keep) {   // introspection path: run-time counts, stores tau[] and last[]
     launch_transit_t<0, -1, true>(c, tabs, wts, status, status_col, spectra, tau_keep, last_keep, nmodels, use_tma, s);
     return;

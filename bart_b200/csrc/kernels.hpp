@@ -28,7 +28,7 @@ void launch_transit_weights(const DevConfig &c, const double *tabs, double *wts,
                             bool keep, cudaStream_t s);
 void launch_transit(const DevConfig &c, const double *tabs, const double *wts, const int *status,
                     int *status_col, double *spectra, double *tau_keep, int *last_keep,
-                    int nmodels, bool keep, int use_tma, cudaStream_t s);
+                    int nmodels, bool keep, bool sc, int use_tma, cudaStream_t s);
 void launch_merge_status(int *status, const int *status_col, int nmodels, cudaStream_t s);
 // mol_only: 0 = total extinction, 1 = molecular lines only, 2 = CIA only
 void launch_extinction(const DevConfig &c, const double *tabs, double *ext, int nmodels,

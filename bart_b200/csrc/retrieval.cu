@@ -173,6 +173,37 @@ void launch_convert_params(const ConvConfig &cc, const double *params, int npars
 }
 
 // ---------------------------------------------------------------------------------------
+// Energy balance (BARTfunc.py:366-383): e_out = np.trapz(spectrum, specwn) * 4 (100 Rp)^2 against
+// e_in = sigma Ts^4 Rs^2 pi Rp^2 / a^2 * 1e7 (computed once on the host).  One CTA per model,
+// fixed-shape reduction (deterministic); the comparison is a threshold test, so the summation order
+// (numpy's pairwise sum in the reference) matters only for a model exactly on the threshold.
+__global__ void __launch_bounds__(256)
+energy_balance_kernel(const double *__restrict__ spectra, const double *__restrict__ wn, int nwave,
+                      double out_scale, double e_in, int *__restrict__ status, int nmodels) {
+  const int m = blockIdx.x;
+  if (m >= nmodels || status[m] != 0) return;               // CTA-uniform
+  const double *sp = spectra + (size_t)m * nwave;
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < nwave - 1; i += blockDim.x)
+    acc += (wn[i + 1] - wn[i]) * (sp[i + 1] + sp[i]) / 2.0;
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  __shared__ double s_part[8];
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; w++) t += s_part[w];
+    if (t * out_scale > e_in) status[m] = REJ_ENERGY;
+  }
+}
+
+void launch_energy_balance(const double *spectra, const double *wn, int nwave, double out_scale,
+                           double e_in, int *status, int nmodels, cudaStream_t s) {
+  if (nmodels <= 0) return;
+  energy_balance_kernel<<<nmodels, 256, 0, s>>>(spectra, wn, nwave, out_scale, e_in, status, nmodels);
+}
+
+// ---------------------------------------------------------------------------------------
 // DE-MC proposal (mcmc.py:524-575): jump = gamma1 (x_r1 - x_r2) + fepsilon * support
 __global__ void demc_propose_kernel(McmcDev mc) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;

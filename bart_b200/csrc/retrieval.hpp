@@ -13,7 +13,7 @@
 
 namespace bart {
 
-enum { REJ_TBOUNDS = 16, REJ_ABUND = 32 };
+enum { REJ_TBOUNDS = 16, REJ_ABUND = 32, REJ_ENERGY = 128 };
 enum { PT_ISO = 0, PT_LINE = 1, PT_ADIABATIC = 2 };
 constexpr int kMaxPars = 64;
 
@@ -40,6 +40,12 @@ struct ConvKnobs {
 
 void launch_convert_params(const ConvConfig &cc, const double *params, int npars, double *profiles,
                            int n_in, int *status, const ConvKnobs &kn, int nmodels, cudaStream_t s);
+
+// Energy-balance test of BARTfunc.py:366-383 on the spectra of a batch: a model whose outgoing
+// energy trapz(spectrum, wn) * out_scale exceeds e_in gets REJ_ENERGY (its band fluxes then come
+// out as -1, like every rejected model).  Models already rejected are left alone.
+void launch_energy_balance(const double *spectra, const double *wn, int nwave, double out_scale,
+                           double e_in, int *status, int nmodels, cudaStream_t s);
 
 // DE-MC state (device pointers), one population of `nchains` chains
 struct McmcDev {

@@ -126,6 +126,9 @@ struct State {
   DevBuf<double> d_fweight, d_fstar;
   bool have_star = false;
   double rprs2 = 1.0;
+  // energy-balance rejection (BARTfunc.py:366-383), applied wherever band fluxes are produced
+  bool eb_on = false;
+  double eb_ein = 0.0, eb_scale = 0.0;
   // debug
   bool keep = false;
   int last_batch = 0;
@@ -391,7 +394,7 @@ static void reset_state() {
   G.d_Z.release(); G.d_Zchisq.release(); G.mc_zsize = 0; G.mc_zcap = 0; G.mc_ztemplate.clear();
   if (G.mc_graph) { cudaGraphExecDestroy(G.mc_graph); G.mc_graph = nullptr; }
   G.conv = ConvConfig(); G.mc = McmcDev(); G.mc_ready = false; G.pre_status = nullptr;
-  G.nfilters = 0; G.knob_models = 0; G.last_batch = 0;
+  G.nfilters = 0; G.knob_models = 0; G.last_batch = 0; G.eb_on = false;
   G.cia.clear(); G.wn.clear(); G.angles.clear();
   G.init = false;
 }
@@ -653,11 +656,11 @@ static void launch_models(const double *d_prof, int off, int count, int total, i
     check_launch("atm_prep");
   }
   if (G.lbl) lbl_extinction(d_prof, off, count, n_in);
+  // scattering / cloud terms of the table records (prep_table_row): all zero unless a flag is set
+  const bool sc = k.scat_flag || k.cloudtop || k.scat_flag_all != 0 ||
+                  (k.cloud_flag_all == 1 && k.cloudext_all != 0.0);
   if (c.eclipse) {
     KernelScope ks("eclipse_column");
-    // scattering / cloud terms of the table records (prep_table_row): all zero unless a flag is set
-    const bool sc = k.scat_flag || k.cloudtop || k.scat_flag_all != 0 ||
-                    (k.cloud_flag_all == 1 && k.cloudext_all != 0.0);
     launch_eclipse(c, tabs, status, d_spec, tau, last, count, G.keep, sc, G.use_tma, G.stream);
     check_launch("eclipse_column");
   } else {
@@ -671,7 +674,7 @@ static void launch_models(const double *d_prof, int off, int count, int total, i
     }
     {
       KernelScope ks("transit_column");
-      launch_transit(c, tabs, wts, status, scol, d_spec, tau, last, count, G.keep, G.use_tma, G.stream);
+      launch_transit(c, tabs, wts, status, scol, d_spec, tau, last, count, G.keep, sc, G.use_tma, G.stream);
       check_launch("transit_column");
     }
     launch_merge_status(status, scol, count, G.stream);
@@ -694,6 +697,12 @@ static void band_device(const double *d_spec, int nmodels, const int *d_status, 
     launch_peer_signal(G.pw, G.stream);
     check_launch("peer_signal");
     return;
+  }
+  if (G.eb_on && d_status) {
+    KernelScope ks("energy_balance");
+    launch_energy_balance(d_spec, G.d_wn.p, G.dc.nwave, G.eb_scale, G.eb_ein, const_cast<int *>(d_status),
+                          nmodels, G.stream);
+    check_launch("energy_balance");
   }
   KernelScope ks("band_integrate");
   launch_band_integrate(d_spec, G.d_wn.p, G.d_fstart.p, G.d_fcount.p, G.d_foffset.p, G.d_fweight.p,
@@ -1218,6 +1227,35 @@ int bart_set_filters(int nfilters, const int *start, const int *count, const dou
 }
 
 int bart_nfilters(void) { return G.nfilters; }
+
+int bart_set_energy_balance(int on, double e_in, double out_scale) {
+  API_BEGIN
+  if (on && !(e_in > 0 && out_scale > 0)) fail("bart_set_energy_balance: e_in and out_scale must be positive");
+  G.eb_on = on != 0; G.eb_ein = e_in; G.eb_scale = out_scale;
+  return 0;
+  API_END_INT
+}
+
+int bart_energy_balance(const double *spectra, int nmodels, int nwave, int *rejected) {
+  API_BEGIN
+  if (!G.init || G.opt.justOpacity) fail("Transit init not run, please initialize transit.");
+  if (!G.eb_on) fail("bart_set_energy_balance has not been called");
+  if (nwave != G.dc.nwave) fail("bart_energy_balance: spectra have %d samples, expected %d", nwave, G.dc.nwave);
+  if (nmodels <= 0) return 0;
+  G.d_spec.ensure((size_t)nmodels * nwave);
+  G.d_status.ensure(nmodels);
+  CUDA_OK(cudaMemcpyAsync(G.d_spec.p, spectra, (size_t)nmodels * nwave * 8, cudaMemcpyHostToDevice, G.stream));
+  CUDA_OK(cudaMemsetAsync(G.d_status.p, 0, nmodels * sizeof(int), G.stream));
+  {
+    KernelScope ks("energy_balance");
+    launch_energy_balance(G.d_spec.p, G.d_wn.p, nwave, G.eb_scale, G.eb_ein, G.d_status.p, nmodels, G.stream);
+    check_launch("energy_balance");
+  }
+  CUDA_OK(cudaMemcpyAsync(rejected, G.d_status.p, nmodels * sizeof(int), cudaMemcpyDeviceToHost, G.stream));
+  finish_stream();
+  return 0;
+  API_END_INT
+}
 
 int bart_band_integrate(const double *spectra, int nmodels, int nwave, double *bandflux) {
   API_BEGIN

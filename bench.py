@@ -20,6 +20,7 @@ The line proves itself:
   hr_lookup    the stand-alone opacity-lookup kernel on a 6.4 GB grid (1e5 wavenumbers), the
                kernel the north star's >=70 % of HBM target is about
   latency      small-population generation latency (10 chains, CUDA-graph replay)
+  transit      the transit-geometry configuration (demo BART_transit.cfg shape) on the same GPU
 `--impl reference` times the unmodified reference C (oracle/_ref; else the oracle port) on the host
 cores for the same configuration.
 """
@@ -490,7 +491,7 @@ def main():
             if not parity["ok"]:
                 rc = 1
 
-        hr, builder, latency = None, None, None
+        hr, builder, latency, transit = None, None, None, None
         if extras:
             # the kernel the north star's ">= 70 % of HBM" target is meaningful for: the stand-alone
             # lookup on a grid far larger than the L2 (1e5 wavenumbers, 6.4 GB), one model per launch
@@ -508,6 +509,7 @@ def main():
                                          b["shape"]["nwave"], b["shape"]["wnosamp"]),
                            "per_slice_ms": b["per_slice_ms"]}
             latency = run_tool("bench_latency.py", [])
+            transit = run_tool("bench_transit.py", [])
 
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": W, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
@@ -539,6 +541,8 @@ def main():
             line["builder"] = builder
         if latency is not None:
             line["latency"] = latency
+        if transit is not None:
+            line["transit"] = transit
         if rc:
             line["valid"] = False
         print(json.dumps(line))

@@ -120,6 +120,14 @@ int  bart_run_batch_device(const double *d_profiles, int nmodels, int n_in, doub
 int  bart_set_filters(int nfilters, const int *start, const int *count, const double *weight,
                       const double *star, double rprs);
 int  bart_nfilters(void);            /* filters configured by bart_set_filters (0 before) */
+/* Energy-balance rejection (code/BARTfunc.py:366-383), applied by every call that returns band
+ * fluxes once switched on: a model with trapz(spectrum, wn) * out_scale > e_in is rejected
+ * (BART_REJ_ENERGY, band fluxes -1).  The caller computes e_in = sigma Ts^4 Rs^2 pi Rp^2 / a^2 * 1e7
+ * and out_scale = 4 (100 Rp)^2 (Rp in m) like BARTfunc does.
+ * bart_energy_balance applies the test to host spectra[nmodels][nwave] (rejected[m] = 0 or
+ * BART_REJ_ENERGY): the kernel on its own, for parity tests.                                     */
+int  bart_set_energy_balance(int on, double e_in, double out_scale);
+int  bart_energy_balance(const double *spectra, int nmodels, int nwave, int *rejected);
 int  bart_band_integrate(const double *spectra, int nmodels, int nwave, double *bandflux);
 /* profiles -> band fluxes in one call; spectra never leave the device.
  * bandflux[nmodels][nfilters]; rejected models get -1 in every band (BARTfunc.py:327-330).  */
@@ -197,6 +205,7 @@ int  bart_voigt_profile(int idop, int ilor, float *out, long long capacity, long
 
 #define BART_REJ_TBOUNDS 16  /* temperature profile outside [Tmin, Tmax] (BARTfunc.py:327-330)   */
 #define BART_REJ_ABUND   32  /* sum of metal abundances > 1 (BARTfunc.py:339-344)                */
+#define BART_REJ_ENERGY  128 /* energy balance failed: E_out > E_in (BARTfunc.py:366-383)            */
 
 /* replaces the input-converter set-up of code/BARTfunc.py:139-222.
  * pt_type: 0 PT_iso (1 parameter), 1 PT_line (5: log kappa, log gamma1, log gamma2, alpha, beta;

@@ -195,6 +195,15 @@ class Converter:
         return prof, status, knobs
 
 
+def energy_balance(spectrum, specwn, tstar, rstar, sma, rplanet):
+    """code/BARTfunc.py:366-383: -> (e_in, e_out, rejected).  tstar [K]; rstar, sma, rplanet [m]
+    (BARTfunc.py:169,369-373); sigma from code/constants.py:19."""
+    sig, j2erg = 5.670367e-8, 1e7
+    e_in = sig * tstar ** 4 * rstar ** 2 * np.pi * rplanet ** 2 / sma ** 2 * j2erg
+    e_out = np.sum(np.diff(specwn) * (spectrum[1:] + spectrum[:-1]) / 2.0) * 4 * (rplanet * 100) ** 2
+    return e_in, e_out, bool(e_out > e_in)
+
+
 def chisq(model, data, uncert, prioroff=None, priorlow=None, priorup=None):
     """chisq.c:111-142 + stats.h:72-103: sequential sums, pow(.,2)."""
     c = 0.0

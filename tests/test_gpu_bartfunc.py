@@ -1,0 +1,82 @@
+"""the reference's worker drives the module unchanged.
+
+tests/golden/bartfunc_trace.npz was recorded by running the reference's UNMODIFIED
+code/BARTfunc.py::main(comm) (tests/golden/make_golden_bartfunc.py: stand-in mpi4py master,
+recording transit_module with oracle spectra).  Here the recorded calls -- same names, same order,
+same argument types and shapes -- are replayed on the real CUDA-backed
+bart_b200/python/transit_module, and the band fluxes BARTfunc computed from the returned spectra
+(BARTfunc.py:386-396, with the star / filter arrays wine.py derived) must come out the same."""
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "bartfunc_trace.npz"))
+CALLS = json.loads(str(G["calls"]))
+
+
+def test_recorded_trace_is_the_swig_surface():
+    """CPU: what BARTfunc.main called, against the surface of transit/src/transit.i:12-31."""
+    names = [c[0] for c in CALLS]
+    assert names[:3] == ["transit_init", "get_no_samples", "get_waveno_arr"]
+    assert names[-1] == "free_memory" and names.count("run_transit") == 4
+    init = CALLS[0][1]
+    assert init[0] == {"int": 3} and [list(d.keys())[0] for d in init[1]["list"]] == ["str", "str", "str"]
+    run = [c for c in CALLS if c[0] == "run_transit"][0][1]
+    assert run[0]["dtype"] == "float64" and len(run[0]["ndarray"]) == 1 and run[0]["contiguous"]
+    assert list(run[1].keys()) == ["int"]
+    bf = G["bandflux"]
+    assert bf.shape == (6, 10) and (bf[3] == -1).all() and (bf[4] == -1).all()      # BARTfunc.py:327-344
+    assert (bf[[0, 1, 2, 5]] > 0).all()
+
+
+@pytest.mark.gpu
+def test_replay_on_cuda_transit_module(workdir):
+    from bart_b200 import synth
+    case = synth.make_case(os.path.join(workdir, "bartfunc_case"), **json.loads(str(G["case"])))
+    assert hashlib.sha256(np.fromfile(case["opacity"], dtype=np.uint8).tobytes()).hexdigest() == str(G["grid_sha"])
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bart_b200", "python"))
+    import transit_module as trm                      # the module BARTfunc.py:28-30 imports
+    specwn, rprs = G["specwn"], float(G["rprs"])
+    start, count = G["start"], G["count"]
+    off = np.concatenate([[0], np.cumsum(count)])
+    ok_rows = [i for i in range(len(G["bandflux"])) if G["bandflux"][i, 0] != -1]
+    k = 0
+    nwave = None
+    for name, args in CALLS:
+        if name == "transit_init":
+            argv = ["transit", "-c", case["cfg"]]
+            trm.transit_init(len(argv), argv)
+        elif name == "get_no_samples":
+            nwave = trm.get_no_samples()
+            assert isinstance(nwave, int) and nwave == len(specwn)
+        elif name == "get_waveno_arr":
+            wn = trm.get_waveno_arr(nwave)
+            assert isinstance(wn, np.ndarray) and wn.dtype == np.float64 and np.array_equal(wn, specwn)
+        elif name == "run_transit":
+            prof = np.ascontiguousarray(G["profiles"][k])
+            assert list(prof.shape) == args[0]["ndarray"]
+            spectrum = trm.run_transit(prof, nwave)
+            assert isinstance(spectrum, np.ndarray) and spectrum.shape == (nwave,)
+            band = np.zeros(len(start))
+            for i in range(len(start)):                # BARTfunc.py:386-391 + wine.bandintegrate
+                idx = np.arange(start[i], start[i] + count[i])
+                fluxrat = spectrum[idx] / G["star"][off[i]:off[i + 1]] * rprs * rprs
+                y = fluxrat * G["weight"][off[i]:off[i + 1]]
+                band[i] = np.sum(np.diff(specwn[idx]) * (y[1:] + y[:-1]) / 2.0)
+            ref = G["bandflux"][ok_rows[k]]
+            assert np.max(np.abs(band / ref - 1)) < 1e-8, (k, band, ref)
+            k += 1
+        elif name == "free_memory":
+            # before letting go: the additive batched entry gives the same band fluxes in one call
+            trm.set_filters(start.astype(np.int32), count.astype(np.int32), G["weight"], G["star"], rprs)
+            bf, st = trm.band_flux_batch(np.ascontiguousarray(G["profiles"]), len(start))
+            assert (st == 0).all()
+            assert np.max(np.abs(bf / G["bandflux"][ok_rows] - 1)) < 1e-8
+            trm.free_memory()
+        else:
+            raise AssertionError("the worker called %s, which the replay does not know" % name)
+    assert k == 4

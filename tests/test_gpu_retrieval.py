@@ -277,3 +277,38 @@ def test_grtest_segments_leave_the_chains_unchanged(walk, api, workdir):
     assert np.array_equal(out["allmodel"] == 0, d["allmodel"] == 0)
     assert relerr(out["allmodel"], d["allmodel"]) < 1e-6
     tr.free_memory()
+
+
+@pytest.mark.gpu
+def test_energy_balance_rejection_vs_bartfunc_golden(workdir):
+    """The device energy-balance test (retrieval.cu energy_balance_kernel through
+    bart_energy_balance / bart_set_energy_balance) against code/BARTfunc.py:366-383 run verbatim
+    (tests/golden/ebalance.npz: 16 spectra on the WASP-12b wavenumber grid straddling the
+    threshold), and end to end: a rejected model returns -1 band fluxes and BART_REJ_ENERGY."""
+    import os
+    from bart_b200 import api, synth
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ebalance.npz"))
+    case = synth.make_case(os.path.join(workdir, "w12_eb"), shape="w12", solution="eclipse", seed=2026)
+    tr = api.Transit(case["cfg"])
+    wn = tr.get_waveno_arr()
+    assert np.array_equal(wn, g["specwn"])
+    e_in = tr.set_energy_balance(float(g["tstar"]), float(g["rstar"]), float(g["sma"]), float(g["rplanet"]))
+    assert abs(e_in / g["e_in"][0] - 1) < 1e-14
+    flags = tr.energy_balance(g["spectra"])
+    assert np.array_equal(flags != 0, g["rejected"])
+    assert set(np.unique(flags)) <= {0, api.REJ_ENERGY}
+    # end to end through the band-flux call: the same models with the test off, with a budget no
+    # spectrum can exceed, and with one every spectrum exceeds
+    start, count, weight, star = api.filters_from_files(wn, case["filters"], wn, np.ones_like(wn))
+    tr.set_filters(start, count, weight, star, 0.1)
+    models = synth.make_models(case, 6, seed=3, molfit=("H2O", "CO2", "CO", "CH4"))
+    api._check(api.lib().bart_set_energy_balance(0, 1.0, 1.0))
+    bf0, st0 = tr.bandflux_batch(models)
+    assert (st0 == 0).all() and (bf0 > 0).all()
+    api._check(api.lib().bart_set_energy_balance(1, 1e300, 1.0))
+    bf1, st1 = tr.bandflux_batch(models)
+    assert np.array_equal(bf1, bf0) and (st1 == 0).all()
+    api._check(api.lib().bart_set_energy_balance(1, 1e-300, 1.0))
+    bf2, st2 = tr.bandflux_batch(models)
+    assert (st2 == api.REJ_ENERGY).all() and (bf2 == -1).all()
+    tr.free_memory()

@@ -152,3 +152,20 @@ def test_run_segments_follows_mc3_convergence_logic():
     calls = []
     driver.run_segments(lambda lo, hi: calls.append((lo, hi)) or run(lo, hi), lambda: state["piece"], chainsize)
     assert calls == [(0, chainsize)]
+
+
+def test_energy_balance_oracle_vs_bartfunc_golden():
+    """SURVEY 8 f2, third rejection test: oracle.retrieval_oracle.energy_balance against the
+    statements of code/BARTfunc.py:366-383 executed verbatim with the reference's constants.py /
+    reader.py on the shipped WASP-12b TEP file (tests/golden/ebalance.npz)."""
+    import os
+    import numpy as np
+    from oracle import retrieval_oracle as ro
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ebalance.npz"))
+    assert g["rejected"].sum() == 8 and len(g["rejected"]) == 16
+    for m in range(len(g["rejected"])):
+        e_in, e_out, rej = ro.energy_balance(g["spectra"][m], g["specwn"], float(g["tstar"]), float(g["rstar"]),
+                                             float(g["sma"]), float(g["rplanet"]))
+        assert abs(e_in / g["e_in"][m] - 1) < 1e-14
+        assert abs(e_out / g["e_out"][m] - 1) < 1e-13
+        assert rej == bool(g["rejected"][m])
