@@ -1287,11 +1287,33 @@ int bart_bandflux_batch(const double *profiles, int nmodels, int n_in, double *b
   API_BEGIN
   if (!G.init || G.opt.justOpacity) fail("Transit init not run, please initialize transit.");
   if (nmodels <= 0) return 0;
+  const int nw = G.dc.nwave;
   G.d_prof.ensure((size_t)nmodels * n_in);
-  G.d_spec.ensure((size_t)nmodels * G.dc.nwave);
+  G.d_spec.ensure((size_t)nmodels * nw);
   G.d_band.ensure((size_t)nmodels * std::max(1, G.nfilters));
-  CUDA_OK(cudaMemcpyAsync(G.d_prof.p, profiles, (size_t)nmodels * n_in * 8, cudaMemcpyHostToDevice, G.stream));
-  run_models_device(G.d_prof.p, nmodels, n_in, G.d_spec.p);
+  prepare_batch(nmodels, n_in);
+  // the profiles of chunk k+1 are copied in (copy stream) while chunk k computes; the band
+  // integration and the small copy out follow the last chunk
+  const int nchunks = (G.keep || G.profile || G.lbl || nmodels < 1024) ? 1 : std::max(1, nmodels / 512);
+  while ((int)G.ev_pool.size() < nchunks + 1) {
+    cudaEvent_t e;
+    CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    G.ev_pool.push_back(e);
+  }
+  cudaEvent_t ev_start = G.ev_pool[nchunks];
+  CUDA_OK(cudaEventRecord(ev_start, G.stream));
+  CUDA_OK(cudaStreamWaitEvent(G.s_h2d, ev_start, 0));
+  int off = 0;
+  for (int c = 0; c < nchunks; c++) {
+    const int cnt = nmodels / nchunks + (c < nmodels % nchunks ? 1 : 0);
+    CUDA_OK(cudaMemcpyAsync(G.d_prof.p + (size_t)off * n_in, profiles + (size_t)off * n_in,
+                            (size_t)cnt * n_in * 8, cudaMemcpyHostToDevice, G.s_h2d));
+    CUDA_OK(cudaEventRecord(G.ev_pool[c], G.s_h2d));
+    CUDA_OK(cudaStreamWaitEvent(G.stream, G.ev_pool[c], 0));
+    launch_models(G.d_prof.p + (size_t)off * n_in, off, cnt, nmodels, n_in, G.d_spec.p + (size_t)off * nw);
+    off += cnt;
+  }
+  G.last_batch = nmodels;
   band_device(G.d_spec.p, nmodels, G.d_status.p, G.d_band.p);
   CUDA_OK(cudaMemcpyAsync(bandflux, G.d_band.p, (size_t)nmodels * G.nfilters * 8, cudaMemcpyDeviceToHost, G.stream));
   if (status)
