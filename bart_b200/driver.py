@@ -9,7 +9,8 @@
   (modules/MCcubed/MCcubed/mc/mcmc.py:583-585, code/BARTfunc.py:312,399): chains are split into
   contiguous blocks, one per rank (= one per GPU); every rank evaluates its block as one batch
   and a single all-gather per generation returns every chain's band fluxes to every rank.
-  The communicator is pluggable: `TorchComm` (torch.distributed, gloo on CPU in the tests, nccl
+  The communicator is pluggable: a communicator object with `rank`, `world` and `allgather(local, counts)` (the tests bring a
+  torch.distributed/gloo one, tests/util.py TorchComm; nccl
   on GPUs) or `LibComm` (the library's own NCCL communicator on device buffers).
 
 `BandModel` takes any callable `pt_func(pressure_bar, pt_params) -> T[layers]` (Madhusudhan and
@@ -97,24 +98,6 @@ class BandModel:
             flux[status != 0] = -1.0
             out[ok] = flux
         return out
-
-
-class TorchComm:
-    """All-gather through torch.distributed (backend gloo on CPU, nccl on GPUs)."""
-
-    def __init__(self, dist, device="cpu"):
-        self.dist, self.device = dist, device
-        self.rank, self.world = dist.get_rank(), dist.get_world_size()
-
-    def allgather(self, local, counts):
-        import torch
-        width = local.shape[1]
-        pad = max(counts)
-        buf = torch.zeros((pad, width), dtype=torch.float64, device=self.device)
-        buf[:local.shape[0]] = torch.as_tensor(local, dtype=torch.float64)
-        outs = [torch.zeros_like(buf) for _ in range(self.world)]
-        self.dist.all_gather(outs, buf)
-        return np.concatenate([o[:n].cpu().numpy() for o, n in zip(outs, counts)], axis=0)
 
 
 class LibComm:

@@ -29,7 +29,8 @@ def _worker(rank, world, port, tmp):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    comm = driver.TorchComm(dist)
+    from util import TorchComm
+    comm = TorchComm(dist)
     rng = np.random.default_rng(7)
     for nchains in (10, 7, 2, 1):
         params = rng.uniform(-1, 1, (nchains, 5))

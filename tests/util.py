@@ -48,3 +48,21 @@ def parse_dump(path):
 
 DUMPS = ("tau.dat", "CIA.dat", "mol_extion.dat", "total_extion.dat", "cloud_extion.dat",
          "scatt_extion.dat")
+
+
+class TorchComm:
+    """All-gather through torch.distributed (backend gloo on CPU, nccl on GPUs)."""
+
+    def __init__(self, dist, device="cpu"):
+        self.dist, self.device = dist, device
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+
+    def allgather(self, local, counts):
+        import torch
+        width = local.shape[1]
+        pad = max(counts)
+        buf = torch.zeros((pad, width), dtype=torch.float64, device=self.device)
+        buf[:local.shape[0]] = torch.as_tensor(local, dtype=torch.float64)
+        outs = [torch.zeros_like(buf) for _ in range(self.world)]
+        self.dist.all_gather(outs, buf)
+        return np.concatenate([o[:n].cpu().numpy() for o, n in zip(outs, counts)], axis=0)

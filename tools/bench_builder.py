@@ -22,13 +22,16 @@ ap.add_argument("--ntemp", type=int, default=2, help="temperatures of the slice 
 ap.add_argument("--nlayer", type=int, default=100)
 ap.add_argument("--ethresh", type=float, default=1e-6)
 ap.add_argument("--check", type=int, default=0, help="compare N (layer,T) cells with the builder oracle")
+ap.add_argument("--ntemp-grid", type=int, default=27, help="temperatures of the grid (400 K upwards, 100 K apart)")
+ap.add_argument("--planes", default="", help="comma list of temperature indices to build (default: --ntemp planes spread over the grid)")
 a = ap.parse_args()
 
 tmp = tempfile.mkdtemp(prefix="bart_build_")
 t0 = time.time()
 shape = dict(wnlow=a.wnlow, wnhigh=a.wnhigh, wndelt=a.wndelt, mols=a.mols.split(","), toomuch=10.0)
 case = synth.make_case(tmp, shape=shape, nlayer=a.nlayer, with_grid=False, nlines=a.nlines,
-                       tempdelt=100.0, seed=2026, ethresh=a.ethresh, wnosamp=a.wnosamp)
+                       tempdelt=100.0, thigh=400.0 + 100.0 * (a.ntemp_grid - 1), seed=2026, ethresh=a.ethresh,
+                       wnosamp=a.wnosamp)
 t_gen = time.time() - t0
 L = api.lib()
 # init without building the file: BART_TSLICE=0:0 makes --justOpacity build an empty slice
@@ -41,6 +44,8 @@ nmol = len(shape["mols"])
 nt_all = len(case["grid_temps"])
 # spread the slice over the grid's temperature range (cold and hot planes cost differently)
 picks = sorted(set(int(round(x)) for x in np.linspace(0, nt_all - 1, a.ntemp + 2)[1:-1]))
+if a.planes:
+    picks = [int(x) for x in a.planes.split(",")]
 out = np.zeros((nl, 1, nmol, nw))
 names = ("read_tli_host", "grouping_host", "voigt_table", "kmax", "strength", "widths", "accumulate", "d2h")
 api._check(L.bart_build_opacity_slice(picks[-1], picks[-1] + 1, out.ctypes.data_as(api.dp)))   # warm-up: allocations
