@@ -270,13 +270,15 @@ class Transit:
         return out
 
     # ---- retrieval loop on the device (include/bart_b200.h part 3) -------------------------
-    PT_TYPES = {"iso": 0, "line": 1, "adiabatic": 2}
+    PT_TYPES = {"iso": 0, "line": 1, "adiabatic": 2, "madhu_noinv": 3, "madhu_inv": 4, "piette": 5}
+    PT_NPARS = {"iso": 1, "line": 5, "adiabatic": 3, "madhu_noinv": 5, "madhu_inv": 6, "piette": 8}
 
     def converter_init(self, pressure_bar, species, abundances, molfit, pt_type="line", pt_args=None,
                        tint_type="const", tmin=400.0, tmax=3000.0, nrad=None, ncloud=0, nray=0):
         """Input-converter set-up of code/BARTfunc.py:139-222: `abundances[layer][species]`,
         `pressure_bar[layer]` and `species` as makeatm.readatm returns them; `molfit` the fitted
-        molecule names; pt_args = (R_star, T_star, T_int, sma, gravity) for PT_line."""
+        molecule names; pt_type one of BARTfunc.py:150-155's names; pt_args = (R_star, T_star, T_int,
+        sma, gravity) for PT_line."""
         species = list(species)
         press = np.ascontiguousarray(pressure_bar, dtype=np.float64)
         ab = np.ascontiguousarray(abundances, dtype=np.float64)
@@ -285,7 +287,7 @@ class Transit:
         imol = np.array([species.index(m) for m in molfit], dtype=np.int32)
         imetals = np.array([i for i, s in enumerate(species) if s not in ("H2", "He", "H-", "e-")],
                            dtype=np.int32)
-        npt = {"iso": 1, "line": 5, "adiabatic": 3}[pt_type]
+        npt = self.PT_NPARS[pt_type]
         if nrad is None:
             nrad = 0 if self.eclipse else 1
         args = np.ascontiguousarray(pt_args if pt_args is not None else np.zeros(5), dtype=np.float64)

@@ -507,6 +507,17 @@ __device__ __forceinline__ float ldg_f32(const float *p) {
 // wavenumbers, ms per 2 planes): 1 CTA/SM 716, 2: 390, 3: 307, 4: 266, 5: 258, 6: 257, 8: 295 -- the
 // kernel lives on warps in flight (its inner loop waits on scattered 512-byte profile segments served
 // by the L2), while below 48 registers the spills eat the gain at the W12 shape (9.0 -> 9.3 -> 10.3 ms).
+// What bounds it there (ncu profiles/r02_builder_accumulate_hr_v8.txt: 133 ms per plane, 3.2e11 bin
+// updates): the L1 data stage at 57 % (a warp's 128 bytes of one profile row start at an arbitrary
+// float, so every load is two wavefronts) with the issue slots at 51 %; one update is LDG + F2F + DFMA
+// plus a quarter of the per-group address arithmetic.  Measured and dropped in round 2 (ms per 2
+// planes, against 266-272): (i) every group reading phase 0 of its profile -- the bound of ANY
+// reordering that would make co-resident groups share profile rows in the L1 (sorting the candidate
+// groups by sub-bin phase): 235, i.e. the L2 latency the stall samples point at is worth 14 % at most;
+// (ii) float -> double as one integer multiply-add (bits * 2^29 + bias, exact for the positive normal
+// floats the Voigt pool holds) instead of F2F on the XU pipe: 272 vs 267, the conversion is not the
+// limiter; (iii) splitting a batch into tile-covering and partial groups by ballot masks: 290 (the
+// mask loops lose the unrolled loads); (iv) 256- and 512-bin tiles: 284 and 356.
 #ifndef BART_ACC_MINB
 #define BART_ACC_MINB 4
 #endif

@@ -4,7 +4,9 @@
 //
 //   convert_params_kernel  one CTA per proposal, thread <-> layer: temperature profile (PT_line of
 //                          Line et al. 2013 with E_2 by series / continued fraction, PT_iso,
-//                          PT_adiabatic), abundance scaling 10^p, H2/He renormalisation, the two
+//                          PT_adiabatic; the layer-smoothing models PT_NoInversion / PT_Inversion of
+//                          Madhusudhan & Seager 2009 and PT_piette, with scipy's Gaussian filter
+//                          restated), abundance scaling 10^p, H2/He renormalisation, the two
 //                          rejection tests, per-model radius / cloud-top / scattering knobs.
 //                          Writes the profiles buffer in run_transit's layout, so atm_prep reads it
 //                          unchanged.
@@ -96,6 +98,68 @@ __device__ double pt_temperature(const ConvConfig &cc, const double *par, double
   return pow(0.75 * (ti4 * (2.0 / 3.0 + tau) + tr4 * (1 - alpha) * xi1 + tr4 * alpha * xi2), 0.25);
 }
 
+// Raw (unsmoothed) temperature of the smoothing PT models at one layer.  Arithmetic in the
+// reference's order with separately rounded operations, so that only `log` (<= 1 ulp here,
+// correctly rounded in glibc) can differ from PT.py.  *bad is set for the parameter sets the
+// reference refuses (negative boundary temperatures, PT.py:337-340,543-545).
+__device__ __forceinline__ double sq_rn(double x) { return __dmul_rn(x, x); }
+__device__ double pt_raw_temperature(const ConvConfig &cc, const double *par, int l, int *bad) {
+  const double p = cc.press_bar[l], p0 = cc.p_top;
+  if (cc.pt_type == PT_MADHU_NOINV) {           // a1 a2 p1 p3 T3 (PT.py:384-586)
+    const double a1 = par[0], a2 = par[1], p1 = par[2], p3 = par[3], T3 = par[4];
+    const double T1 = __dsub_rn(T3, sq_rn(log(p3 / p1) / a2));
+    const double T0 = __dsub_rn(T1, sq_rn(log(p1 / p0) / a1));
+    if (T0 < 0 || T1 < 0 || T3 < 0) *bad = 1;
+    if (p >= p0 && p < p1) return __dadd_rn(sq_rn(log(p / p0) / a1), T0);
+    if (p >= p1 && p < p3) return __dadd_rn(sq_rn(log(p / p1) / a2), T1);
+    if (p >= p3 && p <= cc.p_bot) return T3;
+    return 0.0;
+  }
+  if (cc.pt_type == PT_MADHU_INV) {             // a1 a2 p1 p2 p3 T3 (PT.py:157-377)
+    const double a1 = par[0], a2 = par[1], p1 = par[2], p2 = par[3], p3 = par[4], T3 = par[5];
+    const double T2 = __dsub_rn(T3, sq_rn(log(p3 / p2) / a2));
+    const double s10 = sq_rn(log(p1 / p0) / a1);
+    const double T0 = __dsub_rn(__dadd_rn(T2, sq_rn(log(p1 / p2) / -a2)), s10);
+    const double T1 = __dadd_rn(T0, s10);
+    if (T0 < 0 || T1 < 0 || T2 < 0 || T3 < 0) *bad = 1;
+    if (p >= p0 && p < p1) return __dadd_rn(sq_rn(log(p / p0) / a1), T0);
+    if (p >= p1 && p < p2) return __dadd_rn(sq_rn(log(p / p2) / -a2), T2);
+    if (p >= p2 && p < p3) return __dadd_rn(sq_rn(log(p / p2) / a2), T2);
+    if (p >= p3 && p <= cc.p_bot) return T3;
+    return 0.0;
+  }
+  // PT_piette (PT.py:752-812): T0 dTbot_32 dT32_10 dT10_0 dT0_1 dT1_01 dT01_001 dT001_top; knots
+  // top, 10 mbar, 0.1, 1, 3.2, 10, 32 bar, bottom; degree-1 B-spline in log10 p (FITPACK fpbspl, k = 1)
+  double Tn[8];
+  Tn[4] = par[0];
+  Tn[5] = __dadd_rn(par[0], par[3]);
+  Tn[6] = __dadd_rn(Tn[5], par[2]);
+  Tn[7] = __dadd_rn(Tn[6], par[1]);
+  Tn[3] = __dsub_rn(par[0], par[4]);
+  Tn[2] = __dsub_rn(Tn[3], par[5]);
+  Tn[1] = __dsub_rn(Tn[2], par[6]);
+  Tn[0] = __dsub_rn(Tn[1], par[7]);
+  const int k = cc.node_seg[l];
+  const double x = cc.node_x[l], t0 = cc.node_t[k], t1 = cc.node_t[k + 1];
+  const double f = 1.0 / __dsub_rn(t1, t0);
+  return __dadd_rn(__dmul_rn(Tn[k], __dmul_rn(f, __dsub_rn(t1, x))),
+                   __dmul_rn(Tn[k + 1], __dmul_rn(f, __dsub_rn(x, t0))));
+}
+
+// scipy.ndimage.gaussian_filter1d(T, sigma, mode='nearest') at layer l: the symmetric branch of
+// NI_Correlate1D -- centre term first, then the pairs from the outermost inwards, the ends
+// extended with the end values.  Symmetric in the layer order, so it does not matter that the
+// reference smooths the top -> bottom array (BARTfunc.py:176,321).
+__device__ double smooth_nearest(const ConvConfig &cc, const double *T, int l) {
+  const int r = cc.smooth_r, nl = cc.nlayer;
+  double t = __dmul_rn(T[l], cc.smooth_w[r]);
+  for (int j = -r; j < 0; j++) {
+    const int a = max(l + j, 0), b = min(l - j, nl - 1);
+    t = __dadd_rn(t, __dmul_rn(__dadd_rn(T[a], T[b]), cc.smooth_w[r + j]));
+  }
+  return t;
+}
+
 constexpr int kConvThreads = 256;               // two lanes per layer
 __global__ void __launch_bounds__(kConvThreads)
 convert_params_kernel(ConvConfig cc, const double *__restrict__ params, int npars,
@@ -103,6 +167,7 @@ convert_params_kernel(ConvConfig cc, const double *__restrict__ params, int npar
                       ConvKnobs kn, int nmodels) {
   const int m = blockIdx.x;
   if (m >= nmodels) return;
+  extern __shared__ double s_T[];               // [nlayer] raw temperatures (smoothing PT models)
   __shared__ int s_bad;
   __shared__ double s_par[kMaxPars];
   __shared__ double s_fac[kMaxPars];            // 10^p of the abundance parameters
@@ -117,13 +182,24 @@ convert_params_kernel(ConvConfig cc, const double *__restrict__ params, int npar
   __syncthreads();
   double *out = profiles + (size_t)m * n_in;
   int bad = 0;
+  const bool smoothed = cc.pt_type >= PT_MADHU_NOINV;
+  if (smoothed) {
+    int refused = 0;
+    for (int l = threadIdx.x; l < nl; l += blockDim.x) s_T[l] = pt_raw_temperature(cc, s_par, l, &refused);
+    // The reference catches the ValueError and carries on with the profile of the worker's PREVIOUS
+    // proposal ("FINDME: what to do here?", BARTfunc.py:323-325); a batch has no previous proposal,
+    // the model is rejected
+    if (refused) bad |= REJ_PTMODEL;
+    __syncthreads();
+  }
   const int half = threadIdx.x & 1;
   // every lane of a warp runs the same number of passes (the pair exchange is a warp shuffle)
   const int npass = (nl + kConvThreads / 2 - 1) / (kConvThreads / 2);
   for (int pass = 0; pass < npass; pass++) {
     const int l = pass * (kConvThreads / 2) + (threadIdx.x >> 1);
     const bool live = l < nl;
-    const double T = pt_temperature(cc, s_par, cc.press_bar[live ? l : nl - 1], half);
+    const double T = smoothed ? smooth_nearest(cc, s_T, live ? l : nl - 1)
+                              : pt_temperature(cc, s_par, cc.press_bar[live ? l : nl - 1], half);
     if (!live || half) continue;
     if (!(T >= cc.tmin) || !(T <= cc.tmax)) bad |= REJ_TBOUNDS;   // also catches NaN
     out[l] = T;
@@ -149,7 +225,7 @@ convert_params_kernel(ConvConfig cc, const double *__restrict__ params, int npar
   __syncthreads();
   if (threadIdx.x == 0) {
     // the temperature test comes first and wins (BARTfunc.py:327-330 before 339-344)
-    status[m] = (s_bad & REJ_TBOUNDS) ? REJ_TBOUNDS : s_bad;
+    status[m] = (s_bad & REJ_PTMODEL) ? REJ_PTMODEL : (s_bad & REJ_TBOUNDS) ? REJ_TBOUNDS : s_bad;
     int c = cc.npt;
     if (cc.nrad) kn.r0[m] = s_par[c++];
     if (cc.ncloud) kn.cloudtop[m] = s_par[c++];
@@ -169,7 +245,8 @@ void launch_convert_params(const ConvConfig &cc, const double *params, int npars
     cudaMemcpyToSymbol(c_recip, h, sizeof(h));
     table_ready = true;
   }
-  convert_params_kernel<<<nmodels, kConvThreads, 0, s>>>(cc, params, npars, profiles, n_in, status, kn, nmodels);
+  const size_t smem = cc.pt_type >= PT_MADHU_NOINV ? (size_t)cc.nlayer * sizeof(double) : 0;
+  convert_params_kernel<<<nmodels, kConvThreads, smem, s>>>(cc, params, npars, profiles, n_in, status, kn, nmodels);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -13,8 +13,8 @@
 
 namespace bart {
 
-enum { REJ_TBOUNDS = 16, REJ_ABUND = 32, REJ_ENERGY = 128 };
-enum { PT_ISO = 0, PT_LINE = 1, PT_ADIABATIC = 2 };
+enum { REJ_TBOUNDS = 16, REJ_ABUND = 32, REJ_ENERGY = 128, REJ_PTMODEL = 256 };
+enum { PT_ISO = 0, PT_LINE = 1, PT_ADIABATIC = 2, PT_MADHU_NOINV = 3, PT_MADHU_INV = 4, PT_PIETTE = 5 };
 constexpr int kMaxPars = 64;
 
 // Input converter set-up (BARTfunc.py:139-222).  Arrays live on the device.
@@ -30,6 +30,13 @@ struct ConvConfig {
   const double *press_bar;                 // [nlayer] atmosphere-file order (bottom -> top)
   const double *base;                      // [nspec][nlayer] abundances of the atmosphere file
   const double *ratio;                     // [nlayer] H2/He
+  // PT models that smooth over the layers (PT.py:157-586 Madhusudhan & Seager, 752-812 Piette):
+  double p_top, p_bot;                     // min / max pressure (bar)
+  int smooth_r;                            // Gaussian kernel radius, int(4 sigma + 0.5)
+  const double *smooth_w;                  // [2 r + 1] normalised weights
+  const double *node_x;                    // [nlayer] log10 p (Piette's interpolation abscissa)
+  const int *node_seg;                     // [nlayer] knot interval of every layer
+  double node_t[8];                        // Piette's eight knots (log10 p of the node layers)
 };
 
 // per-model knob arrays written by the converter (BARTfunc.py:350-360)

@@ -160,7 +160,8 @@ struct State {
   std::vector<int> h_lbl_status;
   // input converter (retrieval.hpp)
   ConvConfig conv{};
-  DevBuf<double> d_cpress, d_cbase, d_cratio, d_cparams;
+  DevBuf<double> d_cpress, d_cbase, d_cratio, d_cparams, d_csmooth, d_cnodex;
+  DevBuf<int> d_cnodeseg;
   DevBuf<int> d_cstatus;
   const int *pre_status = nullptr;         // converter rejections of the batch being launched
   // DE-MC loop
@@ -386,6 +387,7 @@ static void reset_state() {
   if (G.builder) { builder_free(G.builder); G.builder = nullptr; }
   G.d_lbl_ext.release(); G.d_lbl_dens.release(); G.lbl = false;
   G.d_cpress.release(); G.d_cbase.release(); G.d_cratio.release(); G.d_cparams.release();
+  G.d_csmooth.release(); G.d_cnodex.release(); G.d_cnodeseg.release();
   G.d_cstatus.release(); G.d_mcband.release(); G.d_mcgather.release();
   G.d_mccur.release(); G.d_mcallm.release();
   for (auto &b : G.d_mcd) b.release();
@@ -1665,8 +1667,10 @@ int bart_converter_init(int pt_type, int npt, const double *pt_args, int tint_th
   if (!G.init || G.opt.justOpacity) fail("Transit init not run, please initialize transit.");
   const DevConfig &c = G.dc;
   ConvConfig cc{};
-  const int want = pt_type == PT_ISO ? 1 : pt_type == PT_LINE ? 5 : pt_type == PT_ADIABATIC ? 3 : -1;
-  if (want < 0) fail("unknown PT model %d (0 iso, 1 line, 2 adiabatic)", pt_type);
+  const int want = pt_type == PT_ISO ? 1 : pt_type == PT_LINE ? 5 : pt_type == PT_ADIABATIC ? 3 :
+                   pt_type == PT_MADHU_NOINV ? 5 : pt_type == PT_MADHU_INV ? 6 : pt_type == PT_PIETTE ? 8 : -1;
+  if (want < 0)
+    fail("unknown PT model %d (0 iso, 1 line, 2 adiabatic, 3 madhu_noinv, 4 madhu_inv, 5 piette)", pt_type);
   if (npt != want) fail("PT model %d takes %d parameters, got %d", pt_type, want, npt);
   if (nmolfit < 0 || nmolfit > kMaxGridMol) fail("too many fitted molecules (%d)", nmolfit);
   if (nmetals < 0 || nmetals > kMaxSpec) fail("too many metal species (%d)", nmetals);
@@ -1704,6 +1708,67 @@ int bart_converter_init(int pt_type, int npt, const double *pt_args, int tint_th
   }
   upload(G.d_cpress, press); upload(G.d_cbase, base); upload(G.d_cratio, ratio);
   cc.press_bar = G.d_cpress.p; cc.base = G.d_cbase.p; cc.ratio = G.d_cratio.p;
+  if (pt_type >= PT_MADHU_NOINV) {
+    // the layer-smoothing models: Gaussian kernel of scipy.ndimage.gaussian_filter1d (truncate 4),
+    // sigma = 4 layers (PT.py:372,581) or 0.3 dex (PT.py:810-811)
+    cc.p_top = *std::min_element(press.begin(), press.end());
+    cc.p_bot = *std::max_element(press.begin(), press.end());
+    std::vector<double> x(nl);
+    for (int l = 0; l < nl; l++) x[l] = log10(press[l]);
+    double sigma = 4.0;
+    if (pt_type == PT_PIETTE) {
+      if (nl < 2) fail("PT_piette needs at least two layers");
+      sigma = 0.3 / fabs(x[nl - 1] - x[nl - 2]);           // the reference's p runs top -> bottom
+    }
+    const int r = (int)(4.0 * sigma + 0.5);
+    std::vector<double> w(2 * r + 1);
+    const double c = -0.5 / (sigma * sigma);
+    for (int k = -r; k <= r; k++) w[k + r] = exp(c * (double)(k * k));
+    // numpy's pairwise sum (what phi_x.sum() evaluates)
+    double tot = 0.0;
+    const int n = 2 * r + 1;
+    if (n < 8) { for (int k = 0; k < n; k++) tot += w[k]; }
+    else {
+      double acc[8];
+      for (int j = 0; j < 8; j++) acc[j] = w[j];
+      int k = 8;
+      for (; k < n - (n % 8); k += 8) for (int j = 0; j < 8; j++) acc[j] += w[k + j];
+      tot = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+      for (; k < n; k++) tot += w[k];
+    }
+    if (n > 128) fail("PT smoothing kernel of %d layers is not supported", n);
+    for (auto &v : w) v /= tot;
+    upload(G.d_csmooth, w);
+    cc.smooth_r = r; cc.smooth_w = G.d_csmooth.p;
+    std::vector<int> seg(nl, 0);
+    if (pt_type == PT_PIETTE) {
+      // node layers on the reference's top -> bottom array (np.argmin: first occurrence)
+      auto rev = [&](int i) { return press[nl - 1 - i]; };
+      auto argmin_abs = [&](double target) {
+        int best = 0;
+        for (int i = 1; i < nl; i++) if (fabs(rev(i) - target) < fabs(rev(best) - target)) best = i;
+        return best;
+      };
+      int top = 0, bot = 0;
+      for (int i = 1; i < nl; i++) { if (rev(i) < rev(top)) top = i; if (rev(i) > rev(bot)) bot = i; }
+      const int lay[8] = {top, argmin_abs(0.01), argmin_abs(0.1), argmin_abs(1.0), argmin_abs(3.2),
+                          argmin_abs(10.0), argmin_abs(32.0), bot};
+      for (int k = 0; k < 8; k++) cc.node_t[k] = x[nl - 1 - lay[k]];
+      for (int k = 0; k < 7; k++)
+        if (!(cc.node_t[k + 1] > cc.node_t[k]))
+          fail("PT_piette: the pressure grid does not separate the eight node layers "
+               "(top, 0.01, 0.1, 1, 3.2, 10, 32 bar, bottom)");
+      for (int l = 0; l < nl; l++) {
+        int k = 0;
+        while (k < 6 && x[l] >= cc.node_t[k + 1]) k++;
+        seg[l] = k;
+      }
+    }
+    upload(G.d_cnodex, x);
+    G.d_cnodeseg.ensure(nl);
+    CUDA_OK(cudaMemcpy(G.d_cnodeseg.p, seg.data(), nl * sizeof(int), cudaMemcpyHostToDevice));
+    cc.node_x = G.d_cnodex.p; cc.node_seg = G.d_cnodeseg.p;
+  }
   cc.ready = 1;
   G.conv = cc;
   return 0;

@@ -13,9 +13,9 @@
   torch.distributed/gloo one, tests/util.py TorchComm; nccl
   on GPUs) or `LibComm` (the library's own NCCL communicator on device buffers).
 
-`BandModel` takes any callable `pt_func(pressure_bar, pt_params) -> T[layers]` (Madhusudhan and
-Piette profiles smooth over layers and stay on the caller's side); for the pointwise PT models
-(line, iso, adiabatic) the whole converter runs on the device: `Transit.converter_init` +
+`BandModel` takes any callable `pt_func(pressure_bar, pt_params) -> T[layers]` (a caller's own
+PT model); for the reference's six PT models (BARTfunc.py:150-155: line, iso, adiabatic, and the
+layer-smoothing madhu_noinv, madhu_inv, piette) the whole converter runs on the device: `Transit.converter_init` +
 `Transit.bandflux_from_params`, and `run_demc` below keeps MC3's DE-MC generation loop there too.
 """
 import numpy as np

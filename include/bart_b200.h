@@ -206,10 +206,17 @@ int  bart_voigt_profile(int idop, int ilor, float *out, long long capacity, long
 #define BART_REJ_TBOUNDS 16  /* temperature profile outside [Tmin, Tmax] (BARTfunc.py:327-330)   */
 #define BART_REJ_ABUND   32  /* sum of metal abundances > 1 (BARTfunc.py:339-344)                */
 #define BART_REJ_ENERGY  128 /* energy balance failed: E_out > E_in (BARTfunc.py:366-383)            */
+#define BART_REJ_PTMODEL 256 /* Madhusudhan-Seager parameters the reference's PT.py refuses (negative
+                                boundary temperatures, code/PT.py:337-340,543-545)                  */
 
 /* replaces the input-converter set-up of code/BARTfunc.py:139-222.
  * pt_type: 0 PT_iso (1 parameter), 1 PT_line (5: log kappa, log gamma1, log gamma2, alpha, beta;
- * code/PT.py:589-697), 2 PT_adiabatic (3; PT.py:741-750).  pt_args[5] = {R_star m, T_star K,
+ * code/PT.py:589-697), 2 PT_adiabatic (3; PT.py:741-750), 3 PT_NoInversion (5: a1 a2 p1 p3 T3;
+ * PT.py:384-586), 4 PT_Inversion (6: a1 a2 p1 p2 p3 T3; PT.py:157-377), 5 PT_piette (8: T0 and seven
+ * temperature steps; PT.py:752-812).  Models 3-5 smooth over the layers with
+ * scipy.ndimage.gaussian_filter1d(mode='nearest'), restated on the device (sigma 4 layers, or 0.3 dex
+ * for PT_piette, whose pressure grid must be uniform in log p and separate the eight node layers).
+ * pt_args[5] = {R_star m, T_star K,
  * T_int K, sma m, gravity cm s-2} for PT_line (BARTfunc.py:206-211); tint_thorngren != 0 computes
  * T_int after Thorngren et al. 2019 (PT.py:671-676).  pressure_bar[nlayer] and
  * abundances[nlayer][nspecies] as read from the atmosphere file (bottom -> top).  imol: species

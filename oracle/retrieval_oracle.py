@@ -7,7 +7,13 @@ What is restated, in numpy, the literal way:
 * input converter  code/BARTfunc.py:309-360  (PT profile, abundance scaling, H2/He
   renormalisation, the temperature-bounds and sum-of-metals rejections, the per-model knobs)
 * PT models        code/PT.py:589-739 PT_line + xi (Line et al. 2013 eq. 13-14), PT.py:700-716
-  PT_iso, PT.py:741-750 PT_adiabatic
+  PT_iso, PT.py:741-750 PT_adiabatic, PT.py:157-377 PT_Inversion and 384-586 PT_NoInversion
+  (Madhusudhan & Seager 2009), PT.py:752-812 PT_piette
+* smoothing        third-party: scipy.ndimage.gaussian_filter1d (scipy 1.18.1 here; kernel
+  exp(-x^2 / 2 sigma^2) truncated at int(4 sigma + 0.5) samples and normalised, symmetric
+  correlation centre first then outermost pair inwards, edges extended with the end values:
+  mode='nearest') and the interpolating degree-1 scipy.interpolate.splrep / splev (FITPACK's
+  B-spline basis for k = 1), restated from the published algorithms
 * E_2(x)           third-party: scipy.special.expn (scipy 1.18.1 here; cephes `expn.c`, Moshier):
   power series for x <= 1, continued fraction for x > 1, restated from the published algorithm
 * chi-squared      modules/MCcubed/src_c/chisq.c:111-142 + include/stats.h:72-103 (priors)
@@ -122,7 +128,110 @@ def PT_adiabatic(p, T0, gamma, logp0):
     return T0 / (1 + (gamma - 1) / gamma * np.log(p0 / p))
 
 
-PT_TYPES = {"iso": 0, "line": 1, "adiabatic": 2}
+def gaussian_kernel(sigma):
+    """scipy.ndimage._filters._gaussian_kernel1d (order 0) with truncate = 4."""
+    radius = int(4.0 * float(sigma) + 0.5)
+    x = np.arange(-radius, radius + 1)
+    phi = np.exp(-0.5 / (sigma * sigma) * x ** 2)
+    return phi / phi.sum()
+
+
+def gaussian_filter_nearest(v, sigma):
+    """gaussian_filter1d(v, sigma, mode='nearest'): NI_Correlate1D's symmetric branch."""
+    w = gaussian_kernel(sigma)
+    r = len(w) // 2
+    n = len(v)
+    ext = np.concatenate([np.full(r, v[0]), np.asarray(v, dtype=float), np.full(r, v[-1])])
+    out = np.empty(n)
+    for l in range(n):
+        c = l + r
+        t = ext[c] * w[r]
+        for j in range(-r, 0):
+            t = t + (ext[c + j] + ext[c - j]) * w[r + j]
+        out[l] = t
+    return out
+
+
+class NonPhysical(ValueError):
+    pass
+
+
+def PT_NoInversion(p, a1, a2, p1, p3, T3):
+    """PT.py:384-586 (p: top -> bottom); raises like the reference when T0, T1 or T3 < 0."""
+    p0 = np.amin(p)
+    T1 = T3 - (np.log(p3 / p1) / a2) ** 2.0
+    T0 = T1 - (np.log(p1 / p0) / a1) ** 2.0
+    if T0 < 0 or T1 < 0 or T3 < 0:
+        raise NonPhysical()
+    T = np.zeros(len(p))
+    for i, pi in enumerate(p):
+        if p0 <= pi < p1:
+            T[i] = (np.log(pi / p0) / a1) ** 2 + T0
+        elif p1 <= pi < p3:
+            T[i] = (np.log(pi / p1) / a2) ** 2 + T1
+        elif p3 <= pi <= np.amax(p):
+            T[i] = T3
+    return gaussian_filter_nearest(T, 4)
+
+
+def PT_Inversion(p, a1, a2, p1, p2, p3, T3):
+    """PT.py:157-377."""
+    p0 = np.amin(p)
+    T2 = T3 - (np.log(p3 / p2) / a2) ** 2
+    T0 = T2 + (np.log(p1 / p2) / -a2) ** 2 - (np.log(p1 / p0) / a1) ** 2
+    T1 = T0 + (np.log(p1 / p0) / a1) ** 2
+    if T0 < 0 or T1 < 0 or T2 < 0 or T3 < 0:
+        raise NonPhysical()
+    T = np.zeros(len(p))
+    for i, pi in enumerate(p):
+        if p0 <= pi < p1:
+            T[i] = (np.log(pi / p0) / a1) ** 2 + T0
+        elif p1 <= pi < p2:
+            T[i] = (np.log(pi / p2) / -a2) ** 2 + T2
+        elif p2 <= pi < p3:
+            T[i] = (np.log(pi / p2) / a2) ** 2 + T2
+        elif p3 <= pi <= np.amax(p):
+            T[i] = T3
+    return gaussian_filter_nearest(T, 4)
+
+
+PIETTE_NODES = (0.01, 0.1, 1.0, 3.2, 10.0, 32.0)
+
+
+def piette_layers(p):
+    """PT.py:787-794: the eight node layers (top, 10 mbar, 0.1, 1, 3.2, 10, 32 bar, bottom)."""
+    return np.array([np.argmin(p)] + [np.argmin(np.abs(p - x)) for x in PIETTE_NODES] + [np.argmax(p)])
+
+
+def PT_piette(p, T0, dTbot_32, dT32_10, dT10_0, dT0_1, dT1_01, dT01_001, dT001_top):
+    """PT.py:752-812 (p: top -> bottom, uniform in log p).  Node temperatures, degree-1
+    interpolating B-spline in log10 p (splrep k=1 / splev), Gaussian smoothing of 0.3 dex."""
+    ilays = piette_layers(p)
+    Tn = np.zeros(8)
+    Tn[4] = T0
+    Tn[5] = T0 + dT10_0
+    Tn[6] = Tn[5] + dT32_10
+    Tn[7] = Tn[6] + dTbot_32
+    Tn[3] = T0 - dT0_1
+    Tn[2] = Tn[3] - dT1_01
+    Tn[1] = Tn[2] - dT01_001
+    Tn[0] = Tn[1] - dT001_top
+    x = np.log10(p)
+    t = x[ilays]
+    if np.any(np.diff(t) <= 0):
+        raise ValueError("piette: the pressure grid does not separate the eight node layers")
+    T = np.zeros(len(p))
+    for i, xi_ in enumerate(x):
+        l = min(max(np.searchsorted(t, xi_, side="right") - 1, 0), 6)
+        f = 1.0 / (t[l + 1] - t[l])
+        T[i] = Tn[l] * (f * (t[l + 1] - xi_)) + Tn[l + 1] * (f * (xi_ - t[l]))
+    sig = 0.3 / np.abs(x[0] - x[1])
+    return gaussian_filter_nearest(T, sig)
+
+
+PT_TYPES = {"iso": 0, "line": 1, "adiabatic": 2, "madhu_noinv": 3, "madhu_inv": 4, "piette": 5}
+PT_NPARS = {"iso": 1, "line": 5, "adiabatic": 3, "madhu_noinv": 5, "madhu_inv": 6, "piette": 8}
+REJ_PTMODEL = 256
 
 
 class Converter:
@@ -141,7 +250,7 @@ class Converter:
         self.pt_type, self.pt_args, self.tint_type = pt_type, pt_args, tint_type
         self.tmin, self.tmax = tmin, tmax
         self.nrad, self.ncloud, self.nray = nrad, ncloud, nray
-        self.npt = {"iso": 1, "line": 5, "adiabatic": 3}[pt_type]
+        self.npt = PT_NPARS[pt_type]
         self.npars = self.npt + nrad + ncloud + nray + len(self.imol)
 
     def temperature(self, ptpars):
@@ -151,8 +260,11 @@ class Converter:
             T = PT_line(p, *ptpars, rstar, tstar, tint, sma, grav, self.tint_type)
         elif self.pt_type == "iso":
             T = PT_iso(p, *ptpars)
-        else:
+        elif self.pt_type == "adiabatic":
             T = PT_adiabatic(p, *ptpars)
+        else:
+            T = {"madhu_noinv": PT_NoInversion, "madhu_inv": PT_Inversion,
+                 "piette": PT_piette}[self.pt_type](p, *ptpars)
         return T[::-1]
 
     def profiles(self, params):
@@ -165,7 +277,14 @@ class Converter:
         status = np.zeros(M, dtype=np.int32)
         off = self.npt + self.nrad + self.ncloud + self.nray
         for m in range(M):
-            T = self.temperature(params[m, :self.npt])
+            try:
+                T = self.temperature(params[m, :self.npt])
+            except NonPhysical:
+                # The reference catches the ValueError and goes on with the profile of the worker's
+                # PREVIOUS proposal ("FINDME: what to do here?", BARTfunc.py:323-325); a batch has no
+                # previous proposal: the model is rejected
+                status[m] = REJ_PTMODEL
+                continue
             if np.any(T < self.tmin) or np.any(T > self.tmax) or not np.all(np.isfinite(T)):
                 status[m] = 16
                 continue

@@ -4,6 +4,8 @@ container (neither /root/reference nor the /tmp build exist on the GPU box):
 
   * retrieval_pt.npz      code/PT.py PT_line / PT_iso / PT_adiabatic (imported from
                           /root/reference/code) on seeded parameter draws, incl. scipy's expn(2, x)
+  * retrieval_pt_smooth.npz  code/PT.py PT_NoInversion / PT_Inversion / PT_piette (the models that
+                          smooth over the layers with scipy's gaussian_filter1d)
   * retrieval_conv_*.npz  the per-proposal input converter: the statements of
                           code/BARTfunc.py:320-347 executed verbatim in numpy around the
                           reference's PT_generator
@@ -18,7 +20,7 @@ Shims applied from the outside, none to the reference sources: `numpy.int/float`
 from numpy 2), stub `matplotlib` and `dwt` modules (absent / built on a removed numpy C API; neither
 is used on this path).
 
-    python tests/golden/make_golden_retrieval.py [pt] [conv] [demc] [snooker]
+    python tests/golden/make_golden_retrieval.py [pt] [ptsmooth] [conv] [demc] [snooker]
 """
 import glob
 import os
@@ -82,6 +84,46 @@ def golden_pt(pt):
                         pars=pars, T_const=T_const, T_thorngren=T_thorn, apars=apars, T_adiabatic=T_adia,
                         x=x, expn2=sp.expn(2, x))
     print("retrieval_pt.npz: T range %.0f..%.0f K" % (T_const.min(), T_const.max()))
+
+
+def golden_pt_smooth(pt):
+    """retrieval_pt_smooth.npz: code/PT.py PT_NoInversion / PT_Inversion (Madhusudhan & Seager 2009)
+    and PT_piette on seeded draws, called the way BARTfunc.py:176,321 does (pressure reversed to
+    top -> bottom, the result reversed back to the atmosphere file's order).  Draws the reference
+    refuses (ValueError: negative boundary temperatures) are recorded with phys = 0."""
+    rng = np.random.default_rng(4242)
+    out = {}
+    for tag, pfile in (("a", np.logspace(2, -5, 100)), ("b", np.logspace(2.5, -6, 60))):
+        p = pfile[::-1]                                       # BARTfunc.py:176
+
+        def run(fn, pars):
+            T, ok = np.zeros((len(pars), len(p))), np.zeros(len(pars), dtype=np.int32)
+            for i, q in enumerate(pars):
+                try:
+                    T[i] = pt.PT_generator(p, q, fn)[::-1]
+                    ok[i] = 1
+                except ValueError:
+                    pass
+            return T, ok
+        n = 48
+        noinv = np.column_stack([rng.uniform(0.25, 1.0, n), rng.uniform(0.08, 0.6, n),
+                                 10 ** rng.uniform(-4.5, -1.5, n), 10 ** rng.uniform(-0.5, 1.5, n),
+                                 rng.uniform(900, 2600, n)])
+        noinv[0] = [0.99, 0.19, 1e-3, 1.0, 1500.0]
+        inv = np.column_stack([rng.uniform(0.25, 1.0, n), rng.uniform(0.15, 0.8, n),
+                               10 ** rng.uniform(-4.5, -2.5, n), 10 ** rng.uniform(-2.0, -0.5, n),
+                               10 ** rng.uniform(0.0, 1.5, n), rng.uniform(900, 2600, n)])
+        piette = np.column_stack([rng.uniform(1000, 2200, n)] + [rng.uniform(0, 350, n) for _ in range(7)])
+        out["pressure_" + tag] = pfile
+        for name, fn, pars in (("noinv", pt.PT_NoInversion, noinv), ("inv", pt.PT_Inversion, inv),
+                               ("piette", pt.PT_piette, piette)):
+            T, ok = run(fn, pars)
+            out["%s_pars_%s" % (name, tag)] = pars
+            out["%s_T_%s" % (name, tag)] = T
+            out["%s_phys_%s" % (name, tag)] = ok
+            print("retrieval_pt_smooth %s/%s: %d physical of %d, T %.0f..%.0f K" % (
+                name, tag, ok.sum(), len(ok), T[ok == 1].min(), T[ok == 1].max()))
+    np.savez_compressed(os.path.join(HERE, "retrieval_pt_smooth.npz"), **out)
 
 
 def golden_converter(pt, name, tmp):
@@ -268,6 +310,8 @@ def main():
     mc3 = build_mc3()
     if want("pt"):
         golden_pt(pt)
+    if want("ptsmooth"):
+        golden_pt_smooth(pt)
     if want("gr"):
         golden_gr()
     with tempfile.TemporaryDirectory() as tmp:

@@ -76,6 +76,37 @@ def test_pt_line_thorngren_and_adiabatic(api, workdir):
     tr.free_memory()
 
 
+def test_smoothed_pt_models_on_device(api, workdir):
+    """Madhusudhan-Seager (inverted / non-inverted) and Piette profiles incl. the Gaussian smoothing
+    over the layers, on the device, against code/PT.py (golden) and the oracle; parameter sets
+    PT.py refuses come back as BART_REJ_PTMODEL."""
+    from oracle import retrieval_oracle as ro
+    case, spec, extra, tr = setup(api, "retr_tiny_eclipse", workdir)
+    g = np.load(os.path.join(G, "retrieval_pt_smooth.npz"))
+    assert np.allclose(g["pressure_a"], case["press_bar"], rtol=1e-14)
+    nl = tr.nlayer
+    for name, key in (("madhu_noinv", "noinv"), ("madhu_inv", "inv"), ("piette", "piette")):
+        tr.converter_init(case["press_bar"], case["species"], case["abund"], (), name, tmin=0.0,
+                          tmax=1e9, nrad=0)
+        pars, T, phys = (g["%s_%s_a" % (key, k)] for k in ("pars", "T", "phys"))
+        prof, status, _ = tr.profiles_from_params(pars)
+        assert np.array_equal(status == 256, phys == 0) and np.all(status[phys == 1] == 0)
+        ok = phys == 1
+        assert np.max(np.abs(prof[ok, :nl] / T[ok] - 1)) < 1e-13
+        conv = ro.Converter(case["press_bar"], case["species"], case["abund"], (), name, tmin=0.0, tmax=1e9)
+        oprof, ostatus, _ = conv.profiles(pars)
+        assert np.array_equal(ostatus, status)
+        assert np.max(np.abs(prof[ok] / oprof[ok] - 1)) < 1e-13
+    # temperature bounds act on the smoothed profile (BARTfunc.py:327-330)
+    tr.converter_init(case["press_bar"], case["species"], case["abund"], (), "piette", tmin=400.0,
+                      tmax=3000.0, nrad=0)
+    pars, T, phys = (g["piette_%s_a" % k] for k in ("pars", "T", "phys"))
+    prof, status, _ = tr.profiles_from_params(pars)
+    want = np.where((T < 400.0).any(axis=1) | (T > 3000.0).any(axis=1), 16, 0)
+    assert np.array_equal(status, want) and (want == 0).any() and (want == 16).any()
+    tr.free_memory()
+
+
 @pytest.mark.parametrize("name", list(cases.RETRIEVAL))
 def test_bandflux_from_params_vs_oracle(name, api, workdir):
     """parameters -> band fluxes in one call (one BARTfunc worker iteration) against the oracle

@@ -25,6 +25,39 @@ def test_expn2_and_pt_models_vs_reference():
         assert np.array_equal(ro.PT_adiabatic(p, *q), T)
 
 
+def test_smoothed_pt_models_vs_reference():
+    """PT_NoInversion / PT_Inversion / PT_piette (incl. the restated scipy Gaussian filter and
+    degree-1 spline) against code/PT.py on two pressure grids; the parameter sets PT.py refuses
+    are refused."""
+    g = np.load(os.path.join(G, "retrieval_pt_smooth.npz"))
+    for tag in "ab":
+        p = g["pressure_" + tag][::-1]
+        for name, fn in (("noinv", ro.PT_NoInversion), ("inv", ro.PT_Inversion), ("piette", ro.PT_piette)):
+            pars, T, phys = (g["%s_%s_%s" % (name, k, tag)] for k in ("pars", "T", "phys"))
+            assert phys.sum() >= 30
+            for q, Tref, ok in zip(pars, T, phys):
+                try:
+                    t = fn(p, *q)[::-1]
+                except ro.NonPhysical:
+                    assert not ok
+                    continue
+                assert ok and np.max(np.abs(t - Tref) / Tref) < 2e-15
+
+
+def test_converter_rejects_refused_pt_parameters():
+    g = np.load(os.path.join(G, "retrieval_pt_smooth.npz"))
+    press = g["pressure_a"]
+    nl = len(press)
+    species = ["H2", "He", "H2O"]
+    ab = np.tile([0.85, 0.149, 1e-3], (nl, 1))
+    conv = ro.Converter(press, species, ab, ("H2O",), "madhu_noinv", tmin=0.0, tmax=1e9)
+    pars = np.column_stack([g["noinv_pars_a"], np.zeros(len(g["noinv_pars_a"]))])
+    prof, status, _ = conv.profiles(pars)
+    assert np.array_equal(status == ro.REJ_PTMODEL, g["noinv_phys_a"] == 0) and (status == 0).sum() >= 30
+    ok = status == 0
+    assert np.max(np.abs(prof[ok, :nl] / g["noinv_T_a"][ok] - 1)) < 2e-15
+
+
 @pytest.mark.parametrize("name", list(cases.RETRIEVAL))
 def test_converter_vs_reference(name, workdir):
     case, spec, extra = cases.build_retrieval(name, workdir)
