@@ -98,6 +98,7 @@ def lib():
     L.bart_mcmc_init.argtypes = [C.c_int, C.c_int, dp, dp, dp, dp, dp, dp, C.c_int, dp, dp,
                                  C.c_double, C.c_double, C.c_int]
     L.bart_mcmc_run.argtypes = [C.c_int, dp, ip, ip, dp, dp]
+    L.bart_mcmc_resume.argtypes = [C.c_int, dp]
     L.bart_mcmc_snooker_init.argtypes = [C.c_int, C.c_int, dp]
     L.bart_mcmc_run_snooker.argtypes = [C.c_int, dp, ip, ip, ip, ip, dp, ip, dp, dp]
     L.bart_mcmc_get.restype = C.c_longlong
@@ -336,6 +337,15 @@ class Transit:
                                     float(fgamma), float(fepsilon), int(burnin)))
         self._mc_shape = (nchains, npars, int(np.sum(stepsize > 0)), len(data))
 
+    def mcmc_resume(self, nold, curmodel=None):
+        """MC3's resume=True (mcmc.py:254-269) after mcmc_init with the old run's last states."""
+        if curmodel is not None:
+            curmodel = np.ascontiguousarray(curmodel, dtype=np.float64)
+            nchains, npars, nfree, ndata = self._mc_shape
+            if curmodel.shape != (nchains, ndata):
+                raise BartError("curmodel must be [%d chains][%d data]" % (nchains, ndata))
+        _check(lib().bart_mcmc_resume(int(nold), None if curmodel is None else _d(curmodel)))
+
     def mcmc_run(self, support, r1, r2, unif, ugamma):
         support = np.ascontiguousarray(support, dtype=np.float64)
         unif = np.ascontiguousarray(unif, dtype=np.float64)
@@ -412,6 +422,29 @@ class Transit:
 
 
 # ---- module-level helpers ----
+def bind_to_device_numa(device):
+    """Pin this process to the CPU cores NVML reports as local to GPU `device` (what `numactl` /
+    `mpirun --bind-to` do for a one-process-per-GPU job).  Call it before the library is
+    initialised: pinned host buffers then come from the GPU's own NUMA node and 8 ranks do not
+    funnel their host copies through one socket.  Returns the CPU list, or None when NVML or the
+    affinity call is not available (nothing changes then)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device))
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
+
+
 def device_info():
     name = C.create_string_buffer(256)
     sm, ma, mi = C.c_int(), C.c_int(), C.c_int()

@@ -1295,8 +1295,18 @@ int bart_bandflux_batch(const double *profiles, int nmodels, int n_in, double *b
   G.d_band.ensure((size_t)nmodels * std::max(1, G.nfilters));
   prepare_batch(nmodels, n_in);
   // the profiles of chunk k+1 are copied in (copy stream) while chunk k computes; the band
-  // integration and the small copy out follow the last chunk
-  const int nchunks = (G.keep || G.profile || G.lbl || nmodels < 1024) ? 1 : std::max(1, nmodels / 512);
+  // integration and the small copy out follow the last chunk.  Chunks double from 256 models: the
+  // only copy nothing hides is the first (2 MB), the copy engine then runs ahead of the kernels, and
+  // the last chunk takes whatever is left -- at least half of the batch, so most of the batch runs
+  // as one launch without the tail of a small grid
+  std::vector<int> sizes;
+  if (G.keep || G.profile || G.lbl || nmodels < 1024) sizes.push_back(nmodels);
+  else {
+    int left = nmodels;
+    for (int c = 256; left - c >= 2 * c; c *= 2) { sizes.push_back(c); left -= c; }
+    sizes.push_back(left);
+  }
+  const int nchunks = (int)sizes.size();
   while ((int)G.ev_pool.size() < nchunks + 1) {
     cudaEvent_t e;
     CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -1307,7 +1317,7 @@ int bart_bandflux_batch(const double *profiles, int nmodels, int n_in, double *b
   CUDA_OK(cudaStreamWaitEvent(G.s_h2d, ev_start, 0));
   int off = 0;
   for (int c = 0; c < nchunks; c++) {
-    const int cnt = nmodels / nchunks + (c < nmodels % nchunks ? 1 : 0);
+    const int cnt = sizes[c];
     CUDA_OK(cudaMemcpyAsync(G.d_prof.p + (size_t)off * n_in, profiles + (size_t)off * n_in,
                             (size_t)cnt * n_in * 8, cudaMemcpyHostToDevice, G.s_h2d));
     CUDA_OK(cudaEventRecord(G.ev_pool[c], G.s_h2d));
@@ -1914,6 +1924,23 @@ int bart_mcmc_init(int nchains, int npars, const double *params, const double *p
   finish_stream();
   check_peer_window("bart_mcmc_init");
   G.mc_ready = true;
+  return 0;
+  API_END_INT
+}
+
+// MC3's resume=True for walk='demc' (mcmc.py:254-269): iterations of the previous run count towards
+// burn-in and the savemodel trace continues from the previous run's last column
+int bart_mcmc_resume(int nold, const double *curmodel) {
+  API_BEGIN
+  if (!G.mc_ready) fail("bart_mcmc_init has not been called");
+  McmcDev &mc = G.mc;
+  if (mc.nold != 0 || mc.chainsize != 0) fail("bart_mcmc_resume must come before the first bart_mcmc_run");
+  if (nold < 0) fail("bart_mcmc_resume: nold = %d", nold);
+  mc.nold = nold;
+  if (curmodel)
+    CUDA_OK(cudaMemcpyAsync(G.d_mccur.p, curmodel, (size_t)mc.nchains * mc.ndata * 8,
+                            cudaMemcpyHostToDevice, G.stream));
+  finish_stream();
   return 0;
   API_END_INT
 }

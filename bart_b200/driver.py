@@ -165,16 +165,27 @@ def demc_draws(rng, nchains, chainsize, step_free):
 
 def run_demc(transit, data, uncert, params, pmin, pmax, stepsize, numit, nchains, prior=None,
              priorlow=None, burnin=0, fgamma=1.0, fepsilon=0.0, rng=np.random, draws=None,
-             savefile=None, savemodel=None, grtest=False, grexit=False, thinning=1):
+             savefile=None, savemodel=None, grtest=False, grexit=False, thinning=1, resume=False):
     """`MCcubed.mc.mcmc(..., walk='demc', leastsq=False)` with the whole generation loop on the
     GPU: the host only draws the random streams (once, up front, exactly like mcmc.py does) and
     reads the trace back at the end.  `transit` must have its converter and filters set
     (Transit.converter_init / set_filters).  Returns MC3's arrays: allparams
-    [nchains][nfree][chainsize], the stacked posterior after burn-in, bestp, numaccept, ..."""
+    [nchains][nfree][chainsize], the stacked posterior after burn-in, bestp, numaccept, ...
+    resume=True continues the run whose `savefile` (and `savemodel`) are on disk, like
+    mcmc.py:254-269: chains restart from their last states, the new iterations are appended to the
+    old traces, burn-in and the convergence test count from the old run's first iteration."""
     params = np.atleast_2d(np.array(params, dtype=float))
     pmin, pmax, stepsize = (np.asarray(a, dtype=float) for a in (pmin, pmax, stepsize))
     ifree = np.where(stepsize > 0)[0]
     chainsize = int(np.ceil(numit / nchains))
+    nold, oldparams, oldmodel = 0, None, None
+    if resume:
+        oldparams = np.load(savefile)
+        nold = oldparams.shape[2]
+        if savemodel is not None:
+            oldmodel = np.load(savemodel)
+        params = np.repeat(params[:1], nchains, 0)
+        params[:, ifree] = oldparams[:, :, -1]
     if params.shape[0] != nchains:                                   # mcmc.py:296-306
         params = np.repeat(params, nchains, 0)
         for p in ifree:
@@ -183,6 +194,8 @@ def run_demc(transit, data, uncert, params, pmin, pmax, stepsize, numit, nchains
             params[np.where(params[:, p] > pmax[p]), p] = pmax[p]
     transit.mcmc_init(params, pmin, pmax, stepsize, data, uncert, prior=prior, priorlow=priorlow,
                       fgamma=fgamma, fepsilon=fepsilon, burnin=burnin)
+    if resume:
+        transit.mcmc_resume(nold, None if oldmodel is None else oldmodel[:, :, -1])
     if draws is None:
         draws = demc_draws(rng, nchains, chainsize, stepsize[ifree])
     def run(lo, hi):
@@ -191,7 +204,9 @@ def run_demc(transit, data, uncert, params, pmin, pmax, stepsize, numit, nchains
                          draws["ugamma"][h])
     allp, allm, history, chainlen = run_segments(
         run, lambda: (transit.mcmc_get("allparams"), transit.mcmc_get("allmodel")), chainsize,
-        burnin=burnin, thinning=thinning, grtest=grtest, grexit=grexit)
+        burnin=burnin, thinning=thinning, grtest=grtest, grexit=grexit, nold=nold,
+        old=None if not resume else (oldparams, oldmodel if oldmodel is not None
+                                     else np.zeros((nchains, len(data), nold))))
     out = {k: transit.mcmc_get(k) for k in ("params", "currchisq", "numaccept",
                                             "outbounds", "bestp", "bestmodel", "models")}
     out["allparams"], out["allmodel"], out["psrf"] = allp, allm, history
@@ -221,14 +236,18 @@ def gr_checkpoints(chainsize):
     return [i for i in range(1, chainsize) if (i + 1) % intsteps == 0]
 
 
-def run_segments(run, fetch, chainsize, burnin=0, thinning=1, grtest=False, grexit=False, nold=0):
+def run_segments(run, fetch, chainsize, burnin=0, thinning=1, grtest=False, grexit=False, nold=0,
+                 old=None):
     """Drive a device-resident walk in the segments MC3's loop is observable in (mcmc.py:662-690).
     `run(lo, hi)` advances generations [lo, hi) (state stays on the device); `fetch()` returns that
-    call's allparams / allmodel pieces.  Without grtest it is one segment.  Returns (allparams,
-    allmodel, psrf history [(iteration, psrf)], number of generations run)."""
+    call's allparams / allmodel pieces.  Without grtest it is one segment.  `old` = (allparams,
+    allmodel) of the run being resumed (nold iterations).  Returns (allparams, allmodel, psrf
+    history [(iteration, psrf)], number of iterations in the traces)."""
     cuts = gr_checkpoints(chainsize) if grtest else []
     edges = sorted(set([c + 1 for c in cuts] + [chainsize]))
     pieces_p, pieces_m, history = [], [], []
+    if old is not None:
+        pieces_p.append(old[0]); pieces_m.append(old[1])
     lo, grflag = 0, False
     for hi in edges:
         run(lo, hi)
@@ -246,7 +265,7 @@ def run_segments(run, fetch, chainsize, burnin=0, thinning=1, grtest=False, grex
                 grflag = True
             else:
                 grflag = False
-    return np.concatenate(pieces_p, axis=2), np.concatenate(pieces_m, axis=2), history, lo
+    return np.concatenate(pieces_p, axis=2), np.concatenate(pieces_m, axis=2), history, nold + lo
 
 
 def _save_mc3_files(out, savefile, savemodel):

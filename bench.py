@@ -257,6 +257,11 @@ def main():
 
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     dist = None
+    numa_cpus = None
+    if world > 1 and os.environ.get("BART_BENCH_NUMA", "1") != "0":
+        # one process per GPU: keep each rank (and its pinned host buffers) on its GPU's NUMA node
+        from bart_b200 import api as _api
+        numa_cpus = _api.bind_to_device_numa(local)
     if world > 1:
         import torch
         import torch.distributed as dist
@@ -523,13 +528,19 @@ def main():
                            "l2": "flushed between steps (256 MB write); grid 209 MB > L2",
                            "device": info["name"], "sm_count": info["sm_count"]},
                 "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": M * n_in * 8,
-                        "d2h_bytes_per_step": M * nw * 8 + M * 4,
-                        "path": "bart_run_batch: pinned host profiles -> H2D -> kernels -> D2H spectra"},
-                "e2e_bandflux": {"value": e2b_value, "unit": UNIT, "h2d_bytes_per_step": M * n_in * 8,
-                                 "d2h_bytes_per_step": M * nf * 8 + M * 4,
-                                 "path": "bart_bandflux_batch: pinned host profiles -> H2D -> kernels -> D2H band "
-                                         "fluxes (what BARTfunc.py:386-399 hands to MC3)"},
+                "numa_bound_cpus_rank0": (len(numa_cpus) if numa_cpus else None),
+                # what a BART worker hands to MC3 per proposal is the band fluxes (BARTfunc.py:386-399):
+                # host profiles in, band fluxes out is the end-to-end unit of the retrieval loop
+                "e2e": {"value": e2b_value, "unit": UNIT, "h2d_bytes_per_step": M * n_in * 8,
+                        "d2h_bytes_per_step": M * nf * 8 + M * 4,
+                        "path": "bart_bandflux_batch: pinned host profiles -> H2D -> kernels (forward model + "
+                                "band integration) -> D2H band fluxes + status, i.e. run_transit + "
+                                "BARTfunc.py:386-399 for a batch of proposals"},
+                # the same with the full spectra returned to the host (batched run_transit, 19 KB per
+                # model): at N = 8 this leg is bound by the host's memory system, not by the GPUs
+                "e2e_spectra": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": M * n_in * 8,
+                                "d2h_bytes_per_step": M * nw * 8 + M * 4,
+                                "path": "bart_run_batch: pinned host profiles -> H2D -> kernels -> D2H spectra"},
                 "gpu_launches": int(launches), "kernels": stats, "clocks": clocks}
         if gather is not None:
             line["gather_check"] = gather

@@ -258,6 +258,14 @@ int  bart_mcmc_init(int nchains, int npars, const double *params, const double *
                     const double *pmax, const double *stepsize, const double *prior,
                     const double *priorlow, int ndata, const double *data, const double *uncert,
                     double fgamma, double fepsilon, int burnin);
+/* MC3's `resume` (mcmc.py:254-269) for walk='demc': call bart_mcmc_init with the chains' last
+ * states of the previous run (oldparams[:, :, -1] in the free columns), then this with nold = the
+ * previous run's iterations per chain (they count towards burn-in, mcmc.py:616) and curmodel
+ * [nchains][ndata] = the last column of the previous run's `savemodel` array (a chain whose proposals
+ * are rejected keeps showing it, mcmc.py:649-651; NULL: zeros, as without savemodel).  Before the
+ * first bart_mcmc_run.  (The reference's snooker resume rebuilds its history from the log file's
+ * text and is not offered.)                                                                       */
+int  bart_mcmc_resume(int nold, const double *curmodel);
 /* niter generations without a host round trip.  The random streams are the caller's, in MC3's
  * shapes with chainsize = niter (mcmc.py:484-507): support[niter][nchains][nfree],
  * r1/r2[nchains][niter], unif/ugamma[niter][nchains].                                            */

@@ -342,8 +342,11 @@ def chisq(model, data, uncert, prioroff=None, priorlow=None, priorup=None):
 
 def demc(func, data, uncert, params, pmin, pmax, stepsize, numit, nchains, prior=None,
          priorlow=None, priorup=None, burnin=0, fgamma=1.0, fepsilon=0.0, rng=np.random,
-         draws=None):
-    """walk='demc' of mcmc.py, MPI-mode semantics.  `func(params[nchains][npars]) ->
+         draws=None, resume=None):
+    """walk='demc' of mcmc.py, MPI-mode semantics.  resume = (oldparams[nchains][nfree][nold],
+    oldmodel[nchains][ndata][nold]): mcmc.py:254-269 -- the chains start from the last state of the
+    previous run (no initial jump, no random numbers consumed for it), the traces are appended to the
+    old ones, burn-in counts from the old run's first iteration.  `func(params[nchains][npars]) ->
     models[nchains][ndata]`.  Random numbers are drawn from `rng` in MC3's order (mcmc.py:300,
     484-507) unless `draws` supplies them.  Returns a dict with MC3's arrays."""
     data, uncert = np.asarray(data, float), np.asarray(uncert, float)
@@ -359,6 +362,12 @@ def demc(func, data, uncert, params, pmin, pmax, stepsize, numit, nchains, prior
     ifree = np.where(stepsize > 0)[0]
     ishare = np.where(stepsize < 0)[0]
     gamma = fgamma * 2.4 / np.sqrt(2 * nfree)
+    nold = 0
+    if resume is not None:                                           # mcmc.py:254-267
+        oldparams, oldmodel = (np.asarray(a, float) for a in resume)
+        nold = oldparams.shape[2]
+        params = np.repeat(params, nchains, 0)
+        params[:, ifree] = oldparams[:, :, -1]
     if params.shape[0] != nchains:                                   # mcmc.py:296-306
         params = np.repeat(params, nchains, 0)
         for p in ifree:
@@ -398,6 +407,9 @@ def demc(func, data, uncert, params, pmin, pmax, stepsize, numit, nchains, prior
     allparams = np.zeros((nchains, nfree, chainsize))
     allmodels = np.zeros((chainsize, nchains, ndata))
     allmodel = np.zeros((nchains, ndata, chainsize))          # MC3's savemodel array (mcmc.py:250-252)
+    if resume is not None:
+        allparams = np.dstack((oldparams, allparams))
+        allmodel = np.dstack((oldmodel, allmodel))
     for i in range(chainsize):
         gamma1[ugamma[i] >= 0.1] = gamma
         gamma1[ugamma[i] < 0.1] = 0.98
@@ -420,7 +432,7 @@ def demc(func, data, uncert, params, pmin, pmax, stepsize, numit, nchains, prior
         with np.errstate(over="ignore", invalid="ignore"):
             accept = np.exp(0.5 * (currchisq - nextchisq))
         accepted = accept >= unif[i]
-        if i >= burnin:
+        if nold + i >= burnin:
             numaccept += accepted
         params[accepted] = nextp[accepted]
         currchisq[accepted] = nextchisq[accepted]
@@ -428,12 +440,13 @@ def demc(func, data, uncert, params, pmin, pmax, stepsize, numit, nchains, prior
             bestp = params[np.argmin(c2)].copy()
             bestmodel = models[np.argmin(c2)].copy()
             bestchisq = np.amin(c2)
-        allparams[:, :, i] = params[:, ifree]
+        allparams[:, :, i + nold] = params[:, ifree]
         # mcmc.py:649-651 -- rejected chains keep the previous column; at i = 0 that is column -1,
-        # still zeros, so a chain shows zeros until its first accepted proposal
+        # still zeros, so a chain shows zeros until its first accepted proposal (a resumed run
+        # continues from the old trace's last column)
         cur = models.copy()
-        cur[~accepted] = allmodel[~accepted, :, i - 1]
-        allmodel[:, :, i] = cur
+        cur[~accepted] = allmodel[~accepted, :, i + nold - 1]
+        allmodel[:, :, i + nold] = cur
     return dict(allparams=allparams, params=params, currchisq=currchisq, numaccept=numaccept,
                 outbounds=outbounds, bestp=bestp, bestchisq=bestchisq, bestmodel=bestmodel,
                 params0=params0, allmodels=allmodels, allmodel=allmodel,

@@ -215,8 +215,20 @@ def golden_mc3(mc3, name, tmp):
                       burnin=spec["burnin"], plots=False, savefile=sav, savemodel=savm, log=log)
     allparams = np.load(sav)                       # [nchains][nfree][chainsize] (mcmc.py:842-843)
     allmodel = np.load(savm)                       # [nchains][ndata][chainsize] (mcmc.py:647-651,849-850)
+    # the same run resumed (mcmc.py:254-269): MC3 loads savefile / savemodel, starts every chain from
+    # its last state and appends; a fresh seed for the new random streams
+    np.random.seed(spec["seed"] + 1)
+    log2 = open(os.path.join(tmp, name + "_resume.log"), "w")
+    out2 = mc3.mc.mcmc(data, uncert, band, [], params=np.array(spec["params"]),
+                       pmin=np.array(spec["pmin"]), pmax=np.array(spec["pmax"]),
+                       stepsize=np.array(spec["stepsize"], dtype=float), numit=spec["numit"],
+                       nchains=spec["nchains"], walk="demc", leastsq=False, grtest=False,
+                       burnin=spec["burnin"], plots=False, savefile=sav, savemodel=savm, log=log2,
+                       resume=True)
     np.savez_compressed(os.path.join(HERE, "retrieval_mc3_%s.npz" % name), data=data, uncert=uncert,
-                        allparams=allparams, allstack=out[0], bestp=out[1], allmodel=allmodel)
+                        allparams=allparams, allstack=out[0], bestp=out[1], allmodel=allmodel,
+                        resume_allparams=np.load(sav), resume_allmodel=np.load(savm),
+                        resume_allstack=out2[0], resume_bestp=out2[1])
     print("retrieval_mc3_%s.npz: trace %s, posterior %s, best %s" % (
         name, allparams.shape, out[0].shape, np.array2string(out[1], precision=4)))
 

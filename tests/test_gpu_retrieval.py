@@ -173,6 +173,20 @@ def test_demc_on_device_reproduces_reference_mc3(name, graph, api, workdir, monk
     assert abs(out["bestchisq"] / ref["bestchisq"] - 1) < 1e-6
     assert relerr(out["bestmodel"], ref["bestmodel"]) < 1e-6
     assert relerr(out["models"], ref["allmodels"][-1]) < 1e-6
+    # MC3's resume=True (mcmc.py:254-269) on the files just written, against the reference's own
+    # resumed run: chains restart from their last states, traces are appended
+    np.save(sm, out["allmodel"])
+    np.random.seed(spec["seed"] + 1)
+    res = driver.run_demc(tr, d["data"], d["uncert"], spec["params"], spec["pmin"], spec["pmax"],
+                          spec["stepsize"], spec["numit"], spec["nchains"], burnin=spec["burnin"],
+                          savefile=sf, savemodel=sm, resume=True)
+    assert res["allparams"].shape[2] == 2 * chainsize
+    assert np.array_equal(res["allparams"], d["resume_allparams"])
+    assert np.array_equal(res["allstack"], d["resume_allstack"])
+    assert np.array_equal(res["bestp"], d["resume_bestp"])
+    assert np.array_equal(res["allmodel"] == 0, d["resume_allmodel"] == 0)
+    assert relerr(res["allmodel"], d["resume_allmodel"]) < 1e-6
+    assert np.array_equal(np.load(sf), d["resume_allparams"])
     tr.free_memory()
 
 

@@ -100,6 +100,16 @@ def test_demc_oracle_reproduces_reference_mc3(name, built, workdir):
     assert (d["allmodel"][:, :, 0] == 0).all(axis=1).any()
     nacc = out["numaccept"].sum()
     assert 0 < nacc < spec["numit"]
+    # the run resumed from its own savefile / savemodel (mcmc.py:254-269), new seed
+    np.random.seed(spec["seed"] + 1)
+    out2 = ro.demc(band, d["data"], d["uncert"], spec["params"], spec["pmin"], spec["pmax"],
+                   spec["stepsize"], spec["numit"], spec["nchains"], burnin=spec["burnin"],
+                   resume=(out["allparams"], out["allmodel"]))
+    nold = d["allparams"].shape[2]
+    assert d["resume_allparams"].shape[2] == 2 * nold
+    assert np.array_equal(out2["allparams"], d["resume_allparams"])
+    assert np.array_equal(out2["allmodel"], d["resume_allmodel"])
+    assert np.array_equal(out2["bestp"], d["resume_bestp"])
 
 
 @pytest.mark.parametrize("thinning", [1, 3])
