@@ -39,6 +39,8 @@
 #include <chrono>
 #include <unistd.h>
 #include <fcntl.h>
+#include <cub/device/device_scan.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
 
 namespace bart {
 
@@ -88,6 +90,7 @@ struct BuilderState {
   double *d_gwavn = nullptr;
   std::vector<long long> iso_gbeg;          // [niso+1] group range per isotope
   std::vector<int> h_iown;                  // per-line trace (leader bin, or -2-bin when co-added)
+  int *d_trace = nullptr;                   // the same trace when the grouping ran on the device
   // Voigt table
   int nDop = 0, nLor = 0;
   std::vector<double> aDop, aLor;
@@ -221,6 +224,103 @@ __global__ void line_index_kernel(const double *wl, long long n, double wn_lo, d
   }
   iown_out[i] = iown;
   idwn_out[i] = idwn;
+}
+
+// ---------------------------------------------------------------------------------------
+// Co-add grouping on the device (extinction.c:450-462).  The reference walks the lines once: an
+// in-range line that no earlier leader absorbed leads a group and absorbs the FOLLOWING lines of its
+// isotope while |wavn - owns[iown_leader]| < odwn.  Who leads depends on who led before -- a chain --
+// but the chain breaks wherever a line cannot be absorbed whoever leads before it: with the lines of
+// an isotope sorted (TLI order) the leader's node lies within odwn/2 of a wavenumber >= the previous
+// line's, so a gap of more than 1.5 odwn to the previous line proves a new group (a "definite
+// leader"; so are the first in-range line and an in-range line that opens an isotope).  One thread per
+// definite leader then walks the short stretch to the next one exactly like the reference does.  The
+// result is the reference's grouping for every input the checks accept; unsorted input takes the
+// host walk.
+__global__ void group_check_kernel(const double *wl, const short *iso, const unsigned char *inr,
+                                   long long n, int niso, int *flags, unsigned long long *first_in) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int is = iso[i];
+  int f = 0;
+  if (is < 0 || is >= niso) f |= 1;
+  if (i > 0) {
+    const int ip = iso[i - 1];
+    if (is < ip) f |= 2;
+    if (is == ip && wl[i] < wl[i - 1]) f |= 4;
+  }
+  if (f) atomicOr(flags, f);
+  if (inr[i]) atomicMin(first_in, (unsigned long long)i);
+}
+
+__global__ void group_definite_kernel(const double *wavn, const short *iso, const unsigned char *inr,
+                                      long long n, double odwn, const unsigned long long *first_in,
+                                      unsigned char *dl) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  bool d = false;
+  if (inr[i]) {
+    if (i == 0 || (unsigned long long)i == *first_in || iso[i] != iso[i - 1]) d = true;
+    else {
+      const double w = wavn[i];
+      d = wavn[i - 1] - w > 1.5 * odwn + 1e-10 * fmax(1.0, fabs(w));
+    }
+  }
+  dl[i] = d ? 1 : 0;
+}
+
+// flag bit 0: leads a group; bit 1: member of a group (leader or absorbed)
+__global__ void group_chain_kernel(const double *wavn, const short *iso, const unsigned char *inr,
+                                   const int *iown, const unsigned char *dl, long long n, double wn_lo,
+                                   double odwn, unsigned char *flag, int *trace) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n || !dl[i]) return;
+  long long ln = i;
+  for (;;) {
+    const int io = iown[ln];
+    const short is = iso[ln];
+    const double vnode = __dadd_rn(wn_lo, __dmul_rn((double)io, odwn));
+    flag[ln] = 3; trace[ln] = io;
+    long long e = ln + 1;
+    while (e < n && iso[e] == is && fabs(wavn[e] - vnode) < odwn) { flag[e] = 2; trace[e] = -2 - io; e++; }
+    while (e < n && !inr[e]) e++;                  // out-of-range lines never lead
+    if (e >= n || dl[e]) break;
+    ln = e;
+  }
+}
+
+// first group of every isotope = leaders before the first line whose isotope index is >= k
+__global__ void group_isobeg_kernel(const short *iso, long long n, int niso, const long long *lrank,
+                                    long long ngroups, long long *out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k > niso) return;
+  long long lo = 0, hi = n;
+  while (lo < hi) { const long long mid = (lo + hi) >> 1; if (iso[mid] < k) lo = mid + 1; else hi = mid; }
+  out[k] = lo < n ? lrank[lo] : ngroups;
+}
+
+struct FlagBit {
+  int bit;
+  __host__ __device__ long long operator()(unsigned char f) const { return (f >> bit) & 1; }
+};
+
+__global__ void group_fill_kernel(const double *wavn, const double *elow, const double *gf,
+                                  const short *iso, const int *iown, const int *idwn,
+                                  const unsigned char *flag, const long long *lrank,
+                                  const long long *mrank, long long n, long long *gstart, int *giown,
+                                  int *gidwn, short *giso, double *gwavn, double *c_wavn,
+                                  double *c_elow, double *c_gf) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned char f = flag[i];
+  if (f & 2) {
+    const long long c = mrank[i];
+    c_wavn[c] = wavn[i]; c_elow[c] = elow[i]; c_gf[c] = gf[i];
+    if (f & 1) {
+      const long long g = lrank[i];
+      gstart[g] = c; giown[g] = iown[i]; gidwn[g] = idwn[i]; giso[g] = iso[i]; gwavn[g] = wavn[i];
+    }
+  }
 }
 
 // A PLANE is one temperature: per-isotope factors, the strongest line per output molecule, and
@@ -821,18 +921,195 @@ static void build_profiles(BuilderState *b, const Options &o, cudaStream_t s) {
   b->profiles_ready = true;
 }
 
+// One column slice set of the TLI file -> device, through two pinned staging buffers: the pread of
+// chunk k + 1 (page cache or disk) overlaps the H2D copy of chunk k.  No host copy of the line list
+// is kept (2.6 GB at 1e8 lines).
+struct PinnedStage {
+  static constexpr size_t kBytes = (size_t)64 << 20;
+  char *buf[2] = {nullptr, nullptr};
+  cudaEvent_t ev[2];
+  int k = 0;
+  PinnedStage() {
+    for (int i = 0; i < 2; i++) {
+      BCUDA(cudaMallocHost((void **)&buf[i], kBytes));
+      BCUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+    }
+  }
+  ~PinnedStage() { for (int i = 0; i < 2; i++) { cudaFreeHost(buf[i]); cudaEventDestroy(ev[i]); } }
+};
+
+static void upload_file_column(int fd, const TliLineMap &m, long long col_off, int esize, void *d_dst,
+                               PinnedStage &st, cudaStream_t s) {
+  char *dst = (char *)d_dst;
+  for (size_t i = 0; i < m.count.size(); i++) {
+    long long off = col_off + m.first[i] * esize, left = m.count[i] * esize;
+    while (left > 0) {
+      const size_t chunk = (size_t)std::min<long long>(left, (long long)PinnedStage::kBytes);
+      char *hb = st.buf[st.k];
+      BCUDA(cudaEventSynchronize(st.ev[st.k]));            // the copy that last used this buffer
+      size_t got_total = 0;
+      while (got_total < chunk) {
+        const ssize_t got = pread(fd, hb + got_total, chunk - got_total, (off_t)(off + (long long)got_total));
+        if (got <= 0) fail("TLI file: read failed");
+        got_total += (size_t)got;
+      }
+      BCUDA(cudaMemcpyAsync(dst, hb, chunk, cudaMemcpyHostToDevice, s));
+      BCUDA(cudaEventRecord(st.ev[st.k], s));
+      st.k ^= 1;
+      dst += chunk; off += (long long)chunk; left -= (long long)chunk;
+    }
+  }
+}
+
+// Lines -> device -> indices -> co-add groups, all on the device.  Returns false (nothing kept) when
+// the line list is not sorted within an isotope: the caller then takes the host walk.
+static bool load_lines_device(BuilderState *b, const Options &o, const Tli &t, double lo, double hi_hint,
+                              cudaStream_t s) {
+  auto t0 = std::chrono::steady_clock::now();
+  auto lap = [&](const char *name) {
+    auto now = std::chrono::steady_clock::now();
+    b->phase_ms[name] += std::chrono::duration<double, std::milli>(now - t0).count();
+    t0 = now;
+  };
+  TliLineMap m;
+  map_tli_lines(o.linedb, t, lo, hi_hint, m);
+  const long long n = m.total;
+  const long long na = std::max<long long>(1, n);
+  double *d_wl, *d_elow, *d_gf, *d_wavn;
+  short *d_iso;
+  int *d_iown, *d_idwn, *d_flags, *d_trace;
+  unsigned char *d_inr, *d_dl, *d_flag;
+  unsigned long long *d_first;
+  long long *d_lrank, *d_mrank;
+  BCUDA(cudaMalloc((void **)&d_wl, na * 8)); BCUDA(cudaMalloc((void **)&d_elow, na * 8));
+  BCUDA(cudaMalloc((void **)&d_gf, na * 8)); BCUDA(cudaMalloc((void **)&d_iso, na * 2));
+  {
+    PinnedStage st;
+    const int fd = open(o.linedb.c_str(), O_RDONLY);
+    if (fd < 0) fail("Data file '%s' not found.", o.linedb.c_str());
+    upload_file_column(fd, m, m.wl_off, 8, d_wl, st, s);
+    upload_file_column(fd, m, m.iso_off, 2, d_iso, st, s);
+    upload_file_column(fd, m, m.el_off, 8, d_elow, st, s);
+    upload_file_column(fd, m, m.gf_off, 8, d_gf, st, s);
+    BCUDA(cudaStreamSynchronize(s));
+    close(fd);
+  }
+  lap("read_tli_host");
+  BCUDA(cudaMalloc((void **)&d_wavn, na * 8)); BCUDA(cudaMalloc((void **)&d_iown, na * 4));
+  BCUDA(cudaMalloc((void **)&d_idwn, na * 4)); BCUDA(cudaMalloc((void **)&d_inr, na));
+  BCUDA(cudaMalloc((void **)&d_dl, na)); BCUDA(cudaMalloc((void **)&d_flag, na));
+  BCUDA(cudaMalloc((void **)&d_trace, na * 4));
+  BCUDA(cudaMalloc((void **)&d_flags, 4)); BCUDA(cudaMalloc((void **)&d_first, 8));
+  BCUDA(cudaMalloc((void **)&d_lrank, (na + 1) * 8)); BCUDA(cudaMalloc((void **)&d_mrank, (na + 1) * 8));
+  auto drop = [&](std::initializer_list<void *> ps) { for (void *q : ps) cudaFree(q); };
+  const double own_last = b->wn_lo + (double)(b->nowns - 1) * b->odwn;
+  const unsigned grid = (unsigned)((na + 255) / 256);
+  BCUDA(cudaMemsetAsync(d_flags, 0, 4, s));
+  BCUDA(cudaMemsetAsync(d_first, 0xff, 8, s));
+  BCUDA(cudaMemsetAsync(d_flag, 0, na, s));
+  BCUDA(cudaMemsetAsync(d_trace, 0xff, na * 4, s));                 // -1: in no group
+  int flags = 0;
+  if (n > 0) {
+    line_index_kernel<<<grid, 256, 0, s>>>(d_wl, n, b->wn_lo, own_last, b->odwn, b->dwn, d_wavn, d_iown,
+                                           d_idwn, d_inr);
+    group_check_kernel<<<grid, 256, 0, s>>>(d_wl, d_iso, d_inr, n, b->niso, d_flags, d_first);
+    BCUDA(cudaGetLastError());
+    BCUDA(cudaMemcpyAsync(&flags, d_flags, 4, cudaMemcpyDeviceToHost, s));
+    BCUDA(cudaStreamSynchronize(s));
+  }
+  if (flags & 1) fail("a TLI line has an isotope index outside [0,%d)", b->niso);
+  if (flags & 2) fail("TLI lines are not grouped by isotope");
+  if (flags & 4) {
+    drop({d_wl, d_elow, d_gf, d_iso, d_wavn, d_iown, d_idwn, d_inr, d_dl, d_flag, d_trace, d_flags,
+          d_first, d_lrank, d_mrank});
+    return false;
+  }
+  long long ngroups = 0, nmember = 0;
+  if (n > 0) {
+    group_definite_kernel<<<grid, 256, 0, s>>>(d_wavn, d_iso, d_inr, n, b->odwn, d_first, d_dl);
+    group_chain_kernel<<<grid, 256, 0, s>>>(d_wavn, d_iso, d_inr, d_iown, d_dl, n, b->wn_lo, b->odwn, d_flag,
+                                            d_trace);
+    BCUDA(cudaGetLastError());
+    // ranks of the leaders (group numbers) and of the members (positions in the grouped line
+    // arrays): exclusive sums over n + 1 flags, the last entry being the total
+    cub::TransformInputIterator<long long, FlagBit, const unsigned char *> lead(d_flag, FlagBit{0}),
+        memb(d_flag, FlagBit{1});
+    size_t tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, lead, d_lrank, n, s);
+    void *d_tmp = nullptr;
+    BCUDA(cudaMalloc(&d_tmp, std::max<size_t>(1, tmp_bytes)));
+    cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, lead, d_lrank, n, s);
+    cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, memb, d_mrank, n, s);
+    BCUDA(cudaGetLastError());
+    long long lastr[2];
+    unsigned char lastf = 0;
+    BCUDA(cudaMemcpyAsync(&lastr[0], d_lrank + (n - 1), 8, cudaMemcpyDeviceToHost, s));
+    BCUDA(cudaMemcpyAsync(&lastr[1], d_mrank + (n - 1), 8, cudaMemcpyDeviceToHost, s));
+    BCUDA(cudaMemcpyAsync(&lastf, d_flag + (n - 1), 1, cudaMemcpyDeviceToHost, s));
+    BCUDA(cudaStreamSynchronize(s));
+    cudaFree(d_tmp);
+    ngroups = lastr[0] + (lastf & 1);
+    nmember = lastr[1] + ((lastf >> 1) & 1);
+  }
+  b->nlines = n;
+  b->ngroups = ngroups;
+  BCUDA(cudaMalloc((void **)&b->d_gstart, (ngroups + 1) * 8));
+  BCUDA(cudaMalloc((void **)&b->d_giown, std::max<long long>(1, ngroups) * 4));
+  BCUDA(cudaMalloc((void **)&b->d_gidwn, std::max<long long>(1, ngroups) * 4));
+  BCUDA(cudaMalloc((void **)&b->d_giso, std::max<long long>(1, ngroups) * 2));
+  BCUDA(cudaMalloc((void **)&b->d_gwavn, std::max<long long>(1, ngroups) * 8));
+  BCUDA(cudaMalloc((void **)&b->d_c_wavn, std::max<long long>(1, nmember) * 8));
+  BCUDA(cudaMalloc((void **)&b->d_c_elow, std::max<long long>(1, nmember) * 8));
+  BCUDA(cudaMalloc((void **)&b->d_c_gf, std::max<long long>(1, nmember) * 8));
+  if (n > 0) {
+    group_fill_kernel<<<grid, 256, 0, s>>>(d_wavn, d_elow, d_gf, d_iso, d_iown, d_idwn, d_flag, d_lrank,
+                                           d_mrank, n, b->d_gstart, b->d_giown, b->d_gidwn, b->d_giso,
+                                           b->d_gwavn, b->d_c_wavn, b->d_c_elow, b->d_c_gf);
+    BCUDA(cudaGetLastError());
+  }
+  BCUDA(cudaMemcpyAsync(b->d_gstart + ngroups, &nmember, 8, cudaMemcpyHostToDevice, s));
+  b->iso_gbeg.assign(b->niso + 1, ngroups);
+  if (n > 0) {
+    long long *d_gbeg = nullptr;
+    BCUDA(cudaMalloc((void **)&d_gbeg, (b->niso + 1) * 8));
+    group_isobeg_kernel<<<1, 128, 0, s>>>(d_iso, n, b->niso, d_lrank, ngroups, d_gbeg);
+    BCUDA(cudaGetLastError());
+    BCUDA(cudaMemcpyAsync(b->iso_gbeg.data(), d_gbeg, (b->niso + 1) * 8, cudaMemcpyDeviceToHost, s));
+    BCUDA(cudaStreamSynchronize(s));
+    cudaFree(d_gbeg);
+  }
+  BCUDA(cudaStreamSynchronize(s));
+  b->h_iown.clear();
+  b->d_trace = d_trace;
+  drop({d_wl, d_elow, d_gf, d_iso, d_wavn, d_iown, d_idwn, d_inr, d_dl, d_flag, d_flags, d_first, d_lrank,
+        d_mrank});
+  lap("grouping_device");
+  return true;
+}
+
 static void load_lines(BuilderState *b, const Options &o, Tli &t, const std::vector<double> &wn,
                        cudaStream_t s) {
   if (b->lines_loaded) return;
   double lo = wn.front(), hi_hint;
   // readdatarng selects with the HINTED limits wns.i / wns.f (readlineinfo.c:435-436)
   hi_hint = o.wnhigh > 0 ? o.wnhigh * o.wnfct : 1.0 / (o.wllow * o.wlfct);
+  const char *force_host = getenv("BART_GROUP_HOST");
+  if (!(force_host && atoi(force_host) != 0) && load_lines_device(b, o, t, lo, hi_hint, s)) {
+    b->lines_loaded = true;
+    return;
+  }
   auto tp0 = std::chrono::steady_clock::now();
   read_tli_lines(o.linedb, t, lo, hi_hint);
   auto tp1 = std::chrono::steady_clock::now();
   b->phase_ms["read_tli_host"] += std::chrono::duration<double, std::milli>(tp1 - tp0).count();
   const long long n = (long long)t.wl.size();
   b->nlines = n;
+  auto lap = [&](const char *name, std::chrono::steady_clock::time_point &from) {
+    auto now = std::chrono::steady_clock::now();
+    b->phase_ms[name] += std::chrono::duration<double, std::milli>(now - from).count();
+    from = now;
+  };
+  auto tl = std::chrono::steady_clock::now();
   b->d_wl = dev_upload(t.wl); b->d_elow = dev_upload(t.elow); b->d_gf = dev_upload(t.gf);
   b->d_isoid = dev_upload(t.isoid);
   BCUDA(cudaMalloc((void **)&b->d_wavn, std::max<long long>(1, n) * 8));
@@ -856,6 +1133,7 @@ static void load_lines(BuilderState *b, const Options &o, Tli &t, const std::vec
     BCUDA(cudaMemcpy(idwn.data(), b->d_idwn, n * 4, cudaMemcpyDeviceToHost));
     BCUDA(cudaMemcpy(inr.data(), b->d_inrange, n, cudaMemcpyDeviceToHost));
   }
+  lap("lines_h2d_index_d2h", tl);
   // co-add grouping (extinction.c:450-462): a leader absorbs the following lines of the same
   // isotope while |wavn - owns[iown_leader]| < odwn.  Out-of-range lines never lead, but are
   // absorbed when they follow a leader (the reference does not re-test the range in its while
@@ -896,6 +1174,7 @@ static void load_lines(BuilderState *b, const Options &o, Tli &t, const std::vec
   b->ngroups = (long long)giown.size();
   b->phase_ms["grouping_host"] += std::chrono::duration<double, std::milli>(
       std::chrono::steady_clock::now() - tg0).count();
+  tl = std::chrono::steady_clock::now();
   b->d_gstart = dev_upload(bounds);
   b->d_giown = dev_upload(giown); b->d_gidwn = dev_upload(gidwn); b->d_giso = dev_upload(giso);
   b->d_gwavn = dev_upload(gwavn);
@@ -906,6 +1185,7 @@ static void load_lines(BuilderState *b, const Options &o, Tli &t, const std::vec
                    (void **)&b->d_isoid, (void **)&b->d_iown, (void **)&b->d_idwn, (void **)&b->d_inrange}) {
     cudaFree(*q); *q = nullptr;
   }
+  lap("groups_h2d", tl);
   b->lines_loaded = true;
 }
 
@@ -1231,6 +1511,10 @@ double builder_phase_ms(BuilderState *b, const char *name) {
 }
 
 long long builder_line_bins(BuilderState *b, long long *iown_out, long long capacity) {
+  if (b->h_iown.empty() && b->d_trace && b->nlines > 0) {
+    b->h_iown.resize((size_t)b->nlines);
+    BCUDA(cudaMemcpy(b->h_iown.data(), b->d_trace, (size_t)b->nlines * 4, cudaMemcpyDeviceToHost));
+  }
   const long long n = (long long)b->h_iown.size();
   for (long long i = 0; i < n && i < capacity; i++) iown_out[i] = b->h_iown[i];
   return n;
@@ -1257,7 +1541,7 @@ void builder_free(BuilderState *b) {
   if (!b) return;
   void *ptrs[] = {b->d_wl, b->d_elow, b->d_gf, b->d_wavn, b->d_c_wavn, b->d_c_elow, b->d_c_gf,
                   b->d_isoid, b->d_iown, b->d_idwn, b->d_inrange, b->d_gstart, b->d_giown,
-                  b->d_gidwn, b->d_giso, b->d_gwavn, b->d_prof, b->d_aDop, b->d_aLor,
+                  b->d_gidwn, b->d_giso, b->d_gwavn, b->d_trace, b->d_prof, b->d_aDop, b->d_aLor,
                   b->d_prof_off, b->d_prof_size, b->dens.p, b->out.p};
   for (void *p : ptrs) if (p) cudaFree(p);
   if (b->work) {

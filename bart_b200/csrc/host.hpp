@@ -104,6 +104,16 @@ struct Tli {          // reference: transit/src/readlineinfo.c:87-244,416-537
 };
 void read_tli_header(const std::string &path, Tli &t);
 void read_tli_lines(const std::string &path, Tli &t, double wnlow, double wnhigh);
+// Where the in-range lines sit in the file (readdatarng's per-isotope binary searches,
+// readlineinfo.c:416-537) without reading them: byte offsets of the four columns and, per isotope,
+// the first record and the record count of its slice.
+struct TliLineMap {
+  long long nlines = 0;                     // records in the file
+  long long wl_off = 0, iso_off = 0, el_off = 0, gf_off = 0;   // column starts (bytes)
+  std::vector<long long> first, count;      // per isotope with lines in the file
+  long long total = 0;                      // sum of count
+};
+void map_tli_lines(const std::string &path, const Tli &t, double wnlow, double wnhigh, TliLineMap &m);
 
 struct CiaTable {     // reference: transit/src/crosssec.c:9-268
   std::string file;

@@ -225,7 +225,7 @@ void read_tli_header(const std::string &path, Tli &t) {
 // The line block is memory-mapped: the per-isotope binary searches touch O(log n) pages of the
 // wavelength array and only the selected slices of the four columns are copied, so a 1e8-line TLI
 // (2.6 GB) costs what its in-range part costs.  Selection = readdatarng (readlineinfo.c:416-537).
-void read_tli_lines(const std::string &path, Tli &t, double wnlow, double wnhigh) {
+void map_tli_lines(const std::string &path, const Tli &t, double wnlow, double wnhigh, TliLineMap &m) {
   int fd = open(path.c_str(), O_RDONLY);
   if (fd < 0) fail("Data file '%s' not found.", path.c_str());
   struct stat st;
@@ -247,41 +247,66 @@ void read_tli_lines(const std::string &path, Tli &t, double wnlow, double wnhigh
   std::vector<long long> per(niso);
   memcpy(per.data(), base + pos, (size_t)niso * 8); pos += (long long)niso * 8;
   const long long start = pos;
-  const long long iso_loc = start + nlines * 8, el_loc = iso_loc + nlines * 2,
-                  gf_loc = el_loc + nlines * 8;
-  need(gf_loc, nlines * 8);
+  m = TliLineMap();
+  m.nlines = nlines;
+  m.wl_off = start; m.iso_off = start + nlines * 8; m.el_off = m.iso_off + nlines * 2;
+  m.gf_off = m.el_off + nlines * 8;
+  need(m.gf_off, nlines * 8);
   // the columns are not 8-byte aligned in the file in general: copy through memcpy
   auto wl_at = [&](long long i) { double v; memcpy(&v, base + start + i * 8, 8); return v; };
   const double iniw = 1.0 / wnhigh / 1e-4, finw = 1.0 / wnlow / 1e-4;   // micron
-  t.wl.clear(); t.elow.clear(); t.gf.clear(); t.isoid.clear();
   long long off = 0;
   for (int i = 0; i < niso; i++) {
     const long long n = per[i];
+    long long first = 0, nread = 0;
     if (n > 0) {
       auto w = [&](long long k) { return wl_at(off + k); };
       // datafileBS(..., up=0): binary search then walk down while the previous record >= target
       long long lo = 0, hi = n - 1;
       do { long long loc = (hi + lo) / 2; if (iniw > w(loc)) lo = loc; else hi = loc; } while (hi - lo > 1);
-      long long first = hi;
+      first = hi;
       while (first > 0 && !(w(first - 1) < iniw)) first--;
       // datafileBS(..., up=1): walk up while the next record <= target
       lo = 0; hi = n - 1;
       do { long long loc = (hi + lo) / 2; if (finw > w(loc)) lo = loc; else hi = loc; } while (hi - lo > 1);
       long long last = lo;
       while (last < n - 1 && !(w(last + 1) > finw)) last++;
-      const long long nread = last - first + 1;
-      if (nread > 0) {
-        const size_t b0 = t.wl.size();
-        t.wl.resize(b0 + nread); t.isoid.resize(b0 + nread); t.elow.resize(b0 + nread); t.gf.resize(b0 + nread);
-        memcpy(t.wl.data() + b0, base + start + (off + first) * 8, (size_t)nread * 8);
-        memcpy(t.isoid.data() + b0, base + iso_loc + (off + first) * 2, (size_t)nread * 2);
-        memcpy(t.elow.data() + b0, base + el_loc + (off + first) * 8, (size_t)nread * 8);
-        memcpy(t.gf.data() + b0, base + gf_loc + (off + first) * 8, (size_t)nread * 8);
-      }
+      nread = std::max<long long>(0, last - first + 1);
     }
+    m.first.push_back(off + first);
+    m.count.push_back(nread);
+    m.total += nread;
     off += n;
   }
   munmap(mp, fsize);
+}
+
+void read_tli_lines(const std::string &path, Tli &t, double wnlow, double wnhigh) {
+  TliLineMap m;
+  map_tli_lines(path, t, wnlow, wnhigh, m);
+  int fd = open(path.c_str(), O_RDONLY);
+  if (fd < 0) fail("Data file '%s' not found.", path.c_str());
+  t.wl.assign((size_t)m.total, 0.0); t.elow.assign((size_t)m.total, 0.0); t.gf.assign((size_t)m.total, 0.0);
+  t.isoid.assign((size_t)m.total, 0);
+  auto rd = [&](void *dst, long long off, long long bytes) {
+    char *d = (char *)dst;
+    while (bytes > 0) {
+      const ssize_t got = pread(fd, d, (size_t)bytes, (off_t)off);
+      if (got <= 0) { close(fd); fail("TLI file: read failed"); }
+      d += got; off += got; bytes -= got;
+    }
+  };
+  size_t b0 = 0;
+  for (size_t i = 0; i < m.count.size(); i++) {
+    const long long f = m.first[i], n = m.count[i];
+    if (n <= 0) continue;
+    rd(t.wl.data() + b0, m.wl_off + f * 8, n * 8);
+    rd(t.isoid.data() + b0, m.iso_off + f * 2, n * 2);
+    rd(t.elow.data() + b0, m.el_off + f * 8, n * 8);
+    rd(t.gf.data() + b0, m.gf_off + f * 8, n * 8);
+    b0 += (size_t)n;
+  }
+  close(fd);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -105,6 +105,46 @@ def test_line_bins_million_lines(api, workdir, monkeypatch):
     tr.free_memory()
 
 
+def test_device_grouping_equals_host_walk(api, workdir, monkeypatch):
+    """The co-add grouping on the device (definite leaders + chain walks, streamed TLI upload)
+    against the sequential host walk of extinction.c:450-462 ($BART_GROUP_HOST=1): the per-line trace
+    and the grid planes built from the groups are identical, on a dense line list (0.5 oversampled
+    bins between lines: long chains, a third of the lines co-added) and on a sparse one."""
+    import ctypes as C
+    import os
+    from bart_b200 import synth
+    L = api.lib()
+    for tag, nlines, osamp in (("dense", 300000, 1080), ("sparse", 20000, 2160)):
+        case = synth.make_case(os.path.join(workdir, "grp_" + tag),
+                               shape=dict(wnlow=2000.0, wnhigh=2300.0, wndelt=1.0, mols=["H2O", "CH4"], toomuch=10.0),
+                               nlayer=6, with_grid=False, nlines=nlines, tempdelt=1300.0, seed=99,
+                               ethresh=1e-5, wnosamp=osamp)
+        got = {}
+        for host in ("1", "0"):
+            monkeypatch.setenv("BART_GROUP_HOST", host)
+            monkeypatch.setenv("BART_TSLICE", "0:0")
+            tr = api.Transit(argv=["transit", "-c", case["cfg"], "--justOpacity"])
+            monkeypatch.delenv("BART_TSLICE")
+            nl, nw = tr.nlayer, tr.nwave
+            nmol = 2
+            nlines_c, ngroups_c, neval_c = C.c_longlong(), C.c_longlong(), C.c_longlong()
+            out = np.zeros((nl, 1, nmol, nw))
+            api._check(L.bart_build_opacity_slice(1, 2, out.ctypes.data_as(api.dp)))
+            L.bart_builder_stats(C.byref(nlines_c), C.byref(ngroups_c), C.byref(neval_c))
+            n = nlines_c.value
+            bins = np.zeros(n, dtype=np.int64)
+            assert L.bart_line_bins(bins.ctypes.data_as(C.POINTER(C.c_longlong)), n) == n
+            got[host] = (n, ngroups_c.value, neval_c.value, bins, out)
+            tr.free_memory()
+        h, d = got["1"], got["0"]
+        assert h[0] == d[0] > 0.9 * nlines and h[1] == d[1] and h[2] == d[2]
+        assert np.array_equal(h[3], d[3])
+        assert np.array_equal(h[4], d[4]) and (h[4] > 0).any()
+        nco = int((h[3] <= -2).sum())
+        assert nco > (0.2 * nlines if tag == "dense" else 0)
+    monkeypatch.delenv("BART_GROUP_HOST")
+
+
 def test_temperature_sharded_build(api, workdir):
     """T-sharded build (bart_build_opacity_slice): slices reassemble to the full grid bit for bit."""
     case = cases.build_builder_case("build_ch4", workdir)
