@@ -34,6 +34,9 @@ case = synth.make_case(tmp, shape=shape, nlayer=a.nlayer, with_grid=False, nline
                        wnosamp=a.wnosamp)
 t_gen = time.time() - t0
 L = api.lib()
+t0 = time.time()
+api.device_info()                                   # CUDA initialisation, timed on its own
+t_cuda = time.time() - t0
 # init without building the file: BART_TSLICE=0:0 makes --justOpacity build an empty slice
 os.environ["BART_TSLICE"] = "0:0"
 t0 = time.time()
@@ -65,7 +68,7 @@ dev_ms = sum(after[n] - before[n] for n in ("kmax", "strength", "widths", "accum
 res = {"shape": {"nwave": nw, "nlayer": nl, "ntemp_built": len(picks), "ntemp_grid": nt_all, "nmol": nmol,
                  "wnosamp": a.wnosamp, "wndelt": a.wndelt, "lines_per_bin": a.nlines / nw},
        "nlines_in_range": nlines.value, "ngroups": ngroups.value, "evaluated_group_cells": neval.value,
-       "gen_s": t_gen, "init_s": t_init,
+       "gen_s": t_gen, "cuda_init_s": t_cuda, "init_s": t_init,
        "first_slice_s": t_warm,
        "one_time_ms": {n: L.bart_builder_phase_ms(n.encode()) for n in once},
        "per_slice_ms": {n: after[n] - before[n] for n in names if after[n] - before[n] > 0},

@@ -21,7 +21,9 @@ t0 = time.time()
 for r in range(a.gpus):
     if share[r] == 0:
         continue
-    env = dict(os.environ, BART_DEVICE=str(r))
+    # one process per GPU, each seeing only its own device (CUDA initialisation then does not walk
+    # all eight GPUs in every process)
+    env = dict(os.environ, BART_DEVICE="0", CUDA_VISIBLE_DEVICES=str(r))
     env.pop("LOCAL_RANK", None)
     extra = []
     if a.full:
@@ -40,6 +42,6 @@ print(json.dumps({"n_gpus": a.gpus, "planes_per_rank": share, "nlines": outs[0][
                   "line_cells_per_s_wall": cells / wall, "line_cells_per_s_device": cells / dev,
                   "per_rank_line_cells_per_s_device": [o["line_cells_per_s_device"] for o in outs],
                   "per_rank_wall_s": [o["wall_s"] for o in outs], "per_rank_gen_s": [o["gen_s"] for o in outs],
-                  "per_rank_init_s": [o["init_s"] for o in outs], "one_time_ms_rank0": outs[0]["one_time_ms"],
+                  "per_rank_init_s": [o["init_s"] for o in outs], "per_rank_cuda_init_s": [o.get("cuda_init_s") for o in outs], "one_time_ms_rank0": outs[0]["one_time_ms"],
                   "per_slice_ms_rank0": outs[0]["per_slice_ms"], "full_config": bool(a.full),
                   "elapsed_incl_init_s": t_all}))
