@@ -947,12 +947,7 @@ static void upload_file_column(int fd, const TliLineMap &m, long long col_off, i
       const size_t chunk = (size_t)std::min<long long>(left, (long long)PinnedStage::kBytes);
       char *hb = st.buf[st.k];
       BCUDA(cudaEventSynchronize(st.ev[st.k]));            // the copy that last used this buffer
-      size_t got_total = 0;
-      while (got_total < chunk) {
-        const ssize_t got = pread(fd, hb + got_total, chunk - got_total, (off_t)(off + (long long)got_total));
-        if (got <= 0) fail("TLI file: read failed");
-        got_total += (size_t)got;
-      }
+      if (!parallel_pread(fd, hb, chunk, off)) fail("TLI file: read failed");
       BCUDA(cudaMemcpyAsync(dst, hb, chunk, cudaMemcpyHostToDevice, s));
       BCUDA(cudaEventRecord(st.ev[st.k], s));
       st.k ^= 1;

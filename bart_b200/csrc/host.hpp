@@ -114,6 +114,10 @@ struct TliLineMap {
   long long total = 0;                      // sum of count
 };
 void map_tli_lines(const std::string &path, const Tli &t, double wnlow, double wnhigh, TliLineMap &m);
+// pread of `bytes` at file offset `off` into `dst`, split over a few threads (one thread copies out
+// of the page cache at 2-3 GB/s; the staging buffers of the grid and line-list uploads are filled
+// several times faster this way).  Returns false on a short read.
+bool parallel_pread(int fd, void *dst, size_t bytes, long long off);
 
 struct CiaTable {     // reference: transit/src/crosssec.c:9-268
   std::string file;

@@ -13,6 +13,8 @@
 #include <fstream>
 #include <sstream>
 #include <algorithm>
+#include <thread>
+#include <atomic>
 
 namespace bart {
 
@@ -225,6 +227,31 @@ void read_tli_header(const std::string &path, Tli &t) {
 // The line block is memory-mapped: the per-isotope binary searches touch O(log n) pages of the
 // wavelength array and only the selected slices of the four columns are copied, so a 1e8-line TLI
 // (2.6 GB) costs what its in-range part costs.  Selection = readdatarng (readlineinfo.c:416-537).
+bool parallel_pread(int fd, void *dst, size_t bytes, long long off) {
+  auto part = [fd](char *d, size_t n, long long o) {
+    while (n > 0) {
+      const ssize_t got = pread(fd, d, n, (off_t)o);
+      if (got <= 0) return false;
+      d += got; o += got; n -= (size_t)got;
+    }
+    return true;
+  };
+  int nthr = 4;
+  if (const char *e = getenv("BART_IO_THREADS")) nthr = std::max(1, std::min(16, atoi(e)));
+  if (bytes < ((size_t)4 << 20) || nthr == 1) return part((char *)dst, bytes, off);
+  const size_t per = ((bytes + nthr - 1) / nthr + 4095) & ~(size_t)4095;
+  std::atomic<bool> ok(true);
+  std::vector<std::thread> th;
+  for (int k = 0; k < nthr; k++) {
+    const size_t b0 = (size_t)k * per;
+    if (b0 >= bytes) break;
+    const size_t n = std::min(per, bytes - b0);
+    th.emplace_back([&, b0, n] { if (!part((char *)dst + b0, n, off + (long long)b0)) ok = false; });
+  }
+  for (auto &t : th) t.join();
+  return ok;
+}
+
 void map_tli_lines(const std::string &path, const Tli &t, double wnlow, double wnhigh, TliLineMap &m) {
   int fd = open(path.c_str(), O_RDONLY);
   if (fd < 0) fail("Data file '%s' not found.", path.c_str());

@@ -23,6 +23,7 @@
 #include <map>
 #include <algorithm>
 #include <unistd.h>
+#include <fcntl.h>
 #include <sys/stat.h>
 
 namespace bart {
@@ -323,9 +324,9 @@ static void load_grid_to_device(const std::string &path) {
   const size_t cell_in = (size_t)g.nmol * g.nwave, cell_out = (size_t)gms * g.nwave;
   G.d_grid.ensure(ncell * cell_out + (size_t)kEclPad * gms);   // + padding (kernels.hpp kEclPad)
   CUDA_OK(cudaMemsetAsync(G.d_grid.p + ncell * cell_out, 0, (size_t)kEclPad * gms * sizeof(double), G.stream));
-  FILE *f = fopen(path.c_str(), "rb");
-  if (!f) fail("Opening opacity file '%s' failed.", path.c_str());
-  fseek(f, g.data_offset, SEEK_SET);
+  const int fd = open(path.c_str(), O_RDONLY);
+  if (fd < 0) fail("Opening opacity file '%s' failed.", path.c_str());
+  long long fpos = g.data_offset;
   // stream whole (layer, temperature) cells through two pinned staging buffers (files reach tens
   // of GB at high resolution); each chunk is re-laid out on the device while the next is read
   const size_t cells_per_chunk = std::max<size_t>(1, (size_t)(64u << 20) / (cell_in * 8));
@@ -345,7 +346,8 @@ static void load_grid_to_device(const std::string &path) {
     const size_t nc = std::min(cells_per_chunk, ncell - cell);
     const size_t want = nc * cell_in * 8;
     CUDA_OK(cudaEventSynchronize(done_ev[which]));           // staging buffer free again
-    if (fread(stage[which], 1, want, f) != want) { bad = true; break; }
+    if (!parallel_pread(fd, stage[which], want, fpos)) { bad = true; break; }
+    fpos += (long long)want;
     CUDA_OK(cudaMemcpyAsync(d_stage[which].p, stage[which], want, cudaMemcpyHostToDevice, G.stream));
     launch_grid_relayout(d_stage[which].p, G.d_grid.p + cell * cell_out, (int)nc, (int)g.nmol, gms,
                          (int)g.nwave, G.stream);
@@ -355,7 +357,7 @@ static void load_grid_to_device(const std::string &path) {
   }
   cudaStreamSynchronize(G.stream);
   for (int i = 0; i < 2; i++) { cudaFreeHost(stage[i]); d_stage[i].release(); cudaEventDestroy(done_ev[i]); }
-  fclose(f);
+  close(fd);
   if (bad) fail("Opacity file '%s' is truncated.", path.c_str());
   check_launch("grid_relayout");
 }
