@@ -269,6 +269,20 @@ def test_batch_properties_w12_shape(api, workdir):
             assert (col[:-1] <= 10.0).all()
             assert col[-1] > 10.0 or last[w] == tr.nlayer - 1
     tr.debug_keep(False)
+    # the pipelined host paths (>= 1024 models: chunked H2D / kernels / D2H on three streams) give
+    # the bits of plain small calls, with a rejected model inside a chunk, for both entry points
+    wn = tr.get_waveno_arr()
+    tr.set_filters(*api.filters_from_files(wn, case["filters"], wn, np.ones_like(wn)), 0.1)
+    big = np.tile(models, (25, 1))[:1100].copy()
+    big[700, :tr.nlayer] = 5000.0                      # outside the opacity grid's temperatures
+    sp_big, st_big = tr.run_batch(big)
+    bf_big, st_bf = tr.bandflux_batch(big)
+    assert st_big[700] != 0 and (np.delete(st_big, 700) == 0).all() and np.array_equal(st_big, st_bf)
+    assert (sp_big[700] == -1.0).all() and (bf_big[700] == -1.0).all()
+    ok = np.arange(1100) != 700
+    assert np.array_equal(sp_big[ok], np.tile(spectra, (25, 1))[:1100][ok])
+    bf_small, _ = tr.bandflux_batch(models)
+    assert np.array_equal(bf_big[ok], np.tile(bf_small, (25, 1))[:1100][ok])
     tr.free_memory()
 
 
