@@ -270,13 +270,18 @@ __global__ void group_definite_kernel(const double *wavn, const short *iso, cons
 }
 
 // flag bit 0: leads a group; bit 1: member of a group (leader or absorbed)
+// A line list so dense that definite leaders are rare (many lines per oversampled bin everywhere)
+// would leave one thread walking millions of lines: a walk longer than kChainLimit lines raises
+// *too_long and the caller takes the host walk instead.
+constexpr long long kChainLimit = 1 << 16;
 __global__ void group_chain_kernel(const double *wavn, const short *iso, const unsigned char *inr,
                                    const int *iown, const unsigned char *dl, long long n, double wn_lo,
-                                   double odwn, unsigned char *flag, int *trace) {
+                                   double odwn, unsigned char *flag, int *trace, int *too_long) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= n || !dl[i]) return;
   long long ln = i;
   for (;;) {
+    if (ln - i > kChainLimit) { *too_long = 1; return; }
     const int io = iown[ln];
     const short is = iso[ln];
     const double vnode = __dadd_rn(wn_lo, __dmul_rn((double)io, odwn));
@@ -1022,9 +1027,17 @@ static bool load_lines_device(BuilderState *b, const Options &o, const Tli &t, d
   long long ngroups = 0, nmember = 0;
   if (n > 0) {
     group_definite_kernel<<<grid, 256, 0, s>>>(d_wavn, d_iso, d_inr, n, b->odwn, d_first, d_dl);
+    BCUDA(cudaMemsetAsync(d_flags, 0, 4, s));
     group_chain_kernel<<<grid, 256, 0, s>>>(d_wavn, d_iso, d_inr, d_iown, d_dl, n, b->wn_lo, b->odwn, d_flag,
-                                            d_trace);
+                                            d_trace, d_flags);
     BCUDA(cudaGetLastError());
+    BCUDA(cudaMemcpyAsync(&flags, d_flags, 4, cudaMemcpyDeviceToHost, s));
+    BCUDA(cudaStreamSynchronize(s));
+    if (flags) {                                   // too dense for the chain walks: host path
+      drop({d_wl, d_elow, d_gf, d_iso, d_wavn, d_iown, d_idwn, d_inr, d_dl, d_flag, d_trace, d_flags,
+            d_first, d_lrank, d_mrank});
+      return false;
+    }
     // ranks of the leaders (group numbers) and of the members (positions in the grouped line
     // arrays): exclusive sums over n + 1 flags, the last entry being the total
     cub::TransformInputIterator<long long, FlagBit, const unsigned char *> lead(d_flag, FlagBit{0}),

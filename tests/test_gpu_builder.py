@@ -114,9 +114,12 @@ def test_device_grouping_equals_host_walk(api, workdir, monkeypatch):
     import os
     from bart_b200 import synth
     L = api.lib()
-    for tag, nlines, osamp in (("dense", 300000, 1080), ("sparse", 20000, 2160)):
+    # "extreme": 40 lines per oversampled bin, no definite leader for > 65536 lines -- the device
+    # path gives up and the library takes the host walk by itself
+    for tag, nlines, osamp, wnhigh in (("dense", 300000, 1080, 2300.0), ("sparse", 20000, 2160, 2300.0),
+                                       ("extreme", 250000, 120, 2050.0)):
         case = synth.make_case(os.path.join(workdir, "grp_" + tag),
-                               shape=dict(wnlow=2000.0, wnhigh=2300.0, wndelt=1.0, mols=["H2O", "CH4"], toomuch=10.0),
+                               shape=dict(wnlow=2000.0, wnhigh=wnhigh, wndelt=1.0, mols=["H2O", "CH4"], toomuch=10.0),
                                nlayer=6, with_grid=False, nlines=nlines, tempdelt=1300.0, seed=99,
                                ethresh=1e-5, wnosamp=osamp)
         got = {}
@@ -135,6 +138,9 @@ def test_device_grouping_equals_host_walk(api, workdir, monkeypatch):
             bins = np.zeros(n, dtype=np.int64)
             assert L.bart_line_bins(bins.ctypes.data_as(C.POINTER(C.c_longlong)), n) == n
             got[host] = (n, ngroups_c.value, neval_c.value, bins, out)
+            L.bart_builder_phase_ms.restype = C.c_double
+            on_host = L.bart_builder_phase_ms(b"grouping_host") > 0
+            assert on_host == (host == "1" or tag == "extreme"), (tag, host)
             tr.free_memory()
         h, d = got["1"], got["0"]
         assert h[0] == d[0] > 0.9 * nlines and h[1] == d[1] and h[2] == d[2]
