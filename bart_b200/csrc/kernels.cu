@@ -593,6 +593,9 @@ transit_mma_kernel(DevConfig c, const double *__restrict__ tabs, const double *_
         for (int j = 0; j < kMmLoadBatch; j++) {
           const int d = d0 + 4 * (j0 + j) + warp;
           if (d < nl) {
+            // both columns are combined before either is stored: with no shared-memory store in
+            // between, the depth's table record is read once for the two of them
+            double ev[2];
 #pragma unroll
             for (int k = 0; k < 2; k++) {
               if (CellData<NMOL, NCIA>::kStaticCia) {
@@ -601,9 +604,10 @@ transit_mma_kernel(DevConfig c, const double *__restrict__ tabs, const double *_
                   if (fresh[j]) pq[k][f] = x[j][k].q[f]; else x[j][k].q[f] = pq[k][f];
                 }
               }
-              s_er[(size_t)d * kMmW + ((lane + 32 * k) ^ ((d & 3) << 2))] =
-                  cell_combine<NMOL, NCIA, SC>(c, P, s_tab + (size_t)d * nf, x[j][k], wn4[k], false, k * gstep, k * cstep);
+              ev[k] = cell_combine<NMOL, NCIA, SC>(c, P, s_tab + (size_t)d * nf, x[j][k], wn4[k], false, k * gstep, k * cstep);
             }
+#pragma unroll
+            for (int k = 0; k < 2; k++) s_er[(size_t)d * kMmW + ((lane + 32 * k) ^ ((d & 3) << 2))] = ev[k];
           }
         }
       }
