@@ -151,6 +151,39 @@ def test_device_grouping_equals_host_walk(api, workdir, monkeypatch):
     monkeypatch.delenv("BART_GROUP_HOST")
 
 
+def test_high_resolution_wide_profiles_vs_oracle(api, workdir, monkeypatch):
+    """The sweep's resolution (0.02423 cm-1 per sample, wnosamp 2160): pressure-broadened profiles
+    span hundreds to thousands of bins, i.e. the accumulate kernel's lane-per-bin paths (tile-covering
+    loop and range-tested ends) carry the result.  Random (layer, T) cells against the builder oracle."""
+    import os
+    from bart_b200 import synth
+    from oracle import oracle as orc
+    case = synth.make_case(os.path.join(workdir, "hr_wide"),
+                           shape=dict(wnlow=2000.0, wnhigh=2000.0 + 0.02423 * 12000, wndelt=0.02423,
+                                      mols=["H2O", "CO2", "CO", "CH4"], toomuch=10.0),
+                           nlayer=100, with_grid=False, nlines=60000, tempdelt=100.0, seed=2026,
+                           ethresh=1e-6, wnosamp=2160)
+    monkeypatch.setenv("BART_TSLICE", "0:0")
+    tr = api.Transit(argv=["transit", "-c", case["cfg"], "--justOpacity"])
+    monkeypatch.delenv("BART_TSLICE")
+    L = api.lib()
+    nl, nw, nmol = tr.nlayer, tr.nwave, 4
+    assert nw == 12001
+    B = orc.BuilderOracle(case["cfg"])
+    out = np.zeros((nl, 1, nmol, nw))
+    it = 9
+    api._check(L.bart_build_opacity_slice(it, it + 1, out.ctypes.data_as(api.dp)))
+    worst = 0.0
+    for r in (0, 3, 41, 99):                          # bottom (widest profiles) ... top (Doppler cores)
+        ref = np.asarray(B.build(layers=[r], temps=[it])).reshape(nmol, nw)
+        got = out[r, 0]
+        m = ref > 0
+        assert np.array_equal(got > 0, m) and m.any()
+        worst = max(worst, float(np.max(np.abs(got[m] - ref[m]) / ref[m])))
+    assert worst < 1e-12, worst
+    tr.free_memory()
+
+
 def test_temperature_sharded_build(api, workdir):
     """T-sharded build (bart_build_opacity_slice): slices reassemble to the full grid bit for bit."""
     case = cases.build_builder_case("build_ch4", workdir)
