@@ -229,69 +229,92 @@ __global__ void line_index_kernel(const double *wl, long long n, double wn_lo, d
 // ---------------------------------------------------------------------------------------
 // Co-add grouping on the device (extinction.c:450-462).  The reference walks the lines once: an
 // in-range line that no earlier leader absorbed leads a group and absorbs the FOLLOWING lines of its
-// isotope while |wavn - owns[iown_leader]| < odwn.  Who leads depends on who led before -- a chain --
-// but the chain breaks wherever a line cannot be absorbed whoever leads before it: with the lines of
-// an isotope sorted (TLI order) the leader's node lies within odwn/2 of a wavenumber >= the previous
-// line's, so a gap of more than 1.5 odwn to the previous line proves a new group (a "definite
-// leader"; so are the first in-range line and an in-range line that opens an isotope).  One thread per
-// definite leader then walks the short stretch to the next one exactly like the reference does.  The
-// result is the reference's grouping for every input the checks accept; unsorted input takes the
-// host walk.
-__global__ void group_check_kernel(const double *wl, const short *iso, const unsigned char *inr,
-                                   long long n, int niso, int *flags, unsigned long long *first_in) {
+// isotope while |wavn - owns[iown_leader]| < odwn; the next leader is the first in-range line after
+// the run.  Who leads depends on who led before -- a chain through the whole list -- but the chain
+// forgets its past quickly: where it goes from a line depends on that line only, so two walks that
+// ever stand on the same line coincide from there on.
+//   1. group_spec_kernel   one thread per block of kGrpBlock lines walks the chain SPECULATIVELY
+//                          from the block's first in-range line, marks the leaders it visits and
+//                          records where it leaves the block;
+//   2. group_fix_kernel    one thread follows the TRUE chain from the first in-range line of the
+//                          list, block by block, only until it steps on a speculative mark (from
+//                          there the block's speculative marks and exit are the true ones): a
+//                          step or two per block, whatever the line density;
+//   3. group_mark_kernel   one thread per line: the true leaders (fix-up marks, and speculative
+//                          marks at or after their block's merge point) mark their runs.
+// This IS the reference's walk for any input (no ordering assumed); a list on which the walks never
+// merge would make step 2 sequential, so it gives up after a bounded number of steps and the caller
+// takes the host walk.
+constexpr int kGrpBlock = 4096;
+__global__ void group_check_kernel(const short *iso, const unsigned char *inr, long long n, int niso,
+                                   int *flags) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int is = iso[i];
   int f = 0;
   if (is < 0 || is >= niso) f |= 1;
-  if (i > 0) {
-    const int ip = iso[i - 1];
-    if (is < ip) f |= 2;
-    if (is == ip && wl[i] < wl[i - 1]) f |= 4;
-  }
+  if (i > 0 && is < iso[i - 1]) f |= 2;
   if (f) atomicOr(flags, f);
-  if (inr[i]) atomicMin(first_in, (unsigned long long)i);
 }
 
-__global__ void group_definite_kernel(const double *wavn, const short *iso, const unsigned char *inr,
-                                      long long n, double odwn, const unsigned long long *first_in,
-                                      unsigned char *dl) {
-  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  bool d = false;
-  if (inr[i]) {
-    if (i == 0 || (unsigned long long)i == *first_in || iso[i] != iso[i - 1]) d = true;
-    else {
-      const double w = wavn[i];
-      d = wavn[i - 1] - w > 1.5 * odwn + 1e-10 * fmax(1.0, fabs(w));
-    }
+struct GroupArgs {
+  const double *wavn; const short *iso; const unsigned char *inr; const int *iown;
+  long long n; double wn_lo, odwn;
+};
+__device__ __forceinline__ long long grp_run_end(const GroupArgs &a, long long ln) {
+  const short is = a.iso[ln];
+  const double vnode = __dadd_rn(a.wn_lo, __dmul_rn((double)a.iown[ln], a.odwn));
+  long long e = ln + 1;
+  while (e < a.n && a.iso[e] == is && fabs(a.wavn[e] - vnode) < a.odwn) e++;
+  return e;
+}
+__device__ __forceinline__ long long grp_next_leader(const GroupArgs &a, long long e) {
+  while (e < a.n && !a.inr[e]) e++;                  // out-of-range lines never lead
+  return e;
+}
+
+__global__ void group_spec_kernel(GroupArgs a, long long nblocks, unsigned char *spec, long long *exit_of) {
+  const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (b >= nblocks) return;
+  const long long lo = b * kGrpBlock, hi = min(a.n, lo + kGrpBlock);
+  long long ln = grp_next_leader(a, lo);
+  while (ln < hi) {
+    spec[ln] = 1;
+    ln = grp_next_leader(a, grp_run_end(a, ln));
   }
-  dl[i] = d ? 1 : 0;
+  exit_of[b] = ln;
+}
+
+__global__ void group_fix_kernel(GroupArgs a, long long nblocks, const unsigned char *spec,
+                                 const long long *exit_of, unsigned char *fixl, long long *merge_at,
+                                 int *gave_up) {
+  long long entry = grp_next_leader(a, 0);
+  long long steps = 0;
+  const long long limit = 8 * nblocks + (1 << 20);
+  for (long long b = 0; b < nblocks; b++) {
+    const long long hi = min(a.n, (b + 1) * kGrpBlock);
+    long long ln = entry, m = a.n;
+    while (ln < hi) {
+      if (spec[ln]) { m = ln; break; }
+      fixl[ln] = 1;
+      ln = grp_next_leader(a, grp_run_end(a, ln));
+      if (++steps > limit) { *gave_up = 1; return; }
+    }
+    merge_at[b] = m;
+    entry = m < hi ? exit_of[b] : ln;
+  }
 }
 
 // flag bit 0: leads a group; bit 1: member of a group (leader or absorbed)
-// A line list so dense that definite leaders are rare (many lines per oversampled bin everywhere)
-// would leave one thread walking millions of lines: a walk longer than kChainLimit lines raises
-// *too_long and the caller takes the host walk instead.
-constexpr long long kChainLimit = 1 << 16;
-__global__ void group_chain_kernel(const double *wavn, const short *iso, const unsigned char *inr,
-                                   const int *iown, const unsigned char *dl, long long n, double wn_lo,
-                                   double odwn, unsigned char *flag, int *trace, int *too_long) {
+__global__ void group_mark_kernel(GroupArgs a, const unsigned char *spec, const unsigned char *fixl,
+                                  const long long *merge_at, unsigned char *flag, int *trace) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i >= n || !dl[i]) return;
-  long long ln = i;
-  for (;;) {
-    if (ln - i > kChainLimit) { *too_long = 1; return; }
-    const int io = iown[ln];
-    const short is = iso[ln];
-    const double vnode = __dadd_rn(wn_lo, __dmul_rn((double)io, odwn));
-    flag[ln] = 3; trace[ln] = io;
-    long long e = ln + 1;
-    while (e < n && iso[e] == is && fabs(wavn[e] - vnode) < odwn) { flag[e] = 2; trace[e] = -2 - io; e++; }
-    while (e < n && !inr[e]) e++;                  // out-of-range lines never lead
-    if (e >= n || dl[e]) break;
-    ln = e;
-  }
+  if (i >= a.n) return;
+  if (!(fixl[i] || (spec[i] && i >= merge_at[i / kGrpBlock]))) return;
+  const int io = a.iown[i];
+  flag[i] = 3; trace[i] = io;
+  const long long e = grp_run_end(a, i);
+  for (long long k = i + 1; k < e; k++) { flag[k] = 2; trace[k] = -2 - io; }
 }
 
 // first group of every isotope = leaders before the first line whose isotope index is >= k
@@ -978,9 +1001,8 @@ static bool load_lines_device(BuilderState *b, const Options &o, const Tli &t, d
   double *d_wl, *d_elow, *d_gf, *d_wavn;
   short *d_iso;
   int *d_iown, *d_idwn, *d_flags, *d_trace;
-  unsigned char *d_inr, *d_dl, *d_flag;
-  unsigned long long *d_first;
-  long long *d_lrank, *d_mrank;
+  unsigned char *d_inr, *d_spec, *d_fixl, *d_flag;
+  long long *d_lrank, *d_mrank, *d_exit, *d_merge;
   BCUDA(cudaMalloc((void **)&d_wl, na * 8)); BCUDA(cudaMalloc((void **)&d_elow, na * 8));
   BCUDA(cudaMalloc((void **)&d_gf, na * 8)); BCUDA(cudaMalloc((void **)&d_iso, na * 2));
   {
@@ -997,47 +1019,51 @@ static bool load_lines_device(BuilderState *b, const Options &o, const Tli &t, d
   lap("read_tli_host");
   BCUDA(cudaMalloc((void **)&d_wavn, na * 8)); BCUDA(cudaMalloc((void **)&d_iown, na * 4));
   BCUDA(cudaMalloc((void **)&d_idwn, na * 4)); BCUDA(cudaMalloc((void **)&d_inr, na));
-  BCUDA(cudaMalloc((void **)&d_dl, na)); BCUDA(cudaMalloc((void **)&d_flag, na));
+  const long long nblocks = (na + kGrpBlock - 1) / kGrpBlock;
+  BCUDA(cudaMalloc((void **)&d_spec, na)); BCUDA(cudaMalloc((void **)&d_fixl, na));
+  BCUDA(cudaMalloc((void **)&d_flag, na));
   BCUDA(cudaMalloc((void **)&d_trace, na * 4));
-  BCUDA(cudaMalloc((void **)&d_flags, 4)); BCUDA(cudaMalloc((void **)&d_first, 8));
+  BCUDA(cudaMalloc((void **)&d_flags, 4));
+  BCUDA(cudaMalloc((void **)&d_exit, nblocks * 8)); BCUDA(cudaMalloc((void **)&d_merge, nblocks * 8));
   BCUDA(cudaMalloc((void **)&d_lrank, (na + 1) * 8)); BCUDA(cudaMalloc((void **)&d_mrank, (na + 1) * 8));
   auto drop = [&](std::initializer_list<void *> ps) { for (void *q : ps) cudaFree(q); };
   const double own_last = b->wn_lo + (double)(b->nowns - 1) * b->odwn;
   const unsigned grid = (unsigned)((na + 255) / 256);
   BCUDA(cudaMemsetAsync(d_flags, 0, 4, s));
-  BCUDA(cudaMemsetAsync(d_first, 0xff, 8, s));
+  BCUDA(cudaMemsetAsync(d_spec, 0, na, s));
+  BCUDA(cudaMemsetAsync(d_fixl, 0, na, s));
   BCUDA(cudaMemsetAsync(d_flag, 0, na, s));
   BCUDA(cudaMemsetAsync(d_trace, 0xff, na * 4, s));                 // -1: in no group
   int flags = 0;
   if (n > 0) {
     line_index_kernel<<<grid, 256, 0, s>>>(d_wl, n, b->wn_lo, own_last, b->odwn, b->dwn, d_wavn, d_iown,
                                            d_idwn, d_inr);
-    group_check_kernel<<<grid, 256, 0, s>>>(d_wl, d_iso, d_inr, n, b->niso, d_flags, d_first);
+    group_check_kernel<<<grid, 256, 0, s>>>(d_iso, d_inr, n, b->niso, d_flags);
     BCUDA(cudaGetLastError());
     BCUDA(cudaMemcpyAsync(&flags, d_flags, 4, cudaMemcpyDeviceToHost, s));
     BCUDA(cudaStreamSynchronize(s));
   }
+  auto drop_all = [&]() {
+    drop({d_wl, d_elow, d_gf, d_iso, d_wavn, d_iown, d_idwn, d_inr, d_spec, d_fixl, d_flag, d_trace, d_flags,
+          d_exit, d_merge, d_lrank, d_mrank});
+  };
+  if (flags & 3) drop_all();
   if (flags & 1) fail("a TLI line has an isotope index outside [0,%d)", b->niso);
   if (flags & 2) fail("TLI lines are not grouped by isotope");
-  if (flags & 4) {
-    drop({d_wl, d_elow, d_gf, d_iso, d_wavn, d_iown, d_idwn, d_inr, d_dl, d_flag, d_trace, d_flags,
-          d_first, d_lrank, d_mrank});
-    return false;
-  }
   long long ngroups = 0, nmember = 0;
   if (n > 0) {
-    group_definite_kernel<<<grid, 256, 0, s>>>(d_wavn, d_iso, d_inr, n, b->odwn, d_first, d_dl);
-    BCUDA(cudaMemsetAsync(d_flags, 0, 4, s));
-    group_chain_kernel<<<grid, 256, 0, s>>>(d_wavn, d_iso, d_inr, d_iown, d_dl, n, b->wn_lo, b->odwn, d_flag,
-                                            d_trace, d_flags);
+    GroupArgs ga{d_wavn, d_iso, d_inr, d_iown, n, b->wn_lo, b->odwn};
+    group_spec_kernel<<<(unsigned)((nblocks + 127) / 128), 128, 0, s>>>(ga, nblocks, d_spec, d_exit);
+    group_fix_kernel<<<1, 1, 0, s>>>(ga, nblocks, d_spec, d_exit, d_fixl, d_merge, d_flags);
     BCUDA(cudaGetLastError());
     BCUDA(cudaMemcpyAsync(&flags, d_flags, 4, cudaMemcpyDeviceToHost, s));
     BCUDA(cudaStreamSynchronize(s));
-    if (flags) {                                   // too dense for the chain walks: host path
-      drop({d_wl, d_elow, d_gf, d_iso, d_wavn, d_iown, d_idwn, d_inr, d_dl, d_flag, d_trace, d_flags,
-            d_first, d_lrank, d_mrank});
+    if (flags) {                                   // the walks never merged: host path
+      drop_all();
       return false;
     }
+    group_mark_kernel<<<grid, 256, 0, s>>>(ga, d_spec, d_fixl, d_merge, d_flag, d_trace);
+    BCUDA(cudaGetLastError());
     // ranks of the leaders (group numbers) and of the members (positions in the grouped line
     // arrays): exclusive sums over n + 1 flags, the last entry being the total
     cub::TransformInputIterator<long long, FlagBit, const unsigned char *> lead(d_flag, FlagBit{0}),
@@ -1089,8 +1115,8 @@ static bool load_lines_device(BuilderState *b, const Options &o, const Tli &t, d
   BCUDA(cudaStreamSynchronize(s));
   b->h_iown.clear();
   b->d_trace = d_trace;
-  drop({d_wl, d_elow, d_gf, d_iso, d_wavn, d_iown, d_idwn, d_inr, d_dl, d_flag, d_flags, d_first, d_lrank,
-        d_mrank});
+  drop({d_wl, d_elow, d_gf, d_iso, d_wavn, d_iown, d_idwn, d_inr, d_spec, d_fixl, d_flag, d_flags, d_exit,
+        d_merge, d_lrank, d_mrank});
   lap("grouping_device");
   return true;
 }
