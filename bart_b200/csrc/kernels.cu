@@ -46,6 +46,11 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
       "l"(src), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
 }
+// arrive (release.cta): what the arriving thread wrote -- and, after a __syncwarp, what its warp
+// wrote -- is visible to a thread whose try_wait (acquire.cta) sees the phase complete
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   uint32_t ok;
   do {
@@ -289,7 +294,7 @@ transit_tile_kernel(DevConfig c, const double *__restrict__ tabs, const double *
   double *s_er = s_wt + (size_t)nl * kTrRow;                   // [nl][kTrW]
   double *s_tau = s_er + (size_t)nl * kTrW;                    // [kTrChunk][kTrW]
   double *s_fd = s_tau + (size_t)kTrChunk * kTrW;              // [kTrChunk][kTrW] exp(-tau) b
-  __shared__ int s_ready[kTrMaxChunks];                        // producer warps that finished the chunk
+  __shared__ __align__(8) uint64_t s_ready[kTrMaxChunks];      // mbarriers: the chunk's producer warps arrive
   __shared__ int s_stop, s_alive[2];                           // [chunk parity]
   const int m = blockIdx.x % nmodels;
   const int tile = blockIdx.x / nmodels;
@@ -305,7 +310,8 @@ transit_tile_kernel(DevConfig c, const double *__restrict__ tabs, const double *
     return;
   }
   if (threadIdx.x == 0) { mbar_init(&bar_w, 1); s_stop = 0; s_alive[0] = s_alive[1] = 0; }
-  if (threadIdx.x < kTrMaxChunks) s_ready[threadIdx.x] = 0;
+  if (threadIdx.x < kTrMaxChunks) mbar_init(&s_ready[threadIdx.x], kTrCons / 32);
+  fence_mbar_init();
   stage_table(s_tab, tabs + (size_t)m * nd, nd, &bar, use_tma != 0, s_etab);
   __syncthreads();
   const int nchunks = tr_nchunks(nl);
@@ -334,7 +340,7 @@ transit_tile_kernel(DevConfig c, const double *__restrict__ tabs, const double *
         }
       }
       __syncwarp();
-      if (lane == 0) { __threadfence_block(); atomicAdd(&s_ready[ch], 1); }
+      if (lane == 0) mbar_arrive(&s_ready[ch]);
     }
     return;
   }
@@ -367,8 +373,7 @@ transit_tile_kernel(DevConfig c, const double *__restrict__ tabs, const double *
     const int d0 = ch * kTrChunk;
     const int dn = min(kTrChunk, nl - d0);
     // the chunk's extinction rows (and, by program order of the producers, all earlier ones)
-    while (*(volatile int *)&s_ready[ch] < kTrCons / 32) __nanosleep(32);
-    __threadfence_block();
+    mbar_wait(&s_ready[ch], 0);
     if (use_tma) { mbar_wait(&bar_w, wphase); wphase ^= 1u; }
     else bar_consumers();
     pending = false;
@@ -523,7 +528,7 @@ transit_mma_kernel(DevConfig c, const double *__restrict__ tabs, const double *_
   double *s_er = s_wt + (size_t)kMmChunk * mm_rs(nchunks - 1); // [nlp][64], swizzled
   double *s_tau = s_er + (size_t)nlp * kMmW;                   // [16][64]
   double *s_fd = s_tau + (size_t)kMmChunk * kMmW;              // [16][64] exp(-tau) b
-  __shared__ int s_ready[kMmMaxChunks];
+  __shared__ __align__(8) uint64_t s_ready[kMmMaxChunks];      // mbarriers: the chunk's producer warps arrive
   __shared__ int s_stop, s_alive[2];
   const int m = blockIdx.x % nmodels;
   const int tile = blockIdx.x / nmodels;
@@ -539,7 +544,8 @@ transit_mma_kernel(DevConfig c, const double *__restrict__ tabs, const double *_
     return;
   }
   if (threadIdx.x == 0) { mbar_init(&bar_w, 1); s_stop = 0; s_alive[0] = s_alive[1] = 0; }
-  if (threadIdx.x < kMmMaxChunks) s_ready[threadIdx.x] = 0;
+  if (threadIdx.x < kMmMaxChunks) mbar_init(&s_ready[threadIdx.x], kMmCons / 32);
+  fence_mbar_init();
   // rows past the last layer: zero extinction (their weights are zero as well)
   for (int i = nl * kMmW + threadIdx.x; i < nlp * kMmW; i += kMmThreads) s_er[i] = 0.0;
   stage_table(s_tab, tabs + (size_t)m * nd, nd, &bar, use_tma != 0, s_etab);
@@ -612,7 +618,7 @@ transit_mma_kernel(DevConfig c, const double *__restrict__ tabs, const double *_
         }
       }
       __syncwarp();
-      if (lane == 0) { __threadfence_block(); atomicAdd(&s_ready[ch], 1); }
+      if (lane == 0) mbar_arrive(&s_ready[ch]);
     }
     return;
   }
@@ -643,8 +649,7 @@ transit_mma_kernel(DevConfig c, const double *__restrict__ tabs, const double *_
   for (int ch = 0; ch < nchunks; ch++) {
     const int d0 = ch * kMmChunk;
     const int dn = min(kMmChunk, nl - d0);
-    while (*(volatile int *)&s_ready[ch] < kMmCons / 32) __nanosleep(32);
-    __threadfence_block();
+    mbar_wait(&s_ready[ch], 0);
     if (use_tma) { mbar_wait(&bar_w, wphase); wphase ^= 1u; }
     else bar_consumers();
     pending = false;
