@@ -10,8 +10,11 @@
 //                              bin-averaged in float32 with the reference's operation order.
 //   line_index_kernel          per line: wavenumber, oversampled/coarse bin indices with
 //                              non-contracted IEEE ops (bit-exact indices).
-//   (host)                     co-add grouping of neighbouring lines -- temperature independent,
-//                              sequential by construction (extinction.c:450-462), done once.
+//   group_spec / fix / mark    co-add grouping of neighbouring lines (extinction.c:450-462) --
+//                              temperature independent, done once: the reference's sequential
+//                              leader chain as speculative per-block walks + one fix-up walk,
+//                              then scans and a fill (load_lines_device); the line list itself
+//                              streams file -> pinned staging -> HBM without a host copy.
 //   K6a+b strength_kmax_kernel per plane (temperature): ONE pass over the lines evaluates the two
 //                              exponentials that serve both the strongest line per molecule
 //                              (extinction.c:400-427) and the co-added group strengths (439-464);
@@ -21,9 +24,9 @@
 //   K6c widths_kernel          per (layer, isotope): Lorentz/Doppler widths, table indices, the
 //                              carried Doppler index of the reference's sequential loop.
 //   K6d accumulate_kernel      per (layer, 128-bin wavenumber tile): GATHER over the candidate
-//                              groups in line order -- no atomics, summation order identical to
-//                              the reference, profile samples fetched with the reference's
-//                              stride-`wnosamp` indexing.
+//                              groups -- no atomics, deterministic; the Voigt pool is stored
+//                              phase-major so that the samples a line adds to consecutive bins
+//                              (stride `wnosamp` in the reference's array) are contiguous.
 //
 // The temperature axis is the sharding axis (bart_build_opacity_slice): planes are independent.
 #include "builder.hpp"
