@@ -22,6 +22,7 @@
 #include <vector>
 #include <map>
 #include <algorithm>
+#include <functional>
 #include <unistd.h>
 #include <fcntl.h>
 #include <sys/stat.h>
@@ -1736,19 +1737,23 @@ int bart_converter_init(int pt_type, int npt, const double *pt_args, int tint_th
     std::vector<double> w(2 * r + 1);
     const double c = -0.5 / (sigma * sigma);
     for (int k = -r; k <= r; k++) w[k + r] = exp(c * (double)(k * k));
-    // numpy's pairwise sum (what phi_x.sum() evaluates)
-    double tot = 0.0;
-    const int n = 2 * r + 1;
-    if (n < 8) { for (int k = 0; k < n; k++) tot += w[k]; }
-    else {
-      double acc[8];
-      for (int j = 0; j < 8; j++) acc[j] = w[j];
-      int k = 8;
-      for (; k < n - (n % 8); k += 8) for (int j = 0; j < 8; j++) acc[j] += w[k + j];
-      tot = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
-      for (; k < n; k++) tot += w[k];
-    }
-    if (n > 128) fail("PT smoothing kernel of %d layers is not supported", n);
+    // numpy's pairwise sum (what phi_x.sum() evaluates; numpy/_core/src/umath/loops_utils.h.src)
+    std::function<double(const double *, long)> pairwise = [&](const double *a, long n) -> double {
+      if (n < 8) { double r = 0.0; for (long k = 0; k < n; k++) r += a[k]; return r; }
+      if (n <= 128) {
+        double acc[8];
+        for (int j = 0; j < 8; j++) acc[j] = a[j];
+        long k = 8;
+        for (; k < n - (n % 8); k += 8) for (int j = 0; j < 8; j++) acc[j] += a[k + j];
+        double r = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+        for (; k < n; k++) r += a[k];
+        return r;
+      }
+      long n2 = n / 2;
+      n2 -= n2 % 8;
+      return pairwise(a, n2) + pairwise(a + n2, n - n2);
+    };
+    const double tot = pairwise(w.data(), (long)w.size());
     for (auto &v : w) v /= tot;
     upload(G.d_csmooth, w);
     cc.smooth_r = r; cc.smooth_w = G.d_csmooth.p;

@@ -97,6 +97,22 @@ def test_smoothed_pt_models_on_device(api, workdir):
         oprof, ostatus, _ = conv.profiles(pars)
         assert np.array_equal(ostatus, status)
         assert np.max(np.abs(prof[ok] / oprof[ok] - 1)) < 1e-13
+    # a second pressure grid (60 layers, 0.144 dex per layer: Piette's sigma 2.08 layers)
+    import os as _os
+    from bart_b200 import synth
+    c60 = synth.make_case(_os.path.join(workdir, "pt60"), shape="tiny", solution="eclipse", seed=5, nlayer=60)
+    tr.free_memory()
+    tr60 = api.Transit(c60["cfg"])
+    pb = g["pressure_b"]
+    for name, key in (("madhu_noinv", "noinv"), ("madhu_inv", "inv"), ("piette", "piette")):
+        tr60.converter_init(pb, c60["species"], c60["abund"], (), name, tmin=0.0, tmax=1e9, nrad=0)
+        pars, T, phys = (g["%s_%s_b" % (key, k)] for k in ("pars", "T", "phys"))
+        prof, status, _ = tr60.profiles_from_params(pars)
+        assert np.array_equal(status == 256, phys == 0)
+        ok = phys == 1
+        assert np.max(np.abs(prof[ok, :60] / T[ok] - 1)) < 1e-13
+    tr60.free_memory()
+    tr = api.Transit(case["cfg"])
     # temperature bounds act on the smoothed profile (BARTfunc.py:327-330)
     tr.converter_init(case["press_bar"], case["species"], case["abund"], (), "piette", tmin=400.0,
                       tmax=3000.0, nrad=0)
