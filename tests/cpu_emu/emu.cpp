@@ -199,6 +199,25 @@ long long emu_read_tli(const char *path, double wnlow, double wnhigh, long long 
   } catch (std::exception &) { return -1; }
 }
 
+// Chord optical depths through the DEVICE code's weight construction (column_math.cuh
+// transit_weight_row_acc, what transit_weights_kernel runs per depth): radii by depth (top -> bottom),
+// extinction by depth; tau[d] = sum_{i<=d} W[d][i] ex[i] / rfct'.  For the analytic known-answer
+// tests of the reference's own test design (transit/test/test_slantpath.c:177-198).
+void emu_chord_tau(int nl, const double *radius_by_depth, const double *ex_by_depth, double *tau) {
+  DevConfig c{};
+  c.nlayer = nl; c.rfct = 1.0;
+  c.lay.nl = nl; c.lay.ngmol = 1; c.lay.ncia = 0;
+  const int nf = c.lay.nf();
+  std::vector<double> tab((size_t)nf * nl, 0.0), wt(nl);
+  for (int d = 0; d < nl; d++) tab[(size_t)d * nf + TabLayout::RAD] = radius_by_depth[d];
+  for (int d = 0; d < nl; d++) {
+    transit_weight_row(c, tab.data(), d, wt.data());
+    double t = 0.0;
+    for (int i = 0; i <= d; i++) t += wt[i] * ex_by_depth[i];
+    tau[d] = t;
+  }
+}
+
 double emu_fast_exp(double x) { unsigned long long t[kExpTabSize]; fill_exp_table(t); return fast_exp(x, t); }
 
 }  // extern "C"
