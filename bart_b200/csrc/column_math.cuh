@@ -875,9 +875,7 @@ BART_HD void eclipse_columns(const DevConfig &c, const double *tab, const unsign
     unsigned sm = 0;                                           // bit k: slot k takes the series
 #pragma unroll
     for (int k = 0; k < NCOL; k++) sm |= BART_WARP_ALL(small[k]) ? 1u << k : 0u;
-#ifdef BART_ECL_PAIR_DECISION                                  // A/B experiment: one decision per warp
-    sm = sm == (1u << NCOL) - 1u ? sm : 0u;
-#endif
+    // (one decision for the whole warp instead of one per slot measured slower)
     if (sm == (1u << NCOL) - 1u) series(0, NCOL);
     else if (sm == 0u) exponentials(0, NCOL);
     else {                                                     // slots disagree (a few depths per column)
