@@ -368,6 +368,7 @@ struct PlaneArgs {
   const long long *gstart; const short *giso; const double *wavn, *elow, *gf;
   long long ngroups;
   const double *plane_T, *plane_fac2 /*[P][niso]*/, *plane_facfull /*[P][niso]*/;
+  const double *plane_tq;           // [P] -EXPCTE / T, divided once per plane on the host
   double *kmax /*[P][kMaxGridMol]*/;
   double *S /*[P][ngroups]*/;
   const int *iso_out;
@@ -401,7 +402,7 @@ strength_kmax_kernel(PlaneArgs a, int nplanes) {
 #pragma unroll
     for (int q = 0; q < kPlanesPerThread; q++) {
       const int p = min(p0 + q, nplanes - 1);              // planes past the end shadow the last one
-      Tq[q] = -kEXPCTE / a.plane_T[p];                     // one division per plane, not two per line
+      Tq[q] = a.plane_tq[p];                               // -EXPCTE / T: no division in the kernel
       ff[q] = a.plane_facfull[(size_t)p * a.niso + iso];
       pk[q] = 0.0; lmax[q] = 0.0;
     }
@@ -1229,7 +1230,7 @@ static void load_lines(BuilderState *b, const Options &o, Tli &t, const std::vec
 // ---------------------------------------------------------------------------------------
 // Plane / cell driver shared by the grid build and the line-by-line forward mode.
 struct PlaneWork {
-  DevBuf T, facfull, fac2, kmax, blk, total, base, cisobeg, S;        // per plane
+  DevBuf T, tq, facfull, fac2, kmax, blk, total, base, cisobeg, S;    // per plane
   DevBuf c_idx;                                                        // compact pool
   DevBuf cell_plane, cell_out, cellinfo;                               // per cell
   DevBuf iso_spec, iso_out, iso_mass, spec_mass, spec_radius;          // static tables
@@ -1278,6 +1279,10 @@ static long long run_planes(BuilderState *b, const Options &o, const Molecules &
   long long *d_total = w.total.get<long long>(nplanes), *d_base = w.base.get<long long>(nplanes),
             *d_cisobeg = w.cisobeg.get<long long>((size_t)nplanes * (niso + 1));
   BCUDA(cudaMemcpyAsync(d_T, plane_T, nplanes * 8, cudaMemcpyHostToDevice, s));
+  std::vector<double> tq(nplanes);
+  for (int p = 0; p < nplanes; p++) tq[p] = -kEXPCTE / plane_T[p];
+  double *d_tq = w.tq.get<double>(nplanes);
+  BCUDA(cudaMemcpyAsync(d_tq, tq.data(), nplanes * 8, cudaMemcpyHostToDevice, s));
   BCUDA(cudaMemcpyAsync(d_facfull, facfull.data(), facfull.size() * 8, cudaMemcpyHostToDevice, s));
   BCUDA(cudaMemcpyAsync(d_fac2, fac2.data(), fac2.size() * 8, cudaMemcpyHostToDevice, s));
   BCUDA(cudaMemsetAsync(d_kmax, 0, (size_t)nplanes * kMaxGridMol * 8, s));
@@ -1287,6 +1292,7 @@ static long long run_planes(BuilderState *b, const Options &o, const Molecules &
   PlaneArgs pa;
   pa.gstart = b->d_gstart; pa.giso = b->d_giso; pa.wavn = b->d_c_wavn; pa.elow = b->d_c_elow; pa.gf = b->d_c_gf;
   pa.ngroups = b->ngroups; pa.plane_T = d_T; pa.plane_fac2 = d_fac2; pa.plane_facfull = d_facfull;
+  pa.plane_tq = d_tq;
   pa.kmax = d_kmax; pa.S = w.S.get<double>((size_t)nplanes * std::max<long long>(1, b->ngroups));
   pa.iso_out = d_iso_out; pa.niso = niso; pa.nout = nout; pa.ethresh = o.ethreshold; pa.nblk = nblk;
   pa.wn_lo = b->wn_lo; pa.own_last = b->wn_lo + (double)(b->nowns - 1) * b->odwn;
@@ -1583,7 +1589,7 @@ void builder_free(BuilderState *b) {
   for (void *p : ptrs) if (p) cudaFree(p);
   if (b->work) {
     PlaneWork &w = *b->work;
-    DevBuf *bufs[] = {&w.T, &w.facfull, &w.fac2, &w.kmax, &w.S, &w.blk, &w.total, &w.base, &w.cisobeg,
+    DevBuf *bufs[] = {&w.T, &w.tq, &w.facfull, &w.fac2, &w.kmax, &w.S, &w.blk, &w.total, &w.base, &w.cisobeg,
                       &w.c_idx, &w.cell_plane, &w.cell_out, &w.cellinfo,
                       &w.iso_spec, &w.iso_out, &w.iso_mass, &w.spec_mass, &w.spec_radius};
     for (DevBuf *d : bufs) d->release();
