@@ -127,41 +127,46 @@ struct PhaseTimer {
 };
 
 // ---------------------------------------------------------------------------------------
-// Voigt function (voigt.c:132-200).  Region I is a power series the reference evaluates in
-// 80-bit long double; fp64 here (difference <= 1e-10 relative before the float32 rounding).
-__constant__ double c_ferf[64];
+// Voigt function K(x, y) sqrt(ln2/pi) / alphaD (pu/src/voigt.c:132-200) as float.  Region I
+// (x < 3, y < 1.8): w(z) = exp(-z^2) (1 + (2i/sqrt(pi)) int_0^z exp(t^2) dt), the integral as its
+// Maclaurin series sum_k z^(2k+1) / (k! (2k+1)) carried as the running power p_k = -i z^(2k+1)
+// (the reference evaluates it in 80-bit long double; fp64 here: <= 1e-10 relative before the
+// float32 rounding).  Regions II / III: Pierluissi's sums over poles, Re sum_j c_j / (z^2 - s_j) in
+// real arithmetic.  Operation order as in the reference's expressions (1-ulp parity of the table).
+__constant__ double c_ferf[64];               // 1 / (k! (2k + 1))
+__constant__ double c_pole2[3][2] = {{0.46131350, 0.19016350}, {0.09999216, 1.78449270},
+                                     {0.002883894, 5.52534370}};      // {weight, shift}, region II
+__constant__ double c_pole3[2][2] = {{0.51242424, 0.27525510}, {0.05176536, 2.72474500}};
 
 __device__ float voigtxy_dev(double x, double y, double alphaD) {
-  const double A1 = 0.46131350, A2 = 0.19016350, A3 = 0.09999216, A4 = 1.78449270,
-               A5 = 0.002883894, A6 = 5.52534370, B1 = 0.51242424, B2 = 0.27525510,
-               B3 = 0.05176536, B4 = 2.72474500;
-  const double SQRTLN2PI = 0.46971863934982566689, TWOOSQRTPI = 1.12837916709551257389;
-  const double x2y2 = x * x - y * y, xy2 = 2 * x * y;
+  const double norm = 0.46971863934982566689 / alphaD;               // sqrt(ln 2 / pi) / alphaD
+  const double two_over_sqrtpi = 1.12837916709551257389;
+  const double zre = x * x - y * y, zim = 2 * x * y;                 // z^2, z = x + i y
   if (x < 3 && y < 1.8) {
-    double sinxy, cosxy;
-    sincos(xy2, &sinxy, &cosxy);
-    const int n = (x < 1 ? 15 : (int)(6.842 * x + 8.0)) + 1;
-    double orr = y, oi = -x, ar = y, ai = -x;
-    for (int i = 1; i <= n; i++) {
-      const double ni = orr * xy2 + oi * x2y2;
-      const double nr = orr * x2y2 - oi * xy2;
-      ai += ni * c_ferf[i];
-      ar += nr * c_ferf[i];
-      oi = ni; orr = nr;
+    double sn, cs;
+    sincos(zim, &sn, &cs);
+    const int nterms = (x < 1 ? 15 : (int)(6.842 * x + 8.0)) + 1;
+    double pre = y, pim = -x;                                        // -i z
+    double sre = pre, sim = pim;
+    for (int k = 1; k <= nterms; k++) {
+      const double nim = pre * zim + pim * zre;                      // (pre + i pim) z^2
+      const double nre = pre * zre - pim * zim;
+      sim += nim * c_ferf[k];
+      sre += nre * c_ferf[k];
+      pim = nim; pre = nre;
     }
-    return (float)(SQRTLN2PI / alphaD * exp(-x2y2) *
-                   (cosxy * (1 - ar * TWOOSQRTPI) - sinxy * ai * TWOOSQRTPI));
+    return (float)(norm * exp(-zre) * (cs * (1 - sre * two_over_sqrtpi) - sn * sim * two_over_sqrtpi));
   }
-  const double ar = xy2 * xy2, nr = xy2 * x;
+  const double im2 = zim * zim, xim = zim * x;
   if (x < 5 && y < 5) {
-    const double ni = x2y2 - A2, ai = x2y2 - A4, oi = x2y2 - A6;
-    return (float)(SQRTLN2PI / alphaD * (A1 * ((nr - ni * y) / (ni * ni + ar)) +
-                                         A3 * ((nr - ai * y) / (ai * ai + ar)) +
-                                         A5 * ((nr - oi * y) / (oi * oi + ar))));
+    const double d0 = zre - c_pole2[0][1], d1 = zre - c_pole2[1][1], d2 = zre - c_pole2[2][1];
+    return (float)(norm * (c_pole2[0][0] * ((xim - d0 * y) / (d0 * d0 + im2)) +
+                           c_pole2[1][0] * ((xim - d1 * y) / (d1 * d1 + im2)) +
+                           c_pole2[2][0] * ((xim - d2 * y) / (d2 * d2 + im2))));
   }
-  const double ni = x2y2 - B2, ai = x2y2 - B4;
-  return (float)(SQRTLN2PI / alphaD * (B1 * ((nr - ni * y) / (ni * ni + ar)) +
-                                       B3 * ((nr - ai * y) / (ai * ai + ar))));
+  const double d0 = zre - c_pole3[0][1], d1 = zre - c_pole3[1][1];
+  return (float)(norm * (c_pole3[0][0] * ((xim - d0 * y) / (d0 * d0 + im2)) +
+                         c_pole3[1][0] * ((xim - d1 * y) / (d1 * d1 + im2))));
 }
 
 struct ProfJob {          // one unique profile

@@ -529,37 +529,50 @@ int orc_forward_lbl(const orc_config *c, const orc_lbl_fwd *F, int eclipse, cons
 /* ====================================================================================== */
 /* Line-by-line builder (stage d)                                                         */
 
-/* pu/src/voigt.c:132-200.  The reference evaluates region I in `long double`; so does this. */
+/* Voigt function of pu/src/voigt.c:132-200, K(x, y) * sqrt(ln2/pi) / alphaD, as float.
+   Region I (x < 3, y < 1.8): w(z) = exp(-z^2) (1 + (2i/sqrt(pi)) int_0^z exp(t^2) dt) with the
+   integral as its Maclaurin series sum_k z^(2k+1) / (k! (2k+1)), carried here as the running power
+   p_k = -i z^(2k+1) (long double, like the reference).  Regions II / III: Pierluissi's sums over
+   poles, Re sum_j c_j / (z^2 - s_j) written out in real arithmetic.  The order of the floating-point
+   operations follows the reference's expressions.                                            */
+typedef struct { long double re, im; } cxl;
 static float voigtxy(double x, double y, double alphaD){
-  /* series coefficients 1/(n!(2n+1)) (the table at voigt.c:47-108) are generated on the fly */
-  const double A1=0.46131350, A2=0.19016350, A3=0.09999216, A4=1.78449270, A5=0.002883894,
-               A6=5.52534370, B1=0.51242424, B2=0.27525510, B3=0.05176536, B4=2.72474500;
-  const double SQRTLN2PI = 0.46971863934982566689, TWOOSQRTPI = 1.12837916709551257389;
-  const long double x2y2 = x*x - y*y, xy2 = 2*x*y;
+  static const double pole2[3][2] = {{0.46131350, 0.19016350}, {0.09999216, 1.78449270},
+                                     {0.002883894, 5.52534370}};      /* {weight, shift}, region II  */
+  static const double pole3[2][2] = {{0.51242424, 0.27525510}, {0.05176536, 2.72474500}};
+  const double norm = 0.46971863934982566689 / alphaD;                /* sqrt(ln 2 / pi) / alphaD    */
+  const double two_over_sqrtpi = 1.12837916709551257389;
+  const cxl zsq = {(long double)(x*x - y*y), (long double)(2*x*y)};   /* z^2, z = x + i y            */
   if (x < 3 && y < 1.8){
-    const long double cosxy = cosl(xy2), sinxy = sinl(xy2);
-    int n = (x < 1 ? 15 : (int)(6.842*x + 8.0)) + 1, i;
-    long double orr = y, oi = -x, ar = y, ai = -x, nr, ni, fac = 1.0L;
-    for (i=1; i<=n; i++){
-      ni = orr*xy2 + oi*x2y2;
-      nr = orr*x2y2 - oi*xy2;
-      fac *= i;                                  /* i! */
-      long double f = 1.0L/(fac*(2*i+1));        /* table value ferf[i] */
-      ai += ni*f;
-      ar += nr*f;
-      oi = ni; orr = nr;
+    const int nterms = (x < 1 ? 15 : (int)(6.842*x + 8.0)) + 1;
+    cxl pw = {y, -x};                                                 /* -i z                        */
+    cxl sum = pw;
+    long double kfact = 1.0L;
+    int k;
+    for (k = 1; k <= nterms; k++){
+      const cxl nx = {pw.re*zsq.re - pw.im*zsq.im, pw.re*zsq.im + pw.im*zsq.re};   /* pw * z^2      */
+      kfact *= k;
+      const long double coef = 1.0L/(kfact*(2*k + 1));
+      sum.im += nx.im*coef;
+      sum.re += nx.re*coef;
+      pw = nx;
     }
-    return (float)(SQRTLN2PI/alphaD*exp(-x2y2)*
-                   (cosxy*(1-ar*TWOOSQRTPI) - sinxy*ai*TWOOSQRTPI));
+    return (float)(norm*exp(-zsq.re)*(cosl(zsq.im)*(1 - sum.re*two_over_sqrtpi) -
+                                      sinl(zsq.im)*sum.im*two_over_sqrtpi));
   }
-  long double ar = xy2*xy2, nr = xy2*x;
-  if (x < 5 && y < 5){
-    long double ni = x2y2-A2, ai = x2y2-A4, oi = x2y2-A6;
-    return (float)(SQRTLN2PI/alphaD*(A1*((nr-ni*y)/(ni*ni+ar)) + A3*((nr-ai*y)/(ai*ai+ar)) +
-                                     A5*((nr-oi*y)/(oi*oi+ar))));
+  {
+    const long double im2 = zsq.im*zsq.im, xim = zsq.im*x;
+    const int np = (x < 5 && y < 5) ? 3 : 2;
+    const double (*pole)[2] = np == 3 ? pole2 : pole3;
+    long double acc = 0.0L;
+    int j;
+    for (j = 0; j < np; j++){
+      const long double d = zsq.re - pole[j][1];
+      const long double term = pole[j][0]*((xim - d*y)/(d*d + im2));
+      acc = j == 0 ? term : acc + term;
+    }
+    return (float)(norm*acc);
   }
-  long double ni = x2y2-B2, ai = x2y2-B4;
-  return (float)(SQRTLN2PI/alphaD*(B1*((nr-ni*y)/(ni*ni+ar)) + B3*((nr-ai*y)/(ai*ai+ar))));
 }
 
 /* pu/src/voigt.c:369-483 (voigtn), 489-554 (meanintegSimp / meanintegTrap, float math)    */
