@@ -280,12 +280,38 @@ SHAPES = {
 }
 
 
+def read_tea_atm(path):
+    """Parse a TEA-style atmosphere file (the layout readatm.c:425-470 reads): -> species, radius,
+    pressure (file units), temperature, abundances[layer][species].  For building proposal models
+    from an atmosphere file that was not written by write_atm."""
+    species, rows, section = None, [], None
+    for line in open(path):
+        t = line.strip()
+        if not t:
+            continue
+        if t.startswith("#"):
+            section = t[1:].strip().upper()
+            continue
+        if section == "SPECIES" and species is None:
+            species = t.split()
+            continue
+        parts = t.split()
+        try:
+            vals = [float(x) for x in parts]
+        except ValueError:
+            continue                                     # unit keywords: ur / up / q ...
+        if species is not None and len(vals) == 3 + len(species):
+            rows.append(vals)
+    a = np.array(rows)
+    return species, a[:, 0], a[:, 1], a[:, 2], a[:, 3:]
+
+
 def make_case(workdir, shape="demo", solution="eclipse", seed=12345, nlayer=100,
               tlow=400.0, thigh=3000.0, tempdelt=100.0, with_cia=True, with_grid=True,
               nlines=0, wnosamp=2160, extra_cfg=None, nfilters=None, overrides=None,
               cia_path=None, starrad=1.155, refpress=0.1, gsurf=1165.02,
               refradius_km=123820.0, ethresh=1e-6, nwidth=20, outputs=False, verb=0,
-              no_opacity=False, cia_h2he=False):
+              no_opacity=False, cia_h2he=False, atm_path=None, mol_path=None):
     """Create every input file of one configuration under `workdir`; returns paths + arrays."""
     os.makedirs(workdir, exist_ok=True)
     sh = dict(SHAPES[shape]) if isinstance(shape, str) else dict(shape)
@@ -299,9 +325,14 @@ def make_case(workdir, shape="demo", solution="eclipse", seed=12345, nlayer=100,
     case = dict(workdir=workdir, shape=sh, wn=wn, press_bar=press, temp=temp,
                 abund=np.tile(abund, (nlayer, 1)), species=list(SPECIES), solution=solution,
                 nlayer=nlayer)
-    case["molfile"] = write_molecules(P("molecules.dat"))
-    case["atm"] = write_atm(P("atm.dat"), press, temp, abund, gsurf=gsurf,
-                            r0_km=refradius_km * 0.97)
+    case["molfile"] = mol_path or write_molecules(P("molecules.dat"))
+    if atm_path:          # an existing atmosphere file (e.g. the reference's shipped demo atmosphere)
+        sp, _, press, temp, ab = read_tea_atm(atm_path)
+        nlayer = len(press)
+        case.update(press_bar=press, temp=temp, abund=ab, species=list(sp), nlayer=nlayer, atm=atm_path)
+    else:
+        case["atm"] = write_atm(P("atm.dat"), press, temp, abund, gsurf=gsurf,
+                                r0_km=refradius_km * 0.97)
     if with_cia:
         case["cia"] = cia_path or write_cia(P("CIA_H2H2_synth.dat"))
         if cia_h2he:      # a second, two-species table like examples/WASP-12b/BART.cfg's H2-He file

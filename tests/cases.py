@@ -15,6 +15,9 @@ from bart_b200 import synth  # noqa: E402
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 
+REF_INPUTS = {k: os.path.join(GOLDEN_DIR, "ref_inputs", v) for k, v in
+              (("atm", "HD209458b_demo.atm"), ("mol", "molecules.dat"), ("cia", "CIA_H2H2_400-7000K.dat"))}
+
 # name -> (make_case kwargs, n_models, model seed, setters)
 CASES = {
     "tiny_eclipse": (dict(shape="tiny", solution="eclipse", seed=12345), 3, 99, {}),
@@ -48,6 +51,13 @@ CASES = {
     "tiny_eclipse_9": (dict(shape="tiny", solution="eclipse", seed=885, nlayer=9), 2, 86, {}),
     "tiny_eclipse_t20": (dict(shape="tiny", solution="eclipse", seed=4243,
                               overrides={"toomuch": 20.0}, nlayer=60), 2, 92, {}),
+    # the input files the reference ships (tests/golden/ref_inputs/: TEA demo atmosphere, molecules.dat,
+    # the H2-H2 CIA table of examples/demo) through the product's readers, demo spectral range
+    "real_inputs_eclipse": (dict(shape="demo", solution="eclipse", seed=2024, atm_path=REF_INPUTS["atm"],
+                                 mol_path=REF_INPUTS["mol"], cia_path=REF_INPUTS["cia"]), 3, 85, {}),
+    "real_inputs_transit": (dict(shape="demo", solution="transit", seed=2025, atm_path=REF_INPUTS["atm"],
+                                 mol_path=REF_INPUTS["mol"], cia_path=REF_INPUTS["cia"],
+                                 refradius_km=95000.0), 2, 84, {"radius": 94300.0}),
 }
 
 
