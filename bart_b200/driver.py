@@ -129,6 +129,39 @@ class LibComm:
         return np.concatenate([recv[r, :c] for r, c in enumerate(counts)], axis=0)
 
 
+# ---------------------------------------------------------------------------------------------
+# System parameters of the converter set-up (code/BARTfunc.py:157-172,204-211)
+RSUN, RJUP, MJUP = 6.96e8, 7.1492e7, 1.8983e27        # code/constants.py (m, m, kg)
+AU, GNEWT = 149597870700.0, 6.6743e-11                # scipy.constants au, G (CODATA 2018)
+
+
+def read_tep(path):
+    """Parameter -> list of value strings of a TEP file (code/reader.py File: `name value uncert
+    unit origin  # comment` lines; the first occurrence of a name wins like reader.checkpar)."""
+    out = {}
+    for line in open(path):
+        t = line.split("#", 1)[0].split()
+        if t and t[0] not in out:
+            out[t[0]] = t[1:]
+    return out
+
+
+def system_from_tep(path, tint=100.0):
+    """What BARTfunc.py:157-172 extracts from the TEP file and 204-211 derives from it: stellar
+    temperature [K] and radius [m], semi-major axis [m], planetary radius [m] and mass [kg], surface
+    gravity [cm s-2]; `pt_args` is the tuple Transit.converter_init takes for PT_line, `rprs` the
+    radius ratio of the eclipse band integration (BARTfunc.py:246)."""
+    v = read_tep(path)
+    tstar = float(v["Ts"][0])
+    rstar = float(v["Rs"][0]) * RSUN
+    sma = float(v["a"][0]) * AU
+    rplanet = float(v["Rp"][0]) * RJUP
+    mplanet = float(v["Mp"][0]) * MJUP
+    gplanet = 100.0 * GNEWT * mplanet / rplanet ** 2
+    return dict(tstar=tstar, rstar=rstar, sma=sma, rplanet=rplanet, mplanet=mplanet, gplanet=gplanet,
+                pt_args=(rstar, tstar, float(tint), sma, gplanet), rprs=rplanet / rstar)
+
+
 def evaluate_generation(evaluate, params_all, comm):
     """One MCMC generation: `params_all[nchains, npars]` (identical on every rank, as after MC3's
     proposal step) -> band fluxes [nchains, nfilters] on every rank."""

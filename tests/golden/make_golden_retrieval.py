@@ -20,7 +20,7 @@ Shims applied from the outside, none to the reference sources: `numpy.int/float`
 from numpy 2), stub `matplotlib` and `dwt` modules (absent / built on a removed numpy C API; neither
 is used on this path).
 
-    python tests/golden/make_golden_retrieval.py [pt] [ptsmooth] [conv] [demc] [snooker]
+    python tests/golden/make_golden_retrieval.py [pt] [ptsmooth] [tep] [conv] [demc] [snooker]
 """
 import glob
 import os
@@ -124,6 +124,30 @@ def golden_pt_smooth(pt):
             print("retrieval_pt_smooth %s/%s: %d physical of %d, T %.0f..%.0f K" % (
                 name, tag, ok.sum(), len(ok), T[ok == 1].min(), T[ok == 1].max()))
     np.savez_compressed(os.path.join(HERE, "retrieval_pt_smooth.npz"), **out)
+
+
+def golden_tep():
+    """tep_systems.npz: the system parameters BARTfunc.py:157-172,204-211,246 extracts from a TEP file
+    with the reference's code/reader.py and constants -- statements executed verbatim -- on the two TEP
+    files the reference ships (copied to tests/golden/ref_inputs/ as data fixtures)."""
+    import shutil
+    import reader as rd
+    import constants as c
+    import scipy.constants as sc
+    out = {}
+    for name, path in (("wasp12b", os.path.join(REF, "examples", "WASP-12b", "WASP-12b.tep")),
+                       ("hd209458b", os.path.join(REF, "inputs", "tep", "HD209458b.tep"))):
+        tep = rd.File(path)
+        tstar = float(tep.getvalue('Ts')[0])
+        rstar = float(tep.getvalue('Rs')[0]) * c.Rsun
+        sma = float(tep.getvalue('a')[0]) * sc.au
+        rplanet = float(tep.getvalue('Rp')[0]) * c.Rjup
+        mplanet = float(tep.getvalue('Mp')[0]) * c.Mjup
+        gplanet = 100.0 * sc.G * mplanet / rplanet**2
+        out[name] = np.array([tstar, rstar, sma, rplanet, mplanet, gplanet, rplanet / rstar])
+        shutil.copy(path, os.path.join(HERE, "ref_inputs", os.path.basename(path)))
+    np.savez(os.path.join(HERE, "tep_systems.npz"), **out)
+    print("tep_systems.npz:", {k: v[:3] for k, v in out.items()})
 
 
 def golden_converter(pt, name, tmp):
@@ -326,6 +350,8 @@ def main():
         golden_pt_smooth(pt)
     if want("gr"):
         golden_gr()
+    if want("tep"):
+        golden_tep()
     with tempfile.TemporaryDirectory() as tmp:
         for name in cases.RETRIEVAL:
             if want("conv"):

@@ -25,6 +25,18 @@ def test_expn2_and_pt_models_vs_reference():
         assert np.array_equal(ro.PT_adiabatic(p, *q), T)
 
 
+def test_system_parameters_from_tep_files():
+    """driver.system_from_tep against the reference's reader.py + BARTfunc.py:157-172,204-211 on the
+    two TEP files the reference ships."""
+    from bart_b200 import driver
+    g = np.load(os.path.join(G, "tep_systems.npz"))
+    for name, fn in (("wasp12b", "WASP-12b.tep"), ("hd209458b", "HD209458b.tep")):
+        s = driver.system_from_tep(os.path.join(G, "ref_inputs", fn), tint=100.0)
+        got = np.array([s["tstar"], s["rstar"], s["sma"], s["rplanet"], s["mplanet"], s["gplanet"], s["rprs"]])
+        assert np.array_equal(got, g[name]), (name, got, g[name])
+        assert s["pt_args"] == (s["rstar"], s["tstar"], 100.0, s["sma"], s["gplanet"])
+
+
 def test_smoothed_pt_models_vs_reference():
     """PT_NoInversion / PT_Inversion / PT_piette (incl. the restated scipy Gaussian filter and
     degree-1 spline) against code/PT.py on two pressure grids; the parameter sets PT.py refuses
