@@ -468,6 +468,39 @@ def kernel_stats():
     return out
 
 
+def read_kurucz(kfile, temperature, logg):
+    """Stellar spectrum of the Kurucz grid model nearest to (temperature, logg): what
+    code/wine.py:69-124 `readkurucz` returns through code/kurucz_inten.py:162-318 -- (starfl [erg s-1
+    cm-2 cm], starwn [cm-1] ascending, model temperature, model log g).  File layout: a FORTRAN
+    reader as preamble ending in a line `END`, the wavelength table (nm, 10-character fields), then
+    per model a `TEFF ... GRAVITY ...` line, the line-blanketed Eddington fluxes and the continuum
+    fluxes (10-character fields, erg cm-2 s-1 Hz-1 sr-1).  Only the selected model is parsed."""
+    c_light = 299792458.0                                     # scipy.constants.c
+    with open(kfile, "r") as f:
+        lines = f.read().replace("\r", "\n").split("\n")
+    heads = [i for i, ln in enumerate(lines) if ln.startswith("TEFF")]
+    temp = np.array([float(lines[i][5:12]) for i in heads])
+    grav = np.array([float(lines[i][22:29]) for i in heads])
+    start = max(i for i, ln in enumerate(lines[:heads[0]]) if ln.endswith("END")) + 1
+    fields = lambda block: [float(block[j:j + 10]) for j in range(0, len(block), 10) if block[j:j + 10].strip()]
+    wave = np.array(fields("".join(lines[start:heads[0]])))
+    wave = wave[wave != 0] * 1e-9                             # nm -> m
+    nline = (heads[2] - heads[1] - 1) // 2
+    tmodel = temp[np.argmin(np.abs(temp - temperature))]
+    gmodel = grav[np.argmin(np.abs(grav - logg))]
+    imodel = np.where((temp == tmodel) & (grav >= gmodel))[0][0]
+    h = heads[imodel]
+    inten = np.zeros(wave.size)
+    vals = fields("".join(lines[h + 1:h + 1 + nline]))
+    inten[:len(vals)] = vals[:wave.size]
+    inten *= 4.0 * 1e-3                                       # Eddington flux -> brightness, cgs -> MKS
+    freq = np.flipud(c_light / wave)
+    inten = inten[::-1]
+    starwn = freq / c_light * 1e-2
+    starfl = inten * 1e3 * np.pi * (1e2 * c_light)            # per Hz -> per cm-1, MKS -> cgs, sr-1 -> flux
+    return starfl, starwn, tmodel, gmodel
+
+
 def filters_from_files(specwn, filter_files, starwn=None, starfl=None):
     """Host-side precompute of stage (c): the same resampling BARTfunc.py:245-291 does with
     wine.readfilter / wine.resample (linear interpolation of filter and stellar spectrum onto the

@@ -68,3 +68,17 @@ def test_api_filters_from_files(name, tmp_path):
         band = 0.5 * np.sum(np.diff(specwn[idx]) * (y[1:] + y[:-1]))
         assert abs(band / G[key + "band_eclipse"] - 1) < 1e-12
         off += count[i]
+
+
+def test_read_kurucz_vs_reference():
+    """api.read_kurucz against wine.readkurucz (golden wine.npz) on the Kurucz grid the reference
+    ships (11.8 MB: read from /root/reference, so this runs in the build container only)."""
+    import pytest
+    from bart_b200 import api
+    kfile = "/root/reference/inputs/kurucz/fp00k2odfnew.pck"
+    if not os.path.exists(kfile):
+        pytest.skip("the reference's Kurucz grid is not on this machine")
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "wine.npz"))
+    starfl, starwn, tmodel, gmodel = api.read_kurucz(kfile, 6000.0, 4.5)
+    assert np.array_equal(starwn, g["starwn"]) and np.array_equal(starfl, g["starfl"])
+    assert (tmodel, gmodel) == tuple(g["star_model"])
