@@ -146,6 +146,19 @@ def read_tep(path):
     return out
 
 
+def read_atm(atmfile):
+    """species, pressure, temperature, abundances[layer][species] of a TEA atmosphere file, with or
+    without a radius column -- what code/makeatm.py:753-848 `readatm` hands to BARTfunc.py:185 (the
+    converter must see the file's printed pressures and abundances, not the values they were
+    rounded from)."""
+    lines = open(atmfile).readlines()
+    species = lines[lines.index("#SPECIES\n") + 1].split()
+    start = lines.index("#TEADATA\n") + 2
+    rows = np.array([[float(x) for x in ln.split()] for ln in lines[start:] if ln.strip()])
+    first = rows.shape[1] - len(species) - 2               # 1 with a radius column, else 0
+    return species, rows[:, first], rows[:, first + 1], rows[:, first + 2:]
+
+
 def system_from_tep(path, tint=100.0):
     """What BARTfunc.py:157-172 extracts from the TEP file and 204-211 derives from it: stellar
     temperature [K] and radius [m], semi-major axis [m], planetary radius [m] and mass [kg], surface

@@ -80,3 +80,34 @@ def test_replay_on_cuda_transit_module(workdir):
         else:
             raise AssertionError("the worker called %s, which the replay does not know" % name)
     assert k == 4
+
+
+@pytest.mark.gpu
+def test_device_worker_equals_unmodified_bartfunc(workdir):
+    """The whole worker iteration on the device -- parameters -> PT profile, abundance scaling, the
+    two rejections, forward model, band integration (bart_bandflux_from_params) -- set up the way
+    BARTfunc.py:139-222 sets itself up (TEP file, atmosphere, molfit, filters), against the band
+    fluxes the UNMODIFIED BARTfunc.main sent back to MC3 for the same parameter vectors."""
+    from bart_b200 import api, driver, synth
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden_bartfunc as gen                 # the generator's constants (TEP text, molfit)
+    case = synth.make_case(os.path.join(workdir, "bartfunc_case_dev"), **json.loads(str(G["case"])))
+    tepfile = os.path.join(workdir, "planet.tep")
+    open(tepfile, "w").write(gen.TEP)
+    sysp = driver.system_from_tep(tepfile, tint=100.0)
+    assert abs(sysp["rprs"] / float(G["rprs"]) - 1) < 1e-15
+    tr = api.Transit(case["cfg"])
+    tr.set_filters(G["start"].astype(np.int32), G["count"].astype(np.int32), G["weight"], G["star"],
+                   sysp["rprs"])
+    species, press, _, abund = driver.read_atm(case["atm"])          # BARTfunc.py:185 (mat.readatm)
+    assert species == case["species"] and np.allclose(press, case["press_bar"], rtol=1e-4)
+    npars = tr.converter_init(press, species, abund, gen.MOLFIT, "line",
+                              pt_args=sysp["pt_args"], tmin=400.0, tmax=3000.0)   # BARTfunc's defaults
+    assert npars == G["params"].shape[1]
+    bf, status = tr.bandflux_from_params(G["params"])
+    ref = G["bandflux"]
+    rej = ref[:, 0] == -1
+    assert list(status[rej]) == [16, 32] and (bf[rej] == -1).all()    # BARTfunc.py:327-330, 339-344
+    assert (status[~rej] == 0).all()
+    assert np.max(np.abs(bf[~rej] / ref[~rej] - 1)) < 1e-8
+    tr.free_memory()
