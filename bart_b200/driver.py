@@ -175,6 +175,56 @@ def system_from_tep(path, tint=100.0):
                 pt_args=(rstar, tstar, float(tint), sma, gplanet), rprs=rplanet / rstar)
 
 
+class BartWorker:
+    """One BART worker (code/BARTfunc.py::main) for a batch of proposals: reads the same `[MCMC]`
+    configuration section BARTfunc reads (config_file keys of BARTfunc.py:49-121: tconfig, atmfile,
+    PTtype, tint, tint_type, molfit, Tmin, Tmax, filters, tep_name, kurucz, solution, cloudtop,
+    scattering, ebalance), sets up transit, the input converter and the output converter on the
+    device, and maps parameter vectors [M][npars] to band fluxes [M][nfilters] (rejected proposals:
+    -1, like the arrays BARTfunc gathers).  `star=(starwn, starfl)` overrides the Kurucz file."""
+
+    def __init__(self, cfgfile, device=None, star=None, section="MCMC"):
+        import configparser
+        from . import api
+        cp = configparser.ConfigParser(inline_comment_prefixes=("#",))
+        cp.optionxform = str
+        cp.read([cfgfile])
+        get = lambda k, d=None: cp.get(section, k) if cp.has_option(section, k) else d
+        self.solution = get("solution")
+        if self.solution not in ("transit", "eclipse", "direct"):
+            raise ValueError("solution must be transit, eclipse or direct (BARTfunc.py:117)")
+        self.molfit = (get("molfit") or "").split()
+        pttype = get("PTtype", "none")
+        cloudtop, scattering = get("cloudtop"), get("scattering")
+        self.tr = tr = api.Transit(get("tconfig"), device=device)
+        wn = tr.get_waveno_arr()
+        filters = (get("filters") or "").split()
+        sysp = system_from_tep(get("tep_name"), tint=float(get("tint", 100.0))) if get("tep_name") else None
+        if self.solution in ("eclipse", "transit") and star is None and get("kurucz"):
+            logg = float(read_tep(get("tep_name"))["loggstar"][0])
+            starfl, starwn, _, _ = api.read_kurucz(get("kurucz"), sysp["tstar"], logg)
+            star = (starwn, starfl)
+        if self.solution == "eclipse":                       # BARTfunc.py:244-270, 388-391
+            tr.set_filters(*api.filters_from_files(wn, filters, star[0], star[1]), sysp["rprs"])
+        else:                                                # transit / direct: no stellar division
+            start, count, weight, _ = api.filters_from_files(wn, filters)
+            tr.set_filters(start, count, weight, None, 1.0)
+        species, press, _, abund = read_atm(get("atmfile"))
+        nray = 0 if scattering is None else (2 if "polar" in scattering else 1)
+        self.npars = tr.converter_init(
+            press, species, abund, self.molfit, pttype, pt_args=sysp["pt_args"] if pttype == "line" else None,
+            tint_type=get("tint_type", "const"), tmin=float(get("Tmin", 400.0)), tmax=float(get("Tmax", 3000.0)),
+            nrad=int(self.solution == "transit"), ncloud=int(cloudtop is not None), nray=nray)
+        if str(get("ebalance", "False")).strip() in ("True", "1"):
+            tr.set_energy_balance(sysp["tstar"], sysp["rstar"], sysp["sma"], sysp["rplanet"])
+
+    def __call__(self, params):
+        return self.tr.bandflux_from_params(params)[0]
+
+    def close(self):
+        self.tr.free_memory()
+
+
 def evaluate_generation(evaluate, params_all, comm):
     """One MCMC generation: `params_all[nchains, npars]` (identical on every rank, as after MC3's
     proposal step) -> band fluxes [nchains, nfilters] on every rank."""

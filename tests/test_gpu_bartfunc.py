@@ -111,3 +111,40 @@ def test_device_worker_equals_unmodified_bartfunc(workdir):
     assert (status[~rej] == 0).all()
     assert np.max(np.abs(bf[~rej] / ref[~rej] - 1)) < 1e-8
     tr.free_memory()
+
+
+@pytest.mark.gpu
+def test_bartworker_from_the_mcmc_configuration(workdir):
+    """driver.BartWorker reads the [MCMC] section BARTfunc reads (the one the golden run used, minus
+    the Kurucz file, which does not travel: the stellar spectrum wine.readkurucz returned is passed
+    in) and returns what the unmodified BARTfunc gathered."""
+    from bart_b200 import driver, synth
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden_bartfunc as gen
+    case = synth.make_case(os.path.join(workdir, "bartfunc_case_cfg"), **json.loads(str(G["case"])))
+    tepfile = os.path.join(workdir, "planet2.tep")
+    open(tepfile, "w").write(gen.TEP)
+    cfg = os.path.join(workdir, "MCMC.cfg")
+    with open(cfg, "w") as f:                              # as make_golden_bartfunc.main writes it
+        f.write("[MCMC]\n")
+        f.write("params = %s\n" % " ".join("%r" % v for v in gen.PARAMS[0]))
+        f.write("molfit = %s\n" % " ".join(gen.MOLFIT))
+        f.write("atmfile = %s\nPTtype = line\ntint = 100.0\ntint_type = const\n" % case["atm"])
+        f.write("tconfig = %s\n" % case["cfg"])
+        f.write("filters = %s\n" % "\n    ".join(case["filters"]))
+        f.write("tep_name = %s\nsolution = eclipse\n" % tepfile)
+    # the star on the spectrum grid, as wine.resample left it in the fixture: rebuild (wn, flux) pairs
+    # that interpolate to exactly those values on every filter's sample range
+    wn = G["specwn"]
+    starfl = np.interp(wn, wn, np.ones_like(wn))
+    off = np.concatenate([[0], np.cumsum(G["count"])])
+    for i in range(len(G["start"])):
+        starfl[G["start"][i]:G["start"][i] + G["count"][i]] = G["star"][off[i]:off[i + 1]]
+    w = driver.BartWorker(cfg, star=(wn, starfl))
+    assert w.npars == G["params"].shape[1] and w.tr.nfilters == len(G["start"])
+    bf = w(G["params"])
+    ref = G["bandflux"]
+    rej = ref[:, 0] == -1
+    assert (bf[rej] == -1).all()
+    assert np.max(np.abs(bf[~rej] / ref[~rej] - 1)) < 1e-8
+    w.close()
