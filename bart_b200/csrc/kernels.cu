@@ -570,8 +570,10 @@ transit_mma_kernel(DevConfig c, const double *__restrict__ tabs, const double *_
       const double v = c.wn[min(wa + 32 * k, c.nwave - 1)];
       wn4[k] = (v * v) * (v * v);
     }
+    // x[0][k].q holds the CIA samples of the current bracket rows: a load with `fresh` false leaves
+    // them in place (one stage only: kMmLoadBatch is 1)
+    static_assert(kMmLoadBatch == 1, "the CIA samples live in the single load stage");
     CellData<NMOL, NCIA> x[kMmLoadBatch][2];
-    D4 pq[2][CellData<NMOL, NCIA>::NC];                        // CIA samples of the current bracket rows
     CellOffs<NCIA> have;
     bool first = true;
     for (int ch = 0; ch < nchunks; ch++) {
@@ -604,12 +606,6 @@ transit_mma_kernel(DevConfig c, const double *__restrict__ tabs, const double *_
             double ev[2];
 #pragma unroll
             for (int k = 0; k < 2; k++) {
-              if (CellData<NMOL, NCIA>::kStaticCia) {
-#pragma unroll
-                for (int f = 0; f < (NCIA > 0 ? NCIA : 0); f++) {
-                  if (fresh[j]) pq[k][f] = x[j][k].q[f]; else x[j][k].q[f] = pq[k][f];
-                }
-              }
               ev[k] = cell_combine<NMOL, NCIA, SC>(c, P, s_tab + (size_t)d * nf, x[j][k], wn4[k], false, k * gstep, k * cstep);
             }
 #pragma unroll
