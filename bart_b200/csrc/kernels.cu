@@ -559,7 +559,10 @@ transit_mma_kernel(DevConfig c, const double *__restrict__ tabs, const double *_
     // bracket row (as in eclipse_columns).  Columns past the end of the spectrum read the padding.
     // (Measured alternative: two tensor-core warps with 16 x 32 tiles and six producer warps, the
     // next depth's loads in flight while the current one is combined -- 12.3 ms against 8.3 ms: the
-    // second register stage spills.)
+    // second register stage spills.  Without a second stage, the next depth's loads issued column by
+    // column under the other column's arithmetic: 7.87 against 7.73 ms; an L1 prefetch of the next
+    // depth's samples: 7.99 against 7.74; the consumer warps looking up half of the first chunk
+    // instead of waiting for it: 7.76 / 7.70 against 7.73 / 7.80 at the W12 / demo shapes, i.e. nothing.)
     const int wa = tile * kMmW + lane;
     const ColPtrs P = col_ptrs<NCIA>(c, wa);
     constexpr bool kStatic = CellData<NMOL, NCIA>::kStatic;
