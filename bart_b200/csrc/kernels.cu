@@ -150,7 +150,9 @@ atm_prep_kernel(DevConfig c, Knobs knobs, const double *__restrict__ profiles, i
 // fused eclipse column kernel
 // 128 registers, 8 CTAs (16 warps) per SM.  Measured alternatives (W12, 4096 models): 112 registers /
 // 18 warps 4.43 ms (spills go through the L1 data pipe, the busiest unit), 144 registers / 14 warps
-// 5.07 ms, against 4.07 ms.
+// 5.07 ms, against 4.07 ms.  One column per thread (the slot kernel's arithmetic) in CTAs of 128 threads
+// at 72 registers, 28 warps per SM: 4.30 against 4.12 ms -- the depth's table record is then read per
+// column and the Planck chaining is lost; the kernel is bound by its pipes, not by latency.
 template <int NMOL, int NCIA, int NANG, bool KEEP, int SQ, bool SC>
 __global__ void __launch_bounds__(kEclThreads, 8)
 eclipse_column_kernel(DevConfig c, const double *__restrict__ tabs, const int *__restrict__ status,
