@@ -368,24 +368,42 @@ BART_HD KnobVals knobs_for(const Knobs &k, int m) {
 }
 
 // ---------------------------------------------------------------------------------------
+// The configuration arrays the preparation stages read, by pointer: atm_prep_kernel points them at
+// its shared-memory copies (the kernel parameter itself stays read-only), everything else at the
+// configuration's own arrays (prep_ptrs_of).
+struct PrepPtrs {
+  const double *press, *gtemp, *mass, *pol;
+  const double *ciaT[kMaxCia];
+};
+BART_HD PrepPtrs prep_ptrs_of(const DevConfig &c) {
+  PrepPtrs q;
+  q.press = c.press; q.gtemp = c.gtemp; q.mass = c.mass; q.pol = c.pol;
+  for (int f = 0; f < kMaxCia; f++) q.ciaT[f] = c.ciaT[f];
+  return q;
+}
+
 // atm_prep stage 1, one layer: mean molecular mass and mass densities.
 // Reference: checkaddmm readatm.c:122-159 (number abundances), stateeqnford transit.h:58-69,
 // reloadatm readatm.c:722-784.  rho[j*rho_stride] receives the density of species j.
-BART_HD int prep_layer(const DevConfig &c, const double *in, int l, double *rho, int rho_stride,
-                       double *mu_out) {
+BART_HD int prep_layer(const DevConfig &c, const PrepPtrs &pp, const double *__restrict__ in, int l,
+                       double *__restrict__ rho, int rho_stride, double *mu_out) {
   const int nl = c.nlayer;
   const double T = in[l];
-  const double p = c.press[l] * c.pfct;
+  const double p = pp.press[l] * c.pfct;
   double mu = 0.0, sumq = 0.0;
   for (int j = 0; j < c.nspec; j++) {
     const double q = in[(size_t)nl * (j + 1) + l];
-    mu += q * c.mass[j];
+    mu += q * pp.mass[j];
     sumq += q;
     const double r = cAMU * q * p / cKB / T;
-    rho[(size_t)j * rho_stride] = r * c.mass[j];
+    rho[(size_t)j * rho_stride] = r * pp.mass[j];
   }
   *mu_out = mu;
   return sumq > 1.001 ? REJ_SUMQ : 0;
+}
+BART_HD int prep_layer(const DevConfig &c, const double *in, int l, double *rho, int rho_stride,
+                       double *mu_out) {
+  return prep_layer(c, prep_ptrs_of(c), in, l, rho, rho_stride, mu_out);
 }
 
 // atm_prep stage 2: hydrostatic radii.  Reference: radpress readatm.c:787-865 integrates
@@ -395,9 +413,12 @@ BART_HD int prep_layer(const DevConfig &c, const double *in, int l, double *rho,
 // computed in parallel over layers (hydro_coef) and the sequential part is the two-instruction
 // recurrence r_i = r_{i+1} - hc_i r_{i+1}^2 / (g0 r0^2) (hydrostatic_radii); the gravity product
 // telescopes, so the results agree with the reference's running product to rounding (1e-15).
-BART_HD double hydro_coef(const DevConfig &c, const double *temp, const double *mu, int i) {
+BART_HD double hydro_coef(const DevConfig &c, const PrepPtrs &pp, const double *temp, const double *mu, int i) {
   return 0.5 * (temp[i] / mu[i] + temp[i + 1] / mu[i + 1]) *
-         (cKB / cAMU * log(c.press[i] / c.press[i + 1])) / c.rfct;
+         (cKB / cAMU * log(pp.press[i] / pp.press[i + 1])) / c.rfct;
+}
+BART_HD double hydro_coef(const DevConfig &c, const double *temp, const double *mu, int i) {
+  return hydro_coef(c, prep_ptrs_of(c), temp, mu, i);
 }
 
 // the layer nearest to the reference pressure p0 (first minimum of |p - p0|, radpress
@@ -412,10 +433,10 @@ inline int ref_layer_of(const double *press, int nl, double p0) {
   return i0;
 }
 
-BART_HD void hydrostatic_radii(const DevConfig &c, double r0, const double *temp, const double *mu,
-                               const double *hc, double *radius) {
+BART_HD void hydrostatic_radii(const DevConfig &c, const PrepPtrs &pp, double r0, const double *temp,
+                               const double *mu, const double *hc, double *radius) {
   const int nl = c.nlayer;
-  const double *pr = c.press;
+  const double *pr = pp.press;
   const double p0 = c.p0, g0 = c.gsurf, rfct = c.rfct;
   const int i0 = c.ref_layer;                 // nearest layer to the reference pressure (ref_layer_of)
   if (pr[i0] > p0) {
@@ -444,6 +465,11 @@ BART_HD void hydrostatic_radii(const DevConfig &c, double r0, const double *temp
   }
 }
 
+BART_HD void hydrostatic_radii(const DevConfig &c, double r0, const double *temp, const double *mu,
+                               const double *hc, double *radius) {
+  hydrostatic_radii(c, prep_ptrs_of(c), r0, temp, mu, hc, radius);
+}
+
 // floor-bracket search: the reference finds the NEAREST node (iomisc.c:1088-1108) and steps
 // down when the value is below it (extinction.c:560-564, spline.c:149-154), i.e. the largest k
 // with x[k] <= v, clamped so that k+1 is a valid node.
@@ -461,9 +487,9 @@ BART_HD int bracket(const double *x, int n, double v) {
 // atm_prep stage 3, one depth d (0 = top): every per-layer coefficient the column kernels need,
 // written as one record (layout: TabLayout).  temp/radius are indexed by layer (bottom -> top);
 // rho[j*rho_stride + layer].
-BART_HD int prep_table_row(const DevConfig &c, const KnobVals &kv, int d, const double *temp,
-                           const double *rho, int rho_stride, const double *radius, double *tab,
-                           int model = 0) {
+BART_HD int prep_table_row(const DevConfig &c, const PrepPtrs &pp, const KnobVals &kv, int d,
+                           const double *temp, const double *rho, int rho_stride, const double *radius,
+                           double *tab, int model = 0) {
   const TabLayout &L = c.lay;
   const int nl = c.nlayer;
   const int l = nl - 1 - d;
@@ -477,9 +503,9 @@ BART_HD int prep_table_row(const DevConfig &c, const KnobVals &kv, int d, const 
   row[L.GOFF + 1] = 0.0;
 
   // opacity-grid bracket and folded weights (interpolmolext, extinction.c:534-581)
-  if (T < c.gtemp[0] || T > c.gtemp[c.ntemp - 1]) status |= REJ_TGRID;
-  const int it = bracket(c.gtemp, c.ntemp, T);
-  const double t0 = c.gtemp[it], t1 = c.gtemp[it + 1];
+  if (T < pp.gtemp[0] || T > pp.gtemp[c.ntemp - 1]) status |= REJ_TGRID;
+  const int it = bracket(pp.gtemp, c.ntemp, T);
+  const double t0 = pp.gtemp[it], t1 = pp.gtemp[it + 1];
   row[L.GOFF] = bits_to_double((((long long)l * c.ntemp + it) * c.gms) * (long long)c.nwave * 8);
   if (c.lbl) {
     // line-by-line mode: the "grid" is ext[model][layer][wave] with the densities folded in
@@ -496,15 +522,17 @@ BART_HD int prep_table_row(const DevConfig &c, const KnobVals &kv, int d, const 
 
   // CIA: cubic-spline-in-T coefficients (splinterp_pt, spline.c:131-183) applied to the
   // wavenumber-pre-splined tables, times the density product (interpcs, crosssec.c:321-336)
-  for (int f = 0; f < c.ncia; f++) {
-    const double *x = c.ciaT[f];
+#pragma unroll
+  for (int f = 0; f < kMaxCia; f++) {
+    if (f >= c.ncia) break;
+    const double *x = pp.ciaT[f];
     const int nt = c.cia_nt[f];
     if (T < x[0] || T > x[nt - 1]) status |= REJ_TCIA;
     const int k = bracket(x, nt, T);
     double dens = 1.0;
     for (int s = 0; s < c.cia_nspec[f]; s++) {
       const int sp = c.cia_spec[f][s];
-      dens *= rho[(size_t)sp * rho_stride + l] / (cAMU * c.mass[sp] * cAMAGAT);
+      dens *= rho[(size_t)sp * rho_stride + l] / (cAMU * pp.mass[sp] * cAMAGAT);
     }
     double cy0, cy1, cz0, cz1;
     if (x[k] == T) { cy0 = 1.0; cy1 = 0.0; cz0 = 0.0; cz1 = 0.0; }
@@ -527,13 +555,13 @@ BART_HD int prep_table_row(const DevConfig &c, const KnobVals &kv, int d, const 
 
   // scattering (computeextscat, extinction.c:586-624): coefficient of wn^4
   double sc = 0.0;
-  if (kv.scat_flag == 1) sc = pow(10.0, kv.scat_logext) * cE0H2 * c.press[l] / T;
+  if (kv.scat_flag == 1) sc = pow(10.0, kv.scat_logext) * cE0H2 * pp.press[l] / T;
   else if (kv.scat_flag == 2) {
     const double k4 = (2.0 * cPI * cMICRON) * (2.0 * cPI * cMICRON) * (2.0 * cPI * cMICRON) *
                       (2.0 * cPI * cMICRON);
     for (int j = 0; j < c.nspec; j++)
-      sc += cPI * 8e-32 / 3.0 * (c.pol[j] * c.pol[j]) * k4 * rho[(size_t)j * rho_stride + l] /
-            c.mass[j] * cNAVO;
+      sc += cPI * 8e-32 / 3.0 * (pp.pol[j] * pp.pol[j]) * k4 * rho[(size_t)j * rho_stride + l] /
+            pp.mass[j] * cNAVO;
   }
   row[L.SCAT] = sc;
 
@@ -541,7 +569,7 @@ BART_HD int prep_table_row(const DevConfig &c, const KnobVals &kv, int d, const 
   double cl = 0.0;
   if (kv.cloud_flag == 1 && kv.cloudext != 0.0) {
     const double top = pow(10.0, kv.cloudtop), bot = pow(10.0, kv.cloudbot);
-    if (c.press[l] >= top && c.press[l] < bot) cl = kv.cloudext;
+    if (pp.press[l] >= top && pp.press[l] < bot) cl = kv.cloudext;
   }
   row[L.CLOUD] = cl;
 
@@ -565,6 +593,11 @@ BART_HD int prep_table_row(const DevConfig &c, const KnobVals &kv, int d, const 
   row[L.SC] = scf;
   row[L.TR] = tr;
   return status;
+}
+BART_HD int prep_table_row(const DevConfig &c, const KnobVals &kv, int d, const double *temp,
+                           const double *rho, int rho_stride, const double *radius, double *tab,
+                           int model = 0) {
+  return prep_table_row(c, prep_ptrs_of(c), kv, d, temp, rho, rho_stride, radius, tab, model);
 }
 
 // ---------------------------------------------------------------------------------------

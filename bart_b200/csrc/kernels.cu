@@ -101,10 +101,24 @@ __device__ __forceinline__ void stage_table(double *s_tab, const double *g_tab, 
 
 // ---------------------------------------------------------------------------------------
 // K0
+// Everything a model's preparation reads more than once -- its profile, the pressure / mass /
+// polarizability columns and the temperature axes the bracket searches walk (opacity grid, CIA
+// tables) -- is staged into shared memory by one round of coalesced loads, and the record table is
+// assembled there and written out as one coalesced stream: at MC3's population sizes (3-10 models per
+// launch) this kernel is a chain of memory latencies, not of arithmetic (a binary search over a
+// global array alone is five dependent ~0.3 us round trips).  Same arithmetic, same order.
+__host__ __device__ inline size_t atm_prep_smem_doubles(const DevConfig &c) {
+  size_t n = ((size_t)c.nspec + 3) * c.nlayer;                 // rho, mu, radius, hydrostatic coefficients
+  n += ((size_t)c.nspec + 1) * c.nlayer;                       // the model's profile
+  n += (size_t)c.nlayer + c.ntemp + 2 * (size_t)c.nspec;       // press, gtemp, mass, pol
+  for (int f = 0; f < c.ncia; f++) n += c.cia_nt[f];
+  n += (size_t)c.lay.stride();                                 // the record table
+  return n + 8;
+}
 __global__ void __launch_bounds__(128)
 atm_prep_kernel(DevConfig c, Knobs knobs, const double *__restrict__ profiles, int n_in,
                 double *__restrict__ tabs, int *__restrict__ status,
-                const int *__restrict__ pre_status, int nmodels) {
+                const int *__restrict__ pre_status, int nmodels, int staged) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int m = blockIdx.x;
   if (m >= nmodels) return;
@@ -119,23 +133,50 @@ atm_prep_kernel(DevConfig c, Knobs knobs, const double *__restrict__ profiles, i
   double *s_hc = s_rad + nl;                                   // [nl]
   __shared__ int s_status;
   if (threadIdx.x == 0) s_status = 0;
-  __syncthreads();
   const double *in = profiles + (size_t)m * n_in;
+  double *tab = tabs + (size_t)m * c.lay.stride();
+  const double *s_in = in;                                     // unstaged (very large configurations):
+  double *s_tabrec = tab;                                      // everything straight from / to HBM
+  PrepPtrs pp = prep_ptrs_of(c);
+  if (staged) {
+    double *w_in = s_hc + nl;                                  // [(1 + nspec)][nl]
+    double *s_press = w_in + ((size_t)c.nspec + 1) * nl;       // [nl]
+    double *s_gtemp = s_press + nl;                            // [ntemp]
+    double *s_mass = s_gtemp + c.ntemp;                        // [nspec]
+    double *s_pol = s_mass + c.nspec;                          // [nspec]
+    double *s_ciaT = s_pol + c.nspec;                          // [sum cia_nt]
+    const int nprof = (c.nspec + 1) * nl;
+    for (int i = threadIdx.x; i < nprof; i += blockDim.x) w_in[i] = in[i];
+    for (int i = threadIdx.x; i < nl; i += blockDim.x) s_press[i] = c.press[i];
+    for (int i = threadIdx.x; i < c.ntemp; i += blockDim.x) s_gtemp[i] = c.gtemp[i];
+    for (int i = threadIdx.x; i < c.nspec; i += blockDim.x) { s_mass[i] = c.mass[i]; s_pol[i] = c.pol ? c.pol[i] : 0.0; }
+    double *dst = s_ciaT;
+#pragma unroll
+    for (int f = 0; f < kMaxCia; f++)
+      if (f < c.ncia) {
+        for (int i = threadIdx.x; i < c.cia_nt[f]; i += blockDim.x) dst[i] = c.ciaT[f][i];
+        pp.ciaT[f] = dst;
+        dst += c.cia_nt[f];
+      }
+    pp.press = s_press; pp.gtemp = s_gtemp; pp.mass = s_mass; pp.pol = s_pol;
+    s_in = w_in;
+    s_tabrec = dst + ((reinterpret_cast<uintptr_t>(dst) & 8) ? 1 : 0);   // 16-byte aligned records
+  }
+  __syncthreads();
   int st = 0;
-  for (int l = threadIdx.x; l < nl; l += blockDim.x) st |= prep_layer(c, in, l, s_rho + l, nl, s_mu + l);
+  for (int l = threadIdx.x; l < nl; l += blockDim.x) st |= prep_layer(c, pp, s_in, l, s_rho + l, nl, s_mu + l);
   if (st) atomicOr(&s_status, st);
   __syncthreads();
   const KnobVals kv = knobs_for(knobs, m);
-  for (int l = threadIdx.x; l < nl - 1; l += blockDim.x) s_hc[l] = hydro_coef(c, in, s_mu, l);
+  for (int l = threadIdx.x; l < nl - 1; l += blockDim.x) s_hc[l] = hydro_coef(c, pp, s_in, s_mu, l);
   __syncthreads();
   if (knobs.radius_file) {
     for (int l = threadIdx.x; l < nl; l += blockDim.x) s_rad[l] = knobs.radius_file[l];
-  } else if (threadIdx.x == 0) hydrostatic_radii(c, kv.r0, in, s_mu, s_hc, s_rad);
+  } else if (threadIdx.x == 0) hydrostatic_radii(c, pp, kv.r0, s_in, s_mu, s_hc, s_rad);
   __syncthreads();
-  double *tab = tabs + (size_t)m * c.lay.stride();
   st = 0;
   for (int d = threadIdx.x; d < nl; d += blockDim.x)
-    st |= prep_table_row(c, kv, d, in, s_rho, nl, s_rad, tab, c.lbl_model0 + m);
+    st |= prep_table_row(c, pp, kv, d, s_in, s_rho, nl, s_rad, s_tabrec, c.lbl_model0 + m);
   if (c.lbl)
     for (int i = threadIdx.x; i < nl * c.nspec; i += blockDim.x) {
       const int l = i / c.nspec, j = i - l * c.nspec;
@@ -143,6 +184,10 @@ atm_prep_kernel(DevConfig c, Knobs knobs, const double *__restrict__ profiles, i
     }
   if (st) atomicOr(&s_status, st);
   __syncthreads();
+  if (staged) {
+    const int nd = c.lay.stride();
+    for (int i = threadIdx.x; i < nd; i += blockDim.x) tab[i] = s_tabrec[i];
+  }
   if (threadIdx.x == 0) status[m] = s_status;
 }
 
@@ -236,6 +281,154 @@ eclipse_slot_kernel(DevConfig c, const double *__restrict__ tabs, const int *__r
   eclipse_columns<NMOL, NCIA, NANG, false, 1, SQ, true, kEclThreads, NMOL == 0, SC>(c, s_tab, s_etab, w, valid, tk,
                                                                                     lk, flux, upper);
   if (valid[0]) out[w] = flux[0];
+}
+
+// Latency kernel for the smallest batches (one run_transit call, a 3-10 chain MC3 generation):
+// lanes <-> LAYERS.  A warp owns kScanCols adjacent wavenumber columns of one model at a time;
+// lane = (depth in round) * kScanCols + column, so one round covers 32 / kScanCols = 8 consecutive
+// depths of 4 columns, and the lookups, Planck functions and D(tau) of those depths proceed side by
+// side instead of as dependent steps of one thread (100 layers: 13 rounds instead of 100 steps):
+//   extinction  a lane reads ITS depth's table record (the four lanes of a depth broadcast) and its
+//               two 32-byte grid samples + one per CIA file; the four columns of a depth are
+//               contiguous in the grid, so a warp's load touches 8 full 128-byte lines like the
+//               throughput kernel's (lanes <-> 32 layers of ONE column measured 7 us per model: 32
+//               lines of one sector each per load);
+//   tau         top-aligned Simpson prefix (eclipse_columns above): the panel that ends at an even
+//               depth d is SA er[d] + SB er[d-1] + SC er[d-2] (neighbours by shuffle, the previous
+//               round's last two depths carried), tau(even d) = inclusive segmented scan of the
+//               panels over the round + carry, tau(odd d) = tau(d-1) + TR (er[d] + er[d-1]);
+//   last        first depth with tau > toomuch: ballot + find-first-set per column; a finished
+//               column idles and the warp leaves when its four columns are done;
+//   flux        trapezoid terms (D_d - D_{d-1})(B_d + B_{d-1}) for 1 <= d <= last summed per lane
+//               over the rounds, one butterfly reduction per column at the end.
+// The panels are summed in scan order, the series / exponentials choice for D(tau) is taken per lane
+// and the Planck exponential is not chained between columns: spectra agree with the throughput
+// kernel to the accuracy of those approximations (~1e-11 relative), not to the bit.  Configurations
+// outside the specialised instantiations (run-time molecule / CIA counts, the per-column Planck
+// clamp) stay on the slot kernel.
+constexpr int kScanThreads = 128;                // 4 warps: fine-grained CTAs balance a 10-model batch over the SMs
+constexpr int kScanCols = 4;                     // columns per warp task
+constexpr int kScanDepths = 32 / kScanCols;      // depths per round
+constexpr long long kScanMaxColumns = 40000;     // batches up to this many (model, wavenumber) columns take it
+template <int NMOL, int NCIA, int NANG, int SQ, bool SC>
+__device__ __forceinline__ double eclipse_scan_columns(const DevConfig &c, const double *tab,
+                                                       const unsigned long long *etab, int w0, int lane) {
+  typedef TabLayout L;
+  const unsigned FULL = 0xffffffffu;
+  const int nl = c.nlayer, nf = c.lay.nf();
+  const int nang = NANG > 0 ? NANG : c.nang;
+  const int small_hi = hi_word(c.tau_small);
+  const int col = lane & (kScanCols - 1), dl = lane / kScanCols;
+  const int w = min(w0 + col, c.nwave - 1);                    // a column past the end repeats the last one
+  const double wn = c.wn[w];
+  const double wn4 = (wn * wn) * (wn * wn);
+  const double c2n = cH * wn * cLS / cKB * kExpScale;          // Planck exponent x N/ln2, per 1/T
+  const ColPtrs P = col_ptrs<NCIA>(c, w);
+  const bool odd = dl & 1;                                     // rounds start at even depths
+  const int top = (kScanDepths - 1) * kScanCols + col;         // lane of the round's last depth, this column
+  double s_carry = 0.0;                                        // Simpson sum at the end of the previous round
+  double er_p = 0.0, d_p = c.d0, b_p = 0.0;                    // this lane's er, D, B of the previous round
+  double trap = 0.0, BL = 0.0, DL = 0.0;
+  bool done = false;                                           // this lane's column has its `last`
+  const int nround = (nl + kScanDepths - 1) / kScanDepths;
+  CellData<NMOL, NCIA> x;
+  cell_load<NMOL, NCIA>(c, P, tab + (size_t)min(dl, nl - 1) * nf, x);
+  for (int r = 0; r < nround; r++) {
+    const int d = r * kScanDepths + dl;
+    const bool live = d < nl;
+    const double *row = tab + (size_t)(live ? d : nl - 1) * nf;
+    const double er = cell_combine<NMOL, NCIA, SC>(c, P, row, x, wn4, 0);
+    // the next round's samples (same registers) are in flight under the rest of this round
+    cell_load<NMOL, NCIA>(c, P, tab + (size_t)min(d + kScanDepths, nl - 1) * nf, x);
+    // Planck function without its prefactor (eclipse_intens, eclipse.c:130-140)
+    const double B = fast_rcp1(exp_w(c2n, row[L::INVT], etab, -1.0));
+    const D2 s1 = ld2(row + L::SA);                             // (SA, SB)
+    const D2 s2 = ld2(row + L::SC);                             // (SC, TR)
+    // er of the two depths above by lane rotation: the lanes of the round's last two depths hand over
+    // what they held in the previous round (depths 8 r - 1, 8 r - 2)
+    const double e1 = __shfl_sync(FULL, dl == kScanDepths - 1 ? er_p : er, (lane - kScanCols) & 31);
+    const double e2 = __shfl_sync(FULL, dl >= kScanDepths - 2 ? er_p : er, (lane - 2 * kScanCols) & 31);
+    double v = (!odd && d >= 2 && live) ? fma(s1.x, er, fma(s1.y, e1, s2.x * e2)) : 0.0;
+#pragma unroll
+    for (int s = 1; s < kScanDepths; s <<= 1) {
+      const double t = __shfl_up_sync(FULL, v, s * kScanCols);
+      if (dl >= s) v += t;
+    }
+    const double S = s_carry + v;                               // Simpson sum up to the last even depth <= d
+    double tau = odd ? fma(s2.y, er + e1, S) : S;
+    if (d == 0) tau = 0.0;
+    const bool cross = !done && live && (d >= 1 ? tau > c.toomuch : 0.0 > c.toomuch);
+    const unsigned bal = (__ballot_sync(FULL, cross) >> col) & 0x11111111u;   // this column's depths
+    const int first = bal ? (__ffs(bal) - 1) / kScanCols : kScanDepths;       // depth-in-round of `last`
+    const bool use = !done && live && d >= 1 && dl <= first;    // depths 1..last enter the flux
+    double D = c.d0;
+    if (use) {
+      if (hi_word(tau) < small_hi) {
+        const double u = fma(tau, c.ser_s, -1.0);
+        double p = c.taylor[kTaylorN - 1];
+#pragma unroll
+        for (int i = kTaylorN - 2; i >= 0; i--) p = fma(p, u, c.taylor[i]);
+        D = p;
+      } else {
+        const double tc = tau < c.tau_clamp ? tau : c.tau_clamp;   // exp arguments stay above -690
+        if (SQ >= 0) {
+          const double e = exp_w(tc, -c.exp_a[SQ >> 4], etab + (1 + (SQ >> 4)) * kExpTabSize, 0.0);
+          D = fma(e * e, c.sq_coef, e);
+        } else D = 0.0;
+#pragma unroll
+        for (int a = 0; a < (NANG > 0 ? NANG : kMaxAng); a++)
+          if (a < nang && !(SQ >= 0 && (a == (SQ >> 4) || a == (SQ & 15))))
+            D = exp_w(tc, -c.exp_a[a], etab + (1 + a) * kExpTabSize, D);
+      }
+    }
+    const double Dm = __shfl_sync(FULL, dl == kScanDepths - 1 ? d_p : D, (lane - kScanCols) & 31);
+    const double Bm = __shfl_sync(FULL, dl == kScanDepths - 1 ? b_p : B, (lane - kScanCols) & 31);
+    if (use) trap = fma(D - Dm, B + Bm, trap);
+    // the column's last depth: the crossing, or the bottom layer in the final round
+    const bool ends = !done && (bal != 0u || r == nround - 1);
+    const int f = (bal ? first : (nl - 1) % kScanDepths) * kScanCols + col;
+    const double bf = __shfl_sync(FULL, B, f), df = __shfl_sync(FULL, D, f);
+    if (ends) { BL = bf; DL = df; done = true; }
+    if (__all_sync(FULL, done)) break;
+    s_carry += __shfl_sync(FULL, v, top);
+    er_p = er; d_p = D; b_p = B;
+  }
+#pragma unroll
+  for (int s = 16; s >= kScanCols; s >>= 1) trap += __shfl_xor_sync(FULL, trap, s);
+  const double c1 = 2.0 * cH * (wn * wn * wn) * cLS * cLS;
+  return cPI * c1 * (BL * DL - 0.5 * trap);                     // lanes 0 .. kScanCols-1 hold their column's flux
+}
+
+template <int NMOL, int NCIA, int NANG, int SQ, bool SC>
+__global__ void __launch_bounds__(kScanThreads, 6)
+eclipse_scan_kernel(DevConfig c, const double *__restrict__ tabs, const int *__restrict__ status,
+                    double *__restrict__ spectra, int nmodels, int use_tma, int tasks_per_warp) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t bar;
+  unsigned long long *s_etab = reinterpret_cast<unsigned long long *>(smem_raw);
+  const int n_etab = ecl_tab_entries(NANG > 0 ? NANG : c.nang);
+  double *s_tab = reinterpret_cast<double *>(s_etab + n_etab);
+  constexpr int kWarps = kScanThreads / 32;
+  const int m = blockIdx.x % nmodels;
+  const int tile = blockIdx.x / nmodels;
+  const int per = kWarps * tasks_per_warp * kScanCols;         // columns of one CTA
+  const int wbase = tile * per;
+  const int nd = c.lay.stride();
+  double *out = spectra + (size_t)m * c.nwave;
+  if (status[m] != 0) {                          // rejected model: -1 fill (BARTfunc.py:327-330)
+    for (int i = threadIdx.x; i < per; i += blockDim.x)
+      if (wbase + i < c.nwave) out[wbase + i] = -1.0;
+    return;
+  }
+  stage_table(s_tab, tabs + (size_t)m * nd, nd, &bar, use_tma != 0, s_etab, n_etab);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // the warps of a CTA work on adjacent column groups at the same time
+  for (int j = 0; j < tasks_per_warp; j++) {
+    const int w0 = wbase + (j * kWarps + warp) * kScanCols;
+    if (w0 >= c.nwave) break;
+    const double flux = eclipse_scan_columns<NMOL, NCIA, NANG, SQ, SC>(c, s_tab, s_etab, w0, lane);
+    if (lane < kScanCols && w0 + lane < c.nwave) out[w0 + lane] = flux;
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -984,21 +1177,54 @@ void launch_grid_relayout(const double *in, double *out, int ncells, int nmol, i
 void launch_atm_prep(const DevConfig &c, const Knobs &k, const double *profiles, int n_in,
                      double *tabs, int *status, const int *pre_status, int nmodels,
                      cudaStream_t s) {
-  const size_t smem = ((size_t)c.nspec + 3) * c.nlayer * sizeof(double);
+  // staged through shared memory when it fits comfortably (W12: 41 KB), else the plain form
+  size_t smem = atm_prep_smem_doubles(c) * sizeof(double);
+  const int staged = smem <= 160 * 1024;
+  if (!staged) smem = ((size_t)c.nspec + 3) * c.nlayer * sizeof(double);
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
-    cudaFuncSetAttribute(atm_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (cudaFuncSetAttribute(atm_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return;                                    // surfaces as the launch error of the call below
     configured = smem;
   }
-  atm_prep_kernel<<<nmodels, 128, smem, s>>>(c, k, profiles, n_in, tabs, status, pre_status, nmodels);
+  atm_prep_kernel<<<nmodels, 128, smem, s>>>(c, k, profiles, n_in, tabs, status, pre_status, nmodels, staged);
 }
 
+// scan-kernel launch (specialised instantiations only; `if constexpr` keeps the run-time-count forms
+// from instantiating it)
+template <int NMOL, int NCIA, int NANG, int SQ, bool SC>
+static void launch_eclipse_scan(const DevConfig &c, const double *tabs, const int *status, double *spectra,
+                                int nmodels, int use_tma, size_t smem, cudaStream_t s) {
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaFuncSetAttribute(eclipse_scan_kernel<NMOL, NCIA, NANG, SQ, SC>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = smem;
+  }
+  // about one resident wave of warp tasks (4 columns each): 148 SMs x 6 CTAs x 4 warps
+  constexpr int kWarps = kScanThreads / 32;
+  const long long tasks = ((long long)(c.nwave + kScanCols - 1) / kScanCols) * nmodels;
+  int tpw = (int)((tasks + 148LL * 6 * kWarps - 1) / (148LL * 6 * kWarps));
+  tpw = tpw < 1 ? 1 : (tpw > 8 ? 8 : tpw);
+  const int per = kWarps * tpw * kScanCols;
+  const int tiles = (c.nwave + per - 1) / per;
+  eclipse_scan_kernel<NMOL, NCIA, NANG, SQ, SC><<<(unsigned)((size_t)tiles * nmodels), kScanThreads, smem, s>>>(
+      c, tabs, status, spectra, nmodels, use_tma, tpw);
+}
+
+// small: 0 = throughput kernel, 1 = slot kernel, 2 = scan kernel (where it exists, else the slot kernel)
 template <int NMOL, int NCIA, int NANG, bool KEEP, int SQ = -1, bool SC = true>
 static void launch_eclipse_t(const DevConfig &c, const double *tabs, const int *status,
                              double *spectra, double *tau_keep, int *last_keep, int nmodels,
-                             int use_tma, bool slots, cudaStream_t s) {
+                             int use_tma, int small, cudaStream_t s) {
   const size_t smem = ((size_t)c.lay.stride() + ecl_tab_entries(c.nang)) * sizeof(double);
-  if (slots && !KEEP) {
+  if constexpr (!KEEP && CellData<NMOL, NCIA>::kStaticCia) {
+    if (small == 2) {
+      launch_eclipse_scan<NMOL, NCIA, NANG, SQ, SC>(c, tabs, status, spectra, nmodels, use_tma, smem, s);
+      return;
+    }
+  }
+  if (small && !KEEP) {
     static size_t configured_s = 0;
     if (smem > 48 * 1024 && smem > configured_s) {
       cudaFuncSetAttribute(eclipse_slot_kernel<NMOL, NCIA, NANG, SQ, SC>,
@@ -1028,59 +1254,64 @@ static void launch_eclipse_t(const DevConfig &c, const double *tabs, const int *
 // run-time-count kernel.
 template <int NMOL, int NCIA, bool SC>
 static void launch_eclipse_nang(const DevConfig &c, const double *tabs, const int *status,
-                                double *spectra, int nmodels, int use_tma, bool slots, cudaStream_t s) {
+                                double *spectra, int nmodels, int use_tma, int small, cudaStream_t s) {
   // the default ray grid (0 20 40 60 80 degrees): exp(-tau/cos 60) = exp(-tau/cos 0)^2
   if (c.nang == 5 && c.sq_src == 0 && c.sq_dst == 3)
-    launch_eclipse_t<NMOL, NCIA, 5, false, 0x03, SC>(c, tabs, status, spectra, nullptr, nullptr, nmodels, use_tma, slots, s);
-  else launch_eclipse_t<NMOL, NCIA, 0, false, -1, SC>(c, tabs, status, spectra, nullptr, nullptr, nmodels, use_tma, slots, s);
+    launch_eclipse_t<NMOL, NCIA, 5, false, 0x03, SC>(c, tabs, status, spectra, nullptr, nullptr, nmodels, use_tma, small, s);
+  else launch_eclipse_t<NMOL, NCIA, 0, false, -1, SC>(c, tabs, status, spectra, nullptr, nullptr, nmodels, use_tma, small, s);
 }
 
 template <int NMOL, bool SC>
 static void launch_eclipse_ncia(const DevConfig &c, const double *tabs, const int *status,
-                                double *spectra, int nmodels, int use_tma, bool slots, cudaStream_t s) {
+                                double *spectra, int nmodels, int use_tma, int small, cudaStream_t s) {
   switch (c.ncia) {
-    case 0: launch_eclipse_nang<NMOL, 0, SC>(c, tabs, status, spectra, nmodels, use_tma, slots, s); break;
-    case 1: launch_eclipse_nang<NMOL, 1, SC>(c, tabs, status, spectra, nmodels, use_tma, slots, s); break;
-    case 2: launch_eclipse_nang<NMOL, 2, SC>(c, tabs, status, spectra, nmodels, use_tma, slots, s); break;
-    default: launch_eclipse_t<0, -1, 0, false>(c, tabs, status, spectra, nullptr, nullptr, nmodels, use_tma, slots, s);
+    case 0: launch_eclipse_nang<NMOL, 0, SC>(c, tabs, status, spectra, nmodels, use_tma, small, s); break;
+    case 1: launch_eclipse_nang<NMOL, 1, SC>(c, tabs, status, spectra, nmodels, use_tma, small, s); break;
+    case 2: launch_eclipse_nang<NMOL, 2, SC>(c, tabs, status, spectra, nmodels, use_tma, small, s); break;
+    default: launch_eclipse_t<0, -1, 0, false>(c, tabs, status, spectra, nullptr, nullptr, nmodels, use_tma, small, s);
   }
 }
 
 template <bool SC>
 static void launch_eclipse_nmol(const DevConfig &c, const double *tabs, const int *status,
-                                double *spectra, int nmodels, int use_tma, bool slots, cudaStream_t s) {
+                                double *spectra, int nmodels, int use_tma, int small, cudaStream_t s) {
   switch (c.ngmol) {
-    case 1: launch_eclipse_ncia<1, SC>(c, tabs, status, spectra, nmodels, use_tma, slots, s); break;
-    case 2: launch_eclipse_ncia<2, SC>(c, tabs, status, spectra, nmodels, use_tma, slots, s); break;
-    case 3: launch_eclipse_ncia<3, SC>(c, tabs, status, spectra, nmodels, use_tma, slots, s); break;
-    case 4: launch_eclipse_ncia<4, SC>(c, tabs, status, spectra, nmodels, use_tma, slots, s); break;
-    default: launch_eclipse_t<0, -1, 0, false>(c, tabs, status, spectra, nullptr, nullptr, nmodels, use_tma, slots, s);
+    case 1: launch_eclipse_ncia<1, SC>(c, tabs, status, spectra, nmodels, use_tma, small, s); break;
+    case 2: launch_eclipse_ncia<2, SC>(c, tabs, status, spectra, nmodels, use_tma, small, s); break;
+    case 3: launch_eclipse_ncia<3, SC>(c, tabs, status, spectra, nmodels, use_tma, small, s); break;
+    case 4: launch_eclipse_ncia<4, SC>(c, tabs, status, spectra, nmodels, use_tma, small, s); break;
+    default: launch_eclipse_t<0, -1, 0, false>(c, tabs, status, spectra, nullptr, nullptr, nmodels, use_tma, small, s);
   }
 }
 
-bool eclipse_prefers_slots(const DevConfig &c, int nmodels) {
-  // the throughput kernel needs ~8 CTAs per SM to hide its latencies; below ~4 the slot kernel's
-  // fourfold CTA count wins (measured at the W12 shape: DESIGN.md section 4)
+// Which eclipse kernel a batch of `nmodels` takes: 0 = throughput kernel (two columns per thread),
+// 1 = slot kernel (one warp per 32 columns, bit-identical to 0), 2 = scan kernel (lanes <-> layers).
+// $BART_ECL_SMALL = 0 / 1 / 2 forces one.
+int eclipse_small_mode(const DevConfig &c, int nmodels) {
   const char *e = getenv("BART_ECL_SMALL");
-  if (e && *e) return atoi(e) != 0;
+  if (e && *e) return atoi(e);
+  // the scan kernel's time grows with the column count from the first model on; the throughput
+  // kernel needs ~8 CTAs per SM to hide its latencies and the slot kernel's fourfold CTA count
+  // bridges the two (measured at the W12 shape: DESIGN.md section 4)
+  if ((long long)c.nwave * nmodels <= kScanMaxColumns) return 2;
   const long long tiles = (c.nwave + kEclThreads * kEclCols - 1) / (kEclThreads * kEclCols);
-  return tiles * nmodels <= 4LL * 148;
+  return tiles * nmodels <= 4LL * 148 ? 1 : 0;
 }
 
 void launch_eclipse(const DevConfig &c, const double *tabs, const int *status, double *spectra,
                     double *tau_keep, int *last_keep, int nmodels, bool keep, bool sc, int use_tma,
                     cudaStream_t s) {
   if (keep) {   // introspection path: run-time counts, stores tau[] and last[]
-    launch_eclipse_t<0, -1, 0, true>(c, tabs, status, spectra, tau_keep, last_keep, nmodels, use_tma, false, s);
+    launch_eclipse_t<0, -1, 0, true>(c, tabs, status, spectra, tau_keep, last_keep, nmodels, use_tma, 0, s);
     return;
   }
-  const bool slots = eclipse_prefers_slots(c, nmodels);
+  const int small = eclipse_small_mode(c, nmodels);
   if (c.planck_generic) {   // extreme Planck exponents: the kernel with the per-column clamp, degree 5
-    launch_eclipse_t<0, -1, 0, false>(c, tabs, status, spectra, nullptr, nullptr, nmodels, use_tma, slots, s);
+    launch_eclipse_t<0, -1, 0, false>(c, tabs, status, spectra, nullptr, nullptr, nmodels, use_tma, small, s);
     return;
   }
-  if (sc) launch_eclipse_nmol<true>(c, tabs, status, spectra, nmodels, use_tma, slots, s);
-  else launch_eclipse_nmol<false>(c, tabs, status, spectra, nmodels, use_tma, slots, s);
+  if (sc) launch_eclipse_nmol<true>(c, tabs, status, spectra, nmodels, use_tma, small, s);
+  else launch_eclipse_nmol<false>(c, tabs, status, spectra, nmodels, use_tma, small, s);
 }
 
 void launch_merge_status(int *status, const int *status_col, int nmodels, cudaStream_t s) {

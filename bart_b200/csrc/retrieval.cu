@@ -24,78 +24,78 @@
 namespace bart {
 
 // ---------------------------------------------------------------------------------------
-// E_2(x): exponential integral of order 2 (scipy.special.expn(2, x) in code/PT.py:736; cephes
-// expn: power series for x <= 1, continued fraction above).  Same recurrences and stopping rules as
-// cephes, restated without a division inside the loops (a generation at MC3's 10-chain populations
-// is latency-bound, and the two divisions per continued-fraction step were most of it): the
-// convergence test |ans - r| <= eps |r| on consecutive convergents p'/q', p/q is evaluated as
-// |p' q - p q'| <= eps |p q'|, and the series divides by the integers k through a reciprocal table.
-// Agreement with scipy: <= 4e-16 relative (tests/test_gpu_retrieval.py, against PT.py's profiles).
-__constant__ double c_recip[48];            // 1/k, k = 1..47 (entry 0 unused)
-__device__ double expint2(double x) {
-  const double EUL = 0.57721566490153286060, MACHEP = 1.11022302462515654042e-16;
-  const double BIG = 1.44115188075855872e17, MAXLOG = 7.09782712893383996843e2;
-  const int n = 2;
+// E_2(x): exponential integral of order 2 (scipy.special.expn(2, x) in code/PT.py:736).  A
+// generation at MC3's 10-chain populations is bound by the longest dependent instruction chain of
+// each of its kernels, and cephes' algorithm (power series for x <= 1, continued fraction above,
+// each run to convergence) was most of the converter's: ~4700 instructions per warp.  Here
+//   x <  1   E_2 = exp(-x) - x (h(x) - ln x), h(x) = E_1(x) + ln x = -gamma - sum_k (-x)^k / (k k!),
+//            an entire function taken to degree kE2SeriesN - 1;
+//   x >= 1   E_2 = F(x) exp(-x) / x, F(x) = x exp(x) E_2(x) (0.40 .. 1) from one polynomial per binade
+//            2^k <= x < 2^(k+1), k = 0..9, in u = x / 2^(k-1) - 3 (Chebyshev interpolants in the monomial
+//            basis)
+// with tables computed at 60 digits by tools/gen_expint2_table.py: <= 1e-15 relative against mpmath
+// on both branches (scipy's own expn is not closer), two orders inside what the profiles are held
+// to against PT.py (1e-12, tests/test_gpu_retrieval.py).
+#include "expint2_table.inc"
+constexpr int kE2TableN = kE2SeriesN + kE2Intervals * kE2ChebN;
+__device__ double g_e2_table[kE2TableN];        // series coefficients, then the binade polynomials
+__device__ double expint2(double x, const double *tab) {
+  const double MAXLOG = 7.09782712893383996843e2;
   if (!(x <= MAXLOG)) return x != x ? x : 0.0;
   if (x == 0.0) return 1.0;
-  if (x > 1.0) {
-    int k = 1;
-    double pkm2 = 1.0, qkm2 = x, pkm1 = 1.0, qkm1 = x + n;
-    bool more;
-    do {
-      k++;
-      double yk, xk;
-      if (k & 1) { yk = 1.0; xk = n + (k - 1) / 2; }
-      else { yk = x; xk = k / 2; }
-      const double pk = __dadd_rn(__dmul_rn(pkm1, yk), __dmul_rn(pkm2, xk));
-      const double qk = __dadd_rn(__dmul_rn(qkm1, yk), __dmul_rn(qkm2, xk));
-      // consecutive convergents pkm1/qkm1 and pk/qk
-      const double pq = pk * qkm1;
-      more = qk == 0.0 || fabs(fma(pkm1, qk, -pq)) > MACHEP * fabs(pq);
-      pkm2 = pkm1; pkm1 = pk; qkm2 = qkm1; qkm1 = qk;
-      if (fabs(pk) > BIG) { pkm2 *= 1.0 / BIG; pkm1 *= 1.0 / BIG; qkm2 *= 1.0 / BIG; qkm1 *= 1.0 / BIG; }
-    } while (more && k < 100000);
-    return pkm1 / qkm1 * exp(-x);
+  if (x >= 1.0) {
+    const int hi = __double2hiint(x);
+    const int k = (hi >> 20) - 1023;                                   // binade, 0..9
+    const double scale = __hiloint2double((1024 - k) << 20, 0);        // 2^(1-k)
+    const double u = fma(x, scale, -3.0);
+    const double *t = tab + kE2SeriesN + k * kE2ChebN;
+    double p = t[kE2ChebN - 1];
+#pragma unroll
+    for (int i = kE2ChebN - 2; i >= 0; i--) p = fma(p, u, t[i]);
+    return p * exp(-x) / x;
   }
-  double psi = -EUL - log(x);
-  psi += 1.0;                                   // sum_{i=1}^{n-1} 1/i
-  const double z = -x;
-  double yk = 1.0, ans = -1.0;                  // 1 / (1 - n)
-  int k = 0;
-  bool more;
-  do {
-    k++;
-    yk *= k < 48 ? z * c_recip[k] : z / k;
-    if (k != n - 1) ans += k - (n - 1) < 48 ? yk * c_recip[k - (n - 1)] : yk / (k - (n - 1));
-    more = ans != 0.0 ? fabs(yk) > MACHEP * fabs(ans) : true;
-  } while (more && k < 100000);
-  return __dmul_rn(z, psi) - ans;               // z^(n-1) psi / Gamma(n) - series
+  double h = tab[kE2SeriesN - 1];
+#pragma unroll
+  for (int i = kE2SeriesN - 2; i >= 0; i--) h = fma(h, x, tab[i]);
+  return exp(-x) - x * (h - log(x));
 }
 
 // eq. 14 of Line et al. 2013 (PT.py:719-737)
-__device__ double line_xi(double gamma, double tau) {
+__device__ double line_xi(double gamma, double tau, const double *e2tab) {
   const double gt = gamma * tau;
   return (2.0 / 3) * (1 + (1. / gamma) * (1 + (0.5 * gamma * tau - 1) * exp(-gt)) +
-                      gamma * (1 - 0.5 * (tau * tau)) * expint2(gt));
+                      gamma * (1 - 0.5 * (tau * tau)) * expint2(gt, e2tab));
 }
 
 // PT_line (PT.py:664-697) splits over a pair of adjacent lanes: each evaluates one of the two
 // visible streams' xi (the expensive part), lane 0 of the pair combines them.  `half` = lane & 1.
-__device__ double pt_temperature(const ConvConfig &cc, const double *par, double p_bar, int half) {
+// The quantities that depend on the parameters only are computed once per model (pt_line_consts):
+// ptc = (kappa, gamma1, gamma2, Tint^4, Tirr^4).
+enum { PTC_KAPPA = 0, PTC_G1 = 1, PTC_G2 = 2, PTC_TI4 = 3, PTC_TR4 = 4, PTC_N = 5 };
+__device__ void pt_line_consts(const ConvConfig &cc, const double *par, int which, double *ptc) {
+  if (which < 3) ptc[which] = pow(10.0, par[which]);
+  else if (which == 3) ptc[PTC_TI4] = pow(cc.tint, 4.0);
+  else if (which == 4) {
+    const double tirr = par[4] * sqrt(cc.rstar / (2.0 * cc.sma)) * cc.tstar;
+    ptc[PTC_TR4] = pow(tirr, 4.0);
+  }
+}
+__device__ double pt_temperature(const ConvConfig &cc, const double *par, const double *ptc,
+                                 const double *e2tab, double p_bar, int half) {
   if (cc.pt_type == PT_ISO) return par[0];
   if (cc.pt_type == PT_ADIABATIC) {             // PT.py:741-750
     const double p0 = pow(10.0, par[2]);
     return par[0] / (1 + (par[1] - 1) / par[1] * log(p0 / p_bar));
   }
-  const double kappa = pow(10.0, par[0]), g = pow(10.0, par[1 + half]);
-  const double alpha = par[3], beta = par[4];
-  const double tirr = beta * sqrt(cc.rstar / (2.0 * cc.sma)) * cc.tstar;
+  const double kappa = ptc[PTC_KAPPA], g = ptc[PTC_G1 + half];
+  const double alpha = par[3];
   const double tau = kappa * (p_bar * 1e6) / cc.grav;
-  const double xi_mine = line_xi(g, tau);
+  const double xi_mine = line_xi(g, tau, e2tab);
   const double xi_other = __shfl_xor_sync(0xffffffffu, xi_mine, 1);
   const double xi1 = half ? xi_other : xi_mine, xi2 = half ? xi_mine : xi_other;
-  const double ti4 = pow(cc.tint, 4.0), tr4 = pow(tirr, 4.0);
-  return pow(0.75 * (ti4 * (2.0 / 3.0 + tau) + tr4 * (1 - alpha) * xi1 + tr4 * alpha * xi2), 0.25);
+  const double ti4 = ptc[PTC_TI4], tr4 = ptc[PTC_TR4];
+  // the fourth root as two square roots (each correctly rounded; PT.py's ** 0.25 is libm's pow)
+  return sqrt(sqrt(0.75 * (ti4 * (2.0 / 3.0 + tau) + tr4 * (1 - alpha) * xi1 + tr4 * alpha * xi2)));
 }
 
 // Raw (unsmoothed) temperature of the smoothing PT models at one layer.  Arithmetic in the
@@ -161,26 +161,49 @@ __device__ double smooth_nearest(const ConvConfig &cc, const double *T, int l) {
 }
 
 constexpr int kConvThreads = 256;               // two lanes per layer
+// `staged`: the arrays of the set-up (pressures, base abundances, H2/He ratio) come in through one
+// round of coalesced loads into shared memory and the profile is assembled there and written out as
+// one stream -- at MC3's population sizes the kernel is a chain of memory latencies (the abundance
+// loop alone was a dependent global load + store per species).  Same arithmetic, same order.
+// Shared-memory doubles: [nlayer] raw temperatures | staged: press[nl], ratio[nl], base[nspec][nl],
+// profile[(1 + nspec)][nl]
 __global__ void __launch_bounds__(kConvThreads)
 convert_params_kernel(ConvConfig cc, const double *__restrict__ params, int npars,
                       double *__restrict__ profiles, int n_in, int *__restrict__ status,
-                      ConvKnobs kn, int nmodels) {
+                      ConvKnobs kn, int nmodels, int staged) {
   const int m = blockIdx.x;
   if (m >= nmodels) return;
   extern __shared__ double s_T[];               // [nlayer] raw temperatures (smoothing PT models)
   __shared__ int s_bad;
   __shared__ double s_par[kMaxPars];
   __shared__ double s_fac[kMaxPars];            // 10^p of the abundance parameters
+  __shared__ double s_ptc[PTC_N];               // per-model constants of PT_line
+  __shared__ double s_e2[kE2TableN];
   if (threadIdx.x == 0) s_bad = 0;
+  const bool line = cc.pt_type == PT_LINE;
+  if (line)
+    for (int i = threadIdx.x; i < kE2TableN; i += blockDim.x) s_e2[i] = g_e2_table[i];
   const int nl = cc.nlayer;
   const int off = cc.npt + cc.nrad + cc.ncloud + cc.nray;
+  double *gout = profiles + (size_t)m * n_in;
+  const double *press = cc.press_bar, *ratio_a = cc.ratio, *base = cc.base;
+  double *out = gout;
+  if (staged) {
+    double *s_press = s_T + nl, *s_ratio = s_press + nl, *s_base = s_ratio + nl;
+    double *s_prof = s_base + (size_t)cc.nspec * nl;
+    for (int i = threadIdx.x; i < nl; i += blockDim.x) { s_press[i] = cc.press_bar[i]; s_ratio[i] = cc.ratio[i]; }
+    for (int i = threadIdx.x; i < cc.nspec * nl; i += blockDim.x) s_base[i] = cc.base[i];
+    press = s_press; ratio_a = s_ratio; base = s_base; out = s_prof;
+  }
   for (int i = threadIdx.x; i < npars; i += blockDim.x) {
     const double v = params[(size_t)m * npars + i];
     s_par[i] = v;
     if (i >= off && i - off < cc.nmolfit) s_fac[i - off] = pow(10.0, v);
   }
+  // PT_line's per-model constants, one thread each (the last warp: the first ones hold the pows above)
+  if (line && threadIdx.x >= kConvThreads - PTC_N)
+    pt_line_consts(cc, params + (size_t)m * npars, threadIdx.x - (kConvThreads - PTC_N), s_ptc);
   __syncthreads();
-  double *out = profiles + (size_t)m * n_in;
   int bad = 0;
   const bool smoothed = cc.pt_type >= PT_MADHU_NOINV;
   if (smoothed) {
@@ -199,14 +222,14 @@ convert_params_kernel(ConvConfig cc, const double *__restrict__ params, int npar
     const int l = pass * (kConvThreads / 2) + (threadIdx.x >> 1);
     const bool live = l < nl;
     const double T = smoothed ? smooth_nearest(cc, s_T, live ? l : nl - 1)
-                              : pt_temperature(cc, s_par, cc.press_bar[live ? l : nl - 1], half);
+                              : pt_temperature(cc, s_par, s_ptc, s_e2, press[live ? l : nl - 1], half);
     if (!live || half) continue;
     if (!(T >= cc.tmin) || !(T <= cc.tmax)) bad |= REJ_TBOUNDS;   // also catches NaN
     out[l] = T;
     // scaled abundances and the metal sum in the reference's order (BARTfunc.py:333-338)
     double metals = 0.0;
     for (int j = 0; j < cc.nspec; j++) {
-      double a = cc.base[(size_t)j * nl + l];
+      double a = base[(size_t)j * nl + l];
       for (int k = 0; k < cc.nmolfit; k++)
         if (cc.imol[k] == j) a = a * s_fac[k];
       if (j != cc.iH2 && j != cc.iHe) out[(size_t)(j + 1) * nl + l] = a;
@@ -217,12 +240,16 @@ convert_params_kernel(ConvConfig cc, const double *__restrict__ params, int npar
     }
     const double q = 1.0 - metals;
     if (q < 0.0) bad |= REJ_ABUND;
-    const double ratio = cc.ratio[l];
+    const double ratio = ratio_a[l];
     out[(size_t)(cc.iH2 + 1) * nl + l] = ratio * q / (1.0 + ratio);
     out[(size_t)(cc.iHe + 1) * nl + l] = q / (1.0 + ratio);
   }
   if (bad) atomicOr(&s_bad, bad);
   __syncthreads();
+  if (staged) {
+    const int nprof = (cc.nspec + 1) * nl;
+    for (int i = threadIdx.x; i < nprof; i += blockDim.x) gout[i] = out[i];
+  }
   if (threadIdx.x == 0) {
     // the temperature test comes first and wins (BARTfunc.py:327-330 before 339-344)
     status[m] = (s_bad & REJ_PTMODEL) ? REJ_PTMODEL : (s_bad & REJ_TBOUNDS) ? REJ_TBOUNDS : s_bad;
@@ -239,14 +266,22 @@ void launch_convert_params(const ConvConfig &cc, const double *params, int npars
   if (nmodels <= 0) return;
   static bool table_ready = false;
   if (!table_ready) {
-    double h[48];
-    h[0] = 0.0;
-    for (int k = 1; k < 48; k++) h[k] = 1.0 / k;
-    cudaMemcpyToSymbol(c_recip, h, sizeof(h));
+    double h[kE2TableN];
+    for (int i = 0; i < kE2SeriesN; i++) h[i] = kE2SeriesHost[i];
+    for (int i = 0; i < kE2Intervals * kE2ChebN; i++) h[kE2SeriesN + i] = kE2ChebHost[i];
+    cudaMemcpyToSymbol(g_e2_table, h, sizeof(h));
     table_ready = true;
   }
-  const size_t smem = cc.pt_type >= PT_MADHU_NOINV ? (size_t)cc.nlayer * sizeof(double) : 0;
-  convert_params_kernel<<<nmodels, kConvThreads, smem, s>>>(cc, params, npars, profiles, n_in, status, kn, nmodels);
+  size_t smem = ((size_t)cc.nlayer * 3 + (size_t)cc.nspec * cc.nlayer * 2 + cc.nlayer) * sizeof(double);
+  const int staged = smem <= 96 * 1024;
+  if (!staged) smem = (size_t)cc.nlayer * sizeof(double);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    if (cudaFuncSetAttribute(convert_params_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return;                                   // surfaces as the launch error of the call below
+    configured = smem;
+  }
+  convert_params_kernel<<<nmodels, kConvThreads, smem, s>>>(cc, params, npars, profiles, n_in, status, kn, nmodels, staged);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -24,7 +24,7 @@ def api(built):
 
 
 @pytest.mark.parametrize("name", list(cases.CASES))
-def test_spectra_vs_oracle_and_golden(name, api, get_case):
+def test_spectra_vs_oracle_and_golden(name, api, get_case, monkeypatch):
     from oracle import oracle as orc
     case, models, setters = get_case(name)
     g = np.load(cases.golden_path(name))
@@ -63,6 +63,16 @@ def test_spectra_vs_oracle_and_golden(name, api, get_case):
         # the reference's own single-model entry point gives the same numbers as the batch
         one = tr.run_transit(models[m])
         assert np.array_equal(one, spectra2[m])
+    # batches this small take the latency kernel (eclipse: lanes <-> layers scan); the throughput
+    # kernel and the slot kernel on the same models, against the same oracle / golden spectra
+    for mode in ("0", "1"):
+        monkeypatch.setenv("BART_ECL_SMALL", mode)
+        spectra3, _ = tr.run_batch(models)
+        assert relerr(spectra3, spectra2) < 1e-9
+        for m in range(models.shape[0]):
+            assert relerr(spectra3[m], g["spectra"][m]) < TOL
+        assert relerr(spectra3[-1], o["spectrum"]) < TIGHT
+    monkeypatch.delenv("BART_ECL_SMALL")
     tr.free_memory()
 
 
@@ -211,6 +221,36 @@ def test_small_batch_kernel_bit_identical(name, api, get_case, workdir, monkeypa
     tr.free_memory()
 
 
+@pytest.mark.parametrize("name", ["w12", "tiny_eclipse", "small4_eclipse_cloud", "demo_eclipse",
+                                  "small4_eclipse_polar", "small4_eclipse_2cia", "tiny_eclipse_3ang",
+                                  "tiny_eclipse_9", "tiny_eclipse_t20", "real_inputs_eclipse"])
+def test_scan_kernel(name, api, get_case, workdir, monkeypatch):
+    """The latency kernel of the smallest batches (lanes <-> layers, kernels.cu eclipse_scan_kernel:
+    Simpson panels summed by a warp scan, series / exponentials choice of D(tau) per lane) against
+    the throughput kernel on the same models: equal to the accuracy of the two kernels' approximations
+    (1e-9; the parity gate is 1e-6), and a model's spectrum does not depend on the batch it came in
+    (bit-exact within the kernel)."""
+    import os
+    from bart_b200 import synth
+    if name == "w12":
+        case = synth.make_case(os.path.join(workdir, "w12"), shape="w12", solution="eclipse", seed=2026)
+        models = synth.make_models(case, 12, seed=11, molfit=("H2O", "CO2", "CO", "CH4"))
+        setters = {}
+    else:
+        case, models, setters = get_case(name)
+    tr = api.Transit(case["cfg"])
+    apply_setters(tr, setters)
+    monkeypatch.setenv("BART_ECL_SMALL", "0")
+    big, st = tr.run_batch(models)
+    monkeypatch.setenv("BART_ECL_SMALL", "2")
+    scan, st2 = tr.run_batch(models)
+    one, st3 = tr.run_batch(models[1:2])
+    assert (st == 0).all() and (st2 == 0).all() and (st3 == 0).all()
+    assert relerr(scan, big) < 1e-9
+    assert np.array_equal(one[0], scan[1])
+    tr.free_memory()
+
+
 def test_band_integration_vs_wine_golden(api, get_case):
     """K4 through the C ABI on the arrays the reference's own code/wine.py produced
     (tests/golden/wine.npz: shipped demo filters + Kurucz star on the demo wavenumber grid):
@@ -239,7 +279,8 @@ def test_band_integration_vs_wine_golden(api, get_case):
 
 def test_batch_properties_w12_shape(api, workdir):
     """Full WASP-12b shape (2424 wn x 100 layers x 27 T x 4 molecules): (i) a sample of models
-    against the oracle; (ii) permutation equivariance and batch-size independence, bit-exact;
+    against the oracle; (ii) permutation equivariance and batch-size independence, bit-exact
+    (between the throughput and the slot kernel; the one-model latency kernel to 1e-9);
     (iii) monotone optical depth and last[] consistent with toomuch."""
     import os
     from bart_b200 import synth
@@ -256,8 +297,11 @@ def test_batch_properties_w12_shape(api, workdir):
     perm = np.random.default_rng(3).permutation(models.shape[0])
     sp2, _ = tr.run_batch(models[perm])
     assert np.array_equal(sp2, spectra[perm])
-    sp3, _ = tr.run_batch(models[5:6])
-    assert np.array_equal(sp3[0], spectra[5])
+    sp3, _ = tr.run_batch(models[4:28])           # 24 models: the slot kernel, bit-identical
+    assert np.array_equal(sp3, spectra[4:28])
+    sp4, _ = tr.run_batch(models[5:6])            # one model: the scan kernel, equal to its approximations
+    assert relerr(sp4[0], spectra[5]) < 1e-9
+    assert relerr(sp4[0], O.run(models[5])) < TIGHT
     tr.debug_keep(True)
     tr.run_batch(models[:2])
     for m in range(2):
