@@ -385,21 +385,29 @@ BART_HD PrepPtrs prep_ptrs_of(const DevConfig &c) {
 // atm_prep stage 1, one layer: mean molecular mass and mass densities.
 // Reference: checkaddmm readatm.c:122-159 (number abundances), stateeqnford transit.h:58-69,
 // reloadatm readatm.c:722-784.  rho[j*rho_stride] receives the density of species j.
-BART_HD int prep_layer(const DevConfig &c, const PrepPtrs &pp, const double *__restrict__ in, int l,
-                       double *__restrict__ rho, int rho_stride, double *mu_out) {
-  const int nl = c.nlayer;
+// mass density of species j at layer l
+BART_HD double prep_density(const DevConfig &c, const PrepPtrs &pp, const double *in, int l, int j) {
   const double T = in[l];
   const double p = pp.press[l] * c.pfct;
+  const double q = in[(size_t)c.nlayer * (j + 1) + l];
+  const double r = cAMU * q * p / cKB / T;
+  return r * pp.mass[j];
+}
+// mean molecular mass of layer l (species in file order) and the abundance-sum test
+BART_HD int prep_mu(const DevConfig &c, const PrepPtrs &pp, const double *in, int l, double *mu_out) {
   double mu = 0.0, sumq = 0.0;
   for (int j = 0; j < c.nspec; j++) {
-    const double q = in[(size_t)nl * (j + 1) + l];
+    const double q = in[(size_t)c.nlayer * (j + 1) + l];
     mu += q * pp.mass[j];
     sumq += q;
-    const double r = cAMU * q * p / cKB / T;
-    rho[(size_t)j * rho_stride] = r * pp.mass[j];
   }
   *mu_out = mu;
   return sumq > 1.001 ? REJ_SUMQ : 0;
+}
+BART_HD int prep_layer(const DevConfig &c, const PrepPtrs &pp, const double *in, int l,
+                       double *rho, int rho_stride, double *mu_out) {
+  for (int j = 0; j < c.nspec; j++) rho[(size_t)j * rho_stride] = prep_density(c, pp, in, l, j);
+  return prep_mu(c, pp, in, l, mu_out);
 }
 BART_HD int prep_layer(const DevConfig &c, const double *in, int l, double *rho, int rho_stride,
                        double *mu_out) {
@@ -487,9 +495,11 @@ BART_HD int bracket(const double *x, int n, double v) {
 // atm_prep stage 3, one depth d (0 = top): every per-layer coefficient the column kernels need,
 // written as one record (layout: TabLayout).  temp/radius are indexed by layer (bottom -> top);
 // rho[j*rho_stride + layer].
-BART_HD int prep_table_row(const DevConfig &c, const PrepPtrs &pp, const KnobVals &kv, int d,
-                           const double *temp, const double *rho, int rho_stride, const double *radius,
-                           double *tab, int model = 0) {
+// The record of depth d in four independent parts (disjoint fields), so that atm_prep_kernel can
+// deal them to different threads: thermal (temperature, Planck chaining factor, opacity-grid
+// bracket and weights), CIA, scattering / cloud, and the radius-dependent quadrature coefficients.
+BART_HD int prep_row_thermal(const DevConfig &c, const PrepPtrs &pp, int d, const double *temp,
+                             const double *rho, int rho_stride, double *tab, int model = 0) {
   const TabLayout &L = c.lay;
   const int nl = c.nlayer;
   const int l = nl - 1 - d;
@@ -498,7 +508,6 @@ BART_HD int prep_table_row(const DevConfig &c, const PrepPtrs &pp, const KnobVal
   int status = 0;
   row[L.T] = T;
   row[L.INVT] = 1.0 / T;
-  row[L.RAD] = radius[l];
   row[L.PF] = c.planck_cols > 0 ? exp(c.planck_step / T) : 1.0;
   row[L.GOFF + 1] = 0.0;
 
@@ -519,9 +528,18 @@ BART_HD int prep_table_row(const DevConfig &c, const PrepPtrs &pp, const KnobVal
     row[L.W + 2 * m] = r * (t1 - T) / (t1 - t0);
     row[L.W + 2 * m + 1] = r * (T - t0) / (t1 - t0);
   }
+  return status;
+}
 
-  // CIA: cubic-spline-in-T coefficients (splinterp_pt, spline.c:131-183) applied to the
-  // wavenumber-pre-splined tables, times the density product (interpcs, crosssec.c:321-336)
+// CIA: cubic-spline-in-T coefficients (splinterp_pt, spline.c:131-183) applied to the
+// wavenumber-pre-splined tables, times the density product (interpcs, crosssec.c:321-336)
+BART_HD int prep_row_cia(const DevConfig &c, const PrepPtrs &pp, int d, const double *temp,
+                         const double *rho, int rho_stride, double *tab) {
+  const TabLayout &L = c.lay;
+  const int l = c.nlayer - 1 - d;
+  const double T = temp[l];
+  double *row = tab + (size_t)d * L.nf();
+  int status = 0;
 #pragma unroll
   for (int f = 0; f < kMaxCia; f++) {
     if (f >= c.ncia) break;
@@ -552,7 +570,15 @@ BART_HD int prep_table_row(const DevConfig &c, const PrepPtrs &pp, const KnobVal
     cr[4] = cz0 * dens;
     cr[5] = cz1 * dens;
   }
+  return status;
+}
 
+BART_HD void prep_row_scat(const DevConfig &c, const PrepPtrs &pp, const KnobVals &kv, int d,
+                           const double *temp, const double *rho, int rho_stride, double *tab) {
+  const TabLayout &L = c.lay;
+  const int l = c.nlayer - 1 - d;
+  const double T = temp[l];
+  double *row = tab + (size_t)d * L.nf();
   // scattering (computeextscat, extinction.c:586-624): coefficient of wn^4
   double sc = 0.0;
   if (kv.scat_flag == 1) sc = pow(10.0, kv.scat_logext) * cE0H2 * pp.press[l] / T;
@@ -572,9 +598,15 @@ BART_HD int prep_table_row(const DevConfig &c, const PrepPtrs &pp, const KnobVal
     if (pp.press[l] >= top && pp.press[l] < bot) cl = kv.cloudext;
   }
   row[L.CLOUD] = cl;
+}
 
-  // Simpson / trapezoid coefficients on the radius spacing (geth + simpson, numerical.c:390-525),
-  // top-aligned panels: the panel ending at even depth d spans depths d-2, d-1, d.
+// Simpson / trapezoid coefficients on the radius spacing (geth + simpson, numerical.c:390-525),
+// top-aligned panels: the panel ending at even depth d spans depths d-2, d-1, d.
+BART_HD void prep_row_radius(const DevConfig &c, int d, const double *radius, double *tab) {
+  const TabLayout &L = c.lay;
+  const int l = c.nlayer - 1 - d;
+  double *row = tab + (size_t)d * L.nf();
+  row[L.RAD] = radius[l];
   double sa = 0.0, sb = 0.0, scf = 0.0, tr = 0.0;
   if (d >= 1) {
     const double h0 = radius[l + 1] - radius[l];            // interval (d, d-1)
@@ -592,6 +624,15 @@ BART_HD int prep_table_row(const DevConfig &c, const PrepPtrs &pp, const KnobVal
   row[L.SB] = sb;
   row[L.SC] = scf;
   row[L.TR] = tr;
+}
+
+BART_HD int prep_table_row(const DevConfig &c, const PrepPtrs &pp, const KnobVals &kv, int d,
+                           const double *temp, const double *rho, int rho_stride, const double *radius,
+                           double *tab, int model = 0) {
+  int status = prep_row_thermal(c, pp, d, temp, rho, rho_stride, tab, model);
+  status |= prep_row_cia(c, pp, d, temp, rho, rho_stride, tab);
+  prep_row_scat(c, pp, kv, d, temp, rho, rho_stride, tab);
+  prep_row_radius(c, d, radius, tab);
   return status;
 }
 BART_HD int prep_table_row(const DevConfig &c, const KnobVals &kv, int d, const double *temp,

@@ -107,6 +107,7 @@ __device__ __forceinline__ void stage_table(double *s_tab, const double *g_tab, 
 // assembled there and written out as one coalesced stream: at MC3's population sizes (3-10 models per
 // launch) this kernel is a chain of memory latencies, not of arithmetic (a binary search over a
 // global array alone is five dependent ~0.3 us round trips).  Same arithmetic, same order.
+constexpr int kPrepThreads = 256;
 __host__ __device__ inline size_t atm_prep_smem_doubles(const DevConfig &c) {
   size_t n = ((size_t)c.nspec + 3) * c.nlayer;                 // rho, mu, radius, hydrostatic coefficients
   n += ((size_t)c.nspec + 1) * c.nlayer;                       // the model's profile
@@ -115,7 +116,7 @@ __host__ __device__ inline size_t atm_prep_smem_doubles(const DevConfig &c) {
   n += (size_t)c.lay.stride();                                 // the record table
   return n + 8;
 }
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kPrepThreads)
 atm_prep_kernel(DevConfig c, Knobs knobs, const double *__restrict__ profiles, int n_in,
                 double *__restrict__ tabs, int *__restrict__ status,
                 const int *__restrict__ pre_status, int nmodels, int staged) {
@@ -163,9 +164,16 @@ atm_prep_kernel(DevConfig c, Knobs knobs, const double *__restrict__ profiles, i
     s_tabrec = dst + ((reinterpret_cast<uintptr_t>(dst) & 8) ? 1 : 0);   // 16-byte aligned records
   }
   __syncthreads();
+  // The stages are dealt out so that no thread carries a long dependent chain (at 3-10 models per
+  // launch the kernel's time is its longest chain): densities per (species, layer) pair; the record
+  // parts that do not need the radii (thermal / CIA / scattering, one part per thread) run on the other
+  // warps while thread 0 walks the hydrostatic recurrence.
   int st = 0;
-  for (int l = threadIdx.x; l < nl; l += blockDim.x) st |= prep_layer(c, pp, s_in, l, s_rho + l, nl, s_mu + l);
-  if (st) atomicOr(&s_status, st);
+  for (int i = threadIdx.x; i < c.nspec * nl; i += blockDim.x) {
+    const int j = i / nl, l = i - j * nl;
+    s_rho[i] = prep_density(c, pp, s_in, l, j);
+  }
+  for (int l = threadIdx.x; l < nl; l += blockDim.x) st |= prep_mu(c, pp, s_in, l, s_mu + l);
   __syncthreads();
   const KnobVals kv = knobs_for(knobs, m);
   for (int l = threadIdx.x; l < nl - 1; l += blockDim.x) s_hc[l] = hydro_coef(c, pp, s_in, s_mu, l);
@@ -173,10 +181,20 @@ atm_prep_kernel(DevConfig c, Knobs knobs, const double *__restrict__ profiles, i
   if (knobs.radius_file) {
     for (int l = threadIdx.x; l < nl; l += blockDim.x) s_rad[l] = knobs.radius_file[l];
   } else if (threadIdx.x == 0) hydrostatic_radii(c, pp, kv.r0, s_in, s_mu, s_hc, s_rad);
+  {
+    // warp 0 is busy with the radii unless they come from the file
+    const int first = knobs.radius_file ? 0 : 32;
+    const int nthr = (int)blockDim.x - first;
+    if ((int)threadIdx.x >= first)
+      for (int i = (int)threadIdx.x - first; i < 3 * nl; i += nthr) {
+        const int part = i / nl, d = i - part * nl;
+        if (part == 0) st |= prep_row_thermal(c, pp, d, s_in, s_rho, nl, s_tabrec, c.lbl_model0 + m);
+        else if (part == 1) st |= prep_row_cia(c, pp, d, s_in, s_rho, nl, s_tabrec);
+        else prep_row_scat(c, pp, kv, d, s_in, s_rho, nl, s_tabrec);
+      }
+  }
   __syncthreads();
-  st = 0;
-  for (int d = threadIdx.x; d < nl; d += blockDim.x)
-    st |= prep_table_row(c, pp, kv, d, s_in, s_rho, nl, s_rad, s_tabrec, c.lbl_model0 + m);
+  for (int d = threadIdx.x; d < nl; d += blockDim.x) prep_row_radius(c, d, s_rad, s_tabrec);
   if (c.lbl)
     for (int i = threadIdx.x; i < nl * c.nspec; i += blockDim.x) {
       const int l = i / c.nspec, j = i - l * c.nspec;
@@ -1187,7 +1205,7 @@ void launch_atm_prep(const DevConfig &c, const Knobs &k, const double *profiles,
       return;                                    // surfaces as the launch error of the call below
     configured = smem;
   }
-  atm_prep_kernel<<<nmodels, 128, smem, s>>>(c, k, profiles, n_in, tabs, status, pre_status, nmodels, staged);
+  atm_prep_kernel<<<nmodels, kPrepThreads, smem, s>>>(c, k, profiles, n_in, tabs, status, pre_status, nmodels, staged);
 }
 
 // scan-kernel launch (specialised instantiations only; `if constexpr` keeps the run-time-count forms
