@@ -441,8 +441,12 @@ inline int ref_layer_of(const double *press, int nl, double p0) {
   return i0;
 }
 
+// dirs: bit 0 = walk the layers below the reference layer, bit 1 = those above; either walk
+// computes the reference layer's radius itself, so two threads can take one direction each.  The
+// coefficient of the next step is fetched before the current step's radius is stored (the
+// recurrence is the kernel's longest dependent chain at small batches).
 BART_HD void hydrostatic_radii(const DevConfig &c, const PrepPtrs &pp, double r0, const double *temp,
-                               const double *mu, const double *hc, double *radius) {
+                               const double *mu, const double *hc, double *radius, int dirs = 3) {
   const int nl = c.nlayer;
   const double *pr = pp.press;
   const double p0 = c.p0, g0 = c.gsurf, rfct = c.rfct;
@@ -461,15 +465,24 @@ BART_HD void hydrostatic_radii(const DevConfig &c, const PrepPtrs &pp, double r0
     radius[i0] = r0 - 0.5 * (temp[i0] / mu[i0] + t0 / m0) * (cKB / cAMU * log(pr[i0] / p0) / g0) / rfct;
   }
   const double q = 1.0 / (g0 * r0 * r0);
-  double r = radius[i0];
-  for (int i = i0 - 1; i >= 0; i--) {
-    r = fma(-(hc[i] * q), r * r, r);
-    radius[i] = r;
+  const double ri0 = radius[i0];
+  if ((dirs & 1) && i0 > 0) {
+    double r = ri0, h = hc[i0 - 1] * q;
+    for (int i = i0 - 1; i >= 0; i--) {
+      const double hn = i > 0 ? hc[i - 1] * q : 0.0;
+      r = fma(-h, r * r, r);
+      radius[i] = r;
+      h = hn;
+    }
   }
-  r = radius[i0];
-  for (int i = i0 + 1; i < nl; i++) {
-    r = fma(hc[i - 1] * q, r * r, r);
-    radius[i] = r;
+  if ((dirs & 2) && i0 + 1 < nl) {
+    double r = ri0, h = hc[i0] * q;
+    for (int i = i0 + 1; i < nl; i++) {
+      const double hn = i + 1 < nl ? hc[i] * q : 0.0;
+      r = fma(h, r * r, r);
+      radius[i] = r;
+      h = hn;
+    }
   }
 }
 

@@ -180,10 +180,11 @@ atm_prep_kernel(DevConfig c, Knobs knobs, const double *__restrict__ profiles, i
   __syncthreads();
   if (knobs.radius_file) {
     for (int l = threadIdx.x; l < nl; l += blockDim.x) s_rad[l] = knobs.radius_file[l];
-  } else if (threadIdx.x == 0) hydrostatic_radii(c, pp, kv.r0, s_in, s_mu, s_hc, s_rad);
+  } else if (threadIdx.x == 0 || threadIdx.x == 32)          // one direction each, in different warps
+    hydrostatic_radii(c, pp, kv.r0, s_in, s_mu, s_hc, s_rad, threadIdx.x == 0 ? 1 : 2);
   {
-    // warp 0 is busy with the radii unless they come from the file
-    const int first = knobs.radius_file ? 0 : 32;
+    // warps 0 and 1 are busy with the radii unless they come from the file
+    const int first = knobs.radius_file ? 0 : 64;
     const int nthr = (int)blockDim.x - first;
     if ((int)threadIdx.x >= first)
       for (int i = (int)threadIdx.x - first; i < 3 * nl; i += nthr) {
@@ -1075,18 +1076,38 @@ band_integrate_kernel(const double *__restrict__ spectra, const double *__restri
                       const double *__restrict__ star, double rprs2, const int *__restrict__ status,
                       double *__restrict__ bandflux, int nfilters, int nwave, PeerOut po) {
   const int m = blockIdx.x, f = blockIdx.y;
-  const bool rejected = status && status[m] != 0;        // CTA-uniform
+  // (the four scalars are fetched together: at MC3's population sizes this kernel is a chain of
+  // memory round trips, so the loop below also issues the loads of kBandUnroll trapezoids before it
+  // touches the first; a thread's terms are added in the same order as ever)
+  const int stat = status ? status[m] : 0;
+  const int s0 = fstart[f], n = fcount[f], off = foffset[f];
+  const bool rejected = stat != 0;                       // CTA-uniform
   double acc = 0.0;
   if (!rejected) {
-    const int s0 = fstart[f], n = fcount[f], off = foffset[f];
     const double *sp = spectra + (size_t)m * nwave + s0;
     const double *x = wn + s0;
     const double *wt = weight + off;
     const double *st = star ? star + off : nullptr;
-    for (int k = threadIdx.x; k < n - 1; k += blockDim.x) {
-      double y0 = sp[k], y1 = sp[k + 1];
-      if (st) { y0 = y0 / st[k] * rprs2; y1 = y1 / st[k + 1] * rprs2; }
-      acc += (x[k + 1] - x[k]) * (y1 * wt[k + 1] + y0 * wt[k]);
+    constexpr int kBandUnroll = 4;
+    for (int k0 = threadIdx.x; k0 < n - 1; k0 += kBandUnroll * blockDim.x) {
+      double y0[kBandUnroll], y1[kBandUnroll], w0[kBandUnroll], w1[kBandUnroll], x0[kBandUnroll],
+          x1[kBandUnroll], d0[kBandUnroll], d1[kBandUnroll];
+#pragma unroll
+      for (int u = 0; u < kBandUnroll; u++) {
+        const int k = k0 + u * blockDim.x;
+        const int kk = k < n - 1 ? k : 0;                // a slot past the end re-reads sample 0, unused
+        y0[u] = sp[kk]; y1[u] = sp[kk + 1];
+        w0[u] = wt[kk]; w1[u] = wt[kk + 1];
+        x0[u] = x[kk]; x1[u] = x[kk + 1];
+        d0[u] = st ? st[kk] : 1.0; d1[u] = st ? st[kk + 1] : 1.0;
+      }
+#pragma unroll
+      for (int u = 0; u < kBandUnroll; u++) {
+        if (k0 + u * (int)blockDim.x >= n - 1) break;
+        double a = y0[u], b = y1[u];
+        if (st) { a = a / d0[u] * rprs2; b = b / d1[u] * rprs2; }
+        acc += (x1[u] - x0[u]) * (b * w1[u] + a * w0[u]);
+      }
     }
   }
   // fixed-shape reduction: deterministic for a given launch configuration

@@ -10,7 +10,7 @@
 //                          rejection tests, per-model radius / cloud-top / scattering knobs.
 //                          Writes the profiles buffer in run_transit's layout, so atm_prep reads it
 //                          unchanged.
-//   demc_propose_kernel    thread <-> chain: DE-MC jump from two other chains' current states,
+//   demc_propose_kernel    warp <-> chain, lanes over parameters: DE-MC jump from two other chains' current states,
 //                          boundary clamp, shared parameters.  Products and sums are rounded
 //                          separately (no FMA contraction) so chains are bit-identical to numpy.
 //   chisq_accept_kernel    one CTA: per-chain chi-squared with priors, Metropolis rule, state
@@ -317,36 +317,48 @@ void launch_energy_balance(const double *spectra, const double *wn, int nwave, d
 
 // ---------------------------------------------------------------------------------------
 // DE-MC proposal (mcmc.py:524-575): jump = gamma1 (x_r1 - x_r2) + fepsilon * support
-__global__ void demc_propose_kernel(McmcDev mc) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= mc.nchains) return;
+// One warp per chain, lanes over the free parameters: the loads of a jump (two other chains' states,
+// the support draw, the bounds) go out side by side instead of as one dependent round trip per
+// parameter (at MC3's population sizes the kernel's time is its chain of memory latencies).
+__global__ void __launch_bounds__(256) demc_propose_kernel(McmcDev mc) {
+  const int lane = threadIdx.x & 31;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (c >= mc.nchains) return;                  // whole warps
   const int i = *mc.iter;
   const int np = mc.npars;
   const double *cur = mc.params + (size_t)c * np;
   double *nx = mc.nextp + (size_t)c * np;
-  const double *a = mc.params + (size_t)mc.r1[(size_t)c * mc.chainsize + i] * np;
-  const double *b = mc.params + (size_t)mc.r2[(size_t)c * mc.chainsize + i] * np;
-  const double g = mc.ugamma[(size_t)i * mc.nchains + c] < 0.1 ? 0.98 : mc.gamma;
+  const int ra = mc.r1[(size_t)c * mc.chainsize + i], rb = mc.r2[(size_t)c * mc.chainsize + i];
+  const double ug = mc.ugamma[(size_t)i * mc.nchains + c];
+  const double *a = mc.params + (size_t)ra * np;
+  const double *b = mc.params + (size_t)rb * np;
+  const double g = ug < 0.1 ? 0.98 : mc.gamma;
   const double *sup = mc.support + ((size_t)i * mc.nchains + c) * mc.nfree;
   int out = 0;
-  for (int f = 0; f < mc.nfree; f++) {
+  for (int f = lane; f < mc.nfree; f += 32) {
     const int p = mc.ifree[f];
-    const double jump = __dadd_rn(__dmul_rn(g, __dsub_rn(a[p], b[p])), __dmul_rn(mc.fepsilon, sup[f]));
-    double v = __dadd_rn(cur[p], jump);
-    const int o = (v < mc.pmin[p]) || (v > mc.pmax[p]);
+    const double ap = a[p], bp = b[p], cp = cur[p], sf = sup[f], lo = mc.pmin[p], hi = mc.pmax[p];
+    const int ob = mc.outbounds[(size_t)c * mc.nfree + f];
+    const double jump = __dadd_rn(__dmul_rn(g, __dsub_rn(ap, bp)), __dmul_rn(mc.fepsilon, sf));
+    double v = __dadd_rn(cp, jump);
+    const int o = (v < lo) || (v > hi);
     out |= o;
-    mc.outbounds[(size_t)c * mc.nfree + f] += o;
-    if (v < mc.pmin[p]) v = mc.pmin[p];
-    if (v > mc.pmax[p]) v = mc.pmax[p];
+    mc.outbounds[(size_t)c * mc.nfree + f] = ob + o;
+    if (v < lo) v = lo;
+    if (v > hi) v = hi;
     nx[p] = v;
   }
-  for (int s = 0; s < mc.nshare; s++) nx[mc.share_dst[s]] = nx[mc.share_src[s]];
-  mc.outflag[c] = out;
+  out = __any_sync(0xffffffffu, out) ? 1 : 0;
+  __syncwarp();                                 // the lanes' nx[] are visible to lane 0
+  if (lane == 0) {
+    for (int s = 0; s < mc.nshare; s++) nx[mc.share_dst[s]] = nx[mc.share_src[s]];
+    mc.outflag[c] = out;
+  }
 }
 
 void launch_demc_propose(const McmcDev &mc, cudaStream_t s) {
-  const int threads = 128;
-  demc_propose_kernel<<<(mc.nchains + threads - 1) / threads, threads, 0, s>>>(mc);
+  const int threads = 256;                      // 8 chains per CTA
+  demc_propose_kernel<<<(mc.nchains * 32 + threads - 1) / threads, threads, 0, s>>>(mc);
 }
 
 // ---------------------------------------------------------------------------------------
