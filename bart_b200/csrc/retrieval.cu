@@ -493,7 +493,37 @@ __device__ void chain_chisq(const McmcDev &mc, const double *model, const double
   *c2 = c - jc;
 }
 
-__global__ void __launch_bounds__(256)
+// chain_chisq by a whole warp: the residuals of 32 data points at a time side by side, their squares
+// added in index order (every lane carries the same running sum), priors as in chain_chisq
+__device__ void warp_chain_chisq(const McmcDev &mc, const double *model, const double *p, int lane,
+                                 double *chisq, double *c2) {
+  double c = 0.0;
+  for (int base = 0; base < mc.ndata; base += 32) {
+    const int idx = base + lane;
+    double r2 = 0.0;
+    if (idx < mc.ndata) {
+      const double r = (model[idx] - mc.data[idx]) / mc.uncert[idx];
+      r2 = __dmul_rn(r, r);
+    }
+    const int cnt = min(32, mc.ndata - base);
+    for (int k = 0; k < cnt; k++) c = __dadd_rn(c, __shfl_sync(0xffffffffu, r2, k));
+  }
+  double jc = 0.0;
+  for (int k = 0; k < mc.nprior; k++) {
+    const int ip = mc.iprior[k];
+    const double off = p[ip] - mc.prior[ip], lo = mc.priorlow[ip];
+    if (lo == -1) { const double t = 2.0 * log(off); c += t; jc += t; }
+    else { const double r = off / lo; c = __dadd_rn(c, __dmul_rn(r, r)); }
+  }
+  *chisq = c;
+  *c2 = c - jc;
+}
+
+// One CTA; a warp per chain with lanes over the data points / parameters, so that a chain's
+// residuals, state copy and trace stores go out side by side (thread-per-chain was ~20 dependent
+// memory round trips: 11 us at 10 chains).  The snooker norm keeps its 256-slot reduction tree.
+constexpr int kChisqThreads = 512;
+__global__ void __launch_bounds__(kChisqThreads)
 chisq_accept_kernel(McmcDev mc, const double *__restrict__ models, ModelMap mp, int first) {
   const int np = mc.npars;
   const int i = *mc.iter;
@@ -507,20 +537,22 @@ chisq_accept_kernel(McmcDev mc, const double *__restrict__ models, ModelMap mp, 
   __shared__ double s_n1[256], s_n2[256];
   double mrf = 1.0;
   if (snooker) {
-    double a1 = 0.0, a2 = 0.0;
-    for (int c = threadIdx.x; c < mc.nchains; c += blockDim.x) {
-      const bool sj = mc.ugamma[(size_t)i * mc.nchains + c] < 0.1;
-      if (!sj || mc.noproj[c] || mc.outflag[c]) continue;
-      const double *z = mc.Z + ((size_t)mc.iz[(size_t)i * mc.nchains + c] * mc.nchains +
-                                mc.ic[(size_t)i * mc.nchains + c]) * np;
-      const double *cur = mc.params + (size_t)c * np, *nx = mc.nextp + (size_t)c * np;
-      for (int f = 0; f < mc.nfree; f++) {
-        const int p = mc.ifree[f];
-        const double d1 = nx[p] - z[p], d2 = cur[p] - z[p];
-        a1 += d1 * d1; a2 += d2 * d2;
+    if (threadIdx.x < 256) {
+      double a1 = 0.0, a2 = 0.0;
+      for (int c = threadIdx.x; c < mc.nchains; c += 256) {
+        const bool sj = mc.ugamma[(size_t)i * mc.nchains + c] < 0.1;
+        if (!sj || mc.noproj[c] || mc.outflag[c]) continue;
+        const double *z = mc.Z + ((size_t)mc.iz[(size_t)i * mc.nchains + c] * mc.nchains +
+                                  mc.ic[(size_t)i * mc.nchains + c]) * np;
+        const double *cur = mc.params + (size_t)c * np, *nx = mc.nextp + (size_t)c * np;
+        for (int f = 0; f < mc.nfree; f++) {
+          const int p = mc.ifree[f];
+          const double d1 = nx[p] - z[p], d2 = cur[p] - z[p];
+          a1 += d1 * d1; a2 += d2 * d2;
+        }
       }
+      s_n1[threadIdx.x] = a1; s_n2[threadIdx.x] = a2;
     }
-    s_n1[threadIdx.x] = a1; s_n2[threadIdx.x] = a2;
     __syncthreads();
     for (int o = 128; o > 0; o >>= 1) {
       if ((int)threadIdx.x < o) { s_n1[threadIdx.x] += s_n1[threadIdx.x + o]; s_n2[threadIdx.x] += s_n2[threadIdx.x + o]; }
@@ -528,41 +560,52 @@ chisq_accept_kernel(McmcDev mc, const double *__restrict__ models, ModelMap mp, 
     }
     mrf = pow(sqrt(s_n1[0]) / sqrt(s_n2[0]), (double)(mc.nfree - 1));
   }
-  for (int c = threadIdx.x; c < mc.nchains; c += blockDim.x) {
+  const int lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int c = threadIdx.x >> 5; c < mc.nchains; c += nwarps) {
     const double *model = chain_model(models, mp, c, mc.ndata);
     double *cur = mc.params + (size_t)c * np;
     if (first) {
-      chain_chisq(mc, model, cur, &mc.currchisq[c], &mc.c2[c]);
+      double chisq, c2;
+      warp_chain_chisq(mc, model, cur, lane, &chisq, &c2);
+      if (lane == 0) { mc.currchisq[c] = chisq; mc.c2[c] = c2; }
       continue;
     }
     const double *nx = mc.nextp + (size_t)c * np;
-    double next;
-    if (!mc.outflag[c]) {
-      chain_chisq(mc, model, nx, &next, &mc.c2[c]);
-    } else next = INFINITY;                                  // mcmc.py:598
-    mc.nextchisq[c] = next;
-    double accept = exp(0.5 * (mc.currchisq[c] - next));
-    if (snooker && mc.ugamma[(size_t)i * mc.nchains + c] < 0.1 && !mc.noproj[c] && !mc.outflag[c])
-      accept = __dmul_rn(accept, mrf);
-    const bool ok = accept >= mc.unif[(size_t)i * mc.nchains + c];
-    if (ok) {
-      for (int p = 0; p < np; p++) cur[p] = nx[p];
-      mc.currchisq[c] = next;
-      if (mc.nold + i >= mc.burnin) mc.numaccept[c] += 1.0;
+    const int oflag = mc.outflag[c];
+    const double currc = mc.currchisq[c];
+    const double u = mc.unif[(size_t)i * mc.nchains + c];
+    const bool proj = snooker && mc.ugamma[(size_t)i * mc.nchains + c] < 0.1 && !mc.noproj[c] && !oflag;
+    double next = INFINITY, c2 = 0.0;                          // mcmc.py:598
+    if (!oflag) warp_chain_chisq(mc, model, nx, lane, &next, &c2);
+    double accept = exp(0.5 * (currc - next));
+    if (proj) accept = __dmul_rn(accept, mrf);
+    const bool ok = accept >= u;
+    const double *state = ok ? nx : cur;                        // the chain's state after this generation
+    for (int f = lane; f < mc.nfree; f += 32)
+      mc.allparams[((size_t)c * mc.nfree + f) * mc.chainsize + i] = state[mc.ifree[f]];
+    if (snooker && (mc.nold + i) % mc.thinning == 0) {         // mcmc.py:653-660
+      double *zr = mc.Z + ((size_t)zrow * mc.nchains + c) * np;
+      for (int f = lane; f < mc.nfree; f += 32) zr[mc.ifree[f]] = state[mc.ifree[f]];
+      if (lane == 0) mc.Zchisq[(size_t)zrow * mc.nchains + c] = ok ? next : currc;
     }
-    for (int f = 0; f < mc.nfree; f++)
-      mc.allparams[((size_t)c * mc.nfree + f) * mc.chainsize + i] = cur[mc.ifree[f]];
     {                                                          // mcmc.py:636-651
       double *cm = mc.curmodel + (size_t)c * mc.ndata;
-      for (int d = 0; d < mc.ndata; d++) {
-        if (ok) cm[d] = model[d];
-        mc.allmodel[((size_t)c * mc.ndata + d) * mc.chainsize + i] = cm[d];
+      for (int d = lane; d < mc.ndata; d += 32) {
+        const double v = ok ? model[d] : cm[d];
+        if (ok) cm[d] = v;
+        mc.allmodel[((size_t)c * mc.ndata + d) * mc.chainsize + i] = v;
       }
     }
-    if (snooker && (mc.nold + i) % mc.thinning == 0) {                   // mcmc.py:653-660
-      double *zr = mc.Z + ((size_t)zrow * mc.nchains + c) * np;
-      for (int f = 0; f < mc.nfree; f++) zr[mc.ifree[f]] = cur[mc.ifree[f]];
-      mc.Zchisq[(size_t)zrow * mc.nchains + c] = mc.currchisq[c];
+    __syncwarp();                                              // every lane has read `state` = cur when !ok
+    if (ok)
+      for (int p = lane; p < np; p += 32) cur[p] = nx[p];
+    if (lane == 0) {
+      if (!oflag) mc.c2[c] = c2;
+      mc.nextchisq[c] = next;
+      if (ok) {
+        mc.currchisq[c] = next;
+        if (mc.nold + i >= mc.burnin) mc.numaccept[c] += 1.0;
+      }
     }
   }
   __syncthreads();
@@ -648,7 +691,7 @@ void launch_zrow_chisq(const McmcDev &mc, const double *models, ModelMap map, in
 
 void launch_chisq_accept(const McmcDev &mc, const double *models, ModelMap map, int first,
                          cudaStream_t s) {
-  chisq_accept_kernel<<<1, 256, 0, s>>>(mc, models, map, first);
+  chisq_accept_kernel<<<1, kChisqThreads, 0, s>>>(mc, models, map, first);
 }
 
 }  // namespace bart
