@@ -1333,8 +1333,10 @@ int eclipse_small_mode(const DevConfig &c, int nmodels) {
   // kernel needs ~8 CTAs per SM to hide its latencies and the slot kernel's fourfold CTA count
   // bridges the two (measured at the W12 shape: DESIGN.md section 4)
   if ((long long)c.nwave * nmodels <= kScanMaxColumns) return 2;
-  const long long tiles = (c.nwave + kEclThreads * kEclCols - 1) / (kEclThreads * kEclCols);
-  return tiles * nmodels <= 4LL * 148 ? 1 : 0;
+  // the slot kernel (one resident wave of one-warp CTAs, ~8 per SM by shared memory) is what is left
+  // for the configurations the scan kernel is not instantiated for
+  const long long nslots = (c.nwave + 31) / 32;
+  return nslots * nmodels <= 8LL * 148 ? 1 : 0;
 }
 
 void launch_eclipse(const DevConfig &c, const double *tabs, const int *status, double *spectra,

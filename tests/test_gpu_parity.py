@@ -297,7 +297,7 @@ def test_batch_properties_w12_shape(api, workdir):
     perm = np.random.default_rng(3).permutation(models.shape[0])
     sp2, _ = tr.run_batch(models[perm])
     assert np.array_equal(sp2, spectra[perm])
-    sp3, _ = tr.run_batch(models[4:28])           # 24 models: the slot kernel, bit-identical
+    sp3, _ = tr.run_batch(models[4:28])           # 24 models: another batch size, same bits
     assert np.array_equal(sp3, spectra[4:28])
     sp4, _ = tr.run_batch(models[5:6])            # one model: the scan kernel, equal to its approximations
     assert relerr(sp4[0], spectra[5]) < 1e-9

@@ -5,6 +5,7 @@ fill 148 SMs with the throughput mapping.  Reports
   us_per_generation   the device-resident DE-MC loop (propose -> converter -> atm_prep -> eclipse
                       columns -> band integration -> chi^2/accept), CUDA-graph replay, 10 chains
   forward_only        one batched call of 10 proposal models -> band fluxes, device-resident inputs
+  run_transit         the reference's own one-model call (transit_module.run_transit), host arrays
 and the kernel that was picked for the small batch.
 usage: bench_latency.py [--chains 10] [--gens 1200]"""
 import argparse, json, os, sys, tempfile, time
@@ -82,11 +83,23 @@ L.bart_sync()
 us_fwd = 1e6 * (time.perf_counter() - t0) / reps
 L.bart_profile_enable(0)
 ks = {k: 1e3 * v["ms"] / v["launches"] for k, v in api.kernel_stats().items()}
+L.bart_dev_free(d_prof); L.bart_dev_free(d_band)
+
+# the reference's own entry point, one model per call, host arrays in and out: what an unmodified
+# BARTfunc.py worker pays per proposal (H2D profile, atm_prep, eclipse columns, D2H spectrum, sync)
+for _ in range(20):
+    tr.run_transit(prof[0])
+t0 = time.perf_counter()
+for k in range(reps):
+    tr.run_transit(prof[k % nch])
+us_legacy = 1e6 * (time.perf_counter() - t0) / reps
+
 out = {"workload": "WASP-12b eclipse shape, %d chains, 9 free parameters (PT_line + 4 abundances)" % nch,
        "us_per_generation": us_gen, "generations_timed": ngen - 100,
        "accept_rate": float(np.sum(numaccept)) / (nch * ngen),
        "generation_kernels_us": gen_kernels,
        "forward_only_us_per_call": us_fwd, "forward_kernels_us": ks,
+       "run_transit_us_per_call": us_legacy,
        "small_batch_kernel": os.environ.get("BART_ECL_SMALL", "auto"),
        "reference_note": "the reference evaluates a generation as 10 concurrent run_transit calls, one MPI "
                          "process per chain: 1 / cpu_baseline.single_thread_value seconds"}
