@@ -119,6 +119,8 @@ struct State {
   DevBuf<int> d_status, d_status_col, d_last;
   int *h_status = nullptr;                 // pinned staging for per-model status
   size_t h_status_cap = 0;
+  double *h_lean = nullptr;                // pinned staging of the small-call path (bart_run_batch)
+  size_t h_lean_cap = 0;                   // doubles
   DevBuf<double> d_kr0, d_kcloud, d_klogext;
   DevBuf<int> d_kflag;
   int knob_models = 0;
@@ -1141,6 +1143,33 @@ int bart_run_batch(const double *profiles, int nmodels, int n_in, double *spectr
   G.d_prof.ensure((size_t)nmodels * n_in);
   G.d_spec.ensure((size_t)nmodels * nw);
   prepare_batch(nmodels, n_in);
+  // Small calls (run_transit = one model; a worker's handful of proposals): one stream, copies
+  // through one pinned staging buffer (profiles in, spectra and status back), one synchronisation --
+  // the three-stream pipeline below costs more in events and cross-stream hand-offs than such a
+  // call has to overlap, and pageable buffers make every copy a staged, blocking one.
+  const size_t lean_doubles = (size_t)nmodels * ((size_t)n_in + nw + 1);
+  static const bool lean_on = [] { const char *e = getenv("BART_LEAN"); return !e || atoi(e) != 0; }();
+  if (lean_on && lean_doubles * 8 <= (1u << 20)) {
+    if (lean_doubles > G.h_lean_cap) {
+      if (G.h_lean) cudaFreeHost(G.h_lean);
+      G.h_lean = nullptr; G.h_lean_cap = 0;
+      CUDA_OK(cudaMallocHost((void **)&G.h_lean, lean_doubles * 8));
+      G.h_lean_cap = lean_doubles;
+    }
+    double *h_in = G.h_lean, *h_out = h_in + (size_t)nmodels * n_in;
+    int *h_st = reinterpret_cast<int *>(h_out + (size_t)nmodels * nw);
+    memcpy(h_in, profiles, (size_t)nmodels * n_in * 8);
+    CUDA_OK(cudaMemcpyAsync(G.d_prof.p, h_in, (size_t)nmodels * n_in * 8, cudaMemcpyHostToDevice, G.stream));
+    launch_models(G.d_prof.p, 0, nmodels, nmodels, n_in, G.d_spec.p);
+    CUDA_OK(cudaMemcpyAsync(h_out, G.d_spec.p, (size_t)nmodels * nw * 8, cudaMemcpyDeviceToHost, G.stream));
+    if (status)
+      CUDA_OK(cudaMemcpyAsync(h_st, G.d_status.p, nmodels * sizeof(int), cudaMemcpyDeviceToHost, G.stream));
+    G.last_batch = nmodels;
+    finish_stream();
+    for (int m = 0; m < nmodels; m++) memcpy(spectra + (size_t)m * n_out, h_out + (size_t)m * nw, (size_t)nw * 8);
+    if (status) memcpy(status, h_st, nmodels * sizeof(int));
+    return 0;
+  }
   // Software pipeline over chunks of the batch: H2D of chunk k+1 and D2H of chunk k-1 run on
   // their own streams (both copy engines) while chunk k computes.  Buffers are indexed by the
   // global model number, so chunks never alias.
