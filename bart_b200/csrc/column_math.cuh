@@ -1049,15 +1049,19 @@ BART_HD double eclipse_column(const DevConfig &c, const double *tab, const unsig
 // construction, result x2 (both halves of the chord) and x rfct (tau.c:274).
 // `W(i)` returns a reference to where the weight of depth i lives (packed row, or the tiled layout
 // below).
-template <class Acc>
-BART_HD void transit_weight_row_acc(const DevConfig &c, const double *tab, int d, Acc W) {
-  const int nf = c.lay.nf();
-  auto rad = [&](int i) { return tab[(size_t)i * nf + TabLayout::RAD]; };   // depth-indexed radii
-  for (int i = 0; i <= d; i++) W(i) = 0.0;
-  if (d == 0) return;
+// Every element of the row is stored exactly once (an element shared by two Simpson panels is the
+// sum of the lower panel's bottom term, kept in a register, and the upper panel's top term, in
+// that order -- the order the reference's accumulation gives), and a row can be split over
+// `nparts` workers: part k takes a contiguous share of the row's panels, recomputing the one panel
+// below its first for that carried term, and the last part the trailing element(s).  rad(i): radius
+// of depth i.
+template <class Acc, class Rad>
+BART_HD void transit_weight_row_parts(const DevConfig &c, Rad rad, int d, Acc W, int part, int nparts) {
+  if (d == 0) { if (part == 0) W(0) = 0.0; return; }
   const double b = rad(d);
   const double f = 2.0 * c.rfct;
   if (d == 1) {
+    if (part != 0) return;
     const double rm = (rad(1) + rad(0)) / 2.0;
     const double s1 = sqrt(rm * rm - b * b), s2 = sqrt(rad(0) * rad(0) - b * b);
     const double h0 = s1, h1 = s2 - s1;
@@ -1070,19 +1074,45 @@ BART_HD void transit_weight_row_acc(const DevConfig &c, const double *tab, int d
   }
   // s at depth i
   auto sdep = [&](int i) { return i == d ? 0.0 : sqrt(rad(i) * rad(i) - b * b); };
-  for (int p = 0; 2 * p + 2 <= d; p++) {
-    const double sB = sdep(2 * p + 2), sM = sdep(2 * p + 1), sT = sdep(2 * p);
+  // the three terms of the panel spanning depths 2p (top), 2p+1, 2p+2 (bottom)
+  auto panel = [&](double sT, double sM, double sB, double &top, double &mid, double &bot) {
     const double h0 = sM - sB, h1 = sT - sM;
     const double hsum = h0 + h1, hratio = h1 / h0, hfactor = hsum * hsum / (h0 * h1);
-    W(2 * p + 2) += f * (2.0 - hratio) * hsum / 6.0;
-    W(2 * p + 1) += f * hfactor * hsum / 6.0;
-    W(2 * p)     += f * (2.0 - 1.0 / hratio) * hsum / 6.0;
+    bot = f * (2.0 - hratio) * hsum / 6.0;
+    mid = f * hfactor * hsum / 6.0;
+    top = f * (2.0 - 1.0 / hratio) * hsum / 6.0;
+  };
+  const int P = d / 2;                                       // panels p = 0 .. P-1
+  const int p0 = (int)((long long)P * part / nparts), p1 = (int)((long long)P * (part + 1) / nparts);
+  const bool tail = part == nparts - 1;
+  if (p0 == p1 && !tail) return;
+  double sT = sdep(2 * p0), carry = 0.0;                     // carry: the term element 2 p0 has from panel p0 - 1
+  if (p0 > 0) {
+    double t, m, bt;
+    panel(sdep(2 * p0 - 2), sdep(2 * p0 - 1), sT, t, m, bt);
+    carry = 0.0 + bt;
   }
+  for (int p = p0; p < p1; p++) {
+    const double sM = sdep(2 * p + 1), sB = sdep(2 * p + 2);
+    double top, mid, bot;
+    panel(sT, sM, sB, top, mid, bot);
+    W(2 * p) = carry + top;
+    W(2 * p + 1) = 0.0 + mid;
+    carry = 0.0 + bot;
+    sT = sB;
+  }
+  if (!tail) return;
   if (d & 1) {                                               // even count: bottom trapezoid
     const double h = sdep(d - 1);
-    W(d)     += f * h / 2.0;
-    W(d - 1) += f * h / 2.0;
-  }
+    W(d - 1) = carry + f * h / 2.0;
+    W(d) = 0.0 + f * h / 2.0;
+  } else W(d) = carry;
+}
+template <class Acc>
+BART_HD void transit_weight_row_acc(const DevConfig &c, const double *tab, int d, Acc W, int part = 0,
+                                    int nparts = 1) {
+  const int nf = c.lay.nf();
+  transit_weight_row_parts(c, [tab, nf](int i) { return tab[(size_t)i * nf + TabLayout::RAD]; }, d, W, part, nparts);
 }
 
 // packed row: wt[i], i = 0..d
@@ -1105,10 +1135,13 @@ BART_HD size_t tr_chunk_off(int nl, int ch) {
 }
 BART_HD int tr_nchunks(int nl) { return (nl + kTrChunk - 1) / kTrChunk; }
 BART_HD size_t tr_stride(int nl) { return tr_chunk_off(nl, tr_nchunks(nl)); }
-BART_HD void transit_weight_row_tiled(const DevConfig &c, const double *tab, int d, double *wm) {
+// rad: radii by depth (the kernel's shared-memory copy); part / nparts: transit_weight_row_parts
+BART_HD void transit_weight_row_tiled(const DevConfig &c, const double *rad, int d, double *wm,
+                                      int part = 0, int nparts = 1) {
   const int ch = d / kTrChunk, dl = d % kTrChunk;
   double *base = wm + tr_chunk_off(c.nlayer, ch) + (dl / kTrTD) * kTrGroup + dl % kTrTD;
-  transit_weight_row_acc(c, tab, d, [base](int i) -> double & { return base[(size_t)i * kTrRow]; });
+  transit_weight_row_parts(c, [rad](int i) { return rad[i]; }, d,
+                           [base](int i) -> double & { return base[(size_t)i * kTrRow]; }, part, nparts);
 }
 
 // Layout of one model's chord weights for the tensor-core tile kernel (transit_mma_kernel): depth
@@ -1121,10 +1154,12 @@ BART_HD int mm_nchunks(int nl) { return (nl + kMmChunk - 1) / kMmChunk; }
 BART_HD int mm_rs(int ch) { return kMmChunk * (ch + 1) + 4; }
 BART_HD size_t mm_chunk_off(int ch) { return (size_t)128 * ch * (ch + 1) + (size_t)64 * ch; }
 BART_HD size_t mm_stride(int nl) { return mm_chunk_off(mm_nchunks(nl)); }
-BART_HD void transit_weight_row_mm(const DevConfig &c, const double *tab, int d, double *wm) {
+BART_HD void transit_weight_row_mm(const DevConfig &c, const double *rad, int d, double *wm,
+                                   int part = 0, int nparts = 1) {
   const int ch = d / kMmChunk;
   double *base = wm + mm_chunk_off(ch) + (size_t)(d % kMmChunk) * mm_rs(ch);
-  transit_weight_row_acc(c, tab, d, [base](int i) -> double & { return base[i]; });
+  transit_weight_row_parts(c, [rad](int i) { return rad[i]; }, d,
+                           [base](int i) -> double & { return base[i]; }, part, nparts);
 }
 
 // modulationm1 (slantpath.c:446-473), modlevel -1: the planet as an opaque disc whose radius is

@@ -453,22 +453,30 @@ eclipse_scan_kernel(DevConfig c, const double *__restrict__ tabs, const int *__r
 // ---------------------------------------------------------------------------------------
 // transit geometry
 //
-// transit_weights_kernel: one CTA per model, thread <-> depth; writes the chord weights in the
-// tiled layout of column_math.cuh (zero-filled first: weights above the diagonal are zero).
-__global__ void __launch_bounds__(128)
+// transit_weights_kernel: one CTA per model; writes the chord weights in the tiled layout of
+// column_math.cuh (zero-filled first: weights above the diagonal are zero).  kTwParts threads share
+// a depth's row (contiguous shares of its Simpson panels), the radii come from shared memory and
+// every weight is stored once: the first form -- a thread per depth adding each panel's terms into
+// global memory -- was a chain of ~150 dependent read-modify-write round trips, 51 us per launch
+// whatever the batch size.
+constexpr int kTwParts = 4, kTwThreads = 512;
+__global__ void __launch_bounds__(kTwThreads)
 transit_weights_kernel(DevConfig c, const double *__restrict__ tabs, double *__restrict__ wts,
                        int nmodels, int mma_layout) {
+  extern __shared__ double s_radius[];          // [nlayer] radii by depth
   const int m = blockIdx.x;
   if (m >= nmodels) return;
-  const int nl = c.nlayer;
+  const int nl = c.nlayer, nf = c.lay.nf();
   const size_t stride = mma_layout ? mm_stride(nl) : tr_stride(nl);
   const double *tab = tabs + (size_t)m * c.lay.stride();
   double *wm = wts + (size_t)m * stride;
+  for (int i = threadIdx.x; i < nl; i += blockDim.x) s_radius[i] = tab[(size_t)i * nf + TabLayout::RAD];
   for (size_t i = threadIdx.x; i < stride; i += blockDim.x) wm[i] = 0.0;
   __syncthreads();
-  for (int d = threadIdx.x; d < nl; d += blockDim.x) {
-    if (mma_layout) transit_weight_row_mm(c, tab, d, wm);
-    else transit_weight_row_tiled(c, tab, d, wm);
+  for (int item = threadIdx.x; item < nl * kTwParts; item += blockDim.x) {
+    const int d = item / kTwParts, part = item - d * kTwParts;
+    if (mma_layout) transit_weight_row_mm(c, s_radius, d, wm, part, kTwParts);
+    else transit_weight_row_tiled(c, s_radius, d, wm, part, kTwParts);
   }
 }
 
@@ -1436,7 +1444,8 @@ static void launch_transit_ncia(const DevConfig &c, const double *tabs, const do
 
 void launch_transit_weights(const DevConfig &c, const double *tabs, double *wts, int nmodels,
                             bool keep, cudaStream_t s) {
-  transit_weights_kernel<<<nmodels, 128, 0, s>>>(c, tabs, wts, nmodels, transit_uses_mma(c, keep) ? 1 : 0);
+  transit_weights_kernel<<<nmodels, kTwThreads, (size_t)c.nlayer * sizeof(double), s>>>(c, tabs, wts, nmodels,
+                                                                                         transit_uses_mma(c, keep) ? 1 : 0);
 }
 
 void launch_transit(const DevConfig &c, const double *tabs, const double *wts, const int *status,

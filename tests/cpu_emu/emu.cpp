@@ -218,6 +218,28 @@ void emu_chord_tau(int nl, const double *radius_by_depth, const double *ex_by_de
   }
 }
 
+// A chord-weight row assembled from `nparts` shares of its panels (what transit_weights_kernel does
+// with kTwParts threads per depth) against the whole row: number of elements that differ in any bit,
+// over all depths.
+int emu_chord_parts_mismatch(int nl, const double *radius_by_depth, int nparts) {
+  DevConfig c{};
+  c.nlayer = nl; c.rfct = 1e5;
+  int bad = 0;
+  std::vector<double> whole(nl), split(nl);
+  for (int d = 0; d < nl; d++) {
+    auto rad = [radius_by_depth](int i) { return radius_by_depth[i]; };
+    std::fill(whole.begin(), whole.end(), -1.0);
+    std::fill(split.begin(), split.end(), -1.0);
+    double *w = whole.data(), *sp = split.data();
+    transit_weight_row_parts(c, rad, d, [w](int i) -> double & { return w[i]; }, 0, 1);
+    for (int k = 0; k < nparts; k++)
+      transit_weight_row_parts(c, rad, d, [sp](int i) -> double & { return sp[i]; }, k, nparts);
+    for (int i = 0; i < nl; i++) bad += memcmp(&whole[i], &split[i], 8) != 0;
+    for (int i = 0; i <= d; i++) bad += whole[i] == -1.0;       // every element of the row is written
+  }
+  return bad;
+}
+
 double emu_fast_exp(double x) { unsigned long long t[kExpTabSize]; fill_exp_table(t); return fast_exp(x, t); }
 
 }  // extern "C"

@@ -124,3 +124,17 @@ def test_voigt_against_recorded_table_and_faddeeva(built):
         idx = g["rows"] * sub + (first + j) + 8
         worst = max(worst, float(np.max(np.abs(out[idx] / g["table"][:, j] - 1))))
     assert worst < 1.5e-2, worst
+
+
+@pytest.mark.parametrize("nl", [1, 2, 3, 4, 9, 37, 100, 101])
+def test_chord_weight_rows_split_over_workers(nl, built):
+    """transit_weights_kernel deals a depth's row to several threads, each taking a share of the
+    row's Simpson panels (column_math.cuh transit_weight_row_parts): for 1..7 workers the assembled
+    row equals the whole row bit for bit and every element is written, at layer counts with odd and
+    even panel tails and fewer panels than workers."""
+    E = emu()
+    E.emu_chord_parts_mismatch.argtypes = [C.c_int, dp, C.c_int]
+    rng = np.random.default_rng(nl)
+    rad = np.sort(7.0e9 + np.cumsum(rng.uniform(2e6, 9e6, nl)))[::-1].copy()     # by depth: top first
+    for nparts in (1, 2, 3, 4, 7):
+        assert E.emu_chord_parts_mismatch(nl, rad.ctypes.data_as(dp), nparts) == 0

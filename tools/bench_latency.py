@@ -17,19 +17,23 @@ from bart_b200 import api, driver, synth  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--chains", type=int, default=10)
 ap.add_argument("--gens", type=int, default=1200)
+ap.add_argument("--solution", default="eclipse", choices=("eclipse", "transit"))
 a = ap.parse_args()
 
 RSUN, RJUP, MJUP, AU, G = 6.955e10, 7.1492e9, 1.8986e30, 1.4959787e13, 6.67384e-8
 PTARGS = (1.57 * RSUN, 6300.0, 100.0, 0.0229 * AU, 100.0 * G * 1.41 * MJUP / (1.79 * RJUP) ** 2)
 tmp = tempfile.mkdtemp(prefix="bart_lat_")
-case = synth.make_case(tmp, shape="w12", solution="eclipse", seed=2026)
+if a.solution == "eclipse":
+    case = synth.make_case(tmp, shape="w12", solution="eclipse", seed=2026)
+else:
+    case = synth.make_case(tmp, shape="w12", solution="transit", seed=2026, refradius_km=95000.0)
 tr = api.Transit(case["cfg"])
 L = api.lib()
 wn = tr.get_waveno_arr()
 hc_k = 6.6260755e-27 * 2.99792458e10 / 1.380658e-16
 star = 2 * 6.6260755e-27 * 2.99792458e10 ** 2 * wn ** 3 / np.expm1(hc_k * wn / 6300.0) * np.pi
 start, count, weight, st = api.filters_from_files(wn, case["filters"], wn, star)
-tr.set_filters(start, count, weight, st, 0.117)
+tr.set_filters(start, count, weight, st if a.solution == "eclipse" else None, 0.117 if a.solution == "eclipse" else 1.0)
 molfit = ("H2O", "CO2", "CO", "CH4")
 tr.converter_init(case["press_bar"], case["species"], case["abund"], molfit, "line", pt_args=PTARGS)
 # 5 PT_line parameters (kappa, gamma1, gamma2, alpha, beta) + 4 log abundance factors
@@ -37,6 +41,9 @@ params = np.array([-0.5, -0.2, 1.0, 0.0, 1.1, 0.3, -0.2, 0.1, 0.2])
 pmin = np.array([-5.0, -3.0, -2.0, 0.0, 0.55, -9.0, -9.0, -9.0, -9.0])
 pmax = np.array([2.0, 2.0, 3.0, 1.0, 1.4, 3.0, 3.0, 3.0, 3.0])
 stepsize = np.array([0.05, 0.05, 0.0, 0.0, 0.01, 0.3, 0.3, 0.3, 0.3])
+if a.solution == "transit":          # the planet radius at the reference pressure (km) rides along
+    ins = lambda v, x: np.insert(v, 5, x)
+    params, pmin, pmax, stepsize = ins(params, 94500.0), ins(pmin, 90000.0), ins(pmax, 99000.0), ins(stepsize, 20.0)
 nch = a.chains
 truth, status = tr.bandflux_from_params(params[None, :])
 assert status[0] == 0, "the reference point of the latency run is rejected by the converter"
@@ -94,7 +101,7 @@ for k in range(reps):
     tr.run_transit(prof[k % nch])
 us_legacy = 1e6 * (time.perf_counter() - t0) / reps
 
-out = {"workload": "WASP-12b eclipse shape, %d chains, 9 free parameters (PT_line + 4 abundances)" % nch,
+out = {"workload": "WASP-12b %s shape, %d chains, 9 free parameters (PT_line + 4 abundances)" % (a.solution, nch),
        "us_per_generation": us_gen, "generations_timed": ngen - 100,
        "accept_rate": float(np.sum(numaccept)) / (nch * ngen),
        "generation_kernels_us": gen_kernels,
