@@ -459,7 +459,7 @@ eclipse_scan_kernel(DevConfig c, const double *__restrict__ tabs, const int *__r
 // every weight is stored once: the first form -- a thread per depth adding each panel's terms into
 // global memory -- was a chain of ~150 dependent read-modify-write round trips, 51 us per launch
 // whatever the batch size.
-constexpr int kTwParts = 4, kTwThreads = 512;
+constexpr int kTwParts = 4, kTwThreads = 512;   // (8 x 1024: 13.8 vs 15.9 us small, 0.23 vs 0.18 ms per 4096 models)
 __global__ void __launch_bounds__(kTwThreads)
 transit_weights_kernel(DevConfig c, const double *__restrict__ tabs, double *__restrict__ wts,
                        int nmodels, int mma_layout) {
