@@ -462,10 +462,11 @@ eclipse_scan_kernel(DevConfig c, const double *__restrict__ tabs, const int *__r
 constexpr int kTwParts = 4, kTwThreads = 512;   // (8 x 1024: 13.8 vs 15.9 us small, 0.23 vs 0.18 ms per 4096 models)
 __global__ void __launch_bounds__(kTwThreads)
 transit_weights_kernel(DevConfig c, const double *__restrict__ tabs, double *__restrict__ wts,
-                       int nmodels, int mma_layout) {
+                       int nmodels, int mma_layout, int *__restrict__ status_col) {
   extern __shared__ double s_radius[];          // [nlayer] radii by depth
   const int m = blockIdx.x;
   if (m >= nmodels) return;
+  if (status_col && threadIdx.x == 0) status_col[m] = 0;      // (saves the launch a memset node)
   const int nl = c.nlayer, nf = c.lay.nf();
   const size_t stride = mma_layout ? mm_stride(nl) : tr_stride(nl);
   const double *tab = tabs + (size_t)m * c.lay.stride();
@@ -1443,9 +1444,9 @@ static void launch_transit_ncia(const DevConfig &c, const double *tabs, const do
 }
 
 void launch_transit_weights(const DevConfig &c, const double *tabs, double *wts, int nmodels,
-                            bool keep, cudaStream_t s) {
-  transit_weights_kernel<<<nmodels, kTwThreads, (size_t)c.nlayer * sizeof(double), s>>>(c, tabs, wts, nmodels,
-                                                                                         transit_uses_mma(c, keep) ? 1 : 0);
+                            bool keep, int *status_col, cudaStream_t s) {
+  transit_weights_kernel<<<nmodels, kTwThreads, (size_t)c.nlayer * sizeof(double), s>>>(
+      c, tabs, wts, nmodels, transit_uses_mma(c, keep) ? 1 : 0, status_col);
 }
 
 void launch_transit(const DevConfig &c, const double *tabs, const double *wts, const int *status,

@@ -24,8 +24,9 @@ void launch_eclipse(const DevConfig &c, const double *tabs, const int *status, d
 // chord weights of one model in the tiled layout (doubles per model), K2t, and the tile kernel
 size_t transit_weights_stride(int nlayer);
 // keep: the launch that follows is the introspection one (it takes the DFMA kernel's layout)
+// status_col (or nullptr): the per-model column-status words of the launch that follows, cleared here
 void launch_transit_weights(const DevConfig &c, const double *tabs, double *wts, int nmodels,
-                            bool keep, cudaStream_t s);
+                            bool keep, int *status_col, cudaStream_t s);
 void launch_transit(const DevConfig &c, const double *tabs, const double *wts, const int *status,
                     int *status_col, double *spectra, double *tau_keep, int *last_keep,
                     int nmodels, bool keep, bool sc, int use_tma, cudaStream_t s);

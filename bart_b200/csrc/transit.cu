@@ -671,12 +671,11 @@ static void launch_models(const double *d_prof, int off, int count, int total, i
     launch_eclipse(c, tabs, status, d_spec, tau, last, count, G.keep, sc, G.use_tma, G.stream);
     check_launch("eclipse_column");
   } else {
-    int *scol = G.d_status_col.p + off;
-    CUDA_OK(cudaMemsetAsync(scol, 0, count * sizeof(int), G.stream));
+    int *scol = G.d_status_col.p + off;         // cleared by the weights kernel
     double *wts = G.d_wts.p + (size_t)off * transit_weights_stride(c.nlayer);
     {
       KernelScope ks("transit_weights");
-      launch_transit_weights(c, tabs, wts, count, G.keep, G.stream);
+      launch_transit_weights(c, tabs, wts, count, G.keep, scol, G.stream);
       check_launch("transit_weights");
     }
     {
