@@ -34,8 +34,9 @@ namespace bart {
 //            2^k <= x < 2^(k+1), k = 0..9, in u = x / 2^(k-1) - 3 (Chebyshev interpolants in the monomial
 //            basis)
 // with tables computed at 60 digits by tools/gen_expint2_table.py: <= 1e-15 relative against mpmath
-// on both branches (scipy's own expn is not closer), two orders inside what the profiles are held
-// to against PT.py (1e-12, tests/test_gpu_retrieval.py).
+// on both branches (scipy's own expn is up to 3.5e-15 off just below x = 1: tests/test_expint2_table.py
+// evaluates the tables on the CPU the way this function does), three orders inside what the profiles
+// are held to against PT.py (1e-12, tests/test_gpu_retrieval.py).
 #include "expint2_table.inc"
 constexpr int kE2TableN = kE2SeriesN + kE2Intervals * kE2ChebN;
 __device__ double g_e2_table[kE2TableN];        // series coefficients, then the binade polynomials
