@@ -400,6 +400,8 @@ static void reset_state() {
   G.d_snk_usn.release(); G.d_snk_idx.release(); G.d_snk_off.release();
   G.d_Z.release(); G.d_Zchisq.release(); G.mc_zsize = 0; G.mc_zcap = 0; G.mc_ztemplate.clear();
   if (G.mc_graph) { cudaGraphExecDestroy(G.mc_graph); G.mc_graph = nullptr; }
+  if (G.h_lean) { cudaFreeHost(G.h_lean); G.h_lean = nullptr; G.h_lean_cap = 0; }
+  if (G.h_status) { cudaFreeHost(G.h_status); G.h_status = nullptr; G.h_status_cap = 0; }
   G.conv = ConvConfig(); G.mc = McmcDev(); G.mc_ready = false; G.pre_status = nullptr;
   G.nfilters = 0; G.knob_models = 0; G.last_batch = 0; G.eb_on = false;
   G.cia.clear(); G.wn.clear(); G.angles.clear();
