@@ -389,18 +389,26 @@ __device__ double np_pairwise_sum(const double *a, int n) {
 // along x - z (zp = projections of z1, z2), or u (z2 - z1) when z coincides with the chain's
 // state.  The uniform factors u come in the reference from two calls whose sizes depend on the
 // states (unprojected chains first): `slot` reproduces that assignment.
-__global__ void __launch_bounds__(256) snooker_propose_kernel(McmcDev mc) {
+// One CTA (the slot numbering below is one ordered pass over the chains); a warp per chain with
+// lanes over the parameters, like demc_propose_kernel: the loads of a jump go out side by side and the
+// projection's three dot products are numpy's pairwise sums (np_pairwise_sum, every lane the same
+// sequence) over the warp's products in shared memory.
+constexpr int kSnkThreads = 512;
+__global__ void __launch_bounds__(kSnkThreads) snooker_propose_kernel(McmcDev mc) {
+  __shared__ double s_dz[kSnkThreads / 32][kMaxPars], s_t[3][kSnkThreads / 32][kMaxPars];
   const int i = *mc.iter;
   const int np = mc.npars, nc = mc.nchains;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int *gi1 = mc.i1 + (size_t)i * nc, *gi2 = mc.i2 + (size_t)i * nc;
   const int *giz = mc.iz + (size_t)i * nc, *gic = mc.ic + (size_t)i * nc;
   const double *ug = mc.ugamma + (size_t)i * nc;
-  for (int c = threadIdx.x; c < nc; c += blockDim.x) {
+  for (int c = warp; c < nc; c += nwarps) {
     const double *z = mc.Z + ((size_t)giz[c] * nc + gic[c]) * np;
     const double *cur = mc.params + (size_t)c * np;
     int same = 1;
-    for (int p = 0; p < np; p++) same &= (z[p] == cur[p]);   // np.all(z == params, axis=1)
-    mc.noproj[c] = same;
+    for (int p = lane; p < np; p += 32) same &= (z[p] == cur[p]);   // np.all(z == params, axis=1)
+    same = __all_sync(0xffffffffu, same) ? 1 : 0;
+    if (lane == 0) mc.noproj[c] = same;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -409,59 +417,60 @@ __global__ void __launch_bounds__(256) snooker_propose_kernel(McmcDev mc) {
     for (int c = 0; c < nc; c++) if (ug[c] < 0.1 && !mc.noproj[c]) mc.slot[c] = k++;
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < nc; c += blockDim.x) {
+  const int nfree = mc.nfree;
+  for (int c = warp; c < nc; c += nwarps) {
     const double *cur = mc.params + (size_t)c * np;
     double *nx = mc.nextp + (size_t)c * np;
     const double *z1 = mc.Z + (size_t)gi1[c] * np;
     const double *z2 = mc.Z + (size_t)gi2[c] * np;
     const double *z = mc.Z + ((size_t)giz[c] * nc + gic[c]) * np;
     const bool sj = ug[c] < 0.1;
-    const double *sup = mc.support + ((size_t)i * nc + c) * mc.nfree;
-    double jump[kMaxPars];
-    if (!sj) {
-      for (int f = 0; f < mc.nfree; f++) {
+    const bool proj = sj && !mc.noproj[c];
+    const double *sup = mc.support + ((size_t)i * nc + c) * nfree;
+    const double *u = sj ? mc.usn + (size_t)mc.slot[c] * nfree : nullptr;
+    double dzp = 0.0, d2 = 1.0;
+    if (proj) {
+      for (int f = lane; f < nfree; f += 32) {
         const int p = mc.ifree[f];
-        jump[f] = __dadd_rn(__dmul_rn(mc.gamma, __dsub_rn(z1[p], z2[p])), __dmul_rn(mc.fepsilon, sup[f]));
+        const double dz = __dsub_rn(cur[p], z[p]);
+        s_dz[warp][f] = dz;
+        s_t[0][warp][f] = __dmul_rn(z1[p], dz);
+        s_t[1][warp][f] = __dmul_rn(z2[p], dz);
+        s_t[2][warp][f] = __dmul_rn(dz, dz);
       }
-    } else {
-      const double *u = mc.usn + (size_t)mc.slot[c] * mc.nfree;
-      if (mc.noproj[c]) {
-        for (int f = 0; f < mc.nfree; f++) {
-          const int p = mc.ifree[f];
-          jump[f] = __dmul_rn(u[f], __dsub_rn(z2[p], z1[p]));
-        }
-      } else {
-        double dz[kMaxPars], t[kMaxPars];
-        for (int f = 0; f < mc.nfree; f++) dz[f] = __dsub_rn(cur[mc.ifree[f]], z[mc.ifree[f]]);
-        for (int f = 0; f < mc.nfree; f++) t[f] = __dmul_rn(z1[mc.ifree[f]], dz[f]);
-        const double zp1 = np_pairwise_sum(t, mc.nfree);
-        for (int f = 0; f < mc.nfree; f++) t[f] = __dmul_rn(z2[mc.ifree[f]], dz[f]);
-        const double zp2 = np_pairwise_sum(t, mc.nfree);
-        for (int f = 0; f < mc.nfree; f++) t[f] = __dmul_rn(dz[f], dz[f]);
-        const double d2 = np_pairwise_sum(t, mc.nfree);
-        const double dzp = __dsub_rn(zp1, zp2);
-        for (int f = 0; f < mc.nfree; f++)
-          jump[f] = __dmul_rn(__ddiv_rn(__dmul_rn(u[f], dzp), d2), dz[f]);
-      }
+      __syncwarp();
+      const double zp1 = np_pairwise_sum(s_t[0][warp], nfree);
+      const double zp2 = np_pairwise_sum(s_t[1][warp], nfree);
+      d2 = np_pairwise_sum(s_t[2][warp], nfree);
+      dzp = __dsub_rn(zp1, zp2);
     }
     int out = 0;
-    for (int f = 0; f < mc.nfree; f++) {
+    for (int f = lane; f < nfree; f += 32) {
       const int p = mc.ifree[f];
-      double v = __dadd_rn(cur[p], jump[f]);
-      const int o = (v < mc.pmin[p]) || (v > mc.pmax[p]);
+      double jump;
+      if (!sj) jump = __dadd_rn(__dmul_rn(mc.gamma, __dsub_rn(z1[p], z2[p])), __dmul_rn(mc.fepsilon, sup[f]));
+      else if (!proj) jump = __dmul_rn(u[f], __dsub_rn(z2[p], z1[p]));
+      else jump = __dmul_rn(__ddiv_rn(__dmul_rn(u[f], dzp), d2), s_dz[warp][f]);
+      const double lo = mc.pmin[p], hi = mc.pmax[p];
+      double v = __dadd_rn(cur[p], jump);
+      const int o = (v < lo) || (v > hi);
       out |= o;
-      mc.outbounds[(size_t)c * mc.nfree + f] += o;
-      if (v < mc.pmin[p]) v = mc.pmin[p];
-      if (v > mc.pmax[p]) v = mc.pmax[p];
+      mc.outbounds[(size_t)c * nfree + f] += o;
+      if (v < lo) v = lo;
+      if (v > hi) v = hi;
       nx[p] = v;
     }
-    for (int s = 0; s < mc.nshare; s++) nx[mc.share_dst[s]] = nx[mc.share_src[s]];
-    mc.outflag[c] = out;
+    out = __any_sync(0xffffffffu, out) ? 1 : 0;
+    __syncwarp();                               // the lanes' nx[] are visible to lane 0; s_dz / s_t free again
+    if (lane == 0) {
+      for (int s = 0; s < mc.nshare; s++) nx[mc.share_dst[s]] = nx[mc.share_src[s]];
+      mc.outflag[c] = out;
+    }
   }
 }
 
 void launch_snooker_propose(const McmcDev &mc, cudaStream_t s) {
-  snooker_propose_kernel<<<1, 256, 0, s>>>(mc);
+  snooker_propose_kernel<<<1, kSnkThreads, 0, s>>>(mc);
 }
 
 // ---------------------------------------------------------------------------------------

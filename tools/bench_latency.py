@@ -101,12 +101,30 @@ for k in range(reps):
     tr.run_transit(prof[k % nch])
 us_legacy = 1e6 * (time.perf_counter() - t0) / reps
 
+# BART's configured walk, DE-MC with snooker updates (MC3 walk='snooker'): the same measurement through
+# bart_mcmc_run_snooker, random streams drawn up front like driver.run_snooker does
+nfree = int(free.sum())
+hsize = nch + 1
+ds = driver.snooker_draws(np.random.RandomState(11), nch, nfree, ngen, hsize, 1, stepsize[free], pmin[free], pmax[free])
+tr.mcmc_init(p0, pmin, pmax, stepsize, data, uncert)
+tr.mcmc_snooker_init(ds["z0"], 1)
+def run_snk(lo, hi):
+    h = slice(lo, hi)
+    off = np.asarray(ds["usn_offset"])[lo:hi + 1]
+    tr.mcmc_run_snooker(ds["support"][h], ds["i1"][h], ds["i2"][h], ds["iz"][h], ds["ic"][h],
+                        ds["usnooker"][off[0]:off[-1]], off - off[0], ds["unif"][h], ds["ugamma"][h])
+run_snk(0, 100)
+t0 = time.perf_counter()
+run_snk(100, ngen)
+us_snooker = 1e6 * (time.perf_counter() - t0) / (ngen - 100)
+
 out = {"workload": "WASP-12b %s shape, %d chains, 9 free parameters (PT_line + 4 abundances)" % (a.solution, nch),
        "us_per_generation": us_gen, "generations_timed": ngen - 100,
        "accept_rate": float(np.sum(numaccept)) / (nch * ngen),
        "generation_kernels_us": gen_kernels,
        "forward_only_us_per_call": us_fwd, "forward_kernels_us": ks,
        "run_transit_us_per_call": us_legacy,
+       "us_per_generation_snooker": us_snooker,
        "small_batch_kernel": os.environ.get("BART_ECL_SMALL", "auto"),
        "reference_note": "the reference evaluates a generation as 10 concurrent run_transit calls, one MPI "
                          "process per chain: 1 / cpu_baseline.single_thread_value seconds"}
